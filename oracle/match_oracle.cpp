@@ -1,0 +1,290 @@
+/*
+ * oracle/match_oracle.cpp — CPU ORACLE for the Hamming matchers.  TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * Restates /root/reference/src/ORBmatcher.cc, src/LSDmatcher.cpp (knnMatch-based entry points),
+ * src/Frame.cc:190-215 (lineDescriptorMAD) and cv::BFMatcher(NORM_HAMMING).knnMatch(k=2)
+ * (pinned against cv2 in tests/).  KeyFrame/Frame/MapPoint pointers of the reference
+ * are replaced by indices + validity masks; DBoW2::FeatureVector (std::map<node, vector<idx>>) is
+ * passed as CSR with ascending node ids (FeatureVector.cpp:31-45 keeps per-node indices ascending).
+ */
+#include "oracle.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace {
+const int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;   // ORBmatcher.cc:37-39
+
+/* ORBmatcher::ComputeThreeMaxima — ORBmatcher.cc:1604-1645 */
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+inline int rot_bin(float a1, float a2) {                     // ORBmatcher.cc:241-246
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)roundf(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+/* std::map::lower_bound merge-walk over two CSR feature vectors: calls f(i1, i2) for every common node */
+template <class F>
+void walk_common_nodes(const int32_t* nodes1, int nn1, const int32_t* nodes2, int nn2, F f) {
+    int i1 = 0, i2 = 0;
+    while (i1 < nn1 && i2 < nn2) {
+        if (nodes1[i1] == nodes2[i2]) { f(i1, i2); i1++; i2++; }
+        else if (nodes1[i1] < nodes2[i2]) i1 = (int)(std::lower_bound(nodes1 + i1, nodes1 + nn1, nodes2[i2]) - nodes1);
+        else i2 = (int)(std::lower_bound(nodes2 + i2, nodes2 + nn2, nodes1[i1]) - nodes2);
+    }
+}
+}  // namespace
+
+/* ORBmatcher::DescriptorDistance — ORBmatcher.cc:1650-1666 (= LSDmatcher.cpp:364-380) */
+extern "C" int orc_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t pa, pb;
+        memcpy(&pa, a + 4 * i, 4); memcpy(&pb, b + 4 * i, 4);
+        unsigned int v = pa ^ pb;
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+/* cv::BFMatcher(NORM_HAMMING,false).knnMatch(q,t,out,2) — SURVEY.md A.7: ascending distance, ties -> lower trainIdx */
+extern "C" void orc_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out) {
+    for (int i = 0; i < nq; i++) {
+        int d0 = 1 << 30, i0 = -1, d1 = 1 << 30, i1 = -1;
+        for (int j = 0; j < nt; j++) {
+            int d = orc_descriptor_distance(q + 32 * (size_t)i, t + 32 * (size_t)j);
+            if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = j; }
+            else if (d < d1) { d1 = d; i1 = j; }
+        }
+        out[4 * i] = i0; out[4 * i + 1] = i0 < 0 ? -1 : d0; out[4 * i + 2] = i1; out[4 * i + 3] = i1 < 0 ? -1 : d1;
+    }
+}
+
+/* Synthetic stand-in for DBoW2 TemplatedVocabulary::transform (TemplatedVocabulary.h:1218-1259) collapsed
+   to one level: nearest centroid by Hamming distance, strict '<' so the first best centroid wins. */
+extern "C" void orc_bow_assign(const uint8_t* desc, int n, const uint8_t* centroids, int nc, int32_t* node) {
+    for (int i = 0; i < n; i++) {
+        int best = 1 << 30, bi = 0;
+        for (int c = 0; c < nc; c++) {
+            int d = orc_descriptor_distance(desc + 32 * (size_t)i, centroids + 32 * (size_t)c);
+            if (d < best) { best = d; bi = c; }
+        }
+        node[i] = bi;
+    }
+}
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) — ORBmatcher.cc:159-291 */
+extern "C" int orc_search_by_bow(const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                                 const int32_t* nodes1, const int32_t* off1, const int32_t* idx1, int nn1,
+                                 const int32_t* nodes2, const int32_t* off2, const int32_t* idx2, int nn2,
+                                 const uint8_t* valid1, const float* angle1, const float* angle2,
+                                 float nnratio, int checkOri, int32_t* match2) {
+    (void)n1;
+    for (int j = 0; j < n2; j++) match2[j] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    walk_common_nodes(nodes1, nn1, nodes2, nn2, [&](int a, int b) {
+        for (int iKF = off1[a]; iKF < off1[a + 1]; iKF++) {
+            const int realIdxKF = idx1[iKF];
+            if (!valid1[realIdxKF]) continue;                                         // :196-200
+            int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+            for (int iF = off2[b]; iF < off2[b + 1]; iF++) {
+                const int realIdxF = idx2[iF];
+                if (match2[realIdxF] >= 0) continue;                                  // :212
+                const int dist = orc_descriptor_distance(d1 + 32 * (size_t)realIdxKF, d2 + 32 * (size_t)realIdxF);
+                if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                else if (dist < bestDist2) bestDist2 = dist;
+            }
+            if (bestDist1 <= TH_LOW) {                                                // :231
+                if ((float)bestDist1 < nnratio * (float)bestDist2) {                  // :233
+                    match2[bestIdxF] = realIdxKF;
+                    if (checkOri) rotHist[rot_bin(angle1[realIdxKF], angle2[bestIdxF])].push_back(bestIdxF);
+                    nmatches++;
+                }
+            }
+        }
+    });
+    if (checkOri) {                                                                   // :270-288
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { match2[j] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) — ORBmatcher.cc:525-658 */
+extern "C" int orc_search_by_bow_kf(const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                                    const int32_t* nodes1, const int32_t* off1, const int32_t* idx1, int nn1,
+                                    const int32_t* nodes2, const int32_t* off2, const int32_t* idx2, int nn2,
+                                    const uint8_t* valid1, const uint8_t* valid2, const float* angle1, const float* angle2,
+                                    float nnratio, int checkOri, int32_t* match12) {
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    std::vector<char> matched2(n2, 0);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    walk_common_nodes(nodes1, nn1, nodes2, nn2, [&](int a, int b) {
+        for (int i1 = off1[a]; i1 < off1[a + 1]; i1++) {
+            const int id1 = idx1[i1];
+            if (!valid1[id1]) continue;
+            int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+            for (int i2 = off2[b]; i2 < off2[b + 1]; i2++) {
+                const int id2 = idx2[i2];
+                if (matched2[id2] || !valid2[id2]) continue;                          // :579-583
+                int dist = orc_descriptor_distance(d1 + 32 * (size_t)id1, d2 + 32 * (size_t)id2);
+                if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = id2; }
+                else if (dist < bestDist2) bestDist2 = dist;
+            }
+            if (bestDist1 < TH_LOW) {                                                 // :601 (strict)
+                if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                    match12[id1] = bestIdx2;
+                    matched2[bestIdx2] = 1;
+                    if (checkOri) rotHist[rot_bin(angle1[id1], angle2[bestIdx2])].push_back(id1);
+                    nmatches++;
+                }
+            }
+        }
+    });
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { match12[j] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+/* ORBmatcher::SearchForTriangulation — ORBmatcher.cc:660-826 with CheckDistEpipolarLine :140-157.
+   Monocular restatement: mvuRight < 0 everywhere (bStereo1 = bStereo2 = false), bOnlyStereo = false. */
+extern "C" int orc_search_for_triangulation(const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                        const int32_t* nodes1, const int32_t* off1, const int32_t* idx1, int nn1,
+                        const int32_t* nodes2, const int32_t* off2, const int32_t* idx2, int nn2,
+                        const uint8_t* has_mp1, const uint8_t* has_mp2,
+                        const float* x1, const float* y1, const float* a1,
+                        const float* x2, const float* y2, const float* a2, const int32_t* oct2,
+                        const float* F12, float ex, float ey, const float* scale, const float* sigma2,
+                        int checkOri, int32_t* pairs) {
+    (void)n2;
+    std::vector<int> m12(n1, -1);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    walk_common_nodes(nodes1, nn1, nodes2, nn2, [&](int a, int b) {
+        for (int i1 = off1[a]; i1 < off1[a + 1]; i1++) {
+            const int id1 = idx1[i1];
+            if (has_mp1[id1]) continue;                                               // :702-706
+            int bestDist = TH_LOW, bestIdx2 = -1;
+            for (int i2 = off2[b]; i2 < off2[b + 1]; i2++) {
+                const int id2 = idx2[i2];
+                if (has_mp2[id2]) continue;                                           // :725-729 (vbMatched2 never set)
+                const int dist = orc_descriptor_distance(d1 + 32 * (size_t)id1, d2 + 32 * (size_t)id2);
+                if (dist > TH_LOW || dist > bestDist) continue;                       // :741
+                {                                                                     // :746-752
+                    const float distex = ex - x2[id2], distey = ey - y2[id2];
+                    if (distex * distex + distey * distey < 100 * scale[oct2[id2]]) continue;
+                }
+                // CheckDistEpipolarLine :140-157
+                const float la = x1[id1] * F12[0] + y1[id1] * F12[3] + F12[6];
+                const float lb = x1[id1] * F12[1] + y1[id1] * F12[4] + F12[7];
+                const float lc = x1[id1] * F12[2] + y1[id1] * F12[5] + F12[8];
+                const float num = la * x2[id2] + lb * y2[id2] + lc;
+                const float den = la * la + lb * lb;
+                if (den == 0) continue;
+                const float dsqr = num * num / den;
+                if (dsqr < 3.84 * sigma2[oct2[id2]]) { bestIdx2 = id2; bestDist = dist; }   // double compare (:156)
+            }
+            if (bestIdx2 >= 0) {
+                m12[id1] = bestIdx2;
+                nmatches++;
+                if (checkOri) rotHist[rot_bin(a1[id1], a2[bestIdx2])].push_back(id1);
+            }
+        }
+    });
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { m12[j] = -1; nmatches--; }
+        }
+    }
+    int k = 0;
+    for (int i = 0; i < n1; i++) if (m12[i] >= 0) { pairs[2 * k] = i; pairs[2 * k + 1] = m12[i]; k++; }   // :818-823
+    return nmatches;
+}
+
+/* Frame::lineDescriptorMAD — Frame.cc:190-215.  std::sort there is unstable but only the median VALUE
+   is read, which does not depend on the order of equal elements. */
+extern "C" void orc_line_mad(const int32_t* knn, int nq, double* nn_mad, double* nn12_mad) {
+    if (nq <= 0) { *nn_mad = 0; *nn12_mad = 0; return; }
+    std::vector<float> a(nq);
+    for (int i = 0; i < nq; i++) a[i] = (float)knn[4 * i + 1];
+    std::sort(a.begin(), a.end());
+    double med = a[nq / 2];
+    for (int i = 0; i < nq; i++) a[i] = fabsf((float)((float)knn[4 * i + 1] - med));
+    std::sort(a.begin(), a.end());
+    *nn_mad = 1.4826 * a[nq / 2];
+    std::vector<float> g(nq);
+    for (int i = 0; i < nq; i++) g[i] = (float)knn[4 * i + 3] - (float)knn[4 * i + 1];
+    std::sort(g.begin(), g.end(), [](float x, float y) { return x > y; });      // descending (:206)
+    double med12 = g[nq / 2];
+    for (int i = 0; i < nq; i++) a[i] = fabsf((float)((float)knn[4 * i + 3] - (float)knn[4 * i + 1] - med12));
+    std::sort(a.begin(), a.end());
+    *nn12_mad = 1.4826 * a[nq / 2];
+}
+
+/* LSDmatcher knn-based entry points — LSDmatcher.cpp:143-183 / 286-327 (mode 0), 257-284 (mode 1),
+   329-362 (mode 2), 382-415 (mode 3).  q = d1, train = d2 in all of them.
+   mode 0: out[tdx] = qdx (table of size n2, -1 = none), later queries overwrite; returns nmatches (counts overwrites, as the reference does)
+   mode 1: out = pairs (qdx,tdx);   mode 2: out[qdx] = tdx (table of size n1);   mode 3: out = pairs */
+extern "C" int orc_line_match(int mode, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                              const uint8_t* has_ml1, const uint8_t* has_ml2, int32_t* out, int* nout) {
+    std::vector<int32_t> knn(4 * (size_t)std::max(n1, 1));
+    orc_knn2(d1, n1, d2, n2, knn.data());
+    double nn_mad, nn12_mad;
+    orc_line_mad(knn.data(), n1, &nn_mad, &nn12_mad);
+    int nmatches = 0, k = 0;
+    if (mode == 0) for (int j = 0; j < n2; j++) out[j] = -1;
+    if (mode == 2) for (int i = 0; i < n1; i++) out[i] = -1;
+    const float minRatio = 1.0f / 1.5f;
+    for (int i = 0; i < n1; i++) {                  // already in queryIdx order
+        const int tdx = knn[4 * i];
+        const float dist0 = (float)knn[4 * i + 1], dist1 = (float)knn[4 * i + 3];
+        if (mode == 0) {
+            double dist_12 = dist0 / dist1;                                     // float division, widened (:167)
+            if (dist_12 < minRatio && has_ml1[i]) { out[tdx] = i; nmatches++; }
+        } else if (mode == 1) {
+            double dist_12 = dist1 - dist0;
+            if (dist_12 > nn12_mad * 0.5) { out[2 * k] = i; out[2 * k + 1] = tdx; k++; nmatches++; }
+        } else if (mode == 2) {
+            double dist_12 = dist1 - dist0;
+            if (dist_12 > nn12_mad * 0.5 && has_ml2[tdx]) { out[i] = tdx; nmatches++; }
+        } else {
+            if (has_ml1[i] || has_ml2[tdx]) continue;                           // :403
+            double dist_12 = dist1 - dist0;
+            if (dist_12 > nn12_mad * 0.1) { out[2 * k] = i; out[2 * k + 1] = tdx; k++; nmatches++; }
+        }
+    }
+    if (nout) *nout = k;
+    return nmatches;
+}

@@ -1,0 +1,263 @@
+"""ctypes bindings of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: import from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                           ("octave", "<i4"), ("class_id", "<i4")])
+KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
+                          ("response", "<f4"), ("size", "<f4"),
+                          ("startPointX", "<f4"), ("startPointY", "<f4"), ("endPointX", "<f4"), ("endPointY", "<f4"),
+                          ("sPointInOctaveX", "<f4"), ("sPointInOctaveY", "<f4"),
+                          ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"),
+                          ("lineLength", "<f4"), ("numOfPixels", "<i4")])
+assert KEYPOINT_DTYPE.itemsize == 28 and KEYLINE_DTYPE.itemsize == 68
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h", ".inc")) or f == "Makefile"]
+    stale = (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_fast_atan2.restype = C.c_float
+        _lib.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        _lib.orc_orb_create.restype = C.c_void_p
+        _lib.orc_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        if hasattr(_lib, "orc_line_create"):
+            _lib.orc_line_create.restype = C.c_void_p
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    assert img.ndim == 2
+    return img
+
+
+def resize_linear(img, dw, dh):
+    img = _u8(img)
+    out = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), dw, dh, dw)
+    return out
+
+
+def border_reflect101(img, b):
+    img = _u8(img)
+    out = np.empty((img.shape[0] + 2 * b, img.shape[1] + 2 * b), np.uint8)
+    lib().orc_border_reflect101_u8(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), out.strides[0], b)
+    return out
+
+
+def sepfilter_fixed(img, taps):
+    img = _u8(img)
+    taps = np.ascontiguousarray(taps, np.int32)
+    out = np.empty_like(img)
+    lib().orc_sepfilter_fixed_u8(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), out.strides[0],
+                                 _p(taps), len(taps))
+    return out
+
+
+def gauss7_sigma2(img):
+    return sepfilter_fixed(img, [18, 34, 48, 56, 48, 34, 18])
+
+
+def fast9_16(img, threshold, cap=1 << 16):
+    img = _u8(img)
+    xs = np.empty(cap, np.int32); ys = np.empty(cap, np.int32); ss = np.empty(cap, np.int32)
+    n = lib().orc_fast9_16(_p(img), img.shape[1], img.shape[0], img.strides[0], int(threshold), _p(xs), _p(ys), _p(ss), cap)
+    assert n <= cap
+    return xs[:n].copy(), ys[:n].copy(), ss[:n].copy()
+
+
+def fast_atan2(y, x):
+    return float(lib().orc_fast_atan2(float(y), float(x)))
+
+
+def octree(xs, ys, resp, minX, maxX, minY, maxY, N):
+    xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32); resp = np.ascontiguousarray(resp, np.int32)
+    out = np.empty(len(xs) + 8, np.int32)
+    n = lib().orc_octree(_p(xs), _p(ys), _p(resp), len(xs), minX, maxX, minY, maxY, N, _p(out), len(out))
+    return out[:n].copy()
+
+
+class OrbOracle:
+    """ORBextractor restatement (ORBextractor.cc:410-470 ctor, :1043 operator())."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self.h = C.c_void_p(lib().orc_orb_create(nfeatures, scale_factor, nlevels, ini_th, min_th))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_orb_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        L = self.nlevels
+        sc, isc, s2, is2 = (np.empty(L, np.float32) for _ in range(4))
+        nf = np.empty(L, np.int32); um = np.empty(16, np.int32)
+        lib().orc_orb_tables(self.h, _p(sc), _p(isc), _p(s2), _p(is2), _p(nf), _p(um))
+        return dict(scale=sc, invscale=isc, sigma2=s2, invsigma2=is2, nfeat=nf, umax=um)
+
+    def extract(self, img):
+        img = _u8(img)
+        cap = self.nfeatures + 4 * self.nlevels + 64
+        kps = np.zeros(cap, KEYPOINT_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+        n = lib().orc_orb_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap)
+        assert n <= cap
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level_size(self, l):
+        w = C.c_int(); h = C.c_int()
+        lib().orc_orb_level_size(self.h, l, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level(self, l, bordered=False):
+        w, h = self.level_size(l)
+        b = 19 if bordered else 0
+        out = np.empty((h + 2 * b, w + 2 * b), np.uint8)
+        lib().orc_orb_level_copy(self.h, l, int(bordered), _p(out), out.strides[0])
+        return out
+
+    def blurred(self, l):
+        w, h = self.level_size(l)
+        out = np.zeros((h, w), np.uint8)
+        lib().orc_orb_blur_copy(self.h, l, _p(out), out.strides[0])
+        return out
+
+    def candidates(self, l, cap=1 << 16):
+        xs = np.empty(cap, np.int32); ys = np.empty(cap, np.int32); rs = np.empty(cap, np.int32)
+        n = lib().orc_orb_candidates(self.h, l, _p(xs), _p(ys), _p(rs), cap)
+        return xs[:n].copy(), ys[:n].copy(), rs[:n].copy()
+
+    def level_keypoints(self, l, cap=1 << 14):
+        xs = np.empty(cap, np.int32); ys = np.empty(cap, np.int32); rs = np.empty(cap, np.int32); an = np.empty(cap, np.float32)
+        n = lib().orc_orb_level_keypoints(self.h, l, _p(xs), _p(ys), _p(rs), _p(an), cap)
+        return xs[:n].copy(), ys[:n].copy(), rs[:n].copy(), an[:n].copy()
+
+    def stage_ms(self):
+        ms = np.empty(6, np.float64)
+        lib().orc_orb_stage_ms(self.h, _p(ms))
+        return dict(zip(["pyramid", "fast", "octree", "orient", "blur", "brief"], ms.tolist()))
+
+
+# ---------------- matching ----------------
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return int(lib().orc_descriptor_distance(_p(a), _p(b)))
+
+
+def knn2(q, t):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    out = np.empty((max(len(q), 1), 4), np.int32)
+    lib().orc_knn2(_p(q), len(q), _p(t), len(t), _p(out))
+    return out[:len(q)]
+
+
+def bow_assign(desc, centroids):
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); centroids = np.ascontiguousarray(centroids, np.uint8).reshape(-1, 32)
+    node = np.empty(max(len(desc), 1), np.int32)
+    lib().orc_bow_assign(_p(desc), len(desc), _p(centroids), len(centroids), _p(node))
+    return node[:len(desc)]
+
+
+def feature_vector_csr(node):
+    """DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>, FeatureVector.cpp:31-45) flattened to CSR:
+    node ids ascending, feature indices ascending inside a node."""
+    node = np.asarray(node, np.int32)
+    order = np.argsort(node, kind="stable").astype(np.int32)
+    ids, counts = np.unique(node, return_counts=True)
+    off = np.zeros(len(ids) + 1, np.int32)
+    off[1:] = np.cumsum(counts)
+    return ids.astype(np.int32), off, order
+
+
+def _csr(args):
+    return [np.ascontiguousarray(a, np.int32) for a in args]
+
+
+def search_by_bow(d1, d2, fv1, fv2, valid1, angle1, angle2, nnratio=0.7, check_ori=True):
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    n1s, o1, i1 = _csr(fv1); n2s, o2, i2 = _csr(fv2)
+    valid1 = np.ascontiguousarray(valid1, np.uint8)
+    angle1 = np.ascontiguousarray(angle1, np.float32); angle2 = np.ascontiguousarray(angle2, np.float32)
+    m = np.empty(max(len(d2), 1), np.int32)
+    n = lib().orc_search_by_bow(_p(d1), len(d1), _p(d2), len(d2), _p(n1s), _p(o1), _p(i1), len(n1s),
+                                _p(n2s), _p(o2), _p(i2), len(n2s), _p(valid1), _p(angle1), _p(angle2),
+                                C.c_float(nnratio), int(check_ori), _p(m))
+    return n, m[:len(d2)]
+
+
+def search_by_bow_kf(d1, d2, fv1, fv2, valid1, valid2, angle1, angle2, nnratio=0.7, check_ori=True):
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    n1s, o1, i1 = _csr(fv1); n2s, o2, i2 = _csr(fv2)
+    valid1 = np.ascontiguousarray(valid1, np.uint8); valid2 = np.ascontiguousarray(valid2, np.uint8)
+    angle1 = np.ascontiguousarray(angle1, np.float32); angle2 = np.ascontiguousarray(angle2, np.float32)
+    m = np.empty(max(len(d1), 1), np.int32)
+    n = lib().orc_search_by_bow_kf(_p(d1), len(d1), _p(d2), len(d2), _p(n1s), _p(o1), _p(i1), len(n1s),
+                                   _p(n2s), _p(o2), _p(i2), len(n2s), _p(valid1), _p(valid2), _p(angle1), _p(angle2),
+                                   C.c_float(nnratio), int(check_ori), _p(m))
+    return n, m[:len(d1)]
+
+
+def search_for_triangulation(d1, d2, fv1, fv2, has_mp1, has_mp2, kp1, kp2, F12, ex, ey, scale, sigma2, check_ori=True):
+    """kp1/kp2: structured KEYPOINT arrays (x, y, angle, octave used)."""
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    n1s, o1, i1 = _csr(fv1); n2s, o2, i2 = _csr(fv2)
+    has_mp1 = np.ascontiguousarray(has_mp1, np.uint8); has_mp2 = np.ascontiguousarray(has_mp2, np.uint8)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    x1, y1, a1 = f(kp1["x"]), f(kp1["y"]), f(kp1["angle"])
+    x2, y2, a2 = f(kp2["x"]), f(kp2["y"]), f(kp2["angle"])
+    oc2 = np.ascontiguousarray(kp2["octave"], np.int32)
+    F12 = f(F12).reshape(9); scale = f(scale); sigma2 = f(sigma2)
+    pairs = np.empty((max(len(d1), 1), 2), np.int32)
+    n = lib().orc_search_for_triangulation(_p(d1), len(d1), _p(d2), len(d2), _p(n1s), _p(o1), _p(i1), len(n1s),
+                                           _p(n2s), _p(o2), _p(i2), len(n2s), _p(has_mp1), _p(has_mp2),
+                                           _p(x1), _p(y1), _p(a1), _p(x2), _p(y2), _p(a2), _p(oc2),
+                                           _p(F12), C.c_float(ex), C.c_float(ey), _p(scale), _p(sigma2),
+                                           int(check_ori), _p(pairs))
+    return n, pairs[:n].copy()
+
+
+def line_mad(knn):
+    knn = np.ascontiguousarray(knn, np.int32)
+    a = C.c_double(); b = C.c_double()
+    lib().orc_line_mad(_p(knn), len(knn), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def line_match(mode, d1, d2, has_ml1=None, has_ml2=None):
+    d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+    has_ml1 = np.ascontiguousarray(has_ml1 if has_ml1 is not None else np.zeros(len(d1)), np.uint8)
+    has_ml2 = np.ascontiguousarray(has_ml2 if has_ml2 is not None else np.zeros(len(d2)), np.uint8)
+    out = np.full(2 * max(len(d1), len(d2), 1), -1, np.int32)
+    k = C.c_int()
+    n = lib().orc_line_match(mode, _p(d1), len(d1), _p(d2), len(d2), _p(has_ml1), _p(has_ml2), _p(out), C.byref(k))
+    if mode == 0:
+        return n, out[:len(d2)].copy()
+    if mode == 2:
+        return n, out[:len(d1)].copy()
+    return n, out[:2 * k.value].reshape(-1, 2).copy()
