@@ -1,0 +1,207 @@
+/*
+ * include/sslpl.h — C ABI of the B200-native point/line front-end (libsslpl_b200.so).
+ *
+ * This is the drop-in boundary for the three data-parallel hot paths of
+ * yanyan-li/Structure-SLAM-PointLine's Tracking::TrackWithPL():
+ *   (1) ORBextractor::operator()            reference: include/ORBextractor.h:45-111, src/ORBextractor.cc:1043
+ *   (2) LineSegment::ExtractLineSegment     reference: include/ExtractLineSegment.h:53-76, src/ExtractLineSegment.cpp:18
+ *   (3) ORBmatcher / LSDmatcher Hamming     reference: include/ORBmatcher.h:36-101, include/LSDmatcher.h:36-64
+ * The reference has no FFI; its boundary is the C++ class surface.  The adapters in
+ * structure-slam-pointline_b200/host/ re-expose those class signatures on top of this ABI
+ * (see INTEGRATION.md).  Plain pointers and sizes only; no torch / OpenCV types.
+ *
+ * Conventions: every entry point returns 0 on success or a negative sslpl_status; nothing throws;
+ * the callee never allocates caller-visible memory; `*_device` variants take device pointers and
+ * enqueue on the handle's stream without synchronising (call sslpl_*_sync).  Handles are not
+ * thread-safe individually, but any number of handles may be used concurrently from different
+ * threads (the reference calls the matchers from Tracking and LocalMapping threads at once).
+ * There is NO CPU fallback: without a CUDA device every create call fails with SSLPL_ERR_CUDA.
+ */
+#ifndef SSLPL_H
+#define SSLPL_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSLPL_VERSION 1
+#define SSLPL_MAX_LEVELS 16
+
+typedef enum {
+    SSLPL_OK = 0,
+    SSLPL_ERR_ARG = -1,        /* bad argument (null pointer, size out of the handle's capacity, ...) */
+    SSLPL_ERR_CUDA = -2,       /* CUDA runtime error; see sslpl_last_error() */
+    SSLPL_ERR_CAPACITY = -3,   /* an internal or caller-provided buffer was too small (no partial result) */
+    SSLPL_ERR_UNSUPPORTED = -4
+} sslpl_status;
+
+const char* sslpl_last_error(void);          /* thread-local message of the last failing call */
+int  sslpl_version(void);
+int  sslpl_device_count(void);               /* 0 when no CUDA device / driver */
+
+/* pinned host memory for frames / results (so H2D/D2H run at link speed) */
+int  sslpl_host_alloc(void** p, size_t bytes);
+int  sslpl_host_free(void* p);
+
+/* ---- POD mirrors of the OpenCV types that cross the reference boundary ---- */
+typedef struct { float x, y, size, angle, response; int32_t octave, class_id; } sslpl_keypoint;   /* cv::KeyPoint, 28 B */
+typedef struct {                                                                                  /* cv::line_descriptor::KeyLine, 68 B */
+    float angle; int32_t class_id; int32_t octave; float pt_x, pt_y; float response; float size;
+    float startPointX, startPointY, endPointX, endPointY;
+    float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+    float lineLength; int32_t numOfPixels;
+} sslpl_keyline;
+
+/* =====================================================================================
+ * (1) ORB extractor — replaces ORBextractor (src/ORBextractor.cc)
+ * ===================================================================================== */
+typedef struct {
+    int   nfeatures;      /* ORBextractor.nFeatures   (Examples/ICL.yaml:41)  */
+    float scaleFactor;    /* ORBextractor.scaleFactor (ICL.yaml:44)           */
+    int   nlevels;        /* ORBextractor.nLevels     (ICL.yaml:47), <= SSLPL_MAX_LEVELS */
+    int   iniThFAST;      /* ICL.yaml:53 */
+    int   minThFAST;      /* ICL.yaml:54 */
+    int   max_width, max_height;   /* largest frame this handle will see (device workspace is sized once) */
+    int   max_batch;      /* frames per call for the batched entry points (>=1) */
+    int   device;         /* CUDA device ordinal */
+} sslpl_orb_params;
+
+typedef struct sslpl_orb sslpl_orb;
+
+int  sslpl_orb_create(const sslpl_orb_params* p, sslpl_orb** out);            /* ORBextractor::ORBextractor, ORBextractor.cc:410 */
+void sslpl_orb_destroy(sslpl_orb* h);
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+   (ORBextractor.h:63-77) + mnFeaturesPerLevel + umax; each array has nlevels (umax: 16) entries; NULL = skip */
+int  sslpl_orb_tables(const sslpl_orb* h, float* scale, float* invscale, float* sigma2, float* invsigma2,
+                      int* nfeat_per_level, int* umax16);
+int  sslpl_orb_max_keypoints(const sslpl_orb* h);  /* capacity per frame: sum_l (mnFeaturesPerLevel[l] + 3) */
+
+/* ORBextractor::operator() (ORBextractor.cc:1043) on one HOST frame (CV_8UC1, `pitch` bytes per row).
+   kps[cap], desc[cap*32]; *n = number of keypoints (0 for an empty image, as the reference's silent return). */
+int  sslpl_orb_extract(sslpl_orb* h, const uint8_t* img, int width, int height, int pitch,
+                       sslpl_keypoint* kps, uint8_t* desc, int cap, int* n);
+/* Batched frames, HOST buffers: frame f at imgs + f*frame_stride; outputs kps[f*cap + i], desc[(f*cap+i)*32], n[f]. */
+int  sslpl_orb_extract_batch(sslpl_orb* h, const uint8_t* imgs, int nframes, int width, int height, int pitch,
+                             size_t frame_stride, sslpl_keypoint* kps, uint8_t* desc, int cap, int* n);
+/* Batched frames already resident in HBM; results stay in HBM (see sslpl_orb_device_results). Asynchronous. */
+int  sslpl_orb_extract_batch_device(sslpl_orb* h, const uint8_t* d_imgs, int nframes, int width, int height, int pitch,
+                                    size_t frame_stride);
+/* Device result buffers of the last *_device call: d_kps[f*cap+i], d_desc[(f*cap+i)*32], d_n[f]. */
+int  sslpl_orb_device_results(sslpl_orb* h, const sslpl_keypoint** d_kps, const uint8_t** d_desc, const int** d_n, int* cap);
+int  sslpl_orb_sync(sslpl_orb* h);           /* wait for the handle's stream; reports deferred device-side errors */
+void* sslpl_orb_stream(sslpl_orb* h);        /* cudaStream_t of the handle */
+/* mvImagePyramid[level] (ORBextractor.h:79) of frame f of the last call; bordered=1 adds the 19-px
+   BORDER_REFLECT_101 frame of ComputePyramid (ORBextractor.cc:1107-1132). dst is a HOST buffer. */
+int  sslpl_orb_level_size(const sslpl_orb* h, int level, int* w, int* hgt);
+int  sslpl_orb_download_level(sslpl_orb* h, int frame, int level, int bordered, uint8_t* dst, int dpitch);
+/* stage intermediates of the last call, for parity tests: FAST candidates (vToDistributeKeys order),
+   per-level keypoints after DistributeOctTree, blurred level */
+int  sslpl_orb_download_candidates(sslpl_orb* h, int frame, int level, int* xs, int* ys, int* resp, int cap, int* n);
+int  sslpl_orb_download_level_keypoints(sslpl_orb* h, int frame, int level, int* xs, int* ys, int* resp, int cap, int* n);
+int  sslpl_orb_download_blurred(sslpl_orb* h, int frame, int level, uint8_t* dst, int dpitch);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches claim) */
+long long sslpl_orb_launch_count(const sslpl_orb* h);
+/* names + CUDA-event milliseconds of the kernels of the last profiled call (enable with sslpl_orb_set_profiling) */
+int  sslpl_orb_set_profiling(sslpl_orb* h, int on);
+int  sslpl_orb_stage_ms(sslpl_orb* h, float* ms, int cap, const char** names, int* nstages);
+
+/* =====================================================================================
+ * (3) Hamming matching — replaces ORBmatcher / LSDmatcher kernels of work
+ * ===================================================================================== */
+typedef struct sslpl_matcher sslpl_matcher;
+typedef struct {
+    int max_features;     /* largest N (points) per frame */
+    int max_lines;        /* largest NL per frame */
+    int max_nodes;        /* largest number of vocabulary nodes in a FeatureVector */
+    int max_batch;        /* frame pairs per batched call */
+    int device;
+} sslpl_matcher_params;
+int  sslpl_matcher_create(const sslpl_matcher_params* p, sslpl_matcher** out);
+void sslpl_matcher_destroy(sslpl_matcher* m);
+int  sslpl_matcher_sync(sslpl_matcher* m);
+void* sslpl_matcher_stream(sslpl_matcher* m);
+long long sslpl_matcher_launch_count(const sslpl_matcher* m);
+
+/* ORBmatcher::DescriptorDistance (ORBmatcher.cc:1650) for nq pairs a[i] vs b[i] (HOST buffers) */
+int  sslpl_descriptor_distance(sslpl_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist);
+/* cv::BFMatcher(NORM_HAMMING,false).knnMatch(q,t,.,2) as used by LSDmatcher.cpp:155,266,298,341,392:
+   out[4*i+0..3] = trainIdx0, dist0, trainIdx1, dist1 (ties -> lower trainIdx; -1,-1 when nt < 2) */
+int  sslpl_hamming_knn2(sslpl_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out);
+/* Vocabulary-node assignment (synthetic one-level stand-in for DBoW2 transform, TemplatedVocabulary.h:1218-1259) */
+int  sslpl_bow_assign(sslpl_matcher* m, const uint8_t* desc, int n, const uint8_t* centroids, int nc, int32_t* node);
+
+/* DBoW2::FeatureVector flattened to CSR: nodes[nn] ascending, off[nn+1], idx[off[nn]] */
+typedef struct { const int32_t* nodes; const int32_t* off; const int32_t* idx; int nn; } sslpl_featvec;
+
+/* ORBmatcher::SearchByBoW(KeyFrame*,Frame&,vector<MapPoint*>&) (ORBmatcher.cc:159-291).
+   valid1[i] != 0 <=> KF feature i has a non-bad MapPoint.  match2[j] = KF feature index matched to frame
+   feature j, or -1 (the adapter maps indices back to MapPoint*).  *nmatches = return value of the reference. */
+int  sslpl_search_by_bow(sslpl_matcher* m, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                         const sslpl_featvec* fv1, const sslpl_featvec* fv2,
+                         const uint8_t* valid1, const float* angle1, const float* angle2,
+                         float nnratio, int checkOrientation, int32_t* match2, int* nmatches);
+/* ORBmatcher::SearchByBoW(KeyFrame*,KeyFrame*,vector<MapPoint*>&) (ORBmatcher.cc:525-658): match12[i] = KF2 index or -1 */
+int  sslpl_search_by_bow_kf(sslpl_matcher* m, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                            const sslpl_featvec* fv1, const sslpl_featvec* fv2,
+                            const uint8_t* valid1, const uint8_t* valid2, const float* angle1, const float* angle2,
+                            float nnratio, int checkOrientation, int32_t* match12, int* nmatches);
+/* ORBmatcher::SearchForTriangulation (ORBmatcher.cc:660-826), monocular (bOnlyStereo=false, mvuRight<0).
+   kp1/kp2 = mvKeysUn; has_mp = "feature already has a MapPoint"; F12 row-major 3x3 f32; (ex,ey) epipole;
+   scale = mvScaleFactors, sigma2 = mvLevelSigma2 of KF2.  pairs[2*k] = (idx1, idx2) sorted by idx1. */
+int  sslpl_search_for_triangulation(sslpl_matcher* m, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                                    const sslpl_featvec* fv1, const sslpl_featvec* fv2,
+                                    const uint8_t* has_mp1, const uint8_t* has_mp2,
+                                    const sslpl_keypoint* kp1, const sslpl_keypoint* kp2,
+                                    const float* F12, float ex, float ey, const float* scale, const float* sigma2, int nlevels,
+                                    int checkOrientation, int32_t* pairs, int* nmatches);
+/* LSDmatcher knnMatch-based entry points (LSDmatcher.cpp). mode 0: SearchByProjection(KF,F) :143 /
+   SearchByDescriptor(KF,F) :286 -> out[tdx] = qdx table (n2 entries);  mode 1: SerachForInitialize :257 -> pairs;
+   mode 2: SearchByDescriptor(KF,KF2) :329 -> out[qdx] = tdx table (n1 entries); mode 3: SearchForTriangulation :382 -> pairs.
+   *nout = number of pairs written (modes 1,3); *nmatches = the reference's return value.
+   Also returns Frame::lineDescriptorMAD (Frame.cc:190) in mad[0..1] when mad != NULL. */
+int  sslpl_line_match(sslpl_matcher* m, int mode, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                      const uint8_t* has_ml1, const uint8_t* has_ml2, int32_t* out, int* nout, int* nmatches, double* mad);
+
+/* Batched consecutive-frame matching, everything resident in HBM (config 5 of BASELINE.json):
+   for pair p (frame p = "KeyFrame", frame p+1 = "Frame"): node assignment of both frames against the
+   vocabulary, FeatureVector build, SearchByBoW (all KF features valid), rotation filter.
+   d_desc/d_kps/d_n as produced by sslpl_orb_extract_batch_device (cap entries per frame, nframes frames);
+   d_match[(p*cap)+j] = KF index or -1 for frame p+1's feature j; d_nmatch[p]. npairs = nframes-1. */
+int  sslpl_match_bow_batch_device(sslpl_matcher* m, const uint8_t* d_desc, const sslpl_keypoint* d_kps, const int* d_n,
+                                  int nframes, int cap, const uint8_t* d_centroids, int nc,
+                                  float nnratio, int checkOrientation, int32_t* d_match, int32_t* d_nmatch);
+/* Batched line matching in HBM: knn2 + ratio rule of LSDmatcher::SearchByProjection(KF,F) (:143-183) with all
+   KF lines valid: d_lmatch[p*capl + tdx] = qdx or -1; d_nlmatch[p]. */
+int  sslpl_match_lines_batch_device(sslpl_matcher* m, const uint8_t* d_ldesc, const int* d_nl, int nframes, int capl,
+                                    int32_t* d_lmatch, int32_t* d_nlmatch);
+
+/* =====================================================================================
+ * (2) Line segments — replaces LineSegment::ExtractLineSegment (src/ExtractLineSegment.cpp:18-69)
+ * ===================================================================================== */
+typedef struct sslpl_line sslpl_line;
+typedef struct {
+    int lsdNFeatures;     /* hard-coded 40 in the reference (ExtractLineSegment.cpp:42) */
+    int max_width, max_height, max_batch, device;
+} sslpl_line_params;
+int  sslpl_line_create(const sslpl_line_params* p, sslpl_line** out);
+void sslpl_line_destroy(sslpl_line* h);
+/* ExtractLineSegment(img, keylines, ldesc, keylineFunctions, scale=1, numOctaves=1): kl[cap], ldesc[cap*32], lineeq[cap*3] */
+int  sslpl_line_extract(sslpl_line* h, const uint8_t* img, int width, int height, int pitch,
+                        sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int cap, int* n);
+int  sslpl_line_extract_batch(sslpl_line* h, const uint8_t* imgs, int nframes, int width, int height, int pitch,
+                              size_t frame_stride, sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int cap, int* n);
+int  sslpl_line_extract_batch_device(sslpl_line* h, const uint8_t* d_imgs, int nframes, int width, int height, int pitch,
+                                     size_t frame_stride);
+int  sslpl_line_device_results(sslpl_line* h, const sslpl_keyline** d_kl, const uint8_t** d_ldesc, const double** d_lineeq,
+                               const int** d_n, int* cap);
+int  sslpl_line_sync(sslpl_line* h);
+void* sslpl_line_stream(sslpl_line* h);
+long long sslpl_line_launch_count(const sslpl_line* h);
+/* raw LSD segments (before the top-N cut) of frame f of the last call: seg[4*i] = x1,y1,x2,y2 */
+int  sslpl_line_download_segments(sslpl_line* h, int frame, float* seg4, int cap, int* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSLPL_H */

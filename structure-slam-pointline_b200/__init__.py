@@ -1,0 +1,238 @@
+"""structure-slam-pointline_b200 — host-side Python mirror of the reference interface over libsslpl_b200.so.
+
+The product is the C-ABI shared library (include/sslpl.h) built from csrc/*.cu for sm_100a; the C++
+adapters with the reference's own class signatures live in host/.  This module is the thin ctypes layer
+the tests and bench.py use; its classes carry the reference's names and argument meaning:
+
+    ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)   include/ORBextractor.h:45-111
+        __call__(image) -> (keypoints, descriptors)                       src/ORBextractor.cc:1043
+    LineSegment().ExtractLineSegment(img) -> (keylines, ldesc, keylineFunctions)   src/ExtractLineSegment.cpp:18
+    ORBmatcher(nnratio, checkOri).SearchByBoW / SearchForTriangulation    src/ORBmatcher.cc:159,525,660
+    LSDmatcher().SearchByProjection / SerachForInitialize / ...           src/LSDmatcher.cpp:143,257,286,329,382
+
+There is no CPU fallback and nothing here imports oracle/: if the CUDA library is missing or no GPU is
+present, construction raises.  (The package directory name contains '-', so import it through
+`__graft_entry__.load_package()`, which registers it as module `sslpl_b200`.)
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsslpl_b200.so")
+
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                           ("octave", "<i4"), ("class_id", "<i4")])
+KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
+                          ("response", "<f4"), ("size", "<f4"),
+                          ("startPointX", "<f4"), ("startPointY", "<f4"), ("endPointX", "<f4"), ("endPointY", "<f4"),
+                          ("sPointInOctaveX", "<f4"), ("sPointInOctaveY", "<f4"),
+                          ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"),
+                          ("lineLength", "<f4"), ("numOfPixels", "<i4")])
+assert KEYPOINT_DTYPE.itemsize == 28 and KEYLINE_DTYPE.itemsize == 68
+
+
+class SslplError(RuntimeError):
+    pass
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scaleFactor", C.c_float), ("nlevels", C.c_int), ("iniThFAST", C.c_int),
+                ("minThFAST", C.c_int), ("max_width", C.c_int), ("max_height", C.c_int), ("max_batch", C.c_int),
+                ("device", C.c_int)]
+
+
+class MatcherParams(C.Structure):
+    _fields_ = [("max_features", C.c_int), ("max_lines", C.c_int), ("max_nodes", C.c_int), ("max_batch", C.c_int),
+                ("device", C.c_int)]
+
+
+class LineParams(C.Structure):
+    _fields_ = [("lsdNFeatures", C.c_int), ("max_width", C.c_int), ("max_height", C.c_int), ("max_batch", C.c_int),
+                ("device", C.c_int)]
+
+
+class FeatVec(C.Structure):
+    _fields_ = [("nodes", C.c_void_p), ("off", C.c_void_p), ("idx", C.c_void_p), ("nn", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libsslpl_b200.so (fails loudly when it has not been built: run __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SslplError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                             " (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.sslpl_last_error.restype = C.c_char_p
+        L.sslpl_orb_stream.restype = C.c_void_p
+        L.sslpl_orb_launch_count.restype = C.c_longlong
+        for name in ("sslpl_matcher_stream", "sslpl_line_stream"):
+            if hasattr(L, name):
+                getattr(L, name).restype = C.c_void_p
+        for name in ("sslpl_matcher_launch_count", "sslpl_line_launch_count"):
+            if hasattr(L, name):
+                getattr(L, name).restype = C.c_longlong
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise SslplError(f"sslpl error {rc}: {lib().sslpl_last_error().decode(errors='replace')}")
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    return int(lib().sslpl_device_count())
+
+
+def host_alloc(shape, dtype=np.uint8):
+    """Pinned host ndarray (sslpl_host_alloc); keeps the allocation alive through .base."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    ptr = C.c_void_p()
+    _check(lib().sslpl_host_alloc(C.byref(ptr), C.c_size_t(max(nbytes, 1))))
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr
+
+
+class ORBextractor:
+    """Mirror of StructureSLAM::ORBextractor (include/ORBextractor.h:45-111)."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7,
+                 max_width=1280, max_height=960, max_batch=1, device=0):
+        self.nfeatures, self.scaleFactor, self.nlevels = nfeatures, scaleFactor, nlevels
+        p = OrbParams(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_width, max_height, max_batch, device)
+        self._h = C.c_void_p()
+        _check(lib().sslpl_orb_create(C.byref(p), C.byref(self._h)))
+        self.max_batch = max_batch
+        self.cap = int(lib().sslpl_orb_max_keypoints(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().sslpl_orb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # ORBextractor.h:60-77
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return self.scaleFactor
+
+    def _tables(self):
+        L = self.nlevels
+        sc, isc, s2, is2 = (np.empty(L, np.float32) for _ in range(4))
+        nf = np.empty(L, np.int32); um = np.empty(16, np.int32)
+        _check(lib().sslpl_orb_tables(self._h, _p(sc), _p(isc), _p(s2), _p(is2), _p(nf), _p(um)))
+        return dict(scale=sc, invscale=isc, sigma2=s2, invsigma2=is2, nfeat=nf, umax=um)
+
+    def GetScaleFactors(self):
+        return self._tables()["scale"]
+
+    def GetInverseScaleFactors(self):
+        return self._tables()["invscale"]
+
+    def GetScaleSigmaSquares(self):
+        return self._tables()["sigma2"]
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._tables()["invsigma2"]
+
+    def __call__(self, image, mask=None):
+        """operator()(image, mask /*ignored*/, keypoints, descriptors) — ORBextractor.cc:1043."""
+        if image is None or image.size == 0:
+            return np.zeros(0, KEYPOINT_DTYPE), np.zeros((0, 32), np.uint8)      # silent return, ORBextractor.cc:1046
+        assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 expected (ORBextractor.cc:1050)"
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        kps = np.zeros(self.cap, KEYPOINT_DTYPE); desc = np.zeros((self.cap, 32), np.uint8)
+        n = C.c_int()
+        _check(lib().sslpl_orb_extract(self._h, _p(image), image.shape[1], image.shape[0], image.strides[0],
+                                       _p(kps), _p(desc), self.cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, frames, out=None):
+        """frames: (B,H,W) uint8 host array (pinned for full H2D speed). Returns (kps[B,cap], desc[B,cap,32], n[B])."""
+        assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.strides[2] == 1
+        B, H, W = frames.shape
+        if out is None:
+            out = (np.zeros((B, self.cap), KEYPOINT_DTYPE), np.zeros((B, self.cap, 32), np.uint8), np.zeros(B, np.int32))
+        kps, desc, n = out
+        _check(lib().sslpl_orb_extract_batch(self._h, _p(frames), B, W, H, frames.strides[1], C.c_size_t(frames.strides[0]),
+                                             _p(kps), _p(desc), self.cap, _p(n)))
+        return kps, desc, n
+
+    def extract_batch_device(self, d_ptr, nframes, width, height, pitch, frame_stride):
+        """Frames already in HBM (raw device pointer, e.g. torch_tensor.data_ptr()); asynchronous."""
+        _check(lib().sslpl_orb_extract_batch_device(self._h, C.c_void_p(d_ptr), nframes, width, height, pitch,
+                                                    C.c_size_t(frame_stride)))
+
+    def device_results(self):
+        kps = C.c_void_p(); desc = C.c_void_p(); n = C.c_void_p(); cap = C.c_int()
+        _check(lib().sslpl_orb_device_results(self._h, C.byref(kps), C.byref(desc), C.byref(n), C.byref(cap)))
+        return kps.value, desc.value, n.value, cap.value
+
+    def sync(self):
+        _check(lib().sslpl_orb_sync(self._h))
+
+    @property
+    def stream(self):
+        return lib().sslpl_orb_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(lib().sslpl_orb_launch_count(self._h))
+
+    # ---- stage intermediates (parity tests) ----
+    def level_size(self, l):
+        w = C.c_int(); h = C.c_int()
+        _check(lib().sslpl_orb_level_size(self._h, l, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def level(self, l, frame=0, bordered=False):
+        """mvImagePyramid[l] (ORBextractor.h:79)."""
+        w, h = self.level_size(l)
+        b = 19 if bordered else 0
+        out = np.empty((h + 2 * b, w + 2 * b), np.uint8)
+        _check(lib().sslpl_orb_download_level(self._h, frame, l, int(bordered), _p(out), out.strides[0]))
+        return out
+
+    def blurred(self, l, frame=0):
+        w, h = self.level_size(l)
+        out = np.empty((h, w), np.uint8)
+        _check(lib().sslpl_orb_download_blurred(self._h, frame, l, _p(out), out.strides[0]))
+        return out
+
+    def candidates(self, l, frame=0, cap=1 << 17):
+        xs = np.empty(cap, np.int32); ys = np.empty(cap, np.int32); rs = np.empty(cap, np.int32); n = C.c_int()
+        _check(lib().sslpl_orb_download_candidates(self._h, frame, l, _p(xs), _p(ys), _p(rs), cap, C.byref(n)))
+        assert n.value <= cap
+        return xs[:n.value].copy(), ys[:n.value].copy(), rs[:n.value].copy()
+
+    def level_keypoints(self, l, frame=0, cap=1 << 15):
+        xs = np.empty(cap, np.int32); ys = np.empty(cap, np.int32); rs = np.empty(cap, np.int32); n = C.c_int()
+        _check(lib().sslpl_orb_download_level_keypoints(self._h, frame, l, _p(xs), _p(ys), _p(rs), cap, C.byref(n)))
+        return xs[:n.value].copy(), ys[:n.value].copy(), rs[:n.value].copy()
+
+    def set_profiling(self, on=True):
+        _check(lib().sslpl_orb_set_profiling(self._h, int(on)))
+
+    def stage_ms(self):
+        ms = (C.c_float * 16)(); names = (C.c_char_p * 16)(); n = C.c_int()
+        _check(lib().sslpl_orb_stage_ms(self._h, ms, 16, names, C.byref(n)))
+        return {names[i].decode(): float(ms[i]) for i in range(n.value)}

@@ -1,0 +1,712 @@
+// match.cu — B200 (sm_100a) Hamming matchers: brute-force 2-NN (cv::BFMatcher knnMatch k=2), vocabulary-node
+// assignment, SearchByBoW (KF-Frame and KF-KF), SearchForTriangulation, rotation-histogram filter, and the
+// knn-based LSDmatcher entry points.  Replaces the distance work of src/ORBmatcher.cc and src/LSDmatcher.cpp.
+//
+// No tensor cores: 256-bit XOR + popcount per pair, reduced with warp shuffles.  Descriptors are read as
+// 2 x uint4 per row.  The batched layout is "a set of frames": frame f owns desc[f*cap..], a CSR feature
+// vector and optional masks; pair p matches frame p (KeyFrame role) against frame p+1 (Frame role).
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace sslpl {
+
+constexpr int TH_LOW = 50;          // ORBmatcher.cc:38
+constexpr int HISTO_LENGTH = 30;    // ORBmatcher.cc:39
+
+// A set of frames in HBM (strides in elements of the respective type)
+struct FrameSet {
+    const uint8_t* desc; long long desc_fs;                  // 32 B per row; frame stride in bytes
+    const int* n; int n_const;                               // per-frame feature count (device array) or constant
+    const int* nodes; const int* off; const int* idx; const int* nn; int nn_const;
+    long long nodes_fs, off_fs, idx_fs;                      // CSR frame strides (ints)
+    const uint8_t* flag; long long flag_fs;                  // valid / has-MapPoint mask (may be null)
+    const float* angle; int angle_es; long long angle_fs;    // keypoint angle: element stride / frame stride in floats
+    const float* x; const float* y; const int* oct;          // same strides as angle (fields of sslpl_keypoint)
+};
+
+__device__ __forceinline__ void load_desc(const uint8_t* p, uint4& a, uint4& b) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    a = __ldg(q); b = __ldg(q + 1);
+}
+
+// -------------------------------------------------------------------------------------------------
+// knnMatch(k=2): one warp per query.  key = dist << 20 | trainIdx  => ascending distance, ties -> lower index
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void top2_insert(unsigned& k0, unsigned& k1, unsigned k) {
+    if (k < k0) { k1 = k0; k0 = k; } else if (k < k1) k1 = k;
+}
+
+__global__ void __launch_bounds__(256) k_knn2(const uint8_t* q, long long q_fs, const int* nq_arr, int nq_const,
+                                               const uint8_t* t, long long t_fs, const int* nt_arr, int nt_const,
+                                               int32_t* out, long long out_fs, int qcap) {
+    const int pair = blockIdx.y, lane = threadIdx.x & 31, qi = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int nq = nq_arr ? min(nq_arr[pair], qcap) : nq_const, nt = nt_arr ? min(nt_arr[pair + 1], qcap) : nt_const;
+    if (qi >= nq) return;
+    uint4 a0, a1;
+    load_desc(q + pair * q_fs + (long long)qi * 32, a0, a1);
+    const uint8_t* T = t + pair * t_fs;
+    unsigned k0 = 0xffffffffu, k1 = 0xffffffffu;
+    for (int j = lane; j < nt; j += 32) {
+        uint4 b0, b1;
+        load_desc(T + (long long)j * 32, b0, b1);
+        top2_insert(k0, k1, ((unsigned)popc256(a0, a1, b0, b1) << 20) | (unsigned)j);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        top2_insert(k0, k1, o0);
+        top2_insert(k0, k1, o1);
+    }
+    if (lane == 0) {
+        int4 r;
+        r.x = k0 == 0xffffffffu ? -1 : (int)(k0 & 0xfffff); r.y = k0 == 0xffffffffu ? -1 : (int)(k0 >> 20);
+        r.z = k1 == 0xffffffffu ? -1 : (int)(k1 & 0xfffff); r.w = k1 == 0xffffffffu ? -1 : (int)(k1 >> 20);
+        reinterpret_cast<int4*>(out + pair * out_fs)[qi] = r;
+    }
+}
+
+// DescriptorDistance for n pairs (ORBmatcher.cc:1650): thread per pair
+__global__ void k_pair_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 a0, a1, b0, b1;
+    load_desc(a + (long long)i * 32, a0, a1); load_desc(b + (long long)i * 32, b0, b1);
+    dist[i] = popc256(a0, a1, b0, b1);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Vocabulary node assignment: nearest centroid, strict '<' (first wins).  Thread per descriptor,
+// centroids staged in shared memory.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_bow_assign(const uint8_t* desc, long long desc_fs, const int* n_arr, int n_const, int cap,
+                                                     const uint8_t* centroids, int nc, int32_t* node, long long node_fs) {
+    extern __shared__ uint4 s_cent[];
+    const int f = blockIdx.y;
+    for (int i = threadIdx.x; i < nc * 2; i += blockDim.x) s_cent[i] = __ldg(reinterpret_cast<const uint4*>(centroids) + i);
+    __syncthreads();
+    const int n = n_arr ? min(n_arr[f], cap) : n_const;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 a0, a1;
+    load_desc(desc + f * desc_fs + (long long)i * 32, a0, a1);
+    int best = 1 << 30, bi = 0;
+    for (int c = 0; c < nc; c++) {
+        const int d = popc256(a0, a1, s_cent[2 * c], s_cent[2 * c + 1]);
+        if (d < best) { best = d; bi = c; }
+    }
+    node[f * node_fs + i] = bi;
+}
+
+// FeatureVector build for a dense vocabulary (every node 0..nc-1 listed, possibly empty): CSR with
+// ascending feature indices per node (FeatureVector.cpp:31-45).  One CTA per frame, thread per node.
+__global__ void __launch_bounds__(128) k_build_csr(const int32_t* node, long long node_fs, const int* n_arr, int cap, int nc,
+                                                    int* off, long long off_fs, int* idx, long long idx_fs) {
+    __shared__ int s_warp[33];
+    extern __shared__ int s_cnt[];        // nc + 1 ints
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n = min(n_arr[f], cap);
+    const int32_t* nd = node + f * node_fs;
+    for (int c = tid; c <= nc; c += blockDim.x) s_cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) atomicAdd(&s_cnt[nd[i]], 1);
+    __syncthreads();
+    block_scan_array(s_cnt, nc + 1, s_warp);                  // exclusive offsets, s_cnt[nc] = n
+    for (int c = tid; c <= nc; c += blockDim.x) off[f * off_fs + c] = s_cnt[c];
+    __syncthreads();
+    // stable fill: thread c walks all features in index order (n * nc / T steps; n ~ 1e3, nc ~ 1e2)
+    for (int c = tid; c < nc; c += blockDim.x) {
+        int o = s_cnt[c];
+        const int e = s_cnt[c + 1];
+        for (int i = 0; i < n && o < e; i++) if (nd[i] == c) idx[f * idx_fs + o++] = i;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// SearchByBoW — one warp per (pair, node of set 1).  Nodes are independent (a feature belongs to exactly
+// one node), the greedy exclusion inside a node is sequential over the KF features in list order.
+//   mode 0: KF vs Frame  (ORBmatcher.cc:159-291): out = match2[F idx] = KF idx, accept best <= TH_LOW
+//   mode 1: KF vs KF     (ORBmatcher.cc:525-658): out = match12[idx1] = idx2, accept best <  TH_LOW, both need MapPoints
+// rot[i] holds the rotation-histogram bin of the match written at out[i] (or 255).
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int rot_bin(float a1, float a2) {                 // ORBmatcher.cc:241-246
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+__device__ __forceinline__ int find_node(const int* nodes, int nn, int id) {   // map::find on the ascending CSR node list
+    int lo = 0, hi = nn;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (nodes[mid] < id) lo = mid + 1; else hi = mid; }
+    return (lo < nn && nodes[lo] == id) ? lo : -1;
+}
+
+__global__ void __launch_bounds__(128) k_bow_match(FrameSet S, int mode, float nnratio, int cap,
+                                                    int32_t* out, long long out_fs, uint8_t* rot, long long rot_fs,
+                                                    uint8_t* taken, long long taken_fs) {
+    const int pair = blockIdx.y, lane = threadIdx.x & 31, a = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int f1 = pair, f2 = pair + 1;
+    const int nn1 = S.nn ? S.nn[f1] : S.nn_const, nn2 = S.nn ? S.nn[f2] : S.nn_const;
+    if (a >= nn1) return;
+    const int* nodes1 = S.nodes + f1 * S.nodes_fs; const int* nodes2 = S.nodes + f2 * S.nodes_fs;
+    const int b = find_node(nodes2, nn2, nodes1[a]);
+    if (b < 0) return;
+    const int* off1 = S.off + f1 * S.off_fs; const int* off2 = S.off + f2 * S.off_fs;
+    const int* idx1 = S.idx + f1 * S.idx_fs; const int* idx2 = S.idx + f2 * S.idx_fs;
+    const uint8_t* D1 = S.desc + f1 * S.desc_fs; const uint8_t* D2 = S.desc + f2 * S.desc_fs;
+    const uint8_t* v1 = S.flag ? S.flag + f1 * S.flag_fs : nullptr;
+    const uint8_t* v2 = S.flag ? S.flag + f2 * S.flag_fs : nullptr;
+    const float* A1 = S.angle + f1 * S.angle_fs; const float* A2 = S.angle + f2 * S.angle_fs;
+    int32_t* O = out + pair * out_fs; uint8_t* R = rot + pair * rot_fs; uint8_t* TK = taken + pair * taken_fs;
+    const int b1 = off1[a], e1 = off1[a + 1], b2 = off2[b], e2 = off2[b + 1];
+    for (int i1 = b1; i1 < e1; i1++) {
+        const int id1 = idx1[i1];
+        if (v1 && !v1[id1]) continue;                                            // :196-200 / :563-567
+        uint4 a0, a1;
+        load_desc(D1 + (long long)id1 * 32, a0, a1);
+        // per-lane best / second best over this lane's candidates, in list order: key = dist << 20 | position
+        unsigned k0 = 0xffffffffu, k1 = 0xffffffffu;
+        for (int i2 = b2 + lane; i2 < e2; i2 += 32) {
+            const int id2 = idx2[i2];
+            if (TK[id2]) continue;                                               // :212 / :579 (already matched)
+            if (mode == 1 && v2 && !v2[id2]) continue;                           // :579-583
+            uint4 c0, c1;
+            load_desc(D2 + (long long)id2 * 32, c0, c1);
+            top2_insert(k0, k1, ((unsigned)popc256(a0, a1, c0, c1) << 20) | (unsigned)(i2 - b2));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+            top2_insert(k0, k1, o0);
+            top2_insert(k0, k1, o1);
+        }
+        // bestDist1 = smallest distance (first position wins), bestDist2 = second order statistic; both start at 256
+        const int best1 = k0 == 0xffffffffu ? 256 : (int)(k0 >> 20);
+        const int best2 = k1 == 0xffffffffu ? 256 : (int)(k1 >> 20);
+        const bool th = mode == 0 ? best1 <= TH_LOW : best1 < TH_LOW;             // :231 / :601
+        if (k0 != 0xffffffffu && th && (float)best1 < __fmul_rn(nnratio, (float)best2)) {      // :233
+            const int id2 = idx2[b2 + (int)(k0 & 0xfffff)];
+            if (lane == 0) {
+                TK[id2] = 1;
+                const int bin = rot_bin(A1[(long long)id1 * S.angle_es], A2[(long long)id2 * S.angle_es]);
+                if (mode == 0) { O[id2] = id1; R[id2] = (uint8_t)bin; }
+                else { O[id1] = id2; R[id1] = (uint8_t)bin; }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// SearchForTriangulation (ORBmatcher.cc:660-826, monocular): warp per node of set 1; no dependency between
+// idx1's (vbMatched2 is never set), so the lanes only cooperate on the scan of the node's idx2 list.
+struct TriArgs { float F[9]; float ex, ey; float scale[SSLPL_MAX_LEVELS]; float sigma2[SSLPL_MAX_LEVELS]; };
+
+__global__ void __launch_bounds__(128) k_tri_match(FrameSet S, TriArgs T, int32_t* out, long long out_fs, uint8_t* rot, long long rot_fs) {
+    const int pair = blockIdx.y, lane = threadIdx.x & 31, a = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int f1 = pair, f2 = pair + 1;
+    const int nn1 = S.nn ? S.nn[f1] : S.nn_const, nn2 = S.nn ? S.nn[f2] : S.nn_const;
+    if (a >= nn1) return;
+    const int* nodes1 = S.nodes + f1 * S.nodes_fs; const int* nodes2 = S.nodes + f2 * S.nodes_fs;
+    const int b = find_node(nodes2, nn2, nodes1[a]);
+    if (b < 0) return;
+    const int* off1 = S.off + f1 * S.off_fs; const int* off2 = S.off + f2 * S.off_fs;
+    const int* idx1 = S.idx + f1 * S.idx_fs; const int* idx2 = S.idx + f2 * S.idx_fs;
+    const uint8_t* D1 = S.desc + f1 * S.desc_fs; const uint8_t* D2 = S.desc + f2 * S.desc_fs;
+    const uint8_t* m1 = S.flag + f1 * S.flag_fs; const uint8_t* m2 = S.flag + f2 * S.flag_fs;
+    const long long es = S.angle_es;
+    const float* A1 = S.angle + f1 * S.angle_fs; const float* A2 = S.angle + f2 * S.angle_fs;
+    const float* X1 = S.x + f1 * S.angle_fs; const float* Y1 = S.y + f1 * S.angle_fs;
+    const float* X2 = S.x + f2 * S.angle_fs; const float* Y2 = S.y + f2 * S.angle_fs;
+    const int* OC2 = S.oct + f2 * S.angle_fs;
+    const int b1 = off1[a], e1 = off1[a + 1], b2 = off2[b], e2 = off2[b + 1];
+    for (int i1 = b1; i1 < e1; i1++) {
+        const int id1 = idx1[i1];
+        if (m1[id1]) continue;                                                    // :702-706
+        uint4 a0, a1;
+        load_desc(D1 + (long long)id1 * 32, a0, a1);
+        const float x1 = X1[id1 * es], y1 = Y1[id1 * es];
+        // epipolar line l = x1' F12 (CheckDistEpipolarLine :143-145), f32 without contraction
+        const float la = __fadd_rn(__fadd_rn(__fmul_rn(x1, T.F[0]), __fmul_rn(y1, T.F[3])), T.F[6]);
+        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(x1, T.F[1]), __fmul_rn(y1, T.F[4])), T.F[7]);
+        const float lc = __fadd_rn(__fadd_rn(__fmul_rn(x1, T.F[2]), __fmul_rn(y1, T.F[5])), T.F[8]);
+        const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+        unsigned best = 0xffffffffu;              // min over (dist << 20 | (0xfffff - position)): min distance, LAST wins (:741)
+        for (int i2 = b2 + lane; i2 < e2; i2 += 32) {
+            const int id2 = idx2[i2];
+            if (m2[id2]) continue;                                                // :725-729
+            uint4 c0, c1;
+            load_desc(D2 + (long long)id2 * 32, c0, c1);
+            const int dist = popc256(a0, a1, c0, c1);
+            if (dist > TH_LOW) continue;
+            const float x2 = X2[id2 * es], y2 = Y2[id2 * es];
+            const int oc = OC2[id2 * es];
+            const float dex = __fsub_rn(T.ex, x2), dey = __fsub_rn(T.ey, y2);
+            if (__fadd_rn(__fmul_rn(dex, dex), __fmul_rn(dey, dey)) < __fmul_rn(100.f, T.scale[oc])) continue;    // :749-751
+            const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, x2), __fmul_rn(lb, y2)), lc);
+            if (den == 0.f) continue;
+            const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+            if (!((double)dsqr < 3.84 * (double)T.sigma2[oc])) continue;          // :156 (double compare)
+            const unsigned key = ((unsigned)dist << 20) | (0xfffffu - (unsigned)(i2 - b2));
+            best = min(best, key);
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (best != 0xffffffffu && lane == 0) {
+            const int id2 = idx2[b2 + (int)(0xfffffu - (best & 0xfffffu))];
+            out[pair * out_fs + id1] = id2;
+            rot[pair * rot_fs + id1] = (uint8_t)rot_bin(A1[id1 * es], A2[id2 * es]);
+        }
+    }
+}
+
+// Rotation-histogram filter (ComputeThreeMaxima, ORBmatcher.cc:1604-1645; application :270-288) and match
+// count, one CTA per pair.  compact != 0 additionally writes the (i, out[i]) pairs in ascending i (:818-823).
+__global__ void __launch_bounds__(256) k_rot_filter(int32_t* out, long long out_fs, const uint8_t* rot, long long rot_fs,
+                                                     const int* n_arr, int n_frame_off, int n_const, int cap, int checkOri,
+                                                     int32_t* nmatch, int32_t* pairs, long long pairs_fs) {
+    __shared__ int s_hist[HISTO_LENGTH];
+    __shared__ int s_keep[3];
+    __shared__ int s_warp[33];
+    const int pair = blockIdx.x, tid = threadIdx.x;
+    const int n = n_arr ? min(n_arr[pair + n_frame_off], cap) : n_const;
+    int32_t* O = out + pair * out_fs; const uint8_t* R = rot + pair * rot_fs;
+    if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+    __syncthreads();
+    if (checkOri) {
+        for (int i = tid; i < n; i += 256) if (O[i] >= 0) atomicAdd(&s_hist[R[i]], 1);
+        __syncthreads();
+        if (tid == 0) {
+            int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                const int s = s_hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                else if (s > max3) { max3 = s; ind3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+            s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+        }
+        __syncthreads();
+        const int k0 = s_keep[0], k1 = s_keep[1], k2 = s_keep[2];
+        for (int i = tid; i < n; i += 256)
+            if (O[i] >= 0) { const int b = R[i]; if (b != k0 && b != k1 && b != k2) O[i] = -1; }
+        __syncthreads();
+    }
+    // count (and optionally compact in ascending index order)
+    const int chunk = (n + 255) / 256, pb = min(n, tid * chunk), pe = min(n, pb + chunk);
+    int c = 0;
+    for (int i = pb; i < pe; i++) c += O[i] >= 0;
+    int total;
+    int o = block_exclusive_scan(c, s_warp, &total);
+    if (pairs) for (int i = pb; i < pe; i++) if (O[i] >= 0) { pairs[pair * pairs_fs + 2 * o] = i; pairs[pair * pairs_fs + 2 * o + 1] = O[i]; o++; }
+    if (tid == 0) nmatch[pair] = total;
+}
+
+__global__ void k_fill_i32(int32_t* p, long long n, int v) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// LSDmatcher::SearchByProjection(KF,F) ratio rule on a knn2 table (LSDmatcher.cpp:161-180): out[tdx] = qdx, the
+// LAST accepted query wins (atomicMax over ascending qdx), nmatch counts every acceptance like the reference.
+__global__ void __launch_bounds__(128) k_line_ratio(const int32_t* knn, long long knn_fs, const int* n_arr, int n_const, int cap,
+                                                     const uint8_t* has_ml1, long long ml_fs,
+                                                     int32_t* out, long long out_fs, int32_t* nmatch) {
+    const int pair = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nq = n_arr ? min(n_arr[pair], cap) : n_const;
+    if (q >= nq) return;
+    const int4 r = reinterpret_cast<const int4*>(knn + pair * knn_fs)[q];
+    if (r.x < 0 || r.z < 0) return;
+    const float ratio = __fdiv_rn((float)r.y, (float)r.w);                         // :167
+    if ((double)ratio < (double)(1.0f / 1.5f)) {                                    // :169
+        if (has_ml1 && !has_ml1[pair * ml_fs + q]) return;
+        atomicMax(&out[pair * out_fs + r.x], q);
+        atomicAdd(&nmatch[pair], 1);
+    }
+}
+
+}  // namespace sslpl
+
+// =================================================================================================
+using namespace sslpl;
+
+struct sslpl_matcher {
+    sslpl_matcher_params p;
+    cudaStream_t stream = nullptr;
+    uint8_t* arena = nullptr; size_t arena_size = 0;
+    int cap = 0;                     // rows per frame slot of the single-call staging (max(features, lines))
+    // single-call staging: 2 frame slots
+    uint8_t* desc; int* nodes; int* off; int* idx; uint8_t* flag; float* kpf; int* nn2; int* ncnt;
+    int32_t* out; uint8_t* rot; uint8_t* taken; int32_t* pairs; int32_t* nmatch; int32_t* knn; uint8_t* cent; int32_t* node;
+    // batch workspace
+    int32_t* b_node; int* b_off; int* b_idx; uint8_t* b_rot; uint8_t* b_taken; int32_t* b_knn; int* iota;
+    int32_t* h_small = nullptr;      // pinned scratch
+    long long launches = 0;
+};
+
+namespace {
+
+int carve(sslpl_matcher* m, Arena& A) {
+    const int cap = m->cap, NN = m->p.max_nodes + 1, B = m->p.max_batch + 1;
+    m->desc = A.take<uint8_t>((size_t)2 * cap * 32);
+    m->nodes = A.take<int>((size_t)2 * NN); m->off = A.take<int>((size_t)2 * (NN + 1)); m->idx = A.take<int>((size_t)2 * cap);
+    m->flag = A.take<uint8_t>((size_t)2 * cap);
+    m->kpf = A.take<float>((size_t)2 * cap * 7);
+    m->nn2 = A.take<int>(2); m->ncnt = A.take<int>(2);
+    m->out = A.take<int32_t>(cap); m->rot = A.take<uint8_t>(cap); m->taken = A.take<uint8_t>(cap);
+    m->pairs = A.take<int32_t>((size_t)2 * cap); m->nmatch = A.take<int32_t>(B);
+    m->knn = A.take<int32_t>((size_t)4 * cap);
+    m->cent = A.take<uint8_t>((size_t)NN * 32); m->node = A.take<int32_t>(cap);
+    const int fc = m->p.max_features + 64, lc = m->p.max_lines + 64;
+    m->b_node = A.take<int32_t>((size_t)B * fc); m->b_off = A.take<int>((size_t)B * (NN + 1)); m->b_idx = A.take<int>((size_t)B * fc);
+    m->b_rot = A.take<uint8_t>((size_t)B * fc); m->b_taken = A.take<uint8_t>((size_t)B * fc);
+    m->b_knn = A.take<int32_t>((size_t)B * lc * 4);
+    m->iota = A.take<int>(NN);
+    return 0;
+}
+
+int upload_featvec(sslpl_matcher* m, int slot, const sslpl_featvec* fv, int n) {
+    const int NN = m->p.max_nodes + 1;
+    SSLPL_REQUIRE(fv && fv->nn >= 0 && fv->nn <= m->p.max_nodes, SSLPL_ERR_ARG, "feature vector has more nodes than max_nodes");
+    if (fv->nn == 0) return SSLPL_OK;
+    SSLPL_REQUIRE(fv->nodes && fv->off && fv->idx, SSLPL_ERR_ARG, "null feature vector arrays");
+    SSLPL_REQUIRE(fv->off[fv->nn] <= n, SSLPL_ERR_ARG, "feature vector indexes more features than given");
+    SSLPL_CUDA(cudaMemcpyAsync(m->nodes + slot * NN, fv->nodes, sizeof(int) * fv->nn, cudaMemcpyHostToDevice, m->stream));
+    SSLPL_CUDA(cudaMemcpyAsync(m->off + slot * (NN + 1), fv->off, sizeof(int) * (fv->nn + 1), cudaMemcpyHostToDevice, m->stream));
+    SSLPL_CUDA(cudaMemcpyAsync(m->idx + slot * m->cap, fv->idx, sizeof(int) * fv->off[fv->nn], cudaMemcpyHostToDevice, m->stream));
+    return SSLPL_OK;
+}
+
+FrameSet staging_set(sslpl_matcher* m, int nn1, int nn2, bool with_flags) {
+    const int NN = m->p.max_nodes + 1;
+    FrameSet S; memset(&S, 0, sizeof(S));
+    S.desc = m->desc; S.desc_fs = (long long)m->cap * 32;
+    S.nodes = m->nodes; S.off = m->off; S.idx = m->idx; S.nodes_fs = NN; S.off_fs = NN + 1; S.idx_fs = m->cap;
+    S.nn = m->nn2; (void)nn1; (void)nn2;
+    S.flag = with_flags ? m->flag : nullptr; S.flag_fs = m->cap;
+    S.angle = m->kpf + 3; S.x = m->kpf; S.y = m->kpf + 1; S.oct = reinterpret_cast<const int*>(m->kpf + 5);
+    S.angle_es = 7; S.angle_fs = (long long)m->cap * 7;
+    return S;
+}
+
+int fill(sslpl_matcher* m, int32_t* p, long long n, int v) {
+    if (n <= 0) return SSLPL_OK;
+    k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(p, n, v); m->launches++;
+    return SSLPL_OK;
+}
+
+// upload angles (or full keypoints) into the 7-float-per-row staging of a slot
+int upload_angles(sslpl_matcher* m, int slot, const float* angle, int n) {
+    if (n == 0) return SSLPL_OK;
+    SSLPL_CUDA(cudaMemcpy2DAsync(m->kpf + (size_t)slot * m->cap * 7 + 3, 7 * sizeof(float), angle, sizeof(float), sizeof(float), n,
+                                 cudaMemcpyHostToDevice, m->stream));
+    return SSLPL_OK;
+}
+
+int common_bow(sslpl_matcher* m, int mode, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+               const sslpl_featvec* fv1, const sslpl_featvec* fv2, const uint8_t* valid1, const uint8_t* valid2,
+               const float* angle1, const float* angle2, float nnratio, int checkOri, int32_t* match, int* nmatches) {
+    SSLPL_REQUIRE(m && match && nmatches && fv1 && fv2, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(n1 >= 0 && n2 >= 0 && n1 <= m->p.max_features && n2 <= m->p.max_features, SSLPL_ERR_ARG, "feature count exceeds max_features");
+    SSLPL_REQUIRE((n1 == 0 || (d1 && angle1 && valid1)) && (n2 == 0 || (d2 && angle2)), SSLPL_ERR_ARG, "null descriptor/angle/valid array");
+    SSLPL_REQUIRE(mode == 0 || n2 == 0 || valid2, SSLPL_ERR_ARG, "valid2 required for the KF-KF variant");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    const int nout = mode == 0 ? n2 : n1;
+    if (nout == 0) { *nmatches = 0; return SSLPL_OK; }
+    cudaStream_t st = m->stream;
+    const int cap = m->cap;
+    if (n1) SSLPL_CUDA(cudaMemcpyAsync(m->desc, d1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
+    if (n2) SSLPL_CUDA(cudaMemcpyAsync(m->desc + (size_t)cap * 32, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+    int rc;
+    if ((rc = upload_featvec(m, 0, fv1, n1)) || (rc = upload_featvec(m, 1, fv2, n2))) return rc;
+    if ((rc = upload_angles(m, 0, angle1, n1)) || (rc = upload_angles(m, 1, angle2, n2))) return rc;
+    if (n1) SSLPL_CUDA(cudaMemcpyAsync(m->flag, valid1, n1, cudaMemcpyHostToDevice, st));
+    if (n2 && valid2) SSLPL_CUDA(cudaMemcpyAsync(m->flag + cap, valid2, n2, cudaMemcpyHostToDevice, st));
+    else if (n2) SSLPL_CUDA(cudaMemsetAsync(m->flag + cap, 1, n2, st));
+    m->h_small[0] = fv1->nn; m->h_small[1] = fv2->nn;
+    SSLPL_CUDA(cudaMemcpyAsync(m->nn2, m->h_small, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+    fill(m, m->out, nout, -1);
+    SSLPL_CUDA(cudaMemsetAsync(m->rot, 255, nout, st));
+    SSLPL_CUDA(cudaMemsetAsync(m->taken, 0, std::max(n2, 1), st));
+    FrameSet S = staging_set(m, fv1->nn, fv2->nn, true);
+    if (fv1->nn > 0 && fv2->nn > 0) {
+        k_bow_match<<<dim3((fv1->nn + 3) / 4, 1), 128, 0, st>>>(S, mode, nnratio, cap, m->out, 0, m->rot, 0, m->taken, 0);
+        m->launches++;
+    }
+    k_rot_filter<<<1, 256, 0, st>>>(m->out, 0, m->rot, 0, nullptr, 0, nout, cap, checkOri, m->nmatch, nullptr, 0); m->launches++;
+    SSLPL_CUDA(cudaGetLastError());
+    SSLPL_CUDA(cudaMemcpyAsync(match, m->out, sizeof(int32_t) * nout, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->h_small + 8, m->nmatch, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    *nmatches = m->h_small[8];
+    return SSLPL_OK;
+}
+
+int run_knn2(sslpl_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out_host) {
+    SSLPL_REQUIRE(nq >= 0 && nt >= 0 && nq <= m->cap && nt <= m->cap, SSLPL_ERR_ARG, "row count exceeds the matcher capacity");
+    SSLPL_REQUIRE(nt < (1 << 20), SSLPL_ERR_ARG, "too many train rows");
+    if (nq == 0) return SSLPL_OK;
+    cudaStream_t st = m->stream;
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc, q, (size_t)nq * 32, cudaMemcpyHostToDevice, st));
+    if (nt) SSLPL_CUDA(cudaMemcpyAsync(m->desc + (size_t)m->cap * 32, t, (size_t)nt * 32, cudaMemcpyHostToDevice, st));
+    k_knn2<<<dim3((nq + 7) / 8, 1), 256, 0, st>>>(m->desc, 0, nullptr, nq, m->desc + (size_t)m->cap * 32, 0, nullptr, nt, m->knn, 0, nq);
+    m->launches++;
+    SSLPL_CUDA(cudaGetLastError());
+    if (out_host) {
+        SSLPL_CUDA(cudaMemcpyAsync(out_host, m->knn, sizeof(int32_t) * 4 * nq, cudaMemcpyDeviceToHost, st));
+        SSLPL_CUDA(cudaStreamSynchronize(st));
+    }
+    return SSLPL_OK;
+}
+
+// Frame::lineDescriptorMAD, Frame.cc:190-215 (host: two medians over <= NL values)
+void line_mad(const int32_t* knn, int nq, double* nn_mad, double* nn12_mad) {
+    if (nq <= 0) { *nn_mad = 0; *nn12_mad = 0; return; }
+    std::vector<float> a(nq), g(nq);
+    for (int i = 0; i < nq; i++) a[i] = (float)knn[4 * i + 1];
+    std::sort(a.begin(), a.end());
+    const double med = a[nq / 2];
+    for (int i = 0; i < nq; i++) a[i] = fabsf((float)((float)knn[4 * i + 1] - med));
+    std::sort(a.begin(), a.end());
+    *nn_mad = 1.4826 * a[nq / 2];
+    for (int i = 0; i < nq; i++) g[i] = (float)knn[4 * i + 3] - (float)knn[4 * i + 1];
+    std::sort(g.begin(), g.end(), [](float x, float y) { return x > y; });
+    const double med12 = g[nq / 2];
+    for (int i = 0; i < nq; i++) a[i] = fabsf((float)((float)knn[4 * i + 3] - (float)knn[4 * i + 1] - med12));
+    std::sort(a.begin(), a.end());
+    *nn12_mad = 1.4826 * a[nq / 2];
+}
+
+}  // namespace
+
+extern "C" {
+
+int sslpl_matcher_create(const sslpl_matcher_params* p, sslpl_matcher** out) {
+    SSLPL_REQUIRE(p && out, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(p->max_features >= 1 && p->max_lines >= 0 && p->max_nodes >= 1 && p->max_batch >= 1, SSLPL_ERR_ARG, "bad matcher capacity");
+    SSLPL_REQUIRE(p->max_features < (1 << 20) && p->max_lines < (1 << 20), SSLPL_ERR_ARG, "capacity too large");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_error("no CUDA device available: libsslpl_b200 has no CPU fallback"); return SSLPL_ERR_CUDA; }
+    SSLPL_CUDA(cudaSetDevice(p->device));
+    sslpl_matcher* m = new sslpl_matcher();
+    m->p = *p;
+    m->cap = std::max(p->max_features, p->max_lines) + 64;
+    Arena A; carve(m, A);
+    m->arena_size = A.used + (1 << 16);
+    cudaError_t e = cudaMalloc(&m->arena, m->arena_size);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", m->arena_size, cudaGetErrorString(e)); delete m; return SSLPL_ERR_CUDA; }
+    SSLPL_CUDA(cudaMemset(m->arena, 0, m->arena_size));
+    Arena B; B.base = m->arena; B.size = m->arena_size; carve(m, B);
+    SSLPL_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    SSLPL_CUDA(cudaHostAlloc((void**)&m->h_small, 64 * sizeof(int32_t), cudaHostAllocDefault));
+    {
+        std::vector<int> iota(p->max_nodes + 1);
+        for (int i = 0; i <= p->max_nodes; i++) iota[i] = i;
+        SSLPL_CUDA(cudaMemcpy(m->iota, iota.data(), sizeof(int) * iota.size(), cudaMemcpyHostToDevice));
+    }
+    *out = m;
+    return SSLPL_OK;
+}
+
+void sslpl_matcher_destroy(sslpl_matcher* m) {
+    if (!m) return;
+    cudaSetDevice(m->p.device);
+    if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+    if (m->arena) cudaFree(m->arena);
+    if (m->h_small) cudaFreeHost(m->h_small);
+    delete m;
+}
+
+int sslpl_matcher_sync(sslpl_matcher* m) {
+    SSLPL_REQUIRE(m, SSLPL_ERR_ARG, "null handle");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    SSLPL_CUDA(cudaStreamSynchronize(m->stream));
+    return SSLPL_OK;
+}
+void* sslpl_matcher_stream(sslpl_matcher* m) { return m ? (void*)m->stream : nullptr; }
+long long sslpl_matcher_launch_count(const sslpl_matcher* m) { return m ? m->launches : 0; }
+
+int sslpl_descriptor_distance(sslpl_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {
+    SSLPL_REQUIRE(m && (n == 0 || (a && b && dist)), SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(n >= 0 && n <= m->cap, SSLPL_ERR_ARG, "n exceeds the matcher capacity");
+    if (n == 0) return SSLPL_OK;
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc, a, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc + (size_t)m->cap * 32, b, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    k_pair_distance<<<(n + 127) / 128, 128, 0, st>>>(m->desc, m->desc + (size_t)m->cap * 32, n, m->out); m->launches++;
+    SSLPL_CUDA(cudaGetLastError());
+    SSLPL_CUDA(cudaMemcpyAsync(dist, m->out, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    return SSLPL_OK;
+}
+
+int sslpl_hamming_knn2(sslpl_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out) {
+    SSLPL_REQUIRE(m && (nq == 0 || (q && out)) && (nt == 0 || t), SSLPL_ERR_ARG, "null argument");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    return run_knn2(m, q, nq, t, nt, out);
+}
+
+int sslpl_bow_assign(sslpl_matcher* m, const uint8_t* desc, int n, const uint8_t* centroids, int nc, int32_t* node) {
+    SSLPL_REQUIRE(m && (n == 0 || (desc && node)) && centroids, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(n >= 0 && n <= m->cap && nc >= 1 && nc <= m->p.max_nodes, SSLPL_ERR_ARG, "n or nc exceeds the matcher capacity");
+    if (n == 0) return SSLPL_OK;
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->cent, centroids, (size_t)nc * 32, cudaMemcpyHostToDevice, st));
+    k_bow_assign<<<dim3((n + 127) / 128, 1), 128, nc * 32, st>>>(m->desc, 0, nullptr, n, n, m->cent, nc, m->node, 0); m->launches++;
+    SSLPL_CUDA(cudaGetLastError());
+    SSLPL_CUDA(cudaMemcpyAsync(node, m->node, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    return SSLPL_OK;
+}
+
+int sslpl_search_by_bow(sslpl_matcher* m, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                        const sslpl_featvec* fv1, const sslpl_featvec* fv2, const uint8_t* valid1, const float* angle1, const float* angle2,
+                        float nnratio, int checkOri, int32_t* match2, int* nmatches) {
+    return common_bow(m, 0, d1, n1, d2, n2, fv1, fv2, valid1, nullptr, angle1, angle2, nnratio, checkOri, match2, nmatches);
+}
+
+int sslpl_search_by_bow_kf(sslpl_matcher* m, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                           const sslpl_featvec* fv1, const sslpl_featvec* fv2, const uint8_t* valid1, const uint8_t* valid2,
+                           const float* angle1, const float* angle2, float nnratio, int checkOri, int32_t* match12, int* nmatches) {
+    return common_bow(m, 1, d1, n1, d2, n2, fv1, fv2, valid1, valid2, angle1, angle2, nnratio, checkOri, match12, nmatches);
+}
+
+int sslpl_search_for_triangulation(sslpl_matcher* m, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                                   const sslpl_featvec* fv1, const sslpl_featvec* fv2, const uint8_t* has_mp1, const uint8_t* has_mp2,
+                                   const sslpl_keypoint* kp1, const sslpl_keypoint* kp2, const float* F12, float ex, float ey,
+                                   const float* scale, const float* sigma2, int nlevels, int checkOri, int32_t* pairs, int* nmatches) {
+    SSLPL_REQUIRE(m && pairs && nmatches && fv1 && fv2 && F12 && scale && sigma2, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(n1 >= 0 && n2 >= 0 && n1 <= m->p.max_features && n2 <= m->p.max_features, SSLPL_ERR_ARG, "feature count exceeds max_features");
+    SSLPL_REQUIRE(nlevels >= 1 && nlevels <= SSLPL_MAX_LEVELS, SSLPL_ERR_ARG, "nlevels out of range");
+    SSLPL_REQUIRE((n1 == 0 || (d1 && kp1 && has_mp1)) && (n2 == 0 || (d2 && kp2 && has_mp2)), SSLPL_ERR_ARG, "null array");
+    *nmatches = 0;
+    if (n1 == 0 || n2 == 0) return SSLPL_OK;
+    for (int i = 0; i < n2; i++) SSLPL_REQUIRE(kp2[i].octave >= 0 && kp2[i].octave < nlevels, SSLPL_ERR_ARG, "keypoint octave out of range");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    const int cap = m->cap;
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc, d1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc + (size_t)cap * 32, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+    int rc;
+    if ((rc = upload_featvec(m, 0, fv1, n1)) || (rc = upload_featvec(m, 1, fv2, n2))) return rc;
+    SSLPL_CUDA(cudaMemcpyAsync(m->kpf, kp1, (size_t)n1 * 28, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->kpf + (size_t)cap * 7, kp2, (size_t)n2 * 28, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->flag, has_mp1, n1, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->flag + cap, has_mp2, n2, cudaMemcpyHostToDevice, st));
+    m->h_small[0] = fv1->nn; m->h_small[1] = fv2->nn;
+    SSLPL_CUDA(cudaMemcpyAsync(m->nn2, m->h_small, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+    fill(m, m->out, n1, -1);
+    SSLPL_CUDA(cudaMemsetAsync(m->rot, 255, n1, st));
+    FrameSet S = staging_set(m, fv1->nn, fv2->nn, true);
+    TriArgs T;
+    for (int i = 0; i < 9; i++) T.F[i] = F12[i];
+    T.ex = ex; T.ey = ey;
+    for (int i = 0; i < SSLPL_MAX_LEVELS; i++) { T.scale[i] = i < nlevels ? scale[i] : 0.f; T.sigma2[i] = i < nlevels ? sigma2[i] : 0.f; }
+    if (fv1->nn > 0 && fv2->nn > 0) { k_tri_match<<<dim3((fv1->nn + 3) / 4, 1), 128, 0, st>>>(S, T, m->out, 0, m->rot, 0); m->launches++; }
+    k_rot_filter<<<1, 256, 0, st>>>(m->out, 0, m->rot, 0, nullptr, 0, n1, cap, checkOri, m->nmatch, m->pairs, 0); m->launches++;
+    SSLPL_CUDA(cudaGetLastError());
+    SSLPL_CUDA(cudaMemcpyAsync(m->h_small + 8, m->nmatch, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    *nmatches = m->h_small[8];
+    if (*nmatches > 0) {
+        SSLPL_CUDA(cudaMemcpyAsync(pairs, m->pairs, sizeof(int32_t) * 2 * (*nmatches), cudaMemcpyDeviceToHost, st));
+        SSLPL_CUDA(cudaStreamSynchronize(st));
+    }
+    return SSLPL_OK;
+}
+
+int sslpl_line_match(sslpl_matcher* m, int mode, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                     const uint8_t* has_ml1, const uint8_t* has_ml2, int32_t* out, int* nout, int* nmatches, double* mad) {
+    SSLPL_REQUIRE(m && out && nmatches && mode >= 0 && mode <= 3, SSLPL_ERR_ARG, "bad argument");
+    SSLPL_REQUIRE(n1 >= 0 && n2 >= 0 && n1 <= m->p.max_lines && n2 <= m->p.max_lines, SSLPL_ERR_ARG, "line count exceeds max_lines");
+    // the reference indexes lmatches[i][1] unconditionally (LSDmatcher.cpp:167): it requires >= 2 train rows
+    SSLPL_REQUIRE(n1 == 0 || n2 >= 2, SSLPL_ERR_ARG, "knnMatch(k=2) needs at least 2 train descriptors (reference reads out of bounds otherwise)");
+    SSLPL_REQUIRE((mode != 0 && mode != 3) || n1 == 0 || has_ml1, SSLPL_ERR_ARG, "has_ml1 required");
+    SSLPL_REQUIRE((mode != 2 && mode != 3) || n2 == 0 || has_ml2, SSLPL_ERR_ARG, "has_ml2 required");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    std::vector<int32_t> knn(4 * (size_t)std::max(n1, 1));
+    int rc = run_knn2(m, d1, n1, d2, n2, knn.data());
+    if (rc) return rc;
+    double nn_mad = 0, nn12_mad = 0;
+    line_mad(knn.data(), n1, &nn_mad, &nn12_mad);
+    if (mad) { mad[0] = nn_mad; mad[1] = nn12_mad; }
+    int nm = 0, k = 0;
+    if (mode == 0) for (int j = 0; j < n2; j++) out[j] = -1;
+    if (mode == 2) for (int i = 0; i < n1; i++) out[i] = -1;
+    const float minRatio = 1.0f / 1.5f;
+    for (int i = 0; i < n1; i++) {                      // knn rows are already in queryIdx order (:161)
+        const int tdx = knn[4 * i];
+        const float dist0 = (float)knn[4 * i + 1], dist1 = (float)knn[4 * i + 3];
+        if (mode == 0) {
+            const double dist_12 = dist0 / dist1;
+            if (dist_12 < minRatio && has_ml1[i]) { out[tdx] = i; nm++; }
+        } else if (mode == 1) {
+            if ((double)(dist1 - dist0) > nn12_mad * 0.5) { out[2 * k] = i; out[2 * k + 1] = tdx; k++; nm++; }
+        } else if (mode == 2) {
+            if ((double)(dist1 - dist0) > nn12_mad * 0.5 && has_ml2[tdx]) { out[i] = tdx; nm++; }
+        } else {
+            if (has_ml1[i] || has_ml2[tdx]) continue;
+            if ((double)(dist1 - dist0) > nn12_mad * 0.1) { out[2 * k] = i; out[2 * k + 1] = tdx; k++; nm++; }
+        }
+    }
+    if (nout) *nout = k;
+    *nmatches = nm;
+    return SSLPL_OK;
+}
+
+int sslpl_match_bow_batch_device(sslpl_matcher* m, const uint8_t* d_desc, const sslpl_keypoint* d_kps, const int* d_n,
+                                 int nframes, int cap, const uint8_t* d_centroids, int nc, float nnratio, int checkOri,
+                                 int32_t* d_match, int32_t* d_nmatch) {
+    SSLPL_REQUIRE(m && d_desc && d_kps && d_n && d_centroids && d_match && d_nmatch, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(nframes >= 2 && nframes <= m->p.max_batch + 1, SSLPL_ERR_ARG, "nframes exceeds max_batch+1");
+    SSLPL_REQUIRE(cap >= 1 && cap <= m->p.max_features + 64 && nc >= 1 && nc <= m->p.max_nodes, SSLPL_ERR_ARG, "cap or nc exceeds the matcher capacity");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    const int npairs = nframes - 1, fc = m->p.max_features + 64, NN = m->p.max_nodes + 1;
+    k_bow_assign<<<dim3((cap + 127) / 128, nframes), 128, nc * 32, st>>>(d_desc, (long long)cap * 32, d_n, 0, cap, d_centroids, nc, m->b_node, fc);
+    k_build_csr<<<nframes, 128, (nc + 1) * sizeof(int), st>>>(m->b_node, fc, d_n, cap, nc, m->b_off, NN + 1, m->b_idx, fc);
+    m->launches += 2;
+    fill(m, d_match, (long long)npairs * cap, -1);
+    SSLPL_CUDA(cudaMemsetAsync(m->b_rot, 255, (size_t)npairs * fc, st));
+    SSLPL_CUDA(cudaMemsetAsync(m->b_taken, 0, (size_t)npairs * fc, st));
+    FrameSet S; memset(&S, 0, sizeof(S));
+    S.desc = d_desc; S.desc_fs = (long long)cap * 32;
+    S.n = d_n;
+    S.nodes = nullptr; S.off = m->b_off; S.idx = m->b_idx; S.off_fs = NN + 1; S.idx_fs = fc;
+    // dense vocabulary: node list is 0..nc-1 for every frame -> reuse one iota array
+    S.nodes = m->iota; S.nodes_fs = 0; S.nn = nullptr; S.nn_const = nc;
+    S.flag = nullptr;
+    const float* kf = reinterpret_cast<const float*>(d_kps);
+    S.angle = kf + 3; S.x = kf; S.y = kf + 1; S.oct = reinterpret_cast<const int*>(kf + 5); S.angle_es = 7; S.angle_fs = (long long)cap * 7;
+    k_bow_match<<<dim3((nc + 3) / 4, npairs), 128, 0, st>>>(S, 0, nnratio, cap, d_match, cap, m->b_rot, fc, m->b_taken, fc);
+    k_rot_filter<<<npairs, 256, 0, st>>>(d_match, cap, m->b_rot, fc, d_n, 1, 0, cap, checkOri, d_nmatch, nullptr, 0);
+    m->launches += 2;
+    SSLPL_CUDA(cudaGetLastError());
+    return SSLPL_OK;
+}
+
+int sslpl_match_lines_batch_device(sslpl_matcher* m, const uint8_t* d_ldesc, const int* d_nl, int nframes, int capl,
+                                   int32_t* d_lmatch, int32_t* d_nlmatch) {
+    SSLPL_REQUIRE(m && d_ldesc && d_nl && d_lmatch && d_nlmatch, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(nframes >= 2 && nframes <= m->p.max_batch + 1 && capl >= 1 && capl <= m->p.max_lines + 64, SSLPL_ERR_ARG, "batch or capacity exceeds the matcher capacity");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    const int npairs = nframes - 1, lc = m->p.max_lines + 64;
+    k_knn2<<<dim3((capl + 7) / 8, npairs), 256, 0, st>>>(d_ldesc, (long long)capl * 32, d_nl, 0, d_ldesc + (size_t)capl * 32, (long long)capl * 32,
+                                                          d_nl, 0, m->b_knn, (long long)lc * 4, capl);
+    m->launches++;
+    fill(m, d_lmatch, (long long)npairs * capl, -1);
+    SSLPL_CUDA(cudaMemsetAsync(d_nlmatch, 0, sizeof(int32_t) * npairs, st));
+    k_line_ratio<<<dim3((capl + 127) / 128, npairs), 128, 0, st>>>(m->b_knn, (long long)lc * 4, d_nl, 0, capl, nullptr, 0, d_lmatch, capl, d_nlmatch);
+    m->launches++;
+    SSLPL_CUDA(cudaGetLastError());
+    return SSLPL_OK;
+}
+
+}  // extern "C"
