@@ -1,0 +1,358 @@
+#!/usr/bin/env python3
+"""bench.py — features+matches/sec of the B200 point/line front-end (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic frames on every GPU:
+ORB extraction (+ line extraction when built) of the rank's frames, vocabulary-node assignment and
+SearchByBoW matching of every consecutive frame pair, and one NCCL all-gather of the match tables (N>1).
+
+  workload "batch640" (default; BASELINE.json config 5 sharded weakly): 64 frames 640x480 per GPU
+            (+1 halo frame so that the pair (last, first-of-next-rank) is local), nFeatures=1000, 8 levels
+  workload "single1280" (config 4): frames 1280x960, nFeatures=4000, 4 frames per GPU
+
+`value`  : whole-job (features+matches)/s with the frames already resident in HBM (CUDA events, max over ranks)
+`e2e`    : same metric through the host-buffer API: pinned-host frames H2D, results D2H, every step
+`roofline`: dominant kernel's algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
+`cpu_baseline`: the same step on the host cores with the CPU oracle (port of the reference CPU path)
+--impl reference : times the CPU oracle (the reference's OpenCV build is not compilable here) on
+                   the same config/metric, all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import numpy as np
+
+METRIC = "features+matches/sec"
+UNIT = "features+matches/s"
+
+WORKLOADS = {
+    "batch640": dict(width=640, height=480, nfeatures=1000, frames_per_gpu=64, nlines=40),
+    "single1280": dict(width=1280, height=960, nfeatures=4000, frames_per_gpu=4, nlines=500),
+}
+NWORDS, NNRATIO = 100, 0.7
+
+
+def gen_frames(cfg, rank, nsets):
+    """nsets distinct input batches (so that the inputs cycle through more than the 126 MB L2)."""
+    import synth
+    B = cfg["frames_per_gpu"] + 1
+    sets = []
+    for s in range(nsets):
+        start = (s * 977 + rank) * B * 3
+        sets.append(synth.batch(cfg["width"], cfg["height"], B, start=start))
+    return sets
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference CPU path), all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_step(O, cfg, frames, voc, nthreads):
+    """One step of the workload on the host: returns (features, matches, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    B = len(frames)
+    tl = threading.local()
+
+    def extract(i):
+        if not hasattr(tl, "orb"):
+            tl.orb = O.OrbOracle(cfg["nfeatures"], 1.2, 8, 20, 7)
+        k, d = tl.orb.extract(frames[i])
+        node = O.bow_assign(d, voc)
+        return k, d, O.feature_vector_csr(node)
+
+    def match(i):
+        (k1, d1, fv1), (k2, d2, fv2) = res[i], res[i + 1]
+        n, _ = O.search_by_bow(d1, d2, fv1, fv2, np.ones(len(d1), np.uint8), k1["angle"], k2["angle"], NNRATIO, True)
+        return n
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(nthreads) as ex:
+        res = list(ex.map(extract, range(B)))
+        nm = list(ex.map(match, range(B - 1)))
+    dt = time.perf_counter() - t0
+    feats = sum(len(r[0]) for r in res[:B - 1])
+    return feats, sum(nm), dt
+
+
+def run_reference(args, cfg):
+    """--impl reference: the CPU implementation of the path on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import __graft_entry__ as g
+    O = g.load_oracle()
+    import synth
+    cores = os.cpu_count() or 1
+    voc = synth.vocabulary(NWORDS)
+    nsample = min(cfg["frames_per_gpu"] + 1, max(9, 2 * cores + 1))
+    frames = gen_frames(cfg, 0, 1)[0][:nsample]
+    for _ in range(args.warmup):
+        cpu_step(O, cfg, frames[:min(len(frames), cores + 1)], voc, cores)
+    tot_units, tot_s = 0, 0.0
+    for _ in range(args.steps):
+        f, m, dt = cpu_step(O, cfg, frames, voc, cores)
+        tot_units += f + m; tot_s += dt
+    val = tot_units / tot_s
+    sample = f"{nsample - 1} frames+pairs of the {args.workload} workload per step, oracle C++ port (-O3), {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, **{k: cfg[k] for k in ("width", "height", "nfeatures")},
+                       "frames_per_step": nsample - 1, "lines": "not included (round 1)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, device_index):
+        self.idx = device_index; self.samples = []; self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="batch640", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    import synth
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    W, H, NF, Bf = cfg["width"], cfg["height"], cfg["nfeatures"], cfg["frames_per_gpu"]
+    B = Bf + 1                                          # + halo frame (first frame of the next rank's block)
+    ext = pkg.ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B, device=local)
+    mt = pkg.Matcher(max_features=ext.cap, max_lines=cfg["nlines"], max_nodes=NWORDS, max_batch=B, device=local)
+    stream = torch.cuda.Stream(device=dev)              # one explicit (non-default) stream for kernels, NCCL waits and the timing events
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ext.set_stream(stream.cuda_stream); mt.set_stream(stream.cuda_stream)
+    cap = ext.cap
+    voc = synth.vocabulary(NWORDS)
+    d_voc = torch.from_numpy(voc).to(dev)
+    nsets = max(2, int(np.ceil(160e6 / (B * W * H))))   # cycle > 126 MB of distinct inputs => inputs never L2-resident
+    sets = gen_frames(cfg, rank, nsets)
+    d_sets = [torch.from_numpy(s).to(dev) for s in sets]
+    d_match = torch.empty((Bf, cap), dtype=torch.int32, device=dev)
+    d_nmatch = torch.empty((Bf,), dtype=torch.int32, device=dev)
+    d_gather = torch.empty((world * Bf, cap), dtype=torch.int32, device=dev) if world > 1 else None
+    d_kps, d_desc, d_n, _ = None, None, None, None
+
+    def step_device(i):
+        fr = d_sets[i % nsets]
+        ext.extract_batch_device(fr.data_ptr(), B, W, H, W, W * H)
+        kps, desc, n, c = ext.device_results()
+        mt.match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match.data_ptr(), d_nmatch.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(d_gather, d_match)
+        return kps, desc, n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then K timed steps, device-resident inputs ----
+    for i in range(args.warmup):
+        step_device(i)
+    ext.sync()
+    launches0 = ext.launch_count + mt.launch_count
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    units = 0
+    e0.record()
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    ext.sync()
+    launches = ext.launch_count + mt.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # units: count features+matches of every step's batch (one extra, untimed pass per distinct set)
+    per_set = []
+    nkp_avg = 0.0
+    for s in range(nsets):
+        _, _, hn = ext.extract_batch(sets[s])                                   # host API: returns the per-frame counts
+        kps_, desc_, n_, c_ = ext.device_results()
+        mt.match_bow_batch_device(desc_, kps_, n_, B, c_, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match.data_ptr(), d_nmatch.data_ptr())
+        torch.cuda.synchronize()
+        per_set.append(int(hn[:Bf].sum()) + int(d_nmatch.cpu().sum()))
+        nkp_avg += float(hn.mean()) / nsets
+    units = sum(per_set[(args.warmup + i) % nsets] for i in range(args.steps))
+    t = torch.tensor([ms_total, float(units)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, units_all = float(tmax[0]), float(tsum[1])
+    else:
+        units_all = float(units)
+    value = units_all / (ms_total * 1e-3)
+
+    # ---- e2e: pinned host frames -> H2D -> kernels -> D2H of keypoints, descriptors, counts, match tables ----
+    h_sets = []
+    for s in sets[:min(nsets, 4)]:
+        hp = pkg.host_alloc(s.shape, np.uint8); hp[...] = s; h_sets.append(hp)
+    h_out = (pkg.host_alloc((B, cap), pkg.KEYPOINT_DTYPE), pkg.host_alloc((B, cap, 32), np.uint8), pkg.host_alloc((B,), np.int32))
+    h_match = torch.empty((Bf, cap), dtype=torch.int32).pin_memory()
+    h_nmatch = torch.empty((Bf,), dtype=torch.int32).pin_memory()
+
+    def step_e2e(i):
+        ext.extract_batch(h_sets[i % len(h_sets)], out=h_out)                 # H2D + kernels + D2H (synchronous API)
+        kps, desc, n, c = ext.device_results()
+        mt.match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match.data_ptr(), d_nmatch.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(d_gather, d_match)
+        h_match.copy_(d_match, non_blocking=True); h_nmatch.copy_(d_nmatch, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return int(h_out[2][:Bf].sum()) + int(h_nmatch.sum())
+
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter(); e0.record()
+    eu = 0
+    for i in range(args.steps):
+        eu += step_e2e(args.warmup + i)
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    t = torch.tensor([e2e_ms, float(eu)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        e2e_ms, eu_all = float(tmax[0]), float(tsum[1])
+    else:
+        eu_all = float(eu)
+    h2d = B * W * H
+    d2h = B * cap * (28 + 32) + B * 4 + Bf * cap * 4 + Bf * 4
+
+    # ---- roofline of the dominant kernel (rank 0): CUDA events between the kernels of one handle ----
+    roofline = None
+    if rank == 0:
+        ext.set_profiling(True)
+        acc = {}
+        nprof = 5
+        for i in range(nprof):
+            step_device(i); ext.sync()
+            for k, v in ext.stage_ms().items():
+                acc[k] = acc.get(k, 0.0) + v / nprof
+        ext.set_profiling(False)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0)); which = "measured" if "hbm_gbs" in peaks else "fallback"
+        P = sum(ext.level_size(l)[0] * ext.level_size(l)[1] for l in range(8))
+        ncand = 0
+        for l in range(8):
+            ncand += len(ext.candidates(l, frame=0)[0])
+        alg = {   # algorithmic bytes per frame, SURVEY.md 8(d) byte table
+            "pyramid": 2 * P - W * H - ext.level_size(7)[0] * ext.level_size(7)[1],
+            "fast": P + 5 * ncand,
+            "blur": 2 * P,
+            "orient_desc": (749 + 512 + 32 + 28 + 4) * nkp_avg,
+            "octree": 8 * ncand,
+        }
+        dom = max(acc, key=acc.get)
+        achieved = alg.get(dom, 0) * B / (acc[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": which, "stage_ms": acc,
+                    "stage_gbs": {k: alg.get(k, 0) * B / (acc[k] * 1e-3) / 1e9 for k in acc}}
+
+    # ---- CPU baseline on the host cores (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        O = g.load_oracle()
+        cores = os.cpu_count() or 1
+        ns = min(B, max(9, 2 * cores + 1))
+        cpu_step(O, cfg, sets[0][:min(ns, cores + 1)], voc, cores)
+        best = None
+        for _ in range(2):
+            f, m, dt = cpu_step(O, cfg, sets[0][:ns], voc, cores)
+            v = (f + m) / dt
+            best = v if best is None or v > best else best
+        cpu = {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{ns - 1} frames+pairs of the {args.workload} workload, oracle C++ port, {cores} threads, best of 2"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": args.workload, "width": W, "height": H, "nfeatures": NF, "nlevels": 8,
+                           "frames_per_gpu": Bf, "halo_frames_per_gpu": 1, "pairs_per_gpu": Bf, "vocabulary_nodes": NWORDS,
+                           "lines": "not included (round 1)", "parallelism": f"frames sharded x{world}, all_gather(match tables)",
+                           "l2": f"inputs cycle through {nsets} distinct batches ({nsets * B * W * H / 1e6:.0f} MB > 126 MB L2)"},
+                "e2e": {"value": eu_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -91,6 +91,8 @@ int  sslpl_orb_extract_batch_device(sslpl_orb* h, const uint8_t* d_imgs, int nfr
 int  sslpl_orb_device_results(sslpl_orb* h, const sslpl_keypoint** d_kps, const uint8_t** d_desc, const int** d_n, int* cap);
 int  sslpl_orb_sync(sslpl_orb* h);           /* wait for the handle's stream; reports deferred device-side errors */
 void* sslpl_orb_stream(sslpl_orb* h);        /* cudaStream_t of the handle */
+/* Run the handle on a caller-owned cudaStream_t (e.g. the framework's current stream) instead of its own. */
+int  sslpl_orb_set_stream(sslpl_orb* h, void* cuda_stream);
 /* mvImagePyramid[level] (ORBextractor.h:79) of frame f of the last call; bordered=1 adds the 19-px
    BORDER_REFLECT_101 frame of ComputePyramid (ORBextractor.cc:1107-1132). dst is a HOST buffer. */
 int  sslpl_orb_level_size(const sslpl_orb* h, int level, int* w, int* hgt);
@@ -121,6 +123,7 @@ int  sslpl_matcher_create(const sslpl_matcher_params* p, sslpl_matcher** out);
 void sslpl_matcher_destroy(sslpl_matcher* m);
 int  sslpl_matcher_sync(sslpl_matcher* m);
 void* sslpl_matcher_stream(sslpl_matcher* m);
+int  sslpl_matcher_set_stream(sslpl_matcher* m, void* cuda_stream);
 long long sslpl_matcher_launch_count(const sslpl_matcher* m);
 
 /* ORBmatcher::DescriptorDistance (ORBmatcher.cc:1650) for nq pairs a[i] vs b[i] (HOST buffers) */
@@ -197,6 +200,7 @@ int  sslpl_line_device_results(sslpl_line* h, const sslpl_keyline** d_kl, const 
                                const int** d_n, int* cap);
 int  sslpl_line_sync(sslpl_line* h);
 void* sslpl_line_stream(sslpl_line* h);
+int  sslpl_line_set_stream(sslpl_line* h, void* cuda_stream);
 long long sslpl_line_launch_count(const sslpl_line* h);
 /* raw LSD segments (before the top-N cut) of frame f of the last call: seg[4*i] = x1,y1,x2,y2 */
 int  sslpl_line_download_segments(sslpl_line* h, int frame, float* seg4, int cap, int* n);

@@ -190,6 +190,9 @@ class ORBextractor:
     def sync(self):
         _check(lib().sslpl_orb_sync(self._h))
 
+    def set_stream(self, cuda_stream):
+        _check(lib().sslpl_orb_set_stream(self._h, C.c_void_p(cuda_stream)))
+
     @property
     def stream(self):
         return lib().sslpl_orb_stream(self._h)
@@ -236,3 +239,172 @@ class ORBextractor:
         ms = (C.c_float * 16)(); names = (C.c_char_p * 16)(); n = C.c_int()
         _check(lib().sslpl_orb_stage_ms(self._h, ms, 16, names, C.byref(n)))
         return {names[i].decode(): float(ms[i]) for i in range(n.value)}
+
+
+# =====================================================================================================
+# Matching
+# =====================================================================================================
+def _featvec(fv):
+    """(nodes, off, idx) int32 arrays -> FeatVec struct (keeps references alive)."""
+    nodes, off, idx = (np.ascontiguousarray(a, np.int32) for a in fv)
+    s = FeatVec(_p(nodes) if len(nodes) else None, _p(off), _p(idx) if len(idx) else None, len(nodes))
+    s._keep = (nodes, off, idx)
+    return s
+
+
+def feature_vector_csr(node):
+    """DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>; FeatureVector.cpp:31-45) flattened to CSR."""
+    node = np.asarray(node, np.int32)
+    order = np.argsort(node, kind="stable").astype(np.int32)
+    ids, counts = np.unique(node, return_counts=True)
+    off = np.zeros(len(ids) + 1, np.int32)
+    off[1:] = np.cumsum(counts)
+    return ids.astype(np.int32), off, order
+
+
+class Matcher:
+    """Device context shared by ORBmatcher / LSDmatcher below (one stream + workspace; create one per thread)."""
+
+    def __init__(self, max_features=4096, max_lines=512, max_nodes=1024, max_batch=1, device=0):
+        p = MatcherParams(max_features, max_lines, max_nodes, max_batch, device)
+        self._h = C.c_void_p()
+        _check(lib().sslpl_matcher_create(C.byref(p), C.byref(self._h)))
+        self.max_features, self.max_lines = max_features, max_lines
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().sslpl_matcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def sync(self):
+        _check(lib().sslpl_matcher_sync(self._h))
+
+    def set_stream(self, cuda_stream):
+        _check(lib().sslpl_matcher_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    @property
+    def stream(self):
+        return lib().sslpl_matcher_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(lib().sslpl_matcher_launch_count(self._h))
+
+    def descriptor_distance(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32); b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        out = np.empty(len(a), np.int32)
+        _check(lib().sslpl_descriptor_distance(self._h, _p(a), _p(b), len(a), _p(out)))
+        return out
+
+    def knn2(self, q, t):
+        """cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2) -> int32 [nq,4] = idx0, d0, idx1, d1."""
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+        out = np.empty((len(q), 4), np.int32)
+        _check(lib().sslpl_hamming_knn2(self._h, _p(q), len(q), _p(t), len(t), _p(out)))
+        return out
+
+    def bow_assign(self, desc, centroids):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); centroids = np.ascontiguousarray(centroids, np.uint8).reshape(-1, 32)
+        node = np.empty(len(desc), np.int32)
+        _check(lib().sslpl_bow_assign(self._h, _p(desc), len(desc), _p(centroids), len(centroids), _p(node)))
+        return node
+
+    def match_bow_batch_device(self, d_desc, d_kps, d_n, nframes, cap, d_centroids, nc, nnratio, check_ori, d_match, d_nmatch):
+        _check(lib().sslpl_match_bow_batch_device(self._h, C.c_void_p(d_desc), C.c_void_p(d_kps), C.c_void_p(d_n), nframes, cap,
+                                                  C.c_void_p(d_centroids), nc, C.c_float(nnratio), int(check_ori),
+                                                  C.c_void_p(d_match), C.c_void_p(d_nmatch)))
+
+    def match_lines_batch_device(self, d_ldesc, d_nl, nframes, capl, d_lmatch, d_nlmatch):
+        _check(lib().sslpl_match_lines_batch_device(self._h, C.c_void_p(d_ldesc), C.c_void_p(d_nl), nframes, capl,
+                                                    C.c_void_p(d_lmatch), C.c_void_p(d_nlmatch)))
+
+
+class ORBmatcher:
+    """Mirror of StructureSLAM::ORBmatcher (include/ORBmatcher.h:36-101) on indices + masks instead of
+    KeyFrame*/MapPoint* (the C++ adapter in host/ maps indices back to pointers)."""
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
+
+    def __init__(self, nnratio=0.6, checkOri=True, ctx=None):
+        self.mfNNratio, self.mbCheckOrientation = float(nnratio), bool(checkOri)
+        self.ctx = ctx or Matcher()
+
+    def DescriptorDistance(self, a, b):
+        return int(self.ctx.descriptor_distance(a, b)[0])
+
+    def SearchByBoW(self, d1, fv1, valid1, angle1, d2, fv2, angle2, valid2=None):
+        """KeyFrame-vs-Frame (valid2 is None; ORBmatcher.cc:159) -> (nmatches, match2[n2] = KF index or -1);
+        KeyFrame-vs-KeyFrame (valid2 given; ORBmatcher.cc:525) -> (nmatches, match12[n1] = KF2 index or -1)."""
+        d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        f1, f2 = _featvec(fv1), _featvec(fv2)
+        valid1 = np.ascontiguousarray(valid1, np.uint8)
+        angle1 = np.ascontiguousarray(angle1, np.float32); angle2 = np.ascontiguousarray(angle2, np.float32)
+        nm = C.c_int()
+        if valid2 is None:
+            out = np.empty(len(d2), np.int32)
+            _check(lib().sslpl_search_by_bow(self.ctx._h, _p(d1), len(d1), _p(d2), len(d2), C.byref(f1), C.byref(f2),
+                                             _p(valid1), _p(angle1), _p(angle2), C.c_float(self.mfNNratio),
+                                             int(self.mbCheckOrientation), _p(out), C.byref(nm)))
+        else:
+            valid2 = np.ascontiguousarray(valid2, np.uint8)
+            out = np.empty(len(d1), np.int32)
+            _check(lib().sslpl_search_by_bow_kf(self.ctx._h, _p(d1), len(d1), _p(d2), len(d2), C.byref(f1), C.byref(f2),
+                                                _p(valid1), _p(valid2), _p(angle1), _p(angle2), C.c_float(self.mfNNratio),
+                                                int(self.mbCheckOrientation), _p(out), C.byref(nm)))
+        return nm.value, out
+
+    def SearchForTriangulation(self, d1, fv1, has_mp1, kp1, d2, fv2, has_mp2, kp2, F12, ex, ey, scale, sigma2):
+        """ORBmatcher.cc:660 (monocular) -> (nmatches, pairs[nmatches,2])."""
+        d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        f1, f2 = _featvec(fv1), _featvec(fv2)
+        has_mp1 = np.ascontiguousarray(has_mp1, np.uint8); has_mp2 = np.ascontiguousarray(has_mp2, np.uint8)
+        kp1 = np.ascontiguousarray(kp1, KEYPOINT_DTYPE); kp2 = np.ascontiguousarray(kp2, KEYPOINT_DTYPE)
+        F12 = np.ascontiguousarray(F12, np.float32).reshape(9)
+        scale = np.ascontiguousarray(scale, np.float32); sigma2 = np.ascontiguousarray(sigma2, np.float32)
+        pairs = np.empty((max(len(d1), 1), 2), np.int32)
+        nm = C.c_int()
+        _check(lib().sslpl_search_for_triangulation(self.ctx._h, _p(d1), len(d1), _p(d2), len(d2), C.byref(f1), C.byref(f2),
+                                                    _p(has_mp1), _p(has_mp2), _p(kp1), _p(kp2), _p(F12), C.c_float(ex), C.c_float(ey),
+                                                    _p(scale), _p(sigma2), len(scale), int(self.mbCheckOrientation),
+                                                    _p(pairs), C.byref(nm)))
+        return nm.value, pairs[:nm.value].copy()
+
+
+class LSDmatcher:
+    """Mirror of the knnMatch-based entry points of StructureSLAM::LSDmatcher (include/LSDmatcher.h:36-64)."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or Matcher()
+
+    def _run(self, mode, d1, d2, has_ml1, has_ml2):
+        d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        h1 = np.ascontiguousarray(has_ml1 if has_ml1 is not None else np.zeros(len(d1)), np.uint8)
+        h2 = np.ascontiguousarray(has_ml2 if has_ml2 is not None else np.zeros(len(d2)), np.uint8)
+        out = np.full(2 * max(len(d1), len(d2), 1), -1, np.int32)
+        k = C.c_int(); nm = C.c_int(); mad = (C.c_double * 2)()
+        _check(lib().sslpl_line_match(self.ctx._h, mode, _p(d1), len(d1), _p(d2), len(d2), _p(h1), _p(h2), _p(out),
+                                      C.byref(k), C.byref(nm), mad))
+        self.last_mad = (mad[0], mad[1])
+        if mode == 0:
+            return nm.value, out[:len(d2)].copy()
+        if mode == 2:
+            return nm.value, out[:len(d1)].copy()
+        return nm.value, out[:2 * k.value].reshape(-1, 2).copy()
+
+    def SearchByProjection(self, ldescKF, has_mapline_KF, ldescF):      # LSDmatcher.cpp:143 (KeyFrame*, Frame&)
+        return self._run(0, ldescKF, ldescF, has_mapline_KF, None)
+
+    SearchByDescriptor = SearchByProjection                             # LSDmatcher.cpp:286 (identical body)
+
+    def SerachForInitialize(self, ldesc1, ldesc2):                      # LSDmatcher.cpp:257 (sic)
+        return self._run(1, ldesc1, ldesc2, None, None)
+
+    def SearchByDescriptorKF(self, ldesc1, ldesc2, has_mapline_KF2):    # LSDmatcher.cpp:329
+        return self._run(2, ldesc1, ldesc2, None, has_mapline_KF2)
+
+    def SearchForTriangulation(self, ldesc1, has_ml1, ldesc2, has_ml2):  # LSDmatcher.cpp:382
+        return self._run(3, ldesc1, ldesc2, has_ml1, has_ml2)
+
+    def DescriptorDistance(self, a, b):                                 # LSDmatcher.cpp:364
+        return int(self.ctx.descriptor_distance(a, b)[0])

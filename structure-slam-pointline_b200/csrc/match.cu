@@ -335,7 +335,7 @@ using namespace sslpl;
 
 struct sslpl_matcher {
     sslpl_matcher_params p;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     uint8_t* arena = nullptr; size_t arena_size = 0;
     int cap = 0;                     // rows per frame slot of the single-call staging (max(features, lines))
     // single-call staging: 2 frame slots
@@ -500,7 +500,8 @@ int sslpl_matcher_create(const sslpl_matcher_params* p, sslpl_matcher** out) {
     if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", m->arena_size, cudaGetErrorString(e)); delete m; return SSLPL_ERR_CUDA; }
     SSLPL_CUDA(cudaMemset(m->arena, 0, m->arena_size));
     Arena B; B.base = m->arena; B.size = m->arena_size; carve(m, B);
-    SSLPL_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    SSLPL_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    m->stream = m->own_stream;
     SSLPL_CUDA(cudaHostAlloc((void**)&m->h_small, 64 * sizeof(int32_t), cudaHostAllocDefault));
     {
         std::vector<int> iota(p->max_nodes + 1);
@@ -514,7 +515,8 @@ int sslpl_matcher_create(const sslpl_matcher_params* p, sslpl_matcher** out) {
 void sslpl_matcher_destroy(sslpl_matcher* m) {
     if (!m) return;
     cudaSetDevice(m->p.device);
-    if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->arena) cudaFree(m->arena);
     if (m->h_small) cudaFreeHost(m->h_small);
     delete m;
@@ -527,6 +529,13 @@ int sslpl_matcher_sync(sslpl_matcher* m) {
     return SSLPL_OK;
 }
 void* sslpl_matcher_stream(sslpl_matcher* m) { return m ? (void*)m->stream : nullptr; }
+int sslpl_matcher_set_stream(sslpl_matcher* m, void* cuda_stream) {
+    SSLPL_REQUIRE(m, SSLPL_ERR_ARG, "null handle");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    SSLPL_CUDA(cudaStreamSynchronize(m->stream));
+    m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
+    return SSLPL_OK;
+}
 long long sslpl_matcher_launch_count(const sslpl_matcher* m) { return m ? m->launches : 0; }
 
 int sslpl_descriptor_distance(sslpl_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {

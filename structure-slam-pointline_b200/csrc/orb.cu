@@ -587,7 +587,7 @@ struct sslpl_orb {
     sslpl_orb_params p;
     std::vector<float> scale, invscale, sigma2, invsigma2;
     std::vector<int> nfeat, umax;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     uint8_t* arena = nullptr; size_t arena_size = 0;
     OrbGeom g; OrbWs ws; View view;
     uint8_t* d_input = nullptr;         // staging for host frames
@@ -801,7 +801,8 @@ int sslpl_orb_create(const sslpl_orb_params* p, sslpl_orb** out) {
     cudaError_t e = cudaMalloc(&h->arena, h->arena_size);
     if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", h->arena_size, cudaGetErrorString(e)); delete h; return SSLPL_ERR_CUDA; }
     SSLPL_CUDA(cudaMemset(h->arena, 0, h->arena_size));
-    SSLPL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    SSLPL_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
     SSLPL_CUDA(cudaHostAlloc((void**)&h->h_err, sizeof(int), cudaHostAllocDefault));
     *out = h;
     return SSLPL_OK;
@@ -810,7 +811,8 @@ int sslpl_orb_create(const sslpl_orb_params* p, sslpl_orb** out) {
 void sslpl_orb_destroy(sslpl_orb* h) {
     if (!h) return;
     cudaSetDevice(h->p.device);
-    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto e : h->ev) cudaEventDestroy(e);
     if (h->arena) cudaFree(h->arena);
     if (h->h_err) cudaFreeHost(h->h_err);
@@ -864,6 +866,14 @@ int sslpl_orb_sync(sslpl_orb* h) {
 }
 
 void* sslpl_orb_stream(sslpl_orb* h) { return h ? (void*)h->stream : nullptr; }
+
+int sslpl_orb_set_stream(sslpl_orb* h, void* cuda_stream) {
+    SSLPL_REQUIRE(h, SSLPL_ERR_ARG, "null handle");
+    SSLPL_CUDA(cudaSetDevice(h->p.device));
+    SSLPL_CUDA(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return SSLPL_OK;
+}
 
 int sslpl_orb_extract_batch(sslpl_orb* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
                             sslpl_keypoint* kps, uint8_t* desc, int cap, int* n) {
