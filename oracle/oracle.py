@@ -261,3 +261,57 @@ def line_match(mode, d1, d2, has_ml1=None, has_ml2=None):
     if mode == 2:
         return n, out[:len(d1)].copy()
     return n, out[:2 * k.value].reshape(-1, 2).copy()
+
+
+# ---------------- lines ----------------
+def lsd_detect_scaled(img, cap=1 << 14):
+    """cv::createLineSegmentDetector(LSD_REFINE_ADV, scale=1.0).detect(img): float32 [n,4]."""
+    img = _u8(img)
+    seg = np.empty((cap, 4), np.float32)
+    n = lib().orc_lsd_detect_scaled(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(seg), cap)
+    assert n <= cap
+    return seg[:n].copy()
+
+
+def lbd_prep(img):
+    img = _u8(img)
+    dx = np.empty(img.shape, np.int16); dy = np.empty(img.shape, np.int16)
+    lib().orc_lbd_prep(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(dx), _p(dy))
+    return dx, dy
+
+
+class LineOracle:
+    """LineSegment::ExtractLineSegment restatement (ExtractLineSegment.cpp:18-69)."""
+
+    def __init__(self, lsd_nfeatures=40):
+        self.nfeat = lsd_nfeatures
+        self.h = C.c_void_p(lib().orc_line_create(lsd_nfeatures))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_line_destroy(self.h)
+            self.h = None
+
+    def extract(self, img):
+        img = _u8(img)
+        cap = self.nfeat
+        kl = np.zeros(cap, KEYLINE_DTYPE); ld = np.zeros((cap, 32), np.uint8); eq = np.zeros((cap, 3), np.float64)
+        n = lib().orc_line_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kl), _p(ld), _p(eq), cap)
+        return kl[:n].copy(), ld[:n].copy(), eq[:n].copy()
+
+    def raw_segments(self, cap=1 << 14):
+        seg = np.empty((cap, 4), np.float32)
+        n = lib().orc_line_raw_segments(self.h, _p(seg), cap)
+        return seg[:n].copy()
+
+    def scaled(self):
+        w = C.c_int(); h = C.c_int()
+        lib().orc_line_scaled_copy(self.h, None, 0, C.byref(w), C.byref(h))
+        out = np.empty((h.value, w.value), np.uint8)
+        lib().orc_line_scaled_copy(self.h, _p(out), out.strides[0], C.byref(w), C.byref(h))
+        return out
+
+    def stage_ms(self):
+        ms = np.empty(4, np.float64)
+        lib().orc_line_stage_ms(self.h, _p(ms))
+        return dict(zip(["prep", "lsd", "keylines", "lbd"], ms.tolist()))
