@@ -204,6 +204,9 @@ int  sslpl_line_set_stream(sslpl_line* h, void* cuda_stream);
 long long sslpl_line_launch_count(const sslpl_line* h);
 /* raw LSD segments (before the top-N cut) of frame f of the last call: seg[4*i] = x1,y1,x2,y2 */
 int  sslpl_line_download_segments(sslpl_line* h, int frame, float* seg4, int cap, int* n);
+/* debug: with SSLPL_LINE_TRACE=1 in the environment at create time, one row of 10 doubles per LSD region that reached
+   region2rect: seed pixel, size before/after refine, log_nfa, x1,y1,x2,y2,width,p (detection scale) */
+int  sslpl_line_debug_trace(sslpl_line* h, int frame, double* out, int cap_rows, int* n);
 
 #ifdef __cplusplus
 }

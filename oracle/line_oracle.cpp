@@ -77,6 +77,7 @@ struct Lsd {
     std::vector<uchar> used;
     std::vector<int> order;      // pixel indices (y*w+x), bins descending, raster inside a bin
     double LOG_NT;
+    std::vector<double> trace;   // per region that reached region2rect: seed, n0, n1, log_nfa, x1, y1, x2, y2, width, p
 
     void ll_angle(const uchar* img, int pitch, double threshold, int n_bins) {
         angles.assign((size_t)w * h, NOTDEF); modgrad.assign((size_t)w * h, 0.0);
@@ -345,7 +346,7 @@ struct Lsd {
         const size_t min_reg_size = size_t(-LOG_NT / std::log10(p));
         used.assign((size_t)w * h, 0);
         std::vector<RegPt> reg;
-        out.clear();
+        out.clear(); trace.clear();
         for (int idx : order) {
             if (used[idx] != 0 || angles[idx] == NOTDEF) continue;
             double reg_angle;
@@ -353,8 +354,10 @@ struct Lsd {
             if (reg.size() < min_reg_size) continue;
             Rect rec;
             region2rect(reg, reg_angle, prec, p, rec);
-            if (!refine(reg, reg_angle, prec, p, rec, DENSITY_TH)) continue;
+            const double n0 = (double)reg.size();
+            if (!refine(reg, reg_angle, prec, p, rec, DENSITY_TH)) { double t[10] = {(double)idx, n0, (double)reg.size(), -1e9, 0, 0, 0, 0, 0, 0}; trace.insert(trace.end(), t, t + 10); continue; }
             const double log_nfa = rect_improve(rec);
+            { double t[10] = {(double)idx, n0, (double)reg.size(), log_nfa, rec.x1, rec.y1, rec.x2, rec.y2, rec.width, rec.p}; trace.insert(trace.end(), t, t + 10); }
             if (log_nfa <= 0.0) continue;
             out.push_back(rec);
         }
@@ -471,6 +474,7 @@ void lbd_descriptor(const orc_keyline& kl, const int16_t* dxImg, const int16_t* 
 
 struct orc_line {
     int nfeat;
+    std::vector<double> trace;
     std::vector<float> raw;       // x1,y1,x2,y2 per raw LSD segment
     std::vector<uchar> scaled; int sw = 0, sh = 0;
     double ms[4];
@@ -512,6 +516,7 @@ extern "C" int orc_line_extract(orc_line* o, const uchar* img, int w, int h, int
     double t1 = now_ms();
     Lsd lsd; std::vector<Rect> recs;
     lsd.detect(o->scaled.data(), o->sw, o->sh, o->sw, recs);
+    o->trace = lsd.trace;
     double t2 = now_ms();
     // LSDDetector::detectImpl (line_descriptor LSDDetector.cpp) [memory]: KeyLine packaging, octave 0, scale 1
     std::vector<orc_keyline> kls;
@@ -580,3 +585,9 @@ extern "C" void orc_line_scaled_copy(const orc_line* o, uchar* dst, int dpitch, 
     if (dst) for (int y = 0; y < o->sh; y++) memcpy(dst + (size_t)y * dpitch, &o->scaled[(size_t)y * o->sw], o->sw);
 }
 extern "C" void orc_line_stage_ms(const orc_line* o, double* ms4) { for (int i = 0; i < 4; i++) ms4[i] = o->ms[i]; }
+
+extern "C" int orc_line_trace(const orc_line* o, double* out, int cap_rows) {
+    const int n = (int)o->trace.size() / 10;
+    for (int i = 0; i < n && i < cap_rows; i++) memcpy(out + 10 * i, &o->trace[10 * i], 80);
+    return n;
+}

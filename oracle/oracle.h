@@ -102,6 +102,8 @@ int   orc_line_extract(orc_line*, const uint8_t* img, int w, int h, int pitch,
 int   orc_line_raw_segments(const orc_line*, float* seg4, int cap);
 void  orc_line_scaled_copy(const orc_line*, uint8_t* dst, int dpitch, int* w, int* h);
 void  orc_line_stage_ms(const orc_line*, double* ms4);
+/* debug trace of the last call: 10 doubles per region that reached region2rect */
+int   orc_line_trace(const orc_line*, double* out, int cap_rows);
 /* LSD on an already-scaled image (scale=1.0 path) */
 int   orc_lsd_detect_scaled(const uint8_t* img, int w, int h, int pitch, float* seg4, int cap);
 void  orc_lbd_prep(const uint8_t* img, int w, int h, int pitch, int16_t* dx, int16_t* dy);

@@ -311,6 +311,11 @@ class LineOracle:
         lib().orc_line_scaled_copy(self.h, _p(out), out.strides[0], C.byref(w), C.byref(h))
         return out
 
+    def trace(self, cap=1 << 16):
+        out = np.empty((cap, 10), np.float64)
+        n = lib().orc_line_trace(self.h, _p(out), cap)
+        return out[:min(n, cap)].copy()
+
     def stage_ms(self):
         ms = np.empty(4, np.float64)
         lib().orc_line_stage_ms(self.h, _p(ms))

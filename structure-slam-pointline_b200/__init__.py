@@ -408,3 +408,77 @@ class LSDmatcher:
 
     def DescriptorDistance(self, a, b):                                 # LSDmatcher.cpp:364
         return int(self.ctx.descriptor_distance(a, b)[0])
+
+
+# =====================================================================================================
+# Lines
+# =====================================================================================================
+class LineSegment:
+    """Mirror of StructureSLAM::LineSegment (include/ExtractLineSegment.h:53-76).  lsdNFeatures is hard-coded to 40
+    in the reference (ExtractLineSegment.cpp:42); it is a constructor parameter here (BASELINE.json config 4: 500)."""
+
+    def __init__(self, lsdNFeatures=40, max_width=1280, max_height=960, max_batch=1, device=0):
+        p = LineParams(lsdNFeatures, max_width, max_height, max_batch, device)
+        self._h = C.c_void_p()
+        _check(lib().sslpl_line_create(C.byref(p), C.byref(self._h)))
+        self.cap = lsdNFeatures
+        self.max_batch = max_batch
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().sslpl_line_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def ExtractLineSegment(self, img, scale=1, numOctaves=1):
+        """-> (keylines, ldesc, keylineFunctions): ExtractLineSegment.cpp:18-69 (scale / numOctaves as the reference
+        passes them: int 1 and 1; other values are not supported)."""
+        assert int(scale) == 1 and numOctaves == 1
+        assert img.dtype == np.uint8 and img.ndim == 2
+        if img.strides[1] != 1:
+            img = np.ascontiguousarray(img)
+        kl = np.zeros(self.cap, KEYLINE_DTYPE); ld = np.zeros((self.cap, 32), np.uint8); eq = np.zeros((self.cap, 3), np.float64)
+        n = C.c_int()
+        _check(lib().sslpl_line_extract(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kl), _p(ld), _p(eq),
+                                        self.cap, C.byref(n)))
+        return kl[:n.value].copy(), ld[:n.value].copy(), eq[:n.value].copy()
+
+    def extract_batch(self, frames, out=None):
+        assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.strides[2] == 1
+        B, H, W = frames.shape
+        if out is None:
+            out = (np.zeros((B, self.cap), KEYLINE_DTYPE), np.zeros((B, self.cap, 32), np.uint8),
+                   np.zeros((B, self.cap, 3), np.float64), np.zeros(B, np.int32))
+        kl, ld, eq, n = out
+        _check(lib().sslpl_line_extract_batch(self._h, _p(frames), B, W, H, frames.strides[1], C.c_size_t(frames.strides[0]),
+                                              _p(kl), _p(ld), _p(eq), self.cap, _p(n)))
+        return kl, ld, eq, n
+
+    def extract_batch_device(self, d_ptr, nframes, width, height, pitch, frame_stride):
+        _check(lib().sslpl_line_extract_batch_device(self._h, C.c_void_p(d_ptr), nframes, width, height, pitch, C.c_size_t(frame_stride)))
+
+    def device_results(self):
+        kl = C.c_void_p(); ld = C.c_void_p(); eq = C.c_void_p(); n = C.c_void_p(); cap = C.c_int()
+        _check(lib().sslpl_line_device_results(self._h, C.byref(kl), C.byref(ld), C.byref(eq), C.byref(n), C.byref(cap)))
+        return kl.value, ld.value, eq.value, n.value, cap.value
+
+    def raw_segments(self, frame=0, cap=1 << 15):
+        seg = np.empty((cap, 4), np.float32); n = C.c_int()
+        _check(lib().sslpl_line_download_segments(self._h, frame, _p(seg), cap, C.byref(n)))
+        return seg[:min(n.value, cap)].copy()
+
+    def debug_trace(self, frame=0, cap=1 << 16):
+        out = np.empty((cap, 10), np.float64); n = C.c_int()
+        _check(lib().sslpl_line_debug_trace(self._h, frame, _p(out), cap, C.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
+    def sync(self):
+        _check(lib().sslpl_line_sync(self._h))
+
+    def set_stream(self, cuda_stream):
+        _check(lib().sslpl_line_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    @property
+    def launch_count(self):
+        return int(lib().sslpl_line_launch_count(self._h))

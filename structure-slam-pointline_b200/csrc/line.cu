@@ -1,0 +1,980 @@
+// line.cu — B200 (sm_100a) line path: LSD (OpenCV 4.13 LineSegmentDetector, LSD_REFINE_ADV) + KeyLine packaging +
+// LBD 256-bit descriptors + line equations.  Replaces LineSegment::ExtractLineSegment
+// (reference src/ExtractLineSegment.cpp:18-69, which delegates to cv::line_descriptor / cv::LineSegmentDetector).
+//
+// Per-pixel stages are ordinary data-parallel kernels (k_sep7, k_resize_exact, k_ll_angle, k_lsd_hist, k_sobel).
+// The region stage (k_lsd_regions) is order-dependent by definition (seeds in descending gradient bins, shared
+// `used` map, incrementally updated region angle): one warp walks one frame; the warp's lanes cooperate on neighbour
+// fetches and on the rectangle scans of rect_nfa, frames of a batch run on different SMs.  It is latency-bound,
+// not HBM-bound, and is reported separately.
+//
+// This file is compiled with -fmad=false: every float/double expression is evaluated as separate IEEE operations,
+// in the same order as the CPU restatement, so that discrete decisions (alignment tests, density, NFA) agree.
+#include "common.cuh"
+#include "mathx.cuh"
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+namespace sslpl {
+
+constexpr double L_PI = 3.14159265358979323846;
+constexpr double L_DEG = L_PI / 180;
+constexpr double L_3_2_PI = (3 * L_PI) / 2;
+constexpr double L_2PI = 2 * L_PI;
+constexpr float NOTDEF_F = -1024.f;
+constexpr int NBINS = 1024;
+constexpr int LT_W = 64, LT_H = 32;          // tile of the separable filter
+
+struct LineGeom {
+    int w, h, pitch;            // input frame (pitch of the staging / view)
+    int bpitch;                 // blurred planes (7-tap for LSD, 5-tap for LBD)
+    int sw, sh, spitch;         // LSD detection scale (0.8x)
+    int tiles_x, tiles_y;
+    int xtab_off, ytab_off;     // INTER_LINEAR_EXACT tables (int2: index, w1)
+    int seg_cap;                // raw segments per frame
+    int kl_cap;                 // lsdNFeatures
+    long long in_stride, blur_stride, scaled_stride, pix_stride /* sw*sh */, full_stride /* w*h */;
+    double rho, prec, p, log_nt;
+    int min_reg_size;
+    int trace_cap;              // rows of the debug trace per frame (0 = off)
+};
+
+struct LineWs {
+    uint8_t* blur7; uint8_t* blur5; uint8_t* scaled;
+    float* angdeg; float2* cs; double* modgrad; uint8_t* used;
+    unsigned long long* maxgrad; int* hist; unsigned* seeds; int* nseeds;
+    unsigned* reg;              // region pixel list (x | y << 16)
+    double* seg;                // raw rectangles: x1,y1,x2,y2 (detection scale, before +0.5)
+    int* nseg;
+    int16_t* dx; int16_t* dy;
+    int2* tab;
+    float* resp; float4* ext;   // per raw segment: response and clamped extremes
+    sslpl_keyline* kl; uint8_t* ldesc; double* lineeq; int* nl;
+    int* err;
+    double* trace; int* ntrace;
+};
+
+struct LView { const uint8_t* base; int pitch; long long frame_stride; };
+
+// -------------------------------------------------------------------------------------------------
+// Separable fixed-point filter (OpenCV 4.13 GaussianBlur 8U path): out = (sum_j k_j sum_i k_i p + 32768) >> 16
+// taps are passed as 7 ints (5-tap kernels are zero-padded), BORDER_REFLECT_101.
+// -------------------------------------------------------------------------------------------------
+struct Taps7 { int k[7]; };
+
+__global__ void __launch_bounds__(256) k_sep7(const __grid_constant__ LineGeom g, LView v, uint8_t* out, long long out_stride, Taps7 t) {
+    __shared__ uint8_t s_in[(LT_H + 6) * (LT_W + 8)];
+    __shared__ unsigned short s_row[(LT_H + 6) * LT_W];
+    const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x, x0 = tx * LT_W, y0 = ty * LT_H;
+    const uint8_t* img = v.base + f * v.frame_stride;
+    constexpr int IW = LT_W + 6, IP = LT_W + 8, IH = LT_H + 6;
+    for (int i = tid; i < IW * IH; i += 256) {
+        const int yy = i / IW, xx = i - yy * IW;
+        s_in[yy * IP + xx] = __ldg(img + (long long)reflect101(y0 + yy - 3, g.h) * v.pitch + reflect101(x0 + xx - 3, g.w));
+    }
+    __syncthreads();
+    for (int i = tid; i < IH * LT_W; i += 256) {
+        const int yy = i / LT_W, xx = i - yy * LT_W;
+        const uint8_t* p = &s_in[yy * IP + xx];
+        s_row[i] = (unsigned short)(t.k[0] * p[0] + t.k[1] * p[1] + t.k[2] * p[2] + t.k[3] * p[3] + t.k[4] * p[4] + t.k[5] * p[5] + t.k[6] * p[6]);
+    }
+    __syncthreads();
+    uint8_t* o = out + f * out_stride;
+    for (int i = tid; i < LT_H * (LT_W / 4); i += 256) {
+        const int yy = i / (LT_W / 4), x4 = (i - yy * (LT_W / 4)) * 4;
+        if (y0 + yy >= g.h || x0 + x4 >= g.w) continue;
+        uint32_t o4 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned short* p = &s_row[yy * LT_W + x4 + k];
+            const int s = t.k[0] * p[0] + t.k[1] * p[LT_W] + t.k[2] * p[2 * LT_W] + t.k[3] * p[3 * LT_W] + t.k[4] * p[4 * LT_W] + t.k[5] * p[5 * LT_W] + t.k[6] * p[6 * LT_W];
+            o4 |= (uint32_t)((s + 32768) >> 16) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(o + (long long)(y0 + yy) * g.bpitch + x0 + x4) = o4;
+    }
+}
+
+// cv::resize(INTER_LINEAR_EXACT) 8U, 8.8 fixed point (SURVEY.md A.6 iii): tables hold (i0, w1)
+__global__ void __launch_bounds__(256) k_resize_exact(const __grid_constant__ LineGeom g, LineWs ws) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    if (x >= g.sw || y >= g.sh) return;
+    const uint8_t* S = ws.blur7 + f * g.blur_stride;
+    const int2 tx = __ldg(&ws.tab[g.xtab_off + x]), ty = __ldg(&ws.tab[g.ytab_off + y]);
+    const int i0 = tx.x, i1 = min(i0 + 1, g.w - 1), w1 = tx.y, w0 = 256 - w1;
+    const uint8_t* S0 = S + (long long)ty.x * g.bpitch;
+    const uint8_t* S1 = S + (long long)min(ty.x + 1, g.h - 1) * g.bpitch;
+    const int r0 = w0 * __ldg(S0 + i0) + w1 * __ldg(S0 + i1), r1 = w0 * __ldg(S1 + i0) + w1 * __ldg(S1 + i1);
+    const int v1 = ty.y, v0 = 256 - v1;
+    ws.scaled[f * g.scaled_stride + (long long)y * g.spitch + x] = (uint8_t)((v0 * r0 + v1 * r1 + 32768) >> 16);
+}
+
+// ll_angle (lsd.cpp): 2x2 gradient, level-line angle, gradient norm, max over defined pixels
+__global__ void __launch_bounds__(256) k_ll_angle(const __grid_constant__ LineGeom g, LineWs ws) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    double norm = 0;
+    bool defined = false;
+    if (x < g.sw && y < g.sh) {
+        const long long pi = f * g.pix_stride + (long long)y * g.sw + x;
+        float ang = NOTDEF_F; float2 cs = make_float2(0.f, 0.f);
+        if (x < g.sw - 1 && y < g.sh - 1) {
+            const uint8_t* p = ws.scaled + f * g.scaled_stride + (long long)y * g.spitch + x;
+            const int DA = (int)p[g.spitch + 1] - (int)p[0], BC = (int)p[1] - (int)p[g.spitch];
+            const int gx = DA + BC, gy = DA - BC;
+            norm = sqrt((double)(gx * gx + gy * gy) / 4.0);
+            if (norm > g.rho) {
+                defined = true;
+                ang = fast_atan2_deg((float)gx, (float)-gy);
+                const float a = (float)((double)ang * L_DEG);
+                cs.x = (float)cos((double)a); cs.y = (float)sin((double)a);
+            }
+        }
+        ws.angdeg[pi] = ang; ws.cs[pi] = cs; ws.modgrad[pi] = norm; ws.used[pi] = 0;
+    }
+    unsigned long long bits = defined ? (unsigned long long)__double_as_longlong(norm) : 0ull;   // positive doubles order like integers
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, bits, o); bits = t > bits ? t : bits; }
+    if ((threadIdx.x & 31) == 0 && bits) atomicMax(ws.maxgrad + f, bits);
+}
+
+__device__ __forceinline__ int lsd_bin(double norm, double max_grad) {
+    const double bin_coef = (max_grad > 0) ? double(NBINS - 1) / max_grad : 0;
+    return (int)(norm * bin_coef);
+}
+
+// histogram of the gradient bins over defined pixels (pseudo-ordering of lsd.cpp)
+__global__ void __launch_bounds__(256) k_lsd_hist(const __grid_constant__ LineGeom g, LineWs ws) {
+    const long long i = blockIdx.x * 256ll + threadIdx.x; const int f = blockIdx.y;
+    if (i >= g.pix_stride) return;
+    if (ws.angdeg[f * g.pix_stride + i] == NOTDEF_F) return;
+    const double mg = __longlong_as_double((long long)ws.maxgrad[f]);
+    atomicAdd(&ws.hist[f * (NBINS + 1) + (NBINS - 1 - lsd_bin(ws.modgrad[f * g.pix_stride + i], mg))], 1);
+}
+
+// stable counting sort of the defined pixels: bins descending, raster order inside a bin.  One warp per frame.
+__global__ void __launch_bounds__(32) k_lsd_order(const __grid_constant__ LineGeom g, LineWs ws) {
+    __shared__ int s_off[NBINS + 1];
+    const int f = blockIdx.x, lane = threadIdx.x;
+    int* hist = ws.hist + f * (NBINS + 1);
+    int carry = 0;
+    for (int b0 = 0; b0 < NBINS; b0 += 32) {
+        const int v = hist[b0 + lane];
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        s_off[b0 + lane] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) ws.nseeds[f] = carry;
+    __syncwarp();
+    const double mg = __longlong_as_double((long long)ws.maxgrad[f]);
+    unsigned* seeds = ws.seeds + f * g.pix_stride;
+    const float* ang = ws.angdeg + f * g.pix_stride; const double* mod = ws.modgrad + f * g.pix_stride;
+    for (long long base = 0; base < g.pix_stride; base += 32) {
+        const long long i = base + lane;
+        const bool def = i < g.pix_stride && ang[i] != NOTDEF_F;
+        if (!__any_sync(0xffffffffu, def)) continue;
+        const int key = def ? (NBINS - 1 - lsd_bin(mod[i], mg)) : (2048 + lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1));
+        int off = 0;
+        if (def && lane == leader) { off = s_off[key]; s_off[key] = off + __popc(peers); }
+        off = __shfl_sync(0xffffffffu, off, leader);
+        if (def) seeds[off + rank] = (unsigned)i;
+        __syncwarp();
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// The sequential region walker.  All lanes run the same control flow on warp-uniform values; loads of 32
+// region points / 9 neighbours are spread over the lanes and broadcast with shuffles; lane 0 does the writes.
+// -------------------------------------------------------------------------------------------------
+struct LRect { double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p; };
+
+struct Walk {
+    int w, h; long long npix;
+    const float* ang; const float2* cs; const double* mod; uint8_t* used; unsigned* reg;
+    double log_nt;
+    int lane;
+};
+
+__device__ __forceinline__ bool l_aligned(float angdeg, double theta, double prec) {
+    if (angdeg == NOTDEF_F) return false;
+    const double a = (double)angdeg * L_DEG;
+    double n = theta - a;
+    if (n < 0) n = -n;
+    if (n > L_3_2_PI) { n -= L_2PI; if (n < 0) n = -n; }
+    return n <= prec;
+}
+
+__device__ int l_region_grow(const Walk& W, int sx, int sy, double prec, double& reg_angle) {
+    const int lane = W.lane;
+    if (lane == 0) { W.reg[0] = (unsigned)sx | ((unsigned)sy << 16); W.used[(long long)sy * W.w + sx] = 1; }
+    reg_angle = (double)W.ang[(long long)sy * W.w + sx] * L_DEG;
+    float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+    int n = 1;
+    __syncwarp();
+    for (int i = 0; i < n; i++) {
+        const unsigned pk = W.reg[i];
+        const int px = pk & 0xffff, py = pk >> 16;
+        // lanes 0..8 fetch the 3x3 neighbourhood (yy outer, xx inner — the scan order of lsd.cpp)
+        const int xx = px - 1 + lane % 3, yy = py - 1 + lane / 3;
+        const bool valid = lane < 9 && xx >= 0 && yy >= 0 && xx < W.w && yy < W.h;
+        uint8_t u = 1; float a = NOTDEF_F; float2 c = make_float2(0.f, 0.f);
+        if (valid) {
+            const long long q = (long long)yy * W.w + xx;
+            u = W.used[q]; a = W.ang[q]; c = W.cs[q];
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const int uk = __shfl_sync(0xffffffffu, (int)u, k);
+            const float ak = __shfl_sync(0xffffffffu, a, k);
+            const float cx = __shfl_sync(0xffffffffu, c.x, k), cy = __shfl_sync(0xffffffffu, c.y, k);
+            if (uk != 1 && l_aligned(ak, reg_angle, prec)) {
+                const int nx = px - 1 + k % 3, ny = py - 1 + k / 3;
+                if (lane == 0) { W.used[(long long)ny * W.w + nx] = 1; W.reg[n] = (unsigned)nx | ((unsigned)ny << 16); }
+                n++;
+                sumdx += cx; sumdy += cy;
+                reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * L_DEG;
+            }
+        }
+        __syncwarp();
+    }
+    return n;
+}
+
+__device__ __forceinline__ double l_angle_diff_signed(double a, double b) {
+    double d = a - b;
+    while (d <= -L_PI) d += L_2PI;
+    while (d > L_PI) d -= L_2PI;
+    return d;
+}
+
+// region2rect + get_theta (lsd.cpp): three sequential passes over the region in list order
+__device__ void l_region2rect(const Walk& W, int n, double reg_angle, double prec, double p, LRect& rec) {
+    const int lane = W.lane;
+    double x = 0, y = 0, sum = 0;
+    for (int b = 0; b < n; b += 32) {
+        const int i = b + lane;
+        int rx = 0, ry = 0; double wg = 0;
+        if (i < n) { const unsigned pk = W.reg[i]; rx = pk & 0xffff; ry = pk >> 16; wg = W.mod[(long long)ry * W.w + rx]; }
+        const int m = min(32, n - b);
+        for (int j = 0; j < m; j++) {
+            const double xj = (double)__shfl_sync(0xffffffffu, rx, j), yj = (double)__shfl_sync(0xffffffffu, ry, j);
+            const double wj = __shfl_sync(0xffffffffu, wg, j);
+            x += xj * wj; y += yj * wj; sum += wj;
+        }
+    }
+    x /= sum; y /= sum;
+    double Ixx = 0, Iyy = 0, Ixy = 0;
+    for (int b = 0; b < n; b += 32) {
+        const int i = b + lane;
+        int rx = 0, ry = 0; double wg = 0;
+        if (i < n) { const unsigned pk = W.reg[i]; rx = pk & 0xffff; ry = pk >> 16; wg = W.mod[(long long)ry * W.w + rx]; }
+        const int m = min(32, n - b);
+        for (int j = 0; j < m; j++) {
+            const double dx = (double)__shfl_sync(0xffffffffu, rx, j) - x, dy = (double)__shfl_sync(0xffffffffu, ry, j) - y;
+            const double wj = __shfl_sync(0xffffffffu, wg, j);
+            Ixx += dy * dy * wj; Iyy += dx * dx * wj; Ixy -= dx * dy * wj;
+        }
+    }
+    const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+    double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
+                                           : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
+    theta *= L_DEG;
+    if (fabs(l_angle_diff_signed(theta, reg_angle)) > prec) theta += L_PI;
+    const double dx = cos(theta), dy = sin(theta);
+    double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+    for (int b = 0; b < n; b += 32) {
+        const int i = b + lane;
+        int rx = 0, ry = 0;
+        if (i < n) { const unsigned pk = W.reg[i]; rx = pk & 0xffff; ry = pk >> 16; }
+        const int m = min(32, n - b);
+        for (int j = 0; j < m; j++) {
+            const double rdx = (double)__shfl_sync(0xffffffffu, rx, j) - x, rdy = (double)__shfl_sync(0xffffffffu, ry, j) - y;
+            const double l = rdx * dx + rdy * dy, ww = -rdx * dy + rdy * dx;
+            if (l > l_max) l_max = l; else if (l < l_min) l_min = l;
+            if (ww > w_max) w_max = ww; else if (ww < w_min) w_min = ww;
+        }
+    }
+    rec.x1 = x + l_min * dx; rec.y1 = y + l_min * dy; rec.x2 = x + l_max * dx; rec.y2 = y + l_max * dy;
+    rec.width = w_max - w_min; rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx; rec.dy = dy; rec.prec = prec; rec.p = p;
+    if (rec.width < 1.0) rec.width = 1.0;
+}
+
+__device__ __forceinline__ double l_dist(double x1, double y1, double x2, double y2) { return sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1)); }
+__device__ __forceinline__ double l_distsq(double x1, double y1, double x2, double y2) { return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1); }
+
+__device__ bool l_reduce_region_radius(const Walk& W, int& n, double reg_angle, double prec, double p, LRect& rec, double density, double density_th) {
+    const unsigned p0 = W.reg[0];
+    const double xc = (double)(p0 & 0xffff), yc = (double)(p0 >> 16);
+    double radSq = fmax(l_distsq(xc, yc, rec.x1, rec.y1), l_distsq(xc, yc, rec.x2, rec.y2));
+    while (density < density_th) {
+        radSq *= 0.75 * 0.75;
+        // swap-with-last removal, sequential semantics (lane 0 does it; the list is short-lived)
+        if (W.lane == 0) {
+            int m = n;
+            for (int i = 0; i < m; i++) {
+                const unsigned pk = W.reg[i];
+                if (l_distsq(xc, yc, (double)(pk & 0xffff), (double)(pk >> 16)) > radSq) {
+                    W.used[(long long)(pk >> 16) * W.w + (pk & 0xffff)] = 0;
+                    const unsigned last = W.reg[m - 1];
+                    W.reg[i] = last; W.reg[m - 1] = pk;
+                    m--; i--;
+                }
+            }
+            n = m;
+        }
+        n = __shfl_sync(0xffffffffu, n, 0);
+        __syncwarp();
+        if (n < 2) return false;
+        l_region2rect(W, n, reg_angle, prec, p, rec);
+        density = (double)n / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+    }
+    return true;
+}
+
+__device__ bool l_refine(const Walk& W, int& n, double& reg_angle, double prec, double p, LRect& rec, double density_th) {
+    double density = (double)n / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+    if (density >= density_th) return true;
+    const unsigned p0 = W.reg[0];
+    const int sx = p0 & 0xffff, sy = p0 >> 16;
+    const double xc = (double)sx, yc = (double)sy;
+    const double ang_c = (double)W.ang[(long long)sy * W.w + sx] * L_DEG;
+    double sum = 0, s_sum = 0; int cnt = 0;
+    for (int b = 0; b < n; b += 32) {
+        const int i = b + W.lane;
+        int rx = 0, ry = 0; float ad = 0;
+        if (i < n) { const unsigned pk = W.reg[i]; rx = pk & 0xffff; ry = pk >> 16; ad = W.ang[(long long)ry * W.w + rx]; W.used[(long long)ry * W.w + rx] = 0; }
+        const int m = min(32, n - b);
+        for (int j = 0; j < m; j++) {
+            const double xj = (double)__shfl_sync(0xffffffffu, rx, j), yj = (double)__shfl_sync(0xffffffffu, ry, j);
+            const float aj = __shfl_sync(0xffffffffu, ad, j);
+            if (l_dist(xc, yc, xj, yj) < rec.width) {
+                const double d = l_angle_diff_signed((double)aj * L_DEG, ang_c);
+                sum += d; s_sum += d * d; ++cnt;
+            }
+        }
+    }
+    __syncwarp();
+    const double mean_angle = sum / (double)cnt;
+    const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
+    n = l_region_grow(W, sx, sy, tau, reg_angle);
+    if (n < 2) return false;
+    l_region2rect(W, n, reg_angle, prec, p, rec);
+    density = (double)n / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+    if (density < density_th) return l_reduce_region_radius(W, n, reg_angle, prec, p, rec, density, density_th);
+    return true;
+}
+
+__device__ double l_log_gamma(double x) {
+    if (x > 15.0) return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
+    const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
+    double a = (x + 0.5) * log(x + 5.5) - (x + 5.5), b = 0;
+    for (int n = 0; n < 7; ++n) { a -= log(x + (double)n); b += q[n] * pow(x, (double)n); }
+    return a + log(b);
+}
+
+__device__ double l_nfa(int n, int k, double p, double LOG_NT) {
+    if (n == 0 || k == 0) return -LOG_NT;
+    if (n == k) return -LOG_NT - (double)n * log10(p);
+    const double p_term = p / (1 - p);
+    const double log1term = l_log_gamma((double)n + 1) - l_log_gamma((double)k + 1) - l_log_gamma((double)(n - k) + 1) +
+                            (double)k * log(p) + (double)(n - k) * log(1.0 - p);
+    double term = exp(log1term);
+    {   // double_equal(term, 0)
+        bool eq = term == 0.0;
+        if (!eq) { double abs_max = fabs(term); if (abs_max < 2.2250738585072014e-308) abs_max = 2.2250738585072014e-308; eq = (fabs(term) / abs_max) <= (100.0 * 2.220446049250313e-16); }
+        if (eq) {
+            if ((double)k > (double)n * p) return -log1term / 2.30258509299404568402 - LOG_NT;
+            return -LOG_NT;
+        }
+    }
+    double bin_tail = term;
+    for (int i = k + 1; i <= n; i++) {
+        const double bin_term = (double)(n - i + 1) / (double)i;
+        const double mult_term = bin_term * p_term;
+        term *= mult_term;
+        bin_tail += term;
+        if (bin_term < 1) {
+            const double err = term * ((1 - pow(mult_term, (double)(n - i + 1))) / (1 - mult_term) - 1);
+            if (err < 0.1 * fabs(-log10(bin_tail) - LOG_NT) * bin_tail) break;
+        }
+    }
+    return -log10(bin_tail) - LOG_NT;
+}
+
+__device__ __forceinline__ int l_x86_d2i(double v) {                 // cvttsd2si semantics
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return INT_MIN;
+    return (int)v;
+}
+
+// rect_nfa of OpenCV 4.13 (see oracle/line_oracle.cpp): rows are distributed over the lanes (or, for flat
+// rectangles, the pixels of a row); the two counts are exact integers, so the reduction order is irrelevant.
+__device__ double l_rect_nfa(const Walk& W, const LRect& rec) {
+    const double half_width = 0.5 * rec.width, dyhw = rec.dy * half_width, dxhw = rec.dx * half_width;
+    const double vx[4] = {rec.x1 - dyhw, rec.x2 - dyhw, rec.x2 + dyhw, rec.x1 + dyhw};
+    const double vy[4] = {rec.y1 + dxhw, rec.y2 + dxhw, rec.y2 - dxhw, rec.y1 - dxhw};
+    int off = 0;
+#pragma unroll
+    for (int i = 1; i < 4; i++) if (vy[i] < vy[off] || (vy[i] == vy[off] && vx[i] < vx[off])) off = i;
+    const double Mx = vx[off], My = vy[off], Ax = vx[(off + 1) & 3], Ay = vy[(off + 1) & 3];
+    const double Bx = vx[(off + 2) & 3], By = vy[(off + 2) & 3], Cx = vx[(off + 3) & 3], Cy = vy[(off + 3) & 3];
+    const int cM = l_x86_d2i(ceil(My)), cA = l_x86_d2i(ceil(Ay)), cB = l_x86_d2i(ceil(By)), cC = l_x86_d2i(ceil(Cy));
+    const double s1 = (cA != cM) ? (Ax - Mx) / (Ay - My) : 0.0;
+    const double s2 = (cB != cA) ? (Bx - Ax) / (By - Ay) : 0.0;
+    const double s3 = (cC != cM) ? (Cx - Mx) / (Cy - My) : 0.0;
+    const double s4 = (cB != cC) ? (Bx - Cx) / (By - Cy) : 0.0;
+    int total = 0, alg = 0;
+    const int y0 = max(cM, 0), y1 = min(cB, W.h - 1);
+    const bool by_rows = (y1 - y0) >= 16;
+    for (int yb = y0; yb <= y1; yb += by_rows ? 32 : 1) {
+        const int y = by_rows ? yb + W.lane : yb;
+        if (y > y1) continue;
+        const double xl = (cA < y) ? ((double)y - Ay) * s2 + Ax : ((double)y - My) * s1 + Mx;
+        const double xr = (cC <= y) ? ((double)y - Cy) * s4 + Cx : ((double)y - My) * s3 + Mx;
+        int xs = l_x86_d2i(ceil(xl));
+        int xe = l_x86_d2i(xr);
+        if (xe < xs) continue;
+        if (xs < 0) xs = 0;
+        if (xe > W.w - 1) xe = W.w - 1;
+        const float* row = W.ang + (long long)y * W.w;
+        if (by_rows) {
+            for (int x = xs; x <= xe; ++x) { ++total; if (l_aligned(row[x], rec.theta, rec.prec)) ++alg; }
+        } else {
+            for (int x = xs + W.lane; x <= xe; x += 32) { ++total; if (l_aligned(row[x], rec.theta, rec.prec)) ++alg; }
+        }
+    }
+    total = __reduce_add_sync(0xffffffffu, total);
+    alg = __reduce_add_sync(0xffffffffu, alg);
+    return l_nfa(total, alg, rec.p, W.log_nt);
+}
+
+__device__ double l_rect_improve(const Walk& W, LRect& rec) {
+    const double delta = 0.5, delta_2 = delta / 2.0;
+    double log_nfa = l_rect_nfa(W, rec);
+    if (log_nfa > 0.0) return log_nfa;
+    LRect r = rec;
+    for (int n = 0; n < 5; ++n) {
+        r.p /= 2; r.prec = r.p * L_PI;
+        const double v = l_rect_nfa(W, r);
+        if (v > log_nfa) { log_nfa = v; rec = r; }
+    }
+    if (log_nfa > 0.0) return log_nfa;
+    r = rec;
+    for (int n = 0; n < 5; ++n)
+        if ((r.width - delta) >= 0.5) {
+            r.width -= delta;
+            const double v = l_rect_nfa(W, r);
+            if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+    if (log_nfa > 0.0) return log_nfa;
+    r = rec;
+    for (int n = 0; n < 5; ++n)
+        if ((r.width - delta) >= 0.5) {
+            r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2; r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2; r.width -= delta;
+            const double v = l_rect_nfa(W, r);
+            if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+    if (log_nfa > 0.0) return log_nfa;
+    r = rec;
+    for (int n = 0; n < 5; ++n)
+        if ((r.width - delta) >= 0.5) {
+            r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2; r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2; r.width -= delta;
+            const double v = l_rect_nfa(W, r);
+            if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+    if (log_nfa > 0.0) return log_nfa;
+    r = rec;
+    for (int n = 0; n < 5; ++n)
+        if ((r.width - delta) >= 0.5) {
+            r.p /= 2; r.prec = r.p * L_PI;
+            const double v = l_rect_nfa(W, r);
+            if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+    return log_nfa;
+}
+
+__global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ LineGeom g, LineWs ws) {
+    const int f = blockIdx.x;
+    Walk W;
+    W.w = g.sw; W.h = g.sh; W.npix = g.pix_stride; W.lane = threadIdx.x;
+    W.ang = ws.angdeg + f * g.pix_stride; W.cs = ws.cs + f * g.pix_stride; W.mod = ws.modgrad + f * g.pix_stride;
+    W.used = ws.used + f * g.pix_stride; W.reg = ws.reg + f * g.pix_stride; W.log_nt = g.log_nt;
+    const unsigned* seeds = ws.seeds + f * g.pix_stride;
+    const int ns = ws.nseeds[f];
+    double* seg = ws.seg + (long long)f * g.seg_cap * 4;
+    int nout = 0, ntr = 0;
+    for (int s = 0; s < ns; s++) {
+        const unsigned idx = seeds[s];
+        if (W.used[idx] != 0) continue;                     // angle != NOTDEF holds for every seed
+        double reg_angle;
+        int n = l_region_grow(W, (int)(idx % (unsigned)W.w), (int)(idx / (unsigned)W.w), g.prec, reg_angle);
+        if (n < g.min_reg_size) continue;
+        LRect rec;
+        l_region2rect(W, n, reg_angle, g.prec, g.p, rec);
+        const int n0 = n;
+        const bool okr = l_refine(W, n, reg_angle, g.prec, g.p, rec, 0.7);
+        const double log_nfa = okr ? l_rect_improve(W, rec) : -1e9;
+        if (g.trace_cap) {
+            if (W.lane == 0 && ntr < g.trace_cap) {
+                double* t = ws.trace + ((long long)f * g.trace_cap + ntr) * 10;
+                t[0] = (double)idx; t[1] = (double)n0; t[2] = (double)n; t[3] = log_nfa;
+                t[4] = okr ? rec.x1 : 0; t[5] = okr ? rec.y1 : 0; t[6] = okr ? rec.x2 : 0; t[7] = okr ? rec.y2 : 0; t[8] = okr ? rec.width : 0; t[9] = okr ? rec.p : 0;
+            }
+            ntr++;
+        }
+        if (!okr) continue;
+        if (log_nfa <= 0.0) continue;
+        if (nout < g.seg_cap && W.lane == 0) { seg[4 * nout] = rec.x1; seg[4 * nout + 1] = rec.y1; seg[4 * nout + 2] = rec.x2; seg[4 * nout + 3] = rec.y2; }
+        nout++;
+    }
+    if (W.lane == 0 && g.trace_cap) ws.ntrace[f] = min(ntr, g.trace_cap);
+    if (W.lane == 0) { ws.nseg[f] = min(nout, g.seg_cap); if (nout > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
+}
+
+// -------------------------------------------------------------------------------------------------
+// KeyLine packaging (line_descriptor LSDDetector::detectImpl), top-N by response (ExtractLineSegment.cpp:45-51),
+// line equations (:56-68).  One CTA per frame.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_keylines(const __grid_constant__ LineGeom g, LineWs ws) {
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n = ws.nseg[f];
+    const double* seg = ws.seg + (long long)f * g.seg_cap * 4;
+    float* resp = ws.resp + (long long)f * g.seg_cap;
+    float4* ext = ws.ext + (long long)f * g.seg_cap;
+    const double SCALE = 0.8;
+    for (int i = tid; i < n; i += 256) {
+        float e[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            double v = seg[4 * i + k] + 0.5;
+            v /= SCALE;
+            float fv = (float)v;
+            const int lim = (k & 1) ? g.h : g.w;                       // checkLineExtremes
+            if (fv < 0) fv = 0;
+            if (fv >= (float)lim) fv = (float)lim - 1.0f;
+            e[k] = fv;
+        }
+        ext[i] = make_float4(e[0], e[1], e[2], e[3]);
+        const float ddx = e[0] - e[2], ddy = e[1] - e[3];
+        const float len = (float)sqrt((double)ddx * (double)ddx + (double)ddy * (double)ddy);
+        resp[i] = len / (float)max(g.w, g.h);
+    }
+    __syncthreads();
+    const int keep = min(n, g.kl_cap);
+    sslpl_keyline* KL = ws.kl + (long long)f * g.kl_cap;
+    double* EQ = ws.lineeq + (long long)f * g.kl_cap * 3;
+    for (int i = tid; i < n; i += 256) {
+        int pos = i;
+        if (n > g.kl_cap) {                       // stable rank by descending response
+            const float r = resp[i];
+            int rank = 0;
+            for (int j = 0; j < n; j++) { const float rj = resp[j]; rank += (rj > r) || (rj == r && j < i); }
+            pos = rank;
+        }
+        if (pos >= keep) continue;
+        const float4 e = ext[i];
+        sslpl_keyline k;
+        k.startPointX = e.x; k.startPointY = e.y; k.endPointX = e.z; k.endPointY = e.w;
+        k.sPointInOctaveX = e.x; k.sPointInOctaveY = e.y; k.ePointInOctaveX = e.z; k.ePointInOctaveY = e.w;
+        const float ddx = e.x - e.z, ddy = e.y - e.w;
+        k.lineLength = (float)sqrt((double)ddx * (double)ddx + (double)ddy * (double)ddy);
+        const int ax = __float2int_rn(e.x), ay = __float2int_rn(e.y), bx = __float2int_rn(e.z), by = __float2int_rn(e.w);
+        k.numOfPixels = max(abs(bx - ax), abs(by - ay)) + 1;          // cv::LineIterator(8-connected).count
+        k.angle = (float)atan2((double)(e.w - e.y), (double)(e.z - e.x));
+        k.class_id = pos; k.octave = 0;
+        k.size = (e.z - e.x) * (e.w - e.y);
+        k.response = resp[i];
+        k.pt_x = (e.z + e.x) / 2; k.pt_y = (e.w + e.y) / 2;
+        KL[pos] = k;
+        const double sx = e.x, sy = e.y, ex = e.z, ey = e.w;
+        const double l0 = sy * 1.0 - 1.0 * ey, l1 = 1.0 * ex - sx * 1.0, l2 = sx * ey - sy * ex;
+        const double nrm = sqrt(l0 * l0 + l1 * l1);
+        EQ[3 * pos] = l0 / nrm; EQ[3 * pos + 1] = l1 / nrm; EQ[3 * pos + 2] = l2 / nrm;
+    }
+    if (tid == 0) ws.nl[f] = keep;
+}
+
+// Sobel 3x3 -> s16 (dx, dy) with BORDER_REFLECT_101 on the 5-tap blurred image
+__global__ void __launch_bounds__(256) k_sobel(const __grid_constant__ LineGeom g, LineWs ws) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    if (x >= g.w || y >= g.h) return;
+    const uint8_t* img = ws.blur5 + f * g.blur_stride;
+    const uint8_t* r0 = img + (long long)reflect101(y - 1, g.h) * g.bpitch;
+    const uint8_t* r1 = img + (long long)y * g.bpitch;
+    const uint8_t* r2 = img + (long long)reflect101(y + 1, g.h) * g.bpitch;
+    const int xm = reflect101(x - 1, g.w), xp = reflect101(x + 1, g.w);
+    const long long o = f * g.full_stride + (long long)y * g.w + x;
+    ws.dx[o] = (int16_t)(((int)r0[xp] - (int)r0[xm]) + 2 * ((int)r1[xp] - (int)r1[xm]) + ((int)r2[xp] - (int)r2[xm]));
+    ws.dy[o] = (int16_t)(((int)r2[xm] - (int)r0[xm]) + 2 * ((int)r2[x] - (int)r0[x]) + ((int)r2[xp] - (int)r0[xp]));
+}
+
+// LBD (BinaryDescriptor::computeLBD, binary_descriptor.cpp) — one CTA (64 threads) per line: thread h walks row h
+// of the 63-row line support region sequentially (float sums keep the reference's order), thread 0 folds the rows
+// into the 9 bands in row order, then builds the 72-float vector and the 32 pair-comparison bytes.
+struct LbdCoef { float G[63]; float L[21]; };
+__constant__ int c_comb[32][2] = {{0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {0, 6}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 7},
+                                  {2, 8}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {3, 8}, {4, 5}, {4, 6}, {4, 7}, {4, 8}, {5, 6}, {5, 7}, {5, 8}, {6, 7}, {6, 8}, {7, 8}};
+
+__global__ void __launch_bounds__(64) k_lbd(const __grid_constant__ LineGeom g, LineWs ws, const __grid_constant__ LbdCoef C) {
+    __shared__ float s_row[63][8];
+    __shared__ float s_des[72];
+    const int li = blockIdx.x, f = blockIdx.y, h = threadIdx.x;
+    if (li >= ws.nl[f]) return;
+    const sslpl_keyline kl = ws.kl[(long long)f * g.kl_cap + li];
+    const int16_t* dxI = ws.dx + f * g.full_stride; const int16_t* dyI = ws.dy + f * g.full_stride;
+    const short imageWidth = (short)(g.w - 1), imageHeight = (short)(g.h - 1);
+    const short lengthOfLSP = (short)kl.numOfPixels, halfWidth = (short)((lengthOfLSP - 1) / 2), halfHeight = 31;
+    const float mx = (float)(0.5 * (double)(kl.sPointInOctaveX + kl.ePointInOctaveX));
+    const float my = (float)(0.5 * (double)(kl.sPointInOctaveY + kl.ePointInOctaveY));
+    const float dL0 = (float)cos((double)kl.angle), dL1 = (float)sin((double)kl.angle);
+    const float dO0 = -dL1, dO1 = dL0;
+    if (h < 63) {
+        // sCorX0 after h steps of (sCorX0 -= dL[1]; sCorY0 += dL[0]) — replay the float recurrence exactly
+        float sx0 = -dL0 * halfWidth + dL1 * halfHeight + mx;
+        float sy0 = -dL1 * halfWidth - dL0 * halfHeight + my;
+        for (int k = 0; k < h; k++) { sx0 -= dL1; sy0 += dL0; }
+        float sx = sx0, sy = sy0, pL = 0, nL = 0, pO = 0, nO = 0;
+        for (short wID = 0; wID < lengthOfLSP; wID++) {
+            short t = (short)roundf(sx);
+            const short xc = (t < 0) ? 0 : (t > imageWidth) ? imageWidth : t;
+            t = (short)roundf(sy);
+            const short yc = (t < 0) ? 0 : (t > imageHeight) ? imageHeight : t;
+            const short dx = dxI[(int)yc * g.w + xc], dy = dyI[(int)yc * g.w + xc];
+            const float gDL = dx * dL0 + dy * dL1, gDO = dx * dO0 + dy * dO1;
+            if (gDL > 0) pL += gDL; else nL -= gDL;
+            if (gDO > 0) pO += gDO; else nO -= gDO;
+            sx += dL0; sy += dL1;
+        }
+        const float cg = C.G[h];
+        pL = cg * pL; nL = cg * nL; pO = cg * pO; nO = cg * nO;
+        s_row[h][0] = pL; s_row[h][1] = nL; s_row[h][2] = pL * pL; s_row[h][3] = nL * nL;
+        s_row[h][4] = pO; s_row[h][5] = nO; s_row[h][6] = pO * pO; s_row[h][7] = nO * nO;
+    }
+    __syncthreads();
+    if (h < 8) {      // thread q accumulates quantity q of every band, rows in order (same add order as the reference)
+        float band[9];
+#pragma unroll
+        for (int b = 0; b < 9; b++) band[b] = 0;
+        const bool sq = (h & 2) != 0;           // quantities 2,3,6,7 use squared local weights
+        for (int r = 0; r < 63; r++) {
+            const float v = s_row[r][h];
+            int b = r / 7;
+            float c = C.L[r % 7 + 7];
+            band[b] += (sq ? c * c : c) * v;
+            b--;
+            if (b >= 0) { c = C.L[r % 7 + 14]; band[b] += (sq ? c * c : c) * v; }
+            b += 2;
+            if (b < 9) { c = C.L[r % 7]; band[b] += (sq ? c * c : c) * v; }
+        }
+        for (int b = 0; b < 9; b++) s_row[b][h] = band[b];      // reuse rows 0..8 as band sums (all reads are done: see sync)
+    }
+    __syncthreads();
+    if (h == 0) {
+        const float invN2 = (float)(1.0 / (7 * 2.0)), invN3 = (float)(1.0 / (7 * 3.0));
+        float* d = s_des;
+        for (int b = 0; b < 9; b++) {
+            const float invN = (b == 0 || b == 8) ? invN2 : invN3;
+            float t = s_row[b][0] * invN; d[8 * b] = t; d[8 * b + 4] = sqrtf(s_row[b][2] * invN - t * t);
+            t = s_row[b][1] * invN; d[8 * b + 1] = t; d[8 * b + 5] = sqrtf(s_row[b][3] * invN - t * t);
+            t = s_row[b][4] * invN; d[8 * b + 2] = t; d[8 * b + 6] = sqrtf(s_row[b][6] * invN - t * t);
+            t = s_row[b][5] * invN; d[8 * b + 3] = t; d[8 * b + 7] = sqrtf(s_row[b][7] * invN - t * t);
+        }
+        float tM = 0, tS = 0;
+        for (int b = 0; b < 9; b++) {
+            for (int i = 0; i < 4; i++) tM += d[8 * b + i] * d[8 * b + i];
+            for (int i = 4; i < 8; i++) tS += d[8 * b + i] * d[8 * b + i];
+        }
+        tM = 1 / sqrtf(tM); tS = 1 / sqrtf(tS);
+        for (int b = 0; b < 9; b++) {
+            for (int i = 0; i < 4; i++) d[8 * b + i] = d[8 * b + i] * tM;
+            for (int i = 4; i < 8; i++) d[8 * b + i] = d[8 * b + i] * tS;
+        }
+        for (int i = 0; i < 72; i++) if ((double)d[i] > 0.4) d[i] = (float)0.4;
+        float t = 0;
+        for (int i = 0; i < 72; i++) t += d[i] * d[i];
+        t = 1 / sqrtf(t);
+        for (int i = 0; i < 72; i++) d[i] = d[i] * t;
+    }
+    __syncthreads();
+    if (h < 32) {
+        const float* f1 = &s_des[8 * c_comb[h][0]]; const float* f2 = &s_des[8 * c_comb[h][1]];
+        unsigned r = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (f1[i] > f2[i]) r += 0x80u >> i;
+        // 32 bytes -> two coalesced 16-byte stores
+        uint32_t w = r << (8 * (h & 3));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        const uint32_t w0 = __shfl_sync(0xffffffffu, w, (h & 16) + 0), w1 = __shfl_sync(0xffffffffu, w, (h & 16) + 4),
+                       w2 = __shfl_sync(0xffffffffu, w, (h & 16) + 8), w3 = __shfl_sync(0xffffffffu, w, (h & 16) + 12);
+        if ((h & 15) == 0) reinterpret_cast<uint4*>(ws.ldesc + ((long long)f * g.kl_cap + li) * 32)[h >> 4] = make_uint4(w0, w1, w2, w3);
+    }
+}
+
+}  // namespace sslpl
+
+// =================================================================================================
+using namespace sslpl;
+
+struct sslpl_line {
+    sslpl_line_params p;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    uint8_t* arena = nullptr; size_t arena_size = 0;
+    LineGeom g; LineWs ws; LView view;
+    uint8_t* d_input = nullptr;
+    LbdCoef coef;
+    bool trace = false;
+    int cur_w = 0, cur_h = 0, cur_frames = 0;
+    long long launches = 0;
+    int* h_err = nullptr;
+};
+
+namespace {
+
+void make_geometry(const sslpl_line* h, int W, int H, LineGeom& g, std::vector<int2>* tab) {
+    memset(&g, 0, sizeof(g));
+    g.w = W; g.h = H; g.pitch = (int)align_up(W, 16);
+    g.bpitch = (int)align_up(W, 64);
+    g.sw = (int)lrint(W * 0.8); g.sh = (int)lrint(H * 0.8); g.spitch = (int)align_up(g.sw, 64);
+    g.tiles_x = (W + LT_W - 1) / LT_W; g.tiles_y = (H + LT_H - 1) / LT_H;
+    g.xtab_off = 0; g.ytab_off = g.sw;
+    g.in_stride = (long long)g.pitch * H;
+    g.blur_stride = (long long)align_up((size_t)g.bpitch * H, 256);
+    g.scaled_stride = (long long)align_up((size_t)g.spitch * g.sh, 256);
+    g.pix_stride = (long long)g.sw * g.sh;
+    g.full_stride = (long long)W * H;
+    g.kl_cap = h->p.lsdNFeatures;
+    // lsd.cpp constants (ANG_TH 22.5, QUANT 2.0); host libm, exactly as the CPU implementation evaluates them
+    g.prec = L_PI * 22.5 / 180; g.p = 22.5 / 180; g.rho = 2.0 / std::sin(g.prec);
+    g.log_nt = 5 * (std::log10(double(g.sw)) + std::log10(double(g.sh))) / 2 + std::log10(11.0);
+    g.min_reg_size = (int)size_t(-g.log_nt / std::log10(g.p));
+    g.seg_cap = (int)(g.pix_stride / std::max(g.min_reg_size, 1)) + 16;
+    g.trace_cap = h->trace ? g.seg_cap : 0;
+    if (tab) {
+        tab->assign(g.sw + g.sh, make_int2(0, 0));
+        for (int axis = 0; axis < 2; axis++) {
+            const int dn = axis ? g.sh : g.sw, sn = axis ? H : W, off = axis ? g.ytab_off : g.xtab_off;
+            const double sc = (double)sn / dn;
+            for (int d = 0; d < dn; d++) {
+                double s = (d + 0.5) * sc - 0.5;
+                int i0 = (int)floor(s);
+                double f = s - i0;
+                if (i0 < 0) { i0 = 0; f = 0; }
+                if (i0 >= sn - 1) { i0 = sn - 1; f = 0; }
+                (*tab)[off + d] = make_int2(i0, (int)lrint(f * 256));
+            }
+        }
+    }
+}
+
+void carve(sslpl_line* h, Arena& A, const LineGeom& g, int B) {
+    LineWs& ws = h->ws;
+    h->d_input = A.take<uint8_t>((size_t)B * g.in_stride + 256);
+    ws.blur7 = A.take<uint8_t>((size_t)B * g.blur_stride); ws.blur5 = A.take<uint8_t>((size_t)B * g.blur_stride);
+    ws.scaled = A.take<uint8_t>((size_t)B * g.scaled_stride);
+    ws.angdeg = A.take<float>((size_t)B * g.pix_stride); ws.cs = A.take<float2>((size_t)B * g.pix_stride);
+    ws.modgrad = A.take<double>((size_t)B * g.pix_stride); ws.used = A.take<uint8_t>((size_t)B * g.pix_stride);
+    ws.maxgrad = A.take<unsigned long long>(B); ws.hist = A.take<int>((size_t)B * (NBINS + 1));
+    ws.seeds = A.take<unsigned>((size_t)B * g.pix_stride); ws.nseeds = A.take<int>(B);
+    ws.reg = A.take<unsigned>((size_t)B * g.pix_stride);
+    ws.seg = A.take<double>((size_t)B * g.seg_cap * 4); ws.nseg = A.take<int>(B);
+    ws.dx = A.take<int16_t>((size_t)B * g.full_stride); ws.dy = A.take<int16_t>((size_t)B * g.full_stride);
+    ws.tab = A.take<int2>(g.sw + g.sh);
+    ws.resp = A.take<float>((size_t)B * g.seg_cap); ws.ext = A.take<float4>((size_t)B * g.seg_cap);
+    ws.kl = A.take<sslpl_keyline>((size_t)B * g.kl_cap); ws.ldesc = A.take<uint8_t>((size_t)B * g.kl_cap * 32);
+    ws.lineeq = A.take<double>((size_t)B * g.kl_cap * 3); ws.nl = A.take<int>(B);
+    ws.err = A.take<int>(1);
+    ws.trace = A.take<double>((size_t)B * g.trace_cap * 10 + 16); ws.ntrace = A.take<int>(B);
+}
+
+int configure(sslpl_line* h, int W, int H) {
+    if (W == h->cur_w && H == h->cur_h) return SSLPL_OK;
+    SSLPL_REQUIRE(W <= h->p.max_width && H <= h->p.max_height, SSLPL_ERR_ARG, "frame larger than the handle's max_width/max_height");
+    SSLPL_REQUIRE(W >= 16 && H >= 16 && W < 32768 && H < 32768, SSLPL_ERR_ARG, "frame size out of range");
+    std::vector<int2> tab;
+    make_geometry(h, W, H, h->g, &tab);
+    Arena A; A.base = h->arena; A.size = h->arena_size;
+    carve(h, A, h->g, h->p.max_batch);
+    SSLPL_REQUIRE(A.used <= h->arena_size, SSLPL_ERR_CAPACITY, "internal: arena too small for this frame size");
+    SSLPL_CUDA(cudaStreamSynchronize(h->stream));
+    SSLPL_CUDA(cudaMemcpy(h->ws.tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    SSLPL_CUDA(cudaMemset(h->ws.err, 0, sizeof(int)));
+    h->cur_w = W; h->cur_h = H;
+    return SSLPL_OK;
+}
+
+int run_pipeline(sslpl_line* h, int B) {
+    const LineGeom& g = h->g;
+    cudaStream_t st = h->stream;
+    const Taps7 t7 = {{0, 4, 56, 136, 56, 4, 0}};       // GaussianBlur(sigma 0.6/0.8) of lsd.cpp, 4.13 fixed point
+    const Taps7 t5 = {{0, 14, 62, 104, 62, 14, 0}};     // GaussianBlur(5x5, sigma 1) of BinaryDescriptor
+    const dim3 tiles(g.tiles_x * g.tiles_y, B);
+    k_sep7<<<tiles, 256, 0, st>>>(g, h->view, h->ws.blur7, g.blur_stride, t7);
+    k_sep7<<<tiles, 256, 0, st>>>(g, h->view, h->ws.blur5, g.blur_stride, t5);
+    k_resize_exact<<<dim3((g.sw + 31) / 32, (g.sh + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
+    SSLPL_CUDA(cudaMemsetAsync(h->ws.maxgrad, 0, sizeof(unsigned long long) * B, st));
+    SSLPL_CUDA(cudaMemsetAsync(h->ws.hist, 0, sizeof(int) * (size_t)B * (NBINS + 1), st));
+    k_ll_angle<<<dim3((g.sw + 31) / 32, (g.sh + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
+    k_lsd_hist<<<dim3((unsigned)((g.pix_stride + 255) / 256), B), 256, 0, st>>>(g, h->ws);
+    k_lsd_order<<<B, 32, 0, st>>>(g, h->ws);
+    k_lsd_regions<<<B, 32, 0, st>>>(g, h->ws);
+    k_keylines<<<B, 256, 0, st>>>(g, h->ws);
+    k_sobel<<<dim3((g.w + 31) / 32, (g.h + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
+    k_lbd<<<dim3(g.kl_cap, B), 64, 0, st>>>(g, h->ws, h->coef);
+    h->launches += 10;
+    SSLPL_CUDA(cudaGetLastError());
+    return SSLPL_OK;
+}
+
+int check_device_err(sslpl_line* h) {
+    SSLPL_CUDA(cudaMemcpyAsync(h->h_err, h->ws.err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    SSLPL_CUDA(cudaStreamSynchronize(h->stream));
+    if (*h->h_err) {
+        set_error("device-side capacity overflow in the line path, flags=0x%x", *h->h_err);
+        cudaMemsetAsync(h->ws.err, 0, sizeof(int), h->stream);
+        return SSLPL_ERR_CAPACITY;
+    }
+    return SSLPL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sslpl_line_create(const sslpl_line_params* p, sslpl_line** out) {
+    SSLPL_REQUIRE(p && out, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(p->lsdNFeatures >= 1 && p->lsdNFeatures <= 65536, SSLPL_ERR_ARG, "lsdNFeatures out of range");
+    SSLPL_REQUIRE(p->max_batch >= 1 && p->max_width >= 16 && p->max_height >= 16, SSLPL_ERR_ARG, "bad max_batch / max size");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_error("no CUDA device available: libsslpl_b200 has no CPU fallback"); return SSLPL_ERR_CUDA; }
+    SSLPL_CUDA(cudaSetDevice(p->device));
+    sslpl_line* h = new sslpl_line();
+    h->p = *p;
+    h->trace = getenv("SSLPL_LINE_TRACE") != nullptr;
+    {   // BinaryDescriptor constructor: local (F_l) and global (F_g) Gaussian weights, widthOfBand 7, 9 bands
+        double u = (7 * 3 - 1) / 2, sigma = (7 * 2 + 1) / 2, inv = -1 / (2 * sigma * sigma);
+        for (int i = 0; i < 21; i++) { const double d = i - u; h->coef.L[i] = (float)exp(d * d * inv); }
+        u = (9 * 7 - 1) / 2; sigma = u; inv = -1 / (2 * sigma * sigma);
+        for (int i = 0; i < 63; i++) { const double d = i - u; h->coef.G[i] = (float)exp(d * d * inv); }
+    }
+    LineGeom g;
+    make_geometry(h, p->max_width, p->max_height, g, nullptr);
+    Arena A; carve(h, A, g, p->max_batch);
+    h->arena_size = A.used + (1 << 20);
+    cudaError_t e = cudaMalloc(&h->arena, h->arena_size);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", h->arena_size, cudaGetErrorString(e)); delete h; return SSLPL_ERR_CUDA; }
+    SSLPL_CUDA(cudaMemset(h->arena, 0, h->arena_size));
+    SSLPL_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    SSLPL_CUDA(cudaHostAlloc((void**)&h->h_err, sizeof(int), cudaHostAllocDefault));
+    *out = h;
+    return SSLPL_OK;
+}
+
+void sslpl_line_destroy(sslpl_line* h) {
+    if (!h) return;
+    cudaSetDevice(h->p.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->arena) cudaFree(h->arena);
+    if (h->h_err) cudaFreeHost(h->h_err);
+    delete h;
+}
+
+int sslpl_line_sync(sslpl_line* h) { SSLPL_REQUIRE(h, SSLPL_ERR_ARG, "null handle"); SSLPL_CUDA(cudaSetDevice(h->p.device)); return check_device_err(h); }
+void* sslpl_line_stream(sslpl_line* h) { return h ? (void*)h->stream : nullptr; }
+int sslpl_line_set_stream(sslpl_line* h, void* s) {
+    SSLPL_REQUIRE(h, SSLPL_ERR_ARG, "null handle");
+    SSLPL_CUDA(cudaSetDevice(h->p.device));
+    SSLPL_CUDA(cudaStreamSynchronize(h->stream));
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return SSLPL_OK;
+}
+long long sslpl_line_launch_count(const sslpl_line* h) { return h ? h->launches : 0; }
+
+int sslpl_line_extract_batch_device(sslpl_line* h, const uint8_t* d_imgs, int nframes, int width, int height, int pitch, size_t frame_stride) {
+    SSLPL_REQUIRE(h && d_imgs, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(nframes >= 1 && nframes <= h->p.max_batch && pitch >= width, SSLPL_ERR_ARG, "bad nframes / pitch");
+    SSLPL_CUDA(cudaSetDevice(h->p.device));
+    int rc = configure(h, width, height);
+    if (rc) return rc;
+    h->view.base = d_imgs; h->view.pitch = pitch; h->view.frame_stride = (long long)frame_stride;
+    h->cur_frames = nframes;
+    return run_pipeline(h, nframes);
+}
+
+int sslpl_line_device_results(sslpl_line* h, const sslpl_keyline** d_kl, const uint8_t** d_ldesc, const double** d_lineeq, const int** d_n, int* cap) {
+    SSLPL_REQUIRE(h, SSLPL_ERR_ARG, "null handle");
+    if (d_kl) *d_kl = h->ws.kl;
+    if (d_ldesc) *d_ldesc = h->ws.ldesc;
+    if (d_lineeq) *d_lineeq = h->ws.lineeq;
+    if (d_n) *d_n = h->ws.nl;
+    if (cap) *cap = h->p.lsdNFeatures;
+    return SSLPL_OK;
+}
+
+int sslpl_line_extract_batch(sslpl_line* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
+                             sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int cap, int* n) {
+    SSLPL_REQUIRE(h && kl && ldesc && lineeq && n && imgs, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(nframes >= 1 && nframes <= h->p.max_batch && pitch >= width, SSLPL_ERR_ARG, "bad nframes / pitch");
+    SSLPL_REQUIRE(cap >= h->p.lsdNFeatures, SSLPL_ERR_CAPACITY, "caller line capacity smaller than lsdNFeatures");
+    SSLPL_CUDA(cudaSetDevice(h->p.device));
+    int rc = configure(h, width, height);
+    if (rc) return rc;
+    const LineGeom& g = h->g;
+    if (frame_stride == (size_t)pitch * height)
+        SSLPL_CUDA(cudaMemcpy2DAsync(h->d_input, g.pitch, imgs, pitch, width, (size_t)height * nframes, cudaMemcpyHostToDevice, h->stream));
+    else
+        for (int f = 0; f < nframes; f++)
+            SSLPL_CUDA(cudaMemcpy2DAsync(h->d_input + f * g.in_stride, g.pitch, imgs + f * frame_stride, pitch, width, height, cudaMemcpyHostToDevice, h->stream));
+    h->view.base = h->d_input; h->view.pitch = g.pitch; h->view.frame_stride = g.in_stride;
+    h->cur_frames = nframes;
+    rc = run_pipeline(h, nframes);
+    if (rc) return rc;
+    const int kc = g.kl_cap;
+    SSLPL_CUDA(cudaMemcpyAsync(n, h->ws.nl, sizeof(int) * nframes, cudaMemcpyDeviceToHost, h->stream));
+    SSLPL_CUDA(cudaMemcpy2DAsync(kl, (size_t)cap * sizeof(sslpl_keyline), h->ws.kl, (size_t)kc * sizeof(sslpl_keyline), (size_t)kc * sizeof(sslpl_keyline), nframes, cudaMemcpyDeviceToHost, h->stream));
+    SSLPL_CUDA(cudaMemcpy2DAsync(ldesc, (size_t)cap * 32, h->ws.ldesc, (size_t)kc * 32, (size_t)kc * 32, nframes, cudaMemcpyDeviceToHost, h->stream));
+    SSLPL_CUDA(cudaMemcpy2DAsync(lineeq, (size_t)cap * 24, h->ws.lineeq, (size_t)kc * 24, (size_t)kc * 24, nframes, cudaMemcpyDeviceToHost, h->stream));
+    return check_device_err(h);
+}
+
+int sslpl_line_extract(sslpl_line* h, const uint8_t* img, int width, int height, int pitch, sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int cap, int* n) {
+    return sslpl_line_extract_batch(h, img, 1, width, height, pitch, (size_t)pitch * height, kl, ldesc, lineeq, cap, n);
+}
+
+int sslpl_line_download_segments(sslpl_line* h, int frame, float* seg4, int cap, int* n) {
+    SSLPL_REQUIRE(h && n && frame >= 0 && frame < h->cur_frames, SSLPL_ERR_ARG, "bad argument");
+    SSLPL_CUDA(cudaSetDevice(h->p.device));
+    SSLPL_CUDA(cudaStreamSynchronize(h->stream));
+    int cnt = 0;
+    SSLPL_CUDA(cudaMemcpy(&cnt, h->ws.nseg + frame, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<double> s((size_t)std::max(cnt, 1) * 4);
+    if (cnt) SSLPL_CUDA(cudaMemcpy(s.data(), h->ws.seg + (size_t)frame * h->g.seg_cap * 4, sizeof(double) * 4 * cnt, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < cnt && i < cap; i++)
+        for (int k = 0; k < 4; k++) { double v = s[4 * i + k] + 0.5; v /= 0.8; seg4[4 * i + k] = (float)v; }
+    *n = cnt;
+    return SSLPL_OK;
+}
+
+
+/* debug (SSLPL_LINE_TRACE=1 at handle creation): one row of 10 doubles per region that reached region2rect */
+int sslpl_line_debug_trace(sslpl_line* h, int frame, double* out, int cap_rows, int* n) {
+    SSLPL_REQUIRE(h && n && frame >= 0 && frame < h->cur_frames, SSLPL_ERR_ARG, "bad argument");
+    SSLPL_REQUIRE(h->g.trace_cap > 0, SSLPL_ERR_UNSUPPORTED, "tracing is off (set SSLPL_LINE_TRACE=1 before creating the handle)");
+    SSLPL_CUDA(cudaSetDevice(h->p.device));
+    SSLPL_CUDA(cudaStreamSynchronize(h->stream));
+    int cnt = 0;
+    SSLPL_CUDA(cudaMemcpy(&cnt, h->ws.ntrace + frame, sizeof(int), cudaMemcpyDeviceToHost));
+    const int m = std::min(cnt, cap_rows);
+    if (m > 0) SSLPL_CUDA(cudaMemcpy(out, h->ws.trace + (size_t)frame * h->g.trace_cap * 10, sizeof(double) * 10 * m, cudaMemcpyDeviceToHost));
+    *n = cnt;
+    return SSLPL_OK;
+}
+
+}  // extern "C"

@@ -10,6 +10,7 @@
 // Bit-exactness notes: all float work uses explicit _rn intrinsics (no FMA contraction); cos/sin are
 // evaluated in double and narrowed (canonical correctly-rounded f32).
 #include "common.cuh"
+#include "mathx.cuh"
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -432,12 +433,6 @@ __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ OrbGeom 
 // ------------------------------------------------------------------------------------------------
 // GaussianBlur 7x7 sigma 2, OpenCV 4.13 fixed-point path, BORDER_REFLECT_101
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int reflect101(int p, int len) {
-    if (len == 1) return 0;
-    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
-    return p;
-}
-
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g, OrbWs ws, View v) {
     __shared__ uint8_t s_in[(BLUR_TH + 6) * (BLUR_TW + 8)];
     __shared__ unsigned short s_row[(BLUR_TH + 6) * BLUR_TW];
@@ -481,24 +476,6 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g,
 // ------------------------------------------------------------------------------------------------
 // IC_Angle + rBRIEF + KeyPoint assembly: one warp per output keypoint
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fast_atan2_deg(float y, float x) {       // cv::fastAtan2, SURVEY.md A.4
-    const float sc = 57.29577951308232f;                                   // (float)(180/CV_PI)
-    const float p1 = __fmul_rn(0.9997878412794807f, sc), p3 = __fmul_rn(-0.3258083974640975f, sc),
-                p5 = __fmul_rn(0.1555786518463281f, sc), p7 = __fmul_rn(-0.04432655554792128f, sc);
-    const float ax = fabsf(x), ay = fabsf(y);
-    float a, c, c2;
-    if (ax >= ay) {
-        c = __fdiv_rn(ay, __fadd_rn(ax, (float)DBL_EPSILON)); c2 = __fmul_rn(c, c);
-        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
-    } else {
-        c = __fdiv_rn(ax, __fadd_rn(ay, (float)DBL_EPSILON)); c2 = __fmul_rn(c, c);
-        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
-    }
-    if (x < 0) a = __fsub_rn(180.f, a);
-    if (y < 0) a = __fsub_rn(360.f, a);
-    return a;
-}
-
 __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ OrbGeom g, OrbWs ws, View v) {
     __shared__ signed char s_pat[1024];
     for (int i = threadIdx.x; i < 1024; i += 256) s_pat[i] = c_pattern[i];

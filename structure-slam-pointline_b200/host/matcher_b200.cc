@@ -1,0 +1,193 @@
+// host/matcher_b200.cc — GPU-backed bodies for the Hamming entry points of the reference's matchers.  Compiled inside
+// the reference tree against ITS headers (ORBmatcher.h, LSDmatcher.h, Frame.h, KeyFrame.h, MapPoint.h, MapLine.h):
+// the class declarations stay untouched; in src/ORBmatcher.cc and src/LSDmatcher.cpp the bodies of the functions
+// below are deleted (or #if 0'ed) and this file is added to the source list.
+//
+// The GPU side works on indices + validity masks; this adapter maps KeyFrame*/MapPoint* data to flat arrays and the
+// index tables back to pointers.  The matchers are constructed on the stack and called concurrently from the Tracking
+// and LocalMapping threads (Tracking.cc:1323, LocalMapping.cc:91): one sslpl_matcher per thread (thread_local).
+#include "ORBmatcher.h"
+#include "LSDmatcher.h"
+#include "sslpl.h"
+#include <stdexcept>
+#include <string>
+
+namespace StructureSLAM
+{
+namespace {
+struct MatcherCtx {
+    sslpl_matcher* h;
+    MatcherCtx(): h(NULL) {
+        sslpl_matcher_params p; p.max_features = 8192; p.max_lines = 1024; p.max_nodes = 100000; p.max_batch = 1; p.device = 0;
+        if(sslpl_matcher_create(&p, &h) != SSLPL_OK) throw std::runtime_error(std::string("sslpl_matcher_create: ") + sslpl_last_error());
+    }
+    ~MatcherCtx() { sslpl_matcher_destroy(h); }
+};
+sslpl_matcher* Ctx() { static thread_local MatcherCtx c; return c.h; }
+
+// DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned int>>) -> CSR
+struct Csr {
+    std::vector<int32_t> nodes, off, idx; sslpl_featvec fv;
+    explicit Csr(const DBoW2::FeatureVector &v) {
+        off.push_back(0);
+        for(DBoW2::FeatureVector::const_iterator it=v.begin(); it!=v.end(); ++it) {
+            nodes.push_back((int32_t)it->first);
+            for(size_t k=0; k<it->second.size(); k++) idx.push_back((int32_t)it->second[k]);
+            off.push_back((int32_t)idx.size());
+        }
+        fv.nodes = nodes.empty() ? NULL : &nodes[0]; fv.off = &off[0]; fv.idx = idx.empty() ? NULL : &idx[0]; fv.nn = (int)nodes.size();
+    }
+};
+void Check(int rc, const char* what) { if(rc != SSLPL_OK) throw std::runtime_error(std::string(what) + ": " + sslpl_last_error()); }
+}
+
+int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)          // ORBmatcher.cc:1650
+{
+    int32_t d = 0;
+    Check(sslpl_descriptor_distance(Ctx(), a.ptr<uchar>(), b.ptr<uchar>(), 1, &d), "sslpl_descriptor_distance");
+    return d;
+}
+
+int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F, vector<MapPoint*> &vpMapPointMatches)   // ORBmatcher.cc:159
+{
+    const vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches = vector<MapPoint*>(F.N,static_cast<MapPoint*>(NULL));
+    const int n1 = pKF->mDescriptors.rows, n2 = F.N;
+    if(n1 == 0 || n2 == 0) return 0;
+    std::vector<uint8_t> valid1(n1);
+    std::vector<float> a1(n1), a2(n2);
+    for(int i=0; i<n1; i++) { MapPoint* p = vpMapPointsKF[i]; valid1[i] = (p && !p->isBad()) ? 1 : 0; a1[i] = pKF->mvKeysUn[i].angle; }
+    for(int i=0; i<n2; i++) a2[i] = F.mvKeys[i].angle;
+    Csr f1(pKF->mFeatVec), f2(F.mFeatVec);
+    std::vector<int32_t> match2(n2);
+    int nmatches = 0;
+    Check(sslpl_search_by_bow(Ctx(), pKF->mDescriptors.ptr<uchar>(), n1, F.mDescriptors.ptr<uchar>(), n2, &f1.fv, &f2.fv,
+                              &valid1[0], &a1[0], &a2[0], mfNNratio, mbCheckOrientation ? 1 : 0, &match2[0], &nmatches), "sslpl_search_by_bow");
+    for(int j=0; j<n2; j++) if(match2[j] >= 0) vpMapPointMatches[j] = vpMapPointsKF[match2[j]];
+    return nmatches;
+}
+
+int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint *> &vpMatches12)   // ORBmatcher.cc:525
+{
+    const vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const vector<MapPoint*> vpMapPoints2 = pKF2->GetMapPointMatches();
+    vpMatches12 = vector<MapPoint*>(vpMapPoints1.size(),static_cast<MapPoint*>(NULL));
+    const int n1 = pKF1->mDescriptors.rows, n2 = pKF2->mDescriptors.rows;
+    if(n1 == 0 || n2 == 0) return 0;
+    std::vector<uint8_t> v1(n1), v2(n2);
+    std::vector<float> a1(n1), a2(n2);
+    for(int i=0; i<n1; i++) { MapPoint* p = vpMapPoints1[i]; v1[i] = (p && !p->isBad()) ? 1 : 0; a1[i] = pKF1->mvKeysUn[i].angle; }
+    for(int i=0; i<n2; i++) { MapPoint* p = vpMapPoints2[i]; v2[i] = (p && !p->isBad()) ? 1 : 0; a2[i] = pKF2->mvKeysUn[i].angle; }
+    Csr f1(pKF1->mFeatVec), f2(pKF2->mFeatVec);
+    std::vector<int32_t> m12(n1);
+    int nmatches = 0;
+    Check(sslpl_search_by_bow_kf(Ctx(), pKF1->mDescriptors.ptr<uchar>(), n1, pKF2->mDescriptors.ptr<uchar>(), n2, &f1.fv, &f2.fv,
+                                 &v1[0], &v2[0], &a1[0], &a2[0], mfNNratio, mbCheckOrientation ? 1 : 0, &m12[0], &nmatches), "sslpl_search_by_bow_kf");
+    for(int i=0; i<n1; i++) if(m12[i] >= 0) vpMatches12[i] = vpMapPoints2[m12[i]];
+    return nmatches;
+}
+
+int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12,
+                                       vector<pair<size_t, size_t> > &vMatchedPairs, const bool bOnlyStereo)   // ORBmatcher.cc:660
+{
+    (void)bOnlyStereo;                                      // monocular pipeline: mvuRight < 0 everywhere
+    // epipole in the second image, ORBmatcher.cc:666-672
+    cv::Mat Cw = pKF1->GetCameraCenter();
+    cv::Mat R2w = pKF2->GetRotation();
+    cv::Mat t2w = pKF2->GetTranslation();
+    cv::Mat C2 = R2w*Cw+t2w;
+    const float invz = 1.0f/C2.at<float>(2);
+    const float ex =pKF2->fx*C2.at<float>(0)*invz+pKF2->cx;
+    const float ey =pKF2->fy*C2.at<float>(1)*invz+pKF2->cy;
+
+    const int n1 = pKF1->N, n2 = pKF2->N;
+    vMatchedPairs.clear();
+    if(n1 == 0 || n2 == 0) return 0;
+    std::vector<uint8_t> h1(n1), h2(n2);
+    std::vector<sslpl_keypoint> k1(n1), k2(n2);
+    for(int i=0; i<n1; i++) { h1[i] = pKF1->GetMapPoint(i) ? 1 : 0; const cv::KeyPoint &k = pKF1->mvKeysUn[i];
+        k1[i].x = k.pt.x; k1[i].y = k.pt.y; k1[i].size = k.size; k1[i].angle = k.angle; k1[i].response = k.response; k1[i].octave = k.octave; k1[i].class_id = k.class_id; }
+    for(int i=0; i<n2; i++) { h2[i] = pKF2->GetMapPoint(i) ? 1 : 0; const cv::KeyPoint &k = pKF2->mvKeysUn[i];
+        k2[i].x = k.pt.x; k2[i].y = k.pt.y; k2[i].size = k.size; k2[i].angle = k.angle; k2[i].response = k.response; k2[i].octave = k.octave; k2[i].class_id = k.class_id; }
+    float F[9];
+    for(int r=0; r<3; r++) for(int c=0; c<3; c++) F[3*r+c] = F12.at<float>(r,c);
+    Csr f1(pKF1->mFeatVec), f2(pKF2->mFeatVec);
+    std::vector<int32_t> pairs(2*(size_t)n1);
+    int nmatches = 0;
+    Check(sslpl_search_for_triangulation(Ctx(), pKF1->mDescriptors.ptr<uchar>(), n1, pKF2->mDescriptors.ptr<uchar>(), n2, &f1.fv, &f2.fv,
+                                         &h1[0], &h2[0], &k1[0], &k2[0], F, ex, ey, &pKF2->mvScaleFactors[0], &pKF2->mvLevelSigma2[0],
+                                         (int)pKF2->mvScaleFactors.size(), mbCheckOrientation ? 1 : 0, &pairs[0], &nmatches), "sslpl_search_for_triangulation");
+    vMatchedPairs.reserve(nmatches);
+    for(int k=0; k<nmatches; k++) vMatchedPairs.push_back(make_pair((size_t)pairs[2*k], (size_t)pairs[2*k+1]));
+    return nmatches;
+}
+
+// ---- LSDmatcher: the knnMatch-based entry points (LSDmatcher.cpp:143, 257, 286, 329, 382) ----
+int LSDmatcher::DescriptorDistance(const Mat &a, const Mat &b)                   // LSDmatcher.cpp:364
+{
+    int32_t d = 0;
+    Check(sslpl_descriptor_distance(Ctx(), a.ptr<uchar>(), b.ptr<uchar>(), 1, &d), "sslpl_descriptor_distance");
+    return d;
+}
+
+static int LineMatchKF_F(KeyFrame* pKF, Frame &currentF, vector<MapLine*> &vpMapLineMatches)
+{
+    const vector<MapLine*> vpMapLinesKF = pKF->GetMapLineMatches();
+    vpMapLineMatches = vector<MapLine*>(currentF.NL,static_cast<MapLine*>(NULL));
+    const int n1 = pKF->mLineDescriptors.rows, n2 = currentF.mLdesc.rows;
+    if(n1 == 0) return 0;
+    std::vector<uint8_t> has1(n1);
+    for(int i=0; i<n1; i++) has1[i] = vpMapLinesKF[i] ? 1 : 0;
+    std::vector<int32_t> out(std::max(n1, n2)*2);
+    int nout = 0, nmatches = 0;
+    Check(sslpl_line_match(Ctx(), 0, pKF->mLineDescriptors.ptr<uchar>(), n1, currentF.mLdesc.ptr<uchar>(), n2, &has1[0], NULL, &out[0], &nout, &nmatches, NULL), "sslpl_line_match");
+    for(int t=0; t<n2; t++) if(out[t] >= 0) vpMapLineMatches[t] = vpMapLinesKF[out[t]];
+    return nmatches;
+}
+int LSDmatcher::SearchByProjection(KeyFrame* pKF,Frame &currentF, vector<MapLine*> &vpMapLineMatches) { return LineMatchKF_F(pKF, currentF, vpMapLineMatches); }   // :143
+int LSDmatcher::SearchByDescriptor(KeyFrame* pKF, Frame &currentF, vector<MapLine*> &vpMapLineMatches) { return LineMatchKF_F(pKF, currentF, vpMapLineMatches); }  // :286
+
+int LSDmatcher::SerachForInitialize(Frame &InitialFrame, Frame &CurrentFrame, vector<pair<int, int>> &LineMatches)   // :257
+{
+    LineMatches.clear();
+    const int n1 = InitialFrame.mLdesc.rows, n2 = CurrentFrame.mLdesc.rows;
+    if(n1 == 0) return 0;
+    std::vector<int32_t> out(std::max(n1, n2)*2);
+    int nout = 0, nmatches = 0;
+    Check(sslpl_line_match(Ctx(), 1, InitialFrame.mLdesc.ptr<uchar>(), n1, CurrentFrame.mLdesc.ptr<uchar>(), n2, NULL, NULL, &out[0], &nout, &nmatches, NULL), "sslpl_line_match");
+    for(int k=0; k<nout; k++) LineMatches.push_back(make_pair(out[2*k], out[2*k+1]));
+    return nmatches;
+}
+
+int LSDmatcher::SearchByDescriptor(KeyFrame* pKF, KeyFrame *pKF2, vector<MapLine*> &vpMapLineMatches)   // :329
+{
+    const vector<MapLine*> vpMapLinesKF = pKF->GetMapLineMatches();
+    const vector<MapLine*> vpMapLinesKF2 = pKF2->GetMapLineMatches();
+    vpMapLineMatches = vector<MapLine*>(vpMapLinesKF.size(),static_cast<MapLine*>(NULL));
+    const int n1 = pKF->mLineDescriptors.rows, n2 = pKF2->mLineDescriptors.rows;
+    if(n1 == 0) return 0;
+    std::vector<uint8_t> has2(std::max(n2, 1));
+    for(int i=0; i<n2; i++) has2[i] = vpMapLinesKF2[i] ? 1 : 0;
+    std::vector<int32_t> out(std::max(n1, n2)*2);
+    int nout = 0, nmatches = 0;
+    Check(sslpl_line_match(Ctx(), 2, pKF->mLineDescriptors.ptr<uchar>(), n1, pKF2->mLineDescriptors.ptr<uchar>(), n2, NULL, &has2[0], &out[0], &nout, &nmatches, NULL), "sslpl_line_match");
+    for(int q=0; q<n1; q++) if(out[q] >= 0) vpMapLineMatches[q] = vpMapLinesKF2[out[q]];
+    return nmatches;
+}
+
+int LSDmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, vector<pair<size_t, size_t>> &vMatchedPairs)   // :382
+{
+    vMatchedPairs.clear();
+    const int n1 = pKF1->mLineDescriptors.rows, n2 = pKF2->mLineDescriptors.rows;
+    if(n1 == 0) return 0;
+    std::vector<uint8_t> has1(n1), has2(std::max(n2, 1));
+    for(int i=0; i<n1; i++) has1[i] = pKF1->GetMapLine(i) ? 1 : 0;
+    for(int i=0; i<n2; i++) has2[i] = pKF2->GetMapLine(i) ? 1 : 0;
+    std::vector<int32_t> out(std::max(n1, n2)*2);
+    int nout = 0, nmatches = 0;
+    Check(sslpl_line_match(Ctx(), 3, pKF1->mLineDescriptors.ptr<uchar>(), n1, pKF2->mLineDescriptors.ptr<uchar>(), n2, &has1[0], &has2[0], &out[0], &nout, &nmatches, NULL), "sslpl_line_match");
+    for(int k=0; k<nout; k++) vMatchedPairs.push_back(make_pair((size_t)out[2*k], (size_t)out[2*k+1]));
+    return nmatches;
+}
+
+} // namespace StructureSLAM

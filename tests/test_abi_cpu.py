@@ -1,0 +1,75 @@
+"""CPU tests (no GPU): the C-ABI library builds, loads, exports every symbol include/sslpl.h declares, fails loudly
+without a CUDA device (no CPU fallback), and the product never references the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "sslpl.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(sslpl_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 45
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, f"declared in include/sslpl.h but not exported: {missing}"
+    assert lib.sslpl_version() == 1
+
+
+def test_library_is_sm100a_only():
+    so = os.path.join(ROOT, "structure-slam-pointline_b200", "libsslpl_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_struct_layouts(pkg):
+    assert pkg.KEYPOINT_DTYPE.itemsize == 28 and pkg.KEYLINE_DTYPE.itemsize == 68          # cv::KeyPoint / KeyLine
+    assert C.sizeof(pkg.OrbParams) == 36 and C.sizeof(pkg.FeatVec) == 32
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="a GPU is present")
+def test_no_cpu_fallback_without_gpu(pkg):
+    """Without a CUDA device every create call must fail loudly (SSLPL_ERR_CUDA), never compute on the host."""
+    assert pkg.device_count() == 0
+    with pytest.raises(pkg.SslplError, match="no CUDA device|CUDA"):
+        pkg.ORBextractor(1000, 1.2, 8, 20, 7)
+    with pytest.raises(pkg.SslplError):
+        pkg.Matcher()
+    with pytest.raises(pkg.SslplError):
+        pkg.LineSegment(40)
+
+
+def test_product_does_not_touch_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use oracle/."""
+    pk = os.path.join(ROOT, "structure-slam-pointline_b200")
+    for dp, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "liboracle" not in txt and "orc_" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+    so = os.path.join(pk, "libsslpl_b200.so")
+    ldd = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+    assert "liboracle" not in ldd
+
+
+def test_feature_vector_csr_matches_oracle_helper(pkg, oracle):
+    rng = np.random.default_rng(0)
+    node = rng.integers(0, 50, 400).astype(np.int32)
+    a = pkg.feature_vector_csr(node); b = oracle.feature_vector_csr(node)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    ids, off, idx = a
+    assert np.all(np.diff(ids) > 0) and off[-1] == 400
+    for k in range(len(ids)):
+        seg = idx[off[k]:off[k + 1]]
+        assert np.all(node[seg] == ids[k]) and np.all(np.diff(seg) > 0)       # ascending feature indices (FeatureVector.cpp:31-45)
