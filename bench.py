@@ -5,9 +5,9 @@ A "step" is one pass of the hot path over one batch of synthetic frames on every
 ORB extraction (+ line extraction when built) of the rank's frames, vocabulary-node assignment and
 SearchByBoW matching of every consecutive frame pair, and one NCCL all-gather of the match tables (N>1).
 
-  workload "batch640" (default; BASELINE.json config 5 sharded weakly): 64 frames 640x480 per GPU
-            (+1 halo frame so that the pair (last, first-of-next-rank) is local), nFeatures=1000, 8 levels
-  workload "single1280" (config 4): frames 1280x960, nFeatures=4000, 4 frames per GPU
+  workload "batch640" (default; BASELINE.json config 5): 512 frames 640x480 per GPU (+1 halo frame so that the pair
+            (last, first-of-next-rank) is local), nFeatures=1000, 8 levels, 40 lines; weak scaling over GPUs
+  workload "single1280" (config 4): frames 1280x960, nFeatures=4000, 500 lines, 16 frames per GPU
 
 `value`  : whole-job (features+matches)/s with the frames already resident in HBM (CUDA events, max over ranks)
 `e2e`    : same metric through the host-buffer API: pinned-host frames H2D, results D2H, every step
@@ -34,8 +34,10 @@ METRIC = "features+matches/sec"
 UNIT = "features+matches/s"
 
 WORKLOADS = {
-    "batch640": dict(width=640, height=480, nfeatures=1000, frames_per_gpu=64, nlines=40),
-    "single1280": dict(width=1280, height=960, nfeatures=4000, frames_per_gpu=4, nlines=500),
+    # BASELINE.json config 5: a batch of 512 synthetic 640x480 frames (per GPU: the job is weak-scaled)
+    "batch640": dict(width=640, height=480, nfeatures=1000, frames_per_gpu=512, nlines=40),
+    # BASELINE.json config 4: 1280x960, nFeatures=4000, 500 lines
+    "single1280": dict(width=1280, height=960, nfeatures=4000, frames_per_gpu=16, nlines=500),
 }
 NWORDS, NNRATIO = 100, 0.7
 
@@ -54,7 +56,7 @@ def gen_frames(cfg, rank, nsets):
 # ------------------------------------------------------------------------------------------------
 # CPU arm (oracle port of the reference CPU path), all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_step(O, cfg, frames, voc, nthreads):
+def cpu_step(O, cfg, frames, voc, nthreads, lines=True):
     """One step of the workload on the host: returns (features, matches, seconds)."""
     from concurrent.futures import ThreadPoolExecutor
     B = len(frames)
@@ -63,13 +65,17 @@ def cpu_step(O, cfg, frames, voc, nthreads):
     def extract(i):
         if not hasattr(tl, "orb"):
             tl.orb = O.OrbOracle(cfg["nfeatures"], 1.2, 8, 20, 7)
+            tl.line = O.LineOracle(cfg["nlines"])
         k, d = tl.orb.extract(frames[i])
         node = O.bow_assign(d, voc)
-        return k, d, O.feature_vector_csr(node)
+        kl, ld, _ = tl.line.extract(frames[i]) if lines else (np.zeros(0), np.zeros((0, 32), np.uint8), None)
+        return k, d, O.feature_vector_csr(node), ld
 
     def match(i):
-        (k1, d1, fv1), (k2, d2, fv2) = res[i], res[i + 1]
+        (k1, d1, fv1, l1), (k2, d2, fv2, l2) = res[i], res[i + 1]
         n, _ = O.search_by_bow(d1, d2, fv1, fv2, np.ones(len(d1), np.uint8), k1["angle"], k2["angle"], NNRATIO, True)
+        if lines and len(l1) >= 1 and len(l2) >= 2:
+            n += O.line_match(0, l1, l2, np.ones(len(l1), np.uint8), None)[0]
         return n
 
     t0 = time.perf_counter()
@@ -77,7 +83,7 @@ def cpu_step(O, cfg, frames, voc, nthreads):
         res = list(ex.map(extract, range(B)))
         nm = list(ex.map(match, range(B - 1)))
     dt = time.perf_counter() - t0
-    feats = sum(len(r[0]) for r in res[:B - 1])
+    feats = sum(len(r[0]) + len(r[3]) for r in res[:B - 1])
     return feats, sum(nm), dt
 
 
@@ -105,7 +111,7 @@ def run_reference(args, cfg):
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, **{k: cfg[k] for k in ("width", "height", "nfeatures")},
-                       "frames_per_step": nsample - 1, "lines": "not included (round 1)"},
+                       "frames_per_step": nsample - 1, "lines": cfg["nlines"]},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -157,6 +163,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="batch640", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lines", action="store_true", help="ORB + point matching only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = WORKLOADS[args.workload]
@@ -177,14 +184,21 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    W, H, NF, Bf = cfg["width"], cfg["height"], cfg["nfeatures"], cfg["frames_per_gpu"]
+    W, H, NF, Bf, NL = cfg["width"], cfg["height"], cfg["nfeatures"], cfg["frames_per_gpu"], cfg["nlines"]
+    LINES = not args.no_lines
     B = Bf + 1                                          # + halo frame (first frame of the next rank's block)
     ext = pkg.ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B, device=local)
-    mt = pkg.Matcher(max_features=ext.cap, max_lines=cfg["nlines"], max_nodes=NWORDS, max_batch=B, device=local)
-    stream = torch.cuda.Stream(device=dev)              # one explicit (non-default) stream for kernels, NCCL waits and the timing events
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    ext.set_stream(stream.cuda_stream); mt.set_stream(stream.cuda_stream)
+    mt = pkg.Matcher(max_features=ext.cap, max_lines=NL, max_nodes=NWORDS, max_batch=B, device=local)
+    ls = pkg.LineSegment(NL, max_width=W, max_height=H, max_batch=B, device=local) if LINES else None
+    lmt = pkg.Matcher(max_features=64, max_lines=NL, max_nodes=2, max_batch=B, device=local) if LINES else None
+    # two explicit streams: points (ORB + BoW matching + NCCL waits + timing events) and lines (LSD/LBD + line matching);
+    # the latency-bound LSD region walker (one warp per frame) overlaps with the wide ORB kernels
+    s_pts = torch.cuda.Stream(device=dev); s_lin = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(s_pts)
+    assert s_pts.cuda_stream != 0 and s_lin.cuda_stream != 0
+    ext.set_stream(s_pts.cuda_stream); mt.set_stream(s_pts.cuda_stream)
+    if LINES:
+        ls.set_stream(s_lin.cuda_stream); lmt.set_stream(s_lin.cuda_stream)
     cap = ext.cap
     voc = synth.vocabulary(NWORDS)
     d_voc = torch.from_numpy(voc).to(dev)
@@ -193,34 +207,52 @@ def main():
     d_sets = [torch.from_numpy(s).to(dev) for s in sets]
     d_match = torch.empty((Bf, cap), dtype=torch.int32, device=dev)
     d_nmatch = torch.empty((Bf,), dtype=torch.int32, device=dev)
+    d_lmatch = torch.empty((Bf, NL), dtype=torch.int32, device=dev)
+    d_nlmatch = torch.zeros((Bf,), dtype=torch.int32, device=dev)
     d_gather = torch.empty((world * Bf, cap), dtype=torch.int32, device=dev) if world > 1 else None
-    d_kps, d_desc, d_n, _ = None, None, None, None
+    d_lgather = torch.empty((world * Bf, NL), dtype=torch.int32, device=dev) if world > 1 else None
+
+    def enqueue_lines(ptr):
+        ls.extract_batch_device(ptr, B, W, H, W, W * H)
+        _, ldesc, _, nl, capl = ls.device_results()
+        lmt.match_lines_batch_device(ldesc, nl, B, capl, d_lmatch.data_ptr(), d_nlmatch.data_ptr())
+
+    def enqueue_points():
+        kps, desc, n, c = ext.device_results()
+        mt.match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match.data_ptr(), d_nmatch.data_ptr())
 
     def step_device(i):
         fr = d_sets[i % nsets]
+        if LINES:
+            s_lin.wait_stream(s_pts)                    # the previous step's readers of d_lmatch are done
+            enqueue_lines(fr.data_ptr())
         ext.extract_batch_device(fr.data_ptr(), B, W, H, W, W * H)
-        kps, desc, n, c = ext.device_results()
-        mt.match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match.data_ptr(), d_nmatch.data_ptr())
+        enqueue_points()
+        if LINES:
+            s_pts.wait_stream(s_lin)
         if world > 1:
             dist.all_gather_into_tensor(d_gather, d_match)
-        return kps, desc, n
+            if LINES:
+                dist.all_gather_into_tensor(d_lgather, d_lmatch)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def launches_now():
+        return ext.launch_count + mt.launch_count + (ls.launch_count + lmt.launch_count if LINES else 0)
+
     # ---- warm-up, then K timed steps, device-resident inputs ----
     for i in range(args.warmup):
         step_device(i)
     ext.sync()
-    launches0 = ext.launch_count + mt.launch_count
+    launches0 = launches_now()
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    units = 0
     e0.record()
     for i in range(args.steps):
         step_device(args.warmup + i)
@@ -228,18 +260,52 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     ext.sync()
-    launches = ext.launch_count + mt.launch_count - launches0
+    if LINES:
+        ls.sync()
+    launches = launches_now() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    # units: count features+matches of every step's batch (one extra, untimed pass per distinct set)
-    per_set = []
-    nkp_avg = 0.0
-    for s in range(nsets):
-        _, _, hn = ext.extract_batch(sets[s])                                   # host API: returns the per-frame counts
-        kps_, desc_, n_, c_ = ext.device_results()
-        mt.match_bow_batch_device(desc_, kps_, n_, B, c_, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match.data_ptr(), d_nmatch.data_ptr())
-        torch.cuda.synchronize()
-        per_set.append(int(hn[:Bf].sum()) + int(d_nmatch.cpu().sum()))
-        nkp_avg += float(hn.mean()) / nsets
+
+    # ---- e2e: pinned host frames -> H2D -> kernels -> D2H of keypoints, descriptors, lines, counts, match tables ----
+    h_sets = []
+    for s in sets[:min(nsets, 2)]:
+        hp = pkg.host_alloc(s.shape, np.uint8); hp[...] = s; h_sets.append(hp)
+    h_out = (pkg.host_alloc((B, cap), pkg.KEYPOINT_DTYPE), pkg.host_alloc((B, cap, 32), np.uint8), pkg.host_alloc((B,), np.int32))
+    h_lout = (pkg.host_alloc((B, NL), pkg.KEYLINE_DTYPE), pkg.host_alloc((B, NL, 32), np.uint8),
+              pkg.host_alloc((B, NL, 3), np.float64), pkg.host_alloc((B,), np.int32)) if LINES else None
+    h_match = torch.empty((Bf, cap), dtype=torch.int32).pin_memory(); h_nmatch = torch.empty((Bf,), dtype=torch.int32).pin_memory()
+    h_lmatch = torch.empty((Bf, NL), dtype=torch.int32).pin_memory(); h_nlmatch = torch.zeros((Bf,), dtype=torch.int32).pin_memory()
+
+    def step_e2e(i):
+        fr = h_sets[i % len(h_sets)]
+        if LINES:                                                             # host API: H2D + kernels + D2H, synchronous
+            s_lin.wait_stream(s_pts)
+            ls.extract_batch(fr, out=h_lout)
+            _, ldesc, _, nl, capl = ls.device_results()
+            lmt.match_lines_batch_device(ldesc, nl, B, capl, d_lmatch.data_ptr(), d_nlmatch.data_ptr())
+        ext.extract_batch(fr, out=h_out)
+        enqueue_points()
+        if LINES:
+            s_pts.wait_stream(s_lin)
+        if world > 1:
+            dist.all_gather_into_tensor(d_gather, d_match)
+            if LINES:
+                dist.all_gather_into_tensor(d_lgather, d_lmatch)
+        h_match.copy_(d_match, non_blocking=True); h_nmatch.copy_(d_nmatch, non_blocking=True)
+        if LINES:
+            h_lmatch.copy_(d_lmatch, non_blocking=True); h_nlmatch.copy_(d_nlmatch, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        u = int(h_out[2][:Bf].sum()) + int(h_nmatch.sum())
+        if LINES:
+            u += int(h_lout[3][:Bf].sum()) + int(h_nlmatch.sum())
+        return u
+
+    per_set = [step_e2e(s) for s in range(nsets)] if nsets <= len(h_sets) else None     # also the units of every input set
+    if per_set is None:
+        per_set = []
+        for s in range(nsets):
+            hp = pkg.host_alloc(sets[s].shape, np.uint8); hp[...] = sets[s]; h_sets.append(hp)
+        per_set = [step_e2e(s) for s in range(nsets)]
+    nkp_avg = float(np.mean(h_out[2][:Bf]))
     units = sum(per_set[(args.warmup + i) % nsets] for i in range(args.steps))
     t = torch.tensor([ms_total, float(units)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -250,28 +316,10 @@ def main():
         units_all = float(units)
     value = units_all / (ms_total * 1e-3)
 
-    # ---- e2e: pinned host frames -> H2D -> kernels -> D2H of keypoints, descriptors, counts, match tables ----
-    h_sets = []
-    for s in sets[:min(nsets, 4)]:
-        hp = pkg.host_alloc(s.shape, np.uint8); hp[...] = s; h_sets.append(hp)
-    h_out = (pkg.host_alloc((B, cap), pkg.KEYPOINT_DTYPE), pkg.host_alloc((B, cap, 32), np.uint8), pkg.host_alloc((B,), np.int32))
-    h_match = torch.empty((Bf, cap), dtype=torch.int32).pin_memory()
-    h_nmatch = torch.empty((Bf,), dtype=torch.int32).pin_memory()
-
-    def step_e2e(i):
-        ext.extract_batch(h_sets[i % len(h_sets)], out=h_out)                 # H2D + kernels + D2H (synchronous API)
-        kps, desc, n, c = ext.device_results()
-        mt.match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match.data_ptr(), d_nmatch.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(d_gather, d_match)
-        h_match.copy_(d_match, non_blocking=True); h_nmatch.copy_(d_nmatch, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return int(h_out[2][:Bf].sum()) + int(h_nmatch.sum())
-
     for i in range(args.warmup):
         step_e2e(i)
     barrier()
-    t0 = time.perf_counter(); e0.record()
+    e0.record()
     eu = 0
     for i in range(args.steps):
         eu += step_e2e(args.warmup + i)
@@ -285,8 +333,8 @@ def main():
         e2e_ms, eu_all = float(tmax[0]), float(tsum[1])
     else:
         eu_all = float(eu)
-    h2d = B * W * H
-    d2h = B * cap * (28 + 32) + B * 4 + Bf * cap * 4 + Bf * 4
+    h2d = B * W * H * (2 if LINES else 1)               # each extractor uploads the frames through its own host API call
+    d2h = B * cap * (28 + 32) + B * 4 + Bf * cap * 4 + Bf * 4 + (B * NL * (68 + 32 + 24) + B * 4 + Bf * NL * 4 + Bf * 4 if LINES else 0)
 
     # ---- roofline of the dominant kernel (rank 0): CUDA events between the kernels of one handle ----
     roofline = None
@@ -311,7 +359,8 @@ def main():
             ncand += len(ext.candidates(l, frame=0)[0])
         alg = {   # algorithmic bytes per frame, SURVEY.md 8(d) byte table
             "pyramid": 2 * P - W * H - ext.level_size(7)[0] * ext.level_size(7)[1],
-            "fast": P + 5 * ncand,
+            "fast_score": P + 5 * ncand,        # the FAST+NMS stage figure (read P, write 5C) is charged to the score kernel
+            "fast_cells": P + 5 * ncand,        # reads the u8 score plane (P) and writes the candidates
             "blur": 2 * P,
             "orient_desc": (749 + 512 + 32 + 28 + 4) * nkp_avg,
             "octree": 8 * ncand,
@@ -328,10 +377,10 @@ def main():
         O = g.load_oracle()
         cores = os.cpu_count() or 1
         ns = min(B, max(9, 2 * cores + 1))
-        cpu_step(O, cfg, sets[0][:min(ns, cores + 1)], voc, cores)
+        cpu_step(O, cfg, sets[0][:min(ns, cores + 1)], voc, cores, LINES)
         best = None
         for _ in range(2):
-            f, m, dt = cpu_step(O, cfg, sets[0][:ns], voc, cores)
+            f, m, dt = cpu_step(O, cfg, sets[0][:ns], voc, cores, LINES)
             v = (f + m) / dt
             best = v if best is None or v > best else best
         cpu = {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
@@ -343,7 +392,7 @@ def main():
                 "dtype": "u8", "data": "synthetic",
                 "config": {"workload": args.workload, "width": W, "height": H, "nfeatures": NF, "nlevels": 8,
                            "frames_per_gpu": Bf, "halo_frames_per_gpu": 1, "pairs_per_gpu": Bf, "vocabulary_nodes": NWORDS,
-                           "lines": "not included (round 1)", "parallelism": f"frames sharded x{world}, all_gather(match tables)",
+                           "lines": NL if LINES else 0, "parallelism": f"frames sharded x{world}, all_gather(match tables)",
                            "l2": f"inputs cycle through {nsets} distinct batches ({nsets * B * W * H / 1e6:.0f} MB > 126 MB L2)"},
                 "e2e": {"value": eu_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps},

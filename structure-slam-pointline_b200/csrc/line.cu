@@ -12,6 +12,7 @@
 // in the same order as the CPU restatement, so that discrete decisions (alignment tests, density, NFA) agree.
 #include "common.cuh"
 #include "mathx.cuh"
+#include "ddtrig.h"
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -55,6 +56,7 @@ struct LineWs {
     sslpl_keyline* kl; uint8_t* ldesc; double* lineeq; int* nl;
     int* err;
     double* trace; int* ntrace;
+    const double* lgam;         // lgam[n] = log_gamma(n + 1) of lsd.cpp (Lanczos / Windschitl), tabulated by the host's libm
 };
 
 struct LView { const uint8_t* base; int pitch; long long frame_stride; };
@@ -198,6 +200,7 @@ struct Walk {
     int w, h; long long npix;
     const float* ang; const float2* cs; const double* mod; uint8_t* used; unsigned* reg;
     double log_nt;
+    const double* lgam;
     int lane;
 };
 
@@ -228,18 +231,22 @@ __device__ int l_region_grow(const Walk& W, int sx, int sy, double prec, double&
             const long long q = (long long)yy * W.w + xx;
             u = W.used[q]; a = W.ang[q]; c = W.cs[q];
         }
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            const int uk = __shfl_sync(0xffffffffu, (int)u, k);
-            const float ak = __shfl_sync(0xffffffffu, a, k);
-            const float cx = __shfl_sync(0xffffffffu, c.x, k), cy = __shfl_sync(0xffffffffu, c.y, k);
-            if (uk != 1 && l_aligned(ak, reg_angle, prec)) {
-                const int nx = px - 1 + k % 3, ny = py - 1 + k / 3;
-                if (lane == 0) { W.used[(long long)ny * W.w + nx] = 1; W.reg[n] = (unsigned)nx | ((unsigned)ny << 16); }
-                n++;
-                sumdx += cx; sumdy += cy;
-                reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * L_DEG;
-            }
+        // Sequential semantics (each neighbour is tested once, in scan order, against the region angle as updated by
+        // the neighbours accepted before it) in as many rounds as there are acceptances: all pending lanes test
+        // against the current angle; the first passing lane k0 is accepted, lanes < k0 are definitively rejected
+        // (they saw exactly the angle the sequential scan would have shown them).
+        unsigned pending = __ballot_sync(0xffffffffu, valid && u != 1 && a != NOTDEF_F);
+        while (pending) {
+            const unsigned okm = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && l_aligned(a, reg_angle, prec)) & pending;
+            if (!okm) break;
+            const int k0 = __ffs(okm) - 1;
+            const float cx = __shfl_sync(0xffffffffu, c.x, k0), cy = __shfl_sync(0xffffffffu, c.y, k0);
+            const int nx = px - 1 + k0 % 3, ny = py - 1 + k0 / 3;
+            if (lane == 0) { W.used[(long long)ny * W.w + nx] = 1; W.reg[n] = (unsigned)nx | ((unsigned)ny << 16); }
+            n++;
+            sumdx += cx; sumdy += cy;
+            reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * L_DEG;
+            pending &= ~((2u << k0) - 1u);
         }
         __syncwarp();
     }
@@ -286,7 +293,9 @@ __device__ void l_region2rect(const Walk& W, int n, double reg_angle, double pre
                                            : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
     theta *= L_DEG;
     if (fabs(l_angle_diff_signed(theta, reg_angle)) > prec) theta += L_PI;
-    const double dx = cos(theta), dy = sin(theta);
+    // correctly-rounded cos/sin (see ddtrig.h): the extreme region pixels sit exactly on the rectangle's end edges
+    double dx, dy;
+    ddtrig::sincos_cr(theta, &dy, &dx);
     double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
     for (int b = 0; b < n; b += 32) {
         const int i = b + lane;
@@ -378,11 +387,11 @@ __device__ double l_log_gamma(double x) {
     return a + log(b);
 }
 
-__device__ double l_nfa(int n, int k, double p, double LOG_NT) {
+__device__ double l_nfa(int n, int k, double p, double LOG_NT, const double* lgam) {
     if (n == 0 || k == 0) return -LOG_NT;
     if (n == k) return -LOG_NT - (double)n * log10(p);
     const double p_term = p / (1 - p);
-    const double log1term = l_log_gamma((double)n + 1) - l_log_gamma((double)k + 1) - l_log_gamma((double)(n - k) + 1) +
+    const double log1term = lgam[n] - lgam[k] - lgam[n - k] +
                             (double)k * log(p) + (double)(n - k) * log(1.0 - p);
     double term = exp(log1term);
     {   // double_equal(term, 0)
@@ -450,7 +459,7 @@ __device__ double l_rect_nfa(const Walk& W, const LRect& rec) {
     }
     total = __reduce_add_sync(0xffffffffu, total);
     alg = __reduce_add_sync(0xffffffffu, alg);
-    return l_nfa(total, alg, rec.p, W.log_nt);
+    return l_nfa(total, alg, rec.p, W.log_nt, W.lgam);
 }
 
 __device__ double l_rect_improve(const Walk& W, LRect& rec) {
@@ -503,7 +512,7 @@ __global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ Line
     Walk W;
     W.w = g.sw; W.h = g.sh; W.npix = g.pix_stride; W.lane = threadIdx.x;
     W.ang = ws.angdeg + f * g.pix_stride; W.cs = ws.cs + f * g.pix_stride; W.mod = ws.modgrad + f * g.pix_stride;
-    W.used = ws.used + f * g.pix_stride; W.reg = ws.reg + f * g.pix_stride; W.log_nt = g.log_nt;
+    W.used = ws.used + f * g.pix_stride; W.reg = ws.reg + f * g.pix_stride; W.log_nt = g.log_nt; W.lgam = ws.lgam;
     const unsigned* seeds = ws.seeds + f * g.pix_stride;
     const int ns = ws.nseeds[f];
     double* seg = ws.seg + (long long)f * g.seg_cap * 4;
@@ -790,6 +799,16 @@ void carve(sslpl_line* h, Arena& A, const LineGeom& g, int B) {
     ws.lineeq = A.take<double>((size_t)B * g.kl_cap * 3); ws.nl = A.take<int>(B);
     ws.err = A.take<int>(1);
     ws.trace = A.take<double>((size_t)B * g.trace_cap * 10 + 16); ws.ntrace = A.take<int>(B);
+    ws.lgam = A.take<double>((size_t)g.pix_stride + 2);
+}
+
+// log_gamma of lsd.cpp on the host (same libm as the CPU implementation): Lanczos for x <= 15, Windschitl above
+double host_log_gamma(double x) {
+    if (x > 15.0) return 0.918938533204673 + (x - 0.5) * std::log(x) - x + 0.5 * x * std::log(x * std::sinh(1 / x) + 1 / (810.0 * std::pow(x, 6.0)));
+    static const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
+    double a = (x + 0.5) * std::log(x + 5.5) - (x + 5.5), b = 0;
+    for (int n = 0; n < 7; ++n) { a -= std::log(x + double(n)); b += q[n] * std::pow(x, double(n)); }
+    return a + std::log(b);
 }
 
 int configure(sslpl_line* h, int W, int H) {
@@ -804,6 +823,11 @@ int configure(sslpl_line* h, int W, int H) {
     SSLPL_CUDA(cudaStreamSynchronize(h->stream));
     SSLPL_CUDA(cudaMemcpy(h->ws.tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     SSLPL_CUDA(cudaMemset(h->ws.err, 0, sizeof(int)));
+    {
+        std::vector<double> lg((size_t)h->g.pix_stride + 2);
+        for (size_t n = 0; n < lg.size(); n++) lg[n] = host_log_gamma((double)n + 1.0);
+        SSLPL_CUDA(cudaMemcpy(const_cast<double*>(h->ws.lgam), lg.data(), lg.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     h->cur_w = W; h->cur_h = H;
     return SSLPL_OK;
 }

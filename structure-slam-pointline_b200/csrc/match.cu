@@ -104,22 +104,23 @@ __global__ void __launch_bounds__(128) k_bow_assign(const uint8_t* desc, long lo
 __global__ void __launch_bounds__(128) k_build_csr(const int32_t* node, long long node_fs, const int* n_arr, int cap, int nc,
                                                     int* off, long long off_fs, int* idx, long long idx_fs) {
     __shared__ int s_warp[33];
-    extern __shared__ int s_cnt[];        // nc + 1 ints
+    extern __shared__ int s_dyn[];        // nc + 1 counters, then the frame's node ids (cap ints)
+    int* s_cnt = s_dyn; int* s_nd = s_dyn + nc + 1;
     const int f = blockIdx.x, tid = threadIdx.x;
     const int n = min(n_arr[f], cap);
     const int32_t* nd = node + f * node_fs;
     for (int c = tid; c <= nc; c += blockDim.x) s_cnt[c] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) atomicAdd(&s_cnt[nd[i]], 1);
+    for (int i = tid; i < n; i += blockDim.x) { const int v = nd[i]; s_nd[i] = v; atomicAdd(&s_cnt[v], 1); }
     __syncthreads();
     block_scan_array(s_cnt, nc + 1, s_warp);                  // exclusive offsets, s_cnt[nc] = n
     for (int c = tid; c <= nc; c += blockDim.x) off[f * off_fs + c] = s_cnt[c];
     __syncthreads();
-    // stable fill: thread c walks all features in index order (n * nc / T steps; n ~ 1e3, nc ~ 1e2)
+    // stable fill: thread c walks the node ids in index order (broadcast reads from shared memory)
     for (int c = tid; c < nc; c += blockDim.x) {
         int o = s_cnt[c];
         const int e = s_cnt[c + 1];
-        for (int i = 0; i < n && o < e; i++) if (nd[i] == c) idx[f * idx_fs + o++] = i;
+        for (int i = 0; i < n && o < e; i++) if (s_nd[i] == c) idx[f * idx_fs + o++] = i;
     }
 }
 
@@ -679,7 +680,7 @@ int sslpl_match_bow_batch_device(sslpl_matcher* m, const uint8_t* d_desc, const 
     cudaStream_t st = m->stream;
     const int npairs = nframes - 1, fc = m->p.max_features + 64, NN = m->p.max_nodes + 1;
     k_bow_assign<<<dim3((cap + 127) / 128, nframes), 128, nc * 32, st>>>(d_desc, (long long)cap * 32, d_n, 0, cap, d_centroids, nc, m->b_node, fc);
-    k_build_csr<<<nframes, 128, (nc + 1) * sizeof(int), st>>>(m->b_node, fc, d_n, cap, nc, m->b_off, NN + 1, m->b_idx, fc);
+    k_build_csr<<<nframes, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->b_node, fc, d_n, cap, nc, m->b_off, NN + 1, m->b_idx, fc);
     m->launches += 2;
     fill(m, d_match, (long long)npairs * cap, -1);
     SSLPL_CUDA(cudaMemsetAsync(m->b_rot, 255, (size_t)npairs * fc, st));

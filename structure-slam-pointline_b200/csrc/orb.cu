@@ -11,9 +11,12 @@
 // evaluated in double and narrowed (canonical correctly-rounded f32).
 #include "common.cuh"
 #include "mathx.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace sslpl {
@@ -35,19 +38,20 @@ struct LevelGeom {
     int nfeat, kp_cap, kp_base;
     int pool_cap; long long pool_off;
     int xtab_off, ytab_off;          // resize tables (int2 entries)
-    int tile_base, tiles_x, tiles_y; // blur tiles
+    int tile_base, tiles_x, tiles_y; // blur tiles (64x32 over the whole level)
+    int fs_base, fs_tx, fs_ty;       // FAST score tiles (64x32 over the detection window [16,w-16)x[16,h-16))
     float scale, patch_size;
 };
 
 struct OrbGeom {
-    int nlevels, total_cells, total_tiles, kp_total_cap, iniTh, minTh, sort_cap, pad0;
+    int nlevels, total_cells, total_tiles, kp_total_cap, iniTh, minTh, sort_cap, total_fs_tiles;
     long long pyr_stride, blur_stride, cand_stride, key_stride, pool_stride;
     int umax[16];
     LevelGeom lv[MAXL];
 };
 
 struct OrbWs {
-    uint8_t* pyr; uint8_t* blur;
+    uint8_t* pyr; uint8_t* blur; uint8_t* score;
     uint32_t* cand; int* cell_cnt; int* cell_off;
     uint32_t* kxyr; int* knode;
     short4* nbox; int* ncnt; int* nq; uint8_t* nalive; unsigned* nbest; int* scan; int* ord;
@@ -55,9 +59,12 @@ struct OrbWs {
     int2* rtab;
     int* err;
     sslpl_keypoint* kps; uint8_t* desc; int* nkp;
+    CUtensorMap* tmaps;          // MAXL tensor maps in global memory (64-byte aligned)
 };
 
 struct View { const uint8_t* base; int pitch; long long frame_stride; };
+
+struct TMaps { CUtensorMap lvl[MAXL]; };     // one 3-D (x, y, frame) u8 tensor map per pyramid level
 
 __constant__ signed char c_pattern[1024] = {
 #include "orb_pattern.inc"
@@ -145,14 +152,143 @@ __device__ __forceinline__ int fast_score_tile(const uint8_t* p, int pitch, int 
     return s >= t ? s : 0;
 }
 
-constexpr int FAST_MAXC = 60;                 // wCell, hCell < 60 (ceil(w / floor(w/30)) < 60)
-constexpr int FAST_TP = FAST_MAXC + 6 + 2;    // tile pitch (bytes)
+// ------------------------------------------------------------------------------------------------
+// TMA / mbarrier helpers (sm_100a): one elected thread arms the barrier with the byte count and issues a
+// cp.async.bulk.tensor.3d tile load (x, y, frame); out-of-bounds elements are zero-filled by the hardware.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (int spin = 0; !ok; spin++) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spin > (1 << 24)) __trap();          // never hang the box on a mis-programmed copy
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
 
-// One CTA per cell.  Equivalent to the reference's per-cell cv::FAST(th=20) with fallback cv::FAST(th=7)
-// (ORBextractor.cc:809-816): score map with floor minTh, NMS inside the cell's detection area with
+constexpr int TL_W = 64, TL_H = 32;            // output tile of the stencil kernels
+constexpr int TL_P = 96, TL_IH = TL_H + 6;     // staged box: 96 x 38 bytes, origin (x0 - 16, y0 - 3).  For 1-byte elements TMA
+                                               // requires the box to START on a 16-byte boundary in x (measured: tools/tma_probe.cu)
+constexpr int TL_X = 16;                       // smem column of the tile's first output pixel
+
+// Stage the 96x38 box of level `l`, frame `f` at (bx, by) into s_img (pitch TL_P).  TMA path: one bulk tensor copy,
+// zero fill outside the level.  Fallback: aligned 32-bit loads (clamped to the row) or byte loads.
+template <bool TMA>
+__device__ __forceinline__ void stage_box(uint8_t* s_img, uint64_t* s_bar, const CUtensorMap* tm, const uint8_t* img, int pitch, int w, int h,
+                                          int l, int f, int bx, int by) {
+    const int tid = threadIdx.x;
+    if (TMA) {
+        if (tid == 0) { mbar_init(s_bar, 1); }
+        __syncthreads();
+        if (tid == 0) {
+            // the descriptor lives in global memory and level 0 is rewritten by the host between launches
+            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tm + l)) : "memory");
+            mbar_expect_tx(s_bar, TL_P * TL_IH);
+            tma_load_3d(s_img, tm + l, bx, by, f, s_bar);
+        }
+        mbar_wait(s_bar, 0);
+    } else {
+        const bool al = ((reinterpret_cast<uintptr_t>(img) | (unsigned)pitch) & 3) == 0 && (bx & 3) == 0 && bx >= 0;
+        if (al) {
+            const int wmax = (pitch - bx) / 4 - 1;                       // last whole word of the row
+            for (int i = tid; i < TL_IH * (TL_P / 4); i += blockDim.x) {
+                const int r = i / (TL_P / 4), wi = i - r * (TL_P / 4);
+                const int gy = min(max(by + r, 0), h - 1);
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(img + (long long)gy * pitch + bx) + min(wi, wmax));
+                reinterpret_cast<uint32_t*>(s_img)[r * (TL_P / 4) + wi] = v;
+            }
+        } else {
+            for (int i = tid; i < TL_IH * TL_P; i += blockDim.x) {
+                const int r = i / TL_P, c = i - r * TL_P;
+                const int gy = min(max(by + r, 0), h - 1), gx = min(max(bx + c, 0), w - 1);
+                s_img[i] = __ldg(img + (long long)gy * pitch + gx);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// FAST score map of the detection window, 64x32 tiles.  Phase A: every pixel runs the cheap opposite-pair test and
+// the survivors are compacted into a queue (ballot + popc); phase B: the full 16-ring score only for queued pixels,
+// all lanes busy.  Scores (0 = not a corner at minThFAST) go to a u8 plane with the level's geometry.
+template <bool TMA>
+__global__ void __launch_bounds__(256) k_fast_score(const __grid_constant__ OrbGeom g, OrbWs ws, View v, const CUtensorMap* tm) {
+    __shared__ __align__(128) uint8_t s_img[TL_IH * TL_P];
+    __shared__ __align__(16) uint8_t s_sc[TL_H * TL_W];
+    __shared__ unsigned short s_q[TL_H * TL_W];
+    __shared__ int s_qn;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    int l = 0;
+    while (l + 1 < g.nlevels && tile >= g.lv[l + 1].fs_base) l++;
+    const LevelGeom& L = g.lv[l];
+    const int t = tile - L.fs_base, ty = t / L.fs_tx, tx = t - ty * L.fs_tx;
+    const int x0 = MINB + tx * TL_W, y0 = MINB + ty * TL_H;
+    int pitch;
+    const uint8_t* img = level_ptr(g, ws, v, l, f, &pitch);
+    if (tid == 0) s_qn = 0;
+    for (int i = tid; i < TL_H * TL_W / 4; i += 256) reinterpret_cast<uint32_t*>(s_sc)[i] = 0u;
+    stage_box<TMA>(s_img, &s_bar, tm, img, pitch, L.w, L.h, l, f, x0 - TL_X, y0 - 3);
+    if (TMA) __syncthreads();                   // s_qn / s_sc initialisation
+    const int vw = min(TL_W, L.maxBX - x0), vh = min(TL_H, L.maxBY - y0);     // valid part of the tile
+    const int th = g.minTh;
+    // phase A
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int p = it * 256 + tid, r = p >> 6, c = p & 63;
+        bool pass = false;
+        if (r < vh && c < vw) {
+            const uint8_t* q = &s_img[(r + 3) * TL_P + c + TL_X];
+            const int ctr = q[0];
+            const int d0 = ctr - q[3 * TL_P], d8 = ctr - q[-3 * TL_P], d4 = ctr - q[3], d12 = ctr - q[-3];
+            const bool br = (d0 > th || d8 > th) && (d4 > th || d12 > th);
+            const bool dk = (d0 < -th || d8 < -th) && (d4 < -th || d12 < -th);
+            pass = br || dk;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_qn, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) s_q[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)p;
+    }
+    __syncthreads();
+    // phase B
+    const int nq = s_qn;
+    for (int qi = tid; qi < nq; qi += 256) {
+        const int p = s_q[qi], r = p >> 6, c = p & 63;
+        s_sc[p] = (uint8_t)fast_score_tile(&s_img[(r + 3) * TL_P + c + TL_X], TL_P, th);
+    }
+    __syncthreads();
+    uint8_t* out = ws.score + (long long)f * g.blur_stride + L.blur_off + (long long)y0 * L.bpitch + x0;
+    if (vw == TL_W) {
+        for (int i = tid; i < vh * 4; i += 256) {
+            const int r = i >> 2, part = i & 3;
+            *reinterpret_cast<uint4*>(out + (long long)r * L.bpitch + part * 16) = reinterpret_cast<const uint4*>(s_sc)[r * 4 + part];
+        }
+    } else {
+        for (int i = tid; i < vh * vw; i += 256) { const int r = i / vw, c = i - r * vw; out[(long long)r * L.bpitch + c] = s_sc[r * TL_W + c]; }
+    }
+}
+
+constexpr int FAST_MAXC = 60;                 // wCell, hCell < 60 (ceil(w / floor(w/30)) < 60)
+constexpr int FAST_TP = FAST_MAXC + 4;        // pitch of the per-cell score tile (1-px zero halo)
+
+// One CTA per cell: in-cell NMS + ordered compaction on the score map.  Equivalent to the reference's per-cell
+// cv::FAST(th=20) with fallback cv::FAST(th=7) (ORBextractor.cc:809-816): NMS inside the cell's detection area with
 // outside pixels = 0, keep survivors >= iniTh or, if none, all survivors (SURVEY.md A.3 [probe]).
-__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g, OrbWs ws, View v) {
-    __shared__ uint8_t s_img[(FAST_MAXC + 6) * FAST_TP];
+__global__ void __launch_bounds__(128) k_fast_cells(const __grid_constant__ OrbGeom g, OrbWs ws) {
     __shared__ uint8_t s_sc[(FAST_MAXC + 2) * FAST_TP];
     __shared__ int s_warp[33];
     const int cell = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
@@ -166,28 +302,20 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
     const int cw = maxX - iniX, ch = maxY - iniY;
     if (iniX >= L.maxBX - 6 || iniY >= L.maxBY - 3 || cw < 7 || ch < 7) { if (tid == 0) *cnt_out = 0; return; }
     const int aw = cw - 6, ah = ch - 6, area = aw * ah;
-    int pitch;
-    const uint8_t* img = level_ptr(g, ws, v, l, f, &pitch);
-    img += (long long)iniY * pitch + iniX;
-    for (int i = tid; i < cw * ch; i += 256) { int y = i / cw, x = i - y * cw; s_img[y * FAST_TP + x] = __ldg(img + (long long)y * pitch + x); }
-    for (int i = tid; i < (aw + 2) * (ah + 2); i += 256) {       // zero halo of the score map
-        int y = i / (aw + 2), x = i - y * (aw + 2);
-        if (y == 0 || y == ah + 1 || x == 0 || x == aw + 1) s_sc[y * FAST_TP + x] = 0;
+    const uint8_t* sc = ws.score + (long long)f * g.blur_stride + L.blur_off + (long long)(iniY + 3) * L.bpitch + iniX + 3;
+    for (int i = tid; i < (aw + 2) * (ah + 2); i += 128) {
+        const int y = i / (aw + 2), x = i - y * (aw + 2);
+        const bool halo = (y == 0 || y == ah + 1 || x == 0 || x == aw + 1);
+        s_sc[y * FAST_TP + x] = halo ? (uint8_t)0 : __ldg(sc + (long long)(y - 1) * L.bpitch + (x - 1));
     }
     __syncthreads();
-    for (int i = tid; i < area; i += 256) {
-        int y = i / aw, x = i - y * aw;
-        s_sc[(y + 1) * FAST_TP + x + 1] = (uint8_t)fast_score_tile(&s_img[(y + 3) * FAST_TP + x + 3], FAST_TP, g.minTh);
-    }
-    __syncthreads();
-    // NMS on this thread's contiguous raster chunk
-    const int chunk = (area + 255) / 256;                  // <= 15
+    const int chunk = (area + 127) / 128;                  // <= 28
     const int pb = min(area, tid * chunk), pe = min(area, pb + chunk);
     uint32_t m_all = 0, m_hi = 0;
     for (int p = pb; p < pe; p++) {
-        int y = p / aw, x = p - y * aw;
+        const int y = p / aw, x = p - y * aw;
         const uint8_t* c = &s_sc[(y + 1) * FAST_TP + x + 1];
-        int s = c[0];
+        const int s = c[0];
         if (s != 0 && s > c[-1] && s > c[1] && s > c[-FAST_TP - 1] && s > c[-FAST_TP] && s > c[-FAST_TP + 1] &&
             s > c[FAST_TP - 1] && s > c[FAST_TP] && s > c[FAST_TP + 1]) {
             m_all |= 1u << (p - pb);
@@ -202,8 +330,8 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
     const int ox = iniX + 3 - MINB, oy = iniY + 3 - MINB;   // coordinates relative to (minBorderX, minBorderY)
     for (int p = pb; p < pe; p++)
         if (m & (1u << (p - pb))) {
-            int y = p / aw, x = p - y * aw;
-            int s = s_sc[(y + 1) * FAST_TP + x + 1];
+            const int y = p / aw, x = p - y * aw;
+            const int s = s_sc[(y + 1) * FAST_TP + x + 1];
             if (off < L.cell_cap) out[off] = (uint32_t)(x + ox) | ((uint32_t)(y + oy) << 12) | ((uint32_t)s << 24);
             off++;
         }
@@ -433,43 +561,65 @@ __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ OrbGeom 
 // ------------------------------------------------------------------------------------------------
 // GaussianBlur 7x7 sigma 2, OpenCV 4.13 fixed-point path, BORDER_REFLECT_101
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g, OrbWs ws, View v) {
-    __shared__ uint8_t s_in[(BLUR_TH + 6) * (BLUR_TW + 8)];
-    __shared__ unsigned short s_row[(BLUR_TH + 6) * BLUR_TW];
+template <bool TMA>
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g, OrbWs ws, View v, const CUtensorMap* tm) {
+    __shared__ __align__(128) uint8_t s_img[TL_IH * TL_P];
+    __shared__ unsigned short s_row[TL_IH * TL_W];
+    __shared__ __align__(8) uint64_t s_bar;
     const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     int l = 0;
     while (l + 1 < g.nlevels && tile >= g.lv[l + 1].tile_base) l++;
     const LevelGeom& L = g.lv[l];
     const int t = tile - L.tile_base, ty = t / L.tiles_x, tx = t - ty * L.tiles_x;
-    const int x0 = tx * BLUR_TW, y0 = ty * BLUR_TH;
+    const int x0 = tx * TL_W, y0 = ty * TL_H, bx = x0 - TL_X, by = y0 - 3;
     int pitch;
     const uint8_t* img = level_ptr(g, ws, v, l, f, &pitch);
-    constexpr int IW = BLUR_TW + 6, IP = BLUR_TW + 8, IH = BLUR_TH + 6;
-    for (int i = tid; i < IW * IH; i += 256) {
-        const int yy = i / IW, xx = i - yy * IW;
-        const int sx = reflect101(x0 + xx - 3, L.w), sy = reflect101(y0 + yy - 3, L.h);
-        s_in[yy * IP + xx] = __ldg(img + (long long)sy * pitch + sx);
+    const bool interior = bx >= 0 && by >= 0 && x0 + TL_W + 3 <= L.w && y0 + TL_H + 3 <= L.h;
+    if (TMA || interior) {
+        stage_box<TMA>(s_img, &s_bar, tm, img, pitch, L.w, L.h, l, f, bx, by);
+        if (!interior) {
+            // BORDER_REFLECT_101 on top of the zero-filled box: columns first (valid rows), then whole rows
+            for (int i = tid; i < TL_IH * 8; i += 256) {
+                const int r = i >> 3, k = i & 7, gy = by + r;
+                if (gy < 0 || gy >= L.h) continue;
+                const int c = k < 4 ? TL_X - 4 + k : (k - 4) + (L.w - bx);   // left halo cols (gx = x0-4..x0-1), right cols gx = w..w+3
+                const int gx = bx + c;
+                if (c >= 0 && c < TL_P && (gx < 0 || gx >= L.w)) { const int sxx = reflect101(gx, L.w) - bx; if (sxx >= 0 && sxx < TL_P) s_img[r * TL_P + c] = s_img[r * TL_P + sxx]; }
+            }
+            __syncthreads();
+            for (int i = tid; i < 6 * TL_P; i += 256) {
+                const int k = i / TL_P, c = i - k * TL_P;
+                const int r = k < 3 ? k : (k - 3) + (L.h - by);            // top halo rows 0..2, bottom rows h-by..h-by+2
+                const int gy = by + r;
+                if (r >= 0 && r < TL_IH && (gy < 0 || gy >= L.h)) { const int sr = reflect101(gy, L.h) - by; if (sr >= 0 && sr < TL_IH) s_img[r * TL_P + c] = s_img[sr * TL_P + c]; }
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int i = tid; i < TL_IH * (TL_W + 6); i += 256) {
+            const int r = i / (TL_W + 6), c = i - r * (TL_W + 6) + TL_X - 3;
+            s_img[r * TL_P + c] = __ldg(img + (long long)reflect101(by + r, L.h) * pitch + reflect101(bx + c, L.w));
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = tid; i < IH * BLUR_TW; i += 256) {
-        const int yy = i / BLUR_TW, xx = i - yy * BLUR_TW;
-        const uint8_t* p = &s_in[yy * IP + xx];
+    for (int i = tid; i < TL_IH * TL_W; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        const uint8_t* p = &s_img[r * TL_P + c + TL_X - 3];
         s_row[i] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);   // <= 65280
     }
     __syncthreads();
     uint8_t* out = ws.blur + (long long)f * g.blur_stride + L.blur_off;
-    for (int i = tid; i < BLUR_TH * (BLUR_TW / 4); i += 256) {
-        const int yy = i / (BLUR_TW / 4), x4 = (i - yy * (BLUR_TW / 4)) * 4;
+    for (int i = tid; i < TL_H * (TL_W / 4); i += 256) {
+        const int yy = i >> 4, x4 = (i & 15) * 4;
         if (y0 + yy >= L.h || x0 + x4 >= L.w) continue;
         uint32_t o4 = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const unsigned short* p = &s_row[yy * BLUR_TW + x4 + k];
-            const int s = 18 * (p[0] + p[6 * BLUR_TW]) + 34 * (p[BLUR_TW] + p[5 * BLUR_TW]) + 48 * (p[2 * BLUR_TW] + p[4 * BLUR_TW]) + 56 * p[3 * BLUR_TW];
-            o4 |= (uint32_t)((s + 32768) >> 16) << (8 * k);
+            const unsigned short* p = &s_row[yy * TL_W + x4 + k];
+            const int sum = 18 * (p[0] + p[6 * TL_W]) + 34 * (p[TL_W] + p[5 * TL_W]) + 48 * (p[2 * TL_W] + p[4 * TL_W]) + 56 * p[3 * TL_W];
+            o4 |= (uint32_t)((sum + 32768) >> 16) << (8 * k);
         }
-        uint8_t* dst = out + (long long)(y0 + yy) * L.bpitch + x0 + x4;
-        *reinterpret_cast<uint32_t*>(dst) = o4;            // bpitch is a multiple of 64; bytes past w are padding
+        *reinterpret_cast<uint32_t*>(out + (long long)(y0 + yy) * L.bpitch + x0 + x4) = o4;      // bytes past w are padding
     }
 }
 
@@ -574,6 +724,10 @@ struct sslpl_orb {
     std::vector<cudaEvent_t> ev; std::vector<const char*> ev_name; int ev_n = 0;
     int* h_err = nullptr;               // pinned
     int octree_smem = 0;
+    TMaps tm;                           // per-level tensor maps (level 0 re-encoded per call: the input view moves)
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    bool tma_levels_ok = false, use_tma = true;
+    const uint8_t* tm0_base = nullptr; int tm0_pitch = 0, tm0_frames = 0; long long tm0_fs = 0;
 };
 
 namespace {
@@ -609,7 +763,7 @@ void make_geometry(const sslpl_orb* h, int W, int H, OrbGeom& g, std::vector<int
     g.nlevels = L; g.iniTh = h->p.iniThFAST; g.minTh = h->p.minThFAST;
     for (int i = 0; i < 16; i++) g.umax[i] = h->umax[i];
     long long pyr = 0, blur = 0, cand = 0, key = 0, pool = 0;
-    int cells = 0, tiles = 0, kpc = 0, rt = 0, maxN = 2;
+    int cells = 0, tiles = 0, kpc = 0, rt = 0, maxN = 2, fst = 0;
     for (int l = 0; l < L; l++) {
         LevelGeom& G = g.lv[l];
         G.w = cvRoundF((float)W * h->invscale[l]); G.h = cvRoundF((float)H * h->invscale[l]);     // ORBextractor.cc:1111-1112
@@ -633,9 +787,11 @@ void make_geometry(const sslpl_orb* h, int W, int H, OrbGeom& g, std::vector<int
         G.xtab_off = rt; rt += G.w; G.ytab_off = rt; rt += G.h;
         G.tiles_x = (G.w + BLUR_TW - 1) / BLUR_TW; G.tiles_y = (G.h + BLUR_TH - 1) / BLUR_TH;
         G.tile_base = tiles; tiles += G.tiles_x * G.tiles_y;
+        G.fs_tx = G.ncells ? (G.maxBX - MINB + TL_W - 1) / TL_W : 0; G.fs_ty = G.ncells ? (G.maxBY - MINB + TL_H - 1) / TL_H : 0;
+        G.fs_base = fst; fst += G.fs_tx * G.fs_ty;
         G.scale = h->scale[l]; G.patch_size = (float)(int)(31 * h->scale[l]);                      // :836 (int truncation)
     }
-    g.total_cells = cells; g.total_tiles = tiles; g.kp_total_cap = kpc;
+    g.total_cells = cells; g.total_tiles = tiles; g.kp_total_cap = kpc; g.total_fs_tiles = fst;
     g.pyr_stride = pyr; g.blur_stride = blur; g.cand_stride = cand; g.key_stride = key; g.pool_stride = pool;
     int sc = 2; while (sc < maxN) sc <<= 1;
     g.sort_cap = sc;
@@ -664,6 +820,7 @@ int carve(sslpl_orb* h, Arena& A, const OrbGeom& g, int B, int W, int H) {
     h->d_input = A.take<uint8_t>((size_t)B * align_up(W, 16) * H + 256);
     ws.pyr = A.take<uint8_t>((size_t)B * g.pyr_stride + 256);
     ws.blur = A.take<uint8_t>((size_t)B * g.blur_stride + 256);
+    ws.score = A.take<uint8_t>((size_t)B * g.blur_stride + 256);
     ws.cand = A.take<uint32_t>((size_t)B * g.cand_stride);
     ws.cell_cnt = A.take<int>((size_t)B * g.total_cells);
     ws.cell_off = A.take<int>((size_t)B * g.total_cells);
@@ -684,7 +841,23 @@ int carve(sslpl_orb* h, Arena& A, const OrbGeom& g, int B, int W, int H) {
     ws.kps = A.take<sslpl_keypoint>((size_t)B * g.kp_total_cap);
     ws.desc = A.take<uint8_t>((size_t)B * g.kp_total_cap * 32);
     ws.nkp = A.take<int>(B);
+    ws.tmaps = A.take<CUtensorMap>(MAXL);
     return 0;
+}
+
+// 3-D u8 tensor map (x, y, frame) with an 80x38x1 box; returns false when the driver entry point is missing or the
+// view does not satisfy TMA's 16-byte alignment rules (then the kernels fall back to ordinary loads).
+bool encode_level_map(sslpl_orb* h, CUtensorMap* out, const uint8_t* base, int w, int hgt, int pitch, long long frame_stride, int frames) {
+    if (!h->encode) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || (frame_stride & 15) || w < 1 || hgt < 1 || frames < 1) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)hgt, (cuuint64_t)frames};
+    const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)TL_P, (cuuint32_t)TL_IH, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = h->encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
 }
 
 int configure(sslpl_orb* h, int W, int H) {
@@ -703,6 +876,13 @@ int configure(sslpl_orb* h, int W, int H) {
     SSLPL_CUDA(cudaMemset(h->ws.err, 0, sizeof(int)));
     h->octree_smem = h->g.sort_cap * 8;
     SSLPL_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(h->octree_smem, 1024)));
+    h->tma_levels_ok = h->encode != nullptr;
+    memset(&h->tm, 0, sizeof(h->tm));
+    for (int l = 1; l < h->g.nlevels && h->tma_levels_ok; l++)
+        h->tma_levels_ok = encode_level_map(h, &h->tm.lvl[l], h->ws.pyr + h->g.lv[l].img_off, h->g.lv[l].w, h->g.lv[l].h, h->g.lv[l].pitch,
+                                            h->g.pyr_stride, h->p.max_batch);
+    if (h->tma_levels_ok) SSLPL_CUDA(cudaMemcpy(h->ws.tmaps, &h->tm, sizeof(h->tm), cudaMemcpyHostToDevice));
+    h->tm0_base = nullptr;
     h->cur_w = W; h->cur_h = H;
     return SSLPL_OK;
 }
@@ -726,11 +906,28 @@ int run_pipeline(sslpl_orb* h, int B) {
         h->launches++;
     }
     mark(h, "pyramid");
-    if (g.total_cells > 0) { k_fast<<<dim3(g.total_cells, B), 256, 0, st>>>(g, h->ws, h->view); h->launches++; }
-    mark(h, "fast");
+    bool tma = h->use_tma && h->tma_levels_ok;
+    if (tma && !(h->tm0_base == h->view.base && h->tm0_pitch == h->view.pitch && h->tm0_fs == h->view.frame_stride && h->tm0_frames >= B)) {
+        // level 0 is the caller's buffer: (re-)encode its map when the view moves
+        tma = encode_level_map(h, &h->tm.lvl[0], h->view.base, g.lv[0].w, g.lv[0].h, h->view.pitch, h->view.frame_stride, B);
+        if (tma) {
+            SSLPL_CUDA(cudaMemcpyAsync(h->ws.tmaps, &h->tm.lvl[0], sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+            h->tm0_base = h->view.base; h->tm0_pitch = h->view.pitch; h->tm0_fs = h->view.frame_stride; h->tm0_frames = B;
+        } else h->tm0_base = nullptr;
+    }
+    if (g.total_cells > 0) {
+        if (tma) k_fast_score<true><<<dim3(g.total_fs_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
+        else k_fast_score<false><<<dim3(g.total_fs_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
+        mark(h, "fast_score");
+        k_fast_cells<<<dim3(g.total_cells, B), 128, 0, st>>>(g, h->ws);
+        h->launches += 2;
+    }
+    mark(h, "fast_cells");
     k_octree<<<dim3(g.nlevels, B), 256, h->octree_smem, st>>>(g, h->ws); h->launches++;
     mark(h, "octree");
-    k_blur<<<dim3(g.total_tiles, B), 256, 0, st>>>(g, h->ws, h->view); h->launches++;
+    if (tma) k_blur<true><<<dim3(g.total_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
+    else k_blur<false><<<dim3(g.total_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
+    h->launches++;
     mark(h, "blur");
     k_orient_desc<<<dim3((g.kp_total_cap + 7) / 8, B), 256, 0, st>>>(g, h->ws, h->view); h->launches++;
     mark(h, "orient_desc");
@@ -781,6 +978,14 @@ int sslpl_orb_create(const sslpl_orb_params* p, sslpl_orb** out) {
     SSLPL_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     SSLPL_CUDA(cudaHostAlloc((void**)&h->h_err, sizeof(int), cudaHostAllocDefault));
+    {   // TMA descriptors are encoded by the driver; resolve the entry point through the runtime (no libcuda link)
+        void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            h->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+        else cudaGetLastError();
+        const char* e = getenv("SSLPL_NO_TMA");
+        h->use_tma = !(e && e[0] == '1');
+    }
     *out = h;
     return SSLPL_OK;
 }

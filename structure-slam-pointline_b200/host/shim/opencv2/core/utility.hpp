@@ -1,0 +1,3 @@
+#pragma once
+#include <opencv2/core/core.hpp>
+

@@ -73,3 +73,18 @@ def test_feature_vector_csr_matches_oracle_helper(pkg, oracle):
     for k in range(len(ids)):
         seg = idx[off[k]:off[k + 1]]
         assert np.all(node[seg] == ids[k]) and np.all(np.diff(seg) > 0)       # ascending feature indices (FeatureVector.cpp:31-45)
+
+
+def test_orbextractor_adapter_compiles_against_shim():
+    """host/ORBextractor.{h,cc} (the reference's class signature over the C ABI) type-checks against the minimal OpenCV
+    shim in host/shim (no OpenCV C++ in this image).  The two adapters that include the reference's own headers
+    (ExtractLineSegment_b200.cc, matcher_b200.cc) can only be compiled inside the reference tree."""
+    H = os.path.join(ROOT, "structure-slam-pointline_b200", "host")
+    r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-Wall", "-I", os.path.join(H, "shim"), "-I", H,
+                        "-I", os.path.join(ROOT, "include"), os.path.join(H, "ORBextractor.cc")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    hdr = open(os.path.join(H, "ORBextractor.h")).read()
+    for sig in ["ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST)",
+                "void operator()( cv::InputArray image, cv::InputArray mask,", "std::vector<cv::Mat> mvImagePyramid;",
+                "GetScaleFactors()", "GetInverseScaleSigmaSquares()"]:
+        assert sig in hdr, sig

@@ -102,3 +102,18 @@ def test_batch_equals_single(pkg, oracle, synth):
         assert n[f] == len(ok)
         assert kps[f, :n[f]].tobytes() == ok.tobytes()
         assert np.array_equal(desc[f, :n[f]], od)
+
+
+def test_non_tma_fallback_path(pkg, oracle, synth, icl_gray, monkeypatch):
+    """The tile kernels stage their input with TMA (cp.async.bulk.tensor) by default; SSLPL_NO_TMA=1 and views that
+    violate TMA's 16-byte rules use ordinary loads.  Both must give the oracle's result."""
+    monkeypatch.setenv("SSLPL_NO_TMA", "1")
+    ext = pkg.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480)
+    monkeypatch.delenv("SSLPL_NO_TMA")
+    orc = oracle.OrbOracle(1000, 1.2, 8, 20, 7)
+    _compare_all(ext, orc, icl_gray, "no-tma")
+    _compare_all(ext, orc, synth.frame(640, 480, 2), "no-tma-syn")
+    # a width that is not a multiple of 16 forces the fallback for level 0 on a TMA-enabled handle
+    ext2 = pkg.ORBextractor(800, 1.2, 8, 20, 7, max_width=700, max_height=500)
+    img = synth.frame(640, 480, 4)[:, :613]
+    _compare_all(ext2, oracle.OrbOracle(800, 1.2, 8, 20, 7), np.ascontiguousarray(img), "w613")
