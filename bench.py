@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--workload", default="batch640", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lines", action="store_true", help="ORB + point matching only")
+    ap.add_argument("--line-ring", type=int, default=6, help="line handles (streams + workspaces) kept in flight")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = WORKLOADS[args.workload]
@@ -189,16 +190,20 @@ def main():
     B = Bf + 1                                          # + halo frame (first frame of the next rank's block)
     ext = pkg.ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B, device=local)
     mt = pkg.Matcher(max_features=ext.cap, max_lines=NL, max_nodes=NWORDS, max_batch=B, device=local)
-    ls = pkg.LineSegment(NL, max_width=W, max_height=H, max_batch=B, device=local) if LINES else None
-    lmt = pkg.Matcher(max_features=64, max_lines=NL, max_nodes=2, max_batch=B, device=local) if LINES else None
-    # two explicit streams: points (ORB + BoW matching + NCCL waits + timing events) and lines (LSD/LBD + line matching);
-    # the latency-bound LSD region walker (one warp per frame) overlaps with the wide ORB kernels
-    s_pts = torch.cuda.Stream(device=dev); s_lin = torch.cuda.Stream(device=dev)
+    # Lines: the LSD region walker is order-dependent inside a frame (one warp per frame, latency-bound), so a single
+    # batch leaves most of the GPU idle.  A ring of R line handles (own stream + workspace each) keeps the walkers of R
+    # consecutive steps in flight while the wide ORB kernels of later steps run — multi-stream pipelining, nothing is skipped:
+    # every step's line results are finished (and gathered) before the timed region ends.
+    R = max(1, args.line_ring) if LINES else 0
+    lsr = [pkg.LineSegment(NL, max_width=W, max_height=H, max_batch=B, device=local) for _ in range(R)]
+    lmr = [pkg.Matcher(max_features=64, max_lines=NL, max_nodes=2, max_batch=B, device=local) for _ in range(R)]
+    s_pts = torch.cuda.Stream(device=dev)               # points: ORB + BoW matching + NCCL + timing events
+    s_lin = [torch.cuda.Stream(device=dev) for _ in range(R)]
     torch.cuda.set_stream(s_pts)
-    assert s_pts.cuda_stream != 0 and s_lin.cuda_stream != 0
+    assert s_pts.cuda_stream != 0
     ext.set_stream(s_pts.cuda_stream); mt.set_stream(s_pts.cuda_stream)
-    if LINES:
-        ls.set_stream(s_lin.cuda_stream); lmt.set_stream(s_lin.cuda_stream)
+    for r in range(R):
+        lsr[r].set_stream(s_lin[r].cuda_stream); lmr[r].set_stream(s_lin[r].cuda_stream)
     cap = ext.cap
     voc = synth.vocabulary(NWORDS)
     d_voc = torch.from_numpy(voc).to(dev)
@@ -207,33 +212,49 @@ def main():
     d_sets = [torch.from_numpy(s).to(dev) for s in sets]
     d_match = torch.empty((Bf, cap), dtype=torch.int32, device=dev)
     d_nmatch = torch.empty((Bf,), dtype=torch.int32, device=dev)
-    d_lmatch = torch.empty((Bf, NL), dtype=torch.int32, device=dev)
-    d_nlmatch = torch.zeros((Bf,), dtype=torch.int32, device=dev)
+    d_lmatch = [torch.empty((Bf, NL), dtype=torch.int32, device=dev) for _ in range(R)]
+    d_nlmatch = [torch.zeros((Bf,), dtype=torch.int32, device=dev) for _ in range(R)]
     d_gather = torch.empty((world * Bf, cap), dtype=torch.int32, device=dev) if world > 1 else None
     d_lgather = torch.empty((world * Bf, NL), dtype=torch.int32, device=dev) if world > 1 else None
+    pending = [False] * R
+    ev_free = [torch.cuda.Event() for _ in range(R)]    # slot r's tables have been consumed (gathered) on s_pts
 
-    def enqueue_lines(ptr):
-        ls.extract_batch_device(ptr, B, W, H, W, W * H)
-        _, ldesc, _, nl, capl = ls.device_results()
-        lmt.match_lines_batch_device(ldesc, nl, B, capl, d_lmatch.data_ptr(), d_nlmatch.data_ptr())
+    def finalize_slot(r):
+        """Join slot r's line results into the points stream (and gather them across ranks)."""
+        if not pending[r]:
+            return
+        s_pts.wait_stream(s_lin[r])
+        if world > 1:
+            dist.all_gather_into_tensor(d_lgather, d_lmatch[r])
+            ev_free[r].record(s_pts)
+        pending[r] = False
+
+    def enqueue_lines_device(r, ptr):
+        if world > 1:
+            s_lin[r].wait_event(ev_free[r])
+        lsr[r].extract_batch_device(ptr, B, W, H, W, W * H)
+        _, ldesc, _, nl, capl = lsr[r].device_results()
+        lmr[r].match_lines_batch_device(ldesc, nl, B, capl, d_lmatch[r].data_ptr(), d_nlmatch[r].data_ptr())
+        pending[r] = True
 
     def enqueue_points():
         kps, desc, n, c = ext.device_results()
         mt.match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match.data_ptr(), d_nmatch.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(d_gather, d_match)
 
     def step_device(i):
         fr = d_sets[i % nsets]
         if LINES:
-            s_lin.wait_stream(s_pts)                    # the previous step's readers of d_lmatch are done
-            enqueue_lines(fr.data_ptr())
+            r = i % R
+            finalize_slot(r)
+            enqueue_lines_device(r, fr.data_ptr())
         ext.extract_batch_device(fr.data_ptr(), B, W, H, W, W * H)
         enqueue_points()
-        if LINES:
-            s_pts.wait_stream(s_lin)
-        if world > 1:
-            dist.all_gather_into_tensor(d_gather, d_match)
-            if LINES:
-                dist.all_gather_into_tensor(d_lgather, d_lmatch)
+
+    def drain():
+        for r in range(R):
+            finalize_slot(r)
 
     def barrier():
         if world > 1:
@@ -241,11 +262,12 @@ def main():
         torch.cuda.synchronize()
 
     def launches_now():
-        return ext.launch_count + mt.launch_count + (ls.launch_count + lmt.launch_count if LINES else 0)
+        return ext.launch_count + mt.launch_count + sum(l.launch_count for l in lsr) + sum(m.launch_count for m in lmr)
 
     # ---- warm-up, then K timed steps, device-resident inputs ----
     for i in range(args.warmup):
         step_device(i)
+    drain()
     ext.sync()
     launches0 = launches_now()
     sampler = ClockSampler(local)
@@ -256,55 +278,68 @@ def main():
     e0.record()
     for i in range(args.steps):
         step_device(args.warmup + i)
+    drain()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
     ext.sync()
-    if LINES:
-        ls.sync()
+    for l in lsr:
+        l.sync()
     launches = launches_now() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: pinned host frames -> H2D -> kernels -> D2H of keypoints, descriptors, lines, counts, match tables ----
     h_sets = []
-    for s in sets[:min(nsets, 2)]:
+    for s in sets:
         hp = pkg.host_alloc(s.shape, np.uint8); hp[...] = s; h_sets.append(hp)
     h_out = (pkg.host_alloc((B, cap), pkg.KEYPOINT_DTYPE), pkg.host_alloc((B, cap, 32), np.uint8), pkg.host_alloc((B,), np.int32))
-    h_lout = (pkg.host_alloc((B, NL), pkg.KEYLINE_DTYPE), pkg.host_alloc((B, NL, 32), np.uint8),
-              pkg.host_alloc((B, NL, 3), np.float64), pkg.host_alloc((B,), np.int32)) if LINES else None
+    h_lout = [(pkg.host_alloc((B, NL), pkg.KEYLINE_DTYPE), pkg.host_alloc((B, NL, 32), np.uint8),
+               pkg.host_alloc((B, NL, 3), np.float64), pkg.host_alloc((B,), np.int32)) for _ in range(R)]
     h_match = torch.empty((Bf, cap), dtype=torch.int32).pin_memory(); h_nmatch = torch.empty((Bf,), dtype=torch.int32).pin_memory()
-    h_lmatch = torch.empty((Bf, NL), dtype=torch.int32).pin_memory(); h_nlmatch = torch.zeros((Bf,), dtype=torch.int32).pin_memory()
+    h_lmatch = [torch.empty((Bf, NL), dtype=torch.int32).pin_memory() for _ in range(R)]
+    h_nlmatch = [torch.zeros((Bf,), dtype=torch.int32).pin_memory() for _ in range(R)]
+    e2e_pending = [False] * R
+
+    def e2e_finalize(r):
+        """Host-side completion of slot r: wait for its stream, then the results are in the pinned host buffers."""
+        if not e2e_pending[r]:
+            return 0
+        if world > 1:
+            s_pts.wait_stream(s_lin[r])
+            dist.all_gather_into_tensor(d_lgather, d_lmatch[r])
+            ev_free[r].record(s_pts)
+        lsr[r].sync()                                                          # stream sync + deferred device error check
+        e2e_pending[r] = False
+        return int(h_lout[r][3][:Bf].sum()) + int(h_nlmatch[r].sum())
 
     def step_e2e(i):
-        fr = h_sets[i % len(h_sets)]
-        if LINES:                                                             # host API: H2D + kernels + D2H, synchronous
-            s_lin.wait_stream(s_pts)
-            ls.extract_batch(fr, out=h_lout)
-            _, ldesc, _, nl, capl = ls.device_results()
-            lmt.match_lines_batch_device(ldesc, nl, B, capl, d_lmatch.data_ptr(), d_nlmatch.data_ptr())
-        ext.extract_batch(fr, out=h_out)
+        fr = h_sets[i % nsets]
+        u = 0
+        if LINES:
+            r = i % R
+            u += e2e_finalize(r)
+            if world > 1:
+                s_lin[r].wait_event(ev_free[r])
+            lsr[r].extract_batch_begin(fr, h_lout[r])                          # H2D + kernels + D2H enqueued on slot r's stream
+            _, ldesc, _, nl, capl = lsr[r].device_results()
+            lmr[r].match_lines_batch_device(ldesc, nl, B, capl, d_lmatch[r].data_ptr(), d_nlmatch[r].data_ptr())
+            with torch.cuda.stream(s_lin[r]):
+                h_lmatch[r].copy_(d_lmatch[r], non_blocking=True); h_nlmatch[r].copy_(d_nlmatch[r], non_blocking=True)
+            e2e_pending[r] = True
+        ext.extract_batch_begin(fr, h_out)                                     # H2D + kernels + D2H on the points stream
         enqueue_points()
-        if LINES:
-            s_pts.wait_stream(s_lin)
-        if world > 1:
-            dist.all_gather_into_tensor(d_gather, d_match)
-            if LINES:
-                dist.all_gather_into_tensor(d_lgather, d_lmatch)
         h_match.copy_(d_match, non_blocking=True); h_nmatch.copy_(d_nmatch, non_blocking=True)
-        if LINES:
-            h_lmatch.copy_(d_lmatch, non_blocking=True); h_nlmatch.copy_(d_nlmatch, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        u = int(h_out[2][:Bf].sum()) + int(h_nmatch.sum())
-        if LINES:
-            u += int(h_lout[3][:Bf].sum()) + int(h_nlmatch.sum())
-        return u
+        ext.sync()
+        return u + int(h_out[2][:Bf].sum()) + int(h_nmatch.sum())
 
-    per_set = [step_e2e(s) for s in range(nsets)] if nsets <= len(h_sets) else None     # also the units of every input set
-    if per_set is None:
-        per_set = []
-        for s in range(nsets):
-            hp = pkg.host_alloc(sets[s].shape, np.uint8); hp[...] = sets[s]; h_sets.append(hp)
-        per_set = [step_e2e(s) for s in range(nsets)]
+    def e2e_drain():
+        return sum(e2e_finalize(r) for r in range(R))
+
+    # units of every distinct input set (untimed): one synchronous pass per set
+    per_set = []
+    for sidx in range(nsets):
+        u = step_e2e(sidx) + e2e_drain()
+        per_set.append(u)
     nkp_avg = float(np.mean(h_out[2][:Bf]))
     units = sum(per_set[(args.warmup + i) % nsets] for i in range(args.steps))
     t = torch.tensor([ms_total, float(units)], dtype=torch.float64, device=dev)
@@ -318,11 +353,13 @@ def main():
 
     for i in range(args.warmup):
         step_e2e(i)
+    e2e_drain()
     barrier()
     e0.record()
     eu = 0
     for i in range(args.steps):
         eu += step_e2e(args.warmup + i)
+    eu += e2e_drain()
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 0.0)
@@ -343,7 +380,7 @@ def main():
         acc = {}
         nprof = 5
         for i in range(nprof):
-            step_device(i); ext.sync()
+            step_device(i); drain(); ext.sync()
             for k, v in ext.stage_ms().items():
                 acc[k] = acc.get(k, 0.0) + v / nprof
         ext.set_profiling(False)
@@ -392,7 +429,7 @@ def main():
                 "dtype": "u8", "data": "synthetic",
                 "config": {"workload": args.workload, "width": W, "height": H, "nfeatures": NF, "nlevels": 8,
                            "frames_per_gpu": Bf, "halo_frames_per_gpu": 1, "pairs_per_gpu": Bf, "vocabulary_nodes": NWORDS,
-                           "lines": NL if LINES else 0, "parallelism": f"frames sharded x{world}, all_gather(match tables)",
+                           "lines": NL if LINES else 0, "line_ring": R, "parallelism": f"frames sharded x{world}, all_gather(match tables)",
                            "l2": f"inputs cycle through {nsets} distinct batches ({nsets * B * W * H / 1e6:.0f} MB > 126 MB L2)"},
                 "e2e": {"value": eu_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps},

@@ -84,6 +84,10 @@ int  sslpl_orb_extract(sslpl_orb* h, const uint8_t* img, int width, int height, 
 /* Batched frames, HOST buffers: frame f at imgs + f*frame_stride; outputs kps[f*cap + i], desc[(f*cap+i)*32], n[f]. */
 int  sslpl_orb_extract_batch(sslpl_orb* h, const uint8_t* imgs, int nframes, int width, int height, int pitch,
                              size_t frame_stride, sslpl_keypoint* kps, uint8_t* desc, int cap, int* n);
+/* Asynchronous form of the above: enqueues H2D + extraction + D2H on the handle's stream and returns; the host buffers
+   (pinned, see sslpl_host_alloc) are valid after sslpl_orb_sync().  Needs cap >= sslpl_orb_max_keypoints(). */
+int  sslpl_orb_extract_batch_begin(sslpl_orb* h, const uint8_t* imgs, int nframes, int width, int height, int pitch,
+                                   size_t frame_stride, sslpl_keypoint* kps, uint8_t* desc, int cap, int* n);
 /* Batched frames already resident in HBM; results stay in HBM (see sslpl_orb_device_results). Asynchronous. */
 int  sslpl_orb_extract_batch_device(sslpl_orb* h, const uint8_t* d_imgs, int nframes, int width, int height, int pitch,
                                     size_t frame_stride);
@@ -194,6 +198,9 @@ int  sslpl_line_extract(sslpl_line* h, const uint8_t* img, int width, int height
                         sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int cap, int* n);
 int  sslpl_line_extract_batch(sslpl_line* h, const uint8_t* imgs, int nframes, int width, int height, int pitch,
                               size_t frame_stride, sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int cap, int* n);
+/* asynchronous form (finish with sslpl_line_sync) */
+int  sslpl_line_extract_batch_begin(sslpl_line* h, const uint8_t* imgs, int nframes, int width, int height, int pitch,
+                                    size_t frame_stride, sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int cap, int* n);
 int  sslpl_line_extract_batch_device(sslpl_line* h, const uint8_t* d_imgs, int nframes, int width, int height, int pitch,
                                      size_t frame_stride);
 int  sslpl_line_device_results(sslpl_line* h, const sslpl_keyline** d_kl, const uint8_t** d_ldesc, const double** d_lineeq,

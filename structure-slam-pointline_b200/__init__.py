@@ -177,6 +177,13 @@ class ORBextractor:
                                              _p(kps), _p(desc), self.cap, _p(n)))
         return kps, desc, n
 
+    def extract_batch_begin(self, frames, out):
+        """Asynchronous host-buffer form: returns immediately; `out` (pinned) is valid after sync()."""
+        B, H, W = frames.shape
+        kps, desc, n = out
+        _check(lib().sslpl_orb_extract_batch_begin(self._h, _p(frames), B, W, H, frames.strides[1], C.c_size_t(frames.strides[0]),
+                                                   _p(kps), _p(desc), self.cap, _p(n)))
+
     def extract_batch_device(self, d_ptr, nframes, width, height, pitch, frame_stride):
         """Frames already in HBM (raw device pointer, e.g. torch_tensor.data_ptr()); asynchronous."""
         _check(lib().sslpl_orb_extract_batch_device(self._h, C.c_void_p(d_ptr), nframes, width, height, pitch,
@@ -454,6 +461,12 @@ class LineSegment:
         _check(lib().sslpl_line_extract_batch(self._h, _p(frames), B, W, H, frames.strides[1], C.c_size_t(frames.strides[0]),
                                               _p(kl), _p(ld), _p(eq), self.cap, _p(n)))
         return kl, ld, eq, n
+
+    def extract_batch_begin(self, frames, out):
+        B, H, W = frames.shape
+        kl, ld, eq, n = out
+        _check(lib().sslpl_line_extract_batch_begin(self._h, _p(frames), B, W, H, frames.strides[1], C.c_size_t(frames.strides[0]),
+                                                    _p(kl), _p(ld), _p(eq), self.cap, _p(n)))
 
     def extract_batch_device(self, d_ptr, nframes, width, height, pitch, frame_stride):
         _check(lib().sslpl_line_extract_batch_device(self._h, C.c_void_p(d_ptr), nframes, width, height, pitch, C.c_size_t(frame_stride)))

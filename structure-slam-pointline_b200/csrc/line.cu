@@ -2,7 +2,7 @@
 // LBD 256-bit descriptors + line equations.  Replaces LineSegment::ExtractLineSegment
 // (reference src/ExtractLineSegment.cpp:18-69, which delegates to cv::line_descriptor / cv::LineSegmentDetector).
 //
-// Per-pixel stages are ordinary data-parallel kernels (k_sep7, k_resize_exact, k_ll_angle, k_lsd_hist, k_sobel).
+// Per-pixel stages are ordinary data-parallel kernels (k_sep7, k_resize_exact, k_ll_angle, k_lsd_compact, k_lsd_nfa, k_sobel).
 // The region stage (k_lsd_regions) is order-dependent by definition (seeds in descending gradient bins, shared
 // `used` map, incrementally updated region angle): one warp walks one frame; the warp's lanes cooperate on neighbour
 // fetches and on the rectangle scans of rect_nfa, frames of a batch run on different SMs.  It is latency-bound,
@@ -45,11 +45,13 @@ struct LineGeom {
 
 struct LineWs {
     uint8_t* blur7; uint8_t* blur5; uint8_t* scaled;
-    float* angdeg; float2* cs; double* modgrad; uint8_t* used;
+    float* angdeg; float2* cs; float2* cs0; double* modgrad;
     unsigned long long* maxgrad; int* hist; unsigned* seeds; int* nseeds;
     unsigned* reg;              // region pixel list (x | y << 16)
     double* seg;                // raw rectangles: x1,y1,x2,y2 (detection scale, before +0.5)
     int* nseg;
+    double* jobs; int* njobs; int* jobflag;   // NFA jobs: 13 doubles per candidate region (LRect + log_nfa), in walker order
+    unsigned* cidx; unsigned short* cbin;     // defined pixels compacted in raster order + their gradient bins
     int16_t* dx; int16_t* dy;
     int2* tab;
     float* resp; float4* ext;   // per raw segment: response and clamped extremes
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(256) k_ll_angle(const __grid_constant__ LineGe
     bool defined = false;
     if (x < g.sw && y < g.sh) {
         const long long pi = f * g.pix_stride + (long long)y * g.sw + x;
-        float ang = NOTDEF_F; float2 cs = make_float2(0.f, 0.f);
+        float ang = NOTDEF_F; float2 cs = make_float2(0.f, 0.f), cs0 = make_float2(0.f, 0.f);
         if (x < g.sw - 1 && y < g.sh - 1) {
             const uint8_t* p = ws.scaled + f * g.scaled_stride + (long long)y * g.spitch + x;
             const int DA = (int)p[g.spitch + 1] - (int)p[0], BC = (int)p[1] - (int)p[g.spitch];
@@ -132,9 +134,11 @@ __global__ void __launch_bounds__(256) k_ll_angle(const __grid_constant__ LineGe
                 ang = fast_atan2_deg((float)gx, (float)-gy);
                 const float a = (float)((double)ang * L_DEG);
                 cs.x = (float)cos((double)a); cs.y = (float)sin((double)a);
+                const double ad = (double)ang * L_DEG;                    // region_grow's seed: float(cos(reg_angle))
+                cs0.x = (float)cos(ad); cs0.y = (float)sin(ad);
             }
         }
-        ws.angdeg[pi] = ang; ws.cs[pi] = cs; ws.modgrad[pi] = norm; ws.used[pi] = 0;
+        ws.angdeg[pi] = ang; ws.cs[pi] = cs; ws.cs0[pi] = cs0; ws.modgrad[pi] = norm;
     }
     unsigned long long bits = defined ? (unsigned long long)__double_as_longlong(norm) : 0ull;   // positive doubles order like integers
 #pragma unroll
@@ -147,20 +151,52 @@ __device__ __forceinline__ int lsd_bin(double norm, double max_grad) {
     return (int)(norm * bin_coef);
 }
 
-// histogram of the gradient bins over defined pixels (pseudo-ordering of lsd.cpp)
-__global__ void __launch_bounds__(256) k_lsd_hist(const __grid_constant__ LineGeom g, LineWs ws) {
-    const long long i = blockIdx.x * 256ll + threadIdx.x; const int f = blockIdx.y;
-    if (i >= g.pix_stride) return;
-    if (ws.angdeg[f * g.pix_stride + i] == NOTDEF_F) return;
+// Defined pixels compacted in raster order (+ their gradient bins and the bin histogram): one CTA of 32 warps per
+// frame, each warp owns a contiguous pixel range (ballot/popc ranks inside a warp, block scan across warps).
+__global__ void __launch_bounds__(1024) k_lsd_compact(const __grid_constant__ LineGeom g, LineWs ws) {
+    __shared__ int s_hist[NBINS + 1];
+    __shared__ int s_wcnt[33];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float* ang = ws.angdeg + f * g.pix_stride; const double* mod = ws.modgrad + f * g.pix_stride;
     const double mg = __longlong_as_double((long long)ws.maxgrad[f]);
-    atomicAdd(&ws.hist[f * (NBINS + 1) + (NBINS - 1 - lsd_bin(ws.modgrad[f * g.pix_stride + i], mg))], 1);
+    for (int i = tid; i <= NBINS; i += 1024) s_hist[i] = 0;
+    const long long per = ((g.pix_stride + 31) / 32 + 31) / 32 * 32;          // pixels per warp, multiple of 32
+    const long long b = wid * per, e = min(g.pix_stride, b + per);
+    int cnt = 0;
+    for (long long i = b + lane; i < b + per; i += 32) cnt += __popc(__ballot_sync(0xffffffffu, i < e && ang[i] != NOTDEF_F));
+    if (lane == 0) s_wcnt[wid] = cnt;
+    __syncthreads();
+    if (wid == 0) {
+        int v = s_wcnt[lane], inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        s_wcnt[lane] = inc - v;
+        if (lane == 31) ws.nseeds[f] = inc;
+    }
+    __syncthreads();
+    int off = s_wcnt[wid];
+    unsigned* cidx = ws.cidx + f * g.pix_stride; unsigned short* cbin = ws.cbin + f * g.pix_stride;
+    for (long long i = b + lane; i < b + per; i += 32) {
+        const bool def = i < e && ang[i] != NOTDEF_F;
+        const unsigned m = __ballot_sync(0xffffffffu, def);
+        if (def) {
+            const int bin = NBINS - 1 - lsd_bin(mod[i], mg);
+            const int o = off + __popc(m & ((1u << lane) - 1));
+            cidx[o] = (unsigned)i; cbin[o] = (unsigned short)bin;
+            atomicAdd(&s_hist[bin], 1);
+        }
+        off += __popc(m);
+    }
+    __syncthreads();
+    for (int i = tid; i <= NBINS; i += 1024) ws.hist[f * (NBINS + 1) + i] = s_hist[i];
 }
 
-// stable counting sort of the defined pixels: bins descending, raster order inside a bin.  One warp per frame.
+// stable counting sort of the compacted pixels: bins descending, raster order inside a bin.  One warp per frame over
+// ~15% of the pixels (the defined ones); ranks inside a 32-group by __match_any_sync.
 __global__ void __launch_bounds__(32) k_lsd_order(const __grid_constant__ LineGeom g, LineWs ws) {
     __shared__ int s_off[NBINS + 1];
     const int f = blockIdx.x, lane = threadIdx.x;
-    int* hist = ws.hist + f * (NBINS + 1);
+    const int* hist = ws.hist + f * (NBINS + 1);
     int carry = 0;
     for (int b0 = 0; b0 < NBINS; b0 += 32) {
         const int v = hist[b0 + lane];
@@ -170,22 +206,21 @@ __global__ void __launch_bounds__(32) k_lsd_order(const __grid_constant__ LineGe
         s_off[b0 + lane] = carry + inc - v;
         carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) ws.nseeds[f] = carry;
     __syncwarp();
-    const double mg = __longlong_as_double((long long)ws.maxgrad[f]);
+    const int n = ws.nseeds[f];
+    const unsigned* cidx = ws.cidx + f * g.pix_stride; const unsigned short* cbin = ws.cbin + f * g.pix_stride;
     unsigned* seeds = ws.seeds + f * g.pix_stride;
-    const float* ang = ws.angdeg + f * g.pix_stride; const double* mod = ws.modgrad + f * g.pix_stride;
-    for (long long base = 0; base < g.pix_stride; base += 32) {
-        const long long i = base + lane;
-        const bool def = i < g.pix_stride && ang[i] != NOTDEF_F;
-        if (!__any_sync(0xffffffffu, def)) continue;
-        const int key = def ? (NBINS - 1 - lsd_bin(mod[i], mg)) : (2048 + lane);
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const bool def = i < n;
+        const int key = def ? (int)cbin[i] : (2048 + lane);
+        const unsigned idx = def ? cidx[i] : 0u;
         const unsigned peers = __match_any_sync(0xffffffffu, key);
         const int leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1));
         int off = 0;
         if (def && lane == leader) { off = s_off[key]; s_off[key] = off + __popc(peers); }
         off = __shfl_sync(0xffffffffu, off, leader);
-        if (def) seeds[off + rank] = (unsigned)i;
+        if (def) seeds[off + rank] = idx;
         __syncwarp();
     }
 }
@@ -198,11 +233,17 @@ struct LRect { double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p; };
 
 struct Walk {
     int w, h; long long npix;
-    const float* ang; const float2* cs; const double* mod; uint8_t* used; unsigned* reg;
+    const float* ang; const float2* cs; const double* mod; unsigned* used; unsigned* reg;   // used: bitmap in SHARED memory
     double log_nt;
     const double* lgam;
+    double* st;                 // shared staging: 3 x 32 doubles (products of a 32-point chunk)
+    const float2* cs0;          // per pixel: (float)cos / sin of the level-line angle taken as double (region seed values)
     int lane;
 };
+
+__device__ __forceinline__ bool l_used(const Walk& W, long long q) { return (W.used[q >> 5] >> (q & 31)) & 1u; }
+__device__ __forceinline__ void l_set_used(const Walk& W, long long q) { atomicOr(&W.used[q >> 5], 1u << (q & 31)); }
+__device__ __forceinline__ void l_clr_used(const Walk& W, long long q) { atomicAnd(&W.used[q >> 5], ~(1u << (q & 31))); }
 
 __device__ __forceinline__ bool l_aligned(float angdeg, double theta, double prec) {
     if (angdeg == NOTDEF_F) return false;
@@ -214,35 +255,39 @@ __device__ __forceinline__ bool l_aligned(float angdeg, double theta, double pre
 }
 
 __device__ int l_region_grow(const Walk& W, int sx, int sy, double prec, double& reg_angle) {
-    const int lane = W.lane;
-    if (lane == 0) { W.reg[0] = (unsigned)sx | ((unsigned)sy << 16); W.used[(long long)sy * W.w + sx] = 1; }
-    reg_angle = (double)W.ang[(long long)sy * W.w + sx] * L_DEG;
-    float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+    const int lane = W.lane, w = W.w, h = W.h;
+    const int sq = sy * w + sx;                                   // 32-bit pixel indices (sw * sh < 2^31)
+    if (lane == 0) { W.reg[0] = (unsigned)sx | ((unsigned)sy << 16); atomicOr(&W.used[sq >> 5], 1u << (sq & 31)); }
+    reg_angle = (double)__ldg(W.ang + sq) * L_DEG;
+    const float2 c0 = __ldg(W.cs0 + sq);
+    float sumdx = c0.x, sumdy = c0.y;
     int n = 1;
+    const int ox = lane % 3 - 1, oy = lane / 3 - 1, doff = oy * w + ox;   // this lane's neighbour (yy outer, xx inner: scan order of lsd.cpp)
     __syncwarp();
     for (int i = 0; i < n; i++) {
         const unsigned pk = W.reg[i];
         const int px = pk & 0xffff, py = pk >> 16;
-        // lanes 0..8 fetch the 3x3 neighbourhood (yy outer, xx inner — the scan order of lsd.cpp)
-        const int xx = px - 1 + lane % 3, yy = py - 1 + lane / 3;
-        const bool valid = lane < 9 && xx >= 0 && yy >= 0 && xx < W.w && yy < W.h;
-        uint8_t u = 1; float a = NOTDEF_F; float2 c = make_float2(0.f, 0.f);
+        const int xx = px + ox, yy = py + oy, q = py * w + px + doff;
+        const bool valid = lane < 9 && (unsigned)xx < (unsigned)w && (unsigned)yy < (unsigned)h;
+        float a = NOTDEF_F; float2 c = make_float2(0.f, 0.f); bool u = true;
         if (valid) {
-            const long long q = (long long)yy * W.w + xx;
-            u = W.used[q]; a = W.ang[q]; c = W.cs[q];
+            a = __ldg(W.ang + q); c = __ldg(W.cs + q);
+            u = (W.used[q >> 5] >> (q & 31)) & 1u;
         }
         // Sequential semantics (each neighbour is tested once, in scan order, against the region angle as updated by
         // the neighbours accepted before it) in as many rounds as there are acceptances: all pending lanes test
         // against the current angle; the first passing lane k0 is accepted, lanes < k0 are definitively rejected
         // (they saw exactly the angle the sequential scan would have shown them).
-        unsigned pending = __ballot_sync(0xffffffffu, valid && u != 1 && a != NOTDEF_F);
+        unsigned pending = __ballot_sync(0xffffffffu, !u && a != NOTDEF_F);
         while (pending) {
             const unsigned okm = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && l_aligned(a, reg_angle, prec)) & pending;
             if (!okm) break;
             const int k0 = __ffs(okm) - 1;
             const float cx = __shfl_sync(0xffffffffu, c.x, k0), cy = __shfl_sync(0xffffffffu, c.y, k0);
-            const int nx = px - 1 + k0 % 3, ny = py - 1 + k0 / 3;
-            if (lane == 0) { W.used[(long long)ny * W.w + nx] = 1; W.reg[n] = (unsigned)nx | ((unsigned)ny << 16); }
+            if (lane == k0) {                                     // the accepted lane records its own pixel
+                W.reg[n] = (unsigned)xx | ((unsigned)yy << 16);
+                atomicOr(&W.used[q >> 5], 1u << (q & 31));
+            }
             n++;
             sumdx += cx; sumdy += cy;
             reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * L_DEG;
@@ -260,33 +305,39 @@ __device__ __forceinline__ double l_angle_diff_signed(double a, double b) {
     return d;
 }
 
-// region2rect + get_theta (lsd.cpp): three sequential passes over the region in list order
+// region2rect + get_theta (lsd.cpp).  The weighted sums must be accumulated in list order to stay bit-identical with
+// the CPU, but only the ADDS are sequential: each lane forms the products of its own point, stages them in shared
+// memory, and the warp then walks the 32 staged values with broadcast loads.  The extents are exact min/max.
 __device__ void l_region2rect(const Walk& W, int n, double reg_angle, double prec, double p, LRect& rec) {
     const int lane = W.lane;
+    double* s0 = W.st; double* s1 = W.st + 32; double* s2 = W.st + 64;
     double x = 0, y = 0, sum = 0;
     for (int b = 0; b < n; b += 32) {
         const int i = b + lane;
-        int rx = 0, ry = 0; double wg = 0;
-        if (i < n) { const unsigned pk = W.reg[i]; rx = pk & 0xffff; ry = pk >> 16; wg = W.mod[(long long)ry * W.w + rx]; }
-        const int m = min(32, n - b);
-        for (int j = 0; j < m; j++) {
-            const double xj = (double)__shfl_sync(0xffffffffu, rx, j), yj = (double)__shfl_sync(0xffffffffu, ry, j);
-            const double wj = __shfl_sync(0xffffffffu, wg, j);
-            x += xj * wj; y += yj * wj; sum += wj;
+        if (i < n) {
+            const unsigned pk = W.reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
+            const double wg = W.mod[(long long)ry * W.w + rx];
+            s0[lane] = (double)rx * wg; s1[lane] = (double)ry * wg; s2[lane] = wg;
         }
+        __syncwarp();
+        const int m = min(32, n - b);
+        for (int j = 0; j < m; j++) { x += s0[j]; y += s1[j]; sum += s2[j]; }
+        __syncwarp();
     }
     x /= sum; y /= sum;
     double Ixx = 0, Iyy = 0, Ixy = 0;
     for (int b = 0; b < n; b += 32) {
         const int i = b + lane;
-        int rx = 0, ry = 0; double wg = 0;
-        if (i < n) { const unsigned pk = W.reg[i]; rx = pk & 0xffff; ry = pk >> 16; wg = W.mod[(long long)ry * W.w + rx]; }
-        const int m = min(32, n - b);
-        for (int j = 0; j < m; j++) {
-            const double dx = (double)__shfl_sync(0xffffffffu, rx, j) - x, dy = (double)__shfl_sync(0xffffffffu, ry, j) - y;
-            const double wj = __shfl_sync(0xffffffffu, wg, j);
-            Ixx += dy * dy * wj; Iyy += dx * dx * wj; Ixy -= dx * dy * wj;
+        if (i < n) {
+            const unsigned pk = W.reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
+            const double wg = W.mod[(long long)ry * W.w + rx];
+            const double dx = (double)rx - x, dy = (double)ry - y;
+            s0[lane] = dy * dy * wg; s1[lane] = dx * dx * wg; s2[lane] = dx * dy * wg;
         }
+        __syncwarp();
+        const int m = min(32, n - b);
+        for (int j = 0; j < m; j++) { Ixx += s0[j]; Iyy += s1[j]; Ixy -= s2[j]; }
+        __syncwarp();
     }
     const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
     double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
@@ -296,18 +347,17 @@ __device__ void l_region2rect(const Walk& W, int n, double reg_angle, double pre
     // correctly-rounded cos/sin (see ddtrig.h): the extreme region pixels sit exactly on the rectangle's end edges
     double dx, dy;
     ddtrig::sincos_cr(theta, &dy, &dx);
-    double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
-    for (int b = 0; b < n; b += 32) {
-        const int i = b + lane;
-        int rx = 0, ry = 0;
-        if (i < n) { const unsigned pk = W.reg[i]; rx = pk & 0xffff; ry = pk >> 16; }
-        const int m = min(32, n - b);
-        for (int j = 0; j < m; j++) {
-            const double rdx = (double)__shfl_sync(0xffffffffu, rx, j) - x, rdy = (double)__shfl_sync(0xffffffffu, ry, j) - y;
-            const double l = rdx * dx + rdy * dy, ww = -rdx * dy + rdy * dx;
-            if (l > l_max) l_max = l; else if (l < l_min) l_min = l;
-            if (ww > w_max) w_max = ww; else if (ww < w_min) w_min = ww;
-        }
+    double l_min = 0, l_max = 0, w_min = 0, w_max = 0;           // max(0, max l), min(0, min l): order-independent
+    for (int i = lane; i < n; i += 32) {
+        const unsigned pk = W.reg[i];
+        const double rdx = (double)(pk & 0xffff) - x, rdy = (double)(pk >> 16) - y;
+        const double l = rdx * dx + rdy * dy, ww = -rdx * dy + rdy * dx;
+        l_max = fmax(l_max, l); l_min = fmin(l_min, l); w_max = fmax(w_max, ww); w_min = fmin(w_min, ww);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        l_max = fmax(l_max, __shfl_xor_sync(0xffffffffu, l_max, o)); l_min = fmin(l_min, __shfl_xor_sync(0xffffffffu, l_min, o));
+        w_max = fmax(w_max, __shfl_xor_sync(0xffffffffu, w_max, o)); w_min = fmin(w_min, __shfl_xor_sync(0xffffffffu, w_min, o));
     }
     rec.x1 = x + l_min * dx; rec.y1 = y + l_min * dy; rec.x2 = x + l_max * dx; rec.y2 = y + l_max * dy;
     rec.width = w_max - w_min; rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx; rec.dy = dy; rec.prec = prec; rec.p = p;
@@ -329,7 +379,7 @@ __device__ bool l_reduce_region_radius(const Walk& W, int& n, double reg_angle, 
             for (int i = 0; i < m; i++) {
                 const unsigned pk = W.reg[i];
                 if (l_distsq(xc, yc, (double)(pk & 0xffff), (double)(pk >> 16)) > radSq) {
-                    W.used[(long long)(pk >> 16) * W.w + (pk & 0xffff)] = 0;
+                    l_clr_used(W, (long long)(pk >> 16) * W.w + (pk & 0xffff));
                     const unsigned last = W.reg[m - 1];
                     W.reg[i] = last; W.reg[m - 1] = pk;
                     m--; i--;
@@ -354,19 +404,21 @@ __device__ bool l_refine(const Walk& W, int& n, double& reg_angle, double prec, 
     const double xc = (double)sx, yc = (double)sy;
     const double ang_c = (double)W.ang[(long long)sy * W.w + sx] * L_DEG;
     double sum = 0, s_sum = 0; int cnt = 0;
+    double* s0 = W.st; double* s1 = W.st + 32; double* s2 = W.st + 64;
     for (int b = 0; b < n; b += 32) {
         const int i = b + W.lane;
-        int rx = 0, ry = 0; float ad = 0;
-        if (i < n) { const unsigned pk = W.reg[i]; rx = pk & 0xffff; ry = pk >> 16; ad = W.ang[(long long)ry * W.w + rx]; W.used[(long long)ry * W.w + rx] = 0; }
-        const int m = min(32, n - b);
-        for (int j = 0; j < m; j++) {
-            const double xj = (double)__shfl_sync(0xffffffffu, rx, j), yj = (double)__shfl_sync(0xffffffffu, ry, j);
-            const float aj = __shfl_sync(0xffffffffu, ad, j);
-            if (l_dist(xc, yc, xj, yj) < rec.width) {
-                const double d = l_angle_diff_signed((double)aj * L_DEG, ang_c);
-                sum += d; s_sum += d * d; ++cnt;
-            }
+        if (i < n) {
+            const unsigned pk = W.reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
+            const float ad = W.ang[(long long)ry * W.w + rx];
+            l_clr_used(W, (long long)ry * W.w + rx);
+            const bool in = l_dist(xc, yc, (double)rx, (double)ry) < rec.width;
+            const double d = l_angle_diff_signed((double)ad * L_DEG, ang_c);
+            s0[W.lane] = d; s1[W.lane] = d * d; s2[W.lane] = in ? 1.0 : 0.0;
         }
+        __syncwarp();
+        const int m = min(32, n - b);
+        for (int j = 0; j < m; j++) if (s2[j] != 0.0) { sum += s0[j]; s_sum += s1[j]; ++cnt; }
+        __syncwarp();
     }
     __syncwarp();
     const double mean_angle = sum / (double)cnt;
@@ -507,42 +559,78 @@ __device__ double l_rect_improve(const Walk& W, LRect& rec) {
     return log_nfa;
 }
 
+// The order-dependent core: seeds in order, region growing, rectangle fit and the density refinement (the only steps
+// that read or write the `used` map).  rect_improve / NFA of a region is a pure function of its rectangle and of the
+// immutable angle map, so it is NOT done here: the walker emits one job per candidate region and k_lsd_nfa evaluates
+// all jobs of all frames in parallel (one warp per job).  `used` lives in shared memory as a bitmap.
 __global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ LineGeom g, LineWs ws) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    double* s_st = reinterpret_cast<double*>(s_dyn);                 // 96 doubles of staging, then the `used` bitmap
+    unsigned* s_used = reinterpret_cast<unsigned*>(s_dyn + 768);
     const int f = blockIdx.x;
     Walk W;
     W.w = g.sw; W.h = g.sh; W.npix = g.pix_stride; W.lane = threadIdx.x;
     W.ang = ws.angdeg + f * g.pix_stride; W.cs = ws.cs + f * g.pix_stride; W.mod = ws.modgrad + f * g.pix_stride;
-    W.used = ws.used + f * g.pix_stride; W.reg = ws.reg + f * g.pix_stride; W.log_nt = g.log_nt; W.lgam = ws.lgam;
+    W.used = s_used; W.reg = ws.reg + f * g.pix_stride; W.log_nt = g.log_nt; W.lgam = ws.lgam;
+    W.st = s_st; W.cs0 = ws.cs0 + f * g.pix_stride;
+    for (long long i = W.lane; i < (g.pix_stride + 31) / 32; i += 32) s_used[i] = 0u;
+    __syncwarp();
     const unsigned* seeds = ws.seeds + f * g.pix_stride;
     const int ns = ws.nseeds[f];
-    double* seg = ws.seg + (long long)f * g.seg_cap * 4;
-    int nout = 0, ntr = 0;
-    for (int s = 0; s < ns; s++) {
-        const unsigned idx = seeds[s];
-        if (W.used[idx] != 0) continue;                     // angle != NOTDEF holds for every seed
-        double reg_angle;
-        int n = l_region_grow(W, (int)(idx % (unsigned)W.w), (int)(idx / (unsigned)W.w), g.prec, reg_angle);
-        if (n < g.min_reg_size) continue;
-        LRect rec;
-        l_region2rect(W, n, reg_angle, g.prec, g.p, rec);
-        const int n0 = n;
-        const bool okr = l_refine(W, n, reg_angle, g.prec, g.p, rec, 0.7);
-        const double log_nfa = okr ? l_rect_improve(W, rec) : -1e9;
-        if (g.trace_cap) {
-            if (W.lane == 0 && ntr < g.trace_cap) {
-                double* t = ws.trace + ((long long)f * g.trace_cap + ntr) * 10;
-                t[0] = (double)idx; t[1] = (double)n0; t[2] = (double)n; t[3] = log_nfa;
-                t[4] = okr ? rec.x1 : 0; t[5] = okr ? rec.y1 : 0; t[6] = okr ? rec.x2 : 0; t[7] = okr ? rec.y2 : 0; t[8] = okr ? rec.width : 0; t[9] = okr ? rec.p : 0;
+    double* jobs = ws.jobs + (long long)f * g.seg_cap * 13;
+    int nj = 0;
+    for (int sb = 0; sb < ns; sb += 32) {
+        const unsigned mine = sb + W.lane < ns ? seeds[sb + W.lane] : 0u;       // 32 seeds per coalesced load
+        const int m = min(32, ns - sb);
+        for (int j = 0; j < m; j++) {
+            const unsigned idx = __shfl_sync(0xffffffffu, mine, j);
+            if (l_used(W, idx)) continue;                   // angle != NOTDEF holds for every seed
+            double reg_angle;
+            int n = l_region_grow(W, (int)(idx % (unsigned)W.w), (int)(idx / (unsigned)W.w), g.prec, reg_angle);
+            if (n < g.min_reg_size) continue;
+            LRect rec;
+            l_region2rect(W, n, reg_angle, g.prec, g.p, rec);
+            const int n0 = n;
+            if (!l_refine(W, n, reg_angle, g.prec, g.p, rec, 0.7)) continue;
+            if (nj < g.seg_cap && W.lane < 13) {
+                const double v[13] = {rec.x1, rec.y1, rec.x2, rec.y2, rec.width, rec.x, rec.y, rec.theta, rec.dx, rec.dy, rec.prec, rec.p, (double)idx * 65536.0 + (double)min(n0, 65535)};
+                double out = v[0];
+#pragma unroll
+                for (int k = 1; k < 13; k++) if (W.lane == k) out = v[k];
+                jobs[(long long)nj * 13 + W.lane] = out;
             }
-            ntr++;
+            nj++;
         }
-        if (!okr) continue;
-        if (log_nfa <= 0.0) continue;
-        if (nout < g.seg_cap && W.lane == 0) { seg[4 * nout] = rec.x1; seg[4 * nout + 1] = rec.y1; seg[4 * nout + 2] = rec.x2; seg[4 * nout + 3] = rec.y2; }
-        nout++;
     }
-    if (W.lane == 0 && g.trace_cap) ws.ntrace[f] = min(ntr, g.trace_cap);
-    if (W.lane == 0) { ws.nseg[f] = min(nout, g.seg_cap); if (nout > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
+    if (W.lane == 0) { ws.njobs[f] = min(nj, g.seg_cap); if (nj > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
+}
+
+// rect_improve + NFA for every candidate region of every frame: one warp per job.  Writes the refined rectangle back
+// and flags accepted jobs (log_nfa > LOG_EPS = 0).
+__global__ void __launch_bounds__(128) k_lsd_nfa(const __grid_constant__ LineGeom g, LineWs ws) {
+    const int f = blockIdx.y, j = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (j >= ws.njobs[f]) return;
+    Walk W;
+    W.w = g.sw; W.h = g.sh; W.npix = g.pix_stride; W.lane = threadIdx.x & 31;
+    W.ang = ws.angdeg + f * g.pix_stride; W.cs = nullptr; W.mod = nullptr; W.used = nullptr; W.reg = nullptr;
+    W.log_nt = g.log_nt; W.lgam = ws.lgam; W.st = nullptr; W.cs0 = nullptr;
+    double* job = ws.jobs + ((long long)f * g.seg_cap + j) * 13;
+    LRect rec;
+    rec.x1 = job[0]; rec.y1 = job[1]; rec.x2 = job[2]; rec.y2 = job[3]; rec.width = job[4]; rec.x = job[5]; rec.y = job[6];
+    rec.theta = job[7]; rec.dx = job[8]; rec.dy = job[9]; rec.prec = job[10]; rec.p = job[11];
+    const double tag = job[12];
+    const double log_nfa = l_rect_improve(W, rec);
+    __syncwarp();
+    if (W.lane == 0) {
+        job[0] = rec.x1; job[1] = rec.y1; job[2] = rec.x2; job[3] = rec.y2; job[4] = rec.width; job[11] = rec.p; job[12] = log_nfa;
+        ws.jobflag[(long long)f * g.seg_cap + j] = log_nfa > 0.0 ? 1 : 0;
+        if (g.trace_cap && j < g.trace_cap) {
+            double* t = ws.trace + ((long long)f * g.trace_cap + j) * 10;
+            const double idx = floor(tag / 65536.0);
+            t[0] = idx; t[1] = tag - idx * 65536.0; t[2] = 0; t[3] = log_nfa;
+            t[4] = rec.x1; t[5] = rec.y1; t[6] = rec.x2; t[7] = rec.y2; t[8] = rec.width; t[9] = rec.p;
+        }
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -550,9 +638,19 @@ __global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ Line
 // line equations (:56-68).  One CTA per frame.
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_keylines(const __grid_constant__ LineGeom g, LineWs ws) {
+    __shared__ int s_warp[33];
     const int f = blockIdx.x, tid = threadIdx.x;
-    const int n = ws.nseg[f];
-    const double* seg = ws.seg + (long long)f * g.seg_cap * 4;
+    // accepted jobs -> raw segment list, in detection order
+    const int nj = ws.njobs[f];
+    int* flag = ws.jobflag + (long long)f * g.seg_cap;
+    const int n = block_scan_array(flag, nj, s_warp);              // exclusive offsets in place
+    double* segw = ws.seg + (long long)f * g.seg_cap * 4;
+    const double* jobs = ws.jobs + (long long)f * g.seg_cap * 13;
+    for (int j = tid; j < nj; j += 256)
+        if (jobs[(long long)j * 13 + 12] > 0.0) { const int o = flag[j]; for (int k = 0; k < 4; k++) segw[4 * o + k] = jobs[(long long)j * 13 + k]; }
+    if (tid == 0) { ws.nseg[f] = n; if (g.trace_cap) ws.ntrace[f] = min(nj, g.trace_cap); }
+    __syncthreads();
+    const double* seg = segw;
     float* resp = ws.resp + (long long)f * g.seg_cap;
     float4* ext = ws.ext + (long long)f * g.seg_cap;
     const double SCALE = 0.8;
@@ -738,6 +836,7 @@ struct sslpl_line {
     uint8_t* d_input = nullptr;
     LbdCoef coef;
     bool trace = false;
+    int used_smem = 0;
     int cur_w = 0, cur_h = 0, cur_frames = 0;
     long long launches = 0;
     int* h_err = nullptr;
@@ -787,11 +886,13 @@ void carve(sslpl_line* h, Arena& A, const LineGeom& g, int B) {
     ws.blur7 = A.take<uint8_t>((size_t)B * g.blur_stride); ws.blur5 = A.take<uint8_t>((size_t)B * g.blur_stride);
     ws.scaled = A.take<uint8_t>((size_t)B * g.scaled_stride);
     ws.angdeg = A.take<float>((size_t)B * g.pix_stride); ws.cs = A.take<float2>((size_t)B * g.pix_stride);
-    ws.modgrad = A.take<double>((size_t)B * g.pix_stride); ws.used = A.take<uint8_t>((size_t)B * g.pix_stride);
+    ws.modgrad = A.take<double>((size_t)B * g.pix_stride); ws.cs0 = A.take<float2>((size_t)B * g.pix_stride);
     ws.maxgrad = A.take<unsigned long long>(B); ws.hist = A.take<int>((size_t)B * (NBINS + 1));
     ws.seeds = A.take<unsigned>((size_t)B * g.pix_stride); ws.nseeds = A.take<int>(B);
     ws.reg = A.take<unsigned>((size_t)B * g.pix_stride);
     ws.seg = A.take<double>((size_t)B * g.seg_cap * 4); ws.nseg = A.take<int>(B);
+    ws.jobs = A.take<double>((size_t)B * g.seg_cap * 13); ws.njobs = A.take<int>(B); ws.jobflag = A.take<int>((size_t)B * g.seg_cap);
+    ws.cidx = A.take<unsigned>((size_t)B * g.pix_stride); ws.cbin = A.take<unsigned short>((size_t)B * g.pix_stride);
     ws.dx = A.take<int16_t>((size_t)B * g.full_stride); ws.dy = A.take<int16_t>((size_t)B * g.full_stride);
     ws.tab = A.take<int2>(g.sw + g.sh);
     ws.resp = A.take<float>((size_t)B * g.seg_cap); ws.ext = A.take<float4>((size_t)B * g.seg_cap);
@@ -822,6 +923,12 @@ int configure(sslpl_line* h, int W, int H) {
     SSLPL_REQUIRE(A.used <= h->arena_size, SSLPL_ERR_CAPACITY, "internal: arena too small for this frame size");
     SSLPL_CUDA(cudaStreamSynchronize(h->stream));
     SSLPL_CUDA(cudaMemcpy(h->ws.tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    h->used_smem = (int)((h->g.pix_stride + 31) / 32 * 4) + 768;
+    SSLPL_REQUIRE(h->used_smem <= 200 * 1024, SSLPL_ERR_UNSUPPORTED, "frame too large for the shared-memory `used` bitmap of the LSD walker");
+    SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(h->used_smem, 1024)));
+    // keep as much of the unified L1 as possible for the angle / gradient maps (4 resident walkers per SM at most)
+    SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    std::min(100, (int)(100.0 * 4 * h->used_smem / (228.0 * 1024)) + 5)));
     SSLPL_CUDA(cudaMemset(h->ws.err, 0, sizeof(int)));
     {
         std::vector<double> lg((size_t)h->g.pix_stride + 2);
@@ -842,15 +949,15 @@ int run_pipeline(sslpl_line* h, int B) {
     k_sep7<<<tiles, 256, 0, st>>>(g, h->view, h->ws.blur5, g.blur_stride, t5);
     k_resize_exact<<<dim3((g.sw + 31) / 32, (g.sh + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
     SSLPL_CUDA(cudaMemsetAsync(h->ws.maxgrad, 0, sizeof(unsigned long long) * B, st));
-    SSLPL_CUDA(cudaMemsetAsync(h->ws.hist, 0, sizeof(int) * (size_t)B * (NBINS + 1), st));
     k_ll_angle<<<dim3((g.sw + 31) / 32, (g.sh + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
-    k_lsd_hist<<<dim3((unsigned)((g.pix_stride + 255) / 256), B), 256, 0, st>>>(g, h->ws);
+    k_lsd_compact<<<B, 1024, 0, st>>>(g, h->ws);
     k_lsd_order<<<B, 32, 0, st>>>(g, h->ws);
-    k_lsd_regions<<<B, 32, 0, st>>>(g, h->ws);
+    k_lsd_regions<<<B, 32, h->used_smem, st>>>(g, h->ws);
+    k_lsd_nfa<<<dim3((g.seg_cap + 3) / 4, B), 128, 0, st>>>(g, h->ws);
     k_keylines<<<B, 256, 0, st>>>(g, h->ws);
     k_sobel<<<dim3((g.w + 31) / 32, (g.h + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
     k_lbd<<<dim3(g.kl_cap, B), 64, 0, st>>>(g, h->ws, h->coef);
-    h->launches += 10;
+    h->launches += 11;
     SSLPL_CUDA(cudaGetLastError());
     return SSLPL_OK;
 }
@@ -942,8 +1049,8 @@ int sslpl_line_device_results(sslpl_line* h, const sslpl_keyline** d_kl, const u
     return SSLPL_OK;
 }
 
-int sslpl_line_extract_batch(sslpl_line* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
-                             sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int cap, int* n) {
+int sslpl_line_extract_batch_begin(sslpl_line* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
+                                   sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int cap, int* n) {
     SSLPL_REQUIRE(h && kl && ldesc && lineeq && n && imgs, SSLPL_ERR_ARG, "null argument");
     SSLPL_REQUIRE(nframes >= 1 && nframes <= h->p.max_batch && pitch >= width, SSLPL_ERR_ARG, "bad nframes / pitch");
     SSLPL_REQUIRE(cap >= h->p.lsdNFeatures, SSLPL_ERR_CAPACITY, "caller line capacity smaller than lsdNFeatures");
@@ -965,6 +1072,13 @@ int sslpl_line_extract_batch(sslpl_line* h, const uint8_t* imgs, int nframes, in
     SSLPL_CUDA(cudaMemcpy2DAsync(kl, (size_t)cap * sizeof(sslpl_keyline), h->ws.kl, (size_t)kc * sizeof(sslpl_keyline), (size_t)kc * sizeof(sslpl_keyline), nframes, cudaMemcpyDeviceToHost, h->stream));
     SSLPL_CUDA(cudaMemcpy2DAsync(ldesc, (size_t)cap * 32, h->ws.ldesc, (size_t)kc * 32, (size_t)kc * 32, nframes, cudaMemcpyDeviceToHost, h->stream));
     SSLPL_CUDA(cudaMemcpy2DAsync(lineeq, (size_t)cap * 24, h->ws.lineeq, (size_t)kc * 24, (size_t)kc * 24, nframes, cudaMemcpyDeviceToHost, h->stream));
+    return SSLPL_OK;
+}
+
+int sslpl_line_extract_batch(sslpl_line* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
+                             sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int cap, int* n) {
+    int rc = sslpl_line_extract_batch_begin(h, imgs, nframes, width, height, pitch, frame_stride, kl, ldesc, lineeq, cap, n);
+    if (rc) return rc;
     return check_device_err(h);
 }
 

@@ -1057,10 +1057,9 @@ int sslpl_orb_set_stream(sslpl_orb* h, void* cuda_stream) {
     return SSLPL_OK;
 }
 
-int sslpl_orb_extract_batch(sslpl_orb* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
-                            sslpl_keypoint* kps, uint8_t* desc, int cap, int* n) {
-    SSLPL_REQUIRE(h && kps && desc && n, SSLPL_ERR_ARG, "null argument");
-    if (!imgs || width <= 0 || height <= 0) { for (int f = 0; f < nframes; f++) n[f] = 0; return SSLPL_OK; }   // ORBextractor.cc:1046
+// Enqueue H2D of the frames, the whole extraction and the D2H of the results on the handle's stream; no host sync.
+static int orb_enqueue_host_batch(sslpl_orb* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
+                                  sslpl_keypoint* kps, uint8_t* desc, int cap, int* n, bool copy_results) {
     SSLPL_REQUIRE(nframes >= 1 && nframes <= h->p.max_batch, SSLPL_ERR_ARG, "nframes exceeds the handle's max_batch");
     SSLPL_REQUIRE(pitch >= width, SSLPL_ERR_ARG, "pitch < width");
     SSLPL_CUDA(cudaSetDevice(h->p.device));
@@ -1079,16 +1078,32 @@ int sslpl_orb_extract_batch(sslpl_orb* h, const uint8_t* imgs, int nframes, int 
     if (rc) return rc;
     const int kc = h->g.kp_total_cap;
     SSLPL_CUDA(cudaMemcpyAsync(n, h->ws.nkp, sizeof(int) * nframes, cudaMemcpyDeviceToHost, h->stream));
-    if (cap >= kc) {
+    if (copy_results) {
         SSLPL_CUDA(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(sslpl_keypoint), h->ws.kps, (size_t)kc * sizeof(sslpl_keypoint),
                                      (size_t)kc * sizeof(sslpl_keypoint), nframes, cudaMemcpyDeviceToHost, h->stream));
         SSLPL_CUDA(cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->ws.desc, (size_t)kc * 32, (size_t)kc * 32, nframes, cudaMemcpyDeviceToHost, h->stream));
-        rc = check_device_err(h);
-        return rc;
     }
-    // caller capacity smaller than the worst case: download counts first, then only what fits
-    rc = check_device_err(h);
+    return SSLPL_OK;
+}
+
+int sslpl_orb_extract_batch_begin(sslpl_orb* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
+                                  sslpl_keypoint* kps, uint8_t* desc, int cap, int* n) {
+    SSLPL_REQUIRE(h && kps && desc && n && imgs && width > 0 && height > 0, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(cap >= sslpl_orb_max_keypoints(h), SSLPL_ERR_CAPACITY, "the asynchronous form needs cap >= sslpl_orb_max_keypoints()");
+    return orb_enqueue_host_batch(h, imgs, nframes, width, height, pitch, frame_stride, kps, desc, cap, n, true);
+}
+
+int sslpl_orb_extract_batch(sslpl_orb* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
+                            sslpl_keypoint* kps, uint8_t* desc, int cap, int* n) {
+    SSLPL_REQUIRE(h && kps && desc && n, SSLPL_ERR_ARG, "null argument");
+    if (!imgs || width <= 0 || height <= 0) { for (int f = 0; f < nframes; f++) n[f] = 0; return SSLPL_OK; }   // ORBextractor.cc:1046
+    const bool fits = cap >= sslpl_orb_max_keypoints(h);
+    int rc = orb_enqueue_host_batch(h, imgs, nframes, width, height, pitch, frame_stride, kps, desc, cap, n, fits);
     if (rc) return rc;
+    rc = check_device_err(h);
+    if (rc || fits) return rc;
+    // caller capacity smaller than the worst case: counts are on the host now, download only what fits
+    const int kc = h->g.kp_total_cap;
     for (int f = 0; f < nframes; f++) SSLPL_REQUIRE(n[f] <= cap, SSLPL_ERR_CAPACITY, "caller keypoint capacity too small");
     SSLPL_CUDA(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(sslpl_keypoint), h->ws.kps, (size_t)kc * sizeof(sslpl_keypoint),
                                  (size_t)cap * sizeof(sslpl_keypoint), nframes, cudaMemcpyDeviceToHost, h->stream));
