@@ -45,7 +45,7 @@ struct LineGeom {
 
 struct LineWs {
     uint8_t* blur7; uint8_t* blur5; uint8_t* scaled;
-    float* angdeg; float2* cs; float2* cs0; double* modgrad;
+    float* angdeg; float2* cs; float2* cs0; double* modgrad; uint8_t* used;
     unsigned long long* maxgrad; int* hist; unsigned* seeds; int* nseeds;
     unsigned* reg;              // region pixel list (x | y << 16)
     double* seg;                // raw rectangles: x1,y1,x2,y2 (detection scale, before +0.5)
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) k_ll_angle(const __grid_constant__ LineGe
                 cs0.x = (float)cos(ad); cs0.y = (float)sin(ad);
             }
         }
-        ws.angdeg[pi] = ang; ws.cs[pi] = cs; ws.cs0[pi] = cs0; ws.modgrad[pi] = norm;
+        ws.angdeg[pi] = ang; ws.cs[pi] = cs; ws.cs0[pi] = cs0; ws.modgrad[pi] = norm; ws.used[pi] = 0;
     }
     unsigned long long bits = defined ? (unsigned long long)__double_as_longlong(norm) : 0ull;   // positive doubles order like integers
 #pragma unroll
@@ -233,7 +233,7 @@ struct LRect { double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p; };
 
 struct Walk {
     int w, h; long long npix;
-    const float* ang; const float2* cs; const double* mod; unsigned* used; unsigned* reg;   // used: bitmap in SHARED memory
+    const float* ang; const float2* cs; const double* mod; uint8_t* used; unsigned* reg;   // used: byte map in global memory (L1-resident; only this warp touches it)
     double log_nt;
     const double* lgam;
     double* st;                 // shared staging: 3 x 32 doubles (products of a 32-point chunk)
@@ -241,9 +241,9 @@ struct Walk {
     int lane;
 };
 
-__device__ __forceinline__ bool l_used(const Walk& W, long long q) { return (W.used[q >> 5] >> (q & 31)) & 1u; }
-__device__ __forceinline__ void l_set_used(const Walk& W, long long q) { atomicOr(&W.used[q >> 5], 1u << (q & 31)); }
-__device__ __forceinline__ void l_clr_used(const Walk& W, long long q) { atomicAnd(&W.used[q >> 5], ~(1u << (q & 31))); }
+__device__ __forceinline__ bool l_used(const Walk& W, long long q) { return W.used[q] != 0; }
+__device__ __forceinline__ void l_set_used(const Walk& W, long long q) { W.used[q] = 1; }
+__device__ __forceinline__ void l_clr_used(const Walk& W, long long q) { W.used[q] = 0; }
 
 __device__ __forceinline__ bool l_aligned(float angdeg, double theta, double prec) {
     if (angdeg == NOTDEF_F) return false;
@@ -257,7 +257,7 @@ __device__ __forceinline__ bool l_aligned(float angdeg, double theta, double pre
 __device__ int l_region_grow(const Walk& W, int sx, int sy, double prec, double& reg_angle) {
     const int lane = W.lane, w = W.w, h = W.h;
     const int sq = sy * w + sx;                                   // 32-bit pixel indices (sw * sh < 2^31)
-    if (lane == 0) { W.reg[0] = (unsigned)sx | ((unsigned)sy << 16); atomicOr(&W.used[sq >> 5], 1u << (sq & 31)); }
+    if (lane == 0) { W.reg[0] = (unsigned)sx | ((unsigned)sy << 16); W.used[sq] = 1; }
     reg_angle = (double)__ldg(W.ang + sq) * L_DEG;
     const float2 c0 = __ldg(W.cs0 + sq);
     float sumdx = c0.x, sumdy = c0.y;
@@ -272,7 +272,7 @@ __device__ int l_region_grow(const Walk& W, int sx, int sy, double prec, double&
         float a = NOTDEF_F; float2 c = make_float2(0.f, 0.f); bool u = true;
         if (valid) {
             a = __ldg(W.ang + q); c = __ldg(W.cs + q);
-            u = (W.used[q >> 5] >> (q & 31)) & 1u;
+            u = W.used[q] != 0;
         }
         // Sequential semantics (each neighbour is tested once, in scan order, against the region angle as updated by
         // the neighbours accepted before it) in as many rounds as there are acceptances: all pending lanes test
@@ -286,7 +286,7 @@ __device__ int l_region_grow(const Walk& W, int sx, int sy, double prec, double&
             const float cx = __shfl_sync(0xffffffffu, c.x, k0), cy = __shfl_sync(0xffffffffu, c.y, k0);
             if (lane == k0) {                                     // the accepted lane records its own pixel
                 W.reg[n] = (unsigned)xx | ((unsigned)yy << 16);
-                atomicOr(&W.used[q >> 5], 1u << (q & 31));
+                W.used[q] = 1;
             }
             n++;
             sumdx += cx; sumdy += cy;
@@ -514,48 +514,93 @@ __device__ double l_rect_nfa(const Walk& W, const LRect& rec) {
     return l_nfa(total, alg, rec.p, W.log_nt, W.lgam);
 }
 
-__device__ double l_rect_improve(const Walk& W, LRect& rec) {
+// Five candidate rectangles of one rect_improve phase at once: lane group g = lane / 6 (6 lanes each, lanes 30-31 idle)
+// scans candidate g's rows, the counts are combined through shared-memory atomics (exact integers), and the five
+// scalar NFA evaluations run side by side in lanes 0, 6, 12, 18, 24.  s_cnt: 10 ints of this warp.
+__device__ void l_rect_nfa5(const Walk& W, const LRect& mine, bool valid, int* s_cnt, double* out5) {
+    const int lane = W.lane, grp = lane / 6, sub = lane - grp * 6;
+    if (lane < 10) s_cnt[lane] = 0;
+    __syncwarp();
+    if (grp < 5 && valid) {
+        const LRect& rec = mine;
+        const double half_width = 0.5 * rec.width, dyhw = rec.dy * half_width, dxhw = rec.dx * half_width;
+        const double vx[4] = {rec.x1 - dyhw, rec.x2 - dyhw, rec.x2 + dyhw, rec.x1 + dyhw};
+        const double vy[4] = {rec.y1 + dxhw, rec.y2 + dxhw, rec.y2 - dxhw, rec.y1 - dxhw};
+        int off = 0;
+#pragma unroll
+        for (int i = 1; i < 4; i++) if (vy[i] < vy[off] || (vy[i] == vy[off] && vx[i] < vx[off])) off = i;
+        const double Mx = vx[off], My = vy[off], Ax = vx[(off + 1) & 3], Ay = vy[(off + 1) & 3];
+        const double Bx = vx[(off + 2) & 3], By = vy[(off + 2) & 3], Cx = vx[(off + 3) & 3], Cy = vy[(off + 3) & 3];
+        const int cM = l_x86_d2i(ceil(My)), cA = l_x86_d2i(ceil(Ay)), cB = l_x86_d2i(ceil(By)), cC = l_x86_d2i(ceil(Cy));
+        const double s1 = (cA != cM) ? (Ax - Mx) / (Ay - My) : 0.0;
+        const double s2 = (cB != cA) ? (Bx - Ax) / (By - Ay) : 0.0;
+        const double s3 = (cC != cM) ? (Cx - Mx) / (Cy - My) : 0.0;
+        const double s4 = (cB != cC) ? (Bx - Cx) / (By - Cy) : 0.0;
+        int total = 0, alg = 0;
+        const int y0 = max(cM, 0), y1 = min(cB, W.h - 1);
+        for (int y = y0 + sub; y <= y1; y += 6) {
+            const double xl = (cA < y) ? ((double)y - Ay) * s2 + Ax : ((double)y - My) * s1 + Mx;
+            const double xr = (cC <= y) ? ((double)y - Cy) * s4 + Cx : ((double)y - My) * s3 + Mx;
+            int xs = l_x86_d2i(ceil(xl));
+            int xe = l_x86_d2i(xr);
+            if (xe < xs) continue;
+            if (xs < 0) xs = 0;
+            if (xe > W.w - 1) xe = W.w - 1;
+            const float* row = W.ang + (long long)y * W.w;
+            for (int x = xs; x <= xe; ++x) { ++total; if (l_aligned(__ldg(row + x), rec.theta, rec.prec)) ++alg; }
+        }
+        if (total) atomicAdd(&s_cnt[2 * grp], total);
+        if (alg) atomicAdd(&s_cnt[2 * grp + 1], alg);
+    }
+    __syncwarp();
+    double v = 0.0;
+    if (grp < 5 && sub == 0 && valid) v = l_nfa(s_cnt[2 * grp], s_cnt[2 * grp + 1], mine.p, W.log_nt, W.lgam);
+#pragma unroll
+    for (int g5 = 0; g5 < 5; g5++) out5[g5] = __shfl_sync(0xffffffffu, v, g5 * 6);
+    __syncwarp();
+}
+
+// rect_improve (lsd.cpp): each of the five refinement phases tries a fixed sequence of five candidate rectangles that
+// does not depend on the NFA values inside the phase, so the five are evaluated at once (l_rect_nfa5) and the
+// reference's "first strict improvement wins" rule is then replayed in order.
+__device__ double l_rect_improve(const Walk& W, LRect& rec, int* s_cnt) {
     const double delta = 0.5, delta_2 = delta / 2.0;
+    const int lane = W.lane, grp = lane / 6, k = min(grp, 4) + 1;     // this lane's candidate = k-th step of the phase
     double log_nfa = l_rect_nfa(W, rec);
     if (log_nfa > 0.0) return log_nfa;
-    LRect r = rec;
-    for (int n = 0; n < 5; ++n) {
-        r.p /= 2; r.prec = r.p * L_PI;
-        const double v = l_rect_nfa(W, r);
-        if (v > log_nfa) { log_nfa = v; rec = r; }
+    double v[5];
+    for (int phase = 0; phase < 5; phase++) {
+        // candidate k of the phase, built exactly as the sequential loop would have built it
+        LRect r = rec;
+        bool valid = true;
+        if (phase == 0 || phase == 4) {
+            if (phase == 4) valid = (r.width - delta) >= 0.5;          // the guard does not change inside the loop
+            for (int i = 0; i < k; i++) { r.p /= 2; r.prec = r.p * L_PI; }
+        } else {
+            for (int i = 0; i < k; i++) {
+                if ((r.width - delta) >= 0.5) {
+                    if (phase == 2) { r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2; r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2; }
+                    if (phase == 3) { r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2; r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2; }
+                    r.width -= delta;
+                } else valid = false;                                   // this step (and all later ones) is skipped
+            }
+        }
+        l_rect_nfa5(W, r, valid, s_cnt, v);
+        // replay: for n = 1..5: if (candidate n exists && v_n > log_nfa) { log_nfa = v_n; rec = candidate n; }
+        int best = -1;
+        for (int n = 0; n < 5; n++) {
+            const bool vn = __shfl_sync(0xffffffffu, valid ? 1 : 0, n * 6) != 0;
+            if (vn && v[n] > log_nfa) { log_nfa = v[n]; best = n; }
+        }
+        if (best >= 0) {                                                // broadcast the winning candidate's fields
+            const int src = best * 6;
+            rec.x1 = __shfl_sync(0xffffffffu, r.x1, src); rec.y1 = __shfl_sync(0xffffffffu, r.y1, src);
+            rec.x2 = __shfl_sync(0xffffffffu, r.x2, src); rec.y2 = __shfl_sync(0xffffffffu, r.y2, src);
+            rec.width = __shfl_sync(0xffffffffu, r.width, src);
+            rec.p = __shfl_sync(0xffffffffu, r.p, src); rec.prec = __shfl_sync(0xffffffffu, r.prec, src);
+        }
+        if (log_nfa > 0.0) return log_nfa;
     }
-    if (log_nfa > 0.0) return log_nfa;
-    r = rec;
-    for (int n = 0; n < 5; ++n)
-        if ((r.width - delta) >= 0.5) {
-            r.width -= delta;
-            const double v = l_rect_nfa(W, r);
-            if (v > log_nfa) { rec = r; log_nfa = v; }
-        }
-    if (log_nfa > 0.0) return log_nfa;
-    r = rec;
-    for (int n = 0; n < 5; ++n)
-        if ((r.width - delta) >= 0.5) {
-            r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2; r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2; r.width -= delta;
-            const double v = l_rect_nfa(W, r);
-            if (v > log_nfa) { rec = r; log_nfa = v; }
-        }
-    if (log_nfa > 0.0) return log_nfa;
-    r = rec;
-    for (int n = 0; n < 5; ++n)
-        if ((r.width - delta) >= 0.5) {
-            r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2; r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2; r.width -= delta;
-            const double v = l_rect_nfa(W, r);
-            if (v > log_nfa) { rec = r; log_nfa = v; }
-        }
-    if (log_nfa > 0.0) return log_nfa;
-    r = rec;
-    for (int n = 0; n < 5; ++n)
-        if ((r.width - delta) >= 0.5) {
-            r.p /= 2; r.prec = r.p * L_PI;
-            const double v = l_rect_nfa(W, r);
-            if (v > log_nfa) { rec = r; log_nfa = v; }
-        }
     return log_nfa;
 }
 
@@ -564,34 +609,35 @@ __device__ double l_rect_improve(const Walk& W, LRect& rec) {
 // immutable angle map, so it is NOT done here: the walker emits one job per candidate region and k_lsd_nfa evaluates
 // all jobs of all frames in parallel (one warp per job).  `used` lives in shared memory as a bitmap.
 __global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ LineGeom g, LineWs ws) {
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    double* s_st = reinterpret_cast<double*>(s_dyn);                 // 96 doubles of staging, then the `used` bitmap
-    unsigned* s_used = reinterpret_cast<unsigned*>(s_dyn + 768);
+    __shared__ double s_st[96];                                      // staging of 32-point chunks (3 quantities)
     const int f = blockIdx.x;
     Walk W;
     W.w = g.sw; W.h = g.sh; W.npix = g.pix_stride; W.lane = threadIdx.x;
     W.ang = ws.angdeg + f * g.pix_stride; W.cs = ws.cs + f * g.pix_stride; W.mod = ws.modgrad + f * g.pix_stride;
-    W.used = s_used; W.reg = ws.reg + f * g.pix_stride; W.log_nt = g.log_nt; W.lgam = ws.lgam;
+    W.used = ws.used + f * g.pix_stride; W.reg = ws.reg + f * g.pix_stride; W.log_nt = g.log_nt; W.lgam = ws.lgam;
     W.st = s_st; W.cs0 = ws.cs0 + f * g.pix_stride;
-    for (long long i = W.lane; i < (g.pix_stride + 31) / 32; i += 32) s_used[i] = 0u;
-    __syncwarp();
     const unsigned* seeds = ws.seeds + f * g.pix_stride;
     const int ns = ws.nseeds[f];
     double* jobs = ws.jobs + (long long)f * g.seg_cap * 13;
     int nj = 0;
     for (int sb = 0; sb < ns; sb += 32) {
-        const unsigned mine = sb + W.lane < ns ? seeds[sb + W.lane] : 0u;       // 32 seeds per coalesced load
+        const bool have = sb + W.lane < ns;
+        const unsigned mine = have ? seeds[sb + W.lane] : 0u;                   // 32 seeds per coalesced load
+        unsigned umask = __ballot_sync(0xffffffffu, !have || W.used[mine] != 0); // their `used` state, one round trip
         const int m = min(32, ns - sb);
         for (int j = 0; j < m; j++) {
+            if ((umask >> j) & 1u) continue;                // angle != NOTDEF holds for every seed
             const unsigned idx = __shfl_sync(0xffffffffu, mine, j);
-            if (l_used(W, idx)) continue;                   // angle != NOTDEF holds for every seed
             double reg_angle;
             int n = l_region_grow(W, (int)(idx % (unsigned)W.w), (int)(idx / (unsigned)W.w), g.prec, reg_angle);
+            umask = __ballot_sync(0xffffffffu, !have || W.used[mine] != 0);     // the region may have swallowed later seeds
             if (n < g.min_reg_size) continue;
             LRect rec;
             l_region2rect(W, n, reg_angle, g.prec, g.p, rec);
             const int n0 = n;
-            if (!l_refine(W, n, reg_angle, g.prec, g.p, rec, 0.7)) continue;
+            const bool okr = l_refine(W, n, reg_angle, g.prec, g.p, rec, 0.7);
+            umask = __ballot_sync(0xffffffffu, !have || W.used[mine] != 0);     // refine can release and re-take pixels
+            if (!okr) continue;
             if (nj < g.seg_cap && W.lane < 13) {
                 const double v[13] = {rec.x1, rec.y1, rec.x2, rec.y2, rec.width, rec.x, rec.y, rec.theta, rec.dx, rec.dy, rec.prec, rec.p, (double)idx * 65536.0 + (double)min(n0, 65535)};
                 double out = v[0];
@@ -608,6 +654,7 @@ __global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ Line
 // rect_improve + NFA for every candidate region of every frame: one warp per job.  Writes the refined rectangle back
 // and flags accepted jobs (log_nfa > LOG_EPS = 0).
 __global__ void __launch_bounds__(128) k_lsd_nfa(const __grid_constant__ LineGeom g, LineWs ws) {
+    __shared__ int s_cnt[4][10];
     const int f = blockIdx.y, j = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (j >= ws.njobs[f]) return;
     Walk W;
@@ -619,7 +666,7 @@ __global__ void __launch_bounds__(128) k_lsd_nfa(const __grid_constant__ LineGeo
     rec.x1 = job[0]; rec.y1 = job[1]; rec.x2 = job[2]; rec.y2 = job[3]; rec.width = job[4]; rec.x = job[5]; rec.y = job[6];
     rec.theta = job[7]; rec.dx = job[8]; rec.dy = job[9]; rec.prec = job[10]; rec.p = job[11];
     const double tag = job[12];
-    const double log_nfa = l_rect_improve(W, rec);
+    const double log_nfa = l_rect_improve(W, rec, s_cnt[threadIdx.x >> 5]);
     __syncwarp();
     if (W.lane == 0) {
         job[0] = rec.x1; job[1] = rec.y1; job[2] = rec.x2; job[3] = rec.y2; job[4] = rec.width; job[11] = rec.p; job[12] = log_nfa;
@@ -886,7 +933,7 @@ void carve(sslpl_line* h, Arena& A, const LineGeom& g, int B) {
     ws.blur7 = A.take<uint8_t>((size_t)B * g.blur_stride); ws.blur5 = A.take<uint8_t>((size_t)B * g.blur_stride);
     ws.scaled = A.take<uint8_t>((size_t)B * g.scaled_stride);
     ws.angdeg = A.take<float>((size_t)B * g.pix_stride); ws.cs = A.take<float2>((size_t)B * g.pix_stride);
-    ws.modgrad = A.take<double>((size_t)B * g.pix_stride); ws.cs0 = A.take<float2>((size_t)B * g.pix_stride);
+    ws.modgrad = A.take<double>((size_t)B * g.pix_stride); ws.cs0 = A.take<float2>((size_t)B * g.pix_stride); ws.used = A.take<uint8_t>((size_t)B * g.pix_stride);
     ws.maxgrad = A.take<unsigned long long>(B); ws.hist = A.take<int>((size_t)B * (NBINS + 1));
     ws.seeds = A.take<unsigned>((size_t)B * g.pix_stride); ws.nseeds = A.take<int>(B);
     ws.reg = A.take<unsigned>((size_t)B * g.pix_stride);
@@ -923,12 +970,6 @@ int configure(sslpl_line* h, int W, int H) {
     SSLPL_REQUIRE(A.used <= h->arena_size, SSLPL_ERR_CAPACITY, "internal: arena too small for this frame size");
     SSLPL_CUDA(cudaStreamSynchronize(h->stream));
     SSLPL_CUDA(cudaMemcpy(h->ws.tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    h->used_smem = (int)((h->g.pix_stride + 31) / 32 * 4) + 768;
-    SSLPL_REQUIRE(h->used_smem <= 200 * 1024, SSLPL_ERR_UNSUPPORTED, "frame too large for the shared-memory `used` bitmap of the LSD walker");
-    SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(h->used_smem, 1024)));
-    // keep as much of the unified L1 as possible for the angle / gradient maps (4 resident walkers per SM at most)
-    SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    std::min(100, (int)(100.0 * 4 * h->used_smem / (228.0 * 1024)) + 5)));
     SSLPL_CUDA(cudaMemset(h->ws.err, 0, sizeof(int)));
     {
         std::vector<double> lg((size_t)h->g.pix_stride + 2);
@@ -952,7 +993,7 @@ int run_pipeline(sslpl_line* h, int B) {
     k_ll_angle<<<dim3((g.sw + 31) / 32, (g.sh + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
     k_lsd_compact<<<B, 1024, 0, st>>>(g, h->ws);
     k_lsd_order<<<B, 32, 0, st>>>(g, h->ws);
-    k_lsd_regions<<<B, 32, h->used_smem, st>>>(g, h->ws);
+    k_lsd_regions<<<B, 32, 0, st>>>(g, h->ws);
     k_lsd_nfa<<<dim3((g.seg_cap + 3) / 4, B), 128, 0, st>>>(g, h->ws);
     k_keylines<<<B, 256, 0, st>>>(g, h->ws);
     k_sobel<<<dim3((g.w + 31) / 32, (g.h + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
