@@ -183,7 +183,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))   # fail fast, never hang the box
 
     W, H, NF, Bf, NL = cfg["width"], cfg["height"], cfg["nfeatures"], cfg["frames_per_gpu"], cfg["nlines"]
     LINES = not args.no_lines
@@ -217,6 +218,7 @@ def main():
     d_gather = torch.empty((world * Bf, cap), dtype=torch.int32, device=dev) if world > 1 else None
     d_lgather = torch.empty((world * Bf, NL), dtype=torch.int32, device=dev) if world > 1 else None
     pending = [False] * R
+    gather = [world > 1]                                # collectives on/off (off in the rank-0-only profiling pass)
     ev_free = [torch.cuda.Event() for _ in range(R)]    # slot r's tables have been consumed (gathered) on s_pts
 
     def finalize_slot(r):
@@ -224,8 +226,9 @@ def main():
         if not pending[r]:
             return
         s_pts.wait_stream(s_lin[r])
-        if world > 1:
+        if gather[0]:
             dist.all_gather_into_tensor(d_lgather, d_lmatch[r])
+        if world > 1:
             ev_free[r].record(s_pts)
         pending[r] = False
 
@@ -240,7 +243,7 @@ def main():
     def enqueue_points():
         kps, desc, n, c = ext.device_results()
         mt.match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match.data_ptr(), d_nmatch.data_ptr())
-        if world > 1:
+        if gather[0]:
             dist.all_gather_into_tensor(d_gather, d_match)
 
     def step_device(i):
@@ -376,14 +379,24 @@ def main():
     # ---- roofline of the dominant kernel (rank 0): CUDA events between the kernels of one handle ----
     roofline = None
     if rank == 0:
+        gather[0] = False                               # this pass runs on rank 0 only: no collectives
         ext.set_profiling(True)
+        if LINES:
+            lsr[0].set_profiling(True)
         acc = {}
         nprof = 5
-        for i in range(nprof):
-            step_device(i); drain(); ext.sync()
-            for k, v in ext.stage_ms().items():
+        for i in range(nprof):                          # serial: one handle at a time, so that the stage times are clean
+            fr = d_sets[i % nsets]
+            ext.extract_batch_device(fr.data_ptr(), B, W, H, W, W * H); ext.sync()
+            st = dict(ext.stage_ms())
+            if LINES:
+                lsr[0].extract_batch_device(fr.data_ptr(), B, W, H, W, W * H); lsr[0].sync()
+                st.update(lsr[0].stage_ms())
+            for k, v in st.items():
                 acc[k] = acc.get(k, 0.0) + v / nprof
         ext.set_profiling(False)
+        if LINES:
+            lsr[0].set_profiling(False)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -401,11 +414,20 @@ def main():
             "blur": 2 * P,
             "orient_desc": (749 + 512 + 32 + 28 + 4) * nkp_avg,
             "octree": 8 * ncand,
+            # line path, S = scaled pixels (0.64 W H): SURVEY.md 8(d)
+            "lsd_prep": W * H + 2 * int(0.64 * W * H) + 2 * W * H,
+            "lsd_ll_angle": int(0.64 * W * H) * (1 + 4 + 8 + 8 + 8),
+            "lsd_seeds": int(0.64 * W * H) * (4 + 8) + 8 * int(0.15 * 0.64 * W * H),
+            "lsd_regions": 17 * int(0.64 * W * H),          # upper bound of the visited-pixel traffic; latency-bound by definition
+            "lsd_nfa": 4 * int(0.64 * W * H),
+            "keylines_lbd": W * H + 8 * W * H + 63 * 4 * 60 * NL,
         }
         dom = max(acc, key=acc.get)
         achieved = alg.get(dom, 0) * B / (acc[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": which, "stage_ms": acc,
+                    "note": ("lsd_regions is the order-dependent LSD region walker (one warp per frame): latency-bound by "
+                             "definition, reported against HBM only for completeness" if dom == "lsd_regions" else ""),
                     "stage_gbs": {k: alg.get(k, 0) * B / (acc[k] * 1e-3) / 1e9 for k in acc}}
 
     # ---- CPU baseline on the host cores (rank 0, N=1 only) ----

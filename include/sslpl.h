@@ -209,6 +209,8 @@ int  sslpl_line_sync(sslpl_line* h);
 void* sslpl_line_stream(sslpl_line* h);
 int  sslpl_line_set_stream(sslpl_line* h, void* cuda_stream);
 long long sslpl_line_launch_count(const sslpl_line* h);
+int  sslpl_line_set_profiling(sslpl_line* h, int on);
+int  sslpl_line_stage_ms(sslpl_line* h, float* ms, int cap, const char** names, int* nstages);
 /* raw LSD segments (before the top-N cut) of frame f of the last call: seg[4*i] = x1,y1,x2,y2 */
 int  sslpl_line_download_segments(sslpl_line* h, int frame, float* seg4, int cap, int* n);
 /* debug: with SSLPL_LINE_TRACE=1 in the environment at create time, one row of 10 doubles per LSD region that reached

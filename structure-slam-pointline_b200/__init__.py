@@ -481,6 +481,14 @@ class LineSegment:
         _check(lib().sslpl_line_download_segments(self._h, frame, _p(seg), cap, C.byref(n)))
         return seg[:min(n.value, cap)].copy()
 
+    def set_profiling(self, on=True):
+        _check(lib().sslpl_line_set_profiling(self._h, int(on)))
+
+    def stage_ms(self):
+        ms = (C.c_float * 16)(); names = (C.c_char_p * 16)(); n = C.c_int()
+        _check(lib().sslpl_line_stage_ms(self._h, ms, 16, names, C.byref(n)))
+        return {names[i].decode(): float(ms[i]) for i in range(n.value)}
+
     def debug_trace(self, frame=0, cap=1 << 16):
         out = np.empty((cap, 10), np.float64); n = C.c_int()
         _check(lib().sslpl_line_debug_trace(self._h, frame, _p(out), cap, C.byref(n)))

@@ -117,3 +117,26 @@ def test_non_tma_fallback_path(pkg, oracle, synth, icl_gray, monkeypatch):
     ext2 = pkg.ORBextractor(800, 1.2, 8, 20, 7, max_width=700, max_height=500)
     img = synth.frame(640, 480, 4)[:, :613]
     _compare_all(ext2, oracle.OrbOracle(800, 1.2, 8, 20, 7), np.ascontiguousarray(img), "w613")
+
+
+def test_async_begin_and_device_paths(pkg, oracle, synth):
+    """The asynchronous host-buffer form (pinned buffers, sslpl_orb_extract_batch_begin + sync) and the device-resident
+    form must give the same keypoints/descriptors as the synchronous call."""
+    frames = synth.batch(640, 480, 4)
+    ext = pkg.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=4)
+    k0, d0, n0 = ext.extract_batch(frames)
+    hp = pkg.host_alloc(frames.shape, np.uint8); hp[...] = frames
+    out = (pkg.host_alloc((4, ext.cap), pkg.KEYPOINT_DTYPE), pkg.host_alloc((4, ext.cap, 32), np.uint8), pkg.host_alloc((4,), np.int32))
+    ext.extract_batch_begin(hp, out)
+    ext.sync()
+    assert np.array_equal(out[2], n0)
+    for f in range(4):
+        assert out[0][f, :n0[f]].tobytes() == k0[f, :n0[f]].tobytes() and np.array_equal(out[1][f, :n0[f]], d0[f, :n0[f]])
+    ls = pkg.LineSegment(40, max_width=640, max_height=480, max_batch=4)
+    kl0, ld0, eq0, nl0 = ls.extract_batch(frames)
+    lout = (pkg.host_alloc((4, 40), pkg.KEYLINE_DTYPE), pkg.host_alloc((4, 40, 32), np.uint8), pkg.host_alloc((4, 40, 3), np.float64), pkg.host_alloc((4,), np.int32))
+    ls.extract_batch_begin(hp, lout)
+    ls.sync()
+    assert np.array_equal(lout[3], nl0)
+    for f in range(4):
+        assert np.array_equal(lout[1][f, :nl0[f]], ld0[f, :nl0[f]]) and lout[0][f, :nl0[f]].tobytes() == kl0[f, :nl0[f]].tobytes()
