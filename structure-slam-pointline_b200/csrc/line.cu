@@ -2,7 +2,7 @@
 // LBD 256-bit descriptors + line equations.  Replaces LineSegment::ExtractLineSegment
 // (reference src/ExtractLineSegment.cpp:18-69, which delegates to cv::line_descriptor / cv::LineSegmentDetector).
 //
-// Per-pixel stages are ordinary data-parallel kernels (k_sep7, k_resize_exact, k_ll_angle, k_lsd_compact, k_lsd_nfa, k_sobel).
+// Per-pixel stages are ordinary data-parallel kernels (k_sep7, k_resize_exact, k_ll_angle, k_lsd_seeds, k_lsd_nfa_*, k_sobel).
 // The region stage (k_lsd_regions) is order-dependent by definition (seeds in descending gradient bins, shared
 // `used` map, incrementally updated region angle): one warp walks one frame; the warp's lanes cooperate on neighbour
 // fetches and on the rectangle scans of rect_nfa, frames of a batch run on different SMs.  It is latency-bound,
@@ -46,12 +46,12 @@ struct LineGeom {
 struct LineWs {
     uint8_t* blur7; uint8_t* blur5; uint8_t* scaled;
     float* angdeg; float2* cs; float2* cs0; double* modgrad; uint8_t* used;
-    unsigned long long* maxgrad; int* hist; unsigned* seeds; int* nseeds;
+    unsigned long long* maxgrad; unsigned* seeds; int* nseeds;
     unsigned* reg;              // region pixel list (x | y << 16)
     double* seg;                // raw rectangles: x1,y1,x2,y2 (detection scale, before +0.5)
     int* nseg;
     double* jobs; int* njobs; int* jobflag;   // NFA jobs: 13 doubles per candidate region (LRect + log_nfa), in walker order
-    unsigned* cidx; unsigned short* cbin;     // defined pixels compacted in raster order + their gradient bins
+    int2* jobnk; double* jobnfa;              // per job: (total, aligned) pixel counts and NFA of the unmodified rectangle
     int16_t* dx; int16_t* dy;
     int2* tab;
     float* resp; float4* ext;   // per raw segment: response and clamped extremes
@@ -151,76 +151,45 @@ __device__ __forceinline__ int lsd_bin(double norm, double max_grad) {
     return (int)(norm * bin_coef);
 }
 
-// Defined pixels compacted in raster order (+ their gradient bins and the bin histogram): one CTA of 32 warps per
-// frame, each warp owns a contiguous pixel range (ballot/popc ranks inside a warp, block scan across warps).
-__global__ void __launch_bounds__(1024) k_lsd_compact(const __grid_constant__ LineGeom g, LineWs ws) {
-    __shared__ int s_hist[NBINS + 1];
-    __shared__ int s_wcnt[33];
+// Seed ordering of lsd.cpp in one kernel: the defined pixels sorted by gradient bin (descending), raster order inside
+// a bin — a stable counting sort.  One CTA of 32 warps per frame; warp w owns the w-th contiguous pixel range (raster
+// order), builds its own 1024-bin histogram in shared memory, the histograms are prefix-summed across warps and bins,
+// and every warp then scatters its pixels in order (ranks inside a 32-group by __match_any_sync).
+__global__ void __launch_bounds__(1024) k_lsd_seeds(const __grid_constant__ LineGeom g, LineWs ws) {
+    extern __shared__ int s_wh[];                    // [32 warps][NBINS] running offsets
+    __shared__ int s_warp[33];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float* ang = ws.angdeg + f * g.pix_stride; const double* mod = ws.modgrad + f * g.pix_stride;
     const double mg = __longlong_as_double((long long)ws.maxgrad[f]);
-    for (int i = tid; i <= NBINS; i += 1024) s_hist[i] = 0;
+    int* wh = s_wh + wid * NBINS;
+    for (int i = tid; i < 32 * NBINS; i += 1024) s_wh[i] = 0;
+    __syncthreads();
     const long long per = ((g.pix_stride + 31) / 32 + 31) / 32 * 32;          // pixels per warp, multiple of 32
     const long long b = wid * per, e = min(g.pix_stride, b + per);
-    int cnt = 0;
-    for (long long i = b + lane; i < b + per; i += 32) cnt += __popc(__ballot_sync(0xffffffffu, i < e && ang[i] != NOTDEF_F));
-    if (lane == 0) s_wcnt[wid] = cnt;
+    for (long long i = b + lane; i < e; i += 32)
+        if (ang[i] != NOTDEF_F) atomicAdd(&wh[NBINS - 1 - lsd_bin(mod[i], mg)], 1);
     __syncthreads();
-    if (wid == 0) {
-        int v = s_wcnt[lane], inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        s_wcnt[lane] = inc - v;
-        if (lane == 31) ws.nseeds[f] = inc;
+    {   // thread = bin: exclusive prefix over the warps, then over the bins
+        int run = 0;
+        for (int w = 0; w < 32; w++) { const int c = s_wh[w * NBINS + tid]; s_wh[w * NBINS + tid] = run; run += c; }
+        int total;
+        const int base = block_exclusive_scan(run, s_warp, &total);
+        for (int w = 0; w < 32; w++) s_wh[w * NBINS + tid] += base;
+        if (tid == 0) ws.nseeds[f] = total;
     }
     __syncthreads();
-    int off = s_wcnt[wid];
-    unsigned* cidx = ws.cidx + f * g.pix_stride; unsigned short* cbin = ws.cbin + f * g.pix_stride;
-    for (long long i = b + lane; i < b + per; i += 32) {
-        const bool def = i < e && ang[i] != NOTDEF_F;
-        const unsigned m = __ballot_sync(0xffffffffu, def);
-        if (def) {
-            const int bin = NBINS - 1 - lsd_bin(mod[i], mg);
-            const int o = off + __popc(m & ((1u << lane) - 1));
-            cidx[o] = (unsigned)i; cbin[o] = (unsigned short)bin;
-            atomicAdd(&s_hist[bin], 1);
-        }
-        off += __popc(m);
-    }
-    __syncthreads();
-    for (int i = tid; i <= NBINS; i += 1024) ws.hist[f * (NBINS + 1) + i] = s_hist[i];
-}
-
-// stable counting sort of the compacted pixels: bins descending, raster order inside a bin.  One warp per frame over
-// ~15% of the pixels (the defined ones); ranks inside a 32-group by __match_any_sync.
-__global__ void __launch_bounds__(32) k_lsd_order(const __grid_constant__ LineGeom g, LineWs ws) {
-    __shared__ int s_off[NBINS + 1];
-    const int f = blockIdx.x, lane = threadIdx.x;
-    const int* hist = ws.hist + f * (NBINS + 1);
-    int carry = 0;
-    for (int b0 = 0; b0 < NBINS; b0 += 32) {
-        const int v = hist[b0 + lane];
-        int inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        s_off[b0 + lane] = carry + inc - v;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    __syncwarp();
-    const int n = ws.nseeds[f];
-    const unsigned* cidx = ws.cidx + f * g.pix_stride; const unsigned short* cbin = ws.cbin + f * g.pix_stride;
     unsigned* seeds = ws.seeds + f * g.pix_stride;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const bool def = i < n;
-        const int key = def ? (int)cbin[i] : (2048 + lane);
-        const unsigned idx = def ? cidx[i] : 0u;
+    for (long long i0 = b; i0 < b + per; i0 += 32) {
+        const long long i = i0 + lane;
+        const bool def = i < e && ang[i] != NOTDEF_F;
+        if (!__any_sync(0xffffffffu, def)) continue;
+        const int key = def ? (NBINS - 1 - lsd_bin(mod[i], mg)) : (2048 + lane);
         const unsigned peers = __match_any_sync(0xffffffffu, key);
         const int leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1));
         int off = 0;
-        if (def && lane == leader) { off = s_off[key]; s_off[key] = off + __popc(peers); }
+        if (def && lane == leader) { off = wh[key]; wh[key] = off + __popc(peers); }
         off = __shfl_sync(0xffffffffu, off, leader);
-        if (def) seeds[off + rank] = idx;
+        if (def) seeds[off + rank] = (unsigned)i;
         __syncwarp();
     }
 }
@@ -254,6 +223,13 @@ __device__ __forceinline__ bool l_aligned(float angdeg, double theta, double pre
     return n <= prec;
 }
 
+__device__ __forceinline__ bool l_aligned_rad(double a, double theta, double prec) {      // a = (double)angdeg * L_DEG, not NOTDEF
+    double n = theta - a;
+    if (n < 0) n = -n;
+    if (n > L_3_2_PI) { n -= L_2PI; if (n < 0) n = -n; }
+    return n <= prec;
+}
+
 __device__ int l_region_grow(const Walk& W, int sx, int sy, double prec, double& reg_angle) {
     const int lane = W.lane, w = W.w, h = W.h;
     const int sq = sy * w + sx;                                   // 32-bit pixel indices (sw * sh < 2^31)
@@ -274,13 +250,14 @@ __device__ int l_region_grow(const Walk& W, int sx, int sy, double prec, double&
             a = __ldg(W.ang + q); c = __ldg(W.cs + q);
             u = W.used[q] != 0;
         }
+        const double ad = (double)a * L_DEG;
         // Sequential semantics (each neighbour is tested once, in scan order, against the region angle as updated by
         // the neighbours accepted before it) in as many rounds as there are acceptances: all pending lanes test
         // against the current angle; the first passing lane k0 is accepted, lanes < k0 are definitively rejected
         // (they saw exactly the angle the sequential scan would have shown them).
         unsigned pending = __ballot_sync(0xffffffffu, !u && a != NOTDEF_F);
         while (pending) {
-            const unsigned okm = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && l_aligned(a, reg_angle, prec)) & pending;
+            const unsigned okm = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && l_aligned_rad(ad, reg_angle, prec)) & pending;
             if (!okm) break;
             const int k0 = __ffs(okm) - 1;
             const float cx = __shfl_sync(0xffffffffu, c.x, k0), cy = __shfl_sync(0xffffffffu, c.y, k0);
@@ -475,7 +452,7 @@ __device__ __forceinline__ int l_x86_d2i(double v) {                 // cvttsd2s
 
 // rect_nfa of OpenCV 4.13 (see oracle/line_oracle.cpp): rows are distributed over the lanes (or, for flat
 // rectangles, the pixels of a row); the two counts are exact integers, so the reduction order is irrelevant.
-__device__ double l_rect_nfa(const Walk& W, const LRect& rec) {
+__device__ void l_rect_count(const Walk& W, const LRect& rec, int& total_out, int& alg_out) {
     const double half_width = 0.5 * rec.width, dyhw = rec.dy * half_width, dxhw = rec.dx * half_width;
     const double vx[4] = {rec.x1 - dyhw, rec.x2 - dyhw, rec.x2 + dyhw, rec.x1 + dyhw};
     const double vy[4] = {rec.y1 + dxhw, rec.y2 + dxhw, rec.y2 - dxhw, rec.y1 - dxhw};
@@ -509,8 +486,13 @@ __device__ double l_rect_nfa(const Walk& W, const LRect& rec) {
             for (int x = xs + W.lane; x <= xe; x += 32) { ++total; if (l_aligned(row[x], rec.theta, rec.prec)) ++alg; }
         }
     }
-    total = __reduce_add_sync(0xffffffffu, total);
-    alg = __reduce_add_sync(0xffffffffu, alg);
+    total_out = __reduce_add_sync(0xffffffffu, total);
+    alg_out = __reduce_add_sync(0xffffffffu, alg);
+}
+
+__device__ double l_rect_nfa(const Walk& W, const LRect& rec) {
+    int total, alg;
+    l_rect_count(W, rec, total, alg);
     return l_nfa(total, alg, rec.p, W.log_nt, W.lgam);
 }
 
@@ -563,11 +545,10 @@ __device__ void l_rect_nfa5(const Walk& W, const LRect& mine, bool valid, int* s
 // rect_improve (lsd.cpp): each of the five refinement phases tries a fixed sequence of five candidate rectangles that
 // does not depend on the NFA values inside the phase, so the five are evaluated at once (l_rect_nfa5) and the
 // reference's "first strict improvement wins" rule is then replayed in order.
-__device__ double l_rect_improve(const Walk& W, LRect& rec, int* s_cnt) {
+__device__ double l_rect_improve(const Walk& W, LRect& rec, int* s_cnt, double log_nfa) {
     const double delta = 0.5, delta_2 = delta / 2.0;
     const int lane = W.lane, grp = lane / 6, k = min(grp, 4) + 1;     // this lane's candidate = k-th step of the phase
-    double log_nfa = l_rect_nfa(W, rec);
-    if (log_nfa > 0.0) return log_nfa;
+    if (log_nfa > 0.0) return log_nfa;           // log_nfa = NFA of the unmodified rectangle (k_lsd_nfa_first)
     double v[5];
     for (int phase = 0; phase < 5; phase++) {
         // candidate k of the phase, built exactly as the sequential loop would have built it
@@ -651,31 +632,64 @@ __global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ Line
     if (W.lane == 0) { ws.njobs[f] = min(nj, g.seg_cap); if (nj > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
 }
 
-// rect_improve + NFA for every candidate region of every frame: one warp per job.  Writes the refined rectangle back
-// and flags accepted jobs (log_nfa > LOG_EPS = 0).
-__global__ void __launch_bounds__(128) k_lsd_nfa(const __grid_constant__ LineGeom g, LineWs ws) {
-    __shared__ int s_cnt[4][10];
+// NFA of every candidate region of every frame, in three data-parallel steps:
+//   k_lsd_nfa_count   one warp per job: the rectangle scan (total / aligned pixel counts)
+//   k_lsd_nfa_first   one THREAD per job: the scalar NFA formula (32 jobs per warp side by side); most jobs are accepted here
+//   k_lsd_nfa_improve one warp per still-rejected job: the five refinement phases of rect_improve
+__global__ void __launch_bounds__(128) k_lsd_nfa_count(const __grid_constant__ LineGeom g, LineWs ws) {
     const int f = blockIdx.y, j = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (j >= ws.njobs[f]) return;
     Walk W;
-    W.w = g.sw; W.h = g.sh; W.npix = g.pix_stride; W.lane = threadIdx.x & 31;
-    W.ang = ws.angdeg + f * g.pix_stride; W.cs = nullptr; W.mod = nullptr; W.used = nullptr; W.reg = nullptr;
-    W.log_nt = g.log_nt; W.lgam = ws.lgam; W.st = nullptr; W.cs0 = nullptr;
-    double* job = ws.jobs + ((long long)f * g.seg_cap + j) * 13;
+    W.w = g.sw; W.h = g.sh; W.npix = g.pix_stride; W.lane = threadIdx.x & 31; W.ang = ws.angdeg + f * g.pix_stride;
+    const double* job = ws.jobs + ((long long)f * g.seg_cap + j) * 13;
     LRect rec;
-    rec.x1 = job[0]; rec.y1 = job[1]; rec.x2 = job[2]; rec.y2 = job[3]; rec.width = job[4]; rec.x = job[5]; rec.y = job[6];
-    rec.theta = job[7]; rec.dx = job[8]; rec.dy = job[9]; rec.prec = job[10]; rec.p = job[11];
-    const double tag = job[12];
-    const double log_nfa = l_rect_improve(W, rec, s_cnt[threadIdx.x >> 5]);
-    __syncwarp();
-    if (W.lane == 0) {
-        job[0] = rec.x1; job[1] = rec.y1; job[2] = rec.x2; job[3] = rec.y2; job[4] = rec.width; job[11] = rec.p; job[12] = log_nfa;
-        ws.jobflag[(long long)f * g.seg_cap + j] = log_nfa > 0.0 ? 1 : 0;
+    rec.x1 = job[0]; rec.y1 = job[1]; rec.x2 = job[2]; rec.y2 = job[3]; rec.width = job[4]; rec.theta = job[7]; rec.dx = job[8]; rec.dy = job[9]; rec.prec = job[10];
+    int total, alg;
+    l_rect_count(W, rec, total, alg);
+    if (W.lane == 0) ws.jobnk[(long long)f * g.seg_cap + j] = make_int2(total, alg);
+}
+
+__global__ void __launch_bounds__(128) k_lsd_nfa_first(const __grid_constant__ LineGeom g, LineWs ws) {
+    const int f = blockIdx.y, j = blockIdx.x * 128 + threadIdx.x;
+    if (j >= ws.njobs[f]) return;
+    const long long q = (long long)f * g.seg_cap + j;
+    const int2 nk = ws.jobnk[q];
+    double* job = ws.jobs + q * 13;
+    const double v = l_nfa(nk.x, nk.y, job[11], g.log_nt, ws.lgam);
+    ws.jobflag[q] = v > 0.0 ? 1 : 0;
+    ws.jobnfa[q] = v;
+}
+
+__global__ void __launch_bounds__(128) k_lsd_nfa_improve(const __grid_constant__ LineGeom g, LineWs ws) {
+    __shared__ int s_cnt[4][10];
+    const int f = blockIdx.y, j = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (j >= ws.njobs[f]) return;
+    const long long q = (long long)f * g.seg_cap + j;
+    double log_nfa = ws.jobnfa[q];
+    double* job = ws.jobs + q * 13;
+    if (!(log_nfa > 0.0)) {
+        Walk W;
+        W.w = g.sw; W.h = g.sh; W.npix = g.pix_stride; W.lane = threadIdx.x & 31;
+        W.ang = ws.angdeg + f * g.pix_stride; W.cs = nullptr; W.mod = nullptr; W.used = nullptr; W.reg = nullptr;
+        W.log_nt = g.log_nt; W.lgam = ws.lgam; W.st = nullptr; W.cs0 = nullptr;
+        LRect rec;
+        rec.x1 = job[0]; rec.y1 = job[1]; rec.x2 = job[2]; rec.y2 = job[3]; rec.width = job[4]; rec.x = job[5]; rec.y = job[6];
+        rec.theta = job[7]; rec.dx = job[8]; rec.dy = job[9]; rec.prec = job[10]; rec.p = job[11];
+        log_nfa = l_rect_improve(W, rec, s_cnt[threadIdx.x >> 5], log_nfa);
+        __syncwarp();
+        if (W.lane == 0) {
+            job[0] = rec.x1; job[1] = rec.y1; job[2] = rec.x2; job[3] = rec.y2; job[4] = rec.width; job[11] = rec.p;
+            ws.jobflag[q] = log_nfa > 0.0 ? 1 : 0;
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        const double tag = job[12];
+        job[12] = log_nfa;
         if (g.trace_cap && j < g.trace_cap) {
             double* t = ws.trace + ((long long)f * g.trace_cap + j) * 10;
             const double idx = floor(tag / 65536.0);
             t[0] = idx; t[1] = tag - idx * 65536.0; t[2] = 0; t[3] = log_nfa;
-            t[4] = rec.x1; t[5] = rec.y1; t[6] = rec.x2; t[7] = rec.y2; t[8] = rec.width; t[9] = rec.p;
+            t[4] = job[0]; t[5] = job[1]; t[6] = job[2]; t[7] = job[3]; t[8] = job[4]; t[9] = job[11];
         }
     }
 }
@@ -887,9 +901,18 @@ struct sslpl_line {
     int cur_w = 0, cur_h = 0, cur_frames = 0;
     long long launches = 0;
     int* h_err = nullptr;
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev; std::vector<const char*> ev_name; int ev_n = 0;
 };
 
 namespace {
+
+void lmark(sslpl_line* h, const char* name) {
+    if (!h->profiling) return;
+    if ((int)h->ev.size() <= h->ev_n) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); h->ev_name.push_back(name); }
+    h->ev_name[h->ev_n] = name;
+    cudaEventRecord(h->ev[h->ev_n++], h->stream);
+}
 
 void make_geometry(const sslpl_line* h, int W, int H, LineGeom& g, std::vector<int2>* tab) {
     memset(&g, 0, sizeof(g));
@@ -934,12 +957,13 @@ void carve(sslpl_line* h, Arena& A, const LineGeom& g, int B) {
     ws.scaled = A.take<uint8_t>((size_t)B * g.scaled_stride);
     ws.angdeg = A.take<float>((size_t)B * g.pix_stride); ws.cs = A.take<float2>((size_t)B * g.pix_stride);
     ws.modgrad = A.take<double>((size_t)B * g.pix_stride); ws.cs0 = A.take<float2>((size_t)B * g.pix_stride); ws.used = A.take<uint8_t>((size_t)B * g.pix_stride);
-    ws.maxgrad = A.take<unsigned long long>(B); ws.hist = A.take<int>((size_t)B * (NBINS + 1));
+    ws.maxgrad = A.take<unsigned long long>(B);
     ws.seeds = A.take<unsigned>((size_t)B * g.pix_stride); ws.nseeds = A.take<int>(B);
     ws.reg = A.take<unsigned>((size_t)B * g.pix_stride);
     ws.seg = A.take<double>((size_t)B * g.seg_cap * 4); ws.nseg = A.take<int>(B);
     ws.jobs = A.take<double>((size_t)B * g.seg_cap * 13); ws.njobs = A.take<int>(B); ws.jobflag = A.take<int>((size_t)B * g.seg_cap);
-    ws.cidx = A.take<unsigned>((size_t)B * g.pix_stride); ws.cbin = A.take<unsigned short>((size_t)B * g.pix_stride);
+    ws.jobnk = A.take<int2>((size_t)B * g.seg_cap); ws.jobnfa = A.take<double>((size_t)B * g.seg_cap);
+
     ws.dx = A.take<int16_t>((size_t)B * g.full_stride); ws.dy = A.take<int16_t>((size_t)B * g.full_stride);
     ws.tab = A.take<int2>(g.sw + g.sh);
     ws.resp = A.take<float>((size_t)B * g.seg_cap); ws.ext = A.take<float4>((size_t)B * g.seg_cap);
@@ -970,6 +994,7 @@ int configure(sslpl_line* h, int W, int H) {
     SSLPL_REQUIRE(A.used <= h->arena_size, SSLPL_ERR_CAPACITY, "internal: arena too small for this frame size");
     SSLPL_CUDA(cudaStreamSynchronize(h->stream));
     SSLPL_CUDA(cudaMemcpy(h->ws.tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_seeds, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * NBINS * (int)sizeof(int)));
     SSLPL_CUDA(cudaMemset(h->ws.err, 0, sizeof(int)));
     {
         std::vector<double> lg((size_t)h->g.pix_stride + 2);
@@ -986,19 +1011,28 @@ int run_pipeline(sslpl_line* h, int B) {
     const Taps7 t7 = {{0, 4, 56, 136, 56, 4, 0}};       // GaussianBlur(sigma 0.6/0.8) of lsd.cpp, 4.13 fixed point
     const Taps7 t5 = {{0, 14, 62, 104, 62, 14, 0}};     // GaussianBlur(5x5, sigma 1) of BinaryDescriptor
     const dim3 tiles(g.tiles_x * g.tiles_y, B);
+    h->ev_n = 0;
+    lmark(h, "start");
     k_sep7<<<tiles, 256, 0, st>>>(g, h->view, h->ws.blur7, g.blur_stride, t7);
     k_sep7<<<tiles, 256, 0, st>>>(g, h->view, h->ws.blur5, g.blur_stride, t5);
     k_resize_exact<<<dim3((g.sw + 31) / 32, (g.sh + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
+    lmark(h, "lsd_prep");
     SSLPL_CUDA(cudaMemsetAsync(h->ws.maxgrad, 0, sizeof(unsigned long long) * B, st));
     k_ll_angle<<<dim3((g.sw + 31) / 32, (g.sh + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
-    k_lsd_compact<<<B, 1024, 0, st>>>(g, h->ws);
-    k_lsd_order<<<B, 32, 0, st>>>(g, h->ws);
+    lmark(h, "lsd_ll_angle");
+    k_lsd_seeds<<<B, 1024, 32 * NBINS * sizeof(int), st>>>(g, h->ws);
+    lmark(h, "lsd_seeds");
     k_lsd_regions<<<B, 32, 0, st>>>(g, h->ws);
-    k_lsd_nfa<<<dim3((g.seg_cap + 3) / 4, B), 128, 0, st>>>(g, h->ws);
+    lmark(h, "lsd_regions");
+    k_lsd_nfa_count<<<dim3((g.seg_cap + 3) / 4, B), 128, 0, st>>>(g, h->ws);
+    k_lsd_nfa_first<<<dim3((g.seg_cap + 127) / 128, B), 128, 0, st>>>(g, h->ws);
+    k_lsd_nfa_improve<<<dim3((g.seg_cap + 3) / 4, B), 128, 0, st>>>(g, h->ws);
+    lmark(h, "lsd_nfa");
     k_keylines<<<B, 256, 0, st>>>(g, h->ws);
     k_sobel<<<dim3((g.w + 31) / 32, (g.h + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
     k_lbd<<<dim3(g.kl_cap, B), 64, 0, st>>>(g, h->ws, h->coef);
-    h->launches += 11;
+    lmark(h, "keylines_lbd");
+    h->launches += 12;
     SSLPL_CUDA(cudaGetLastError());
     return SSLPL_OK;
 }
@@ -1053,6 +1087,7 @@ void sslpl_line_destroy(sslpl_line* h) {
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (auto e : h->ev) cudaEventDestroy(e);
     if (h->arena) cudaFree(h->arena);
     if (h->h_err) cudaFreeHost(h->h_err);
     delete h;
@@ -1068,6 +1103,16 @@ int sslpl_line_set_stream(sslpl_line* h, void* s) {
     return SSLPL_OK;
 }
 long long sslpl_line_launch_count(const sslpl_line* h) { return h ? h->launches : 0; }
+int sslpl_line_set_profiling(sslpl_line* h, int on) { SSLPL_REQUIRE(h, SSLPL_ERR_ARG, "null handle"); h->profiling = on != 0; return SSLPL_OK; }
+int sslpl_line_stage_ms(sslpl_line* h, float* ms, int cap, const char** names, int* nstages) {
+    SSLPL_REQUIRE(h && nstages, SSLPL_ERR_ARG, "null argument");
+    SSLPL_CUDA(cudaStreamSynchronize(h->stream));
+    int k = 0;
+    for (int i = 1; i < h->ev_n; i++, k++)
+        if (k < cap) { float t = 0; cudaEventElapsedTime(&t, h->ev[i - 1], h->ev[i]); if (ms) ms[k] = t; if (names) names[k] = h->ev_name[i]; }
+    *nstages = k;
+    return SSLPL_OK;
+}
 
 int sslpl_line_extract_batch_device(sslpl_line* h, const uint8_t* d_imgs, int nframes, int width, int height, int pitch, size_t frame_stride) {
     SSLPL_REQUIRE(h && d_imgs, SSLPL_ERR_ARG, "null argument");

@@ -244,24 +244,35 @@ __global__ void __launch_bounds__(256) k_fast_score(const __grid_constant__ OrbG
     if (TMA) __syncthreads();                   // s_qn / s_sc initialisation
     const int vw = min(TL_W, L.maxBX - x0), vh = min(TL_H, L.maxBY - y0);     // valid part of the tile
     const int th = g.minTh;
-    // phase A
+    // phase A: the opposite-pair test on 4 pixels per thread with byte-SIMD video instructions
+    const unsigned T4 = 0x01010101u * (unsigned)th;
 #pragma unroll
-    for (int it = 0; it < 8; it++) {
-        const int p = it * 256 + tid, r = p >> 6, c = p & 63;
-        bool pass = false;
-        if (r < vh && c < vw) {
-            const uint8_t* q = &s_img[(r + 3) * TL_P + c + TL_X];
-            const int ctr = q[0];
-            const int d0 = ctr - q[3 * TL_P], d8 = ctr - q[-3 * TL_P], d4 = ctr - q[3], d12 = ctr - q[-3];
-            const bool br = (d0 > th || d8 > th) && (d4 > th || d12 > th);
-            const bool dk = (d0 < -th || d8 < -th) && (d4 < -th || d12 < -th);
-            pass = br || dk;
+    for (int it = 0; it < 2; it++) {
+        const int gidx = it * 256 + tid, r = gidx >> 4, c4 = (gidx & 15) * 4;          // 16 four-pixel groups per row
+        unsigned pm = 0;
+        if (r < vh && c4 < vw) {
+            const unsigned* row = reinterpret_cast<const unsigned*>(&s_img[(r + 3) * TL_P + TL_X + c4]);
+            const unsigned C = row[0];
+            const unsigned Rt = __byte_perm(row[0], row[1], 0x6543), Lf = __byte_perm(row[-1], row[0], 0x4321);   // x+3, x-3
+            const unsigned Dn = row[3 * (TL_P / 4)], Up = row[-3 * (TL_P / 4)];                                   // y+3 (k=0), y-3 (k=8)
+            // A_k: centre brighter than ring_k by more than th; B_k: darker
+            const unsigned A0 = __vcmpgtu4(__vsubus4(C, Dn), T4), A8 = __vcmpgtu4(__vsubus4(C, Up), T4);
+            const unsigned A4 = __vcmpgtu4(__vsubus4(C, Rt), T4), A12 = __vcmpgtu4(__vsubus4(C, Lf), T4);
+            const unsigned B0 = __vcmpgtu4(__vsubus4(Dn, C), T4), B8 = __vcmpgtu4(__vsubus4(Up, C), T4);
+            const unsigned B4 = __vcmpgtu4(__vsubus4(Rt, C), T4), B12 = __vcmpgtu4(__vsubus4(Lf, C), T4);
+            pm = (((A0 | A8) & (A4 | A12)) | ((B0 | B8) & (B4 | B12))) & 0x01010101u;
+            if (c4 + 4 > vw) pm &= (1u << (8 * (vw - c4))) - 1u;                        // clip the last group of a partial tile
         }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        const int cnt = __popc(pm);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t2; }
         int base = 0;
-        if (lane == 0 && m) base = atomicAdd(&s_qn, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (pass) s_q[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)p;
+        if (lane == 31 && inc) base = atomicAdd(&s_qn, inc);
+        base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+        const int p0 = r * TL_W + c4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (pm & (1u << (8 * k))) s_q[base++] = (unsigned short)(p0 + k);
     }
     __syncthreads();
     // phase B
