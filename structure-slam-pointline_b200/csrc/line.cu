@@ -197,22 +197,29 @@ __global__ void __launch_bounds__(1024) k_lsd_seeds(const __grid_constant__ Line
 // -------------------------------------------------------------------------------------------------
 // The sequential region walker.  All lanes run the same control flow on warp-uniform values; loads of 32
 // region points / 9 neighbours are spread over the lanes and broadcast with shuffles; lane 0 does the writes.
+// The walker's CTA is ONE warp; its per-frame context lives in shared memory (file scope) so that the big
+// per-region routines can be real calls (__noinline__): inlined, the kernel was ~175 KB of SASS and the resident
+// warps (each at a different place in it) spent most of their stall time on instruction fetch.
 // -------------------------------------------------------------------------------------------------
 struct LRect { double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p; };
 
-struct Walk {
-    int w, h; long long npix;
-    const float* ang; const float2* cs; const double* mod; uint8_t* used; unsigned* reg;   // used: byte map in global memory (L1-resident; only this warp touches it)
+struct Walk {                   // context of the rectangle scans (k_lsd_nfa_*): registers
+    int w, h;
+    const float* ang;
     double log_nt;
     const double* lgam;
-    double* st;                 // shared staging: 3 x 32 doubles (products of a 32-point chunk)
-    const float2* cs0;          // per pixel: (float)cos / sin of the level-line angle taken as double (region seed values)
     int lane;
 };
 
-__device__ __forceinline__ bool l_used(const Walk& W, long long q) { return W.used[q] != 0; }
-__device__ __forceinline__ void l_set_used(const Walk& W, long long q) { W.used[q] = 1; }
-__device__ __forceinline__ void l_clr_used(const Walk& W, long long q) { W.used[q] = 0; }
+struct WalkCtx {                // context of the walker (k_lsd_regions): shared memory
+    int w, h;
+    const float* ang; const float2* cs; const double* mod;
+    uint8_t* used;              // byte map in global memory (L1-resident; only this warp touches it)
+    unsigned* reg;              // region pixel list (x | y << 16)
+    const float2* cs0;          // per pixel: (float)cos / sin of the level-line angle taken as double (region seed values)
+};
+__shared__ WalkCtx s_W;
+__shared__ __align__(16) double s_st[96];     // staging of a 32-point chunk: 3 quantities x 32
 
 __device__ __forceinline__ bool l_aligned(float angdeg, double theta, double prec) {
     if (angdeg == NOTDEF_F) return false;
@@ -230,25 +237,27 @@ __device__ __forceinline__ bool l_aligned_rad(double a, double theta, double pre
     return n <= prec;
 }
 
-__device__ int l_region_grow(const Walk& W, int sx, int sy, double prec, double& reg_angle) {
-    const int lane = W.lane, w = W.w, h = W.h;
+__device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* reg_angle_out) {
+    const int lane = threadIdx.x, w = s_W.w, h = s_W.h;
+    const float* __restrict__ ang = s_W.ang; const float2* __restrict__ cs = s_W.cs;
+    uint8_t* used = s_W.used; unsigned* reg = s_W.reg;
     const int sq = sy * w + sx;                                   // 32-bit pixel indices (sw * sh < 2^31)
-    if (lane == 0) { W.reg[0] = (unsigned)sx | ((unsigned)sy << 16); W.used[sq] = 1; }
-    reg_angle = (double)__ldg(W.ang + sq) * L_DEG;
-    const float2 c0 = __ldg(W.cs0 + sq);
+    if (lane == 0) { reg[0] = (unsigned)sx | ((unsigned)sy << 16); used[sq] = 1; }
+    double reg_angle = (double)__ldg(ang + sq) * L_DEG;
+    const float2 c0 = __ldg(s_W.cs0 + sq);
     float sumdx = c0.x, sumdy = c0.y;
     int n = 1;
     const int ox = lane % 3 - 1, oy = lane / 3 - 1, doff = oy * w + ox;   // this lane's neighbour (yy outer, xx inner: scan order of lsd.cpp)
     __syncwarp();
     for (int i = 0; i < n; i++) {
-        const unsigned pk = W.reg[i];
+        const unsigned pk = reg[i];
         const int px = pk & 0xffff, py = pk >> 16;
         const int xx = px + ox, yy = py + oy, q = py * w + px + doff;
         const bool valid = lane < 9 && (unsigned)xx < (unsigned)w && (unsigned)yy < (unsigned)h;
         float a = NOTDEF_F; float2 c = make_float2(0.f, 0.f); bool u = true;
         if (valid) {
-            a = __ldg(W.ang + q); c = __ldg(W.cs + q);
-            u = W.used[q] != 0;
+            a = __ldg(ang + q); c = __ldg(cs + q);
+            u = used[q] != 0;
         }
         const double ad = (double)a * L_DEG;
         // Sequential semantics (each neighbour is tested once, in scan order, against the region angle as updated by
@@ -262,8 +271,8 @@ __device__ int l_region_grow(const Walk& W, int sx, int sy, double prec, double&
             const int k0 = __ffs(okm) - 1;
             const float cx = __shfl_sync(0xffffffffu, c.x, k0), cy = __shfl_sync(0xffffffffu, c.y, k0);
             if (lane == k0) {                                     // the accepted lane records its own pixel
-                W.reg[n] = (unsigned)xx | ((unsigned)yy << 16);
-                W.used[q] = 1;
+                reg[n] = (unsigned)xx | ((unsigned)yy << 16);
+                used[q] = 1;
             }
             n++;
             sumdx += cx; sumdy += cy;
@@ -272,6 +281,7 @@ __device__ int l_region_grow(const Walk& W, int sx, int sy, double prec, double&
         }
         __syncwarp();
     }
+    *reg_angle_out = reg_angle;
     return n;
 }
 
@@ -282,40 +292,60 @@ __device__ __forceinline__ double l_angle_diff_signed(double a, double b) {
     return d;
 }
 
+// Sum of the three staged quantities of one chunk, in list order: lane c (c = lane % 3) owns accumulator c, so a
+// point costs one shared load and one add per warp instead of three of each.
+__device__ __noinline__ double l_chunk_sum(const double* sp, int m, double acc) {
+    if (m == 32) {
+        const double2* s2 = reinterpret_cast<const double2*>(sp);
+#pragma unroll
+        for (int j = 0; j < 16; j++) { const double2 v = s2[j]; acc += v.x; acc += v.y; }
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < m; j++) acc += sp[j];
+    }
+    return acc;
+}
+
 // region2rect + get_theta (lsd.cpp).  The weighted sums must be accumulated in list order to stay bit-identical with
 // the CPU, but only the ADDS are sequential: each lane forms the products of its own point, stages them in shared
-// memory, and the warp then walks the 32 staged values with broadcast loads.  The extents are exact min/max.
-__device__ void l_region2rect(const Walk& W, int n, double reg_angle, double prec, double p, LRect& rec) {
-    const int lane = W.lane;
-    double* s0 = W.st; double* s1 = W.st + 32; double* s2 = W.st + 64;
-    double x = 0, y = 0, sum = 0;
+// memory, and lanes 0..2 (replicated over the warp) each walk one of the three staged rows.  The extents are exact
+// min/max.
+__device__ __noinline__ void l_region2rect(int n, double reg_angle, double prec, double p, LRect* out) {
+    const int lane = threadIdx.x, w = s_W.w;
+    const unsigned* reg = s_W.reg; const double* __restrict__ mod = s_W.mod;
+    double* s0 = s_st; double* s1 = s_st + 32; double* s2 = s_st + 64;
+    const double* sp = s_st + (lane % 3) * 32;
+    double acc = 0;
+#pragma unroll 1
     for (int b = 0; b < n; b += 32) {
         const int i = b + lane;
         if (i < n) {
-            const unsigned pk = W.reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
-            const double wg = W.mod[(long long)ry * W.w + rx];
+            const unsigned pk = reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
+            const double wg = mod[ry * w + rx];
             s0[lane] = (double)rx * wg; s1[lane] = (double)ry * wg; s2[lane] = wg;
         }
         __syncwarp();
-        const int m = min(32, n - b);
-        for (int j = 0; j < m; j++) { x += s0[j]; y += s1[j]; sum += s2[j]; }
+        acc = l_chunk_sum(sp, min(32, n - b), acc);
         __syncwarp();
     }
+    double x = __shfl_sync(0xffffffffu, acc, 0), y = __shfl_sync(0xffffffffu, acc, 1);
+    const double sum = __shfl_sync(0xffffffffu, acc, 2);
     x /= sum; y /= sum;
-    double Ixx = 0, Iyy = 0, Ixy = 0;
+    acc = 0;
+#pragma unroll 1
     for (int b = 0; b < n; b += 32) {
         const int i = b + lane;
         if (i < n) {
-            const unsigned pk = W.reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
-            const double wg = W.mod[(long long)ry * W.w + rx];
+            const unsigned pk = reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
+            const double wg = mod[ry * w + rx];
             const double dx = (double)rx - x, dy = (double)ry - y;
-            s0[lane] = dy * dy * wg; s1[lane] = dx * dx * wg; s2[lane] = dx * dy * wg;
+            s0[lane] = dy * dy * wg; s1[lane] = dx * dx * wg; s2[lane] = -(dx * dy * wg);      // Ixy -= v  ==  Ixy += -v
         }
         __syncwarp();
-        const int m = min(32, n - b);
-        for (int j = 0; j < m; j++) { Ixx += s0[j]; Iyy += s1[j]; Ixy -= s2[j]; }
+        acc = l_chunk_sum(sp, min(32, n - b), acc);
         __syncwarp();
     }
+    const double Ixx = __shfl_sync(0xffffffffu, acc, 0), Iyy = __shfl_sync(0xffffffffu, acc, 1), Ixy = __shfl_sync(0xffffffffu, acc, 2);
     const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
     double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
                                            : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
@@ -325,86 +355,145 @@ __device__ void l_region2rect(const Walk& W, int n, double reg_angle, double pre
     double dx, dy;
     ddtrig::sincos_cr(theta, &dy, &dx);
     double l_min = 0, l_max = 0, w_min = 0, w_max = 0;           // max(0, max l), min(0, min l): order-independent
-    for (int i = lane; i < n; i += 32) {
-        const unsigned pk = W.reg[i];
+#pragma unroll 2
+    for (int i = lane; i < n; i += 32) {                         // (no NaNs here: plain compares instead of fmax/fmin)
+        const unsigned pk = reg[i];
         const double rdx = (double)(pk & 0xffff) - x, rdy = (double)(pk >> 16) - y;
         const double l = rdx * dx + rdy * dy, ww = -rdx * dy + rdy * dx;
-        l_max = fmax(l_max, l); l_min = fmin(l_min, l); w_max = fmax(w_max, ww); w_min = fmin(w_min, ww);
+        l_max = l > l_max ? l : l_max; l_min = l < l_min ? l : l_min; w_max = ww > w_max ? ww : w_max; w_min = ww < w_min ? ww : w_min;
     }
-#pragma unroll
+#pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
-        l_max = fmax(l_max, __shfl_xor_sync(0xffffffffu, l_max, o)); l_min = fmin(l_min, __shfl_xor_sync(0xffffffffu, l_min, o));
-        w_max = fmax(w_max, __shfl_xor_sync(0xffffffffu, w_max, o)); w_min = fmin(w_min, __shfl_xor_sync(0xffffffffu, w_min, o));
+        const double a = __shfl_xor_sync(0xffffffffu, l_max, o), b = __shfl_xor_sync(0xffffffffu, l_min, o);
+        const double c = __shfl_xor_sync(0xffffffffu, w_max, o), d = __shfl_xor_sync(0xffffffffu, w_min, o);
+        l_max = a > l_max ? a : l_max; l_min = b < l_min ? b : l_min; w_max = c > w_max ? c : w_max; w_min = d < w_min ? d : w_min;
     }
+    LRect rec;
     rec.x1 = x + l_min * dx; rec.y1 = y + l_min * dy; rec.x2 = x + l_max * dx; rec.y2 = y + l_max * dy;
     rec.width = w_max - w_min; rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx; rec.dy = dy; rec.prec = prec; rec.p = p;
     if (rec.width < 1.0) rec.width = 1.0;
+    *out = rec;
 }
 
 __device__ __forceinline__ double l_dist(double x1, double y1, double x2, double y2) { return sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1)); }
 __device__ __forceinline__ double l_distsq(double x1, double y1, double x2, double y2) { return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1); }
 
-__device__ bool l_reduce_region_radius(const Walk& W, int& n, double reg_angle, double prec, double p, LRect& rec, double density, double density_th) {
-    const unsigned p0 = W.reg[0];
+// reduce_region_radius (lsd.cpp).  The reference removes far points by swap-with-last while scanning forward, which
+// leaves the kept points in a definite order (it matters: region2rect sums in list order): every kept point below the
+// new size m' stays where it is, and the holes below m' (ascending) receive the kept points from positions >= m'
+// in DESCENDING position order.  That is computed here chunk-wise with ballots: a descending cursor collects
+// "fillers", an ascending one "holes", matched through a 32-entry shared buffer.  The removed tail's order is
+// irrelevant (those points are only un-marked).
+__device__ __noinline__ bool l_reduce_region_radius(int* n_io, double reg_angle, double prec, double p, LRect* rec, double density, double density_th) {
+    const int lane = threadIdx.x, w = s_W.w;
+    unsigned* reg = s_W.reg; uint8_t* used = s_W.used;
+    unsigned* s_fill = reinterpret_cast<unsigned*>(s_st);             // 32 filler values (s_st is free between region2rect calls)
+    int n = *n_io;
+    const unsigned p0 = reg[0];
     const double xc = (double)(p0 & 0xffff), yc = (double)(p0 >> 16);
-    double radSq = fmax(l_distsq(xc, yc, rec.x1, rec.y1), l_distsq(xc, yc, rec.x2, rec.y2));
+    double radSq = fmax(l_distsq(xc, yc, rec->x1, rec->y1), l_distsq(xc, yc, rec->x2, rec->y2));
     while (density < density_th) {
         radSq *= 0.75 * 0.75;
-        // swap-with-last removal, sequential semantics (lane 0 does it; the list is short-lived)
-        if (W.lane == 0) {
-            int m = n;
-            for (int i = 0; i < m; i++) {
-                const unsigned pk = W.reg[i];
-                if (l_distsq(xc, yc, (double)(pk & 0xffff), (double)(pk >> 16)) > radSq) {
-                    l_clr_used(W, (long long)(pk >> 16) * W.w + (pk & 0xffff));
-                    const unsigned last = W.reg[m - 1];
-                    W.reg[i] = last; W.reg[m - 1] = pk;
-                    m--; i--;
-                }
+        // pass 1: count the kept points, un-mark the removed ones
+        int kept = 0;
+#pragma unroll 1
+        for (int b = 0; b < n; b += 32) {
+            const int i = b + lane;
+            bool keep = false;
+            if (i < n) {
+                const unsigned pk = reg[i];
+                keep = !(l_distsq(xc, yc, (double)(pk & 0xffff), (double)(pk >> 16)) > radSq);
+                if (!keep) used[(int)(pk >> 16) * w + (int)(pk & 0xffff)] = 0;
             }
-            n = m;
+            kept += __popc(__ballot_sync(0xffffffffu, keep));
         }
-        n = __shfl_sync(0xffffffffu, n, 0);
+        const int m2 = kept;
+        // pass 2: fill the holes below m2 (ascending) with the kept points at or above m2 (descending)
+        int lo = 0;                      // next hole chunk start (ascending, < m2)
+        int hi = n;                      // filler cursor: positions [m2, hi) not yet consumed
+        int nfill = 0, fpos = 0;         // fillers staged in s_fill[fpos .. nfill)
+        while (lo < m2) {
+            const int i = lo + lane;
+            unsigned pk = 0; bool hole = false;
+            if (i < m2) { pk = reg[i]; hole = l_distsq(xc, yc, (double)(pk & 0xffff), (double)(pk >> 16)) > radSq; }
+            unsigned hm = __ballot_sync(0xffffffffu, hole);
+            while (hm) {
+                if (fpos == nfill) {     // stage the next (up to 32) fillers, descending from hi
+                    nfill = 0; fpos = 0;
+                    while (nfill == 0 && hi > m2) {
+                        const int j = hi - 1 - lane;
+                        unsigned fk = 0; bool isf = false;
+                        if (j >= m2) { fk = reg[j]; isf = !(l_distsq(xc, yc, (double)(fk & 0xffff), (double)(fk >> 16)) > radSq); }
+                        const unsigned fm = __ballot_sync(0xffffffffu, isf);
+                        if (isf) s_fill[__popc(fm & ((1u << lane) - 1u))] = fk;
+                        nfill = __popc(fm);
+                        hi -= 32;
+                    }
+                    __syncwarp();
+                    if (nfill == 0) break;                      // cannot happen (holes below m2 == kept at/above m2)
+                }
+                const int t = min(__popc(hm), nfill - fpos);    // holes served in this step
+                const int r = __popc(hm & ((1u << lane) - 1u)); // this lane's rank among the pending holes
+                if (((hm >> lane) & 1u) && r < t) reg[i] = s_fill[fpos + r];
+                fpos += t;
+                // drop the t lowest set bits of hm
+                unsigned served = __ballot_sync(0xffffffffu, ((hm >> lane) & 1u) && r < t);
+                hm &= ~served;
+                __syncwarp();
+            }
+            lo += 32;
+        }
+        n = m2;
         __syncwarp();
-        if (n < 2) return false;
-        l_region2rect(W, n, reg_angle, prec, p, rec);
-        density = (double)n / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+        if (n < 2) { *n_io = n; return false; }
+        l_region2rect(n, reg_angle, prec, p, rec);
+        density = (double)n / (l_dist(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
     }
+    *n_io = n;
     return true;
 }
 
-__device__ bool l_refine(const Walk& W, int& n, double& reg_angle, double prec, double p, LRect& rec, double density_th) {
-    double density = (double)n / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+__device__ __noinline__ bool l_refine(int* n_io, double* reg_angle_io, double prec, double p, LRect* rec, double density_th) {
+    const int lane = threadIdx.x, w = s_W.w;
+    int n = *n_io;
+    double density = (double)n / (l_dist(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
     if (density >= density_th) return true;
-    const unsigned p0 = W.reg[0];
+    const unsigned* reg = s_W.reg; const float* __restrict__ ang = s_W.ang; uint8_t* used = s_W.used;
+    const unsigned p0 = reg[0];
     const int sx = p0 & 0xffff, sy = p0 >> 16;
     const double xc = (double)sx, yc = (double)sy;
-    const double ang_c = (double)W.ang[(long long)sy * W.w + sx] * L_DEG;
-    double sum = 0, s_sum = 0; int cnt = 0;
-    double* s0 = W.st; double* s1 = W.st + 32; double* s2 = W.st + 64;
+    const double ang_c = (double)ang[sy * w + sx] * L_DEG;
+    const double width = rec->width;
+    double* s0 = s_st; double* s1 = s_st + 32;
+    const double* sp = s_st + (lane & 1) * 32;        // lane parity picks the accumulator: sum of d / sum of d*d
+    double acc = 0; int cnt = 0;
+#pragma unroll 1
     for (int b = 0; b < n; b += 32) {
-        const int i = b + W.lane;
+        const int i = b + lane;
+        bool in = false;
         if (i < n) {
-            const unsigned pk = W.reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
-            const float ad = W.ang[(long long)ry * W.w + rx];
-            l_clr_used(W, (long long)ry * W.w + rx);
-            const bool in = l_dist(xc, yc, (double)rx, (double)ry) < rec.width;
+            const unsigned pk = reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
+            const float ad = ang[ry * w + rx];
+            used[ry * w + rx] = 0;
+            in = l_dist(xc, yc, (double)rx, (double)ry) < width;
             const double d = l_angle_diff_signed((double)ad * L_DEG, ang_c);
-            s0[W.lane] = d; s1[W.lane] = d * d; s2[W.lane] = in ? 1.0 : 0.0;
+            // skipped points contribute +0.0, which leaves a running sum unchanged (the sums are never -0.0)
+            s0[lane] = in ? d : 0.0; s1[lane] = in ? d * d : 0.0;
         }
+        cnt += __popc(__ballot_sync(0xffffffffu, in));
         __syncwarp();
-        const int m = min(32, n - b);
-        for (int j = 0; j < m; j++) if (s2[j] != 0.0) { sum += s0[j]; s_sum += s1[j]; ++cnt; }
+        acc = l_chunk_sum(sp, min(32, n - b), acc);
         __syncwarp();
     }
-    __syncwarp();
+    const double sum = __shfl_sync(0xffffffffu, acc, 0), s_sum = __shfl_sync(0xffffffffu, acc, 1);
     const double mean_angle = sum / (double)cnt;
     const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-    n = l_region_grow(W, sx, sy, tau, reg_angle);
+    n = l_region_grow(sx, sy, tau, reg_angle_io);
+    *n_io = n;
     if (n < 2) return false;
-    l_region2rect(W, n, reg_angle, prec, p, rec);
-    density = (double)n / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
-    if (density < density_th) return l_reduce_region_radius(W, n, reg_angle, prec, p, rec, density, density_th);
+    l_region2rect(n, *reg_angle_io, prec, p, rec);
+    density = (double)n / (l_dist(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
+    if (density < density_th) return l_reduce_region_radius(n_io, *reg_angle_io, prec, p, rec, density, density_th);
     return true;
 }
 
@@ -590,46 +679,47 @@ __device__ double l_rect_improve(const Walk& W, LRect& rec, int* s_cnt, double l
 // immutable angle map, so it is NOT done here: the walker emits one job per candidate region and k_lsd_nfa evaluates
 // all jobs of all frames in parallel (one warp per job).  `used` lives in shared memory as a bitmap.
 __global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ LineGeom g, LineWs ws) {
-    __shared__ double s_st[96];                                      // staging of 32-point chunks (3 quantities)
-    const int f = blockIdx.x;
-    Walk W;
-    W.w = g.sw; W.h = g.sh; W.npix = g.pix_stride; W.lane = threadIdx.x;
-    W.ang = ws.angdeg + f * g.pix_stride; W.cs = ws.cs + f * g.pix_stride; W.mod = ws.modgrad + f * g.pix_stride;
-    W.used = ws.used + f * g.pix_stride; W.reg = ws.reg + f * g.pix_stride; W.log_nt = g.log_nt; W.lgam = ws.lgam;
-    W.st = s_st; W.cs0 = ws.cs0 + f * g.pix_stride;
+    const int f = blockIdx.x, lane = threadIdx.x;
+    if (lane == 0) {
+        s_W.w = g.sw; s_W.h = g.sh;
+        s_W.ang = ws.angdeg + f * g.pix_stride; s_W.cs = ws.cs + f * g.pix_stride; s_W.mod = ws.modgrad + f * g.pix_stride;
+        s_W.used = ws.used + f * g.pix_stride; s_W.reg = ws.reg + f * g.pix_stride; s_W.cs0 = ws.cs0 + f * g.pix_stride;
+    }
+    __syncwarp();
+    const uint8_t* used = ws.used + f * g.pix_stride;
     const unsigned* seeds = ws.seeds + f * g.pix_stride;
     const int ns = ws.nseeds[f];
     double* jobs = ws.jobs + (long long)f * g.seg_cap * 13;
     int nj = 0;
     for (int sb = 0; sb < ns; sb += 32) {
-        const bool have = sb + W.lane < ns;
-        const unsigned mine = have ? seeds[sb + W.lane] : 0u;                   // 32 seeds per coalesced load
-        unsigned umask = __ballot_sync(0xffffffffu, !have || W.used[mine] != 0); // their `used` state, one round trip
+        const bool have = sb + lane < ns;
+        const unsigned mine = have ? seeds[sb + lane] : 0u;                   // 32 seeds per coalesced load
+        unsigned umask = __ballot_sync(0xffffffffu, !have || used[mine] != 0); // their `used` state, one round trip
         const int m = min(32, ns - sb);
         for (int j = 0; j < m; j++) {
             if ((umask >> j) & 1u) continue;                // angle != NOTDEF holds for every seed
             const unsigned idx = __shfl_sync(0xffffffffu, mine, j);
             double reg_angle;
-            int n = l_region_grow(W, (int)(idx % (unsigned)W.w), (int)(idx / (unsigned)W.w), g.prec, reg_angle);
-            umask = __ballot_sync(0xffffffffu, !have || W.used[mine] != 0);     // the region may have swallowed later seeds
+            int n = l_region_grow((int)(idx % (unsigned)g.sw), (int)(idx / (unsigned)g.sw), g.prec, &reg_angle);
+            umask = __ballot_sync(0xffffffffu, !have || used[mine] != 0);     // the region may have swallowed later seeds
             if (n < g.min_reg_size) continue;
             LRect rec;
-            l_region2rect(W, n, reg_angle, g.prec, g.p, rec);
+            l_region2rect(n, reg_angle, g.prec, g.p, &rec);
             const int n0 = n;
-            const bool okr = l_refine(W, n, reg_angle, g.prec, g.p, rec, 0.7);
-            umask = __ballot_sync(0xffffffffu, !have || W.used[mine] != 0);     // refine can release and re-take pixels
+            const bool okr = l_refine(&n, &reg_angle, g.prec, g.p, &rec, 0.7);
+            umask = __ballot_sync(0xffffffffu, !have || used[mine] != 0);     // refine can release and re-take pixels
             if (!okr) continue;
-            if (nj < g.seg_cap && W.lane < 13) {
+            if (nj < g.seg_cap && lane < 13) {
                 const double v[13] = {rec.x1, rec.y1, rec.x2, rec.y2, rec.width, rec.x, rec.y, rec.theta, rec.dx, rec.dy, rec.prec, rec.p, (double)idx * 65536.0 + (double)min(n0, 65535)};
                 double out = v[0];
 #pragma unroll
-                for (int k = 1; k < 13; k++) if (W.lane == k) out = v[k];
-                jobs[(long long)nj * 13 + W.lane] = out;
+                for (int k = 1; k < 13; k++) if (lane == k) out = v[k];
+                jobs[(long long)nj * 13 + lane] = out;
             }
             nj++;
         }
     }
-    if (W.lane == 0) { ws.njobs[f] = min(nj, g.seg_cap); if (nj > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
+    if (lane == 0) { ws.njobs[f] = min(nj, g.seg_cap); if (nj > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
 }
 
 // NFA of every candidate region of every frame, in three data-parallel steps:
@@ -640,7 +730,7 @@ __global__ void __launch_bounds__(128) k_lsd_nfa_count(const __grid_constant__ L
     const int f = blockIdx.y, j = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (j >= ws.njobs[f]) return;
     Walk W;
-    W.w = g.sw; W.h = g.sh; W.npix = g.pix_stride; W.lane = threadIdx.x & 31; W.ang = ws.angdeg + f * g.pix_stride;
+    W.w = g.sw; W.h = g.sh; W.lane = threadIdx.x & 31; W.ang = ws.angdeg + f * g.pix_stride; W.log_nt = g.log_nt; W.lgam = ws.lgam;
     const double* job = ws.jobs + ((long long)f * g.seg_cap + j) * 13;
     LRect rec;
     rec.x1 = job[0]; rec.y1 = job[1]; rec.x2 = job[2]; rec.y2 = job[3]; rec.width = job[4]; rec.theta = job[7]; rec.dx = job[8]; rec.dy = job[9]; rec.prec = job[10];
@@ -669,9 +759,8 @@ __global__ void __launch_bounds__(128) k_lsd_nfa_improve(const __grid_constant__
     double* job = ws.jobs + q * 13;
     if (!(log_nfa > 0.0)) {
         Walk W;
-        W.w = g.sw; W.h = g.sh; W.npix = g.pix_stride; W.lane = threadIdx.x & 31;
-        W.ang = ws.angdeg + f * g.pix_stride; W.cs = nullptr; W.mod = nullptr; W.used = nullptr; W.reg = nullptr;
-        W.log_nt = g.log_nt; W.lgam = ws.lgam; W.st = nullptr; W.cs0 = nullptr;
+        W.w = g.sw; W.h = g.sh; W.lane = threadIdx.x & 31;
+        W.ang = ws.angdeg + f * g.pix_stride; W.log_nt = g.log_nt; W.lgam = ws.lgam;
         LRect rec;
         rec.x1 = job[0]; rec.y1 = job[1]; rec.x2 = job[2]; rec.y2 = job[3]; rec.width = job[4]; rec.x = job[5]; rec.y = job[6];
         rec.theta = job[7]; rec.dx = job[8]; rec.dy = job[9]; rec.prec = job[10]; rec.p = job[11];
