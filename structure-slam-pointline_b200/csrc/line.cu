@@ -43,9 +43,13 @@ struct LineGeom {
     int trace_cap;              // rows of the debug trace per frame (0 = off)
 };
 
+// What region growing reads per neighbour, in one 16-byte load: level-line angle (degrees, NOTDEF_F when undefined),
+// (float)cos / sin of (float)(angle in radians) — the values region_grow sums — and the mutable `used` flag.
+struct __align__(16) LPix { float ang, cx, cy; unsigned used; };
+
 struct LineWs {
     uint8_t* blur7; uint8_t* blur5; uint8_t* scaled;
-    float* angdeg; float2* cs; float2* cs0; double* modgrad; uint8_t* used;
+    float* angdeg; LPix* pix; float2* cs0; double* modgrad;
     unsigned long long* maxgrad; unsigned* seeds; int* nseeds;
     unsigned* reg;              // region pixel list (x | y << 16)
     double* seg;                // raw rectangles: x1,y1,x2,y2 (detection scale, before +0.5)
@@ -138,7 +142,9 @@ __global__ void __launch_bounds__(256) k_ll_angle(const __grid_constant__ LineGe
                 cs0.x = (float)cos(ad); cs0.y = (float)sin(ad);
             }
         }
-        ws.angdeg[pi] = ang; ws.cs[pi] = cs; ws.cs0[pi] = cs0; ws.modgrad[pi] = norm; ws.used[pi] = 0;
+        ws.angdeg[pi] = ang; ws.cs0[pi] = cs0; ws.modgrad[pi] = norm;
+        LPix px; px.ang = ang; px.cx = cs.x; px.cy = cs.y; px.used = 0u;
+        ws.pix[pi] = px;
     }
     unsigned long long bits = defined ? (unsigned long long)__double_as_longlong(norm) : 0ull;   // positive doubles order like integers
 #pragma unroll
@@ -213,8 +219,8 @@ struct Walk {                   // context of the rectangle scans (k_lsd_nfa_*):
 
 struct WalkCtx {                // context of the walker (k_lsd_regions): shared memory
     int w, h;
-    const float* ang; const float2* cs; const double* mod;
-    uint8_t* used;              // byte map in global memory (L1-resident; only this warp touches it)
+    const float* ang; const double* mod;
+    LPix* pix;                  // packed per-pixel record incl. the `used` flag (only this warp touches the frame's flags)
     unsigned* reg;              // region pixel list (x | y << 16)
     const float2* cs0;          // per pixel: (float)cos / sin of the level-line angle taken as double (region seed values)
 };
@@ -237,49 +243,63 @@ __device__ __forceinline__ bool l_aligned_rad(double a, double theta, double pre
     return n <= prec;
 }
 
+// region_grow (lsd.cpp).  FOUR queue entries are expanded per step: lane = 8 * slot + neighbour (the centre pixel is
+// always used, so the 3x3 scan has 8 live neighbours, kept in the reference's yy-outer / xx-inner order), i.e. the 32
+// lanes hold the next 32 neighbour tests of the sequential algorithm in order.  Sequential semantics (each neighbour
+// is tested once, in scan order, against the region angle as updated by the neighbours accepted before it) are kept
+// in as many rounds as there are acceptances: all pending lanes test against the current angle; the first passing
+// lane k0 is accepted, lanes < k0 are definitively rejected (they saw exactly the angle the sequential scan would have
+// shown them), later lanes holding the same pixel drop out (the scan would find it used).
 __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* reg_angle_out) {
     const int lane = threadIdx.x, w = s_W.w, h = s_W.h;
-    const float* __restrict__ ang = s_W.ang; const float2* __restrict__ cs = s_W.cs;
-    uint8_t* used = s_W.used; unsigned* reg = s_W.reg;
+    LPix* pix = s_W.pix; unsigned* reg = s_W.reg;
     const int sq = sy * w + sx;                                   // 32-bit pixel indices (sw * sh < 2^31)
-    if (lane == 0) { reg[0] = (unsigned)sx | ((unsigned)sy << 16); used[sq] = 1; }
-    double reg_angle = (double)__ldg(ang + sq) * L_DEG;
+    if (lane == 0) { reg[0] = (unsigned)sx | ((unsigned)sy << 16); pix[sq].used = 1u; }
+    double reg_angle = (double)__ldg(s_W.ang + sq) * L_DEG;
     const float2 c0 = __ldg(s_W.cs0 + sq);
     float sumdx = c0.x, sumdy = c0.y;
     int n = 1;
-    const int ox = lane % 3 - 1, oy = lane / 3 - 1, doff = oy * w + ox;   // this lane's neighbour (yy outer, xx inner: scan order of lsd.cpp)
+    const int slot = lane >> 3, nb = (lane & 7) + ((lane & 7) >= 4 ? 1 : 0);   // neighbour 0..8 without the centre (4)
+    const int ox = nb % 3 - 1, oy = nb / 3 - 1;
     __syncwarp();
-    for (int i = 0; i < n; i++) {
-        const unsigned pk = reg[i];
-        const int px = pk & 0xffff, py = pk >> 16;
-        const int xx = px + ox, yy = py + oy, q = py * w + px + doff;
-        const bool valid = lane < 9 && (unsigned)xx < (unsigned)w && (unsigned)yy < (unsigned)h;
-        float a = NOTDEF_F; float2 c = make_float2(0.f, 0.f); bool u = true;
+    for (int i = 0; i < n;) {
+        const int cnt = min(4, n - i);
+        unsigned pk = 0, pkn = 0;
+        if (slot < cnt) pk = reg[i + slot];
+        const bool hasn = i + 4 + slot < n;                      // the next step's entries, where they already exist:
+        if (hasn) pkn = reg[i + 4 + slot];                       // pull their neighbour records towards L1 now
+        const int xx = (int)(pk & 0xffff) + ox, yy = (int)(pk >> 16) + oy, q = yy * w + xx;
+        const bool valid = slot < cnt && (unsigned)xx < (unsigned)w && (unsigned)yy < (unsigned)h;
+        {
+            const int xn = (int)(pkn & 0xffff) + ox, yn = (int)(pkn >> 16) + oy;
+            if (hasn && (unsigned)xn < (unsigned)w && (unsigned)yn < (unsigned)h)
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(pix + (yn * w + xn)));
+        }
+        float a = NOTDEF_F, cx = 0.f, cy = 0.f; unsigned u = 1u;
         if (valid) {
-            a = __ldg(ang + q); c = __ldg(cs + q);
-            u = used[q] != 0;
+            const uint4 v = *reinterpret_cast<const uint4*>(pix + q);
+            a = __uint_as_float(v.x); cx = __uint_as_float(v.y); cy = __uint_as_float(v.z); u = v.w;
         }
         const double ad = (double)a * L_DEG;
-        // Sequential semantics (each neighbour is tested once, in scan order, against the region angle as updated by
-        // the neighbours accepted before it) in as many rounds as there are acceptances: all pending lanes test
-        // against the current angle; the first passing lane k0 is accepted, lanes < k0 are definitively rejected
-        // (they saw exactly the angle the sequential scan would have shown them).
-        unsigned pending = __ballot_sync(0xffffffffu, !u && a != NOTDEF_F);
+        unsigned pending = __ballot_sync(0xffffffffu, u == 0u && a != NOTDEF_F);
         while (pending) {
-            const unsigned okm = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && l_aligned_rad(ad, reg_angle, prec)) & pending;
+            const unsigned okm = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && l_aligned_rad(ad, reg_angle, prec));
             if (!okm) break;
             const int k0 = __ffs(okm) - 1;
-            const float cx = __shfl_sync(0xffffffffu, c.x, k0), cy = __shfl_sync(0xffffffffu, c.y, k0);
+            const float kx = __shfl_sync(0xffffffffu, cx, k0), ky = __shfl_sync(0xffffffffu, cy, k0);
+            const int q0 = __shfl_sync(0xffffffffu, q, k0);
             if (lane == k0) {                                     // the accepted lane records its own pixel
                 reg[n] = (unsigned)xx | ((unsigned)yy << 16);
-                used[q] = 1;
+                pix[q].used = 1u;
             }
             n++;
-            sumdx += cx; sumdy += cy;
+            sumdx += kx; sumdy += ky;
             reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * L_DEG;
             pending &= ~((2u << k0) - 1u);
+            pending &= ~__ballot_sync(0xffffffffu, q == q0);      // the same pixel seen from another queue entry
         }
         __syncwarp();
+        i += cnt;
     }
     *reg_angle_out = reg_angle;
     return n;
@@ -386,7 +406,7 @@ __device__ __forceinline__ double l_distsq(double x1, double y1, double x2, doub
 // irrelevant (those points are only un-marked).
 __device__ __noinline__ bool l_reduce_region_radius(int* n_io, double reg_angle, double prec, double p, LRect* rec, double density, double density_th) {
     const int lane = threadIdx.x, w = s_W.w;
-    unsigned* reg = s_W.reg; uint8_t* used = s_W.used;
+    unsigned* reg = s_W.reg; LPix* pix = s_W.pix;
     unsigned* s_fill = reinterpret_cast<unsigned*>(s_st);             // 32 filler values (s_st is free between region2rect calls)
     int n = *n_io;
     const unsigned p0 = reg[0];
@@ -403,7 +423,7 @@ __device__ __noinline__ bool l_reduce_region_radius(int* n_io, double reg_angle,
             if (i < n) {
                 const unsigned pk = reg[i];
                 keep = !(l_distsq(xc, yc, (double)(pk & 0xffff), (double)(pk >> 16)) > radSq);
-                if (!keep) used[(int)(pk >> 16) * w + (int)(pk & 0xffff)] = 0;
+                if (!keep) pix[(int)(pk >> 16) * w + (int)(pk & 0xffff)].used = 0u;
             }
             kept += __popc(__ballot_sync(0xffffffffu, keep));
         }
@@ -458,7 +478,7 @@ __device__ __noinline__ bool l_refine(int* n_io, double* reg_angle_io, double pr
     int n = *n_io;
     double density = (double)n / (l_dist(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
     if (density >= density_th) return true;
-    const unsigned* reg = s_W.reg; const float* __restrict__ ang = s_W.ang; uint8_t* used = s_W.used;
+    const unsigned* reg = s_W.reg; const float* __restrict__ ang = s_W.ang; LPix* pix = s_W.pix;
     const unsigned p0 = reg[0];
     const int sx = p0 & 0xffff, sy = p0 >> 16;
     const double xc = (double)sx, yc = (double)sy;
@@ -474,7 +494,7 @@ __device__ __noinline__ bool l_refine(int* n_io, double* reg_angle_io, double pr
         if (i < n) {
             const unsigned pk = reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
             const float ad = ang[ry * w + rx];
-            used[ry * w + rx] = 0;
+            pix[ry * w + rx].used = 0u;
             in = l_dist(xc, yc, (double)rx, (double)ry) < width;
             const double d = l_angle_diff_signed((double)ad * L_DEG, ang_c);
             // skipped points contribute +0.0, which leaves a running sum unchanged (the sums are never -0.0)
@@ -682,11 +702,11 @@ __global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ Line
     const int f = blockIdx.x, lane = threadIdx.x;
     if (lane == 0) {
         s_W.w = g.sw; s_W.h = g.sh;
-        s_W.ang = ws.angdeg + f * g.pix_stride; s_W.cs = ws.cs + f * g.pix_stride; s_W.mod = ws.modgrad + f * g.pix_stride;
-        s_W.used = ws.used + f * g.pix_stride; s_W.reg = ws.reg + f * g.pix_stride; s_W.cs0 = ws.cs0 + f * g.pix_stride;
+        s_W.ang = ws.angdeg + f * g.pix_stride; s_W.mod = ws.modgrad + f * g.pix_stride;
+        s_W.pix = ws.pix + f * g.pix_stride; s_W.reg = ws.reg + f * g.pix_stride; s_W.cs0 = ws.cs0 + f * g.pix_stride;
     }
     __syncwarp();
-    const uint8_t* used = ws.used + f * g.pix_stride;
+    const LPix* pix = ws.pix + f * g.pix_stride;
     const unsigned* seeds = ws.seeds + f * g.pix_stride;
     const int ns = ws.nseeds[f];
     double* jobs = ws.jobs + (long long)f * g.seg_cap * 13;
@@ -694,20 +714,20 @@ __global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ Line
     for (int sb = 0; sb < ns; sb += 32) {
         const bool have = sb + lane < ns;
         const unsigned mine = have ? seeds[sb + lane] : 0u;                   // 32 seeds per coalesced load
-        unsigned umask = __ballot_sync(0xffffffffu, !have || used[mine] != 0); // their `used` state, one round trip
-        const int m = min(32, ns - sb);
-        for (int j = 0; j < m; j++) {
-            if ((umask >> j) & 1u) continue;                // angle != NOTDEF holds for every seed
+        unsigned umask = __ballot_sync(0xffffffffu, !have || pix[mine].used != 0u); // their `used` state, one round trip
+        while (~umask) {                                    // angle != NOTDEF holds for every seed
+            const int j = __ffs(~umask) - 1;
+            umask |= (2u << j) - 1u;                        // seeds up to j are done
             const unsigned idx = __shfl_sync(0xffffffffu, mine, j);
             double reg_angle;
             int n = l_region_grow((int)(idx % (unsigned)g.sw), (int)(idx / (unsigned)g.sw), g.prec, &reg_angle);
-            umask = __ballot_sync(0xffffffffu, !have || used[mine] != 0);     // the region may have swallowed later seeds
+            umask |= __ballot_sync(0xffffffffu, !have || pix[mine].used != 0u);    // the region may have swallowed later seeds
             if (n < g.min_reg_size) continue;
             LRect rec;
             l_region2rect(n, reg_angle, g.prec, g.p, &rec);
             const int n0 = n;
             const bool okr = l_refine(&n, &reg_angle, g.prec, g.p, &rec, 0.7);
-            umask = __ballot_sync(0xffffffffu, !have || used[mine] != 0);     // refine can release and re-take pixels
+            umask = ((2u << j) - 1u) | __ballot_sync(0xffffffffu, !have || pix[mine].used != 0u);   // refine can release and re-take pixels
             if (!okr) continue;
             if (nj < g.seg_cap && lane < 13) {
                 const double v[13] = {rec.x1, rec.y1, rec.x2, rec.y2, rec.width, rec.x, rec.y, rec.theta, rec.dx, rec.dy, rec.prec, rec.p, (double)idx * 65536.0 + (double)min(n0, 65535)};
@@ -1044,8 +1064,8 @@ void carve(sslpl_line* h, Arena& A, const LineGeom& g, int B) {
     h->d_input = A.take<uint8_t>((size_t)B * g.in_stride + 256);
     ws.blur7 = A.take<uint8_t>((size_t)B * g.blur_stride); ws.blur5 = A.take<uint8_t>((size_t)B * g.blur_stride);
     ws.scaled = A.take<uint8_t>((size_t)B * g.scaled_stride);
-    ws.angdeg = A.take<float>((size_t)B * g.pix_stride); ws.cs = A.take<float2>((size_t)B * g.pix_stride);
-    ws.modgrad = A.take<double>((size_t)B * g.pix_stride); ws.cs0 = A.take<float2>((size_t)B * g.pix_stride); ws.used = A.take<uint8_t>((size_t)B * g.pix_stride);
+    ws.angdeg = A.take<float>((size_t)B * g.pix_stride); ws.pix = A.take<LPix>((size_t)B * g.pix_stride);
+    ws.modgrad = A.take<double>((size_t)B * g.pix_stride); ws.cs0 = A.take<float2>((size_t)B * g.pix_stride);
     ws.maxgrad = A.take<unsigned long long>(B);
     ws.seeds = A.take<unsigned>((size_t)B * g.pix_stride); ws.nseeds = A.take<int>(B);
     ws.reg = A.take<unsigned>((size_t)B * g.pix_stride);
