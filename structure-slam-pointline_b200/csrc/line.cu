@@ -56,6 +56,7 @@ struct LineWs {
     int* nseg;
     double* jobs; int* njobs; int* jobflag;   // NFA jobs: 13 doubles per candidate region (LRect + log_nfa), in walker order
     int2* jobnk; double* jobnfa;              // per job: (total, aligned) pixel counts and NFA of the unmodified rectangle
+    int2* rej; int* rejctl;                   // work list of rejected jobs (frame, job); rejctl[0] = count, rejctl[1] = cursor
     int16_t* dx; int16_t* dy;
     int2* tab;
     float* resp; float4* ext;   // per raw segment: response and clamped extremes
@@ -136,10 +137,15 @@ __global__ void __launch_bounds__(256) k_ll_angle(const __grid_constant__ LineGe
             if (norm > g.rho) {
                 defined = true;
                 ang = fast_atan2_deg((float)gx, (float)-gy);
-                const float a = (float)((double)ang * L_DEG);
-                cs.x = (float)cos((double)a); cs.y = (float)sin((double)a);
-                const double ad = (double)ang * L_DEG;                    // region_grow's seed: float(cos(reg_angle))
-                cs0.x = (float)cos(ad); cs0.y = (float)sin(ad);
+                const double ad = (double)ang * L_DEG;
+                const float a = (float)ad;
+                double sn, cn;
+                sincos((double)a, &sn, &cn);
+                cs.x = (float)cn; cs.y = (float)sn;
+                // region_grow's seed values float(cos(ad)), float(sin(ad)): ad = a + d with |d| < 2e-7, so a second-order
+                // Taylor step from (cn, sn) is accurate to a few double ulps (the d^3 term is < 1e-20) — one sincos, not four calls
+                const double d = ad - (double)a, hd2 = 0.5 * d * d;
+                cs0.x = (float)(cn - sn * d - cn * hd2); cs0.y = (float)(sn + cn * d - sn * hd2);
             }
         }
         ws.angdeg[pi] = ang; ws.cs0[pi] = cs0; ws.modgrad[pi] = norm;
@@ -547,8 +553,23 @@ __device__ double l_nfa(int n, int k, double p, double LOG_NT, const double* lga
         term *= mult_term;
         bin_tail += term;
         if (bin_term < 1) {
-            const double err = term * ((1 - pow(mult_term, (double)(n - i + 1))) / (1 - mult_term) - 1);
-            if (err < 0.1 * fabs(-log10(bin_tail) - LOG_NT) * bin_tail) break;
+            // pow(mult_term, m) < 2^-56 whenever mult_term < 1/4 and m >= 28; then 1 - pow rounds to exactly 1.0: skipping
+            // the call is bit-identical (mult_term = bin_term * p / (1 - p) < 1/7 here for every p <= 1/8)
+            const int m = n - i + 1;
+            const double pw = (m >= 28 && mult_term < 0.25) ? 0.0 : pow(mult_term, (double)m);
+            const double err = term * ((1 - pw) / (1 - mult_term) - 1);
+            // threshold 0.1 * |-log10(bin_tail) - LOG_NT| * bin_tail: bracket log10 by the binary exponent first and
+            // evaluate the logarithm only when the bracket cannot decide (same decision as the plain test, always)
+            bool stop;
+            const int e2 = ilogb(bin_tail);
+            if (e2 > -1000 && e2 < 1000) {
+                const double l_lo = -((double)(e2 + 1) * 0.30102999566398120) - LOG_NT, l_hi = -((double)e2 * 0.30102999566398120) - LOG_NT;  // L in [l_lo, l_hi]
+                const double a_lo = (l_lo > 0) ? l_lo : ((l_hi < 0) ? -l_hi : 0.0), a_hi = fmax(fabs(l_lo), fabs(l_hi));
+                if (err < 0.1 * a_lo * bin_tail * (1 - 1e-9)) stop = true;
+                else if (err >= 0.1 * a_hi * bin_tail * (1 + 1e-9)) stop = false;
+                else stop = err < 0.1 * fabs(-log10(bin_tail) - LOG_NT) * bin_tail;
+            } else stop = err < 0.1 * fabs(-log10(bin_tail) - LOG_NT) * bin_tail;
+            if (stop) break;
         }
     }
     return -log10(bin_tail) - LOG_NT;
@@ -742,64 +763,87 @@ __global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ Line
     if (lane == 0) { ws.njobs[f] = min(nj, g.seg_cap); if (nj > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
 }
 
-// NFA of every candidate region of every frame, in three data-parallel steps:
+// NFA of every candidate region of every frame, in three data-parallel steps (grids are sized by the work, not by the
+// per-frame capacity seg_cap, which is ~13k slots of which a few hundred are used):
 //   k_lsd_nfa_count   one warp per job: the rectangle scan (total / aligned pixel counts)
-//   k_lsd_nfa_first   one THREAD per job: the scalar NFA formula (32 jobs per warp side by side); most jobs are accepted here
-//   k_lsd_nfa_improve one warp per still-rejected job: the five refinement phases of rect_improve
+//   k_lsd_nfa_first   one THREAD per job: the scalar NFA formula (32 jobs per warp side by side); most jobs are accepted
+//                     here, the others are appended to a global work list
+//   k_lsd_nfa_improve persistent warps pull rejected jobs from that list: the five refinement phases of rect_improve
+constexpr int NFA_COUNT_CTAS = 16;          // CTAs (4 warps) per frame in k_lsd_nfa_count
+constexpr int NFA_FIRST_CTAS = 2;           // CTAs (128 threads) per frame in k_lsd_nfa_first
+
+__device__ __forceinline__ void l_trace_row(const LineGeom& g, const LineWs& ws, int f, int j, const double* job, double tag, double log_nfa) {
+    if (g.trace_cap && j < g.trace_cap) {
+        double* t = ws.trace + ((long long)f * g.trace_cap + j) * 10;
+        const double idx = floor(tag / 65536.0);
+        t[0] = idx; t[1] = tag - idx * 65536.0; t[2] = 0; t[3] = log_nfa;
+        t[4] = job[0]; t[5] = job[1]; t[6] = job[2]; t[7] = job[3]; t[8] = job[4]; t[9] = job[11];
+    }
+}
+
 __global__ void __launch_bounds__(128) k_lsd_nfa_count(const __grid_constant__ LineGeom g, LineWs ws) {
-    const int f = blockIdx.y, j = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (j >= ws.njobs[f]) return;
+    const int f = blockIdx.y, nj = ws.njobs[f];
     Walk W;
     W.w = g.sw; W.h = g.sh; W.lane = threadIdx.x & 31; W.ang = ws.angdeg + f * g.pix_stride; W.log_nt = g.log_nt; W.lgam = ws.lgam;
-    const double* job = ws.jobs + ((long long)f * g.seg_cap + j) * 13;
-    LRect rec;
-    rec.x1 = job[0]; rec.y1 = job[1]; rec.x2 = job[2]; rec.y2 = job[3]; rec.width = job[4]; rec.theta = job[7]; rec.dx = job[8]; rec.dy = job[9]; rec.prec = job[10];
-    int total, alg;
-    l_rect_count(W, rec, total, alg);
-    if (W.lane == 0) ws.jobnk[(long long)f * g.seg_cap + j] = make_int2(total, alg);
+    for (int j = blockIdx.x * 4 + (threadIdx.x >> 5); j < nj; j += NFA_COUNT_CTAS * 4) {
+        const double* job = ws.jobs + ((long long)f * g.seg_cap + j) * 13;
+        LRect rec;
+        rec.x1 = job[0]; rec.y1 = job[1]; rec.x2 = job[2]; rec.y2 = job[3]; rec.width = job[4]; rec.theta = job[7]; rec.dx = job[8]; rec.dy = job[9]; rec.prec = job[10];
+        int total, alg;
+        l_rect_count(W, rec, total, alg);
+        if (W.lane == 0) ws.jobnk[(long long)f * g.seg_cap + j] = make_int2(total, alg);
+    }
 }
 
 __global__ void __launch_bounds__(128) k_lsd_nfa_first(const __grid_constant__ LineGeom g, LineWs ws) {
-    const int f = blockIdx.y, j = blockIdx.x * 128 + threadIdx.x;
-    if (j >= ws.njobs[f]) return;
-    const long long q = (long long)f * g.seg_cap + j;
-    const int2 nk = ws.jobnk[q];
-    double* job = ws.jobs + q * 13;
-    const double v = l_nfa(nk.x, nk.y, job[11], g.log_nt, ws.lgam);
-    ws.jobflag[q] = v > 0.0 ? 1 : 0;
-    ws.jobnfa[q] = v;
+    const int f = blockIdx.y, nj = ws.njobs[f];
+    for (int j = blockIdx.x * 128 + threadIdx.x; j < nj; j += NFA_FIRST_CTAS * 128) {
+        const long long q = (long long)f * g.seg_cap + j;
+        const int2 nk = ws.jobnk[q];
+        double* job = ws.jobs + q * 13;
+        const double v = l_nfa(nk.x, nk.y, job[11], g.log_nt, ws.lgam);
+        if (v > 0.0) {
+            const double tag = job[12];
+            ws.jobflag[q] = 1; job[12] = v;
+            l_trace_row(g, ws, f, j, job, tag, v);
+        } else {
+            ws.jobflag[q] = 0; ws.jobnfa[q] = v;
+            ws.rej[atomicAdd(ws.rejctl, 1)] = make_int2(f, j);     // order is irrelevant: results go back to the job slot
+        }
+    }
 }
 
 __global__ void __launch_bounds__(128) k_lsd_nfa_improve(const __grid_constant__ LineGeom g, LineWs ws) {
     __shared__ int s_cnt[4][10];
-    const int f = blockIdx.y, j = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (j >= ws.njobs[f]) return;
-    const long long q = (long long)f * g.seg_cap + j;
-    double log_nfa = ws.jobnfa[q];
-    double* job = ws.jobs + q * 13;
-    if (!(log_nfa > 0.0)) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nrej = ws.rejctl[0];
+    for (;;) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(ws.rejctl + 1, 1);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= nrej) break;
+        const int2 fj = ws.rej[r];
+        const int f = fj.x, j = fj.y;
+        const long long q = (long long)f * g.seg_cap + j;
+        double log_nfa = ws.jobnfa[q];
+        double* job = ws.jobs + q * 13;
         Walk W;
-        W.w = g.sw; W.h = g.sh; W.lane = threadIdx.x & 31;
+        W.w = g.sw; W.h = g.sh; W.lane = lane;
         W.ang = ws.angdeg + f * g.pix_stride; W.log_nt = g.log_nt; W.lgam = ws.lgam;
         LRect rec;
         rec.x1 = job[0]; rec.y1 = job[1]; rec.x2 = job[2]; rec.y2 = job[3]; rec.width = job[4]; rec.x = job[5]; rec.y = job[6];
         rec.theta = job[7]; rec.dx = job[8]; rec.dy = job[9]; rec.prec = job[10]; rec.p = job[11];
-        log_nfa = l_rect_improve(W, rec, s_cnt[threadIdx.x >> 5], log_nfa);
+        const double tag = job[12];
         __syncwarp();
-        if (W.lane == 0) {
+        log_nfa = l_rect_improve(W, rec, s_cnt[wid], log_nfa);
+        __syncwarp();
+        if (lane == 0) {
             job[0] = rec.x1; job[1] = rec.y1; job[2] = rec.x2; job[3] = rec.y2; job[4] = rec.width; job[11] = rec.p;
             ws.jobflag[q] = log_nfa > 0.0 ? 1 : 0;
+            job[12] = log_nfa;
+            l_trace_row(g, ws, f, j, job, tag, log_nfa);
         }
-    }
-    if ((threadIdx.x & 31) == 0) {
-        const double tag = job[12];
-        job[12] = log_nfa;
-        if (g.trace_cap && j < g.trace_cap) {
-            double* t = ws.trace + ((long long)f * g.trace_cap + j) * 10;
-            const double idx = floor(tag / 65536.0);
-            t[0] = idx; t[1] = tag - idx * 65536.0; t[2] = 0; t[3] = log_nfa;
-            t[4] = job[0]; t[5] = job[1]; t[6] = job[2]; t[7] = job[3]; t[8] = job[4]; t[9] = job[11];
-        }
+        __syncwarp();
     }
 }
 
@@ -1007,6 +1051,7 @@ struct sslpl_line {
     LbdCoef coef;
     bool trace = false;
     int used_smem = 0;
+    int sm_count = 148;
     int cur_w = 0, cur_h = 0, cur_frames = 0;
     long long launches = 0;
     int* h_err = nullptr;
@@ -1072,6 +1117,7 @@ void carve(sslpl_line* h, Arena& A, const LineGeom& g, int B) {
     ws.seg = A.take<double>((size_t)B * g.seg_cap * 4); ws.nseg = A.take<int>(B);
     ws.jobs = A.take<double>((size_t)B * g.seg_cap * 13); ws.njobs = A.take<int>(B); ws.jobflag = A.take<int>((size_t)B * g.seg_cap);
     ws.jobnk = A.take<int2>((size_t)B * g.seg_cap); ws.jobnfa = A.take<double>((size_t)B * g.seg_cap);
+    ws.rej = A.take<int2>((size_t)B * g.seg_cap); ws.rejctl = A.take<int>(2);
 
     ws.dx = A.take<int16_t>((size_t)B * g.full_stride); ws.dy = A.take<int16_t>((size_t)B * g.full_stride);
     ws.tab = A.take<int2>(g.sw + g.sh);
@@ -1133,15 +1179,16 @@ int run_pipeline(sslpl_line* h, int B) {
     lmark(h, "lsd_seeds");
     k_lsd_regions<<<B, 32, 0, st>>>(g, h->ws);
     lmark(h, "lsd_regions");
-    k_lsd_nfa_count<<<dim3((g.seg_cap + 3) / 4, B), 128, 0, st>>>(g, h->ws);
-    k_lsd_nfa_first<<<dim3((g.seg_cap + 127) / 128, B), 128, 0, st>>>(g, h->ws);
-    k_lsd_nfa_improve<<<dim3((g.seg_cap + 3) / 4, B), 128, 0, st>>>(g, h->ws);
+    SSLPL_CUDA(cudaMemsetAsync(h->ws.rejctl, 0, 2 * sizeof(int), st));
+    k_lsd_nfa_count<<<dim3(NFA_COUNT_CTAS, B), 128, 0, st>>>(g, h->ws);
+    k_lsd_nfa_first<<<dim3(NFA_FIRST_CTAS, B), 128, 0, st>>>(g, h->ws);
+    k_lsd_nfa_improve<<<std::min(h->sm_count * 8, (B * 64 + 3) / 4), 128, 0, st>>>(g, h->ws);
     lmark(h, "lsd_nfa");
     k_keylines<<<B, 256, 0, st>>>(g, h->ws);
     k_sobel<<<dim3((g.w + 31) / 32, (g.h + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
     k_lbd<<<dim3(g.kl_cap, B), 64, 0, st>>>(g, h->ws, h->coef);
     lmark(h, "keylines_lbd");
-    h->launches += 12;
+    h->launches += 12;     // kernels only (the two small memsets are not counted)
     SSLPL_CUDA(cudaGetLastError());
     return SSLPL_OK;
 }
@@ -1170,6 +1217,7 @@ int sslpl_line_create(const sslpl_line_params* p, sslpl_line** out) {
     SSLPL_CUDA(cudaSetDevice(p->device));
     sslpl_line* h = new sslpl_line();
     h->p = *p;
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && v > 0) h->sm_count = v; }
     h->trace = getenv("SSLPL_LINE_TRACE") != nullptr;
     {   // BinaryDescriptor constructor: local (F_l) and global (F_g) Gaussian weights, widthOfBand 7, 9 bands
         double u = (7 * 3 - 1) / 2, sigma = (7 * 2 + 1) / 2, inv = -1 / (2 * sigma * sigma);
