@@ -121,6 +121,26 @@ __global__ void __launch_bounds__(256) k_resize_exact(const __grid_constant__ Li
     ws.scaled[f * g.scaled_stride + (long long)y * g.spitch + x] = (uint8_t)((v0 * r0 + v1 * r1 + 32768) >> 16);
 }
 
+// sin / cos of x in [0, 2 pi] to ~1 ulp (double): Cody-Waite reduction by pi/2 and the fdlibm kernel polynomials.
+// Branch-free and table-free (libm's sincos drags its large-argument path and constant-bank tables through the
+// memory pipe); the callers round the results to float, which hides the last-ulp freedom.
+__device__ __forceinline__ void l_sincos_2pi(double x, double* s_out, double* c_out) {
+    const double k = rint(x * 0.6366197723675814);
+    const double r = (x - k * 1.57079632673412561417e+00) - k * 6.07710050650619224932e-11;
+    const double z = r * r;
+    double ps = 1.58969099521155010221e-10;
+    ps = -2.50507602534068634195e-08 + z * ps; ps = 2.75573137070700676789e-06 + z * ps; ps = -1.98412698298579493134e-04 + z * ps;
+    ps = 8.33333333332248946124e-03 + z * ps; ps = -1.66666666666666324348e-01 + z * ps;
+    const double s = r + r * (z * ps);
+    double pc = -1.13596475577881948265e-11;
+    pc = 2.08757232129817482790e-09 + z * pc; pc = -2.75573143513906633035e-07 + z * pc; pc = 2.48015872894767294178e-05 + z * pc;
+    pc = -1.38888888888741095749e-03 + z * pc; pc = 4.16666666666666019037e-02 + z * pc;
+    const double c = (1.0 - 0.5 * z) + z * (z * pc);
+    const int q = (int)k & 3;
+    *s_out = (q == 0) ? s : (q == 1) ? c : (q == 2) ? -s : -c;
+    *c_out = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
+}
+
 // ll_angle (lsd.cpp): 2x2 gradient, level-line angle, gradient norm, max over defined pixels
 __global__ void __launch_bounds__(256) k_ll_angle(const __grid_constant__ LineGeom g, LineWs ws) {
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
@@ -140,7 +160,7 @@ __global__ void __launch_bounds__(256) k_ll_angle(const __grid_constant__ LineGe
                 const double ad = (double)ang * L_DEG;
                 const float a = (float)ad;
                 double sn, cn;
-                sincos((double)a, &sn, &cn);
+                l_sincos_2pi((double)a, &sn, &cn);
                 cs.x = (float)cn; cs.y = (float)sn;
                 // region_grow's seed values float(cos(ad)), float(sin(ad)): ad = a + d with |d| < 2e-7, so a second-order
                 // Taylor step from (cn, sn) is accurate to a few double ulps (the d^3 term is < 1e-20) — one sincos, not four calls
@@ -171,15 +191,23 @@ __global__ void __launch_bounds__(1024) k_lsd_seeds(const __grid_constant__ Line
     extern __shared__ int s_wh[];                    // [32 warps][NBINS] running offsets
     __shared__ int s_warp[33];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const float* ang = ws.angdeg + f * g.pix_stride; const double* mod = ws.modgrad + f * g.pix_stride;
-    const double mg = __longlong_as_double((long long)ws.maxgrad[f]);
+    // a pixel is defined (angle != NOTDEF) exactly when its gradient norm exceeds rho (k_ll_angle): one array to read
+    const double* mod = ws.modgrad + f * g.pix_stride;
+    const double mg = __longlong_as_double((long long)ws.maxgrad[f]), rho = g.rho;
+    const double bin_coef = (mg > 0) ? double(NBINS - 1) / mg : 0;
     int* wh = s_wh + wid * NBINS;
     for (int i = tid; i < 32 * NBINS; i += 1024) s_wh[i] = 0;
     __syncthreads();
     const long long per = ((g.pix_stride + 31) / 32 + 31) / 32 * 32;          // pixels per warp, multiple of 32
     const long long b = wid * per, e = min(g.pix_stride, b + per);
-    for (long long i = b + lane; i < e; i += 32)
-        if (ang[i] != NOTDEF_F) atomicAdd(&wh[NBINS - 1 - lsd_bin(mod[i], mg)], 1);
+    constexpr int U = 8;                                                       // groups of 32 pixels in flight per warp
+    for (long long i0 = b; i0 < e; i0 += 32 * U) {
+        double m[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const long long i = i0 + u * 32 + lane; m[u] = i < e ? __ldg(mod + i) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < U; u++) if (m[u] > rho) atomicAdd(&wh[NBINS - 1 - (int)(m[u] * bin_coef)], 1);
+    }
     __syncthreads();
     {   // thread = bin: exclusive prefix over the warps, then over the bins
         int run = 0;
@@ -191,18 +219,23 @@ __global__ void __launch_bounds__(1024) k_lsd_seeds(const __grid_constant__ Line
     }
     __syncthreads();
     unsigned* seeds = ws.seeds + f * g.pix_stride;
-    for (long long i0 = b; i0 < b + per; i0 += 32) {
-        const long long i = i0 + lane;
-        const bool def = i < e && ang[i] != NOTDEF_F;
-        if (!__any_sync(0xffffffffu, def)) continue;
-        const int key = def ? (NBINS - 1 - lsd_bin(mod[i], mg)) : (2048 + lane);
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        const int leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1));
-        int off = 0;
-        if (def && lane == leader) { off = wh[key]; wh[key] = off + __popc(peers); }
-        off = __shfl_sync(0xffffffffu, off, leader);
-        if (def) seeds[off + rank] = (unsigned)i;
-        __syncwarp();
+    for (long long i0 = b; i0 < e; i0 += 32 * U) {
+        double m[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const long long i = i0 + u * 32 + lane; m[u] = i < e ? __ldg(mod + i) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < U; u++) {                                          // groups in raster order: a stable sort
+            const bool def = m[u] > rho;
+            if (!__any_sync(0xffffffffu, def)) continue;
+            const int key = def ? (NBINS - 1 - (int)(m[u] * bin_coef)) : (2048 + lane);
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const int leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1));
+            int off = 0;
+            if (def && lane == leader) { off = wh[key]; wh[key] = off + __popc(peers); }
+            off = __shfl_sync(0xffffffffu, off, leader);
+            if (def) seeds[off + rank] = (unsigned)(i0 + u * 32 + lane);
+            __syncwarp();
+        }
     }
 }
 
@@ -287,22 +320,65 @@ __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* r
             a = __uint_as_float(v.x); cx = __uint_as_float(v.y); cy = __uint_as_float(v.z); u = v.w;
         }
         const double ad = (double)a * L_DEG;
+        const unsigned lt = (1u << lane) - 1u;
         unsigned pending = __ballot_sync(0xffffffffu, u == 0u && a != NOTDEF_F);
         while (pending) {
-            const unsigned okm = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && l_aligned_rad(ad, reg_angle, prec));
-            if (!okm) break;
-            const int k0 = __ffs(okm) - 1;
-            const float kx = __shfl_sync(0xffffffffu, cx, k0), ky = __shfl_sync(0xffffffffu, cy, k0);
-            const int q0 = __shfl_sync(0xffffffffu, q, k0);
-            if (lane == k0) {                                     // the accepted lane records its own pixel
-                reg[n] = (unsigned)xx | ((unsigned)yy << 16);
-                pix[q].used = 1u;
+            const bool mep = (pending >> lane) & 1u;
+            const unsigned S0 = __ballot_sync(0xffffffffu, mep && l_aligned_rad(ad, reg_angle, prec));
+            if (!S0) break;                                       // nobody passes at the current angle: all rejected
+            if ((S0 & (S0 - 1u)) == 0u) {
+                // exactly one candidate: the plain sequential step
+                const int k0 = __ffs(S0) - 1;
+                const float kx = __shfl_sync(0xffffffffu, cx, k0), ky = __shfl_sync(0xffffffffu, cy, k0);
+                const int q0 = __shfl_sync(0xffffffffu, q, k0);
+                if (lane == k0) { reg[n] = (unsigned)xx | ((unsigned)yy << 16); pix[q].used = 1u; }
+                n++;
+                sumdx += kx; sumdy += ky;
+                reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * L_DEG;
+                pending &= ~((2u << k0) - 1u);
+                pending &= ~__ballot_sync(0xffffffffu, q == q0);  // the same pixel seen from another queue entry
+                continue;
             }
-            n++;
-            sumdx += kx; sumdy += ky;
-            reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * L_DEG;
-            pending &= ~((2u << k0) - 1u);
-            pending &= ~__ballot_sync(0xffffffffu, q == q0);      // the same pixel seen from another queue entry
+            // Several candidates: SPECULATE that exactly the lanes passing at the current angle (first holder of each
+            // pixel only) will be accepted.  Every lane then forms the running sums the sequential scan would hold when
+            // it reaches that lane (ordered float adds over the earlier members), ONE SIMT atan2 gives every member's
+            // "angle after me", each pending lane re-tests itself against the angle of the member just before it, and
+            // the speculation is accepted up to the first lane whose verified outcome differs from the guess (that
+            // lane's verified outcome is the true one, because everything before it was right).
+            const unsigned peers = __match_any_sync(0xffffffffu, mep ? q : ~lane);
+            const bool inS0 = (S0 >> lane) & 1u;
+            const unsigned S = S0 & ~__ballot_sync(0xffffffffu, inS0 && (peers & S0 & lt) != 0u);
+            const bool inS = (S >> lane) & 1u;
+            float bx = sumdx, by = sumdy;
+            for (unsigned T = S; T; T &= T - 1u) {
+                const int m = __ffs(T) - 1;
+                const float mx = __shfl_sync(0xffffffffu, cx, m), my = __shfl_sync(0xffffffffu, cy, m);
+                if (lane > m) { bx += mx; by += my; }
+            }
+            const float ax = bx + cx, ay = by + cy;
+            const double aft = (double)fast_atan2_deg(ay, ax) * L_DEG;
+            const unsigned prevm = S & lt;
+            double bef = __shfl_sync(0xffffffffu, aft, (31 - __clz(prevm)) & 31);
+            if (!prevm) bef = reg_angle;
+            const bool dup_e = (peers & S & lt) != 0u;            // an earlier member holds my pixel: the scan finds it used
+            const bool actual = mep && !dup_e && l_aligned_rad(ad, bef, prec);
+            const unsigned mism = __ballot_sync(0xffffffffu, mep && (actual != inS));
+            int src; unsigned A;
+            if (!mism) { A = S; src = 31 - __clz(S); }
+            else {
+                src = __ffs(mism) - 1;
+                const unsigned acc = __ballot_sync(0xffffffffu, actual);
+                A = (S & ((1u << src) - 1u)) | (acc & (1u << src));
+            }
+            if ((A >> lane) & 1u) { reg[n + __popc(A & lt)] = (unsigned)xx | ((unsigned)yy << 16); pix[q].used = 1u; }
+            n += __popc(A);
+            const float selx = actual ? ax : bx, sely = actual ? ay : by;
+            const double sela = actual ? aft : bef;
+            sumdx = __shfl_sync(0xffffffffu, selx, src); sumdy = __shfl_sync(0xffffffffu, sely, src);
+            reg_angle = __shfl_sync(0xffffffffu, sela, src);
+            if (!mism) break;                                     // every pending lane is resolved
+            pending &= ~((2u << src) - 1u);
+            pending &= ~__ballot_sync(0xffffffffu, mep && (peers & A) != 0u);   // later holders of accepted pixels
         }
         __syncwarp();
         i += cnt;
@@ -531,13 +607,18 @@ __device__ double l_log_gamma(double x) {
     return a + log(b);
 }
 
-__device__ double l_nfa(int n, int k, double p, double LOG_NT, const double* lgam) {
+__device__ __noinline__ double l_log(double x) { return log(x); }          // one copy of each libm routine per kernel
+__device__ __noinline__ double l_log10(double x) { return log10(x); }
+__device__ __noinline__ double l_exp(double x) { return exp(x); }
+// (a real call everywhere: log / exp / pow / log10 inline to ~10 KB of SASS, and the NFA kernels keep thousands of
+// warps at different program counters — code size is what their instruction cache sees)
+__device__ __noinline__ double l_nfa(int n, int k, double p, double LOG_NT, const double* lgam) {
     if (n == 0 || k == 0) return -LOG_NT;
-    if (n == k) return -LOG_NT - (double)n * log10(p);
+    if (n == k) return -LOG_NT - (double)n * l_log10(p);
     const double p_term = p / (1 - p);
     const double log1term = lgam[n] - lgam[k] - lgam[n - k] +
-                            (double)k * log(p) + (double)(n - k) * log(1.0 - p);
-    double term = exp(log1term);
+                            (double)k * l_log(p) + (double)(n - k) * l_log(1.0 - p);
+    double term = l_exp(log1term);
     {   // double_equal(term, 0)
         bool eq = term == 0.0;
         if (!eq) { double abs_max = fabs(term); if (abs_max < 2.2250738585072014e-308) abs_max = 2.2250738585072014e-308; eq = (fabs(term) / abs_max) <= (100.0 * 2.220446049250313e-16); }
@@ -558,7 +639,7 @@ __device__ double l_nfa(int n, int k, double p, double LOG_NT, const double* lga
             const int m = n - i + 1;
             const double pw = (m >= 28 && mult_term < 0.25) ? 0.0 : pow(mult_term, (double)m);
             const double err = term * ((1 - pw) / (1 - mult_term) - 1);
-            // threshold 0.1 * |-log10(bin_tail) - LOG_NT| * bin_tail: bracket log10 by the binary exponent first and
+            // threshold 0.1 * |-l_log10(bin_tail) - LOG_NT| * bin_tail: bracket log10 by the binary exponent first and
             // evaluate the logarithm only when the bracket cannot decide (same decision as the plain test, always)
             bool stop;
             const int e2 = ilogb(bin_tail);
@@ -567,12 +648,12 @@ __device__ double l_nfa(int n, int k, double p, double LOG_NT, const double* lga
                 const double a_lo = (l_lo > 0) ? l_lo : ((l_hi < 0) ? -l_hi : 0.0), a_hi = fmax(fabs(l_lo), fabs(l_hi));
                 if (err < 0.1 * a_lo * bin_tail * (1 - 1e-9)) stop = true;
                 else if (err >= 0.1 * a_hi * bin_tail * (1 + 1e-9)) stop = false;
-                else stop = err < 0.1 * fabs(-log10(bin_tail) - LOG_NT) * bin_tail;
-            } else stop = err < 0.1 * fabs(-log10(bin_tail) - LOG_NT) * bin_tail;
+                else stop = err < 0.1 * fabs(-l_log10(bin_tail) - LOG_NT) * bin_tail;
+            } else stop = err < 0.1 * fabs(-l_log10(bin_tail) - LOG_NT) * bin_tail;
             if (stop) break;
         }
     }
-    return -log10(bin_tail) - LOG_NT;
+    return -l_log10(bin_tail) - LOG_NT;
 }
 
 __device__ __forceinline__ int l_x86_d2i(double v) {                 // cvttsd2si semantics
@@ -629,7 +710,7 @@ __device__ double l_rect_nfa(const Walk& W, const LRect& rec) {
 // Five candidate rectangles of one rect_improve phase at once: lane group g = lane / 6 (6 lanes each, lanes 30-31 idle)
 // scans candidate g's rows, the counts are combined through shared-memory atomics (exact integers), and the five
 // scalar NFA evaluations run side by side in lanes 0, 6, 12, 18, 24.  s_cnt: 10 ints of this warp.
-__device__ void l_rect_nfa5(const Walk& W, const LRect& mine, bool valid, int* s_cnt, double* out5) {
+__device__ __noinline__ void l_rect_nfa5(const Walk& W, const LRect& mine, bool valid, int* s_cnt, double* out5) {
     const int lane = W.lane, grp = lane / 6, sub = lane - grp * 6;
     if (lane < 10) s_cnt[lane] = 0;
     __syncwarp();
@@ -680,6 +761,7 @@ __device__ double l_rect_improve(const Walk& W, LRect& rec, int* s_cnt, double l
     const int lane = W.lane, grp = lane / 6, k = min(grp, 4) + 1;     // this lane's candidate = k-th step of the phase
     if (log_nfa > 0.0) return log_nfa;           // log_nfa = NFA of the unmodified rectangle (k_lsd_nfa_first)
     double v[5];
+#pragma unroll 1
     for (int phase = 0; phase < 5; phase++) {
         // candidate k of the phase, built exactly as the sequential loop would have built it
         LRect r = rec;
