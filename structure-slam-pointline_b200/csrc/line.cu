@@ -142,37 +142,64 @@ __device__ __forceinline__ void l_sincos_2pi(double x, double* s_out, double* c_
 }
 
 // ll_angle (lsd.cpp): 2x2 gradient, level-line angle, gradient norm, max over defined pixels
+// Four horizontally adjacent pixels per thread: 4 loads and 9 vector stores per 4 pixels instead of 16 + 16 (the
+// scalar version was limited by the memory-instruction queue, not by HBM or by the trigonometry).
 __global__ void __launch_bounds__(256) k_ll_angle(const __grid_constant__ LineGeom g, LineWs ws) {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
-    double norm = 0;
-    bool defined = false;
-    if (x < g.sw && y < g.sh) {
-        const long long pi = f * g.pix_stride + (long long)y * g.sw + x;
-        float ang = NOTDEF_F; float2 cs = make_float2(0.f, 0.f), cs0 = make_float2(0.f, 0.f);
-        if (x < g.sw - 1 && y < g.sh - 1) {
-            const uint8_t* p = ws.scaled + f * g.scaled_stride + (long long)y * g.spitch + x;
-            const int DA = (int)p[g.spitch + 1] - (int)p[0], BC = (int)p[1] - (int)p[g.spitch];
-            const int gx = DA + BC, gy = DA - BC;
-            norm = sqrt((double)(gx * gx + gy * gy) / 4.0);
-            if (norm > g.rho) {
-                defined = true;
-                ang = fast_atan2_deg((float)gx, (float)-gy);
-                const double ad = (double)ang * L_DEG;
-                const float a = (float)ad;
-                double sn, cn;
-                l_sincos_2pi((double)a, &sn, &cn);
-                cs.x = (float)cn; cs.y = (float)sn;
-                // region_grow's seed values float(cos(ad)), float(sin(ad)): ad = a + d with |d| < 2e-7, so a second-order
-                // Taylor step from (cn, sn) is accurate to a few double ulps (the d^3 term is < 1e-20) — one sincos, not four calls
-                const double d = ad - (double)a, hd2 = 0.5 * d * d;
-                cs0.x = (float)(cn - sn * d - cn * hd2); cs0.y = (float)(sn + cn * d - sn * hd2);
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    unsigned long long bits = 0ull;                    // max gradient norm of the defined pixels (positive doubles order like integers)
+    if (x0 < g.sw && y < g.sh) {
+        float ang[4]; float2 cs[4], cs0[4]; double norm[4];
+        const uint8_t* p = ws.scaled + f * g.scaled_stride + (long long)y * g.spitch + x0;
+        unsigned r0 = 0, r1 = 0; int e0 = 0, e1 = 0;    // rows y, y+1: bytes x0..x0+3 and x0+4
+        const bool row_ok = y < g.sh - 1;
+        if (row_ok) {
+            r0 = *reinterpret_cast<const unsigned*>(p); r1 = *reinterpret_cast<const unsigned*>(p + g.spitch);   // spitch % 64 == 0, x0 % 4 == 0
+            if (x0 + 4 < g.sw) { e0 = p[4]; e1 = p[g.spitch + 4]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            ang[k] = NOTDEF_F; cs[k] = make_float2(0.f, 0.f); cs0[k] = make_float2(0.f, 0.f); norm[k] = 0;
+            if (row_ok && x0 + k < g.sw - 1) {
+                const int A = (r0 >> (8 * k)) & 0xff, C = (r1 >> (8 * k)) & 0xff;
+                const int Bv = (k < 3) ? (int)((r0 >> (8 * k + 8)) & 0xff) : e0, D = (k < 3) ? (int)((r1 >> (8 * k + 8)) & 0xff) : e1;
+                const int DA = D - A, BC = Bv - C;
+                const int gx = DA + BC, gy = DA - BC;
+                norm[k] = sqrt((double)(gx * gx + gy * gy) / 4.0);
+                if (norm[k] > g.rho) {
+                    const unsigned long long nb = (unsigned long long)__double_as_longlong(norm[k]);
+                    bits = nb > bits ? nb : bits;
+                    ang[k] = fast_atan2_deg((float)gx, (float)-gy);
+                    const double ad = (double)ang[k] * L_DEG;
+                    const float a = (float)ad;
+                    double sn, cn;
+                    l_sincos_2pi((double)a, &sn, &cn);
+                    cs[k].x = (float)cn; cs[k].y = (float)sn;
+                    // region_grow's seed values float(cos(ad)), float(sin(ad)): ad = a + d with |d| < 2e-7, so a second-order
+                    // Taylor step from (cn, sn) is accurate to a few double ulps (the d^3 term is < 1e-20) — one sincos, not four calls
+                    const double d = ad - (double)a, hd2 = 0.5 * d * d;
+                    cs0[k].x = (float)(cn - sn * d - cn * hd2); cs0[k].y = (float)(sn + cn * d - sn * hd2);
+                }
             }
         }
-        ws.angdeg[pi] = ang; ws.cs0[pi] = cs0; ws.modgrad[pi] = norm;
-        LPix px; px.ang = ang; px.cx = cs.x; px.cy = cs.y; px.used = 0u;
-        ws.pix[pi] = px;
+        const long long pi = f * g.pix_stride + (long long)y * g.sw + x0;
+        if ((g.sw & 3) == 0 && (g.pix_stride & 3) == 0) {                  // rows start 16-byte aligned in every per-pixel array
+            *reinterpret_cast<float4*>(ws.angdeg + pi) = make_float4(ang[0], ang[1], ang[2], ang[3]);
+            float4* c4 = reinterpret_cast<float4*>(ws.cs0 + pi);
+            c4[0] = make_float4(cs0[0].x, cs0[0].y, cs0[1].x, cs0[1].y); c4[1] = make_float4(cs0[2].x, cs0[2].y, cs0[3].x, cs0[3].y);
+            double2* m2 = reinterpret_cast<double2*>(ws.modgrad + pi);
+            m2[0] = make_double2(norm[0], norm[1]); m2[1] = make_double2(norm[2], norm[3]);
+            uint4* px = reinterpret_cast<uint4*>(ws.pix + pi);
+#pragma unroll
+            for (int k = 0; k < 4; k++) px[k] = make_uint4(__float_as_uint(ang[k]), __float_as_uint(cs[k].x), __float_as_uint(cs[k].y), 0u);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (x0 + k < g.sw) {
+                ws.angdeg[pi + k] = ang[k]; ws.cs0[pi + k] = cs0[k]; ws.modgrad[pi + k] = norm[k];
+                LPix px; px.ang = ang[k]; px.cx = cs[k].x; px.cy = cs[k].y; px.used = 0u;
+                ws.pix[pi + k] = px;
+            }
+        }
     }
-    unsigned long long bits = defined ? (unsigned long long)__double_as_longlong(norm) : 0ull;   // positive doubles order like integers
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, bits, o); bits = t > bits ? t : bits; }
     if ((threadIdx.x & 31) == 0 && bits) atomicMax(ws.maxgrad + f, bits);
@@ -1002,18 +1029,40 @@ __global__ void __launch_bounds__(256) k_keylines(const __grid_constant__ LineGe
     if (tid == 0) ws.nl[f] = keep;
 }
 
-// Sobel 3x3 -> s16 (dx, dy) with BORDER_REFLECT_101 on the 5-tap blurred image
+// Sobel 3x3 -> s16 (dx, dy) with BORDER_REFLECT_101 on the 5-tap blurred image.  Four pixels per thread: three
+// aligned 32-bit row loads (+ the two edge bytes) and two 8-byte stores instead of 8 byte loads and 2 short stores per pixel.
 __global__ void __launch_bounds__(256) k_sobel(const __grid_constant__ LineGeom g, LineWs ws) {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
-    if (x >= g.w || y >= g.h) return;
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    if (x0 >= g.w || y >= g.h) return;
     const uint8_t* img = ws.blur5 + f * g.blur_stride;
-    const uint8_t* r0 = img + (long long)reflect101(y - 1, g.h) * g.bpitch;
-    const uint8_t* r1 = img + (long long)y * g.bpitch;
-    const uint8_t* r2 = img + (long long)reflect101(y + 1, g.h) * g.bpitch;
-    const int xm = reflect101(x - 1, g.w), xp = reflect101(x + 1, g.w);
-    const long long o = f * g.full_stride + (long long)y * g.w + x;
-    ws.dx[o] = (int16_t)(((int)r0[xp] - (int)r0[xm]) + 2 * ((int)r1[xp] - (int)r1[xm]) + ((int)r2[xp] - (int)r2[xm]));
-    ws.dy[o] = (int16_t)(((int)r2[xm] - (int)r0[xm]) + 2 * ((int)r2[x] - (int)r0[x]) + ((int)r2[xp] - (int)r0[xp]));
+    const uint8_t* rows[3] = {img + (long long)reflect101(y - 1, g.h) * g.bpitch, img + (long long)y * g.bpitch, img + (long long)reflect101(y + 1, g.h) * g.bpitch};
+    const int xl = reflect101(x0 - 1, g.w);
+    int v[3][6];                                             // columns x0-1 .. x0+4 of the three rows
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const unsigned wv = *reinterpret_cast<const unsigned*>(rows[r] + x0);     // bpitch % 64 == 0, x0 % 4 == 0; x0+3 < bpitch
+        v[r][0] = rows[r][xl];
+        v[r][1] = wv & 0xff; v[r][2] = (wv >> 8) & 0xff; v[r][3] = (wv >> 16) & 0xff; v[r][4] = wv >> 24;
+        v[r][5] = rows[r][reflect101(min(x0 + 4, g.w), g.w)];
+    }
+    // pixels beyond the last column (only when w % 4 != 0) take the reflected neighbours the scalar definition uses
+    short dxs[4], dys[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x = x0 + k;
+        int m0 = v[0][k], m1 = v[1][k], m2 = v[2][k], c0 = v[0][k + 1], c2 = v[2][k + 1], p0 = v[0][k + 2], p1 = v[1][k + 2], p2 = v[2][k + 2];
+        if (x == g.w - 1) { p0 = m0; p1 = m1; p2 = m2; }    // reflect101(w) = w - 2 = x - 1
+        dxs[k] = (short)((p0 - m0) + 2 * (p1 - m1) + (p2 - m2));
+        dys[k] = (short)((m2 - m0) + 2 * (c2 - c0) + (p2 - p0));
+    }
+    const long long o = f * g.full_stride + (long long)y * g.w + x0;
+    if ((g.w & 3) == 0 && (g.full_stride & 3) == 0) {
+        *reinterpret_cast<short4*>(ws.dx + o) = make_short4(dxs[0], dxs[1], dxs[2], dxs[3]);
+        *reinterpret_cast<short4*>(ws.dy + o) = make_short4(dys[0], dys[1], dys[2], dys[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (x0 + k < g.w) { ws.dx[o + k] = dxs[k]; ws.dy[o + k] = dys[k]; }
+    }
 }
 
 // LBD (BinaryDescriptor::computeLBD, binary_descriptor.cpp) — one CTA (64 threads) per line: thread h walks row h
@@ -1255,7 +1304,7 @@ int run_pipeline(sslpl_line* h, int B) {
     k_resize_exact<<<dim3((g.sw + 31) / 32, (g.sh + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
     lmark(h, "lsd_prep");
     SSLPL_CUDA(cudaMemsetAsync(h->ws.maxgrad, 0, sizeof(unsigned long long) * B, st));
-    k_ll_angle<<<dim3((g.sw + 31) / 32, (g.sh + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
+    k_ll_angle<<<dim3((g.sw + 127) / 128, (g.sh + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
     lmark(h, "lsd_ll_angle");
     k_lsd_seeds<<<B, 1024, 32 * NBINS * sizeof(int), st>>>(g, h->ws);
     lmark(h, "lsd_seeds");
@@ -1267,7 +1316,7 @@ int run_pipeline(sslpl_line* h, int B) {
     k_lsd_nfa_improve<<<std::min(h->sm_count * 8, (B * 64 + 3) / 4), 128, 0, st>>>(g, h->ws);
     lmark(h, "lsd_nfa");
     k_keylines<<<B, 256, 0, st>>>(g, h->ws);
-    k_sobel<<<dim3((g.w + 31) / 32, (g.h + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
+    k_sobel<<<dim3((g.w + 127) / 128, (g.h + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
     k_lbd<<<dim3(g.kl_cap, B), 64, 0, st>>>(g, h->ws, h->coef);
     lmark(h, "keylines_lbd");
     h->launches += 12;     // kernels only (the two small memsets are not counted)
