@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lines", action="store_true", help="ORB + point matching only")
     ap.add_argument("--line-ring", type=int, default=6, help="line handles (streams + workspaces) kept in flight")
+    ap.add_argument("--walkers-per-sm", type=float, default=0.0, help="per line handle: resident LSD region walkers per SM (0 = one per frame)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = WORKLOADS[args.workload]
@@ -198,7 +199,13 @@ def main():
     R = max(1, args.line_ring) if LINES else 0
     lsr = [pkg.LineSegment(NL, max_width=W, max_height=H, max_batch=B, device=local) for _ in range(R)]
     lmr = [pkg.Matcher(max_features=64, max_lines=NL, max_nodes=2, max_batch=B, device=local) for _ in range(R)]
-    s_pts = torch.cuda.Stream(device=dev)               # points: ORB + BoW matching + NCCL + timing events
+    if args.walkers_per_sm > 0:
+        nsm = torch.cuda.get_device_properties(local).multi_processor_count
+        for l in lsr:
+            l.set_max_walkers(max(1, int(round(args.walkers_per_sm * nsm))))
+    PRIO = -1 if os.environ.get('SSLPL_BENCH_PRIO', '1') == '1' else 0
+    s_pts = torch.cuda.Stream(device=dev, priority=PRIO)   # points: ORB + BoW matching + NCCL + timing events; high priority so that
+                                                          # its wide kernels are dispatched ahead of queued region-walker CTAs
     s_lin = [torch.cuda.Stream(device=dev) for _ in range(R)]
     torch.cuda.set_stream(s_pts)
     assert s_pts.cuda_stream != 0
@@ -292,28 +299,51 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: pinned host frames -> H2D -> kernels -> D2H of keypoints, descriptors, lines, counts, match tables ----
+    # Both paths are software-pipelined through their public asynchronous entry points (extract_batch_begin): a ring of
+    # R line handles and a ring of 2 point handles, so that the upload of step i+1 overlaps the kernels of step i.  Every
+    # step's results are read back into pinned host memory and consumed (counted) on the host inside the timed region.
     h_sets = []
     for s in sets:
         hp = pkg.host_alloc(s.shape, np.uint8); hp[...] = s; h_sets.append(hp)
-    h_out = (pkg.host_alloc((B, cap), pkg.KEYPOINT_DTYPE), pkg.host_alloc((B, cap, 32), np.uint8), pkg.host_alloc((B,), np.int32))
+    PR = int(os.environ.get('SSLPL_BENCH_PR', '2'))
+    VARIANT = os.environ.get('SSLPL_E2E_VARIANT', '')       # diagnostics; the reported e2e always uses the default (host buffers)
+    exts, mts, s_p, d_match_e, d_nmatch_e = [ext], [mt], [s_pts], [d_match], [d_nmatch]
+    for _ in range(PR - 1):
+        e_ = pkg.ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B, device=local)
+        m_ = pkg.Matcher(max_features=ext.cap, max_lines=NL, max_nodes=NWORDS, max_batch=B, device=local)
+        st_ = torch.cuda.Stream(device=dev, priority=PRIO)
+        e_.set_stream(st_.cuda_stream); m_.set_stream(st_.cuda_stream)
+        exts.append(e_); mts.append(m_); s_p.append(st_)
+        d_match_e.append(torch.empty_like(d_match)); d_nmatch_e.append(torch.empty_like(d_nmatch))
+    h_out = [(pkg.host_alloc((B, cap), pkg.KEYPOINT_DTYPE), pkg.host_alloc((B, cap, 32), np.uint8), pkg.host_alloc((B,), np.int32)) for _ in range(PR)]
     h_lout = [(pkg.host_alloc((B, NL), pkg.KEYLINE_DTYPE), pkg.host_alloc((B, NL, 32), np.uint8),
                pkg.host_alloc((B, NL, 3), np.float64), pkg.host_alloc((B,), np.int32)) for _ in range(R)]
-    h_match = torch.empty((Bf, cap), dtype=torch.int32).pin_memory(); h_nmatch = torch.empty((Bf,), dtype=torch.int32).pin_memory()
+    h_match = [torch.empty((Bf, cap), dtype=torch.int32).pin_memory() for _ in range(PR)]
+    h_nmatch = [torch.empty((Bf,), dtype=torch.int32).pin_memory() for _ in range(PR)]
     h_lmatch = [torch.empty((Bf, NL), dtype=torch.int32).pin_memory() for _ in range(R)]
     h_nlmatch = [torch.zeros((Bf,), dtype=torch.int32).pin_memory() for _ in range(R)]
     e2e_pending = [False] * R
+    pts_pending = [False] * PR
 
     def e2e_finalize(r):
-        """Host-side completion of slot r: wait for its stream, then the results are in the pinned host buffers."""
+        """Host-side completion of line slot r: wait for its stream, then the results are in the pinned host buffers."""
         if not e2e_pending[r]:
             return 0
         if world > 1:
             s_pts.wait_stream(s_lin[r])
-            dist.all_gather_into_tensor(d_lgather, d_lmatch[r])
+            with torch.cuda.stream(s_pts):
+                dist.all_gather_into_tensor(d_lgather, d_lmatch[r])
             ev_free[r].record(s_pts)
         lsr[r].sync()                                                          # stream sync + deferred device error check
         e2e_pending[r] = False
         return int(h_lout[r][3][:Bf].sum()) + int(h_nlmatch[r].sum())
+
+    def pts_finalize(p):
+        if not pts_pending[p]:
+            return 0
+        exts[p].sync()
+        pts_pending[p] = False
+        return int(h_out[p][2][:Bf].sum()) + int(h_nmatch[p].sum())
 
     def step_e2e(i):
         fr = h_sets[i % nsets]
@@ -323,27 +353,39 @@ def main():
             u += e2e_finalize(r)
             if world > 1:
                 s_lin[r].wait_event(ev_free[r])
-            lsr[r].extract_batch_begin(fr, h_lout[r])                          # H2D + kernels + D2H enqueued on slot r's stream
+            if VARIANT == "noh2d":
+                lsr[r].extract_batch_device(d_sets[i % nsets].data_ptr(), B, W, H, W, W * H)   # diagnostic only (SSLPL_E2E_VARIANT)
+            else:
+                lsr[r].extract_batch_begin(fr, h_lout[r])                      # H2D + kernels + D2H enqueued on slot r's stream
             _, ldesc, _, nl, capl = lsr[r].device_results()
             lmr[r].match_lines_batch_device(ldesc, nl, B, capl, d_lmatch[r].data_ptr(), d_nlmatch[r].data_ptr())
             with torch.cuda.stream(s_lin[r]):
                 h_lmatch[r].copy_(d_lmatch[r], non_blocking=True); h_nlmatch[r].copy_(d_nlmatch[r], non_blocking=True)
             e2e_pending[r] = True
-        ext.extract_batch_begin(fr, h_out)                                     # H2D + kernels + D2H on the points stream
-        enqueue_points()
-        h_match.copy_(d_match, non_blocking=True); h_nmatch.copy_(d_nmatch, non_blocking=True)
-        ext.sync()
-        return u + int(h_out[2][:Bf].sum()) + int(h_nmatch.sum())
+        p = i % PR
+        u += pts_finalize(p)
+        if VARIANT == "noh2d":
+            exts[p].extract_batch_device(d_sets[i % nsets].data_ptr(), B, W, H, W, W * H)
+        else:
+            exts[p].extract_batch_begin(fr, h_out[p])                          # H2D + kernels + D2H on point slot p's stream
+        kps, desc, n, c = exts[p].device_results()
+        mts[p].match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match_e[p].data_ptr(), d_nmatch_e[p].data_ptr())
+        with torch.cuda.stream(s_p[p]):
+            if gather[0]:
+                dist.all_gather_into_tensor(d_gather, d_match_e[p])
+            h_match[p].copy_(d_match_e[p], non_blocking=True); h_nmatch[p].copy_(d_nmatch_e[p], non_blocking=True)
+        pts_pending[p] = True
+        return u
 
     def e2e_drain():
-        return sum(e2e_finalize(r) for r in range(R))
+        return sum(e2e_finalize(r) for r in range(R)) + sum(pts_finalize(p) for p in range(PR))
 
     # units of every distinct input set (untimed): one synchronous pass per set
     per_set = []
     for sidx in range(nsets):
         u = step_e2e(sidx) + e2e_drain()
         per_set.append(u)
-    nkp_avg = float(np.mean(h_out[2][:Bf]))
+    nkp_avg = float(np.mean(h_out[(nsets - 1) % PR][2][:Bf]))
     units = sum(per_set[(args.warmup + i) % nsets] for i in range(args.steps))
     t = torch.tensor([ms_total, float(units)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -366,6 +408,32 @@ def main():
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    if os.environ.get("SSLPL_BENCH_TRACE") and rank == 0:      # diagnostics: GPU busy time / gaps of both loops (torch profiler)
+        from torch.profiler import profile, ProfilerActivity
+        for name, body in (("device", lambda: ([step_device(args.warmup + i) for i in range(8)], drain())),
+                           ("e2e", lambda: ([step_e2e(args.warmup + i) for i in range(8)], e2e_drain()))):
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+                body(); torch.cuda.synchronize()
+            evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+            iv = sorted((e.time_range.start, e.time_range.end, e.name) for e in evs)
+            if not iv:
+                continue
+            t0, t1 = iv[0][0], max(b for _, b, _ in iv)
+            busy = 0.0; cur_a, cur_b = iv[0][0], iv[0][1]; gaps = []
+            for a, b, _ in iv[1:]:
+                if a > cur_b:
+                    busy += cur_b - cur_a; gaps.append((a - cur_b, cur_b - t0)); cur_a, cur_b = a, b
+                else:
+                    cur_b = max(cur_b, b)
+            busy += cur_b - cur_a
+            per = {}
+            for a, b, n in iv:
+                k = n.split("(")[0][-28:]; per[k] = per.get(k, 0.0) + (b - a)
+            top = sorted(per.items(), key=lambda kv: -kv[1])[:14]
+            print(f"[trace {name}] wall {(t1 - t0) / 1e3:.1f} ms, union busy {busy / 1e3:.1f} ms, largest gaps (us @ offset ms): "
+                  f"{[(round(g), round(o / 1e3, 1)) for g, o in sorted(gaps, reverse=True)[:6]]}", file=sys.stderr)
+            print(f"[trace {name}] kernel/copy time sums (ms): {[(k, round(v / 1e3, 1)) for k, v in top]}", file=sys.stderr)
     t = torch.tensor([e2e_ms, float(eu)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -416,8 +484,8 @@ def main():
             "octree": 8 * ncand,
             # line path, S = scaled pixels (0.64 W H): SURVEY.md 8(d)
             "lsd_prep": W * H + 2 * int(0.64 * W * H) + 2 * W * H,
-            "lsd_ll_angle": int(0.64 * W * H) * (1 + 4 + 8 + 8 + 8),
-            "lsd_seeds": int(0.64 * W * H) * (4 + 8) + 8 * int(0.15 * 0.64 * W * H),
+            "lsd_ll_angle": int(0.64 * W * H) * (1 + 4 + 16 + 8 + 8),   # read u8, write angle, packed record, seed cos/sin, norm
+            "lsd_seeds": int(0.64 * W * H) * (8 + 8) + 4 * int(0.3 * 0.64 * W * H),   # norm read twice, seed list written
             "lsd_regions": 17 * int(0.64 * W * H),          # upper bound of the visited-pixel traffic; latency-bound by definition
             "lsd_nfa": 4 * int(0.64 * W * H),
             "keylines_lbd": W * H + 8 * W * H + 63 * 4 * 60 * NL,

@@ -481,6 +481,9 @@ class LineSegment:
         _check(lib().sslpl_line_download_segments(self._h, frame, _p(seg), cap, C.byref(n)))
         return seg[:min(n.value, cap)].copy()
 
+    def set_max_walkers(self, n):
+        _check(lib().sslpl_line_set_max_walkers(self._h, int(n)))
+
     def set_profiling(self, on=True):
         _check(lib().sslpl_line_set_profiling(self._h, int(on)))
 

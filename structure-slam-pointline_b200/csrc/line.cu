@@ -56,7 +56,7 @@ struct LineWs {
     int* nseg;
     double* jobs; int* njobs; int* jobflag;   // NFA jobs: 13 doubles per candidate region (LRect + log_nfa), in walker order
     int2* jobnk; double* jobnfa;              // per job: (total, aligned) pixel counts and NFA of the unmodified rectangle
-    int2* rej; int* rejctl;                   // work list of rejected jobs (frame, job); rejctl[0] = count, rejctl[1] = cursor
+    int2* rej; int* rejctl;                   // work list of rejected jobs (frame, job); rejctl[0] = count, rejctl[1] = cursor, rejctl[2] = walker frame cursor
     int16_t* dx; int16_t* dy;
     int2* tab;
     float* resp; float4* ext;   // per raw segment: response and clamped extremes
@@ -214,18 +214,21 @@ __device__ __forceinline__ int lsd_bin(double norm, double max_grad) {
 // a bin — a stable counting sort.  One CTA of 32 warps per frame; warp w owns the w-th contiguous pixel range (raster
 // order), builds its own 1024-bin histogram in shared memory, the histograms are prefix-summed across warps and bins,
 // and every warp then scatters its pixels in order (ranks inside a 32-group by __match_any_sync).
-__global__ void __launch_bounds__(1024) k_lsd_seeds(const __grid_constant__ LineGeom g, LineWs ws) {
-    extern __shared__ int s_wh[];                    // [32 warps][NBINS] running offsets
+constexpr int SEED_WARPS = 8;                       // warps per frame: 32 KB of histograms and ~16k registers per CTA, so that
+                                                    // seed CTAs fit on SMs that are busy with region walkers of other batches
+__global__ void __launch_bounds__(SEED_WARPS * 32) k_lsd_seeds(const __grid_constant__ LineGeom g, LineWs ws) {
+    __shared__ int s_wh[SEED_WARPS * NBINS];         // [warp][bin] running offsets
     __shared__ int s_warp[33];
+    constexpr int NT = SEED_WARPS * 32, BPT = NBINS / NT;   // bins per thread in the prefix step
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // a pixel is defined (angle != NOTDEF) exactly when its gradient norm exceeds rho (k_ll_angle): one array to read
     const double* mod = ws.modgrad + f * g.pix_stride;
     const double mg = __longlong_as_double((long long)ws.maxgrad[f]), rho = g.rho;
     const double bin_coef = (mg > 0) ? double(NBINS - 1) / mg : 0;
     int* wh = s_wh + wid * NBINS;
-    for (int i = tid; i < 32 * NBINS; i += 1024) s_wh[i] = 0;
+    for (int i = tid; i < SEED_WARPS * NBINS; i += NT) s_wh[i] = 0;
     __syncthreads();
-    const long long per = ((g.pix_stride + 31) / 32 + 31) / 32 * 32;          // pixels per warp, multiple of 32
+    const long long per = ((g.pix_stride + SEED_WARPS - 1) / SEED_WARPS + 31) / 32 * 32;   // pixels per warp, multiple of 32
     const long long b = wid * per, e = min(g.pix_stride, b + per);
     constexpr int U = 8;                                                       // groups of 32 pixels in flight per warp
     for (long long i0 = b; i0 < e; i0 += 32 * U) {
@@ -236,12 +239,23 @@ __global__ void __launch_bounds__(1024) k_lsd_seeds(const __grid_constant__ Line
         for (int u = 0; u < U; u++) if (m[u] > rho) atomicAdd(&wh[NBINS - 1 - (int)(m[u] * bin_coef)], 1);
     }
     __syncthreads();
-    {   // thread = bin: exclusive prefix over the warps, then over the bins
-        int run = 0;
-        for (int w = 0; w < 32; w++) { const int c = s_wh[w * NBINS + tid]; s_wh[w * NBINS + tid] = run; run += c; }
+    {   // thread = BPT consecutive bins: exclusive prefix over the warps inside each bin, then over the bins
+        int run[BPT], mine = 0;
+#pragma unroll
+        for (int k = 0; k < BPT; k++) {
+            const int bin = tid * BPT + k;
+            int r = 0;
+            for (int w = 0; w < SEED_WARPS; w++) { const int c = s_wh[w * NBINS + bin]; s_wh[w * NBINS + bin] = r; r += c; }
+            run[k] = r; mine += r;
+        }
         int total;
-        const int base = block_exclusive_scan(run, s_warp, &total);
-        for (int w = 0; w < 32; w++) s_wh[w * NBINS + tid] += base;
+        int base = block_exclusive_scan(mine, s_warp, &total);
+#pragma unroll
+        for (int k = 0; k < BPT; k++) {
+            const int bin = tid * BPT + k;
+            for (int w = 0; w < SEED_WARPS; w++) s_wh[w * NBINS + bin] += base;
+            base += run[k];
+        }
         if (tid == 0) ws.nseeds[f] = total;
     }
     __syncthreads();
@@ -828,8 +842,16 @@ __device__ double l_rect_improve(const Walk& W, LRect& rec, int* s_cnt, double l
 // that read or write the `used` map).  rect_improve / NFA of a region is a pure function of its rectangle and of the
 // immutable angle map, so it is NOT done here: the walker emits one job per candidate region and k_lsd_nfa evaluates
 // all jobs of all frames in parallel (one warp per job).  `used` lives in shared memory as a bitmap.
-__global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ LineGeom g, LineWs ws) {
-    const int f = blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
+    const int lane = threadIdx.x;
+  for (;;) {
+    // frames are pulled from a counter: the grid may be smaller than the batch (sslpl_line_set_max_walkers), which bounds
+    // how many of these long-lived one-warp CTAs (and their registers) sit on every SM next to other kernels
+    int f = 0;
+    if (lane == 0) f = atomicAdd(ws.rejctl + 2, 1);
+    f = __shfl_sync(0xffffffffu, f, 0);
+    if (f >= nframes) break;
+    __syncwarp();
     if (lane == 0) {
         s_W.w = g.sw; s_W.h = g.sh;
         s_W.ang = ws.angdeg + f * g.pix_stride; s_W.mod = ws.modgrad + f * g.pix_stride;
@@ -870,6 +892,8 @@ __global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ Line
         }
     }
     if (lane == 0) { ws.njobs[f] = min(nj, g.seg_cap); if (nj > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
+    __syncwarp();
+  }
 }
 
 // NFA of every candidate region of every frame, in three data-parallel steps (grids are sized by the work, not by the
@@ -1183,6 +1207,7 @@ struct sslpl_line {
     bool trace = false;
     int used_smem = 0;
     int sm_count = 148;
+    int max_walkers = 0;        // 0 = one walker CTA per frame
     int cur_w = 0, cur_h = 0, cur_frames = 0;
     long long launches = 0;
     int* h_err = nullptr;
@@ -1248,7 +1273,7 @@ void carve(sslpl_line* h, Arena& A, const LineGeom& g, int B) {
     ws.seg = A.take<double>((size_t)B * g.seg_cap * 4); ws.nseg = A.take<int>(B);
     ws.jobs = A.take<double>((size_t)B * g.seg_cap * 13); ws.njobs = A.take<int>(B); ws.jobflag = A.take<int>((size_t)B * g.seg_cap);
     ws.jobnk = A.take<int2>((size_t)B * g.seg_cap); ws.jobnfa = A.take<double>((size_t)B * g.seg_cap);
-    ws.rej = A.take<int2>((size_t)B * g.seg_cap); ws.rejctl = A.take<int>(2);
+    ws.rej = A.take<int2>((size_t)B * g.seg_cap); ws.rejctl = A.take<int>(4);
 
     ws.dx = A.take<int16_t>((size_t)B * g.full_stride); ws.dy = A.take<int16_t>((size_t)B * g.full_stride);
     ws.tab = A.take<int2>(g.sw + g.sh);
@@ -1280,7 +1305,6 @@ int configure(sslpl_line* h, int W, int H) {
     SSLPL_REQUIRE(A.used <= h->arena_size, SSLPL_ERR_CAPACITY, "internal: arena too small for this frame size");
     SSLPL_CUDA(cudaStreamSynchronize(h->stream));
     SSLPL_CUDA(cudaMemcpy(h->ws.tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_seeds, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * NBINS * (int)sizeof(int)));
     SSLPL_CUDA(cudaMemset(h->ws.err, 0, sizeof(int)));
     {
         std::vector<double> lg((size_t)h->g.pix_stride + 2);
@@ -1306,11 +1330,11 @@ int run_pipeline(sslpl_line* h, int B) {
     SSLPL_CUDA(cudaMemsetAsync(h->ws.maxgrad, 0, sizeof(unsigned long long) * B, st));
     k_ll_angle<<<dim3((g.sw + 127) / 128, (g.sh + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
     lmark(h, "lsd_ll_angle");
-    k_lsd_seeds<<<B, 1024, 32 * NBINS * sizeof(int), st>>>(g, h->ws);
+    k_lsd_seeds<<<B, SEED_WARPS * 32, 0, st>>>(g, h->ws);
     lmark(h, "lsd_seeds");
-    k_lsd_regions<<<B, 32, 0, st>>>(g, h->ws);
+    SSLPL_CUDA(cudaMemsetAsync(h->ws.rejctl, 0, 4 * sizeof(int), st));
+    k_lsd_regions<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), 32, 0, st>>>(g, h->ws, B);
     lmark(h, "lsd_regions");
-    SSLPL_CUDA(cudaMemsetAsync(h->ws.rejctl, 0, 2 * sizeof(int), st));
     k_lsd_nfa_count<<<dim3(NFA_COUNT_CTAS, B), 128, 0, st>>>(g, h->ws);
     k_lsd_nfa_first<<<dim3(NFA_FIRST_CTAS, B), 128, 0, st>>>(g, h->ws);
     k_lsd_nfa_improve<<<std::min(h->sm_count * 8, (B * 64 + 3) / 4), 128, 0, st>>>(g, h->ws);
@@ -1391,6 +1415,11 @@ int sslpl_line_set_stream(sslpl_line* h, void* s) {
     return SSLPL_OK;
 }
 long long sslpl_line_launch_count(const sslpl_line* h) { return h ? h->launches : 0; }
+int sslpl_line_set_max_walkers(sslpl_line* h, int max_concurrent) {
+    SSLPL_REQUIRE(h && max_concurrent >= 0, SSLPL_ERR_ARG, "bad argument");
+    h->max_walkers = max_concurrent;
+    return SSLPL_OK;
+}
 int sslpl_line_set_profiling(sslpl_line* h, int on) { SSLPL_REQUIRE(h, SSLPL_ERR_ARG, "null handle"); h->profiling = on != 0; return SSLPL_OK; }
 int sslpl_line_stage_ms(sslpl_line* h, float* ms, int cap, const char** names, int* nstages) {
     SSLPL_REQUIRE(h && nstages, SSLPL_ERR_ARG, "null argument");
