@@ -75,34 +75,47 @@ struct LView { const uint8_t* base; int pitch; long long frame_stride; };
 struct Taps7 { int k[7]; };
 
 __global__ void __launch_bounds__(256) k_sep7(const __grid_constant__ LineGeom g, LView v, uint8_t* out, long long out_stride, Taps7 t) {
-    __shared__ uint8_t s_in[(LT_H + 6) * (LT_W + 8)];
-    __shared__ unsigned short s_row[(LT_H + 6) * LT_W];
-    const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    constexpr int IW = LT_W + 6, IP = LT_W + 8, IH = LT_H + 6;           // IP % 4 == 0: rows of s_in are word aligned
+    __shared__ __align__(4) uint8_t s_in[IH * IP];
+    __shared__ __align__(8) unsigned short s_row[IH * LT_W];
+    const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x, x0 = tx * LT_W, y0 = ty * LT_H;
     const uint8_t* img = v.base + f * v.frame_stride;
-    constexpr int IW = LT_W + 6, IP = LT_W + 8, IH = LT_H + 6;
-    for (int i = tid; i < IW * IH; i += 256) {
-        const int yy = i / IW, xx = i - yy * IW;
-        s_in[yy * IP + xx] = __ldg(img + (long long)reflect101(y0 + yy - 3, g.h) * v.pitch + reflect101(x0 + xx - 3, g.w));
+    for (int yy = wid; yy < IH; yy += 8) {                               // a warp per input row: no per-element division
+        const uint8_t* src = img + (long long)reflect101(y0 + yy - 3, g.h) * v.pitch;
+        for (int xx = lane; xx < IW; xx += 32) s_in[yy * IP + xx] = __ldg(src + reflect101(x0 + xx - 3, g.w));
     }
     __syncthreads();
-    for (int i = tid; i < IH * LT_W; i += 256) {
-        const int yy = i / LT_W, xx = i - yy * LT_W;
-        const uint8_t* p = &s_in[yy * IP + xx];
-        s_row[i] = (unsigned short)(t.k[0] * p[0] + t.k[1] * p[1] + t.k[2] * p[2] + t.k[3] * p[3] + t.k[4] * p[4] + t.k[5] * p[5] + t.k[6] * p[6]);
+    // horizontal pass: four outputs per item from ten bytes (three aligned words)
+    for (int i = tid; i < IH * (LT_W / 4); i += 256) {
+        const int yy = i / (LT_W / 4), x4 = (i - yy * (LT_W / 4)) * 4;
+        const unsigned* w = reinterpret_cast<const unsigned*>(&s_in[yy * IP + x4]);
+        const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
+        int b[10];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { b[k] = (w0 >> (8 * k)) & 0xff; b[4 + k] = (w1 >> (8 * k)) & 0xff; }
+        b[8] = w2 & 0xff; b[9] = (w2 >> 8) & 0xff;
+        unsigned r[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            r[k] = (unsigned)(t.k[0] * b[k] + t.k[1] * b[k + 1] + t.k[2] * b[k + 2] + t.k[3] * b[k + 3] + t.k[4] * b[k + 4] + t.k[5] * b[k + 5] + t.k[6] * b[k + 6]) & 0xffffu;
+        *reinterpret_cast<uint2*>(&s_row[yy * LT_W + x4]) = make_uint2(r[0] | (r[1] << 16), r[2] | (r[3] << 16));
     }
     __syncthreads();
     uint8_t* o = out + f * out_stride;
     for (int i = tid; i < LT_H * (LT_W / 4); i += 256) {
         const int yy = i / (LT_W / 4), x4 = (i - yy * (LT_W / 4)) * 4;
         if (y0 + yy >= g.h || x0 + x4 >= g.w) continue;
+        int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const uint2 q = *reinterpret_cast<const uint2*>(&s_row[(yy + j) * LT_W + x4]);
+            acc[0] += t.k[j] * (int)(q.x & 0xffffu); acc[1] += t.k[j] * (int)(q.x >> 16);
+            acc[2] += t.k[j] * (int)(q.y & 0xffffu); acc[3] += t.k[j] * (int)(q.y >> 16);
+        }
         uint32_t o4 = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const unsigned short* p = &s_row[yy * LT_W + x4 + k];
-            const int s = t.k[0] * p[0] + t.k[1] * p[LT_W] + t.k[2] * p[2 * LT_W] + t.k[3] * p[3 * LT_W] + t.k[4] * p[4 * LT_W] + t.k[5] * p[5 * LT_W] + t.k[6] * p[6 * LT_W];
-            o4 |= (uint32_t)((s + 32768) >> 16) << (8 * k);
-        }
+        for (int k = 0; k < 4; k++) o4 |= (uint32_t)((acc[k] + 32768) >> 16) << (8 * k);
         *reinterpret_cast<uint32_t*>(o + (long long)(y0 + yy) * g.bpitch + x0 + x4) = o4;
     }
 }

@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ OrbGeom 
 template <bool TMA>
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g, OrbWs ws, View v, const CUtensorMap* tm) {
     __shared__ __align__(128) uint8_t s_img[TL_IH * TL_P];
-    __shared__ unsigned short s_row[TL_IH * TL_W];
+    __shared__ __align__(8) unsigned short s_row[TL_IH * TL_W];
     __shared__ __align__(8) uint64_t s_bar;
     const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     int l = 0;
@@ -613,21 +613,37 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g,
         }
         __syncthreads();
     }
-    for (int i = tid; i < TL_IH * TL_W; i += 256) {
-        const int r = i >> 6, c = i & 63;
-        const uint8_t* p = &s_img[r * TL_P + c + TL_X - 3];
-        s_row[i] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);   // <= 65280
+    // horizontal pass: four outputs per item from ten bytes, fetched as three aligned words (TL_X - 3 = 13 = 12 + 1)
+    static_assert(TL_X == 16 && TL_P % 4 == 0, "word-aligned row reads assume TL_X == 16");
+    for (int i = tid; i < TL_IH * (TL_W / 4); i += 256) {
+        const int r = i >> 4, x4 = (i & 15) * 4;
+        const unsigned* w = reinterpret_cast<const unsigned*>(&s_img[r * TL_P + x4 + TL_X - 4]);
+        const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
+        int b[10];                                                       // b[k] = pixel x4 - 3 + k
+        b[0] = (w0 >> 8) & 0xff; b[1] = (w0 >> 16) & 0xff; b[2] = w0 >> 24;
+#pragma unroll
+        for (int k = 0; k < 4; k++) b[3 + k] = (w1 >> (8 * k)) & 0xff;
+        b[7] = w2 & 0xff; b[8] = (w2 >> 8) & 0xff; b[9] = (w2 >> 16) & 0xff;
+        unsigned q[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) q[k] = (unsigned)(18 * (b[k] + b[k + 6]) + 34 * (b[k + 1] + b[k + 5]) + 48 * (b[k + 2] + b[k + 4]) + 56 * b[k + 3]);   // <= 65280
+        *reinterpret_cast<uint2*>(&s_row[r * TL_W + x4]) = make_uint2(q[0] | (q[1] << 16), q[2] | (q[3] << 16));
     }
     __syncthreads();
     uint8_t* out = ws.blur + (long long)f * g.blur_stride + L.blur_off;
     for (int i = tid; i < TL_H * (TL_W / 4); i += 256) {
         const int yy = i >> 4, x4 = (i & 15) * 4;
         if (y0 + yy >= L.h || x0 + x4 >= L.w) continue;
+        int e[7][4];
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const uint2 v2 = *reinterpret_cast<const uint2*>(&s_row[(yy + j) * TL_W + x4]);
+            e[j][0] = v2.x & 0xffffu; e[j][1] = v2.x >> 16; e[j][2] = v2.y & 0xffffu; e[j][3] = v2.y >> 16;
+        }
         uint32_t o4 = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const unsigned short* p = &s_row[yy * TL_W + x4 + k];
-            const int sum = 18 * (p[0] + p[6 * TL_W]) + 34 * (p[TL_W] + p[5 * TL_W]) + 48 * (p[2 * TL_W] + p[4 * TL_W]) + 56 * p[3 * TL_W];
+            const int sum = 18 * (e[0][k] + e[6][k]) + 34 * (e[1][k] + e[5][k]) + 48 * (e[2][k] + e[4][k]) + 56 * e[3][k];
             o4 |= (uint32_t)((sum + 32768) >> 16) << (8 * k);
         }
         *reinterpret_cast<uint32_t*>(out + (long long)(y0 + yy) * L.bpitch + x0 + x4) = o4;      // bytes past w are padding
