@@ -81,6 +81,12 @@ def test_line_edge_cases(pkg, oracle, synth):
     _check_frame(pkg, oracle, synth.frame(320, 240, 1), 40, "syn320")
 
 
+def test_line_odd_sizes(pkg, oracle, synth):
+    """Widths that are not multiples of 4 (frame and 0.8x detection scale): the scalar store paths of the vectorised kernels."""
+    for (w, h, seed) in [(333, 251, 2), (322, 243, 3)]:
+        _check_frame(pkg, oracle, synth.frame(w, h, seed), 40, f"syn{w}x{h}")
+
+
 def test_line_batch_equals_single(pkg, oracle, synth):
     frames = synth.batch(640, 480, 5)
     ls = pkg.LineSegment(40, max_width=640, max_height=480, max_batch=5)
