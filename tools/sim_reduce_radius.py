@@ -39,10 +39,14 @@ def mine(reg, keepf):
             fpos+=t; hm&=~served
         lo+=32
     return reg[:m2]
-random.seed(0)
-for it in range(3000):
-    n=random.randint(1,300); pr=random.random()
-    reg=list(range(n)); keep={v:(random.random()<pr) for v in reg}
-    a=ref(reg, lambda v:keep[v]); b=mine(reg, lambda v:keep[v])
-    assert a==b,(n,a,b)
-print("ok")
+def run(iters=3000, seed=0):
+    random.seed(seed)
+    for it in range(iters):
+        n=random.randint(1,300); pr=random.random()
+        reg=list(range(n)); keep={v:(random.random()<pr) for v in reg}
+        a=ref(reg, lambda v:keep[v]); b=mine(reg, lambda v:keep[v])
+        assert a==b,(n,a,b)
+    return True
+
+if __name__ == '__main__':
+    run(); print('ok')

@@ -60,22 +60,27 @@ def spec(lanes,sx,sy,ang,prec):
         pending&=~((2<<src)-1)
         pending&=~sum(1<<j for j in range(32) if mep[j] and (peers[j]&A))
     return accepted,sx,sy,ang,rounds
-random.seed(1); tot_r=0; tot_a=0
-for it in range(20000):
-    base=random.uniform(0,360); spread=random.choice([5,15,25,40])
-    npix=random.randint(3,14)
-    lanes=[]
-    for j in range(32):
-        p=random.random()<0.4
-        q=random.randint(0,npix)
-        a=f32((base+random.uniform(-spread,spread))%360)
-        lanes.append((p,q,a,f32(math.cos(float(a)*DEG)),f32(math.sin(float(a)*DEG))))
-    # same q => same attrs
-    attrs={}
-    lanes=[(p,q)+attrs.setdefault(q,(a,cx,cy)) for (p,q,a,cx,cy) in lanes]
-    n0=random.randint(1,30)
-    sx=f32(n0*math.cos(base*DEG)); sy=f32(n0*math.sin(base*DEG)); ang=float(atan2deg(sy,sx))*DEG
-    r1=seq(lanes,sx,sy,ang,math.pi/8); r2=spec(lanes,sx,sy,ang,math.pi/8)
-    assert r1[0]==r2[0] and r1[1]==r2[1] and r1[2]==r2[2] and r1[3]==r2[3],(it,r1,r2)
-    tot_r+=r2[4]; tot_a+=len(r1[0])
-print("ok", tot_a/20000, "accepts/iter", tot_r/20000, "rounds/iter")
+def run(iters=20000, seed=1):
+    random.seed(seed); tot_r=0; tot_a=0
+    for it in range(iters):
+        base=random.uniform(0,360); spread=random.choice([5,15,25,40])
+        npix=random.randint(3,14)
+        lanes=[]
+        for j in range(32):
+            p=random.random()<0.4
+            q=random.randint(0,npix)
+            a=f32((base+random.uniform(-spread,spread))%360)
+            lanes.append((p,q,a,f32(math.cos(float(a)*DEG)),f32(math.sin(float(a)*DEG))))
+        # same q => same attrs
+        attrs={}
+        lanes=[(p,q)+attrs.setdefault(q,(a,cx,cy)) for (p,q,a,cx,cy) in lanes]
+        n0=random.randint(1,30)
+        sx=f32(n0*math.cos(base*DEG)); sy=f32(n0*math.sin(base*DEG)); ang=float(atan2deg(sy,sx))*DEG
+        r1=seq(lanes,sx,sy,ang,math.pi/8); r2=spec(lanes,sx,sy,ang,math.pi/8)
+        assert r1[0]==r2[0] and r1[1]==r2[1] and r1[2]==r2[2] and r1[3]==r2[3],(it,r1,r2)
+        tot_r+=r2[4]; tot_a+=len(r1[0])
+    return tot_a/iters, tot_r/iters
+
+if __name__ == '__main__':
+    a, r = run()
+    print('ok', a, 'accepts/iter', r, 'rounds/iter')
