@@ -35,11 +35,13 @@ inline int x86_d2i(double v) {                                      // cvttsd2si
     return (int)v;
 }
 
-/* cv::resize(INTER_LINEAR_EXACT) on 8U — SURVEY.md A.6 (iii); exact when sn/dn is dyadic (the 0.8x case: 1.25) */
-void resize_linear_exact(const uchar* src, int sw, int sh, int sp, uchar* dst, int dw, int dh, int dp) {
+/* cv::resize(src, dst, Size(), fx, fy, INTER_LINEAR_EXACT) on 8U — SURVEY.md A.6 (iii).  With fx, fy given, OpenCV maps
+   destination to source coordinates with scale = 1 / fx (NOT src_size / dst_size; they differ whenever fx * size is not an
+   integer), imgproc/resize.cpp.  For fx = 0.8 the scale is exactly 1.25, so the 8.8 weights are exact in double. */
+void resize_linear_exact(const uchar* src, int sw, int sh, int sp, uchar* dst, int dw, int dh, int dp, double fx) {
     std::vector<int> xi(dw), xw(dw), yi(dh), yw(dh);
-    auto tab = [](int dn, int sn, std::vector<int>& idx, std::vector<int>& w1) {
-        const double sc = (double)sn / dn;
+    auto tab = [fx](int dn, int sn, std::vector<int>& idx, std::vector<int>& w1) {
+        const double sc = 1.0 / fx;
         for (int d = 0; d < dn; d++) {
             double s = (d + 0.5) * sc - 0.5;
             int i0 = (int)floor(s);
@@ -512,7 +514,7 @@ extern "C" int orc_line_extract(orc_line* o, const uchar* img, int w, int h, int
     const double SCALE = 0.8;
     o->sw = cvRoundD(w * SCALE); o->sh = cvRoundD(h * SCALE);
     o->scaled.assign((size_t)o->sw * o->sh, 0);
-    resize_linear_exact(blur.data(), w, h, w, o->scaled.data(), o->sw, o->sh, o->sw);
+    resize_linear_exact(blur.data(), w, h, w, o->scaled.data(), o->sw, o->sh, o->sw, 0.8);
     double t1 = now_ms();
     Lsd lsd; std::vector<Rect> recs;
     lsd.detect(o->scaled.data(), o->sw, o->sh, o->sw, recs);

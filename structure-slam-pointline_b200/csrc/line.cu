@@ -1260,7 +1260,8 @@ void make_geometry(const sslpl_line* h, int W, int H, LineGeom& g, std::vector<i
         tab->assign(g.sw + g.sh, make_int2(0, 0));
         for (int axis = 0; axis < 2; axis++) {
             const int dn = axis ? g.sh : g.sw, sn = axis ? H : W, off = axis ? g.ytab_off : g.xtab_off;
-            const double sc = (double)sn / dn;
+            // cv::resize(..., Size(), 0.8, 0.8, INTER_LINEAR_EXACT) maps with scale = 1 / fx = 1.25, not sn / dn (resize.cpp)
+            const double sc = 1.0 / 0.8; (void)sn;
             for (int d = 0; d < dn; d++) {
                 double s = (d + 0.5) * sc - 0.5;
                 int i0 = (int)floor(s);

@@ -36,7 +36,9 @@ def test_lsd_synthetic_shapes_match_cv2(oracle):
 def test_lsd_matches_cv2_on_frames(oracle, icl_gray, synth):
     """Whole detector incl. the 0.8x pre-processing: identical segments in identical order (225 on the ICL frame)."""
     for name, im in [("icl", icl_gray), ("syn0", synth.frame(640, 480, 0)), ("syn5", synth.frame(640, 480, 5)),
-                     ("syn320", synth.frame(320, 240, 2))]:
+                     ("syn320", synth.frame(320, 240, 2)),
+                     # sizes where 0.8 * size is not an integer: cv::resize maps with 1 / fx, not src / dst
+                     ("syn333x251", synth.frame(333, 251, 2)), ("syn322x243", synth.frame(322, 243, 3)), ("syn336x252", synth.frame(336, 252, 2))]:
         lo = oracle.LineOracle(1 << 20)
         lo.extract(im)
         got = lo.raw_segments(); ref = _cv_lsd(im, None)
