@@ -855,7 +855,7 @@ __device__ double l_rect_improve(const Walk& W, LRect& rec, int* s_cnt, double l
 // that read or write the `used` map).  rect_improve / NFA of a region is a pure function of its rectangle and of the
 // immutable angle map, so it is NOT done here: the walker emits one job per candidate region and k_lsd_nfa evaluates
 // all jobs of all frames in parallel (one warp per job).  `used` lives in shared memory as a bitmap.
-__global__ void __launch_bounds__(32) k_lsd_regions(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
+__global__ void __launch_bounds__(32, 28) k_lsd_regions(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
     const int lane = threadIdx.x;
   for (;;) {
     // frames are pulled from a counter: the grid may be smaller than the batch (sslpl_line_set_max_walkers), which bounds

@@ -314,19 +314,17 @@ __global__ void __launch_bounds__(128) k_fast_cells(const __grid_constant__ OrbG
     if (iniX >= L.maxBX - 6 || iniY >= L.maxBY - 3 || cw < 7 || ch < 7) { if (tid == 0) *cnt_out = 0; return; }
     const int aw = cw - 6, ah = ch - 6, area = aw * ah;
     const uint8_t* sc = ws.score + (long long)f * g.blur_stride + L.blur_off + (long long)(iniY + 3) * L.bpitch + iniX + 3;
-    for (int y = tid >> 5; y < ah + 2; y += 4) {           // a warp per row: no per-element division
-        const uint8_t* src = sc + (long long)(y - 1) * L.bpitch - 1;
-        const bool hrow = (y == 0 || y == ah + 1);
-        for (int x = tid & 31; x < aw + 2; x += 32)
-            s_sc[y * FAST_TP + x] = (hrow || x == 0 || x == aw + 1) ? (uint8_t)0 : __ldg(src + x);
+    for (int i = tid; i < (aw + 2) * (ah + 2); i += 128) {
+        const int y = i / (aw + 2), x = i - y * (aw + 2);
+        const bool halo = (y == 0 || y == ah + 1 || x == 0 || x == aw + 1);
+        s_sc[y * FAST_TP + x] = halo ? (uint8_t)0 : __ldg(sc + (long long)(y - 1) * L.bpitch + (x - 1));
     }
     __syncthreads();
     const int chunk = (area + 127) / 128;                  // <= 28
     const int pb = min(area, tid * chunk), pe = min(area, pb + chunk);
     uint32_t m_all = 0, m_hi = 0;
-    int y = pb / aw, x = pb - y * aw;
-    for (int p = pb; p < pe; p++, x++) {
-        if (x == aw) { x = 0; y++; }
+    for (int p = pb; p < pe; p++) {
+        const int y = p / aw, x = p - y * aw;
         const uint8_t* c = &s_sc[(y + 1) * FAST_TP + x + 1];
         const int s = c[0];
         if (s != 0 && s > c[-1] && s > c[1] && s > c[-FAST_TP - 1] && s > c[-FAST_TP] && s > c[-FAST_TP + 1] &&
@@ -341,15 +339,13 @@ __global__ void __launch_bounds__(128) k_fast_cells(const __grid_constant__ OrbG
     int off = block_exclusive_scan(__popc(m), s_warp, &total);
     uint32_t* out = ws.cand + (long long)f * g.cand_stride + L.cand_off + (long long)ci * L.cell_cap;
     const int ox = iniX + 3 - MINB, oy = iniY + 3 - MINB;   // coordinates relative to (minBorderX, minBorderY)
-    for (uint32_t mm = m; mm; mm &= mm - 1) {                // set bits in ascending (raster) order
-        const int p = pb + __ffs(mm) - 1;
-        {
+    for (int p = pb; p < pe; p++)
+        if (m & (1u << (p - pb))) {
             const int y = p / aw, x = p - y * aw;
             const int s = s_sc[(y + 1) * FAST_TP + x + 1];
             if (off < L.cell_cap) out[off] = (uint32_t)(x + ox) | ((uint32_t)(y + oy) << 12) | ((uint32_t)s << 24);
             off++;
         }
-    }
     if (tid == 0) { *cnt_out = min(total, L.cell_cap); if (total > L.cell_cap) atomicOr(ws.err, DERR_KEY_OVERFLOW); }
 }
 
