@@ -178,6 +178,30 @@ int  sslpl_line_match(sslpl_matcher* m, int mode, const uint8_t* d1, int n1, con
 int  sslpl_match_bow_batch_device(sslpl_matcher* m, const uint8_t* d_desc, const sslpl_keypoint* d_kps, const int* d_n,
                                   int nframes, int cap, const uint8_t* d_centroids, int nc,
                                   float nnratio, int checkOrientation, int32_t* d_match, int32_t* d_nmatch);
+/* ---- DBoW2 vocabulary: Frame::ComputeBoW / KeyFrame::ComputeBoW (Frame.cc:474-481, KeyFrame.cc:71-80), i.e.
+   TemplatedVocabulary<FORB>::transform(features, BowVector&, FeatureVector&, levelsup = 4)
+   (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1259).  SURVEY.md 8(f) row 1. ---- */
+typedef struct sslpl_vocab sslpl_vocab;
+/* The tree as arrays (what loadFromTextFile :1338-1420 builds): node 0 = root, parent[i] < i (parent[0] ignored),
+   desc[i][32], weight[i], is_leaf[i] (must agree with the structure).  Word ids number the leaves in node order. */
+int  sslpl_vocab_create(int device, int k, int L, int nnodes, const int32_t* parent, const uint8_t* desc, const double* weight,
+                        const uint8_t* is_leaf, sslpl_vocab** out);
+/* ORBvoc.txt text format (System.cc:70 mpVocabulary->loadFromTextFile); scoring / weighting = the header's n1 / n2 */
+int  sslpl_vocab_load_text(int device, const char* path, sslpl_vocab** out, int* scoring, int* weighting);
+void sslpl_vocab_destroy(sslpl_vocab* v);
+int  sslpl_vocab_info(const sslpl_vocab* v, int* k, int* L, int* nnodes, int* nwords);
+/* number of distinct FeatureVector node values at level L - levelsup (+1 for node 0: root / leaves above that level) */
+int  sslpl_vocab_level_nodes(const sslpl_vocab* v, int levelsup, int* count);
+/* Per feature (HOST buffers): word id, NodeId at level L - levelsup, leaf weight.  weight <= 0 marks a stopped word, which
+   the reference leaves out of both vectors (:1162-1166).  BowVector / FeatureVector assembly from these three arrays is a
+   host-side map insertion (see the Python mirror's Vocabulary.bow_vector / feature_vector_csr). */
+int  sslpl_bow_transform(sslpl_matcher* m, const sslpl_vocab* v, const uint8_t* desc, int n, int levelsup,
+                         int32_t* word, int32_t* node, double* weight);
+/* sslpl_match_bow_batch_device with the real tree instead of the one-level synthetic vocabulary.  Optional per-feature
+   outputs d_word / d_node / d_weight ([nframes][cap], may be NULL) stay in HBM for the caller's BowVector build. */
+int  sslpl_match_bow_batch_device_vocab(sslpl_matcher* m, const uint8_t* d_desc, const sslpl_keypoint* d_kps, const int* d_n,
+                                        int nframes, int cap, const sslpl_vocab* v, int levelsup, float nnratio, int checkOrientation,
+                                        int32_t* d_match, int32_t* d_nmatch, int32_t* d_word, int32_t* d_node, double* d_weight);
 /* Batched line matching in HBM: knn2 + ratio rule of LSDmatcher::SearchByProjection(KF,F) (:143-183) with all
    KF lines valid: d_lmatch[p*capl + tdx] = qdx or -1; d_nlmatch[p]. */
 int  sslpl_match_lines_batch_device(sslpl_matcher* m, const uint8_t* d_ldesc, const int* d_nl, int nframes, int capl,

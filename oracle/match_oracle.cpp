@@ -90,6 +90,46 @@ extern "C" void orc_bow_assign(const uint8_t* desc, int n, const uint8_t* centro
     }
 }
 
+/* DBoW2 TemplatedVocabulary<FORB>::transform(features, BowVector&, FeatureVector&, levelsup)
+   (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1195) with the per-feature tree descent of :1218-1259.
+   The tree is given as arrays (what loadFromTextFile :1338-1420 builds): node 0 = root, parent[i] < i, children of a node
+   in ascending node id, is_leaf[i] as in the file, word ids numbered over the leaves in node order.
+   Per feature: word[i], node[i] (the NodeId at level L - levelsup; 0 when the leaf is reached earlier or the level is <= 0 —
+   the reference leaves it uninitialised in the first case), weight[i] (the leaf's weight; TF_IDF / IDF: idf, TF / BINARY: 1
+   is already folded into the file's weights).  Features with weight <= 0 ("stopped" words) are not part of the
+   FeatureVector (:1162-1166): the caller drops them. */
+extern "C" int orc_vocab_transform(int L, int nnodes, const int32_t* parent, const uint8_t* ndesc, const double* weight,
+                                   const uint8_t* is_leaf, const uint8_t* feats, int n, int levelsup,
+                                   int32_t* word, int32_t* node, double* w) {
+    std::vector<std::vector<int>> children(nnodes);
+    std::vector<int> word_id(nnodes, -1);
+    int nwords = 0;
+    for (int i = 1; i < nnodes; i++) {
+        if (parent[i] < 0 || parent[i] >= i) return -1;
+        children[parent[i]].push_back(i);
+        if (is_leaf[i]) word_id[i] = nwords++;
+    }
+    const int nid_level = L - levelsup;
+    for (int f = 0; f < n; f++) {
+        const uint8_t* feat = feats + 32 * (size_t)f;
+        int nid = 0, final_id = 0, current_level = 0;
+        do {
+            ++current_level;
+            const std::vector<int>& nodes = children[final_id];
+            if (nodes.empty()) break;                              // (an empty vocabulary: the reference returns early)
+            final_id = nodes[0];
+            double best_d = orc_descriptor_distance(feat, ndesc + 32 * (size_t)final_id);
+            for (size_t c = 1; c < nodes.size(); c++) {
+                const double d = orc_descriptor_distance(feat, ndesc + 32 * (size_t)nodes[c]);
+                if (d < best_d) { best_d = d; final_id = nodes[c]; }
+            }
+            if (current_level == nid_level) nid = final_id;
+        } while (!children[final_id].empty());
+        word[f] = word_id[final_id]; node[f] = nid; w[f] = weight[final_id];
+    }
+    return nwords;
+}
+
 /* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) — ORBmatcher.cc:159-291 */
 extern "C" int orc_search_by_bow(const uint8_t* d1, int n1, const uint8_t* d2, int n2,
                                  const int32_t* nodes1, const int32_t* off1, const int32_t* idx1, int nn1,

@@ -62,6 +62,10 @@ int   orc_descriptor_distance(const uint8_t* a, const uint8_t* b);          /* O
 void  orc_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out);
 /* synthetic-vocabulary node assignment (stands in for DBoW2 transform): nearest centroid, first wins */
 void  orc_bow_assign(const uint8_t* desc, int n, const uint8_t* centroids, int nc, int32_t* node);
+/* DBoW2 transform on a vocabulary tree given as arrays (TemplatedVocabulary.h:1127-1259); returns the number of words or -1 */
+int   orc_vocab_transform(int L, int nnodes, const int32_t* parent, const uint8_t* ndesc, const double* weight,
+                          const uint8_t* is_leaf, const uint8_t* feats, int n, int levelsup,
+                          int32_t* word, int32_t* node, double* w);
 /* SearchByBoW(KeyFrame*,Frame&) ORBmatcher.cc:159-291. FeatureVectors in CSR (node ids ascending).
    valid1[i]!=0 <=> KF feature i has a good MapPoint. match2[j] = KF index matched to frame feature j or -1. */
 int   orc_search_by_bow(const uint8_t* d1, int n1, const uint8_t* d2, int n2,

@@ -184,6 +184,20 @@ def bow_assign(desc, centroids):
     return node[:len(desc)]
 
 
+def vocab_transform(L, parent, ndesc, weight, is_leaf, feats, levelsup=4):
+    """DBoW2 transform (TemplatedVocabulary.h:1127-1259) on a tree given as arrays -> (word, node, weight) per feature."""
+    parent = np.ascontiguousarray(parent, np.int32); ndesc = np.ascontiguousarray(ndesc, np.uint8).reshape(-1, 32)
+    weight = np.ascontiguousarray(weight, np.float64); is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+    feats = np.ascontiguousarray(feats, np.uint8).reshape(-1, 32)
+    n = len(feats)
+    word = np.empty(max(n, 1), np.int32); node = np.empty(max(n, 1), np.int32); w = np.empty(max(n, 1), np.float64)
+    lib().orc_vocab_transform.restype = C.c_int
+    nw = lib().orc_vocab_transform(int(L), len(parent), _p(parent), _p(ndesc), _p(weight), _p(is_leaf), _p(feats), n, int(levelsup),
+                                   _p(word), _p(node), _p(w))
+    assert nw >= 0, "malformed vocabulary tree"
+    return word[:n], node[:n], w[:n]
+
+
 def feature_vector_csr(node):
     """DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>, FeatureVector.cpp:31-45) flattened to CSR:
     node ids ascending, feature indices ascending inside a node."""

@@ -323,9 +323,138 @@ class Matcher:
                                                   C.c_void_p(d_centroids), nc, C.c_float(nnratio), int(check_ori),
                                                   C.c_void_p(d_match), C.c_void_p(d_nmatch)))
 
+    def match_bow_batch_device_vocab(self, d_desc, d_kps, d_n, nframes, cap, vocab, levelsup, nnratio, check_ori, d_match, d_nmatch,
+                                     d_word=0, d_node=0, d_weight=0):
+        """Batched SearchByBoW with the DBoW2 tree transform (optional per-feature word / node / weight outputs in HBM)."""
+        _check(lib().sslpl_match_bow_batch_device_vocab(self._h, C.c_void_p(d_desc), C.c_void_p(d_kps), C.c_void_p(d_n), nframes, cap,
+                                                        vocab._h, int(levelsup), C.c_float(nnratio), int(check_ori),
+                                                        C.c_void_p(d_match), C.c_void_p(d_nmatch),
+                                                        C.c_void_p(d_word or None), C.c_void_p(d_node or None), C.c_void_p(d_weight or None)))
+
+    def bow_transform(self, vocab, desc, levelsup=4):
+        """TemplatedVocabulary::transform per feature (TemplatedVocabulary.h:1218-1259): (word, node, weight) arrays."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        word = np.empty(max(n, 1), np.int32); node = np.empty(max(n, 1), np.int32); w = np.empty(max(n, 1), np.float64)
+        _check(lib().sslpl_bow_transform(self._h, vocab._h, _p(desc), n, int(levelsup), _p(word), _p(node), _p(w)))
+        return word[:n], node[:n], w[:n]
+
     def match_lines_batch_device(self, d_ldesc, d_nl, nframes, capl, d_lmatch, d_nlmatch):
         _check(lib().sslpl_match_lines_batch_device(self._h, C.c_void_p(d_ldesc), C.c_void_p(d_nl), nframes, capl,
                                                     C.c_void_p(d_lmatch), C.c_void_p(d_nlmatch)))
+
+
+class Vocabulary:
+    """DBoW2 ORB vocabulary tree on the device (the reference's ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB>,
+    include/ORBVocabulary.h; used by Frame::ComputeBoW Frame.cc:474-481 with levelsup = 4).
+
+    Vocabulary(k, L, parent, desc, weight, is_leaf)   from arrays (node 0 = root)
+    Vocabulary.load_text(path)                          ORBvoc.txt (TemplatedVocabulary.h:1338-1420)
+    Vocabulary.random(k, L, seed)                       synthetic tree for tests / benchmarks"""
+    # scoring / weighting enums of DBoW2 (BowVector.h): the defaults of ORBvoc.txt are L1_NORM (0) and TF_IDF (0)
+    TF_IDF, TF, IDF, BINARY = 0, 1, 2, 3
+
+    def __init__(self, k, L, parent, desc, weight, is_leaf, device=0, scoring=0, weighting=0):
+        self.parent = np.ascontiguousarray(parent, np.int32); self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.weight = np.ascontiguousarray(weight, np.float64); self.is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        self.k, self.L, self.scoring, self.weighting = int(k), int(L), int(scoring), int(weighting)
+        self._h = C.c_void_p()
+        _check(lib().sslpl_vocab_create(device, self.k, self.L, len(self.parent), _p(self.parent), _p(self.desc), _p(self.weight),
+                                        _p(self.is_leaf), C.byref(self._h)))
+
+    @classmethod
+    def load_text(cls, path, device=0):
+        self = cls.__new__(cls)
+        self._h = C.c_void_p(); sc = C.c_int(); we = C.c_int()
+        _check(lib().sslpl_vocab_load_text(device, str(path).encode(), C.byref(self._h), C.byref(sc), C.byref(we)))
+        k = C.c_int(); L = C.c_int()
+        _check(lib().sslpl_vocab_info(self._h, C.byref(k), C.byref(L), None, None))
+        self.k, self.L, self.scoring, self.weighting = k.value, L.value, sc.value, we.value
+        self.parent = self.desc = self.weight = self.is_leaf = None
+        return self
+
+    @staticmethod
+    def random_arrays(k, L, seed=0, stop_fraction=0.0, early_leaf_fraction=0.0):
+        """A random k-ary tree of depth L as arrays, in the node order loadFromTextFile produces for a file written level by
+        level is NOT required: any order with parent[i] < i works.  Some leaves can be 'stopped' (weight 0) or sit above L."""
+        rng = np.random.default_rng(seed)
+        parent = [-1]; depth = [0]; frontier = [0]
+        for d in range(1, L + 1):
+            nxt = []
+            for p in frontier:
+                if d > 1 and rng.random() < early_leaf_fraction:
+                    continue                                        # p stays a leaf above the last level
+                for _ in range(k):
+                    parent.append(p); depth.append(d); nxt.append(len(parent) - 1)
+            frontier = nxt
+        n = len(parent)
+        parent = np.array(parent, np.int32)
+        has_child = np.zeros(n, bool); has_child[parent[1:]] = True
+        is_leaf = (~has_child).astype(np.uint8); is_leaf[0] = 0
+        desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        weight = np.where(is_leaf == 1, rng.random(n) * 5 + 0.1, 0.0)
+        weight[(is_leaf == 1) & (rng.random(n) < stop_fraction)] = 0.0
+        return parent, desc, weight.astype(np.float64), is_leaf
+
+    @classmethod
+    def random(cls, k=10, L=3, seed=0, device=0, **kw):
+        parent, desc, weight, is_leaf = cls.random_arrays(k, L, seed, **kw)
+        return cls(k, L, parent, desc, weight, is_leaf, device=device)
+
+    def info(self):
+        k = C.c_int(); L = C.c_int(); nn = C.c_int(); nw = C.c_int()
+        _check(lib().sslpl_vocab_info(self._h, C.byref(k), C.byref(L), C.byref(nn), C.byref(nw)))
+        return {"k": k.value, "L": L.value, "nodes": nn.value, "words": nw.value}
+
+    def level_nodes(self, levelsup=4):
+        c = C.c_int()
+        _check(lib().sslpl_vocab_level_nodes(self._h, int(levelsup), C.byref(c)))
+        return c.value
+
+    def bow_vector(self, word, weight):
+        """BowVector assembly of TemplatedVocabulary::transform (:1145-1195) from the per-feature arrays: a word -> value map
+        (ascending word id), TF_IDF / TF: weights added in feature order then divided by the number of words unless the scoring
+        normalises (L1 / L2 scoring types 0, 1 do); IDF / BINARY: first weight kept."""
+        bv = {}
+        for wid, w in zip(np.asarray(word).tolist(), np.asarray(weight).tolist()):
+            if not w > 0:
+                continue
+            if self.weighting in (self.TF_IDF, self.TF):
+                bv[wid] = bv.get(wid, 0.0) + w
+            else:
+                bv.setdefault(wid, w)
+        must, l2 = self.scoring in (0, 1), self.scoring == 1      # L1_NORM, L2_NORM normalise (ScoringObject.cpp)
+        keys = sorted(bv)
+        if self.weighting in (self.TF_IDF, self.TF) and bv and not must:
+            nd = float(len(bv))
+            for kk in keys:
+                bv[kk] /= nd
+        if must and bv:
+            norm = 0.0
+            for kk in keys:
+                norm += bv[kk] * bv[kk] if l2 else abs(bv[kk])
+            if l2:
+                norm = float(np.sqrt(norm))
+            if norm > 0.0:
+                for kk in keys:
+                    bv[kk] /= norm
+        return np.array(keys, np.int32), np.array([bv[kk] for kk in keys], np.float64)
+
+    @staticmethod
+    def feature_vector(node, weight):
+        """FeatureVector (node id -> ascending feature indices) as CSR, without the stopped words (:1162-1166)."""
+        node = np.asarray(node, np.int32); keep = np.nonzero(np.asarray(weight) > 0)[0].astype(np.int32)
+        order = keep[np.argsort(node[keep], kind="stable")]
+        ids, counts = np.unique(node[keep], return_counts=True)
+        off = np.zeros(len(ids) + 1, np.int32); off[1:] = np.cumsum(counts)
+        return ids.astype(np.int32), off, order.astype(np.int32)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().sslpl_vocab_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
 
 
 class ORBmatcher:

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <vector>
 
 namespace sslpl {
@@ -99,6 +100,50 @@ __global__ void __launch_bounds__(128) k_bow_assign(const uint8_t* desc, long lo
     node[f * node_fs + i] = bi;
 }
 
+// -------------------------------------------------------------------------------------------------
+// DBoW2 TemplatedVocabulary<FORB>::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1259): descend the
+// k-ary tree by Hamming distance (strict '<': the first best child wins), one thread per descriptor.  The tree is
+// stored as CSR children lists (ascending node id, as loadFromTextFile builds them) + 32-byte node descriptors; the
+// upper levels stay resident in L1/L2 (ORBvoc: 1.1 M nodes x 32 B = 35 MB < 126 MB L2).
+//   word  = word id of the leaf,  node = NodeId at level L - levelsup (0 if the leaf comes earlier),
+//   rank  = dense index of `node` among the possible values (0 = root / early leaf, 1 + rank inside the level), or -1 for a
+//           stopped word (weight <= 0), which the reference keeps out of the FeatureVector (:1162-1166).
+// -------------------------------------------------------------------------------------------------
+struct VocabView { const int* child_off; const int* child_ids; const uint8_t* desc; const double* weight; const int* word_id; const int* level_rank; };
+
+__global__ void __launch_bounds__(128) k_vocab_transform(const uint8_t* desc, long long desc_fs, const int* n_arr, int n_const, int cap,
+                                                          VocabView V, int nid_level, int32_t* word, int32_t* node, int32_t* rank,
+                                                          double* weight, long long out_fs) {
+    const int f = blockIdx.y;
+    const int n = n_arr ? min(n_arr[f], cap) : n_const;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 a0, a1;
+    load_desc(desc + f * desc_fs + (long long)i * 32, a0, a1);
+    int cur = 0, nid = 0, level = 0;
+    int cb = __ldg(V.child_off), ce = __ldg(V.child_off + 1);
+    while (ce > cb) {
+        ++level;
+        int best = 1 << 30, bi = 0;
+        for (int c = cb; c < ce; c++) {
+            const int id = __ldg(V.child_ids + c);
+            uint4 b0, b1;
+            load_desc(V.desc + (long long)id * 32, b0, b1);
+            const int d = popc256(a0, a1, b0, b1);
+            if (d < best) { best = d; bi = id; }
+        }
+        cur = bi;
+        if (level == nid_level) nid = cur;
+        cb = __ldg(V.child_off + cur); ce = __ldg(V.child_off + cur + 1);
+    }
+    const double w = __ldg(V.weight + cur);
+    const long long o = f * out_fs + i;
+    if (word) word[o] = __ldg(V.word_id + cur);
+    if (node) node[o] = nid;
+    if (weight) weight[o] = w;
+    if (rank) rank[o] = (w > 0) ? (nid == 0 ? 0 : 1 + __ldg(V.level_rank + nid)) : -1;
+}
+
 // FeatureVector build for a dense vocabulary (every node 0..nc-1 listed, possibly empty): CSR with
 // ascending feature indices per node (FeatureVector.cpp:31-45).  One CTA per frame, thread per node.
 __global__ void __launch_bounds__(128) k_build_csr(const int32_t* node, long long node_fs, const int* n_arr, int cap, int nc,
@@ -111,7 +156,7 @@ __global__ void __launch_bounds__(128) k_build_csr(const int32_t* node, long lon
     const int32_t* nd = node + f * node_fs;
     for (int c = tid; c <= nc; c += blockDim.x) s_cnt[c] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) { const int v = nd[i]; s_nd[i] = v; atomicAdd(&s_cnt[v], 1); }
+    for (int i = tid; i < n; i += blockDim.x) { const int v = nd[i]; s_nd[i] = v; if (v >= 0) atomicAdd(&s_cnt[v], 1); }   // v < 0: stopped word, not in the FeatureVector
     __syncthreads();
     block_scan_array(s_cnt, nc + 1, s_warp);                  // exclusive offsets, s_cnt[nc] = n
     for (int c = tid; c <= nc; c += blockDim.x) off[f * off_fs + c] = s_cnt[c];
@@ -334,6 +379,14 @@ __global__ void __launch_bounds__(128) k_line_ratio(const int32_t* knn, long lon
 // =================================================================================================
 using namespace sslpl;
 
+struct sslpl_vocab {
+    int device = 0, k = 0, L = 0, nnodes = 0, nwords = 0;
+    uint8_t* arena = nullptr;
+    sslpl::VocabView view{};
+    std::vector<int> depth;              // per node
+    std::vector<int> level_count;        // nodes per depth
+};
+
 struct sslpl_matcher {
     sslpl_matcher_params p;
     cudaStream_t stream = nullptr, own_stream = nullptr;
@@ -342,6 +395,7 @@ struct sslpl_matcher {
     // single-call staging: 2 frame slots
     uint8_t* desc; int* nodes; int* off; int* idx; uint8_t* flag; float* kpf; int* nn2; int* ncnt;
     int32_t* out; uint8_t* rot; uint8_t* taken; int32_t* pairs; int32_t* nmatch; int32_t* knn; uint8_t* cent; int32_t* node;
+    int32_t* word; double* wgt;      // per-feature outputs of the vocabulary transform (single-call staging)
     // batch workspace
     int32_t* b_node; int* b_off; int* b_idx; uint8_t* b_rot; uint8_t* b_taken; int32_t* b_knn; int* iota;
     int32_t* h_small = nullptr;      // pinned scratch
@@ -361,6 +415,7 @@ int carve(sslpl_matcher* m, Arena& A) {
     m->pairs = A.take<int32_t>((size_t)2 * cap); m->nmatch = A.take<int32_t>(B);
     m->knn = A.take<int32_t>((size_t)4 * cap);
     m->cent = A.take<uint8_t>((size_t)NN * 32); m->node = A.take<int32_t>(cap);
+    m->word = A.take<int32_t>(cap); m->wgt = A.take<double>(cap);
     const int fc = m->p.max_features + 64, lc = m->p.max_lines + 64;
     m->b_node = A.take<int32_t>((size_t)B * fc); m->b_off = A.take<int>((size_t)B * (NN + 1)); m->b_idx = A.take<int>((size_t)B * fc);
     m->b_rot = A.take<uint8_t>((size_t)B * fc); m->b_taken = A.take<uint8_t>((size_t)B * fc);
@@ -670,18 +725,13 @@ int sslpl_line_match(sslpl_matcher* m, int mode, const uint8_t* d1, int n1, cons
     return SSLPL_OK;
 }
 
-int sslpl_match_bow_batch_device(sslpl_matcher* m, const uint8_t* d_desc, const sslpl_keypoint* d_kps, const int* d_n,
-                                 int nframes, int cap, const uint8_t* d_centroids, int nc, float nnratio, int checkOri,
-                                 int32_t* d_match, int32_t* d_nmatch) {
-    SSLPL_REQUIRE(m && d_desc && d_kps && d_n && d_centroids && d_match && d_nmatch, SSLPL_ERR_ARG, "null argument");
-    SSLPL_REQUIRE(nframes >= 2 && nframes <= m->p.max_batch + 1, SSLPL_ERR_ARG, "nframes exceeds max_batch+1");
-    SSLPL_REQUIRE(cap >= 1 && cap <= m->p.max_features + 64 && nc >= 1 && nc <= m->p.max_nodes, SSLPL_ERR_ARG, "cap or nc exceeds the matcher capacity");
-    SSLPL_CUDA(cudaSetDevice(m->p.device));
+// common tail of the batched consecutive-frame SearchByBoW: b_node holds the dense node index (or -1) of every feature
+static int bow_batch_tail(sslpl_matcher* m, const uint8_t* d_desc, const sslpl_keypoint* d_kps, const int* d_n, int nframes, int cap, int nc,
+                          float nnratio, int checkOri, int32_t* d_match, int32_t* d_nmatch) {
     cudaStream_t st = m->stream;
     const int npairs = nframes - 1, fc = m->p.max_features + 64, NN = m->p.max_nodes + 1;
-    k_bow_assign<<<dim3((cap + 127) / 128, nframes), 128, nc * 32, st>>>(d_desc, (long long)cap * 32, d_n, 0, cap, d_centroids, nc, m->b_node, fc);
     k_build_csr<<<nframes, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->b_node, fc, d_n, cap, nc, m->b_off, NN + 1, m->b_idx, fc);
-    m->launches += 2;
+    m->launches += 1;
     fill(m, d_match, (long long)npairs * cap, -1);
     SSLPL_CUDA(cudaMemsetAsync(m->b_rot, 255, (size_t)npairs * fc, st));
     SSLPL_CUDA(cudaMemsetAsync(m->b_taken, 0, (size_t)npairs * fc, st));
@@ -699,6 +749,165 @@ int sslpl_match_bow_batch_device(sslpl_matcher* m, const uint8_t* d_desc, const 
     m->launches += 2;
     SSLPL_CUDA(cudaGetLastError());
     return SSLPL_OK;
+}
+
+int sslpl_match_bow_batch_device(sslpl_matcher* m, const uint8_t* d_desc, const sslpl_keypoint* d_kps, const int* d_n,
+                                 int nframes, int cap, const uint8_t* d_centroids, int nc, float nnratio, int checkOri,
+                                 int32_t* d_match, int32_t* d_nmatch) {
+    SSLPL_REQUIRE(m && d_desc && d_kps && d_n && d_centroids && d_match && d_nmatch, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(nframes >= 2 && nframes <= m->p.max_batch + 1, SSLPL_ERR_ARG, "nframes exceeds max_batch+1");
+    SSLPL_REQUIRE(cap >= 1 && cap <= m->p.max_features + 64 && nc >= 1 && nc <= m->p.max_nodes, SSLPL_ERR_ARG, "cap or nc exceeds the matcher capacity");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    const int fc = m->p.max_features + 64;
+    k_bow_assign<<<dim3((cap + 127) / 128, nframes), 128, nc * 32, m->stream>>>(d_desc, (long long)cap * 32, d_n, 0, cap, d_centroids, nc, m->b_node, fc);
+    m->launches += 1;
+    return bow_batch_tail(m, d_desc, d_kps, d_n, nframes, cap, nc, nnratio, checkOri, d_match, d_nmatch);
+}
+
+// ---------------- DBoW2 vocabulary ----------------
+static int vocab_level_nodes(const sslpl_vocab* v, int levelsup) {
+    const int lvl = v->L - levelsup;
+    return 1 + ((lvl >= 1 && lvl < (int)v->level_count.size()) ? v->level_count[lvl] : 0);
+}
+
+int sslpl_vocab_create(int device, int k, int L, int nnodes, const int32_t* parent, const uint8_t* desc, const double* weight,
+                       const uint8_t* is_leaf, sslpl_vocab** out) {
+    SSLPL_REQUIRE(out && parent && desc && weight && is_leaf, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(k >= 1 && L >= 1 && nnodes >= 1, SSLPL_ERR_ARG, "bad vocabulary shape");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_error("no CUDA device available: libsslpl_b200 has no CPU fallback"); return SSLPL_ERR_CUDA; }
+    SSLPL_CUDA(cudaSetDevice(device));
+    std::vector<int> cnt(nnodes + 1, 0), depth(nnodes, 0), word(nnodes, -1), rank(nnodes, 0);
+    for (int i = 1; i < nnodes; i++) {
+        SSLPL_REQUIRE(parent[i] >= 0 && parent[i] < i, SSLPL_ERR_ARG, "vocabulary: parent[i] must be an earlier node");
+        cnt[parent[i] + 1]++; depth[i] = depth[parent[i]] + 1;
+    }
+    for (int i = 0; i < nnodes; i++) cnt[i + 1] += cnt[i];                    // CSR offsets
+    std::vector<int> ids(std::max(nnodes - 1, 1)), fillp(cnt.begin(), cnt.end() - 1);
+    for (int i = 1; i < nnodes; i++) ids[fillp[parent[i]]++] = i;             // ascending ids inside every list
+    int nwords = 0, maxd = 0;
+    for (int i = 1; i < nnodes; i++) {
+        const bool leaf = cnt[i + 1] == cnt[i];
+        SSLPL_REQUIRE(leaf == (is_leaf[i] != 0), SSLPL_ERR_ARG, "vocabulary: is_leaf disagrees with the tree structure");
+        if (leaf) word[i] = nwords++;
+        maxd = std::max(maxd, depth[i]);
+    }
+    sslpl_vocab* v = new sslpl_vocab();
+    v->device = device; v->k = k; v->L = L; v->nnodes = nnodes; v->nwords = nwords; v->depth = depth;
+    v->level_count.assign(maxd + 1, 0);
+    for (int i = 0; i < nnodes; i++) rank[i] = v->level_count[depth[i]]++;    // rank among the nodes of the same depth, ascending id
+    Arena A;
+    A.base = nullptr; A.used = 0;
+    auto carve_all = [&](Arena& a, sslpl::VocabView& w) {
+        w.child_off = a.take<int>(nnodes + 1); w.child_ids = a.take<int>(ids.size()); w.desc = a.take<uint8_t>((size_t)nnodes * 32);
+        w.weight = a.take<double>(nnodes); w.word_id = a.take<int>(nnodes); w.level_rank = a.take<int>(nnodes);
+    };
+    sslpl::VocabView dry{}; carve_all(A, dry);
+    const size_t bytes = A.used + 256;
+    cudaError_t e = cudaMalloc(&v->arena, bytes);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); delete v; return SSLPL_ERR_CUDA; }
+    Arena B2; B2.base = v->arena; B2.used = 0;
+    carve_all(B2, v->view);
+    SSLPL_CUDA(cudaMemcpy(const_cast<int*>(v->view.child_off), cnt.data(), sizeof(int) * (nnodes + 1), cudaMemcpyHostToDevice));
+    SSLPL_CUDA(cudaMemcpy(const_cast<int*>(v->view.child_ids), ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice));
+    SSLPL_CUDA(cudaMemcpy(const_cast<uint8_t*>(v->view.desc), desc, (size_t)nnodes * 32, cudaMemcpyHostToDevice));
+    SSLPL_CUDA(cudaMemcpy(const_cast<double*>(v->view.weight), weight, sizeof(double) * nnodes, cudaMemcpyHostToDevice));
+    SSLPL_CUDA(cudaMemcpy(const_cast<int*>(v->view.word_id), word.data(), sizeof(int) * nnodes, cudaMemcpyHostToDevice));
+    SSLPL_CUDA(cudaMemcpy(const_cast<int*>(v->view.level_rank), rank.data(), sizeof(int) * nnodes, cudaMemcpyHostToDevice));
+    *out = v;
+    return SSLPL_OK;
+}
+
+// ORBvoc.txt text format of TemplatedVocabulary::loadFromTextFile (TemplatedVocabulary.h:1338-1420):
+// "k L scoring weighting" then one line per node: "parent is_leaf b0 .. b31 weight".  Blank lines are skipped (the reference's
+// `while(!f.eof())` loop turns the trailing newline into one bogus node with an uninitialised parent).
+int sslpl_vocab_load_text(int device, const char* path, sslpl_vocab** out, int* scoring, int* weighting) {
+    SSLPL_REQUIRE(path && out, SSLPL_ERR_ARG, "null argument");
+    FILE* f = fopen(path, "r");
+    if (!f) { set_error("cannot open vocabulary file %s", path); return SSLPL_ERR_ARG; }
+    int k = 0, L = 0, n1 = 0, n2 = 0;
+    if (fscanf(f, "%d %d %d %d", &k, &L, &n1, &n2) != 4 || k < 0 || k > 20 || L < 1 || L > 10 || n1 < 0 || n1 > 5 || n2 < 0 || n2 > 3) {
+        fclose(f); set_error("%s is not a DBoW2 text vocabulary", path); return SSLPL_ERR_ARG;
+    }
+    std::vector<int32_t> parent(1, -1); std::vector<uint8_t> desc(32, 0), leaf(1, 0); std::vector<double> weight(1, 0.0);
+    for (;;) {
+        int pid, isleaf;
+        if (fscanf(f, "%d %d", &pid, &isleaf) != 2) break;
+        uint8_t d[32];
+        bool ok = true;
+        for (int i = 0; i < 32 && ok; i++) { int b; ok = fscanf(f, "%d", &b) == 1; d[i] = (uint8_t)b; }
+        double w = 0;
+        ok = ok && fscanf(f, "%lf", &w) == 1;
+        if (!ok) { fclose(f); set_error("%s: truncated node line", path); return SSLPL_ERR_ARG; }
+        parent.push_back(pid); leaf.push_back(isleaf > 0 ? 1 : 0); weight.push_back(w); desc.insert(desc.end(), d, d + 32);
+    }
+    fclose(f);
+    if (scoring) *scoring = n1;
+    if (weighting) *weighting = n2;
+    return sslpl_vocab_create(device, k, L, (int)parent.size(), parent.data(), desc.data(), weight.data(), leaf.data(), out);
+}
+
+void sslpl_vocab_destroy(sslpl_vocab* v) {
+    if (!v) return;
+    cudaSetDevice(v->device);
+    if (v->arena) cudaFree(v->arena);
+    delete v;
+}
+
+int sslpl_vocab_info(const sslpl_vocab* v, int* k, int* L, int* nnodes, int* nwords) {
+    SSLPL_REQUIRE(v, SSLPL_ERR_ARG, "null vocabulary");
+    if (k) *k = v->k;
+    if (L) *L = v->L;
+    if (nnodes) *nnodes = v->nnodes;
+    if (nwords) *nwords = v->nwords;
+    return SSLPL_OK;
+}
+
+int sslpl_vocab_level_nodes(const sslpl_vocab* v, int levelsup, int* count) {
+    SSLPL_REQUIRE(v && count, SSLPL_ERR_ARG, "null argument");
+    *count = vocab_level_nodes(v, levelsup);
+    return SSLPL_OK;
+}
+
+int sslpl_bow_transform(sslpl_matcher* m, const sslpl_vocab* v, const uint8_t* desc, int n, int levelsup,
+                        int32_t* word, int32_t* node, double* weight) {
+    SSLPL_REQUIRE(m && v && (n == 0 || (desc && word && node && weight)), SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(n >= 0 && n <= m->cap, SSLPL_ERR_ARG, "n exceeds the matcher capacity");
+    SSLPL_REQUIRE(v->device == m->p.device, SSLPL_ERR_ARG, "vocabulary and matcher live on different devices");
+    if (n == 0) return SSLPL_OK;
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    k_vocab_transform<<<dim3((n + 127) / 128, 1), 128, 0, st>>>(m->desc, 0, nullptr, n, n, v->view, v->L - levelsup, m->word, m->node, nullptr, m->wgt, 0);
+    m->launches++;
+    SSLPL_CUDA(cudaGetLastError());
+    SSLPL_CUDA(cudaMemcpyAsync(word, m->word, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaMemcpyAsync(node, m->node, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaMemcpyAsync(weight, m->wgt, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    return SSLPL_OK;
+}
+
+int sslpl_match_bow_batch_device_vocab(sslpl_matcher* m, const uint8_t* d_desc, const sslpl_keypoint* d_kps, const int* d_n,
+                                       int nframes, int cap, const sslpl_vocab* v, int levelsup, float nnratio, int checkOri,
+                                       int32_t* d_match, int32_t* d_nmatch, int32_t* d_word, int32_t* d_node, double* d_weight) {
+    SSLPL_REQUIRE(m && v && d_desc && d_kps && d_n && d_match && d_nmatch, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(nframes >= 2 && nframes <= m->p.max_batch + 1, SSLPL_ERR_ARG, "nframes exceeds max_batch+1");
+    const int nc = vocab_level_nodes(v, levelsup);
+    SSLPL_REQUIRE(cap >= 1 && cap <= m->p.max_features + 64 && nc <= m->p.max_nodes, SSLPL_ERR_ARG, "cap or the vocabulary level exceeds the matcher capacity (max_nodes)");
+    SSLPL_REQUIRE(v->device == m->p.device, SSLPL_ERR_ARG, "vocabulary and matcher live on different devices");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    const int fc = m->p.max_features + 64;
+    // optional per-feature outputs use the caller's [nframes][cap] layout; the dense node index goes to the workspace ([..][fc])
+    if (d_word || d_node || d_weight) {
+        k_vocab_transform<<<dim3((cap + 127) / 128, nframes), 128, 0, m->stream>>>(d_desc, (long long)cap * 32, d_n, 0, cap, v->view, v->L - levelsup,
+                                                                                      d_word, d_node, nullptr, d_weight, cap);
+        m->launches += 1;
+    }
+    k_vocab_transform<<<dim3((cap + 127) / 128, nframes), 128, 0, m->stream>>>(d_desc, (long long)cap * 32, d_n, 0, cap, v->view, v->L - levelsup,
+                                                                                  nullptr, nullptr, m->b_node, nullptr, fc);
+    m->launches += 1;
+    return bow_batch_tail(m, d_desc, d_kps, d_n, nframes, cap, nc, nnratio, checkOri, d_match, d_nmatch);
 }
 
 int sslpl_match_lines_batch_device(sslpl_matcher* m, const uint8_t* d_ldesc, const int* d_nl, int nframes, int capl,
