@@ -91,7 +91,7 @@ def test_vocabulary_text_file_round_trip(pkg, oracle, tmp_path):
     with open(path, "w") as f:
         f.write(f"{k} {L} 0 0\n")
         for i in range(1, len(parent)):
-            f.write(f"{parent[i]} {int(is_leaf[i])} " + " ".join(str(int(b)) for b in ndesc[i]) + f" {weight[i]!r}\n")
+            f.write(f"{parent[i]} {int(is_leaf[i])} " + " ".join(str(int(b)) for b in ndesc[i]) + f" {float(weight[i])!r}\n")
     voc = pkg.Vocabulary.load_text(path)
     assert (voc.k, voc.L, voc.scoring, voc.weighting) == (k, L, 0, 0) and voc.info()["nodes"] == len(parent)
     feats = np.random.default_rng(2).integers(0, 256, (300, 32), dtype=np.uint8)
