@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ OrbGeom 
 template <bool TMA>
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g, OrbWs ws, View v, const CUtensorMap* tm) {
     __shared__ __align__(128) uint8_t s_img[TL_IH * TL_P];
-    __shared__ __align__(8) unsigned short s_row[TL_IH * TL_W];
+    __shared__ __align__(16) unsigned s_pair[TL_IH * TL_W];             // [r][x] = row pass of row r | row r+1 << 16
     __shared__ __align__(8) uint64_t s_bar;
     const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     int l = 0;
@@ -613,39 +613,38 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g,
         }
         __syncthreads();
     }
-    // horizontal pass: four outputs per item from ten bytes, fetched as three aligned words (TL_X - 3 = 13 = 12 + 1)
+    // Packed arithmetic (taps 18 34 48 56 48 34 18): horizontal pass = two dp4a per output on byte windows cut out of three
+    // aligned words with funnel shifts (TL_X - 3 = 13 = 12 + 1); the u16 results are stored as vertical PAIRS
+    // (row r | row r+1 << 16) so that the vertical pass is four dp2a per output.  Partial sums stay below 2^16 / 2^32: exact.
     static_assert(TL_X == 16 && TL_P % 4 == 0, "word-aligned row reads assume TL_X == 16");
+    constexpr unsigned T0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), T1 = 48u | (34u << 8) | (18u << 16);
+    unsigned short* s_half = reinterpret_cast<unsigned short*>(s_pair);
     for (int i = tid; i < TL_IH * (TL_W / 4); i += 256) {
         const int r = i >> 4, x4 = (i & 15) * 4;
         const unsigned* w = reinterpret_cast<const unsigned*>(&s_img[r * TL_P + x4 + TL_X - 4]);
-        const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
-        int b[10];                                                       // b[k] = pixel x4 - 3 + k
-        b[0] = (w0 >> 8) & 0xff; b[1] = (w0 >> 16) & 0xff; b[2] = w0 >> 24;
+        const unsigned w0 = w[0], w1 = w[1], w2 = w[2];                   // output k uses bytes 1 + k .. 7 + k of this window
 #pragma unroll
-        for (int k = 0; k < 4; k++) b[3 + k] = (w1 >> (8 * k)) & 0xff;
-        b[7] = w2 & 0xff; b[8] = (w2 >> 8) & 0xff; b[9] = (w2 >> 16) & 0xff;
-        unsigned q[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) q[k] = (unsigned)(18 * (b[k] + b[k + 6]) + 34 * (b[k + 1] + b[k + 5]) + 48 * (b[k + 2] + b[k + 4]) + 56 * b[k + 3]);   // <= 65280
-        *reinterpret_cast<uint2*>(&s_row[r * TL_W + x4]) = make_uint2(q[0] | (q[1] << 16), q[2] | (q[3] << 16));
+        for (int k = 0; k < 4; k++) {
+            const unsigned A = (k < 3) ? __funnelshift_r(w0, w1, 8 * (k + 1)) : w1;
+            const unsigned B = (k < 3) ? __funnelshift_r(w1, w2, 8 * (k + 1)) : w2;
+            const unsigned q = __dp4a(A, T0, __dp4a(B, T1, 0u));          // <= 65280
+            s_half[(r * TL_W + x4 + k) * 2] = (unsigned short)q;
+            if (r > 0) s_half[((r - 1) * TL_W + x4 + k) * 2 + 1] = (unsigned short)q;
+        }
     }
     __syncthreads();
     uint8_t* out = ws.blur + (long long)f * g.blur_stride + L.blur_off;
+    constexpr unsigned C01 = 18u | (34u << 8), C23 = 48u | (56u << 8), C45 = 48u | (34u << 8), C6 = 18u;
     for (int i = tid; i < TL_H * (TL_W / 4); i += 256) {
         const int yy = i >> 4, x4 = (i & 15) * 4;
         if (y0 + yy >= L.h || x0 + x4 >= L.w) continue;
-        int e[7][4];
-#pragma unroll
-        for (int j = 0; j < 7; j++) {
-            const uint2 v2 = *reinterpret_cast<const uint2*>(&s_row[(yy + j) * TL_W + x4]);
-            e[j][0] = v2.x & 0xffffu; e[j][1] = v2.x >> 16; e[j][2] = v2.y & 0xffffu; e[j][3] = v2.y >> 16;
-        }
-        uint32_t o4 = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int sum = 18 * (e[0][k] + e[6][k]) + 34 * (e[1][k] + e[5][k]) + 48 * (e[2][k] + e[4][k]) + 56 * e[3][k];
-            o4 |= (uint32_t)((sum + 32768) >> 16) << (8 * k);
-        }
+        const uint4 p0 = *reinterpret_cast<const uint4*>(&s_pair[yy * TL_W + x4]), p2 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 2) * TL_W + x4]);
+        const uint4 p4 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 4) * TL_W + x4]), p6 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 6) * TL_W + x4]);
+        const unsigned a0 = __dp2a_lo(p0.x, C01, __dp2a_lo(p2.x, C23, __dp2a_lo(p4.x, C45, __dp2a_lo(p6.x, C6, 32768u))));
+        const unsigned a1 = __dp2a_lo(p0.y, C01, __dp2a_lo(p2.y, C23, __dp2a_lo(p4.y, C45, __dp2a_lo(p6.y, C6, 32768u))));
+        const unsigned a2 = __dp2a_lo(p0.z, C01, __dp2a_lo(p2.z, C23, __dp2a_lo(p4.z, C45, __dp2a_lo(p6.z, C6, 32768u))));
+        const unsigned a3 = __dp2a_lo(p0.w, C01, __dp2a_lo(p2.w, C23, __dp2a_lo(p4.w, C45, __dp2a_lo(p6.w, C6, 32768u))));
+        const uint32_t o4 = (a0 >> 16) | ((a1 >> 16) << 8) | ((a2 >> 16) << 16) | ((a3 >> 16) << 24);
         *reinterpret_cast<uint32_t*>(out + (long long)(y0 + yy) * L.bpitch + x0 + x4) = o4;      // bytes past w are padding
     }
 }
