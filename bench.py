@@ -506,14 +506,17 @@ def main():
             "lsd_prep": W * H + 2 * int(0.64 * W * H) + 2 * W * H,
             "lsd_ll_angle": int(0.64 * W * H) * (1 + 4 + 16 + 8 + 8),   # read u8, write angle, packed record, seed cos/sin, norm
             "lsd_seeds": int(0.64 * W * H) * (8 + 8) + 4 * int(0.3 * 0.64 * W * H),   # norm read twice, seed list written
-            "lsd_regions": 17 * int(0.64 * W * H),          # upper bound of the visited-pixel traffic; latency-bound by definition
+            "lsd_regions": 33 * int(0.64 * W * H),          # 16 B record + 4 B flag write + 8 B queue + 8 B norm per visited pixel (upper bound: every pixel visited once); latency-bound by definition
             "lsd_nfa": 4 * int(0.64 * W * H),
             "keylines_lbd": W * H + 8 * W * H + 63 * 4 * 60 * NL,
         }
         dom = max(acc, key=acc.get)
         achieved = alg.get(dom, 0) * B / (acc[dom] * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the same
+        # 513-frame batch (profiles/r01_ncu_k_lsd_regions_513_final.md, profiles/r01_ncu_orb_kernels_final.md); bytes
+        ncu_traffic = {"lsd_regions": 6.93e9, "fast_score": 0.958e9, "fast_cells": 0.488e9, "blur": 1.005e9} if (args.workload == "batch640" and B == 513) else {}
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": which, "stage_ms": acc,
+                    "traffic": ncu_traffic.get(dom), "traffic_unit": "bytes per launch (ncu dram read+write)", "peak_source": which, "stage_ms": acc,
                     "note": ("lsd_regions is the order-dependent LSD region walker (one warp per frame): latency-bound by "
                              "definition, reported against HBM only for completeness" if dom == "lsd_regions" else ""),
                     "stage_gbs": {k: alg.get(k, 0) * B / (acc[k] * 1e-3) / 1e9 for k in acc}}
