@@ -178,6 +178,22 @@ int  sslpl_line_match(sslpl_matcher* m, int mode, const uint8_t* d1, int n1, con
 int  sslpl_match_bow_batch_device(sslpl_matcher* m, const uint8_t* d_desc, const sslpl_keypoint* d_kps, const int* d_n,
                                   int nframes, int cap, const uint8_t* d_centroids, int nc,
                                   float nnratio, int checkOrientation, int32_t* d_match, int32_t* d_nmatch);
+/* ---- ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1331-1473), the
+   matcher of Tracking::TrackWithMotionModel (Tracking.cc:1227), with Frame::AssignFeaturesToGrid / GetFeaturesInArea
+   (Frame.cc:133-148, 368-421) on the device.  SURVEY.md 8(f) row 2.  HOST buffers.
+   Last frame (n1): valid1[i] = mvpMapPoints[i] && !mvbOutlier[i]; obs1[i] = that MapPoint's Observations() > 0; Xw[3i..] =
+   GetWorldPos(); dmp[i][32] = GetDescriptor(); oct1 = mvKeys[i].octave; angle1 = mvKeysUn[i].angle.
+   Current frame (n2): descriptors d2, mvKeysUn x2 / y2 / oct2 / angle2, mvuRight (NULL for monocular), claimed2[j] = the
+   feature already holds a MapPoint with observations (NULL = none).  Tcw / Tlw: 3x4 row-major poses (Tlw only read when
+   !bMono); cam = {fx, fy, cx, cy, mbf, mb}; bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}; scaleFactors[nlevels].
+   Result: assign2[j] = index i of the last-frame MapPoint now held by current feature j, or -1; *nmatches as returned by the
+   reference.  The matcher handle needs max_nodes >= 3072 (grid cells) and at most 8192 features. */
+int  sslpl_search_by_projection_frame(sslpl_matcher* m,
+        int n1, const uint8_t* valid1, const uint8_t* obs1, const float* Xw, const uint8_t* dmp, const int32_t* oct1, const float* angle1,
+        int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* angle2, const float* uright2,
+        const uint8_t* claimed2, const float* Tcw, const float* Tlw, const float* cam, const float* bounds,
+        const float* scaleFactors, int nlevels, float th, int bMono, int checkOrientation, int32_t* assign2, int* nmatches);
+
 /* ---- DBoW2 vocabulary: Frame::ComputeBoW / KeyFrame::ComputeBoW (Frame.cc:474-481, KeyFrame.cc:71-80), i.e.
    TemplatedVocabulary<FORB>::transform(features, BowVector&, FeatureVector&, levelsup = 4)
    (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1259).  SURVEY.md 8(f) row 1. ---- */

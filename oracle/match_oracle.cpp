@@ -172,6 +172,133 @@ extern "C" int orc_search_by_bow(const uint8_t* d1, int n1, const uint8_t* d2, i
     return nmatches;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (Frame.cc:133-148, 462-472, 368-421)
+ * and ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1331-1473).
+ * Pointer state is passed as flags: valid1 = (pMP && !mvbOutlier), obs1 = pMP->Observations() > 0, claimed2 = the current
+ * frame's feature already holds a MapPoint with Observations() > 0.  assign2[j] = index (into the last frame) of the
+ * MapPoint written to CurrentFrame.mvpMapPoints[j], or -1.  Float arithmetic: every expression in float, no contraction;
+ * Rcw*x3Dw+tcw as cv::gemm evaluates it for CV_32F (double accumulation, one rounding per element).
+ * --------------------------------------------------------------------------------------------- */
+namespace {
+struct Grid {
+    static const int COLS = 64, ROWS = 48;                         /* Frame.h:45-46 */
+    float minX, minY, invW, invH;
+    std::vector<int> cell[COLS][ROWS];
+    void build(int n, const float* x, const float* y) {            /* AssignFeaturesToGrid + PosInGrid */
+        for (int i = 0; i < n; i++) {
+            const int px = (int)std::round((x[i] - minX) * invW), py = (int)std::round((y[i] - minY) * invH);
+            if (px < 0 || px >= COLS || py < 0 || py >= ROWS) continue;
+            cell[px][py].push_back(i);
+        }
+    }
+    void area(float x, float y, float r, int minLevel, int maxLevel, const float* kx, const float* ky, const int32_t* oct,
+              std::vector<int>& out) const {                       /* GetFeaturesInArea */
+        out.clear();
+        const int nMinCellX = std::max(0, (int)std::floor((x - minX - r) * invW));
+        if (nMinCellX >= COLS) return;
+        const int nMaxCellX = std::min(COLS - 1, (int)std::ceil((x - minX + r) * invW));
+        if (nMaxCellX < 0) return;
+        const int nMinCellY = std::max(0, (int)std::floor((y - minY - r) * invH));
+        if (nMinCellY >= ROWS) return;
+        const int nMaxCellY = std::min(ROWS - 1, (int)std::ceil((y - minY + r) * invH));
+        if (nMaxCellY < 0) return;
+        const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+            for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+                for (int j : cell[ix][iy]) {
+                    if (bCheckLevels) {
+                        if (oct[j] < minLevel) continue;
+                        if (maxLevel >= 0 && oct[j] > maxLevel) continue;
+                    }
+                    const float distx = kx[j] - x, disty = ky[j] - y;
+                    if (std::fabs(distx) < r && std::fabs(disty) < r) out.push_back(j);
+                }
+    }
+};
+}  // namespace
+
+extern "C" int orc_features_in_area(int n, const float* kx, const float* ky, const int32_t* oct, float minX, float minY, float invW, float invH,
+                                    float x, float y, float r, int minLevel, int maxLevel, int32_t* out, int cap) {
+    Grid* g = new Grid(); g->minX = minX; g->minY = minY; g->invW = invW; g->invH = invH;
+    g->build(n, kx, ky);
+    std::vector<int> v; g->area(x, y, r, minLevel, maxLevel, kx, ky, oct, v);
+    delete g;
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = v[i];
+    return (int)v.size();
+}
+
+extern "C" int orc_search_by_projection_frame(
+        int n1, const uint8_t* valid1, const uint8_t* obs1, const float* Xw, const uint8_t* dmp, const int32_t* oct1, const float* angle1,
+        int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* angle2, const float* uright2,
+        const uint8_t* claimed2, const float* Tcw, const float* Tlw, const float* cam /* fx fy cx cy mbf mb */,
+        const float* bounds /* minX maxX minY maxY */, const float* scaleFactors, float th, int bMono, int checkOri, int32_t* assign2) {
+    const int TH_HIGH = 100;                                                             /* ORBmatcher.cc:37 */
+    const float fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3], mbf = cam[4], mb = cam[5];
+    Grid* g = new Grid();
+    g->minX = bounds[0]; g->minY = bounds[2];
+    g->invW = (float)Grid::COLS / (bounds[1] - bounds[0]); g->invH = (float)Grid::ROWS / (bounds[3] - bounds[2]);   /* Frame.cc:115-116 */
+    g->build(n2, x2, y2);
+    std::vector<uint8_t> claimed(n2, 0);
+    for (int j = 0; j < n2; j++) { assign2[j] = -1; if (claimed2) claimed[j] = claimed2[j]; }
+    /* tlc = Rlw * (-Rcw^T tcw) + tlw, only its z against mb (stereo) */
+    bool bForward = false, bBackward = false;
+    if (!bMono && Tlw) {
+        double twc[3];
+        for (int r = 0; r < 3; r++) twc[r] = -((double)Tcw[0 * 4 + r] * Tcw[3] + (double)Tcw[1 * 4 + r] * Tcw[7] + (double)Tcw[2 * 4 + r] * Tcw[11]);
+        const float twcf[3] = {(float)twc[0], (float)twc[1], (float)twc[2]};
+        const float tlcz = (float)((double)Tlw[8] * twcf[0] + (double)Tlw[9] * twcf[1] + (double)Tlw[10] * twcf[2] + (double)Tlw[11]);
+        bForward = tlcz > mb; bBackward = -tlcz > mb;
+    }
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int> cand;
+    for (int i = 0; i < n1; i++) {
+        if (!valid1[i]) continue;
+        const float* X = Xw + 3 * (size_t)i;
+        float xc3[3];
+        for (int r = 0; r < 3; r++)
+            xc3[r] = (float)((double)Tcw[4 * r] * X[0] + (double)Tcw[4 * r + 1] * X[1] + (double)Tcw[4 * r + 2] * X[2] + (double)Tcw[4 * r + 3]);
+        const float xc = xc3[0], yc = xc3[1];
+        const float invzc = (float)(1.0 / xc3[2]);
+        if (invzc < 0) continue;
+        const float u = fx * xc * invzc + cx, v = fy * yc * invzc + cy;
+        if (u < bounds[0] || u > bounds[1]) continue;
+        if (v < bounds[2] || v > bounds[3]) continue;
+        const int nLastOctave = oct1[i];
+        const float radius = th * scaleFactors[nLastOctave];
+        if (bForward) g->area(u, v, radius, nLastOctave, -1, x2, y2, oct2, cand);
+        else if (bBackward) g->area(u, v, radius, 0, nLastOctave, x2, y2, oct2, cand);
+        else g->area(u, v, radius, nLastOctave - 1, nLastOctave + 1, x2, y2, oct2, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : cand) {
+            if (claimed[i2]) continue;                                                   /* :1400-1402 */
+            if (uright2 && uright2[i2] > 0) {
+                const float ur = u - mbf * invzc, er = std::fabs(ur - uright2[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = orc_descriptor_distance(dmp + 32 * (size_t)i, d2 + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            assign2[bestIdx2] = i; claimed[bestIdx2] = obs1[i] ? 1 : 0;
+            nmatches++;
+            if (checkOri) rotHist[rot_bin(angle1[i], angle2[bestIdx2])].push_back(bestIdx2);
+        }
+    }
+    delete g;
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { assign2[j] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 /* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) — ORBmatcher.cc:525-658 */
 extern "C" int orc_search_by_bow_kf(const uint8_t* d1, int n1, const uint8_t* d2, int n2,
                                     const int32_t* nodes1, const int32_t* off1, const int32_t* idx1, int nn1,

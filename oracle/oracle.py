@@ -198,6 +198,44 @@ def vocab_transform(L, parent, ndesc, weight, is_leaf, feats, levelsup=4):
     return word[:n], node[:n], w[:n]
 
 
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def search_by_projection_frame(last, cur, Tcw, Tlw, cam, bounds, scale_factors, th, mono=True, check_ori=True):
+    """ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (ORBmatcher.cc:1331-1473).
+    last = dict(valid, obs, Xw[n,3], dmp[n,32], oct, angle); cur = dict(desc[n,32], x, y, oct, angle, uright|None, claimed|None).
+    Returns (nmatches, assign2)."""
+    n1, n2 = len(last["valid"]), len(cur["x"])
+    v1 = np.ascontiguousarray(last["valid"], np.uint8); o1 = np.ascontiguousarray(last["obs"], np.uint8)
+    Xw = _f32(last["Xw"]).reshape(-1, 3); dmp = np.ascontiguousarray(last["dmp"], np.uint8).reshape(-1, 32)
+    oc1 = np.ascontiguousarray(last["oct"], np.int32); a1 = _f32(last["angle"])
+    d2 = np.ascontiguousarray(cur["desc"], np.uint8).reshape(-1, 32); x2 = _f32(cur["x"]); y2 = _f32(cur["y"])
+    oc2 = np.ascontiguousarray(cur["oct"], np.int32); a2 = _f32(cur["angle"])
+    ur = _f32(cur["uright"]) if cur.get("uright") is not None else None
+    cl = np.ascontiguousarray(cur["claimed"], np.uint8) if cur.get("claimed") is not None else None
+    Tc = _f32(Tcw).reshape(-1)[:12].copy(); Tl = _f32(Tlw).reshape(-1)[:12].copy() if Tlw is not None else None
+    camv = _f32(cam); bnd = _f32(bounds); sf = _f32(scale_factors)
+    out = np.full(max(n2, 1), -1, np.int32)
+    lib().orc_search_by_projection_frame.restype = C.c_int
+    n = lib().orc_search_by_projection_frame(n1, _p(v1), _p(o1), _p(Xw), _p(dmp), _p(oc1), _p(a1),
+                                             n2, _p(d2), _p(x2), _p(y2), _p(oc2), _p(a2), _p(ur) if ur is not None else None,
+                                             _p(cl) if cl is not None else None, _p(Tc), _p(Tl) if Tl is not None else None,
+                                             _p(camv), _p(bnd), _p(sf), C.c_float(th), int(mono), int(check_ori), _p(out))
+    return n, out[:n2]
+
+
+def features_in_area(kx, ky, oct, bounds, x, y, r, min_level=-1, max_level=-1):
+    """Frame::GetFeaturesInArea (Frame.cc:368-421) over a freshly built grid (AssignFeaturesToGrid, :133-148)."""
+    kx = _f32(kx); ky = _f32(ky); oct = np.ascontiguousarray(oct, np.int32)
+    invw = np.float32(64) / (np.float32(bounds[1]) - np.float32(bounds[0])); invh = np.float32(48) / (np.float32(bounds[3]) - np.float32(bounds[2]))
+    out = np.empty(max(len(kx), 1), np.int32)
+    lib().orc_features_in_area.restype = C.c_int
+    n = lib().orc_features_in_area(len(kx), _p(kx), _p(ky), _p(oct), C.c_float(bounds[0]), C.c_float(bounds[2]), C.c_float(invw), C.c_float(invh),
+                                   C.c_float(x), C.c_float(y), C.c_float(r), int(min_level), int(max_level), _p(out), len(out))
+    return out[:n]
+
+
 def feature_vector_csr(node):
     """DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>, FeatureVector.cpp:31-45) flattened to CSR:
     node ids ascending, feature indices ascending inside a node."""

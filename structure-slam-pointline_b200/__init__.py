@@ -339,6 +339,29 @@ class Matcher:
         _check(lib().sslpl_bow_transform(self._h, vocab._h, _p(desc), n, int(levelsup), _p(word), _p(node), _p(w)))
         return word[:n], node[:n], w[:n]
 
+    def search_by_projection_frame(self, last, cur, Tcw, Tlw, cam, bounds, scale_factors, th, mono=True, check_ori=True):
+        """ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1331-1473).
+        last = dict(valid, obs, Xw[n,3], dmp[n,32], oct, angle); cur = dict(desc[n,32], x, y, oct, angle, uright|None, claimed|None);
+        Tcw / Tlw 3x4 (or 4x4) row-major; cam = (fx, fy, cx, cy, mbf, mb); bounds = (minX, maxX, minY, maxY).
+        Returns (nmatches, assign2) with assign2[j] = index of the last-frame MapPoint given to current feature j or -1."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        n1, n2 = len(last["valid"]), len(cur["x"])
+        v1 = np.ascontiguousarray(last["valid"], np.uint8); o1 = np.ascontiguousarray(last["obs"], np.uint8)
+        Xw = f32(last["Xw"]).reshape(-1, 3); dmp = np.ascontiguousarray(last["dmp"], np.uint8).reshape(-1, 32)
+        oc1 = np.ascontiguousarray(last["oct"], np.int32); a1 = f32(last["angle"])
+        d2 = np.ascontiguousarray(cur["desc"], np.uint8).reshape(-1, 32); x2 = f32(cur["x"]); y2 = f32(cur["y"])
+        oc2 = np.ascontiguousarray(cur["oct"], np.int32); a2 = f32(cur["angle"])
+        ur = f32(cur["uright"]) if cur.get("uright") is not None else None
+        cl = np.ascontiguousarray(cur["claimed"], np.uint8) if cur.get("claimed") is not None else None
+        Tc = f32(Tcw).reshape(-1)[:12].copy(); Tl = f32(Tlw).reshape(-1)[:12].copy() if Tlw is not None else None
+        camv = f32(cam); bnd = f32(bounds); sf = f32(scale_factors)
+        out = np.full(max(n2, 1), -1, np.int32); nm = C.c_int()
+        _check(lib().sslpl_search_by_projection_frame(self._h, n1, _p(v1), _p(o1), _p(Xw), _p(dmp), _p(oc1), _p(a1),
+                                                      n2, _p(d2), _p(x2), _p(y2), _p(oc2), _p(a2), _p(ur), _p(cl), _p(Tc), _p(Tl),
+                                                      _p(camv), _p(bnd), _p(sf), len(sf), C.c_float(th), int(mono), int(check_ori),
+                                                      _p(out), C.byref(nm)))
+        return nm.value, out[:n2]
+
     def match_lines_batch_device(self, d_ldesc, d_nl, nframes, capl, d_lmatch, d_nlmatch):
         _check(lib().sslpl_match_lines_batch_device(self._h, C.c_void_p(d_ldesc), C.c_void_p(d_nl), nframes, capl,
                                                     C.c_void_p(d_lmatch), C.c_void_p(d_nlmatch)))

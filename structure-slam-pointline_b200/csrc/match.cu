@@ -307,6 +307,140 @@ __global__ void __launch_bounds__(128) k_tri_match(FrameSet S, TriArgs T, int32_
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Frame::AssignFeaturesToGrid (Frame.cc:133-148, PosInGrid :462-472) as a CSR over the 64 x 48 cells
+// (cell id = ix * 48 + iy: the traversal order of GetFeaturesInArea, Frame.cc:368-421) and
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1331-1473).
+// The matcher is a greedy scan over the last frame's MapPoints in index order (a feature of the current frame that has
+// received a MapPoint with observations is skipped by later points), so ONE WARP walks a frame pair sequentially; the lanes
+// share the grid cells of each search window.  First-wins ties are kept by reducing (distance, traversal position) keys.
+// -------------------------------------------------------------------------------------------------
+constexpr int GRID_COLS = 64, GRID_ROWS = 48;        // Frame.h:45-46
+constexpr int TH_HIGH = 100;                         // ORBmatcher.cc:37
+
+struct ProjArgs {
+    float T[12];                                     // Tcw, 3x4 row-major
+    float fx, fy, cx, cy, mbf;
+    float minX, maxX, minY, maxY, invW, invH;
+    float th;
+    int forward, backward, checkOri, use_right;
+    float scale[32];                                 // mvScaleFactors
+};
+
+__global__ void __launch_bounds__(128) k_grid_cells(const float* x, const float* y, int n, float minX, float minY, float invW, float invH, int32_t* cell) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(x[i], minX), invW)), py = (int)roundf(__fmul_rn(__fsub_rn(y[i], minY), invH));
+    cell[i] = (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? -1 : px * GRID_ROWS + py;
+}
+
+__global__ void __launch_bounds__(32) k_proj_match(const __grid_constant__ ProjArgs A, int n1, const uint8_t* flag1 /* bit0 valid, bit1 obs>0 */,
+                                                    const float* Xw, const uint8_t* dmp, const int* oct1, const float* angle1,
+                                                    int n2, const uint8_t* d2, const float* x2, const float* y2, const int* oct2, const float* angle2,
+                                                    const float* uright2, uint8_t* claimed, const int* goff, const int* gidx,
+                                                    int32_t* assign2, int32_t* sel, uint8_t* rbin, int32_t* nmatch) {
+    __shared__ int s_hist[HISTO_LENGTH];
+    __shared__ int s_keep[3];
+    const int lane = threadIdx.x;
+    for (int j = lane; j < n2; j += 32) assign2[j] = -1;
+    if (lane < HISTO_LENGTH) s_hist[lane] = 0;
+    __syncwarp();
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) {
+        if (lane == 0) sel[i] = -1;
+        const int fl = flag1[i];
+        if (!(fl & 1)) continue;
+        const float X0 = Xw[3 * i], X1 = Xw[3 * i + 1], X2 = Xw[3 * i + 2];
+        // cv::gemm on CV_32F: double accumulation, one rounding per element (Rcw * x3Dw + tcw)
+        const float xc = (float)((double)A.T[0] * X0 + (double)A.T[1] * X1 + (double)A.T[2] * X2 + (double)A.T[3]);
+        const float yc = (float)((double)A.T[4] * X0 + (double)A.T[5] * X1 + (double)A.T[6] * X2 + (double)A.T[7]);
+        const float zc = (float)((double)A.T[8] * X0 + (double)A.T[9] * X1 + (double)A.T[10] * X2 + (double)A.T[11]);
+        const float invzc = (float)(1.0 / (double)zc);
+        if (invzc < 0) continue;
+        const float u = __fadd_rn(__fmul_rn(__fmul_rn(A.fx, xc), invzc), A.cx), v = __fadd_rn(__fmul_rn(__fmul_rn(A.fy, yc), invzc), A.cy);
+        if (u < A.minX || u > A.maxX || v < A.minY || v > A.maxY) continue;
+        const int lo = oct1[i];
+        const float r = __fmul_rn(A.th, A.scale[lo]);
+        const int minLevel = A.forward ? lo : (A.backward ? 0 : lo - 1), maxLevel = A.forward ? -1 : (A.backward ? lo : lo + 1);
+        // GetFeaturesInArea (Frame.cc:368-421)
+        const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, A.minX), r), A.invW)));
+        if (cx0 >= GRID_COLS) continue;
+        const int cx1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, A.minX), r), A.invW)));
+        if (cx1 < 0) continue;
+        const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, A.minY), r), A.invH)));
+        if (cy0 >= GRID_ROWS) continue;
+        const int cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, A.minY), r), A.invH)));
+        if (cy1 < 0) continue;
+        const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+        const int ny = cy1 - cy0 + 1, ncell = (cx1 - cx0 + 1) * ny;
+        uint4 a0, a1;
+        load_desc(dmp + (long long)i * 32, a0, a1);
+        const float ur = __fsub_rn(u, __fmul_rn(A.mbf, invzc));
+        unsigned long long best = ~0ull;                         // (dist << 40) | (cell rank << 20) | position in the cell
+        for (int c = lane; c < ncell; c += 32) {
+            const int ix = cx0 + c / ny, iy = cy0 + c % ny, cell = ix * GRID_ROWS + iy;
+            const int b = goff[cell], e = goff[cell + 1];
+            for (int q = b; q < e; q++) {
+                const int j = gidx[q];
+                if (checkLevels) {
+                    const int o = oct2[j];
+                    if (o < minLevel) continue;
+                    if (maxLevel >= 0 && o > maxLevel) continue;
+                }
+                if (!(fabsf(__fsub_rn(x2[j], u)) < r && fabsf(__fsub_rn(y2[j], v)) < r)) continue;
+                if (claimed[j]) continue;                        // :1400-1402
+                if (A.use_right && uright2[j] > 0) { if (fabsf(__fsub_rn(ur, uright2[j])) > r) continue; }
+                uint4 b0, b1;
+                load_desc(d2 + (long long)j * 32, b0, b1);
+                const unsigned long long key = ((unsigned long long)popc256(a0, a1, b0, b1) << 40) | ((unsigned long long)c << 20) | (unsigned)(q - b);
+                if (key < best) best = key;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t < best ? t : best; }
+        const int bestDist = best == ~0ull ? 256 : (int)(best >> 40);
+        if (bestDist <= TH_HIGH) {
+            const int c = (int)((best >> 20) & 0xfffff), pos = (int)(best & 0xfffff);
+            const int cell = (cx0 + c / ny) * GRID_ROWS + cy0 + c % ny;
+            const int j = gidx[goff[cell] + pos];
+            if (lane == 0) {
+                assign2[j] = i; claimed[j] = (fl >> 1) & 1;
+                sel[i] = j;
+                const int bin = rot_bin(angle1[i], angle2[j]);
+                rbin[i] = (uint8_t)bin;
+                if (A.checkOri) s_hist[bin]++;
+            }
+            nmatches++;
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    if (A.checkOri) {
+        if (lane == 0) {                                         // ComputeThreeMaxima, ORBmatcher.cc:1604-1645
+            int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                const int sv = s_hist[i];
+                if (sv > max1) { max3 = max2; max2 = max1; max1 = sv; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (sv > max2) { max3 = max2; max2 = sv; ind3 = ind2; ind2 = i; }
+                else if (sv > max3) { max3 = sv; ind3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+            s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+        }
+        __syncwarp();
+        const int k0 = s_keep[0], k1 = s_keep[1], k2 = s_keep[2];
+        for (int i0 = 0; i0 < n1; i0 += 32) {
+            const int i = i0 + lane;
+            bool drop = false;
+            if (i < n1 && sel[i] >= 0) { const int b = rbin[i]; drop = (b != k0 && b != k1 && b != k2); }
+            if (drop) assign2[sel[i]] = -1;
+            nmatches -= __popc(__ballot_sync(0xffffffffu, drop));
+        }
+    }
+    if (lane == 0) *nmatch = nmatches;
+}
+
 // Rotation-histogram filter (ComputeThreeMaxima, ORBmatcher.cc:1604-1645; application :270-288) and match
 // count, one CTA per pair.  compact != 0 additionally writes the (i, out[i]) pairs in ascending i (:818-823).
 __global__ void __launch_bounds__(256) k_rot_filter(int32_t* out, long long out_fs, const uint8_t* rot, long long rot_fs,
@@ -763,6 +897,77 @@ int sslpl_match_bow_batch_device(sslpl_matcher* m, const uint8_t* d_desc, const 
     m->launches += 1;
     return bow_batch_tail(m, d_desc, d_kps, d_n, nframes, cap, nc, nnratio, checkOri, d_match, d_nmatch);
 }
+
+// ---------------- projection-gated matcher ----------------
+int sslpl_search_by_projection_frame(sslpl_matcher* m,
+        int n1, const uint8_t* valid1, const uint8_t* obs1, const float* Xw, const uint8_t* dmp, const int32_t* oct1, const float* angle1,
+        int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* angle2, const float* uright2,
+        const uint8_t* claimed2, const float* Tcw, const float* Tlw, const float* cam, const float* bounds,
+        const float* scaleFactors, int nlevels, float th, int bMono, int checkOri, int32_t* assign2, int* nmatches) {
+    SSLPL_REQUIRE(m && assign2 && nmatches && Tcw && cam && bounds && scaleFactors, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(n1 >= 0 && n2 >= 0 && n1 <= m->cap && n2 <= m->cap && m->cap <= 8192 + 64, SSLPL_ERR_ARG, "n1 / n2 exceed the matcher capacity (<= 8192 features)");
+    SSLPL_REQUIRE(m->p.max_nodes >= GRID_COLS * GRID_ROWS, SSLPL_ERR_ARG, "the matcher needs max_nodes >= 3072 (64 x 48 grid cells)");
+    SSLPL_REQUIRE(nlevels >= 1 && nlevels <= 32, SSLPL_ERR_ARG, "nlevels out of range");
+    SSLPL_REQUIRE(n1 == 0 || (valid1 && obs1 && Xw && dmp && oct1 && angle1), SSLPL_ERR_ARG, "null last-frame array");
+    SSLPL_REQUIRE(n2 == 0 || (d2 && x2 && y2 && oct2 && angle2), SSLPL_ERR_ARG, "null current-frame array");
+    SSLPL_REQUIRE(bMono || Tlw, SSLPL_ERR_ARG, "the stereo direction test needs the last frame's pose");
+    for (int j = 0; j < n2; j++) assign2[j] = -1;
+    *nmatches = 0;
+    if (n1 == 0 || n2 == 0) return SSLPL_OK;
+    for (int i = 0; i < n1; i++) SSLPL_REQUIRE(oct1[i] >= 0 && oct1[i] < nlevels, SSLPL_ERR_ARG, "last-frame octave outside the scale-factor table");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    const int cap = m->cap, NN = m->p.max_nodes + 1, nc = GRID_COLS * GRID_ROWS;
+    ProjArgs A; memset(&A, 0, sizeof(A));
+    for (int k = 0; k < 12; k++) A.T[k] = Tcw[k];
+    A.fx = cam[0]; A.fy = cam[1]; A.cx = cam[2]; A.cy = cam[3]; A.mbf = cam[4];
+    A.minX = bounds[0]; A.maxX = bounds[1]; A.minY = bounds[2]; A.maxY = bounds[3];
+    A.invW = (float)GRID_COLS / (bounds[1] - bounds[0]); A.invH = (float)GRID_ROWS / (bounds[3] - bounds[2]);   // Frame.cc:115-116
+    A.th = th; A.checkOri = checkOri ? 1 : 0; A.use_right = uright2 ? 1 : 0;
+    for (int k = 0; k < nlevels; k++) A.scale[k] = scaleFactors[k];
+    if (!bMono) {                                                        // tlc = Rlw * (-Rcw^T tcw) + tlw against the baseline (:1352-1353)
+        float twc[3];
+        for (int r = 0; r < 3; r++) twc[r] = (float)(-((double)Tcw[r] * Tcw[3] + (double)Tcw[4 + r] * Tcw[7] + (double)Tcw[8 + r] * Tcw[11]));
+        const float tlcz = (float)((double)Tlw[8] * twc[0] + (double)Tlw[9] * twc[1] + (double)Tlw[10] * twc[2] + (double)Tlw[11]);
+        A.forward = tlcz > cam[5]; A.backward = -tlcz > cam[5];
+    }
+    // staging (pinned scratch would avoid the pageable copies; this entry point is per frame pair, not the batched path)
+    std::vector<uint8_t> fl(n1);
+    for (int i = 0; i < n1; i++) fl[i] = (uint8_t)((valid1[i] ? 1 : 0) | (obs1[i] ? 2 : 0));
+    float* k0 = m->kpf; float* k1 = m->kpf + (size_t)cap * 7;
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc, dmp, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc + (size_t)cap * 32, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k0, Xw, sizeof(float) * 3 * n1, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k0 + 3 * (size_t)cap, angle1, sizeof(float) * n1, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k0 + 4 * (size_t)cap, oct1, sizeof(int) * n1, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k1, x2, sizeof(float) * n2, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k1 + (size_t)cap, y2, sizeof(float) * n2, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k1 + 2 * (size_t)cap, angle2, sizeof(float) * n2, cudaMemcpyHostToDevice, st));
+    if (uright2) SSLPL_CUDA(cudaMemcpyAsync(k1 + 3 * (size_t)cap, uright2, sizeof(float) * n2, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k1 + 4 * (size_t)cap, oct2, sizeof(int) * n2, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->flag, fl.data(), n1, cudaMemcpyHostToDevice, st));
+    if (claimed2) SSLPL_CUDA(cudaMemcpyAsync(m->flag + cap, claimed2, n2, cudaMemcpyHostToDevice, st));
+    else SSLPL_CUDA(cudaMemsetAsync(m->flag + cap, 0, n2, st));
+    m->h_small[0] = n2;
+    SSLPL_CUDA(cudaMemcpyAsync(m->ncnt, m->h_small, sizeof(int), cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));                               // fl (pageable) and h_small are reused by the caller / next call
+    int* goff = m->off + (NN + 1); int* gidx = m->idx + cap;
+    k_grid_cells<<<(n2 + 127) / 128, 128, 0, st>>>(k1, k1 + cap, n2, A.minX, A.minY, A.invW, A.invH, m->node);
+    k_build_csr<<<1, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->node, 0, m->ncnt, cap, nc, goff, 0, gidx, 0);
+    k_proj_match<<<1, 32, 0, st>>>(A, n1, m->flag, k0, m->desc, reinterpret_cast<const int*>(k0 + 4 * (size_t)cap), k0 + 3 * (size_t)cap,
+                                   n2, m->desc + (size_t)cap * 32, k1, k1 + cap, reinterpret_cast<const int*>(k1 + 4 * (size_t)cap), k1 + 2 * (size_t)cap,
+                                   k1 + 3 * (size_t)cap, m->flag + cap, goff, gidx, m->out, m->pairs, m->rot, m->nmatch);
+    m->launches += 3;
+    SSLPL_CUDA(cudaGetLastError());
+    SSLPL_CUDA(cudaMemcpyAsync(assign2, m->out, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->h_small, m->nmatch, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    *nmatches = m->h_small[0];
+    return SSLPL_OK;
+}
+
+// Frame::GetFeaturesInArea on its own (Frame.cc:368-421) is host logic over the same CSR; the matcher above is its only
+// device consumer.  (The per-frame grid build is k_grid_cells + k_build_csr.)
 
 // ---------------- DBoW2 vocabulary ----------------
 static int vocab_level_nodes(const sslpl_vocab* v, int levelsup) {

@@ -51,3 +51,26 @@ def test_bow_and_feature_vector_assembly(pkg):
     ids, vals = V.bow_vector(word, np.where(weight > 0, 1.0, 0.0))
     assert ids.tolist() == [2, 5, 7] and np.allclose(vals, 1 / 3)
     V._h = None
+
+
+def test_features_in_area_equals_brute_force(oracle):
+    """Frame::GetFeaturesInArea (Frame.cc:368-421) over AssignFeaturesToGrid (:133-148): the cell walk returns exactly the
+    in-grid features inside the window (and level range), ordered by (cell x, cell y, feature index)."""
+    rng = np.random.default_rng(4)
+    n = 1500
+    kx = rng.uniform(-5, 645, n).astype(np.float32); ky = rng.uniform(-5, 485, n).astype(np.float32); oc = rng.integers(0, 8, n).astype(np.int32)
+    bounds = (0.0, 640.0, 0.0, 480.0)
+    invw = np.float32(64) / np.float32(640); invh = np.float32(48) / np.float32(480)
+    px = np.round((kx - np.float32(0)) * invw).astype(int); py = np.round((ky - np.float32(0)) * invh).astype(int)   # PosInGrid (:462-472); ties .5 do not occur
+    ingrid = (px >= 0) & (px < 64) & (py >= 0) & (py < 48)
+    for (x, y, r, lo, hi) in [(320, 240, 40, -1, -1), (5, 5, 30, -1, -1), (630, 470, 25, 2, 4), (100, 400, 60, 3, -1), (700, 100, 20, -1, -1),
+                              (320, 240, 15, 0, 2), (-50, -50, 10, -1, -1)]:
+        got = oracle.features_in_area(kx, ky, oc, bounds, x, y, r, lo, hi)
+        m = ingrid & (np.abs(kx - np.float32(x)) < r) & (np.abs(ky - np.float32(y)) < r)
+        if lo > 0 or hi >= 0:
+            m &= oc >= lo
+            if hi >= 0:
+                m &= oc <= hi
+        idx = np.nonzero(m)[0]
+        exp = idx[np.lexsort((idx, py[idx], px[idx]))]
+        assert np.array_equal(got, exp), (x, y, r, lo, hi)
