@@ -48,6 +48,47 @@ int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)          
     return d;
 }
 
+// ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) — ORBmatcher.cc:1331-1473, the matcher of
+// Tracking::TrackWithMotionModel (Tracking.cc:1227, :1243).  Both call sites fill CurrentFrame.mvpMapPoints with NULL first;
+// this adapter relies on that (a feature that is not assigned ends up NULL, as in the reference after such a fill).
+int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
+{
+    const int n1 = LastFrame.N, n2 = CurrentFrame.N;
+    if(n1 == 0 || n2 == 0) return 0;
+    std::vector<uint8_t> valid1(n1, 0), obs1(n1, 0), dmp((size_t)n1*32, 0), claimed2(n2, 0), d2((size_t)n2*32);
+    std::vector<float> Xw((size_t)3*n1, 0.f), a1(n1), x2(n2), y2(n2), a2(n2), ur2(n2);
+    std::vector<int32_t> o1(n1), o2(n2), assign(n2);
+    for(int i=0; i<n1; i++) {
+        a1[i] = LastFrame.mvKeysUn[i].angle; o1[i] = LastFrame.mvKeys[i].octave;
+        MapPoint* p = LastFrame.mvpMapPoints[i];
+        if(p && !LastFrame.mvbOutlier[i]) {
+            valid1[i] = 1; obs1[i] = p->Observations() > 0 ? 1 : 0;
+            const cv::Mat X = p->GetWorldPos();
+            for(int k=0; k<3; k++) Xw[3*i+k] = X.at<float>(k);
+            const cv::Mat d = p->GetDescriptor();
+            std::copy(d.ptr<uchar>(), d.ptr<uchar>() + 32, &dmp[(size_t)32*i]);
+        }
+    }
+    for(int j=0; j<n2; j++) {
+        const cv::KeyPoint &kp = CurrentFrame.mvKeysUn[j];
+        x2[j] = kp.pt.x; y2[j] = kp.pt.y; a2[j] = kp.angle; o2[j] = kp.octave; ur2[j] = CurrentFrame.mvuRight[j];
+        MapPoint* q = CurrentFrame.mvpMapPoints[j];
+        claimed2[j] = (q && q->Observations() > 0) ? 1 : 0;
+        std::copy(CurrentFrame.mDescriptors.ptr<uchar>(j), CurrentFrame.mDescriptors.ptr<uchar>(j) + 32, &d2[(size_t)32*j]);
+    }
+    float Tcw[12], Tlw[12];
+    for(int r=0; r<3; r++) for(int c=0; c<4; c++) { Tcw[4*r+c] = CurrentFrame.mTcw.at<float>(r,c); Tlw[4*r+c] = LastFrame.mTcw.at<float>(r,c); }
+    const float cam[6] = {CurrentFrame.fx, CurrentFrame.fy, CurrentFrame.cx, CurrentFrame.cy, CurrentFrame.mbf, CurrentFrame.mb};
+    const float bounds[4] = {CurrentFrame.mnMinX, CurrentFrame.mnMaxX, CurrentFrame.mnMinY, CurrentFrame.mnMaxY};
+    int nmatches = 0;
+    Check(sslpl_search_by_projection_frame(Ctx(), n1, &valid1[0], &obs1[0], &Xw[0], &dmp[0], &o1[0], &a1[0],
+                                           n2, &d2[0], &x2[0], &y2[0], &o2[0], &a2[0], &ur2[0], &claimed2[0], Tcw, Tlw, cam, bounds,
+                                           &CurrentFrame.mvScaleFactors[0], (int)CurrentFrame.mvScaleFactors.size(), th, bMono ? 1 : 0,
+                                           mbCheckOrientation ? 1 : 0, &assign[0], &nmatches), "sslpl_search_by_projection_frame");
+    for(int j=0; j<n2; j++) if(assign[j] >= 0) CurrentFrame.mvpMapPoints[j] = LastFrame.mvpMapPoints[assign[j]];
+    return nmatches;
+}
+
 int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F, vector<MapPoint*> &vpMapPointMatches)   // ORBmatcher.cc:159
 {
     const vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
