@@ -98,6 +98,17 @@ def test_line_batch_equals_single(pkg, oracle, synth):
         assert np.max(np.abs(kl[f, :n[f]]["startPointX"] - okl["startPointX"]), initial=0) <= 1e-4
 
 
+def test_max_walkers_knob_does_not_change_results(pkg, synth):
+    """sslpl_line_set_max_walkers only bounds how many region-walker CTAs are resident (persistent grid pulling frames)."""
+    frames = synth.batch(640, 480, 6)
+    ls = pkg.LineSegment(40, max_width=640, max_height=480, max_batch=6)
+    ref = ls.extract_batch(frames)
+    for cap in (1, 4, 0):
+        ls.set_max_walkers(cap)
+        got = ls.extract_batch(frames)
+        assert np.array_equal(got[3], ref[3]) and np.array_equal(got[1], ref[1]) and got[0].tobytes() == ref[0].tobytes(), cap
+
+
 def test_line_match_two_frames(pkg, oracle, synth):
     """config 3, line half: LSDmatcher::SearchByProjection(KF,F) (LSDmatcher.cpp:143) on LBD descriptors of two frames."""
     ls = pkg.LineSegment(40, max_width=640, max_height=480)
