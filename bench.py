@@ -232,9 +232,9 @@ def main():
     ev_free = [torch.cuda.Event() for _ in range(R)]    # slot r's tables have been consumed (gathered) on s_pts
 
     # One NCCL all-gather per step (north_star: "a single NCCL all-gather of match tables"): the point table of this step and
-    # the line table of the ring slot that has just completed travel together in one [Bf, cap + NL] buffer.
-    d_comb = torch.zeros((Bf, cap + NL), dtype=torch.int32, device=dev) if world > 1 else None
-    d_gcomb = torch.empty((world * Bf, cap + NL), dtype=torch.int32, device=dev) if world > 1 else None
+    # the line table of the ring slot that has just completed travel together in one [Bf, cap + NL] buffer (batch.PackedGather).
+    from sslpl_b200 import batch as sbatch
+    pgather = sbatch.PackedGather(Bf, cap, NL, world, dev) if world > 1 else None
 
     def finalize_slot(r, defer=False):
         """Join slot r's line results into the points stream; gather them across ranks (now, or with this step's point table)."""
@@ -243,7 +243,7 @@ def main():
         s_pts.wait_stream(s_lin[r])
         if gather[0]:
             if defer:
-                d_comb[:, cap:].copy_(d_lmatch[r], non_blocking=True)
+                pgather.stage_lines(d_lmatch[r])
             else:
                 dist.all_gather_into_tensor(d_lgather, d_lmatch[r])
         if world > 1:
@@ -262,8 +262,7 @@ def main():
         kps, desc, n, c = ext.device_results()
         mt.match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match.data_ptr(), d_nmatch.data_ptr())
         if gather[0]:
-            d_comb[:, :cap].copy_(d_match, non_blocking=True)
-            dist.all_gather_into_tensor(d_gcomb, d_comb)
+            pgather.gather(d_match)
 
     def step_device(i):
         fr = d_sets[i % nsets]
@@ -337,7 +336,7 @@ def main():
     e2e_pending = [False] * R
     pts_pending = [False] * PR
 
-    d_comb_e = [d_comb] + [torch.zeros_like(d_comb) for _ in range(PR - 1)] if world > 1 else [None] * PR
+    pg_e = [pgather] + [sbatch.PackedGather(Bf, cap, NL, world, dev) for _ in range(PR - 1)] if world > 1 else [None] * PR
 
     def e2e_finalize(r, p=None):
         """Host-side completion of line slot r: wait for its stream, then the results are in the pinned host buffers.
@@ -349,7 +348,7 @@ def main():
             sp.wait_stream(s_lin[r])
             with torch.cuda.stream(sp):
                 if p is not None:
-                    d_comb_e[p][:, cap:].copy_(d_lmatch[r], non_blocking=True)
+                    pg_e[p].stage_lines(d_lmatch[r])
                 else:
                     dist.all_gather_into_tensor(d_lgather, d_lmatch[r])
             ev_free[r].record(sp)
@@ -391,8 +390,7 @@ def main():
         mts[p].match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match_e[p].data_ptr(), d_nmatch_e[p].data_ptr())
         with torch.cuda.stream(s_p[p]):
             if gather[0]:
-                d_comb_e[p][:, :cap].copy_(d_match_e[p], non_blocking=True)
-                dist.all_gather_into_tensor(d_gcomb, d_comb_e[p])
+                pg_e[p].gather(d_match_e[p])
             h_match[p].copy_(d_match_e[p], non_blocking=True); h_nmatch[p].copy_(d_nmatch_e[p], non_blocking=True)
         pts_pending[p] = True
         return u

@@ -46,3 +46,26 @@ def all_gather_tables(local, group=None):
     out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local.contiguous(), group=group)
     return out
+
+
+class PackedGather:
+    """ONE all-gather per step for both match tables (north_star: "a single NCCL all-gather of match tables"): the point
+    table [per_rank, cap] of this step and a line table [per_rank, nl] travel in one [per_rank, cap + nl] buffer.
+    Buffers are allocated once; all copies are issued on the caller's current stream."""
+
+    def __init__(self, per_rank, cap, nl, world, device, dtype=None):
+        import torch
+        dtype = dtype or torch.int32
+        self.cap, self.nl, self.world, self.per_rank = cap, nl, world, per_rank
+        self.local = torch.full((per_rank, cap + nl), -1, dtype=dtype, device=device)
+        self.full = torch.empty((world * per_rank, cap + nl), dtype=dtype, device=device)
+
+    def stage_lines(self, line_table):
+        self.local[:, self.cap:].copy_(line_table, non_blocking=True)
+
+    def gather(self, point_table, group=None):
+        """-> (points [total, cap], lines [total, nl]) views of the gathered buffer, rows ordered by global pair id."""
+        import torch.distributed as dist
+        self.local[:, :self.cap].copy_(point_table, non_blocking=True)
+        dist.all_gather_into_tensor(self.full, self.local, group=group)
+        return self.full[:, :self.cap], self.full[:, self.cap:]

@@ -41,6 +41,12 @@ def _worker(rank, world, port, q):
     sh = batch.FrameShard(TOTAL, world, rank)
     local = torch.from_numpy(_tables_for(sh.frame_ids()))
     full = batch.all_gather_tables(local)
+    # the packed form used by bench.py: point table + a (synthetic) line table in ONE collective
+    lines = (local[:, :40] * 7 + rank).contiguous()
+    pg = batch.PackedGather(sh.per_rank, CAP, 40, world, "cpu")
+    pg.stage_lines(lines)
+    gp, gl = pg.gather(local)
+    assert torch.equal(gp, full) and torch.equal(gl[rank * sh.per_rank:(rank + 1) * sh.per_rank], lines)
     q.put((rank, sh.frame_ids(), sh.pair_ids(), full.numpy()))
     dist.barrier()
     dist.destroy_process_group()
