@@ -649,6 +649,98 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g,
     }
 }
 
+// Persistent, double-buffered form of k_blur for the TMA path: a CTA walks work items (frame, tile) with stride gridDim.x;
+// while it filters tile i from one shared-memory buffer, the box of tile i+1 is already in flight into the other
+// (cp.async.bulk.tensor + one mbarrier per buffer).  One tile per CTA left the kernel waiting for its box at the start of every
+// CTA (top stall: long scoreboard on the first shared-memory read); arithmetic is identical to k_blur.
+__global__ void __launch_bounds__(256) k_blur_pipe(const __grid_constant__ OrbGeom g, OrbWs ws, const CUtensorMap* tm, int nframes) {
+    __shared__ __align__(128) uint8_t s_buf[2][TL_IH * TL_P];
+    __shared__ __align__(16) unsigned s_pair[TL_IH * TL_W];             // [r][x] = row pass of row r | row r+1 << 16
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const int tid = threadIdx.x;
+    const long long total = (long long)g.total_tiles * nframes;
+    auto decode = [&](long long wi, int& f, int& l, int& x0, int& y0) {
+        f = (int)(wi / g.total_tiles);
+        const int tile = (int)(wi - (long long)f * g.total_tiles);
+        l = 0;
+        while (l + 1 < g.nlevels && tile >= g.lv[l + 1].tile_base) l++;
+        const int t = tile - g.lv[l].tile_base, ty = t / g.lv[l].tiles_x, tx = t - ty * g.lv[l].tiles_x;
+        x0 = tx * TL_W; y0 = ty * TL_H;
+    };
+    auto issue = [&](long long wi, int buf) {                           // thread 0 only
+        int f, l, x0, y0;
+        decode(wi, f, l, x0, y0);
+        asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tm + l)) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the buffer was patched / read by ordinary loads and stores
+        mbar_expect_tx(&s_bar[buf], TL_P * TL_IH);
+        tma_load_3d(s_buf[buf], tm + l, x0 - TL_X, y0 - 3, f, &s_bar[buf]);
+    };
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+    __syncthreads();
+    long long wi = blockIdx.x;
+    if (wi < total && tid == 0) issue(wi, 0);
+    constexpr unsigned T0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), T1 = 48u | (34u << 8) | (18u << 16);
+    constexpr unsigned C01 = 18u | (34u << 8), C23 = 48u | (56u << 8), C45 = 48u | (34u << 8), C6 = 18u;
+    unsigned short* s_half = reinterpret_cast<unsigned short*>(s_pair);
+    for (int it = 0; wi < total; it++, wi += gridDim.x) {
+        const int cur = it & 1;
+        if (wi + gridDim.x < total && tid == 0) issue(wi + gridDim.x, cur ^ 1);   // buffer cur^1 was released by the barrier ending the previous iteration
+        int f, l, x0, y0;
+        decode(wi, f, l, x0, y0);
+        const LevelGeom& L = g.lv[l];
+        const int bx = x0 - TL_X, by = y0 - 3;
+        uint8_t* s_img = s_buf[cur];
+        mbar_wait(&s_bar[cur], (it >> 1) & 1);
+        const bool interior = bx >= 0 && by >= 0 && x0 + TL_W + 3 <= L.w && y0 + TL_H + 3 <= L.h;
+        if (!interior) {
+            // BORDER_REFLECT_101 on top of the zero-filled box: columns first (valid rows), then whole rows
+            for (int i = tid; i < TL_IH * 8; i += 256) {
+                const int r = i >> 3, k = i & 7, gy = by + r;
+                if (gy < 0 || gy >= L.h) continue;
+                const int c = k < 4 ? TL_X - 4 + k : (k - 4) + (L.w - bx);
+                const int gx = bx + c;
+                if (c >= 0 && c < TL_P && (gx < 0 || gx >= L.w)) { const int sxx = reflect101(gx, L.w) - bx; if (sxx >= 0 && sxx < TL_P) s_img[r * TL_P + c] = s_img[r * TL_P + sxx]; }
+            }
+            __syncthreads();
+            for (int i = tid; i < 6 * TL_P; i += 256) {
+                const int k = i / TL_P, c = i - k * TL_P;
+                const int r = k < 3 ? k : (k - 3) + (L.h - by);
+                const int gy = by + r;
+                if (r >= 0 && r < TL_IH && (gy < 0 || gy >= L.h)) { const int sr = reflect101(gy, L.h) - by; if (sr >= 0 && sr < TL_IH) s_img[r * TL_P + c] = s_img[sr * TL_P + c]; }
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < TL_IH * (TL_W / 4); i += 256) {
+            const int r = i >> 4, x4 = (i & 15) * 4;
+            const unsigned* w = reinterpret_cast<const unsigned*>(&s_img[r * TL_P + x4 + TL_X - 4]);
+            const unsigned w0 = w[0], w1 = w[1], w2 = w[2];                   // output k uses bytes 1 + k .. 7 + k of this window
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned A = (k < 3) ? __funnelshift_r(w0, w1, 8 * (k + 1)) : w1;
+                const unsigned B = (k < 3) ? __funnelshift_r(w1, w2, 8 * (k + 1)) : w2;
+                const unsigned q = __dp4a(A, T0, __dp4a(B, T1, 0u));          // <= 65280
+                s_half[(r * TL_W + x4 + k) * 2] = (unsigned short)q;
+                if (r > 0) s_half[((r - 1) * TL_W + x4 + k) * 2 + 1] = (unsigned short)q;
+            }
+        }
+        __syncthreads();
+        uint8_t* out = ws.blur + (long long)f * g.blur_stride + L.blur_off;
+        for (int i = tid; i < TL_H * (TL_W / 4); i += 256) {
+            const int yy = i >> 4, x4 = (i & 15) * 4;
+            if (y0 + yy >= L.h || x0 + x4 >= L.w) continue;
+            const uint4 p0 = *reinterpret_cast<const uint4*>(&s_pair[yy * TL_W + x4]), p2 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 2) * TL_W + x4]);
+            const uint4 p4 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 4) * TL_W + x4]), p6 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 6) * TL_W + x4]);
+            const unsigned a0 = __dp2a_lo(p0.x, C01, __dp2a_lo(p2.x, C23, __dp2a_lo(p4.x, C45, __dp2a_lo(p6.x, C6, 32768u))));
+            const unsigned a1 = __dp2a_lo(p0.y, C01, __dp2a_lo(p2.y, C23, __dp2a_lo(p4.y, C45, __dp2a_lo(p6.y, C6, 32768u))));
+            const unsigned a2 = __dp2a_lo(p0.z, C01, __dp2a_lo(p2.z, C23, __dp2a_lo(p4.z, C45, __dp2a_lo(p6.z, C6, 32768u))));
+            const unsigned a3 = __dp2a_lo(p0.w, C01, __dp2a_lo(p2.w, C23, __dp2a_lo(p4.w, C45, __dp2a_lo(p6.w, C6, 32768u))));
+            *reinterpret_cast<uint32_t*>(out + (long long)(y0 + yy) * L.bpitch + x0 + x4) = (a0 >> 16) | ((a1 >> 16) << 8) | ((a2 >> 16) << 16) | ((a3 >> 16) << 24);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // edge tiles were patched with ordinary stores: order them before the next bulk copy into this buffer
+        __syncthreads();                                                 // s_pair and s_buf[cur] are free again
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // IC_Angle + rBRIEF + KeyPoint assembly: one warp per output keypoint
 // ------------------------------------------------------------------------------------------------
@@ -753,6 +845,8 @@ struct sslpl_orb {
     TMaps tm;                           // per-level tensor maps (level 0 re-encoded per call: the input view moves)
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     bool tma_levels_ok = false, use_tma = true;
+    bool no_pipe = false;            // SSLPL_NO_PIPE=1: one tile per CTA instead of the persistent double-buffered stencil kernels
+    int sm_count = 148;
     const uint8_t* tm0_base = nullptr; int tm0_pitch = 0, tm0_frames = 0; long long tm0_fs = 0;
 };
 
@@ -951,7 +1045,10 @@ int run_pipeline(sslpl_orb* h, int B) {
     mark(h, "fast_cells");
     k_octree<<<dim3(g.nlevels, B), 256, h->octree_smem, st>>>(g, h->ws); h->launches++;
     mark(h, "octree");
-    if (tma) k_blur<true><<<dim3(g.total_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
+    if (tma && !h->no_pipe) {
+        const long long items = (long long)g.total_tiles * B;
+        k_blur_pipe<<<(int)std::min<long long>(items, (long long)h->sm_count * 8), 256, 0, st>>>(g, h->ws, h->ws.tmaps, B);
+    } else if (tma) k_blur<true><<<dim3(g.total_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
     else k_blur<false><<<dim3(g.total_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
     h->launches++;
     mark(h, "blur");
@@ -1011,6 +1108,10 @@ int sslpl_orb_create(const sslpl_orb_params* p, sslpl_orb** out) {
         else cudaGetLastError();
         const char* e = getenv("SSLPL_NO_TMA");
         h->use_tma = !(e && e[0] == '1');
+        const char* e2 = getenv("SSLPL_NO_PIPE");
+        h->no_pipe = e2 && e2[0] == '1';
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && v > 0) h->sm_count = v;
     }
     *out = h;
     return SSLPL_OK;
