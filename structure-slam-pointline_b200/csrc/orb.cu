@@ -293,6 +293,96 @@ __global__ void __launch_bounds__(256) k_fast_score(const __grid_constant__ OrbG
     }
 }
 
+// Persistent, double-buffered form of k_fast_score for the TMA path (see k_blur_pipe): work items (frame, tile) with stride
+// gridDim.x, the box of the next tile in flight while the current one is scored.  Same phases A / B, same output.
+__global__ void __launch_bounds__(256) k_fast_score_pipe(const __grid_constant__ OrbGeom g, OrbWs ws, const CUtensorMap* tm, int nframes) {
+    __shared__ __align__(128) uint8_t s_buf[2][TL_IH * TL_P];
+    __shared__ __align__(16) uint8_t s_sc[TL_H * TL_W];
+    __shared__ unsigned short s_q[TL_H * TL_W];
+    __shared__ int s_qn;
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long total = (long long)g.total_fs_tiles * nframes;
+    auto decode = [&](long long wi, int& f, int& l, int& x0, int& y0) {
+        f = (int)(wi / g.total_fs_tiles);
+        const int tile = (int)(wi - (long long)f * g.total_fs_tiles);
+        l = 0;
+        while (l + 1 < g.nlevels && tile >= g.lv[l + 1].fs_base) l++;
+        const int t = tile - g.lv[l].fs_base, ty = t / g.lv[l].fs_tx, tx = t - ty * g.lv[l].fs_tx;
+        x0 = MINB + tx * TL_W; y0 = MINB + ty * TL_H;
+    };
+    auto issue = [&](long long wi, int buf) {                           // thread 0 only
+        int f, l, x0, y0;
+        decode(wi, f, l, x0, y0);
+        asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tm + l)) : "memory");
+        mbar_expect_tx(&s_bar[buf], TL_P * TL_IH);
+        tma_load_3d(s_buf[buf], tm + l, x0 - TL_X, y0 - 3, f, &s_bar[buf]);
+    };
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+    __syncthreads();
+    long long wi = blockIdx.x;
+    if (wi < total && tid == 0) issue(wi, 0);
+    const int th = g.minTh;
+    const unsigned T4 = 0x01010101u * (unsigned)th;
+    for (int it = 0; wi < total; it++, wi += gridDim.x) {
+        const int cur = it & 1;
+        if (wi + gridDim.x < total && tid == 0) issue(wi + gridDim.x, cur ^ 1);   // (the box buffers are only ever read by the threads)
+        int f, l, x0, y0;
+        decode(wi, f, l, x0, y0);
+        const LevelGeom& L = g.lv[l];
+        const uint8_t* s_img = s_buf[cur];
+        if (tid == 0) s_qn = 0;
+        for (int i = tid; i < TL_H * TL_W / 4; i += 256) reinterpret_cast<uint32_t*>(s_sc)[i] = 0u;
+        mbar_wait(&s_bar[cur], (it >> 1) & 1);
+        __syncthreads();                         // s_qn / s_sc initialisation
+        const int vw = min(TL_W, L.maxBX - x0), vh = min(TL_H, L.maxBY - y0);     // valid part of the tile
+#pragma unroll
+        for (int ph = 0; ph < 2; ph++) {
+            const int gidx = ph * 256 + tid, r = gidx >> 4, c4 = (gidx & 15) * 4;
+            unsigned pm = 0;
+            if (r < vh && c4 < vw) {
+                const unsigned* row = reinterpret_cast<const unsigned*>(&s_img[(r + 3) * TL_P + TL_X + c4]);
+                const unsigned C = row[0];
+                const unsigned Rt = __byte_perm(row[0], row[1], 0x6543), Lf = __byte_perm(row[-1], row[0], 0x4321);
+                const unsigned Dn = row[3 * (TL_P / 4)], Up = row[-3 * (TL_P / 4)];
+                const unsigned A0 = __vcmpgtu4(__vsubus4(C, Dn), T4), A8 = __vcmpgtu4(__vsubus4(C, Up), T4);
+                const unsigned A4 = __vcmpgtu4(__vsubus4(C, Rt), T4), A12 = __vcmpgtu4(__vsubus4(C, Lf), T4);
+                const unsigned B0 = __vcmpgtu4(__vsubus4(Dn, C), T4), B8 = __vcmpgtu4(__vsubus4(Up, C), T4);
+                const unsigned B4 = __vcmpgtu4(__vsubus4(Rt, C), T4), B12 = __vcmpgtu4(__vsubus4(Lf, C), T4);
+                pm = (((A0 | A8) & (A4 | A12)) | ((B0 | B8) & (B4 | B12))) & 0x01010101u;
+                if (c4 + 4 > vw) pm &= (1u << (8 * (vw - c4))) - 1u;
+            }
+            const int cnt = __popc(pm);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t2; }
+            int base = 0;
+            if (lane == 31 && inc) base = atomicAdd(&s_qn, inc);
+            base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+            const int p0 = r * TL_W + c4;
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (pm & (1u << (8 * k))) s_q[base++] = (unsigned short)(p0 + k);
+        }
+        __syncthreads();
+        const int nq = s_qn;
+        for (int qi = tid; qi < nq; qi += 256) {
+            const int p = s_q[qi], r = p >> 6, c = p & 63;
+            s_sc[p] = (uint8_t)fast_score_tile(&s_img[(r + 3) * TL_P + c + TL_X], TL_P, th);
+        }
+        __syncthreads();
+        uint8_t* out = ws.score + (long long)f * g.blur_stride + L.blur_off + (long long)y0 * L.bpitch + x0;
+        if (vw == TL_W) {
+            for (int i = tid; i < vh * 4; i += 256) {
+                const int r = i >> 2, part = i & 3;
+                *reinterpret_cast<uint4*>(out + (long long)r * L.bpitch + part * 16) = reinterpret_cast<const uint4*>(s_sc)[r * 4 + part];
+            }
+        } else {
+            for (int i = tid; i < vh * vw; i += 256) { const int r = i / vw, c = i - r * vw; out[(long long)r * L.bpitch + c] = s_sc[r * TL_W + c]; }
+        }
+        __syncthreads();                         // s_sc, s_q, s_qn and s_buf[cur] are free again
+    }
+}
+
 constexpr int FAST_MAXC = 60;                 // wCell, hCell < 60 (ceil(w / floor(w/30)) < 60)
 constexpr int FAST_TP = FAST_MAXC + 4;        // pitch of the per-cell score tile (1-px zero halo)
 
@@ -846,7 +936,7 @@ struct sslpl_orb {
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     bool tma_levels_ok = false, use_tma = true;
     bool no_pipe = false;            // SSLPL_NO_PIPE=1: one tile per CTA instead of the persistent double-buffered stencil kernels
-    int sm_count = 148;
+    int sm_count = 148, occ_fast = 4, occ_blur = 4;   // persistent grids = SMs x resident CTAs per SM (occupancy API)
     const uint8_t* tm0_base = nullptr; int tm0_pitch = 0, tm0_frames = 0; long long tm0_fs = 0;
 };
 
@@ -1036,7 +1126,10 @@ int run_pipeline(sslpl_orb* h, int B) {
         } else h->tm0_base = nullptr;
     }
     if (g.total_cells > 0) {
-        if (tma) k_fast_score<true><<<dim3(g.total_fs_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
+        if (tma && !h->no_pipe) {
+            const long long items = (long long)g.total_fs_tiles * B;
+            k_fast_score_pipe<<<(int)std::min<long long>(items, (long long)h->sm_count * h->occ_fast), 256, 0, st>>>(g, h->ws, h->ws.tmaps, B);
+        } else if (tma) k_fast_score<true><<<dim3(g.total_fs_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
         else k_fast_score<false><<<dim3(g.total_fs_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
         mark(h, "fast_score");
         k_fast_cells<<<dim3(g.total_cells, B), 128, 0, st>>>(g, h->ws);
@@ -1047,7 +1140,7 @@ int run_pipeline(sslpl_orb* h, int B) {
     mark(h, "octree");
     if (tma && !h->no_pipe) {
         const long long items = (long long)g.total_tiles * B;
-        k_blur_pipe<<<(int)std::min<long long>(items, (long long)h->sm_count * 8), 256, 0, st>>>(g, h->ws, h->ws.tmaps, B);
+        k_blur_pipe<<<(int)std::min<long long>(items, (long long)h->sm_count * h->occ_blur), 256, 0, st>>>(g, h->ws, h->ws.tmaps, B);
     } else if (tma) k_blur<true><<<dim3(g.total_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
     else k_blur<false><<<dim3(g.total_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
     h->launches++;
@@ -1112,6 +1205,9 @@ int sslpl_orb_create(const sslpl_orb_params* p, sslpl_orb** out) {
         h->no_pipe = e2 && e2[0] == '1';
         int v = 0;
         if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && v > 0) h->sm_count = v;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_fast_score_pipe, 256, 0) == cudaSuccess && v > 0) h->occ_fast = v;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_blur_pipe, 256, 0) == cudaSuccess && v > 0) h->occ_blur = v;
+        cudaGetLastError();
     }
     *out = h;
     return SSLPL_OK;
