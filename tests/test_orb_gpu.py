@@ -119,6 +119,15 @@ def test_non_tma_fallback_path(pkg, oracle, synth, icl_gray, monkeypatch):
     _compare_all(ext2, oracle.OrbOracle(800, 1.2, 8, 20, 7), np.ascontiguousarray(img), "w613")
 
 
+def test_one_tile_per_cta_kernels(pkg, oracle, synth, icl_gray, monkeypatch):
+    """SSLPL_NO_PIPE=1 selects the one-tile-per-CTA TMA kernels instead of the persistent double-buffered ones."""
+    monkeypatch.setenv("SSLPL_NO_PIPE", "1")
+    ext = pkg.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480)
+    monkeypatch.delenv("SSLPL_NO_PIPE")
+    _compare_all(ext, oracle.OrbOracle(1000, 1.2, 8, 20, 7), icl_gray, "no-pipe")
+    _compare_all(ext, oracle.OrbOracle(1000, 1.2, 8, 20, 7), synth.frame(640, 480, 7), "no-pipe-syn")
+
+
 def test_async_begin_and_device_paths(pkg, oracle, synth):
     """The asynchronous host-buffer form (pinned buffers, sslpl_orb_extract_batch_begin + sync) and the device-resident
     form must give the same keypoints/descriptors as the synchronous call."""
