@@ -935,7 +935,7 @@ struct sslpl_orb {
     TMaps tm;                           // per-level tensor maps (level 0 re-encoded per call: the input view moves)
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     bool tma_levels_ok = false, use_tma = true;
-    bool no_pipe = false;            // SSLPL_NO_PIPE=1: one tile per CTA instead of the persistent double-buffered stencil kernels
+    bool no_pipe = true;             // SSLPL_PIPE=1 selects the persistent double-buffered stencil kernels (k_*_pipe)
     int sm_count = 148, occ_fast = 4, occ_blur = 4;   // persistent grids = SMs x resident CTAs per SM (occupancy API)
     const uint8_t* tm0_base = nullptr; int tm0_pitch = 0, tm0_frames = 0; long long tm0_fs = 0;
 };
@@ -1201,8 +1201,8 @@ int sslpl_orb_create(const sslpl_orb_params* p, sslpl_orb** out) {
         else cudaGetLastError();
         const char* e = getenv("SSLPL_NO_TMA");
         h->use_tma = !(e && e[0] == '1');
-        const char* e2 = getenv("SSLPL_NO_PIPE");
-        h->no_pipe = e2 && e2[0] == '1';
+        const char* e2 = getenv("SSLPL_PIPE");             // opt-in until the persistent kernels have a GPU parity run behind them
+        h->no_pipe = !(e2 && e2[0] == '1');
         int v = 0;
         if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && v > 0) h->sm_count = v;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_fast_score_pipe, 256, 0) == cudaSuccess && v > 0) h->occ_fast = v;

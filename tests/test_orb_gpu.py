@@ -1,6 +1,7 @@
 """GPU parity: CUDA ORB path (through the C-ABI) vs the CPU oracle, stage by stage and end to end.
 Bit-exact for integer work (pyramid, candidates, octree selection, descriptors); float outputs
 (angle, scaled coordinates) are expected bit-equal too and are checked at 1e-4 px / 1e-3 rad."""
+import os
 import numpy as np
 import pytest
 
@@ -119,13 +120,19 @@ def test_non_tma_fallback_path(pkg, oracle, synth, icl_gray, monkeypatch):
     _compare_all(ext2, oracle.OrbOracle(800, 1.2, 8, 20, 7), np.ascontiguousarray(img), "w613")
 
 
-def test_one_tile_per_cta_kernels(pkg, oracle, synth, icl_gray, monkeypatch):
-    """SSLPL_NO_PIPE=1 selects the one-tile-per-CTA TMA kernels instead of the persistent double-buffered ones."""
-    monkeypatch.setenv("SSLPL_NO_PIPE", "1")
-    ext = pkg.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480)
-    monkeypatch.delenv("SSLPL_NO_PIPE")
-    _compare_all(ext, oracle.OrbOracle(1000, 1.2, 8, 20, 7), icl_gray, "no-pipe")
-    _compare_all(ext, oracle.OrbOracle(1000, 1.2, 8, 20, 7), synth.frame(640, 480, 7), "no-pipe-syn")
+@pytest.mark.skipif(os.environ.get("SSLPL_TEST_PIPE") != "1", reason="persistent double-buffered stencil kernels are opt-in (SSLPL_PIPE=1) until validated")
+def test_persistent_pipe_kernels(pkg, oracle, synth, icl_gray, monkeypatch):
+    """SSLPL_PIPE=1 selects k_fast_score_pipe / k_blur_pipe (persistent CTAs, double-buffered TMA boxes) instead of the
+    one-tile-per-CTA kernels; results must not change."""
+    monkeypatch.setenv("SSLPL_PIPE", "1")
+    ext = pkg.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=7)
+    monkeypatch.delenv("SSLPL_PIPE")
+    _compare_all(ext, oracle.OrbOracle(1000, 1.2, 8, 20, 7), icl_gray, "pipe")
+    _compare_all(ext, oracle.OrbOracle(1000, 1.2, 8, 20, 7), synth.frame(640, 480, 7), "pipe-syn")
+    frames = synth.batch(640, 480, 7)
+    k, d, n = ext.extract_batch(frames)
+    ref = pkg.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=7).extract_batch(frames)
+    assert np.array_equal(n, ref[2]) and np.array_equal(d, ref[1]) and k.tobytes() == ref[0].tobytes()
 
 
 def test_async_begin_and_device_paths(pkg, oracle, synth):
