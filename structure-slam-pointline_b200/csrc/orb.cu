@@ -182,6 +182,7 @@ constexpr int TL_W = 64, TL_H = 32;            // output tile of the stencil ker
 constexpr int TL_P = 96, TL_IH = TL_H + 6;     // staged box: 96 x 38 bytes, origin (x0 - 16, y0 - 3).  For 1-byte elements TMA
                                                // requires the box to START on a 16-byte boundary in x (measured: tools/tma_probe.cu)
 constexpr int TL_X = 16;                       // smem column of the tile's first output pixel
+constexpr int TL_BUF = (TL_IH * TL_P + 127) / 128 * 128;   // one staged box, padded to the 128-byte alignment of TMA destinations
 
 // Stage the 96x38 box of level `l`, frame `f` at (bx, by) into s_img (pitch TL_P).  TMA path: one bulk tensor copy,
 // zero fill outside the level.  Fallback: aligned 32-bit loads (clamped to the row) or byte loads.
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(256) k_fast_score(const __grid_constant__ OrbG
 // Persistent, double-buffered form of k_fast_score for the TMA path (see k_blur_pipe): work items (frame, tile) with stride
 // gridDim.x, the box of the next tile in flight while the current one is scored.  Same phases A / B, same output.
 __global__ void __launch_bounds__(256) k_fast_score_pipe(const __grid_constant__ OrbGeom g, OrbWs ws, const CUtensorMap* tm, int nframes) {
-    __shared__ __align__(128) uint8_t s_buf[2][TL_IH * TL_P];
+    __shared__ __align__(128) uint8_t s_buf[2][TL_BUF];          // each box buffer 128-byte aligned (bulk tensor copies require it)
     __shared__ __align__(16) uint8_t s_sc[TL_H * TL_W];
     __shared__ unsigned short s_q[TL_H * TL_W];
     __shared__ int s_qn;
@@ -744,7 +745,7 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g,
 // (cp.async.bulk.tensor + one mbarrier per buffer).  One tile per CTA left the kernel waiting for its box at the start of every
 // CTA (top stall: long scoreboard on the first shared-memory read); arithmetic is identical to k_blur.
 __global__ void __launch_bounds__(256) k_blur_pipe(const __grid_constant__ OrbGeom g, OrbWs ws, const CUtensorMap* tm, int nframes) {
-    __shared__ __align__(128) uint8_t s_buf[2][TL_IH * TL_P];
+    __shared__ __align__(128) uint8_t s_buf[2][TL_BUF];          // each box buffer 128-byte aligned (bulk tensor copies require it)
     __shared__ __align__(16) unsigned s_pair[TL_IH * TL_W];             // [r][x] = row pass of row r | row r+1 << 16
     __shared__ __align__(8) uint64_t s_bar[2];
     const int tid = threadIdx.x;
