@@ -182,7 +182,6 @@ constexpr int TL_W = 64, TL_H = 32;            // output tile of the stencil ker
 constexpr int TL_P = 96, TL_IH = TL_H + 6;     // staged box: 96 x 38 bytes, origin (x0 - 16, y0 - 3).  For 1-byte elements TMA
                                                // requires the box to START on a 16-byte boundary in x (measured: tools/tma_probe.cu)
 constexpr int TL_X = 16;                       // smem column of the tile's first output pixel
-constexpr int TL_BUF = (TL_IH * TL_P + 127) / 128 * 128;   // one staged box, padded to the 128-byte alignment of TMA destinations
 
 // Stage the 96x38 box of level `l`, frame `f` at (bx, by) into s_img (pitch TL_P).  TMA path: one bulk tensor copy,
 // zero fill outside the level.  Fallback: aligned 32-bit loads (clamped to the row) or byte loads.
@@ -291,96 +290,6 @@ __global__ void __launch_bounds__(256) k_fast_score(const __grid_constant__ OrbG
         }
     } else {
         for (int i = tid; i < vh * vw; i += 256) { const int r = i / vw, c = i - r * vw; out[(long long)r * L.bpitch + c] = s_sc[r * TL_W + c]; }
-    }
-}
-
-// Persistent, double-buffered form of k_fast_score for the TMA path (see k_blur_pipe): work items (frame, tile) with stride
-// gridDim.x, the box of the next tile in flight while the current one is scored.  Same phases A / B, same output.
-__global__ void __launch_bounds__(256) k_fast_score_pipe(const __grid_constant__ OrbGeom g, OrbWs ws, const CUtensorMap* tm, int nframes) {
-    __shared__ __align__(128) uint8_t s_buf[2][TL_BUF];          // each box buffer 128-byte aligned (bulk tensor copies require it)
-    __shared__ __align__(16) uint8_t s_sc[TL_H * TL_W];
-    __shared__ unsigned short s_q[TL_H * TL_W];
-    __shared__ int s_qn;
-    __shared__ __align__(8) uint64_t s_bar[2];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const long long total = (long long)g.total_fs_tiles * nframes;
-    auto decode = [&](long long wi, int& f, int& l, int& x0, int& y0) {
-        f = (int)(wi / g.total_fs_tiles);
-        const int tile = (int)(wi - (long long)f * g.total_fs_tiles);
-        l = 0;
-        while (l + 1 < g.nlevels && tile >= g.lv[l + 1].fs_base) l++;
-        const int t = tile - g.lv[l].fs_base, ty = t / g.lv[l].fs_tx, tx = t - ty * g.lv[l].fs_tx;
-        x0 = MINB + tx * TL_W; y0 = MINB + ty * TL_H;
-    };
-    auto issue = [&](long long wi, int buf) {                           // thread 0 only
-        int f, l, x0, y0;
-        decode(wi, f, l, x0, y0);
-        asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tm + l)) : "memory");
-        mbar_expect_tx(&s_bar[buf], TL_P * TL_IH);
-        tma_load_3d(s_buf[buf], tm + l, x0 - TL_X, y0 - 3, f, &s_bar[buf]);
-    };
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
-    __syncthreads();
-    long long wi = blockIdx.x;
-    if (wi < total && tid == 0) issue(wi, 0);
-    const int th = g.minTh;
-    const unsigned T4 = 0x01010101u * (unsigned)th;
-    for (int it = 0; wi < total; it++, wi += gridDim.x) {
-        const int cur = it & 1;
-        if (wi + gridDim.x < total && tid == 0) issue(wi + gridDim.x, cur ^ 1);   // (the box buffers are only ever read by the threads)
-        int f, l, x0, y0;
-        decode(wi, f, l, x0, y0);
-        const LevelGeom& L = g.lv[l];
-        const uint8_t* s_img = s_buf[cur];
-        if (tid == 0) s_qn = 0;
-        for (int i = tid; i < TL_H * TL_W / 4; i += 256) reinterpret_cast<uint32_t*>(s_sc)[i] = 0u;
-        mbar_wait(&s_bar[cur], (it >> 1) & 1);
-        __syncthreads();                         // s_qn / s_sc initialisation
-        const int vw = min(TL_W, L.maxBX - x0), vh = min(TL_H, L.maxBY - y0);     // valid part of the tile
-#pragma unroll
-        for (int ph = 0; ph < 2; ph++) {
-            const int gidx = ph * 256 + tid, r = gidx >> 4, c4 = (gidx & 15) * 4;
-            unsigned pm = 0;
-            if (r < vh && c4 < vw) {
-                const unsigned* row = reinterpret_cast<const unsigned*>(&s_img[(r + 3) * TL_P + TL_X + c4]);
-                const unsigned C = row[0];
-                const unsigned Rt = __byte_perm(row[0], row[1], 0x6543), Lf = __byte_perm(row[-1], row[0], 0x4321);
-                const unsigned Dn = row[3 * (TL_P / 4)], Up = row[-3 * (TL_P / 4)];
-                const unsigned A0 = __vcmpgtu4(__vsubus4(C, Dn), T4), A8 = __vcmpgtu4(__vsubus4(C, Up), T4);
-                const unsigned A4 = __vcmpgtu4(__vsubus4(C, Rt), T4), A12 = __vcmpgtu4(__vsubus4(C, Lf), T4);
-                const unsigned B0 = __vcmpgtu4(__vsubus4(Dn, C), T4), B8 = __vcmpgtu4(__vsubus4(Up, C), T4);
-                const unsigned B4 = __vcmpgtu4(__vsubus4(Rt, C), T4), B12 = __vcmpgtu4(__vsubus4(Lf, C), T4);
-                pm = (((A0 | A8) & (A4 | A12)) | ((B0 | B8) & (B4 | B12))) & 0x01010101u;
-                if (c4 + 4 > vw) pm &= (1u << (8 * (vw - c4))) - 1u;
-            }
-            const int cnt = __popc(pm);
-            int inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t2; }
-            int base = 0;
-            if (lane == 31 && inc) base = atomicAdd(&s_qn, inc);
-            base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
-            const int p0 = r * TL_W + c4;
-#pragma unroll
-            for (int k = 0; k < 4; k++) if (pm & (1u << (8 * k))) s_q[base++] = (unsigned short)(p0 + k);
-        }
-        __syncthreads();
-        const int nq = s_qn;
-        for (int qi = tid; qi < nq; qi += 256) {
-            const int p = s_q[qi], r = p >> 6, c = p & 63;
-            s_sc[p] = (uint8_t)fast_score_tile(&s_img[(r + 3) * TL_P + c + TL_X], TL_P, th);
-        }
-        __syncthreads();
-        uint8_t* out = ws.score + (long long)f * g.blur_stride + L.blur_off + (long long)y0 * L.bpitch + x0;
-        if (vw == TL_W) {
-            for (int i = tid; i < vh * 4; i += 256) {
-                const int r = i >> 2, part = i & 3;
-                *reinterpret_cast<uint4*>(out + (long long)r * L.bpitch + part * 16) = reinterpret_cast<const uint4*>(s_sc)[r * 4 + part];
-            }
-        } else {
-            for (int i = tid; i < vh * vw; i += 256) { const int r = i / vw, c = i - r * vw; out[(long long)r * L.bpitch + c] = s_sc[r * TL_W + c]; }
-        }
-        __syncthreads();                         // s_sc, s_q, s_qn and s_buf[cur] are free again
     }
 }
 
@@ -740,98 +649,6 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g,
     }
 }
 
-// Persistent, double-buffered form of k_blur for the TMA path: a CTA walks work items (frame, tile) with stride gridDim.x;
-// while it filters tile i from one shared-memory buffer, the box of tile i+1 is already in flight into the other
-// (cp.async.bulk.tensor + one mbarrier per buffer).  One tile per CTA left the kernel waiting for its box at the start of every
-// CTA (top stall: long scoreboard on the first shared-memory read); arithmetic is identical to k_blur.
-__global__ void __launch_bounds__(256) k_blur_pipe(const __grid_constant__ OrbGeom g, OrbWs ws, const CUtensorMap* tm, int nframes) {
-    __shared__ __align__(128) uint8_t s_buf[2][TL_BUF];          // each box buffer 128-byte aligned (bulk tensor copies require it)
-    __shared__ __align__(16) unsigned s_pair[TL_IH * TL_W];             // [r][x] = row pass of row r | row r+1 << 16
-    __shared__ __align__(8) uint64_t s_bar[2];
-    const int tid = threadIdx.x;
-    const long long total = (long long)g.total_tiles * nframes;
-    auto decode = [&](long long wi, int& f, int& l, int& x0, int& y0) {
-        f = (int)(wi / g.total_tiles);
-        const int tile = (int)(wi - (long long)f * g.total_tiles);
-        l = 0;
-        while (l + 1 < g.nlevels && tile >= g.lv[l + 1].tile_base) l++;
-        const int t = tile - g.lv[l].tile_base, ty = t / g.lv[l].tiles_x, tx = t - ty * g.lv[l].tiles_x;
-        x0 = tx * TL_W; y0 = ty * TL_H;
-    };
-    auto issue = [&](long long wi, int buf) {                           // thread 0 only
-        int f, l, x0, y0;
-        decode(wi, f, l, x0, y0);
-        asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tm + l)) : "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the buffer was patched / read by ordinary loads and stores
-        mbar_expect_tx(&s_bar[buf], TL_P * TL_IH);
-        tma_load_3d(s_buf[buf], tm + l, x0 - TL_X, y0 - 3, f, &s_bar[buf]);
-    };
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
-    __syncthreads();
-    long long wi = blockIdx.x;
-    if (wi < total && tid == 0) issue(wi, 0);
-    constexpr unsigned T0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), T1 = 48u | (34u << 8) | (18u << 16);
-    constexpr unsigned C01 = 18u | (34u << 8), C23 = 48u | (56u << 8), C45 = 48u | (34u << 8), C6 = 18u;
-    unsigned short* s_half = reinterpret_cast<unsigned short*>(s_pair);
-    for (int it = 0; wi < total; it++, wi += gridDim.x) {
-        const int cur = it & 1;
-        if (wi + gridDim.x < total && tid == 0) issue(wi + gridDim.x, cur ^ 1);   // buffer cur^1 was released by the barrier ending the previous iteration
-        int f, l, x0, y0;
-        decode(wi, f, l, x0, y0);
-        const LevelGeom& L = g.lv[l];
-        const int bx = x0 - TL_X, by = y0 - 3;
-        uint8_t* s_img = s_buf[cur];
-        mbar_wait(&s_bar[cur], (it >> 1) & 1);
-        const bool interior = bx >= 0 && by >= 0 && x0 + TL_W + 3 <= L.w && y0 + TL_H + 3 <= L.h;
-        if (!interior) {
-            // BORDER_REFLECT_101 on top of the zero-filled box: columns first (valid rows), then whole rows
-            for (int i = tid; i < TL_IH * 8; i += 256) {
-                const int r = i >> 3, k = i & 7, gy = by + r;
-                if (gy < 0 || gy >= L.h) continue;
-                const int c = k < 4 ? TL_X - 4 + k : (k - 4) + (L.w - bx);
-                const int gx = bx + c;
-                if (c >= 0 && c < TL_P && (gx < 0 || gx >= L.w)) { const int sxx = reflect101(gx, L.w) - bx; if (sxx >= 0 && sxx < TL_P) s_img[r * TL_P + c] = s_img[r * TL_P + sxx]; }
-            }
-            __syncthreads();
-            for (int i = tid; i < 6 * TL_P; i += 256) {
-                const int k = i / TL_P, c = i - k * TL_P;
-                const int r = k < 3 ? k : (k - 3) + (L.h - by);
-                const int gy = by + r;
-                if (r >= 0 && r < TL_IH && (gy < 0 || gy >= L.h)) { const int sr = reflect101(gy, L.h) - by; if (sr >= 0 && sr < TL_IH) s_img[r * TL_P + c] = s_img[sr * TL_P + c]; }
-            }
-            __syncthreads();
-        }
-        for (int i = tid; i < TL_IH * (TL_W / 4); i += 256) {
-            const int r = i >> 4, x4 = (i & 15) * 4;
-            const unsigned* w = reinterpret_cast<const unsigned*>(&s_img[r * TL_P + x4 + TL_X - 4]);
-            const unsigned w0 = w[0], w1 = w[1], w2 = w[2];                   // output k uses bytes 1 + k .. 7 + k of this window
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned A = (k < 3) ? __funnelshift_r(w0, w1, 8 * (k + 1)) : w1;
-                const unsigned B = (k < 3) ? __funnelshift_r(w1, w2, 8 * (k + 1)) : w2;
-                const unsigned q = __dp4a(A, T0, __dp4a(B, T1, 0u));          // <= 65280
-                s_half[(r * TL_W + x4 + k) * 2] = (unsigned short)q;
-                if (r > 0) s_half[((r - 1) * TL_W + x4 + k) * 2 + 1] = (unsigned short)q;
-            }
-        }
-        __syncthreads();
-        uint8_t* out = ws.blur + (long long)f * g.blur_stride + L.blur_off;
-        for (int i = tid; i < TL_H * (TL_W / 4); i += 256) {
-            const int yy = i >> 4, x4 = (i & 15) * 4;
-            if (y0 + yy >= L.h || x0 + x4 >= L.w) continue;
-            const uint4 p0 = *reinterpret_cast<const uint4*>(&s_pair[yy * TL_W + x4]), p2 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 2) * TL_W + x4]);
-            const uint4 p4 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 4) * TL_W + x4]), p6 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 6) * TL_W + x4]);
-            const unsigned a0 = __dp2a_lo(p0.x, C01, __dp2a_lo(p2.x, C23, __dp2a_lo(p4.x, C45, __dp2a_lo(p6.x, C6, 32768u))));
-            const unsigned a1 = __dp2a_lo(p0.y, C01, __dp2a_lo(p2.y, C23, __dp2a_lo(p4.y, C45, __dp2a_lo(p6.y, C6, 32768u))));
-            const unsigned a2 = __dp2a_lo(p0.z, C01, __dp2a_lo(p2.z, C23, __dp2a_lo(p4.z, C45, __dp2a_lo(p6.z, C6, 32768u))));
-            const unsigned a3 = __dp2a_lo(p0.w, C01, __dp2a_lo(p2.w, C23, __dp2a_lo(p4.w, C45, __dp2a_lo(p6.w, C6, 32768u))));
-            *reinterpret_cast<uint32_t*>(out + (long long)(y0 + yy) * L.bpitch + x0 + x4) = (a0 >> 16) | ((a1 >> 16) << 8) | ((a2 >> 16) << 16) | ((a3 >> 16) << 24);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // edge tiles were patched with ordinary stores: order them before the next bulk copy into this buffer
-        __syncthreads();                                                 // s_pair and s_buf[cur] are free again
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // IC_Angle + rBRIEF + KeyPoint assembly: one warp per output keypoint
 // ------------------------------------------------------------------------------------------------
@@ -936,8 +753,6 @@ struct sslpl_orb {
     TMaps tm;                           // per-level tensor maps (level 0 re-encoded per call: the input view moves)
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     bool tma_levels_ok = false, use_tma = true;
-    bool no_pipe = true;             // SSLPL_PIPE=1 selects the persistent double-buffered stencil kernels (k_*_pipe)
-    int sm_count = 148, occ_fast = 4, occ_blur = 4;   // persistent grids = SMs x resident CTAs per SM (occupancy API)
     const uint8_t* tm0_base = nullptr; int tm0_pitch = 0, tm0_frames = 0; long long tm0_fs = 0;
 };
 
@@ -1127,10 +942,7 @@ int run_pipeline(sslpl_orb* h, int B) {
         } else h->tm0_base = nullptr;
     }
     if (g.total_cells > 0) {
-        if (tma && !h->no_pipe) {
-            const long long items = (long long)g.total_fs_tiles * B;
-            k_fast_score_pipe<<<(int)std::min<long long>(items, (long long)h->sm_count * h->occ_fast), 256, 0, st>>>(g, h->ws, h->ws.tmaps, B);
-        } else if (tma) k_fast_score<true><<<dim3(g.total_fs_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
+        if (tma) k_fast_score<true><<<dim3(g.total_fs_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
         else k_fast_score<false><<<dim3(g.total_fs_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
         mark(h, "fast_score");
         k_fast_cells<<<dim3(g.total_cells, B), 128, 0, st>>>(g, h->ws);
@@ -1139,10 +951,7 @@ int run_pipeline(sslpl_orb* h, int B) {
     mark(h, "fast_cells");
     k_octree<<<dim3(g.nlevels, B), 256, h->octree_smem, st>>>(g, h->ws); h->launches++;
     mark(h, "octree");
-    if (tma && !h->no_pipe) {
-        const long long items = (long long)g.total_tiles * B;
-        k_blur_pipe<<<(int)std::min<long long>(items, (long long)h->sm_count * h->occ_blur), 256, 0, st>>>(g, h->ws, h->ws.tmaps, B);
-    } else if (tma) k_blur<true><<<dim3(g.total_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
+    if (tma) k_blur<true><<<dim3(g.total_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
     else k_blur<false><<<dim3(g.total_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
     h->launches++;
     mark(h, "blur");
@@ -1202,13 +1011,6 @@ int sslpl_orb_create(const sslpl_orb_params* p, sslpl_orb** out) {
         else cudaGetLastError();
         const char* e = getenv("SSLPL_NO_TMA");
         h->use_tma = !(e && e[0] == '1');
-        const char* e2 = getenv("SSLPL_PIPE");             // opt-in until the persistent kernels have a GPU parity run behind them
-        h->no_pipe = !(e2 && e2[0] == '1');
-        int v = 0;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && v > 0) h->sm_count = v;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_fast_score_pipe, 256, 0) == cudaSuccess && v > 0) h->occ_fast = v;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_blur_pipe, 256, 0) == cudaSuccess && v > 0) h->occ_blur = v;
-        cudaGetLastError();
     }
     *out = h;
     return SSLPL_OK;

@@ -120,21 +120,6 @@ def test_non_tma_fallback_path(pkg, oracle, synth, icl_gray, monkeypatch):
     _compare_all(ext2, oracle.OrbOracle(800, 1.2, 8, 20, 7), np.ascontiguousarray(img), "w613")
 
 
-@pytest.mark.skipif(os.environ.get("SSLPL_TEST_PIPE") != "1", reason="persistent double-buffered stencil kernels are opt-in (SSLPL_PIPE=1) until validated")
-def test_persistent_pipe_kernels(pkg, oracle, synth, icl_gray, monkeypatch):
-    """SSLPL_PIPE=1 selects k_fast_score_pipe / k_blur_pipe (persistent CTAs, double-buffered TMA boxes) instead of the
-    one-tile-per-CTA kernels; results must not change."""
-    monkeypatch.setenv("SSLPL_PIPE", "1")
-    ext = pkg.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=7)
-    monkeypatch.delenv("SSLPL_PIPE")
-    _compare_all(ext, oracle.OrbOracle(1000, 1.2, 8, 20, 7), icl_gray, "pipe")
-    _compare_all(ext, oracle.OrbOracle(1000, 1.2, 8, 20, 7), synth.frame(640, 480, 7), "pipe-syn")
-    frames = synth.batch(640, 480, 7)
-    k, d, n = ext.extract_batch(frames)
-    ref = pkg.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=7).extract_batch(frames)
-    assert np.array_equal(n, ref[2]) and np.array_equal(d, ref[1]) and k.tobytes() == ref[0].tobytes()
-
-
 def test_async_begin_and_device_paths(pkg, oracle, synth):
     """The asynchronous host-buffer form (pinned buffers, sslpl_orb_extract_batch_begin + sync) and the device-resident
     form must give the same keypoints/descriptors as the synchronous call."""

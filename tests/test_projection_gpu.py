@@ -3,11 +3,7 @@ feature grid (Frame.cc:133-148, 368-421) — SURVEY.md 8(f) row 2 — against th
 import numpy as np
 import pytest
 
-import os
-
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SSLPL_TEST_PROJECTION") != "1",
-                                 reason="SURVEY 8(f) row 2 kernel written without GPU access; enable with SSLPL_TEST_PROJECTION=1")]
+pytestmark = pytest.mark.gpu
 
 
 def scenario(oracle, synth, seed, n_claimed=0.05, p_valid=0.85, p_obs=0.9, stereo=False, f0=0):

@@ -5,9 +5,6 @@ TAG=${1:-r1}
 mkdir -p gpurun_out
 cd /root/repo
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -6
-echo "== pytest -m gpu, opt-in kernels"; SSLPL_TEST_PIPE=1 SSLPL_TEST_PROJECTION=1 timeout 600 python -m pytest tests/test_orb_gpu.py tests/test_projection_gpu.py -m gpu -q 2>&1 | tail -12
-echo "== bench with SSLPL_PIPE=1"; SSLPL_PIPE=1 timeout 300 python bench.py --steps 20 --no-cpu-baseline > gpurun_out/bench_pipe_${TAG}.json 2> gpurun_out/bench_pipe_${TAG}.err; python -c "
-import json; d=json.loads(open('gpurun_out/bench_pipe_${TAG}.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['e2e']['ms_per_step'], {k:round(v,2) for k,v in d['roofline']['stage_ms'].items()})"
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 echo "== bench"; timeout 900 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; tail -c 600 gpurun_out/bench_${TAG}.json; tail -3 gpurun_out/bench_${TAG}.err | cut -c1-300
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2>&1; tail -c 900 gpurun_out/bench_ref_${TAG}.json
