@@ -194,6 +194,13 @@ int  sslpl_search_by_projection_frame(sslpl_matcher* m,
         const uint8_t* claimed2, const float* Tcw, const float* Tlw, const float* cam, const float* bounds,
         const float* scaleFactors, int nlevels, float th, int bMono, int checkOrientation, int32_t* assign2, int* nmatches);
 
+/* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-312) / MapLine::ComputeDistinctiveDescriptors (MapLine.cpp:246-317),
+   batched: group g owns descriptors desc[off[g] .. off[g+1]) (HOST buffers, off[0] = 0);
+   best_idx[g] = index inside the group of the descriptor with the least median Hamming distance to the others (median =
+   sorted[int(0.5 (N - 1))], first minimum wins; -1 for an empty group), best_median[g] = that median. */
+int  sslpl_descriptor_medoid_batch(sslpl_matcher* m, const uint8_t* desc, const int32_t* off, int ngroups,
+                                   int32_t* best_idx, int32_t* best_median);
+
 /* ---- DBoW2 vocabulary: Frame::ComputeBoW / KeyFrame::ComputeBoW (Frame.cc:474-481, KeyFrame.cc:71-80), i.e.
    TemplatedVocabulary<FORB>::transform(features, BowVector&, FeatureVector&, levelsup = 4)
    (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1259).  SURVEY.md 8(f) row 1. ---- */

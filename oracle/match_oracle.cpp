@@ -299,6 +299,27 @@ extern "C" int orc_search_by_projection_frame(
     return nmatches;
 }
 
+/* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-312) and MapLine::ComputeDistinctiveDescriptors
+   (MapLine.cpp:246-317): for each group of observed descriptors, the one with the least MEDIAN Hamming distance to the rest
+   (median = sorted[int(0.5 * (N - 1))], first minimum wins).  Groups in CSR form: off[g] .. off[g+1]. */
+extern "C" void orc_descriptor_medoid(const uint8_t* desc, const int32_t* off, int ngroups, int32_t* best_idx, int32_t* best_median) {
+    std::vector<int> row;
+    for (int g = 0; g < ngroups; g++) {
+        const int b = off[g], N = off[g + 1] - b;
+        best_idx[g] = N > 0 ? 0 : -1; best_median[g] = -1;
+        if (N <= 0) continue;
+        int BestMedian = 0x7fffffff, BestIdx = 0;
+        for (int i = 0; i < N; i++) {
+            row.assign(N, 0);
+            for (int j = 0; j < N; j++) row[j] = i == j ? 0 : orc_descriptor_distance(desc + 32 * (size_t)(b + i), desc + 32 * (size_t)(b + j));
+            std::sort(row.begin(), row.end());
+            const int median = row[(size_t)(0.5 * (N - 1))];
+            if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+        }
+        best_idx[g] = BestIdx; best_median[g] = BestMedian;
+    }
+}
+
 /* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) — ORBmatcher.cc:525-658 */
 extern "C" int orc_search_by_bow_kf(const uint8_t* d1, int n1, const uint8_t* d2, int n2,
                                     const int32_t* nodes1, const int32_t* off1, const int32_t* idx1, int nn1,

@@ -66,6 +66,8 @@ void  orc_bow_assign(const uint8_t* desc, int n, const uint8_t* centroids, int n
 int   orc_vocab_transform(int L, int nnodes, const int32_t* parent, const uint8_t* ndesc, const double* weight,
                           const uint8_t* is_leaf, const uint8_t* feats, int n, int levelsup,
                           int32_t* word, int32_t* node, double* w);
+/* MapPoint / MapLine ::ComputeDistinctiveDescriptors (MapPoint.cc:247-312, MapLine.cpp:246-317) for CSR groups of descriptors */
+void  orc_descriptor_medoid(const uint8_t* desc, const int32_t* off, int ngroups, int32_t* best_idx, int32_t* best_median);
 /* SearchByBoW(KeyFrame*,Frame&) ORBmatcher.cc:159-291. FeatureVectors in CSR (node ids ascending).
    valid1[i]!=0 <=> KF feature i has a good MapPoint. match2[j] = KF index matched to frame feature j or -1. */
 int   orc_search_by_bow(const uint8_t* d1, int n1, const uint8_t* d2, int n2,

@@ -236,6 +236,15 @@ def features_in_area(kx, ky, oct, bounds, x, y, r, min_level=-1, max_level=-1):
     return out[:n]
 
 
+def descriptor_medoid(desc, off):
+    """ComputeDistinctiveDescriptors (MapPoint.cc:247-312) for CSR groups: (best index inside each group, its median distance)."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); off = np.ascontiguousarray(off, np.int32)
+    ng = len(off) - 1
+    bi = np.empty(max(ng, 1), np.int32); bm = np.empty(max(ng, 1), np.int32)
+    lib().orc_descriptor_medoid(_p(desc), _p(off), ng, _p(bi), _p(bm))
+    return bi[:ng], bm[:ng]
+
+
 def feature_vector_csr(node):
     """DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>, FeatureVector.cpp:31-45) flattened to CSR:
     node ids ascending, feature indices ascending inside a node."""

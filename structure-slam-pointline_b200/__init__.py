@@ -362,6 +362,14 @@ class Matcher:
                                                       _p(out), C.byref(nm)))
         return nm.value, out[:n2]
 
+    def descriptor_medoid(self, desc, off):
+        """ComputeDistinctiveDescriptors (MapPoint.cc:247-312 / MapLine.cpp:246-317) for CSR groups of descriptors."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); off = np.ascontiguousarray(off, np.int32)
+        ng = len(off) - 1
+        bi = np.empty(max(ng, 1), np.int32); bm = np.empty(max(ng, 1), np.int32)
+        _check(lib().sslpl_descriptor_medoid_batch(self._h, _p(desc), _p(off), ng, _p(bi), _p(bm)))
+        return bi[:ng], bm[:ng]
+
     def match_lines_batch_device(self, d_ldesc, d_nl, nframes, capl, d_lmatch, d_nlmatch):
         _check(lib().sslpl_match_lines_batch_device(self._h, C.c_void_p(d_ldesc), C.c_void_p(d_nl), nframes, capl,
                                                     C.c_void_p(d_lmatch), C.c_void_p(d_nlmatch)))

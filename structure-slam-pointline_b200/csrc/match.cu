@@ -441,6 +441,46 @@ __global__ void __launch_bounds__(32) k_proj_match(const __grid_constant__ ProjA
     if (lane == 0) *nmatch = nmatches;
 }
 
+// -------------------------------------------------------------------------------------------------
+// MapPoint / MapLine ::ComputeDistinctiveDescriptors (MapPoint.cc:247-312, MapLine.cpp:246-317), batched over groups of
+// observed descriptors (CSR): the descriptor with the least median Hamming distance to the others, first minimum wins.
+// One CTA per group, one thread per row; the median of a row (rank r = int(0.5 (N-1)) of N distances in 0..256) is found by
+// bisection on the value with count(d <= v) (8 passes over the row, descriptors stay in L1) — no sort, no per-thread arrays.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_medoid(const uint8_t* desc, const int32_t* off, int32_t* best_idx, int32_t* best_median) {
+    __shared__ unsigned s_best;
+    const int gI = blockIdx.x, b = off[gI], N = off[gI + 1] - b;
+    if (threadIdx.x == 0) s_best = 0xffffffffu;
+    __syncthreads();
+    if (N > 0) {
+        const int r = (int)(0.5 * (double)(N - 1));
+        unsigned mine = 0xffffffffu;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            uint4 a0, a1;
+            load_desc(desc + (long long)(b + i) * 32, a0, a1);
+            int lo = 0, hi = 256;                                        // smallest v with count(d <= v) >= r + 1
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                int cnt = 0;
+                for (int j = 0; j < N; j++) {
+                    uint4 b0, b1;
+                    load_desc(desc + (long long)(b + j) * 32, b0, b1);
+                    cnt += (j == i ? 0 : popc256(a0, a1, b0, b1)) <= mid;
+                }
+                if (cnt >= r + 1) hi = mid; else lo = mid + 1;
+            }
+            const unsigned key = ((unsigned)lo << 20) | (unsigned)i;     // (median, row): the minimum is the first least median
+            mine = min(mine, key);
+        }
+        atomicMin(&s_best, mine);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        best_idx[gI] = N > 0 ? (int)(s_best & 0xfffffu) : -1;
+        best_median[gI] = N > 0 ? (int)(s_best >> 20) : -1;
+    }
+}
+
 // Rotation-histogram filter (ComputeThreeMaxima, ORBmatcher.cc:1604-1645; application :270-288) and match
 // count, one CTA per pair.  compact != 0 additionally writes the (i, out[i]) pairs in ascending i (:818-823).
 __global__ void __launch_bounds__(256) k_rot_filter(int32_t* out, long long out_fs, const uint8_t* rot, long long rot_fs,
@@ -530,6 +570,7 @@ struct sslpl_matcher {
     uint8_t* desc; int* nodes; int* off; int* idx; uint8_t* flag; float* kpf; int* nn2; int* ncnt;
     int32_t* out; uint8_t* rot; uint8_t* taken; int32_t* pairs; int32_t* nmatch; int32_t* knn; uint8_t* cent; int32_t* node;
     int32_t* word; double* wgt;      // per-feature outputs of the vocabulary transform (single-call staging)
+    uint8_t* scratch = nullptr; size_t scratch_size = 0;   // grow-only scratch of sslpl_descriptor_medoid_batch
     // batch workspace
     int32_t* b_node; int* b_off; int* b_idx; uint8_t* b_rot; uint8_t* b_taken; int32_t* b_knn; int* iota;
     int32_t* h_small = nullptr;      // pinned scratch
@@ -708,6 +749,7 @@ void sslpl_matcher_destroy(sslpl_matcher* m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->arena) cudaFree(m->arena);
+    if (m->scratch) cudaFree(m->scratch);
     if (m->h_small) cudaFreeHost(m->h_small);
     delete m;
 }
@@ -968,6 +1010,38 @@ int sslpl_search_by_projection_frame(sslpl_matcher* m,
 
 // Frame::GetFeaturesInArea on its own (Frame.cc:368-421) is host logic over the same CSR; the matcher above is its only
 // device consumer.  (The per-frame grid build is k_grid_cells + k_build_csr.)
+
+// ---------------- descriptor medoids ----------------
+int sslpl_descriptor_medoid_batch(sslpl_matcher* m, const uint8_t* desc, const int32_t* off, int ngroups, int32_t* best_idx, int32_t* best_median) {
+    SSLPL_REQUIRE(m && off && ngroups >= 0 && (ngroups == 0 || (best_idx && best_median)), SSLPL_ERR_ARG, "null argument");
+    if (ngroups == 0) return SSLPL_OK;
+    const int total = off[ngroups];
+    SSLPL_REQUIRE(off[0] == 0 && total >= 0 && (total == 0 || desc), SSLPL_ERR_ARG, "bad group offsets");
+    for (int g = 0; g < ngroups; g++) SSLPL_REQUIRE(off[g + 1] >= off[g] && off[g + 1] - off[g] < (1 << 20), SSLPL_ERR_ARG, "group offsets must be non-decreasing (groups < 2^20 rows)");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    const size_t need = align_up((size_t)total * 32 + 256, 256) + align_up(sizeof(int32_t) * (size_t)(ngroups + 1), 256) + 2 * align_up(sizeof(int32_t) * (size_t)ngroups, 256);
+    if (need > m->scratch_size) {                                        // grow-only scratch of this entry point
+        SSLPL_CUDA(cudaStreamSynchronize(st));
+        if (m->scratch) cudaFree(m->scratch);
+        m->scratch = nullptr; m->scratch_size = 0;
+        cudaError_t e = cudaMalloc(&m->scratch, need);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); return SSLPL_ERR_CUDA; }
+        m->scratch_size = need;
+    }
+    Arena A; A.base = m->scratch; A.used = 0;
+    uint8_t* d_desc = A.take<uint8_t>((size_t)total * 32 + 32); int32_t* d_off = A.take<int32_t>(ngroups + 1);
+    int32_t* d_bi = A.take<int32_t>(ngroups); int32_t* d_bm = A.take<int32_t>(ngroups);
+    if (total) SSLPL_CUDA(cudaMemcpyAsync(d_desc, desc, (size_t)total * 32, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(d_off, off, sizeof(int32_t) * (ngroups + 1), cudaMemcpyHostToDevice, st));
+    k_medoid<<<ngroups, 128, 0, st>>>(d_desc, d_off, d_bi, d_bm);
+    m->launches++;
+    SSLPL_CUDA(cudaGetLastError());
+    SSLPL_CUDA(cudaMemcpyAsync(best_idx, d_bi, sizeof(int32_t) * ngroups, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaMemcpyAsync(best_median, d_bm, sizeof(int32_t) * ngroups, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    return SSLPL_OK;
+}
 
 // ---------------- DBoW2 vocabulary ----------------
 static int vocab_level_nodes(const sslpl_vocab* v, int levelsup) {

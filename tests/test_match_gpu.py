@@ -126,3 +126,25 @@ def test_line_matchers(pkg, oracle):
         assert lm.last_mad == oracle.line_mad(oracle.knn2(d1, d2))
     with pytest.raises(pkg.SslplError):          # < 2 train rows: reference reads out of bounds -> explicit error
         lm.SerachForInitialize(d1, d2[:1])
+
+
+def test_descriptor_medoid_batch(pkg, oracle):
+    """MapPoint / MapLine ::ComputeDistinctiveDescriptors (MapPoint.cc:247-312): least-median descriptor per group, with
+    duplicate rows (ties -> first), singleton and empty groups."""
+    rng = np.random.default_rng(17)
+    sizes = [1, 2, 3, 0, 7, 20, 64, 150, 5, 0, 33]
+    groups = []
+    for nrows in sizes:
+        base = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+        g = np.repeat(base, nrows, 0)
+        flip = rng.random(g.shape) < 0.08
+        g[flip] ^= (1 << rng.integers(0, 8, int(flip.sum()))).astype(np.uint8)
+        if nrows > 4:
+            g[3] = g[1]                                  # exact duplicates => equal medians => the first must win
+        groups.append(g)
+    desc = np.concatenate(groups) if sum(sizes) else np.zeros((0, 32), np.uint8)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    bi_o, bm_o = oracle.descriptor_medoid(desc, off)
+    bi_g, bm_g = pkg.Matcher().descriptor_medoid(desc, off)
+    assert np.array_equal(bi_g, bi_o) and np.array_equal(bm_g, bm_o)
+    assert bi_o[3] == -1 and bi_o[0] == 0
