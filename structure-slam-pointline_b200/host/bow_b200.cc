@@ -7,8 +7,8 @@
 // DBoW2::TemplatedVocabulary are protected, so the device copy is loaded from the same text file: add ONE line after
 // System.cc:65 (`mpVocabulary->loadFromTextFile(strVocFile)`):
 //     StructureSLAM::SslplSetVocabularyFile(strVocFile);
-// Until that call (or for vocabularies that are not L1 / TF-IDF, the ORBvoc.txt defaults) ComputeBoW falls back to the
-// vocabulary object the caller already holds — that is the reference's own code path, not a re-implementation.
+// There is no CPU fallback: ComputeBoW throws until that call has been made, and for vocabularies that are not L1 / TF-IDF
+// (the ORBvoc.txt defaults "10 6 0 0"), whose BowVector arithmetic this adapter does not restate.
 //
 // The device returns (word, node, weight) per feature; the BowVector / FeatureVector are then filled with DBoW2's OWN
 // addWeight / addFeature / normalize in feature order, exactly as transform() does (:1150-1170, :1194), so the two maps
@@ -41,14 +41,14 @@ struct BowCtx {
 };
 sslpl_matcher* Ctx() { static thread_local BowCtx c; return c.h; }     // Tracking and LocalMapping threads both call ComputeBoW
 
-// returns false when the device vocabulary is not available / not applicable: the caller then uses the CPU vocabulary
-bool TransformOnDevice(const cv::Mat &descriptors, DBoW2::BowVector &bow, DBoW2::FeatureVector &fv, int levelsup)
+void TransformOnDevice(const cv::Mat &descriptors, DBoW2::BowVector &bow, DBoW2::FeatureVector &fv, int levelsup)
 {
     VocabCtx &V = Voc();
-    if(!V.v || V.scoring != 0 /* L1_NORM */ || V.weighting != 0 /* TF_IDF */) return false;
+    if(!V.v) throw std::runtime_error("libsslpl_b200: call StructureSLAM::SslplSetVocabularyFile(strVocFile) after loading the vocabulary (no CPU fallback)");
+    if(V.scoring != 0 /* L1_NORM */ || V.weighting != 0 /* TF_IDF */) throw std::runtime_error("libsslpl_b200: only L1 / TF-IDF vocabularies (ORBvoc.txt) are supported");
     const int n = descriptors.rows;
     bow.clear(); fv.clear();
-    if(n == 0) return true;
+    if(n == 0) return;
     cv::Mat d = descriptors.isContinuous() ? descriptors : descriptors.clone();
     std::vector<int32_t> word(n), node(n); std::vector<double> w(n);
     if(sslpl_bow_transform(Ctx(), V.v, d.ptr<uchar>(), n, levelsup, &word[0], &node[0], &w[0]) != SSLPL_OK)
@@ -59,7 +59,6 @@ bool TransformOnDevice(const cv::Mat &descriptors, DBoW2::BowVector &bow, DBoW2:
             fv.addFeature((DBoW2::NodeId)node[i], (unsigned int)i);
         }
     bow.normalize(DBoW2::L1);                                            // L1 scoring always normalises (:1194)
-    return true;
 }
 }
 
@@ -76,11 +75,7 @@ void Frame::ComputeBoW()                                                 // Fram
 {
     if(mBowVec.empty())
     {
-        if(!TransformOnDevice(mDescriptors, mBowVec, mFeatVec, 4))
-        {
-            vector<cv::Mat> vCurrentDesc = Converter::toDescriptorVector(mDescriptors);
-            mpORBvocabulary->transform(vCurrentDesc,mBowVec,mFeatVec,4);
-        }
+        TransformOnDevice(mDescriptors, mBowVec, mFeatVec, 4);
     }
 }
 
@@ -88,11 +83,7 @@ void KeyFrame::ComputeBoW()                                              // KeyF
 {
     if(mBowVec.empty() || mFeatVec.empty())
     {
-        if(!TransformOnDevice(mDescriptors, mBowVec, mFeatVec, 4))
-        {
-            vector<cv::Mat> vCurrentDesc = Converter::toDescriptorVector(mDescriptors);
-            mpORBvocabulary->transform(vCurrentDesc,mBowVec,mFeatVec,4);
-        }
+        TransformOnDevice(mDescriptors, mBowVec, mFeatVec, 4);
     }
 }
 
