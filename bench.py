@@ -97,7 +97,7 @@ def run_reference(args, cfg):
     import synth
     cores = os.cpu_count() or 1
     voc = synth.vocabulary(NWORDS)
-    nsample = min(cfg["frames_per_gpu"] + 1, max(9, 2 * cores + 1))
+    nsample = min(cfg["frames_per_gpu"] + 1, max(9, 4 * cores + 1))      # >= 4 frames per host thread: less tail imbalance
     frames = gen_frames(cfg, 0, 1)[0][:nsample]
     for _ in range(args.warmup):
         cpu_step(O, cfg, frames[:min(len(frames), cores + 1)], voc, cores)
@@ -524,7 +524,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         O = g.load_oracle()
         cores = os.cpu_count() or 1
-        ns = min(B, max(9, 2 * cores + 1))
+        ns = min(B, max(9, 4 * cores + 1))              # >= 4 frames per host thread: less tail imbalance
         cpu_step(O, cfg, sets[0][:min(ns, cores + 1)], voc, cores, LINES)
         best = None
         for _ in range(2):
