@@ -50,6 +50,9 @@ void  orc_orb_level_copy(const orc_orb*, int level, int bordered, uint8_t* dst, 
 void  orc_orb_blur_copy(const orc_orb*, int level, uint8_t* dst, int dpitch);
 int   orc_orb_candidates(const orc_orb*, int level, int* xs, int* ys, int* resp, int cap);
 int   orc_orb_level_keypoints(const orc_orb*, int level, int* xs, int* ys, int* resp, float* angle, int cap);
+/* stage-level entry points (IC_Angle :77-104 on an un-blurred image; computeOrbDescriptor :107-147 on an already blurred one) */
+void  orc_ic_angles(const orc_orb*, const uint8_t* img, int w, int h, int pitch, const int* xs, const int* ys, int n, float* angles);
+void  orc_brief_descriptors(const uint8_t* blurred, int w, int h, int pitch, const int* xs, const int* ys, const float* angles, int n, uint8_t* desc);
 /* per-stage wall times (ms) of the last extract call: pyramid, fast, octree, orient, blur, brief */
 void  orc_orb_stage_ms(const orc_orb*, double* ms6);
 /* DistributeOctTree alone (ORBextractor.cc:539-763) with the canonical (size,counter) tie rule */

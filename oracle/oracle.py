@@ -110,6 +110,22 @@ class OrbOracle:
         self.nfeatures = nfeatures
         self.h = C.c_void_p(lib().orc_orb_create(nfeatures, scale_factor, nlevels, ini_th, min_th))
 
+    def ic_angles(self, img, xs, ys):
+        """IC_Angle (ORBextractor.cc:77-104) at integer positions of an un-blurred image."""
+        img = _u8(img); xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32)
+        out = np.empty(max(len(xs), 1), np.float32)
+        lib().orc_ic_angles(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(xs), _p(ys), len(xs), _p(out))
+        return out[:len(xs)]
+
+    @staticmethod
+    def brief_descriptors(blurred, xs, ys, angles):
+        """computeOrbDescriptor (ORBextractor.cc:107-147) at integer positions of an ALREADY blurred image."""
+        blurred = _u8(blurred); xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32)
+        angles = np.ascontiguousarray(angles, np.float32)
+        out = np.empty((max(len(xs), 1), 32), np.uint8)
+        lib().orc_brief_descriptors(_p(blurred), blurred.shape[1], blurred.shape[0], blurred.strides[0], _p(xs), _p(ys), _p(angles), len(xs), _p(out))
+        return out[:len(xs)]
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().orc_orb_destroy(self.h)

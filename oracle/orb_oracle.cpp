@@ -428,6 +428,19 @@ void orb_descriptor(float kp_angle, const uchar* center, int step, uchar* desc) 
 
 }  // namespace
 
+/* Stage-level entry points so that IC_Angle and the rBRIEF arithmetic can be pinned against cv2.ORB on level 0
+   (tests/test_oracle_cpu.py): orientation of given integer pixel positions on an un-blurred image, and descriptors of given
+   (position, angle) on an ALREADY blurred image.  Positions must keep 19 px from the image border, as the extractor's do. */
+extern "C" void orc_ic_angles(const orc_orb* o, const uchar* img, int w, int h, int pitch, const int* xs, const int* ys, int n, float* angles) {
+    (void)w; (void)h;
+    for (int i = 0; i < n; i++) angles[i] = ic_angle(img + (ptrdiff_t)ys[i] * pitch + xs[i], pitch, o->umax);
+}
+extern "C" void orc_brief_descriptors(const uchar* blurred, int w, int h, int pitch, const int* xs, const int* ys, const float* angles,
+                                      int n, uchar* desc) {
+    (void)w; (void)h;
+    for (int i = 0; i < n; i++) orb_descriptor(angles[i], blurred + (ptrdiff_t)ys[i] * pitch + xs[i], pitch, desc + 32 * (size_t)i);
+}
+
 /* ORBextractor::operator() — ORBextractor.cc:1043-1105 (+ ComputePyramid :1107-1132,
    ComputeKeyPointsOctTree :765-853) */
 extern "C" int orc_orb_extract(orc_orb* o, const uchar* img, int w, int h, int pitch,

@@ -59,6 +59,29 @@ def test_fast_atan2_matches_cv2(oracle):
         assert oracle.fast_atan2(y, x) == np.float32(cv2.fastAtan2(float(y), float(x))), (y, x)
 
 
+def test_ic_angle_and_rbrief_match_cv2_orb(oracle, icl_gray, synth):
+    """IC_Angle (ORBextractor.cc:77-104) and computeOrbDescriptor (:107-147) were copied into ORB-SLAM2 from OpenCV's ORB, and
+    cv2.ORB still evaluates the same formulas on its level 0: feed cv2's own keypoints (integer positions at nlevels = 1) through
+    the oracle's stage entry points and demand bit-equal angles and descriptors.  cv2.ORB blurs a SUBMATRIX of its pyramid buffer,
+    which makes cv::GaussianBlur take its filter-engine path instead of the bit-exact fixed-point one; a float blur rounded to
+    8 bits reproduces that path, and the descriptor stage is handed that image."""
+    total = 0
+    for im in (icl_gray, synth.frame(640, 480, 3), synth.frame(1280, 960, 1)):
+        orb = cv2.ORB_create(nfeatures=3000, scaleFactor=1.2, nlevels=1, edgeThreshold=19, firstLevel=0, WTA_K=2,
+                             scoreType=cv2.ORB_FAST_SCORE, patchSize=31, fastThreshold=20)
+        kps, desc = orb.detectAndCompute(im, None)
+        xs = np.array([kp.pt[0] for kp in kps]); ys = np.array([kp.pt[1] for kp in kps])
+        ang = np.array([kp.angle for kp in kps], np.float32)
+        assert len(kps) > 300 and np.all(xs == np.rint(xs)) and np.all(ys == np.rint(ys))
+        xi, yi = xs.astype(np.int32), ys.astype(np.int32)
+        o = oracle.OrbOracle(1000, 1.2, 8, 20, 7)
+        assert np.array_equal(o.ic_angles(im, xi, yi), ang)
+        blur = np.clip(np.rint(cv2.GaussianBlur(im.astype(np.float32), (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)), 0, 255).astype(np.uint8)
+        assert np.array_equal(oracle.OrbOracle.brief_descriptors(blur, xi, yi, ang), desc)
+        total += len(kps)
+    assert total > 3000
+
+
 def test_knn2_matches_bfmatcher(oracle):
     rng = np.random.default_rng(2)
     bf = cv2.BFMatcher(cv2.NORM_HAMMING, False)
