@@ -84,3 +84,19 @@ def test_extract_line_segment_packaging(oracle, icl_gray):
     # a flat image has no lines
     kl4, ld4, eq4 = oracle.LineOracle(40).extract(np.full((240, 320), 90, np.uint8))
     assert len(kl4) == 0
+
+
+def test_num_of_pixels_is_the_8_connected_line_iterator_count(oracle, icl_gray):
+    """KeyLine.numOfPixels = cv::LineIterator(start, end).count (line_descriptor LSDDetector::detectImpl): for the default
+    8-connected iterator that is max(|dx|, |dy|) + 1 of the ROUNDED end points.  cv2 has no LineIterator binding, but cv2.line
+    draws exactly the iterator's pixels: check the closed form against it, then the oracle's KeyLines against the closed form."""
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        a = rng.integers(0, 200, 2); b = rng.integers(0, 200, 2)
+        img = np.zeros((200, 200), np.uint8)
+        cv2.line(img, (int(a[0]), int(a[1])), (int(b[0]), int(b[1])), 255, 1, cv2.LINE_8)
+        assert int((img > 0).sum()) == max(abs(int(b[0] - a[0])), abs(int(b[1] - a[1]))) + 1
+    kl, _, _ = oracle.LineOracle(1 << 20).extract(icl_gray)
+    r = lambda v: np.rint(v).astype(np.int64)                       # cv::Point(Point2f) rounds half to even, like np.rint
+    exp = np.maximum(np.abs(r(kl["endPointX"]) - r(kl["startPointX"])), np.abs(r(kl["endPointY"]) - r(kl["startPointY"]))) + 1
+    assert len(kl) > 100 and np.array_equal(kl["numOfPixels"], exp)
