@@ -6,6 +6,9 @@
  *   (1) ORBextractor::operator()            reference: include/ORBextractor.h:45-111, src/ORBextractor.cc:1043
  *   (2) LineSegment::ExtractLineSegment     reference: include/ExtractLineSegment.h:53-76, src/ExtractLineSegment.cpp:18
  *   (3) ORBmatcher / LSDmatcher Hamming     reference: include/ORBmatcher.h:36-101, include/LSDmatcher.h:36-64
+ * and, widened after those met the parity + measurement bar (SURVEY.md 8(f) "next" rows 1-3): the DBoW2 vocabulary transform of
+ * Frame::ComputeBoW, ORBmatcher::SearchByProjection(Frame&, const Frame&, ...) with the Frame feature grid, and the descriptor
+ * medoid of MapPoint / MapLine ::ComputeDistinctiveDescriptors.
  * The reference has no FFI; its boundary is the C++ class surface.  The adapters in
  * structure-slam-pointline_b200/host/ re-expose those class signatures on top of this ABI
  * (see INTEGRATION.md).  Plain pointers and sizes only; no torch / OpenCV types.
