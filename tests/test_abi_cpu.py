@@ -88,3 +88,19 @@ def test_orbextractor_adapter_compiles_against_shim():
                 "void operator()( cv::InputArray image, cv::InputArray mask,", "std::vector<cv::Mat> mvImagePyramid;",
                 "GetScaleFactors()", "GetInverseScaleSigmaSquares()"]:
         assert sig in hdr, sig
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/sslpl.h is the C-ABI boundary: it must compile as C (not only C++), and a C program must link against the library."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "sslpl.h"\nint main(void) { return (sslpl_version() > 0 && sslpl_device_count() >= 0) ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = tmp_path / "abi"
+    lib = os.path.join(ROOT, "structure-slam-pointline_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", lib, "-lsslpl_b200",
+                        "-Wl,-rpath," + lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
