@@ -30,8 +30,16 @@ struct Mat {
     const uchar* ptr(int i = 0) const { return data + (size_t)i * step; }
     template <class T> T* ptr(int i = 0) { return (T*)(data + (size_t)i * step); }
     template <class T> const T* ptr(int i = 0) const { return (const T*)(data + (size_t)i * step); }
+    template <class T> T& at(int i) { return ((T*)data)[i]; }
+    template <class T> const T& at(int i) const { return ((const T*)data)[i]; }
+    template <class T> T& at(int r, int c) { return ((T*)(data + (size_t)r * step))[c]; }
+    template <class T> const T& at(int r, int c) const { return ((const T*)(data + (size_t)r * step))[c]; }
+    Mat row(int i) const { Mat m; m.rows = 1; m.cols = cols; m.step = step; m.data = data + (size_t)i * step; return m; }
+    bool isContinuous() const { return step == (size_t)cols; }
+    Mat clone() const { return *this; }
     Mat operator()(const Rect& r) const { Mat m; m.rows = r.height; m.cols = r.width; m.step = step; m.data = data + (size_t)r.y * step + r.x; return m; }
 };
+Mat operator*(const Mat& a, const Mat& b); Mat operator+(const Mat& a, const Mat& b);   // declared only (type check)
 struct _InputArray { const Mat* m; _InputArray(const Mat& a) : m(&a) {} _InputArray() : m(0) {} bool empty() const { return !m || m->empty(); } Mat getMat() const { return *m; } };
 struct _OutputArray { Mat* m; _OutputArray(Mat& a) : m(&a) {} void create(int r, int c, int t) const { m->create(r, c, t); } void release() const { m->release(); } Mat getMat() const { return *m; } };
 typedef const _InputArray& InputArray; typedef const _OutputArray& OutputArray;

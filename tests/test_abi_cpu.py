@@ -77,8 +77,8 @@ def test_feature_vector_csr_matches_oracle_helper(pkg, oracle):
 
 def test_orbextractor_adapter_compiles_against_shim():
     """host/ORBextractor.{h,cc} (the reference's class signature over the C ABI) type-checks against the minimal OpenCV
-    shim in host/shim (no OpenCV C++ in this image).  The two adapters that include the reference's own headers
-    (ExtractLineSegment_b200.cc, matcher_b200.cc) can only be compiled inside the reference tree."""
+    shim in host/shim (no OpenCV C++ in this image).  The adapters that include the reference's own headers are checked
+    against stand-in declarations in test_reference_side_adapters_type_check below."""
     H = os.path.join(ROOT, "structure-slam-pointline_b200", "host")
     r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-Wall", "-I", os.path.join(H, "shim"), "-I", H,
                         "-I", os.path.join(ROOT, "include"), os.path.join(H, "ORBextractor.cc")], capture_output=True, text=True)
@@ -104,3 +104,16 @@ def test_header_is_plain_c99(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout, r.stderr)
+
+
+def test_reference_side_adapters_type_check():
+    """host/{matcher_b200,bow_b200,ExtractLineSegment_b200}.cc include the REFERENCE's headers (ORBmatcher.h, LSDmatcher.h, Frame.h,
+    KeyFrame.h, ExtractLineSegment.h), which cannot be compiled here (OpenCV C++, Eigen, DBoW2, g2o, Pangolin).  tests/refshim holds
+    stand-in declarations of exactly the members the adapters touch (written from the cited header lines): compiling against them
+    type-checks the adapters themselves and every sslpl_* call they make (argument count, order and types)."""
+    H = os.path.join(ROOT, "structure-slam-pointline_b200", "host")
+    inc = ["-I", os.path.join(ROOT, "tests", "refshim"), "-I", os.path.join(H, "shim"), "-I", os.path.join(H, "shim", "eigen3"),
+           "-I", os.path.join(ROOT, "include")]
+    for f in ("matcher_b200.cc", "bow_b200.cc", "ExtractLineSegment_b200.cc"):
+        r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-Wall"] + inc + [os.path.join(H, f)], capture_output=True, text=True)
+        assert r.returncode == 0 and "warning" not in r.stderr, (f, r.stderr[-3000:])
