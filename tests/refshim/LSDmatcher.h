@@ -1,21 +1,16 @@
-// stand-in for include/LSDmatcher.h:36-64
+// Stand-in for the reference's include/LSDmatcher.h (lines 36-64): only the entry points host/matcher_b200.cc defines, with the
+// reference's parameter TYPES (names and layout are this file's own).  Compile-check use only, see README.md here.
 #pragma once
 #include <vector>
-#include "MapLine.h"
-#include "KeyFrame.h"
 #include "Frame.h"
-namespace StructureSLAM {
-class LSDmatcher {
-public:
-    LSDmatcher(float nnratio=0.6, bool checkOri=true);
-    int SearchByDescriptor(KeyFrame* pKF, Frame &currentF, std::vector<MapLine*> &vpMapLineMatches);
-    int SearchByDescriptor(KeyFrame* pKF, KeyFrame *pKF2, std::vector<MapLine*> &vpMapLineMatches);
-    int SearchByProjection(KeyFrame* pKF,Frame &currentF, vector<MapLine*> &vpMapLineMatches);
-    int SerachForInitialize(Frame &InitialFrame, Frame &CurrentFrame, std::vector<std::pair<int,int> > &LineMatches);
-    int SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<std::pair<size_t, size_t> > &vMatchedPairs);
-    static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
-protected:
-    float mfNNratio;
-    bool mbCheckOrientation;
-};
-}
+#include "KeyFrame.h"
+#include "MapLine.h"
+namespace StructureSLAM { class LSDmatcher { public:
+    LSDmatcher(float ratio = 0.6, bool orientation = true);
+    static int DescriptorDistance(const cv::Mat& first, const cv::Mat& second);
+    int SearchByDescriptor(KeyFrame* kf, Frame& frame, std::vector<MapLine*>& out);
+    int SearchByDescriptor(KeyFrame* kf_a, KeyFrame* kf_b, std::vector<MapLine*>& out);
+    int SearchByProjection(KeyFrame* kf, Frame& frame, vector<MapLine*>& out);
+    int SerachForInitialize(Frame& first, Frame& second, std::vector<std::pair<int, int> >& out);
+    int SearchForTriangulation(KeyFrame* kf_a, KeyFrame* kf_b, std::vector<std::pair<size_t, size_t> >& out);
+  protected: float mfNNratio; bool mbCheckOrientation; }; }
