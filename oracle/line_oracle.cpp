@@ -503,32 +503,58 @@ extern "C" void orc_lbd_prep(const uchar* img, int w, int h, int pitch, int16_t*
     sobel3(blur.data(), w, h, w, dx, dy);
 }
 
-/* LineSegment::ExtractLineSegment — ExtractLineSegment.cpp:18-69 (scale=1, numOctaves=1) */
-extern "C" int orc_line_extract(orc_line* o, const uchar* img, int w, int h, int pitch,
-                                orc_keyline* klout, uchar* ldesc, double* lineeq3, int cap) {
+/* cv::LineIterator(img, p1, p2, 8).count after cv::clipLine — imgproc drawing.cpp [memory], pinned to cv2.clipLine in
+   tests/test_line_oracle_cpu.py.  The endpoints are cvRound()ed floats in [0, lim): 639.6 rounds to 640, one past the last
+   column, and OpenCV then clips the segment to the image before counting. */
+extern "C" int orc_clip_line(int w, int h, long long* px1, long long* py1, long long* px2, long long* py2) {
+    long long &x1 = *px1, &y1 = *py1, &x2 = *px2, &y2 = *py2;
+    const long long right = w - 1, bottom = h - 1;
+    if (w <= 0 || h <= 0) return 0;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        long long a;
+        if (c1 & 12) { a = c1 < 8 ? 0 : bottom; x1 += (a - y1) * (x2 - x1) / (y2 - y1); y1 = a; c1 = (x1 < 0) + (x1 > right) * 2; }
+        if (c2 & 12) { a = c2 < 8 ? 0 : bottom; x2 += (a - y2) * (x2 - x1) / (y2 - y1); y2 = a; c2 = (x2 < 0) + (x2 > right) * 2; }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) { a = c1 == 1 ? 0 : right; y1 += (a - x1) * (y2 - y1) / (x2 - x1); x1 = a; c1 = 0; }
+            if (c2) { a = c2 == 1 ? 0 : right; y2 += (a - x2) * (y2 - y1) / (x2 - x1); x2 = a; c2 = 0; }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+extern "C" int orc_line_iterator_count(int w, int h, int ax, int ay, int bx, int by) {
+    long long x1 = ax, y1 = ay, x2 = bx, y2 = by;
+    if ((unsigned)ax >= (unsigned)w || (unsigned)bx >= (unsigned)w || (unsigned)ay >= (unsigned)h || (unsigned)by >= (unsigned)h)
+        if (!orc_clip_line(w, h, &x1, &y1, &x2, &y2)) return 0;
+    return (int)std::max(std::llabs(x2 - x1), std::llabs(y2 - y1)) + 1;
+}
+
+namespace {
+/* LSDDetector::detect(image, keylines, scale=1, numOctaves=1): cv LSD (REFINE_ADV) + KeyLine packaging
+   (line_descriptor LSDDetector.cpp [memory]); all segments, detection order */
+void detect_keylines(const uchar* img, int w, int h, int pitch, std::vector<orc_keyline>& kls, orc_line* o, double* tms) {
     double t0 = now_ms();
     // cv::LineSegmentDetector at scale 0.8: GaussianBlur(sigma 0.6/0.8, 7x7) + INTER_LINEAR_EXACT resize (lsd.cpp)
     static const int taps7[7] = {0, 4, 56, 136, 56, 4, 0};
     std::vector<uchar> blur((size_t)w * h);
     orc_sepfilter_fixed_u8(img, w, h, pitch, blur.data(), w, taps7, 7);
     const double SCALE = 0.8;
-    o->sw = cvRoundD(w * SCALE); o->sh = cvRoundD(h * SCALE);
-    o->scaled.assign((size_t)o->sw * o->sh, 0);
-    resize_linear_exact(blur.data(), w, h, w, o->scaled.data(), o->sw, o->sh, o->sw, 0.8);
+    const int sw = cvRoundD(w * SCALE), sh = cvRoundD(h * SCALE);
+    std::vector<uchar> scaled((size_t)sw * sh, 0);
+    resize_linear_exact(blur.data(), w, h, w, scaled.data(), sw, sh, sw, 0.8);
     double t1 = now_ms();
     Lsd lsd; std::vector<Rect> recs;
-    lsd.detect(o->scaled.data(), o->sw, o->sh, o->sw, recs);
-    o->trace = lsd.trace;
+    lsd.detect(scaled.data(), sw, sh, sw, recs);
     double t2 = now_ms();
-    // LSDDetector::detectImpl (line_descriptor LSDDetector.cpp) [memory]: KeyLine packaging, octave 0, scale 1
-    std::vector<orc_keyline> kls;
-    o->raw.clear();
+    if (o) { o->trace = lsd.trace; o->sw = sw; o->sh = sh; o->scaled.swap(scaled); o->raw.clear(); }
+    kls.clear();
     int class_counter = 0;
     for (Rect r : recs) {
         r.x1 += 0.5; r.y1 += 0.5; r.x2 += 0.5; r.y2 += 0.5;
         r.x1 /= SCALE; r.y1 /= SCALE; r.x2 /= SCALE; r.y2 /= SCALE;
         float e[4] = {float(r.x1), float(r.y1), float(r.x2), float(r.y2)};
-        o->raw.insert(o->raw.end(), e, e + 4);
+        if (o) o->raw.insert(o->raw.end(), e, e + 4);
         // checkLineExtremes
         for (int k = 0; k < 4; k++) {
             const int lim = (k & 1) ? h : w;
@@ -539,10 +565,8 @@ extern "C" int orc_line_extract(orc_line* o, const uchar* img, int w, int h, int
         kl.startPointX = e[0]; kl.startPointY = e[1]; kl.endPointX = e[2]; kl.endPointY = e[3];   // * octaveScale (= 1)
         kl.sPointInOctaveX = e[0]; kl.sPointInOctaveY = e[1]; kl.ePointInOctaveX = e[2]; kl.ePointInOctaveY = e[3];
         kl.lineLength = (float)sqrt(pow((double)(e[0] - e[2]), 2) + pow((double)(e[1] - e[3]), 2));
-        {   // cv::LineIterator(img, Point2f->Point (cvRound), 8-connectivity).count; endpoints are inside the image
-            const int ax = cvRoundD(e[0]), ay = cvRoundD(e[1]), bx = cvRoundD(e[2]), by = cvRoundD(e[3]);
-            kl.numOfPixels = std::max(std::abs(bx - ax), std::abs(by - ay)) + 1;
-        }
+        // cv::LineIterator(img, Point2f->Point (cvRound), 8-connectivity).count
+        kl.numOfPixels = orc_line_iterator_count(w, h, cvRoundD(e[0]), cvRoundD(e[1]), cvRoundD(e[2]), cvRoundD(e[3]));
         kl.angle = (float)atan2((double)(kl.endPointY - kl.startPointY), (double)(kl.endPointX - kl.startPointX));
         kl.class_id = class_counter++;
         kl.octave = 0;
@@ -551,6 +575,31 @@ extern "C" int orc_line_extract(orc_line* o, const uchar* img, int w, int h, int
         kl.pt_x = (kl.endPointX + kl.startPointX) / 2; kl.pt_y = (kl.endPointY + kl.startPointY) / 2;
         kls.push_back(kl);
     }
+    if (tms) { tms[0] = t1 - t0; tms[1] = t2 - t1; }
+}
+}  // namespace
+
+extern "C" int orc_lsd_keylines(const uchar* img, int w, int h, int pitch, orc_keyline* out, int cap) {
+    std::vector<orc_keyline> kls;
+    detect_keylines(img, w, h, pitch, kls, nullptr, nullptr);
+    for (int i = 0; i < (int)kls.size() && i < cap; i++) out[i] = kls[i];
+    return (int)kls.size();
+}
+
+/* BinaryDescriptor::compute(image, keylines, descriptors): GaussianBlur(5x5, 1) + Sobel, then LBD per line [memory] */
+extern "C" void orc_lbd_compute(const uchar* img, int w, int h, int pitch, const orc_keyline* kls, int n, uchar* ldesc) {
+    std::vector<int16_t> dx((size_t)w * h), dy((size_t)w * h);
+    orc_lbd_prep(img, w, h, pitch, dx.data(), dy.data());
+    for (int i = 0; i < n; i++) lbd_descriptor(kls[i], dx.data(), dy.data(), w, h, ldesc + 32 * (size_t)i);
+}
+
+/* LineSegment::ExtractLineSegment — ExtractLineSegment.cpp:18-69 (scale=1, numOctaves=1) */
+extern "C" int orc_line_extract(orc_line* o, const uchar* img, int w, int h, int pitch,
+                                orc_keyline* klout, uchar* ldesc, double* lineeq3, int cap) {
+    std::vector<orc_keyline> kls;
+    double tms[2];
+    detect_keylines(img, w, h, pitch, kls, o, tms);
+    double t2 = now_ms();
     // ExtractLineSegment.cpp:45-51: keep the lsdNFeatures strongest (stable order on exact ties: the reference's
     // std::sort is unstable)
     if ((int)kls.size() > o->nfeat) {
@@ -559,12 +608,9 @@ extern "C" int orc_line_extract(orc_line* o, const uchar* img, int w, int h, int
         for (int i = 0; i < o->nfeat; i++) kls[i].class_id = i;
     }
     double t3 = now_ms();
-    // BinaryDescriptor::compute: GaussianBlur(5x5, 1) + Sobel, then LBD per line
-    std::vector<int16_t> dx((size_t)w * h), dy((size_t)w * h);
-    orc_lbd_prep(img, w, h, pitch, dx.data(), dy.data());
-    const int n = (int)kls.size();
-    for (int i = 0; i < n && i < cap; i++) {
-        lbd_descriptor(kls[i], dx.data(), dy.data(), w, h, ldesc + 32 * (size_t)i);
+    const int n = std::min((int)kls.size(), cap);
+    orc_lbd_compute(img, w, h, pitch, kls.data(), n, ldesc);
+    for (int i = 0; i < n; i++) {
         klout[i] = kls[i];
         // line equation, ExtractLineSegment.cpp:56-68 (double cross product of f32 endpoints, normalised by |(l0,l1)|)
         const double sx = kls[i].startPointX, sy = kls[i].startPointY, ex = kls[i].endPointX, ey = kls[i].endPointY;
@@ -573,7 +619,7 @@ extern "C" int orc_line_extract(orc_line* o, const uchar* img, int w, int h, int
         lineeq3[3 * i] = l0 / nrm; lineeq3[3 * i + 1] = l1 / nrm; lineeq3[3 * i + 2] = l2 / nrm;
     }
     double t4 = now_ms();
-    o->ms[0] = t1 - t0; o->ms[1] = t2 - t1; o->ms[2] = t3 - t2; o->ms[3] = t4 - t3;
+    o->ms[0] = tms[0]; o->ms[1] = tms[1]; o->ms[2] = t3 - t2; o->ms[3] = t4 - t3;
     return n;
 }
 

@@ -107,6 +107,13 @@ orc_line* orc_line_create(int lsdNFeatures);
 void  orc_line_destroy(orc_line*);
 int   orc_line_extract(orc_line*, const uint8_t* img, int w, int h, int pitch,
                        orc_keyline* kl, uint8_t* ldesc, double* lineeq3, int cap);
+/* the two OpenCV-contrib steps on their own: LSDDetector::detect (all KeyLines, detection order; returns the count even when
+   cap is smaller) and BinaryDescriptor::compute on given KeyLines */
+int   orc_lsd_keylines(const uint8_t* img, int w, int h, int pitch, orc_keyline* out, int cap);
+void  orc_lbd_compute(const uint8_t* img, int w, int h, int pitch, const orc_keyline* kls, int n, uint8_t* ldesc);
+/* cv::clipLine on integer points (returns 0 when nothing is left) and cv::LineIterator(...,8).count */
+int   orc_clip_line(int w, int h, long long* x1, long long* y1, long long* x2, long long* y2);
+int   orc_line_iterator_count(int w, int h, int ax, int ay, int bx, int by);
 /* raw LSD segments of the last call, before the top-N cut: x1,y1,x2,y2 (f32) */
 int   orc_line_raw_segments(const orc_line*, float* seg4, int cap);
 void  orc_line_scaled_copy(const orc_line*, uint8_t* dst, int dpitch, int* w, int* h);
