@@ -6,6 +6,9 @@
  * (pinned against cv2 in tests/).  KeyFrame/Frame/MapPoint pointers of the reference
  * are replaced by indices + validity masks; DBoW2::FeatureVector (std::map<node, vector<idx>>) is
  * passed as CSR with ascending node ids (FeatureVector.cpp:31-45 keeps per-node indices ascending).
+ *
+ * PINNED: tests/test_ref_parity_cpu.py runs every function of this file against the reference's own
+ * ORBmatcher.cc / LSDmatcher.cpp / Frame.cc / MapPoint.cc / DBoW2 compiled unmodified (oracle/_ref, oracle/ref_build.sh).
  */
 #include "oracle.h"
 #include <algorithm>
@@ -178,7 +181,8 @@ extern "C" int orc_search_by_bow(const uint8_t* d1, int n1, const uint8_t* d2, i
  * Pointer state is passed as flags: valid1 = (pMP && !mvbOutlier), obs1 = pMP->Observations() > 0, claimed2 = the current
  * frame's feature already holds a MapPoint with Observations() > 0.  assign2[j] = index (into the last frame) of the
  * MapPoint written to CurrentFrame.mvpMapPoints[j], or -1.  Float arithmetic: every expression in float, no contraction;
- * Rcw*x3Dw+tcw as cv::gemm evaluates it for CV_32F (double accumulation, one rounding per element).
+ * Rcw*x3Dw+tcw as cv::gemm evaluates a plain 3x3 * 3x1 + 3x1 CV_32F product on cv2 4.13 (float products summed left to right,
+ * the addend last; tools/probe_cv_gemm.py).  Pinned against the reference itself in tests/test_ref_parity_cpu.py.
  * --------------------------------------------------------------------------------------------- */
 namespace {
 struct Grid {
@@ -241,13 +245,16 @@ extern "C" int orc_search_by_projection_frame(
     g->build(n2, x2, y2);
     std::vector<uint8_t> claimed(n2, 0);
     for (int j = 0; j < n2; j++) { assign2[j] = -1; if (claimed2) claimed[j] = claimed2[j]; }
-    /* tlc = Rlw * (-Rcw^T tcw) + tlw, only its z against mb (stereo) */
+    /* tlc = Rlw * (-Rcw^T tcw) + tlw, only its z against mb (stereo).  cv::gemm as probed on cv2 4.13 (tools/probe_cv_gemm.py,
+       oracle/refshim/minicv.cpp): a transposed operand takes the general path (double accumulation, one rounding); a plain
+       3x3 * 3x1 (+ 3x1) runs in FLOAT, products summed left to right, the addend last. */
     bool bForward = false, bBackward = false;
     if (!bMono && Tlw) {
         double twc[3];
         for (int r = 0; r < 3; r++) twc[r] = -((double)Tcw[0 * 4 + r] * Tcw[3] + (double)Tcw[1 * 4 + r] * Tcw[7] + (double)Tcw[2 * 4 + r] * Tcw[11]);
         const float twcf[3] = {(float)twc[0], (float)twc[1], (float)twc[2]};
-        const float tlcz = (float)((double)Tlw[8] * twcf[0] + (double)Tlw[9] * twcf[1] + (double)Tlw[10] * twcf[2] + (double)Tlw[11]);
+        float s = Tlw[8] * twcf[0]; s = s + Tlw[9] * twcf[1]; s = s + Tlw[10] * twcf[2];
+        const float tlcz = s + Tlw[11];
         bForward = tlcz > mb; bBackward = -tlcz > mb;
     }
     int nmatches = 0;
@@ -257,8 +264,10 @@ extern "C" int orc_search_by_projection_frame(
         if (!valid1[i]) continue;
         const float* X = Xw + 3 * (size_t)i;
         float xc3[3];
-        for (int r = 0; r < 3; r++)
-            xc3[r] = (float)((double)Tcw[4 * r] * X[0] + (double)Tcw[4 * r + 1] * X[1] + (double)Tcw[4 * r + 2] * X[2] + (double)Tcw[4 * r + 3]);
+        for (int r = 0; r < 3; r++) {                                       /* x3Dc = Rcw*x3Dw+tcw (:1364): cv::gemm float path */
+            float s = Tcw[4 * r] * X[0]; s = s + Tcw[4 * r + 1] * X[1]; s = s + Tcw[4 * r + 2] * X[2];
+            xc3[r] = s + Tcw[4 * r + 3];
+        }
         const float xc = xc3[0], yc = xc3[1];
         const float invzc = (float)(1.0 / xc3[2]);
         if (invzc < 0) continue;

@@ -117,8 +117,8 @@ def search_for_triangulation(d1, k1, d2, k2, fv1, fv2, has_mp1, has_mp2, camv, T
     return n, pairs[:n].copy(), (float(epi[0]), float(epi[1]))
 
 
-def search_by_projection_frame(last, cur, Tcw, Tlw, camv, nlevels, scale, th, mono=True, check_ori=True):
-    """last = dict(valid, obs|None, Xw[n,3], dmp[n,32], kps); cur = dict(desc, kps, claimed|None)."""
+def search_by_projection_frame(last, cur, Tcw, Tlw, camv, nlevels, scale, th, mono=True, check_ori=True, mbf=0.0):
+    """last = dict(valid, obs|None, Xw[n,3], dmp[n,32], kps); cur = dict(desc, kps, claimed|None, uright|None)."""
     v1 = np.ascontiguousarray(last["valid"], np.uint8); n1 = len(v1)
     o1 = np.ascontiguousarray(last["obs"], np.uint8) if last.get("obs") is not None else None
     Xw = _f32(last["Xw"]).reshape(-1, 3); dmp = np.ascontiguousarray(last["dmp"], np.uint8).reshape(-1, 32); k1 = _kp(last["kps"])
@@ -126,8 +126,9 @@ def search_by_projection_frame(last, cur, Tcw, Tlw, camv, nlevels, scale, th, mo
     cl = np.ascontiguousarray(cur["claimed"], np.uint8) if cur.get("claimed") is not None else None
     Tc = _f32(Tcw).reshape(-1)[:12].copy(); Tl = _f32(Tlw).reshape(-1)[:12].copy()
     out = np.full(max(n2, 1), -1, np.int32)
+    ur = _f32(cur["uright"]) if cur.get("uright") is not None else None
     n = lib().ref_search_by_projection_frame(n1, _p(v1), _p(o1) if o1 is not None else None, _p(Xw), _p(dmp), _p(k1), n2, _p(d2), _p(k2),
-                                             _p(cl) if cl is not None else None, _p(Tc), _p(Tl), _p(_f32(camv)), nlevels, C.c_float(scale),
+                                             _p(cl) if cl is not None else None, _p(ur) if ur is not None else None, C.c_float(mbf), _p(Tc), _p(Tl), _p(_f32(camv)), nlevels, C.c_float(scale),
                                              C.c_float(th), int(mono), int(check_ori), _p(out))
     return n, out[:n2]
 

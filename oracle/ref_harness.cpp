@@ -282,6 +282,7 @@ int ref_search_for_triangulation(const uint8_t* d1, int n1, const orc_keypoint* 
    holds a MapPoint with observations.  assign2[j] = index of the last-frame feature whose MapPoint was assigned, -1 none. */
 int ref_search_by_projection_frame(int n1, const uint8_t* valid1, const uint8_t* obs1, const float* Xw, const uint8_t* dmp,
                                    const orc_keypoint* k1, int n2, const uint8_t* d2, const orc_keypoint* k2, const uint8_t* claimed2,
+                                   const float* uright2, float mbf,
                                    const float* Tcw, const float* Tlw, const float* cam8, int nlevels, float scaleFactor, float th, int mono, int checkOri,
                                    int32_t* assign2) {
     Scene S;
@@ -290,6 +291,8 @@ int ref_search_by_projection_frame(int n1, const uint8_t* valid1, const uint8_t*
     Frame* L = make_frame(S, cam, nlevels, scaleFactor, k1, n1, zero.data(), nullptr, nullptr, nullptr, 0, Tlw);
     KeyFrame* KFl = make_kf(S, L);
     Frame* Cf = make_frame(S, cam, nlevels, scaleFactor, k2, n2, d2, nullptr, nullptr, nullptr, 0, Tcw);
+    Cf->mbf = mbf; Cf->mb = Cf->mbf / Frame::fx;                 // Frame.cc:128
+    if (uright2) for (int j = 0; j < n2; j++) Cf->mvuRight[j] = uright2[j];
     std::map<MapPoint*, int> index;
     for (int i = 0; i < n1; i++) if (valid1[i]) {
         MapPoint* p = make_mp(S, KFl, Xw + 3 * i);

@@ -33,7 +33,7 @@ void Mat::convertTo(Mat& dst, int rtype, double alpha, double beta) const {
     for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) out.setd(r, c, getd(r, c) * alpha + beta);
     dst = out;
 }
-Mat Mat::t() const { Mat m(cols, rows, type()); for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) m.setd(c, r, getd(r, c)); return m; }
+Mat Mat::transposed() const { Mat m(cols, rows, type()); for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) m.setd(c, r, getd(r, c)); return m; }
 double Mat::dot(const Mat& m) const {        // cv::Mat::dot: double accumulator over the elements in order
     assert(total() == m.total());
     double s = 0; const int n = (int)total();
@@ -72,14 +72,16 @@ Mat Mat::inv(int) const {                     // Gauss-Jordan in double; only re
 
 // cv::gemm as observed on cv2 4.13 (tools/probe_cv_gemm.py, 3000 random cases per shape, all bit-equal):
 //  CV_32F with inner length 2..4 equal to the output width or height: float products summed left to right in float,
-//  then (float)(sum*alpha + c*beta); otherwise double accumulation, one rounding.
-Mat gemm_eval(const Mat& a, const Mat& b, double alpha, const Mat* c, double beta) {
+//  then (float)(sum*alpha + c*beta) (alpha = +-1 probed); otherwise — other shapes, or a transposed operand (GEMM_1_T / GEMM_2_T,
+//  e.g. -Rcw.t()*tcw) — double accumulation and one rounding.
+Mat gemm_eval(const Mat& a0, const Mat& b0, double alpha, const Mat* c, double beta, int flags) {
+    const Mat a = (flags & 1) ? a0.transposed() : a0, b = (flags & 2) ? b0.transposed() : b0;
     assert(a.cols == b.rows && a.type() == b.type());
     const int m = a.rows, len = a.cols, n = b.cols;
     Mat d(m, n, a.type());
     if (c) assert(c->rows == m && c->cols == n);
     if (a.depth() == CV_32F) {
-        const bool small = len >= 2 && len <= 4 && (len == n || len == m);
+        const bool small = flags == 0 && len >= 2 && len <= 4 && (len == n || len == m);   // transposed operands take the general path
         for (int i = 0; i < m; i++) for (int j = 0; j < n; j++) {
             if (small) {
                 float s = a.at<float>(i, 0) * b.at<float>(0, j);
@@ -102,7 +104,7 @@ Mat gemm_eval(const Mat& a, const Mat& b, double alpha, const Mat* c, double bet
     return d;
 }
 void gemm(const Mat& a, const Mat& b, double alpha, const Mat& c, double beta, Mat& dst, int flags) {
-    assert(flags == 0); dst = gemm_eval(a, b, alpha, c.empty() ? nullptr : &c, beta);
+    dst = gemm_eval(a, b, alpha, c.empty() ? nullptr : &c, beta, flags);
 }
 
 static Mat binop(const Mat& a, const Mat& b, int sign) {
@@ -114,7 +116,7 @@ static Mat binop(const Mat& a, const Mat& b, int sign) {
 }
 Mat operator+(const Mat& a, const Mat& b) { return binop(a, b, 1); }
 Mat operator-(const Mat& a, const Mat& b) { return binop(a, b, -1); }
-Mat operator-(const Mat& a) { Mat o(a.rows, a.cols, a.type()); for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) o.setd(r, c, -a.getd(r, c)); return o; }
+Mat negate(const Mat& a) { Mat o(a.rows, a.cols, a.type()); for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) o.setd(r, c, -a.getd(r, c)); return o; }
 Mat operator*(const Mat& a, double s) { Mat o(a.rows, a.cols, a.type()); for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) o.setd(r, c, a.getd(r, c) * s); return o; }
 Mat operator/(const Mat& a, double s) { return a * (1.0 / s); }
 Mat operator+(const Mat& a, const Scalar& s) { Mat o(a.rows, a.cols, a.type()); for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) o.setd(r, c, a.getd(r, c) + s.val[0]); return o; }

@@ -163,6 +163,7 @@ static inline int depth_size(int depth) { static const int s[7] = {1, 1, 2, 2, 4
 
 class Mat;
 struct MatMul;
+struct MatT;
 // Mat::zeros / ones / eye are EXPRESSIONS in OpenCV: assigning one to an existing Mat of the same size and type fills it in
 // place (Mat::create is a no-op then) — ORBextractor.cc:1037 relies on that to write descriptors into a rowRange() view.
 struct MatInit { int rows, cols, type, kind; };
@@ -184,6 +185,7 @@ public:
     Mat(const MatMul& e);
     Mat& operator=(const MatMul& e);
     Mat(const MatInit& e) : Mat() { *this = e; }
+    Mat(const struct MatNeg& e);
     Mat& operator=(const MatInit& e) {
         create(e.rows, e.cols, e.type);
         for (int r = 0; r < rows; r++) memset(ptr(r), 0, (size_t)cols * elemSize());
@@ -261,7 +263,10 @@ public:
 
     double getd(int r, int c) const;         // element as double (8U/16S/32S/32F/64F)
     void setd(int r, int c, double v);
-    Mat t() const;
+    MatT t() const;             // an expression, as in OpenCV: A.t()*B is ONE gemm with a transpose flag
+    Mat transposed() const;
+    Mat(const MatT& e);
+    Mat& operator=(const MatT& e);
     Mat inv(int method = 0) const;
     double dot(const Mat& m) const;
     Mat cross(const Mat& m) const;
@@ -308,11 +313,18 @@ template <class T, class U> MatCommaInitializer_<T> operator<<(const Mat_<T>& m,
 }
 
 // ---- arithmetic (eager, except A*B which stays a product expression so that A*B+C is ONE gemm like cv::MatExpr) ----
+struct MatT {                     // alpha * A^T
+    Mat a; double alpha;
+    MatT(const Mat& m, double s = 1);
+    Mat eval() const;
+    MatT t() const;               // (A^T)^T
+    template <class T> T at(int r, int c) const { return eval().at<T>(r, c); }
+};
 struct MatMul {
-    Mat a, b; double alpha;
-    MatMul(const Mat& x, const Mat& y, double s = 1) : a(x), b(y), alpha(s) {}
+    Mat a, b; double alpha; int flags;          // flags: 1 = a transposed, 2 = b transposed (cv::GEMM_1_T / GEMM_2_T)
+    MatMul(const Mat& x, const Mat& y, double s = 1, int f = 0) : a(x), b(y), alpha(s), flags(f) {}
     Mat eval(const Mat* c = nullptr, double beta = 0) const;
-    Mat t() const { return eval().t(); }
+    MatT t() const;
     Mat row(int i) const { return eval().row(i); }
     Mat col(int i) const { return eval().col(i); }
     template <class T> T at(int i) const { return eval().at<T>(i); }
@@ -321,17 +333,38 @@ struct MatMul {
 };
 inline Mat::Mat(const MatMul& e) : Mat() { *this = e.eval(); }
 inline Mat& Mat::operator=(const MatMul& e) { Mat r = e.eval(); return *this = r; }
+struct MatNeg { Mat a; };            // -A : folds into the following product's alpha, like cv::MatExpr
+inline MatNeg operator-(const Mat& a) { return MatNeg{a}; }
+Mat negate(const Mat& a);
+Mat operator*(const Mat& a, double s);
 
-Mat gemm_eval(const Mat& a, const Mat& b, double alpha, const Mat* c, double beta);
+Mat gemm_eval(const Mat& a, const Mat& b, double alpha, const Mat* c, double beta, int flags = 0);
 void gemm(const Mat& a, const Mat& b, double alpha, const Mat& c, double beta, Mat& dst, int flags = 0);
-inline Mat MatMul::eval(const Mat* c, double beta) const { return gemm_eval(a, b, alpha, c, beta); }
+inline Mat MatMul::eval(const Mat* c, double beta) const { return gemm_eval(a, b, alpha, c, beta, flags); }
+inline Mat::Mat(const MatNeg& e) : Mat() { *this = negate(e.a); }
+inline MatT::MatT(const Mat& m, double s) : a(m), alpha(s) {}
+inline Mat MatT::eval() const { Mat m = a.transposed(); return alpha == 1 ? m : Mat(m * alpha); }
+inline MatT MatT::t() const { return MatT(a.transposed(), alpha); }
+inline MatT Mat::t() const { return MatT(*this); }
+inline MatT MatMul::t() const { return MatT(eval()); }
+inline Mat::Mat(const MatT& e) : Mat() { *this = e.eval(); }
+inline Mat& Mat::operator=(const MatT& e) { Mat r = e.eval(); return *this = r; }
+inline MatT operator-(const MatT& a) { return MatT(a.a, -a.alpha); }
+inline MatT operator*(double s, const MatT& a) { return MatT(a.a, a.alpha * s); }
+inline MatT operator*(const MatT& a, double s) { return MatT(a.a, a.alpha * s); }
+inline MatMul operator*(const MatT& a, const Mat& b) { return MatMul(a.a, b, a.alpha, 1); }
+inline MatMul operator*(const Mat& a, const MatT& b) { return MatMul(a, b.a, b.alpha, 2); }
+inline MatMul operator*(const MatT& a, const MatT& b) { return MatMul(a.a, b.a, a.alpha * b.alpha, 3); }
 
 inline MatMul operator*(const Mat& a, const Mat& b) { return MatMul(a, b); }
+Mat operator*(const Mat& a, double s);
 inline MatMul operator*(const MatMul& a, const Mat& b) { return MatMul(a.eval(), b); }
 inline MatMul operator*(const Mat& a, const MatMul& b) { return MatMul(a, b.eval()); }
-inline MatMul operator*(const MatMul& a, double s) { return MatMul(a.a, a.b, a.alpha * s); }
-inline MatMul operator*(double s, const MatMul& a) { return MatMul(a.a, a.b, a.alpha * s); }
-inline MatMul operator-(const MatMul& a) { return MatMul(a.a, a.b, -a.alpha); }
+inline MatMul operator*(const MatMul& a, double s) { return MatMul(a.a, a.b, a.alpha * s, a.flags); }
+inline MatMul operator*(double s, const MatMul& a) { return MatMul(a.a, a.b, a.alpha * s, a.flags); }
+inline MatMul operator-(const MatMul& a) { return MatMul(a.a, a.b, -a.alpha, a.flags); }
+inline MatMul operator*(const MatMul& a, const MatT& b) { return MatMul(a.eval(), b.a, b.alpha, 2); }
+inline MatMul operator*(const MatT& a, const MatMul& b) { return MatMul(a.a, b.eval(), a.alpha, 1); }
 inline Mat operator+(const MatMul& a, const Mat& c) { return a.eval(&c, 1); }
 inline Mat operator+(const Mat& c, const MatMul& a) { return a.eval(&c, 1); }
 inline Mat operator-(const MatMul& a, const Mat& c) { return a.eval(&c, -1); }
@@ -340,7 +373,8 @@ Mat operator-(const Mat& a, const Mat& b);
 inline Mat operator+(const MatMul& a, const MatMul& b) { return a.eval() + b.eval(); }
 inline Mat operator-(const MatMul& a, const MatMul& b) { return a.eval() - b.eval(); }
 inline Mat operator-(const Mat& a, const MatMul& b) { return a - b.eval(); }
-Mat operator-(const Mat& a);
+inline MatMul operator*(const MatNeg& a, const Mat& b) { return MatMul(a.a, b, -1); }
+inline Mat operator+(const MatNeg& a, const Mat& b) { return b - a.a; }
 Mat operator*(const Mat& a, double s);
 inline Mat operator*(double s, const Mat& a) { return a * s; }
 Mat operator/(const Mat& a, double s);
@@ -361,6 +395,7 @@ public:
     _InputArray() : m(nullptr) {}
     _InputArray(const Mat& a) : m(&a) {}
     _InputArray(const MatMul& e) : own(e.eval()) { m = &own; }
+    _InputArray(const MatT& e) : own(e.eval()) { m = &own; }
     template <class T> _InputArray(const std::vector<T>& v) : own(v) { m = &own; }
     bool empty() const { return !m || m->empty(); }
     Mat getMat(int = -1) const { return m ? *m : Mat(); }

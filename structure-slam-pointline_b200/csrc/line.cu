@@ -994,6 +994,30 @@ __global__ void __launch_bounds__(128) k_lsd_nfa_improve(const __grid_constant__
     }
 }
 
+// cv::LineIterator(img, p1, p2, 8).count: the endpoints are cvRound()ed floats from [0, lim), so 639.6 becomes 640 — one past
+// the last column — and OpenCV clips the segment to the image (cv::clipLine, 64-bit integer arithmetic) before counting.
+// Pinned to cv2.clipLine in tests/test_line_oracle_cpu.py through the oracle's identical restatement.
+__device__ __forceinline__ int line_iterator_count(int w, int h, int ax, int ay, int bx, int by) {
+    long long x1 = ax, y1 = ay, x2 = bx, y2 = by;
+    if ((unsigned)ax < (unsigned)w && (unsigned)bx < (unsigned)w && (unsigned)ay < (unsigned)h && (unsigned)by < (unsigned)h)
+        return max(abs(bx - ax), abs(by - ay)) + 1;
+    const long long right = w - 1, bottom = h - 1;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        long long a;
+        if (c1 & 12) { a = c1 < 8 ? 0 : bottom; x1 += (a - y1) * (x2 - x1) / (y2 - y1); y1 = a; c1 = (x1 < 0) + (x1 > right) * 2; }
+        if (c2 & 12) { a = c2 < 8 ? 0 : bottom; x2 += (a - y2) * (x2 - x1) / (y2 - y1); y2 = a; c2 = (x2 < 0) + (x2 > right) * 2; }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) { a = c1 == 1 ? 0 : right; y1 += (a - x1) * (y2 - y1) / (x2 - x1); x1 = a; c1 = 0; }
+            if (c2) { a = c2 == 1 ? 0 : right; y2 += (a - x2) * (y2 - y1) / (x2 - x1); x2 = a; c2 = 0; }
+        }
+    }
+    if ((c1 | c2) != 0) return 0;
+    const long long dx = x2 > x1 ? x2 - x1 : x1 - x2, dy = y2 > y1 ? y2 - y1 : y1 - y2;
+    return (int)(dx > dy ? dx : dy) + 1;
+}
+
 // -------------------------------------------------------------------------------------------------
 // KeyLine packaging (line_descriptor LSDDetector::detectImpl), top-N by response (ExtractLineSegment.cpp:45-51),
 // line equations (:56-68).  One CTA per frame.
@@ -1052,7 +1076,7 @@ __global__ void __launch_bounds__(256) k_keylines(const __grid_constant__ LineGe
         const float ddx = e.x - e.z, ddy = e.y - e.w;
         k.lineLength = (float)sqrt((double)ddx * (double)ddx + (double)ddy * (double)ddy);
         const int ax = __float2int_rn(e.x), ay = __float2int_rn(e.y), bx = __float2int_rn(e.z), by = __float2int_rn(e.w);
-        k.numOfPixels = max(abs(bx - ax), abs(by - ay)) + 1;          // cv::LineIterator(8-connected).count
+        k.numOfPixels = line_iterator_count(g.w, g.h, ax, ay, bx, by);  // cv::LineIterator(8-connected).count (after cv::clipLine)
         k.angle = (float)atan2((double)(e.w - e.y), (double)(e.z - e.x));
         k.class_id = pos; k.octave = 0;
         k.size = (e.z - e.x) * (e.w - e.y);

@@ -351,10 +351,12 @@ __global__ void __launch_bounds__(32) k_proj_match(const __grid_constant__ ProjA
         const int fl = flag1[i];
         if (!(fl & 1)) continue;
         const float X0 = Xw[3 * i], X1 = Xw[3 * i + 1], X2 = Xw[3 * i + 2];
-        // cv::gemm on CV_32F: double accumulation, one rounding per element (Rcw * x3Dw + tcw)
-        const float xc = (float)((double)A.T[0] * X0 + (double)A.T[1] * X1 + (double)A.T[2] * X2 + (double)A.T[3]);
-        const float yc = (float)((double)A.T[4] * X0 + (double)A.T[5] * X1 + (double)A.T[6] * X2 + (double)A.T[7]);
-        const float zc = (float)((double)A.T[8] * X0 + (double)A.T[9] * X1 + (double)A.T[10] * X2 + (double)A.T[11]);
+        // Rcw * x3Dw + tcw (ORBmatcher.cc:1364): cv::gemm runs a plain 3x3 * 3x1 (+ 3x1) CV_32F product in FLOAT, products summed
+        // left to right, the addend last (probed on cv2 4.13, tools/probe_cv_gemm.py; the reference compiled over that model
+        // agrees with the oracle in tests/test_ref_parity_cpu.py).  Explicit _rn intrinsics: no FMA contraction.
+        const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A.T[0], X0), __fmul_rn(A.T[1], X1)), __fmul_rn(A.T[2], X2)), A.T[3]);
+        const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A.T[4], X0), __fmul_rn(A.T[5], X1)), __fmul_rn(A.T[6], X2)), A.T[7]);
+        const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A.T[8], X0), __fmul_rn(A.T[9], X1)), __fmul_rn(A.T[10], X2)), A.T[11]);
         const float invzc = (float)(1.0 / (double)zc);
         if (invzc < 0) continue;
         const float u = __fadd_rn(__fmul_rn(__fmul_rn(A.fx, xc), invzc), A.cx), v = __fadd_rn(__fmul_rn(__fmul_rn(A.fy, yc), invzc), A.cy);
@@ -970,7 +972,10 @@ int sslpl_search_by_projection_frame(sslpl_matcher* m,
     if (!bMono) {                                                        // tlc = Rlw * (-Rcw^T tcw) + tlw against the baseline (:1352-1353)
         float twc[3];
         for (int r = 0; r < 3; r++) twc[r] = (float)(-((double)Tcw[r] * Tcw[3] + (double)Tcw[4 + r] * Tcw[7] + (double)Tcw[8 + r] * Tcw[11]));
-        const float tlcz = (float)((double)Tlw[8] * twc[0] + (double)Tlw[9] * twc[1] + (double)Tlw[10] * twc[2] + (double)Tlw[11]);
+        // twc = -Rcw.t()*tcw carries a transpose flag => cv::gemm's general path (double accumulation, above); tlc = Rlw*twc+tlw
+        // is a plain product => float path.  Host code: volatile keeps the compiler from contracting the float chain.
+        volatile float s = Tlw[8] * twc[0]; s = s + Tlw[9] * twc[1]; s = s + Tlw[10] * twc[2];
+        const float tlcz = s + Tlw[11];
         A.forward = tlcz > cam[5]; A.backward = -tlcz > cam[5];
     }
     // staging (pinned scratch would avoid the pageable copies; this entry point is per frame pair, not the batched path)

@@ -100,3 +100,25 @@ def test_num_of_pixels_is_the_8_connected_line_iterator_count(oracle, icl_gray):
     r = lambda v: np.rint(v).astype(np.int64)                       # cv::Point(Point2f) rounds half to even, like np.rint
     exp = np.maximum(np.abs(r(kl["endPointX"]) - r(kl["startPointX"])), np.abs(r(kl["endPointY"]) - r(kl["startPointY"]))) + 1
     assert len(kl) > 100 and np.array_equal(kl["numOfPixels"], exp)
+
+
+def test_clip_line_and_iterator_count_match_cv2(oracle):
+    """KeyLine.numOfPixels = cv::LineIterator(img, p1, p2, 8).count: endpoints are cvRound()ed floats in [0, lim), so 639.6
+    becomes 640 — outside — and OpenCV clips the segment to the image first (cv::clipLine).  Pinned to cv2.clipLine."""
+    import ctypes as C
+    import cv2
+    L = oracle.lib()
+    rng = np.random.default_rng(12)
+    W, H = 640, 480
+    for _ in range(4000):
+        p = rng.integers(-3, [W + 4, H + 4], (2, 2))
+        if rng.random() < 0.5:                                      # the case that occurs: one coordinate exactly at the limit
+            p = rng.integers(0, [W, H], (2, 2)); p[rng.integers(0, 2), rng.integers(0, 2)] = [W, H][rng.integers(0, 2)]
+        ok, q1, q2 = cv2.clipLine((0, 0, W, H), (int(p[0, 0]), int(p[0, 1])), (int(p[1, 0]), int(p[1, 1])))
+        x1, y1, x2, y2 = (C.c_longlong(int(v)) for v in (p[0, 0], p[0, 1], p[1, 0], p[1, 1]))
+        r = L.orc_clip_line(W, H, C.byref(x1), C.byref(y1), C.byref(x2), C.byref(y2))
+        assert bool(r) == bool(ok), p
+        if ok:
+            assert (x1.value, y1.value, x2.value, y2.value) == (q1[0], q1[1], q2[0], q2[1]), p
+            n = L.orc_line_iterator_count(W, H, int(p[0, 0]), int(p[0, 1]), int(p[1, 0]), int(p[1, 1]))
+            assert n == max(abs(q2[0] - q1[0]), abs(q2[1] - q1[1])) + 1

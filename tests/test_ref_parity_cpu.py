@@ -195,6 +195,47 @@ def test_features_in_area(oracle, ref, synth):
         assert np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize("seed,th,mono,ori,claimed", [(1, 15.0, True, True, 0.05), (2, 7.0, True, True, 0.0), (3, 30.0, True, False, 0.2),
+                                                       (4, 15.0, False, True, 0.05), (5, 15.0, False, True, 0.0), (6, 100.0, True, True, 0.0)])
+def test_search_by_projection_frame(oracle, ref, synth, seed, th, mono, ori, claimed):
+    """ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) :1331-1473 (TrackWithMotionModel) — the scenarios of
+    tests/test_projection_gpu.py, stereo ones included (forward / backward level windows, uRight test)."""
+    from scenarios import projection_scenario
+    last, cur, Tcw, Tlw, cam, bounds, sf = projection_scenario(oracle, synth, seed, n_claimed=claimed, stereo=not mono, f0=seed)
+    n_o, a_o = oracle.search_by_projection_frame(last, cur, Tcw, Tlw, cam, bounds, sf, th, mono, ori)
+    camv = ref.cam(cam[0], cam[1], cam[2], cam[3], *bounds)
+    n_r, a_r = ref.search_by_projection_frame(last, cur, Tcw, Tlw, camv, 8, 1.2, th, mono, ori, mbf=cam[4])
+    a_r = np.where(a_r == -2, -1, a_r)                           # -2 = the feature still holds the MapPoint it was 'claimed' with
+    assert n_r == n_o and np.array_equal(a_r, a_o), (seed, n_r, n_o, int((a_r != a_o).sum()))
+    assert n_o > 50 or th < 10
+    if seed == 1:          # nothing valid / everything claimed / no observations (later points overwrite earlier ones, counted twice)
+        for mod in ("novalid", "allclaimed", "noobs"):
+            l2, c2 = dict(last), dict(cur)
+            if mod == "novalid": l2["valid"] = np.zeros_like(last["valid"])
+            if mod == "allclaimed": c2["claimed"] = np.ones(len(cur["x"]), np.uint8)
+            if mod == "noobs": l2["obs"] = np.zeros_like(last["obs"]); l2["valid"] = np.ones_like(last["valid"])
+            n_o, a_o = oracle.search_by_projection_frame(l2, c2, Tcw, Tlw, cam, bounds, sf, 20.0, True, True)
+            n_r, a_r = ref.search_by_projection_frame(l2, c2, Tcw, Tlw, camv, 8, 1.2, 20.0, True, True, mbf=cam[4])
+            assert n_r == n_o and np.array_equal(np.where(a_r == -2, -1, a_r), a_o), mod
+
+
+def test_descriptor_medoid(oracle, ref):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-312): least-median descriptor of each observation group."""
+    rng = np.random.default_rng(8)
+    sizes = [1, 2, 3, 4, 7, 20, 33]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    base = rng.integers(0, 256, (len(sizes), 32), dtype=np.uint8)
+    desc = np.concatenate([np.repeat(base[g:g + 1], n, 0) for g, n in enumerate(sizes)])
+    noise = (rng.random(desc.shape) < 0.15) * rng.integers(0, 256, desc.shape)
+    desc = (desc ^ noise.astype(np.uint8)).astype(np.uint8)
+    desc[off[5] + 3] = desc[off[5] + 9]                                   # duplicates inside a group: first minimum wins
+    bi_o, _ = oracle.descriptor_medoid(desc, off)
+    bi_r = ref.descriptor_medoid(desc, off)
+    # the reference returns the descriptor, located here by content: equal rows are interchangeable
+    for g in range(len(sizes)):
+        assert np.array_equal(desc[off[g] + bi_r[g]], desc[off[g] + bi_o[g]]), g
+
+
 # ---------------------------------------------------------------------------------------------- line matchers
 @pytest.mark.parametrize("n1,n2,seed", [(40, 40, 0), (40, 37, 1), (500, 500, 2), (5, 2, 3), (64, 200, 4)])
 def test_line_matchers(oracle, ref, n1, n2, seed):
@@ -298,7 +339,8 @@ def test_frame_constructor(oracle, ref, icl_gray):
     assert fr["keylines"].tobytes() == okl.tobytes() and np.array_equal(fr["ldesc"], old) and np.array_equal(fr["lineeq"], oeq)
     assert list(fr["bounds"]) == [0, 640, 0, 480]
     # grid cell (c, r) holds the features whose rounded cell is (c, r), ascending
-    gx = np.round((ok["x"] - 0) * np.float32(64 / 640)).astype(int); gy = np.round((ok["y"] - 0) * np.float32(48 / 480)).astype(int)
+    rnd = lambda v: np.floor(v.astype(np.float32) + np.float32(0.5)).astype(int)      # C round() on non-negative floats (PosInGrid, Frame.cc:462-472)
+    gx = rnd(ok["x"] * np.float32(64 / 640)); gy = rnd(ok["y"] * np.float32(48 / 480))
     for c, r in [(0, 0), (10, 7), (32, 24), (63, 47), (40, 13)]:
         cell = fr["grid_idx"][fr["grid_off"][c * 48 + r]:fr["grid_off"][c * 48 + r + 1]]
         assert np.array_equal(cell, np.flatnonzero((gx == c) & (gy == r)))
