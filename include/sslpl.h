@@ -259,10 +259,13 @@ int  sslpl_line_sync(sslpl_line* h);
 void* sslpl_line_stream(sslpl_line* h);
 int  sslpl_line_set_stream(sslpl_line* h, void* cuda_stream);
 long long sslpl_line_launch_count(const sslpl_line* h);
-/* Scheduling knob (no effect on results): the LSD region stage runs one long-lived one-warp CTA per frame; bound how many
-   of them one call keeps resident (0 = one per frame, the default).  Useful when several handles are in flight on one GPU
-   next to wide kernels: resident walkers pin registers for tens of milliseconds. */
+/* Scheduling knob (no effect on results): the LSD region stage runs one multi-warp CTA per frame; bound how many of them one
+   call keeps resident (0 = one per frame, the default).  Useful when several handles are in flight on one GPU next to wide
+   kernels: resident walkers pin registers for milliseconds. */
 int  sslpl_line_set_max_walkers(sslpl_line* h, int max_concurrent);
+/* Statistics of the last region-walker launch, 16 values (see csrc/line.cu): regions grown by the turn holder / as speculated,
+   redo causes, cycles under the commit and claim locks, cycles per frame.  Diagnostic only. */
+int  sslpl_line_walker_stats(sslpl_line* h, unsigned long long* out16);
 int  sslpl_line_set_profiling(sslpl_line* h, int on);
 int  sslpl_line_stage_ms(sslpl_line* h, float* ms, int cap, const char** names, int* nstages);
 /* raw LSD segments (before the top-N cut) of frame f of the last call: seg[4*i] = x1,y1,x2,y2 */

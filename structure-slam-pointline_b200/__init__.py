@@ -652,6 +652,13 @@ class LineSegment:
         _check(lib().sslpl_line_stage_ms(self._h, ms, 16, names, C.byref(n)))
         return {names[i].decode(): float(ms[i]) for i in range(n.value)}
 
+    def walker_stats(self):
+        out = (C.c_ulonglong * 16)()
+        _check(lib().sslpl_line_walker_stats(self._h, out))
+        names = ["turn_regions", "turn_cycles", "turn_pixels", "_", "seed_swallowed", "redo_abandoned", "redo_poisoned", "redo_invalid", "redo_presumed",
+                 "committed_as_speculated", "speculated_pixels", "commit_lock_cycles", "claim_lock_cycles", "repeated_attempts", "frame_cycles", "claims"]
+        return {k: int(out[i]) for i, k in enumerate(names)}
+
     def debug_trace(self, frame=0, cap=1 << 16):
         out = np.empty((cap, 10), np.float64); n = C.c_int()
         _check(lib().sslpl_line_debug_trace(self._h, frame, _p(out), cap, C.byref(n)))

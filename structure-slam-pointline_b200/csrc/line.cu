@@ -41,17 +41,21 @@ struct LineGeom {
     double rho, prec, p, log_nt;
     int min_reg_size;
     int trace_cap;              // rows of the debug trace per frame (0 = off)
+    int dbg;                    // SSLPL_WALKER_DBG bit mask (bring-up switches of the region walker)
 };
 
 // What region growing reads per neighbour, in one 16-byte load: level-line angle (degrees, NOTDEF_F when undefined),
 // (float)cos / sin of (float)(angle in radians) — the values region_grow sums — and the mutable `used` flag.
-struct __align__(16) LPix { float ang, cx, cy; unsigned used; };
+struct __align__(16) LPix { float ang, cx, cy; unsigned used; };   // `used` = ticket of the region-growing attempt holding the pixel (0 = none)
 
 struct LineWs {
     uint8_t* blur7; uint8_t* blur5; uint8_t* scaled;
     float* angdeg; LPix* pix; float2* cs0; double* modgrad;
     unsigned long long* maxgrad; unsigned* seeds; int* nseeds;
-    unsigned* reg;              // region pixel list (x | y << 16)
+    unsigned* reg;              // region pixel list (x | y << 16) of the turn holder (whole-frame capacity)
+    unsigned* sreg;             // per frame: WALK_RING speculation slots x WALK_SLOT_CAP list entries
+    double* sjob;               // per frame: one pending NFA job (13 doubles) per speculation slot
+    unsigned long long* wstat;  // walker statistics (whole launch): see sslpl_line_walker_stats
     double* seg;                // raw rectangles: x1,y1,x2,y2 (detection scale, before +0.5)
     int* nseg;
     double* jobs; int* njobs; int* jobflag;   // NFA jobs: 13 doubles per candidate region (LRect + log_nfa), in walker order
@@ -311,15 +315,53 @@ struct Walk {                   // context of the rectangle scans (k_lsd_nfa_*):
     int lane;
 };
 
-struct WalkCtx {                // context of the walker (k_lsd_regions): shared memory
+constexpr int WALK_MAXW = 16;          // warps of a walker CTA (one CTA per frame)
+constexpr int WALK_RING = 64;          // region-growing attempts in flight per frame (speculation slots)
+constexpr int WALK_SLOT_CAP = 2048;    // list entries of a slot: every pixel the attempt ever accepted + the pixels it assumed used
+constexpr int WALK_SMALL = 32;         // attempts with at most this many list entries are committed from shared memory
+constexpr int WALK_WIN = 64;           // seeds staged in shared memory for the claims
+
+struct WalkCtx {                // context of one walker warp (k_lsd_regions): shared memory
     int w, h;
     const float* ang; const double* mod;
-    LPix* pix;                  // packed per-pixel record incl. the `used` flag (only this warp touches the frame's flags)
-    unsigned* reg;              // region pixel list (x | y << 16)
+    LPix* pix;                  // packed per-pixel record; .used holds the ticket (global): who is growing over this pixel right now
+    const unsigned* bits;       // the frame's COMMITTED `used` bitmap (shared memory); bits only ever go 0 -> 1
+    unsigned* reg;              // current region list (x | y << 16)
+    unsigned* base0;            // start of this attempt's list space
     const float2* cs0;          // per pixel: (float)cos / sin of the level-line angle taken as double (region seed values)
+    int cap;                    // entries available at reg (the assumed-used list grows down from reg + cap)
+    int nasm;                   // assumed-used pixels recorded so far
+    int acc;                    // entries of base0[] that hold accepted-ever pixels (validated at commit)
+    int seq;                    // rank of this attempt (claim order)
+    int mode;                   // 0 = speculative, 1 = turn holder (everything of lower rank is committed)
+    int dbg;
+    int abort;                  // speculative attempt abandoned: 1 = capacity, 2 = a live attempt of LOWER rank holds a pixel it needs
+    int conflict;               // abort == 2: that rank (the attempt can be repeated once it has been retired)
+    unsigned ticket;
 };
-__shared__ WalkCtx s_W;
-__shared__ __align__(16) double s_st[96];     // staging of a 32-point chunk: 3 quantities x 32
+struct FrameCtl {               // one per walker CTA
+    unsigned cursor, nclaims, turn;
+    int claim_lock, commit_lock, all_claimed, nj, frame, ns, win_base;
+    unsigned win[WALK_WIN];
+    int seqof[WALK_RING], seedpix[WALK_RING], state[WALK_RING], acc[WALK_RING], nasm[WALK_RING], finoff[WALK_RING], nfin[WALK_RING], job[WALK_RING], poison[WALK_RING];
+    unsigned small[WALK_RING][WALK_SMALL];      // acc + nasm <= WALK_SMALL and finoff == 0: accepted list, then the assumed pixels (as indices)
+};
+__shared__ WalkCtx s_Wc[WALK_MAXW];
+__shared__ FrameCtl s_F;
+__shared__ __align__(16) double s_stc[WALK_MAXW][96];     // per warp: staging of a 32-point chunk: 3 quantities x 32
+#define s_W (s_Wc[threadIdx.x >> 5])
+#define s_st (s_stc[threadIdx.x >> 5])
+
+// SLOT_PRESUMED: the seed was under the ticket of a live attempt of lower rank when its turn to be grown came: it is presumed
+// swallowed; the commit checks (and grows it for real if it was not).  SLOT_ABORTED: to be redone by the turn holder.
+enum { SLOT_EMPTY = 0, SLOT_RUNNING = 1, SLOT_DONE = 2, SLOT_ABORTED = 3, SLOT_PRESUMED = 4 };
+
+// ticket = rank + 1 in bits 0..23, attempt number in bits 24..30, bit 31 = grown by the turn holder
+__device__ __forceinline__ unsigned l_turn() { return *reinterpret_cast<volatile unsigned*>(&s_F.turn); }
+__device__ __forceinline__ bool l_bit(const unsigned* bits, int q) { return (reinterpret_cast<const volatile unsigned*>(bits)[q >> 5] >> (q & 31)) & 1u; }
+// Is ticket m (not mine) held by an attempt that has not been retired yet?  Ranks below `turn` are committed or discarded.
+__device__ __forceinline__ bool l_live(unsigned m, int* seq_out) { const int s = (int)(m & 0xffffffu) - 1; *seq_out = s; return m != 0u && s >= (int)l_turn(); }
+__device__ __forceinline__ void l_release(const WalkCtx& W, int q) { atomicCAS(&W.pix[q].used, W.ticket, 0u); }
 
 __device__ __forceinline__ bool l_aligned(float angdeg, double theta, double prec) {
     if (angdeg == NOTDEF_F) return false;
@@ -344,15 +386,60 @@ __device__ __forceinline__ bool l_aligned_rad(double a, double theta, double pre
 // in as many rounds as there are acceptances: all pending lanes test against the current angle; the first passing
 // lane k0 is accepted, lanes < k0 are definitively rejected (they saw exactly the angle the sequential scan would have
 // shown them), later lanes holding the same pixel drop out (the scan would find it used).
+//
+// "Used" is what the sequential algorithm would see: the frame's committed bitmap (regions of lower rank that are final) or
+// my own ticket.  A pixel under the ticket of a LIVE attempt of lower rank is assumed used and recorded (checked at commit);
+// one under a live ticket of higher rank counts as free (taking it poisons that attempt).  A pixel is taken with one atomic
+// whose result is only looked at one step later (the round trip overlaps the next step's loads): a speculative attempt that
+// lost a pixel to a live attempt of lower rank is abandoned then (abort = 2, conflict = that rank).
+// Returns -1 when the attempt has to be abandoned (s_W.abort says why).
+struct LTake { unsigned seen, old; int q; bool pend; };
+__device__ __forceinline__ void l_take_issue(const WalkCtx& W, LTake& t, int q, unsigned seen) {
+    t.q = q; t.seen = seen; t.pend = true;
+    t.old = W.mode == 0 ? atomicCAS(&W.pix[q].used, seen, W.ticket) : atomicExch(&W.pix[q].used, W.ticket);
+}
+// Looks at the result of the atomic issued one step earlier.  Returns -1 when the pixel is mine, the rank of the live attempt of
+// LOWER rank that holds it (the speculative attempt must be repeated after that rank retires), or -2 when a speculative attempt lost
+// the compare-and-swap to anybody else: the word changed between this attempt's read and its atomic, so other lanes may have acted
+// on the stale ticket during the step in between (the pixel could be in the list twice) — the attempt is simply repeated at once.
+__device__ __forceinline__ int l_take_resolve(const WalkCtx& W, LTake& t) {
+    if (!t.pend) return -1;
+    t.pend = false;
+    const unsigned old = t.old; int s;
+    if (W.mode != 0 || old == t.seen) {                           // the pixel is mine; whoever held it alive (higher rank) is poisoned
+        if (old != W.ticket && l_live(old, &s) && s != W.seq) s_F.poison[s % WALK_RING] = 1;
+        return -1;
+    }
+    return (l_live(old, &s) && s < W.seq) ? s : -2;
+}
+
 __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* reg_angle_out) {
-    const int lane = threadIdx.x, w = s_W.w, h = s_W.h;
-    LPix* pix = s_W.pix; unsigned* reg = s_W.reg;
+    WalkCtx& W = s_W;
+    const int lane = threadIdx.x & 31, w = W.w, h = W.h;
+    LPix* pix = W.pix; unsigned* reg = W.reg; const unsigned* bits = W.bits;
+    const unsigned T = W.ticket; const int myseq = W.seq; const bool spec = W.mode == 0;
     const int sq = sy * w + sx;                                   // 32-bit pixel indices (sw * sh < 2^31)
-    if (lane == 0) { reg[0] = (unsigned)sx | ((unsigned)sy << 16); pix[sq].used = 1u; }
-    double reg_angle = (double)__ldg(s_W.ang + sq) * L_DEG;
-    const float2 c0 = __ldg(s_W.cs0 + sq);
+    LTake tk; tk.pend = false; tk.q = 0; tk.seen = 0u; tk.old = 0u;
+    int failrank = -1;                                            // -1 fine, >= 0 rank to wait for, -2 repeat at once
+    {
+        int fail = 0;
+        if (lane == 0) {
+            reg[0] = (unsigned)sx | ((unsigned)sy << 16);
+            const unsigned m0 = __ldcg(&pix[sq].used);
+            int s0;
+            if (m0 != T) {
+                if (spec && l_live(m0, &s0) && s0 < myseq) fail = 3;          // an in-flight region of lower rank reached the seed first
+                else { l_take_issue(W, tk, sq, m0); const int r = l_take_resolve(W, tk); if (r >= 0) fail = 3; else if (r == -2) fail = 2; }
+            }
+        }
+        fail = __shfl_sync(0xffffffffu, fail, 0);
+        if (fail) { W.abort = fail; W.conflict = -1; return -1; }
+    }
+    double reg_angle = (double)__ldg(W.ang + sq) * L_DEG;
+    const float2 c0 = __ldg(W.cs0 + sq);
     float sumdx = c0.x, sumdy = c0.y;
-    int n = 1;
+    int n = 1, nasm = W.nasm;
+    const int cap = W.cap;
     const int slot = lane >> 3, nb = (lane & 7) + ((lane & 7) >= 4 ? 1 : 0);   // neighbour 0..8 without the centre (4)
     const int ox = nb % 3 - 1, oy = nb / 3 - 1;
     __syncwarp();
@@ -361,32 +448,45 @@ __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* r
         unsigned pk = 0, pkn = 0;
         if (slot < cnt) pk = reg[i + slot];
         const bool hasn = i + 4 + slot < n;                      // the next step's entries, where they already exist:
-        if (hasn) pkn = reg[i + 4 + slot];                       // pull their neighbour records towards L1 now
+        if (hasn) pkn = reg[i + 4 + slot];                       // pull their neighbour records towards L2 now
         const int xx = (int)(pk & 0xffff) + ox, yy = (int)(pk >> 16) + oy, q = yy * w + xx;
         const bool valid = slot < cnt && (unsigned)xx < (unsigned)w && (unsigned)yy < (unsigned)h;
         {
             const int xn = (int)(pkn & 0xffff) + ox, yn = (int)(pkn >> 16) + oy;
             if (hasn && (unsigned)xn < (unsigned)w && (unsigned)yn < (unsigned)h)
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(pix + (yn * w + xn)));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(pix + (yn * w + xn)));
         }
-        float a = NOTDEF_F, cx = 0.f, cy = 0.f; unsigned u = 1u;
-        if (valid) {
-            const uint4 v = *reinterpret_cast<const uint4*>(pix + q);
-            a = __uint_as_float(v.x); cx = __uint_as_float(v.y); cy = __uint_as_float(v.z); u = v.w;
+        uint4 v = make_uint4(__float_as_uint(NOTDEF_F), 0u, 0u, 0u);
+        if (valid) v = __ldcg(reinterpret_cast<const uint4*>(pix + q));       // record + ticket in one load (L2: the ticket is mutable)
+        { const int r = l_take_resolve(W, tk); if (r != -1) failrank = (r >= 0 && r > failrank) ? r : (failrank >= 0 ? failrank : r); }   // last step's atomic, while this step's loads fly
+        const float a = __uint_as_float(v.x), cx = __uint_as_float(v.y), cy = __uint_as_float(v.z);
+        const unsigned m = v.w;
+        bool cand = false, assumed = false;
+        if (valid && a != NOTDEF_F && m != T && !l_bit(bits, q)) {
+            int s;
+            if (spec && l_live(m, &s) && s < myseq) { assumed = true; if (W.dbg & 16) failrank = s > failrank ? s : failrank; }
+            else cand = true;
+        }
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned am = __ballot_sync(0xffffffffu, assumed);
+        if (am) {                                                 // remember what was assumed: the commit checks these bits are set
+            if (n + nasm + __popc(am) > cap) { W.abort = 1; return -1; }
+            if (assumed) reg[cap - 1 - nasm - __popc(am & lt)] = (unsigned)q;
+            nasm += __popc(am);
         }
         const double ad = (double)a * L_DEG;
-        const unsigned lt = (1u << lane) - 1u;
-        unsigned pending = __ballot_sync(0xffffffffu, u == 0u && a != NOTDEF_F);
+        unsigned pending = __ballot_sync(0xffffffffu, cand);
         while (pending) {
             const bool mep = (pending >> lane) & 1u;
             const unsigned S0 = __ballot_sync(0xffffffffu, mep && l_aligned_rad(ad, reg_angle, prec));
             if (!S0) break;                                       // nobody passes at the current angle: all rejected
+            if (n + nasm + __popc(S0) > cap) { W.abort = 1; return -1; }
             if ((S0 & (S0 - 1u)) == 0u) {
                 // exactly one candidate: the plain sequential step
                 const int k0 = __ffs(S0) - 1;
                 const float kx = __shfl_sync(0xffffffffu, cx, k0), ky = __shfl_sync(0xffffffffu, cy, k0);
                 const int q0 = __shfl_sync(0xffffffffu, q, k0);
-                if (lane == k0) { reg[n] = (unsigned)xx | ((unsigned)yy << 16); pix[q].used = 1u; }
+                if (lane == k0) { reg[n] = (unsigned)xx | ((unsigned)yy << 16); l_take_issue(W, tk, q, m); }
                 n++;
                 sumdx += kx; sumdy += ky;
                 reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * L_DEG;
@@ -405,10 +505,10 @@ __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* r
             const unsigned S = S0 & ~__ballot_sync(0xffffffffu, inS0 && (peers & S0 & lt) != 0u);
             const bool inS = (S >> lane) & 1u;
             float bx = sumdx, by = sumdy;
-            for (unsigned T = S; T; T &= T - 1u) {
-                const int m = __ffs(T) - 1;
-                const float mx = __shfl_sync(0xffffffffu, cx, m), my = __shfl_sync(0xffffffffu, cy, m);
-                if (lane > m) { bx += mx; by += my; }
+            for (unsigned Tm = S; Tm; Tm &= Tm - 1u) {
+                const int mm = __ffs(Tm) - 1;
+                const float mx = __shfl_sync(0xffffffffu, cx, mm), my = __shfl_sync(0xffffffffu, cy, mm);
+                if (lane > mm) { bx += mx; by += my; }
             }
             const float ax = bx + cx, ay = by + cy;
             const double aft = (double)fast_atan2_deg(ay, ax) * L_DEG;
@@ -425,7 +525,7 @@ __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* r
                 const unsigned acc = __ballot_sync(0xffffffffu, actual);
                 A = (S & ((1u << src) - 1u)) | (acc & (1u << src));
             }
-            if ((A >> lane) & 1u) { reg[n + __popc(A & lt)] = (unsigned)xx | ((unsigned)yy << 16); pix[q].used = 1u; }
+            if ((A >> lane) & 1u) { reg[n + __popc(A & lt)] = (unsigned)xx | ((unsigned)yy << 16); l_take_issue(W, tk, q, m); }
             n += __popc(A);
             const float selx = actual ? ax : bx, sely = actual ? ay : by;
             const double sela = actual ? aft : bef;
@@ -436,8 +536,14 @@ __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* r
             pending &= ~__ballot_sync(0xffffffffu, mep && (peers & A) != 0u);   // later holders of accepted pixels
         }
         __syncwarp();
+        if (spec && __any_sync(0xffffffffu, failrank != -1)) break;            // lost a pixel: stop growing now
         i += cnt;
     }
+    { const int r = l_take_resolve(W, tk); if (r != -1) failrank = (r >= 0 && r > failrank) ? r : (failrank >= 0 ? failrank : r); }
+    const bool lostany = __any_sync(0xffffffffu, failrank != -1);
+    failrank = __reduce_max_sync(0xffffffffu, failrank);          // the highest rank to wait for (-1 / -2 lanes do not count)
+    W.nasm = nasm;
+    if (lostany) { W.abort = 2; W.conflict = failrank >= 0 ? failrank : -1; return -1; }
     *reg_angle_out = reg_angle;
     return n;
 }
@@ -468,7 +574,7 @@ __device__ __noinline__ double l_chunk_sum(const double* sp, int m, double acc) 
 // memory, and lanes 0..2 (replicated over the warp) each walk one of the three staged rows.  The extents are exact
 // min/max.
 __device__ __noinline__ void l_region2rect(int n, double reg_angle, double prec, double p, LRect* out) {
-    const int lane = threadIdx.x, w = s_W.w;
+    const int lane = threadIdx.x & 31, w = s_W.w;
     const unsigned* reg = s_W.reg; const double* __restrict__ mod = s_W.mod;
     double* s0 = s_st; double* s1 = s_st + 32; double* s2 = s_st + 64;
     const double* sp = s_st + (lane % 3) * 32;
@@ -542,10 +648,16 @@ __device__ __forceinline__ double l_distsq(double x1, double y1, double x2, doub
 // "fillers", an ascending one "holes", matched through a 32-entry shared buffer.  The removed tail's order is
 // irrelevant (those points are only un-marked).
 __device__ __noinline__ bool l_reduce_region_radius(int* n_io, double reg_angle, double prec, double p, LRect* rec, double density, double density_th) {
-    const int lane = threadIdx.x, w = s_W.w;
-    unsigned* reg = s_W.reg; LPix* pix = s_W.pix;
-    unsigned* s_fill = reinterpret_cast<unsigned*>(s_st);             // 32 filler values (s_st is free between region2rect calls)
+    const int lane = threadIdx.x & 31, w = s_W.w;
     int n = *n_io;
+    if (s_W.mode == 0) {               // speculative attempt: keep the list as it is (the commit validates every pixel ever accepted) and work on a copy
+        if (2 * n + s_W.nasm > s_W.cap) { s_W.abort = 1; return false; }
+        for (int i = lane; i < n; i += 32) s_W.reg[n + i] = s_W.reg[i];
+        s_W.reg += n; s_W.cap -= n;
+        __syncwarp();
+    }
+    unsigned* reg = s_W.reg;
+    unsigned* s_fill = reinterpret_cast<unsigned*>(s_st);             // 32 filler values (s_st is free between region2rect calls)
     const unsigned p0 = reg[0];
     const double xc = (double)(p0 & 0xffff), yc = (double)(p0 >> 16);
     double radSq = fmax(l_distsq(xc, yc, rec->x1, rec->y1), l_distsq(xc, yc, rec->x2, rec->y2));
@@ -560,7 +672,7 @@ __device__ __noinline__ bool l_reduce_region_radius(int* n_io, double reg_angle,
             if (i < n) {
                 const unsigned pk = reg[i];
                 keep = !(l_distsq(xc, yc, (double)(pk & 0xffff), (double)(pk >> 16)) > radSq);
-                if (!keep) pix[(int)(pk >> 16) * w + (int)(pk & 0xffff)].used = 0u;
+                if (!keep) l_release(s_W, (int)(pk >> 16) * w + (int)(pk & 0xffff));
             }
             kept += __popc(__ballot_sync(0xffffffffu, keep));
         }
@@ -611,11 +723,11 @@ __device__ __noinline__ bool l_reduce_region_radius(int* n_io, double reg_angle,
 }
 
 __device__ __noinline__ bool l_refine(int* n_io, double* reg_angle_io, double prec, double p, LRect* rec, double density_th) {
-    const int lane = threadIdx.x, w = s_W.w;
+    const int lane = threadIdx.x & 31, w = s_W.w;
     int n = *n_io;
     double density = (double)n / (l_dist(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
     if (density >= density_th) return true;
-    const unsigned* reg = s_W.reg; const float* __restrict__ ang = s_W.ang; LPix* pix = s_W.pix;
+    const unsigned* reg = s_W.reg; const float* __restrict__ ang = s_W.ang;
     const unsigned p0 = reg[0];
     const int sx = p0 & 0xffff, sy = p0 >> 16;
     const double xc = (double)sx, yc = (double)sy;
@@ -631,7 +743,7 @@ __device__ __noinline__ bool l_refine(int* n_io, double* reg_angle_io, double pr
         if (i < n) {
             const unsigned pk = reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
             const float ad = ang[ry * w + rx];
-            pix[ry * w + rx].used = 0u;
+            l_release(s_W, ry * w + rx);
             in = l_dist(xc, yc, (double)rx, (double)ry) < width;
             const double d = l_angle_diff_signed((double)ad * L_DEG, ang_c);
             // skipped points contribute +0.0, which leaves a running sum unchanged (the sums are never -0.0)
@@ -645,7 +757,11 @@ __device__ __noinline__ bool l_refine(int* n_io, double* reg_angle_io, double pr
     const double sum = __shfl_sync(0xffffffffu, acc, 0), s_sum = __shfl_sync(0xffffffffu, acc, 1);
     const double mean_angle = sum / (double)cnt;
     const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
+    __syncwarp();
+    if (s_W.mode == 0) { s_W.reg += n; s_W.cap -= n; }            // speculative: the first list stays (validated at commit), the regrown one follows it
     n = l_region_grow(sx, sy, tau, reg_angle_io);
+    if (n < 0) { *n_io = 0; return false; }
+    if (s_W.mode == 0) s_W.acc += n;
     *n_io = n;
     if (n < 2) return false;
     l_region2rect(n, *reg_angle_io, prec, p, rec);
@@ -855,58 +971,279 @@ __device__ double l_rect_improve(const Walk& W, LRect& rec, int* s_cnt, double l
 // The order-dependent core: seeds in order, region growing, rectangle fit and the density refinement (the only steps
 // that read or write the `used` map).  rect_improve / NFA of a region is a pure function of its rectangle and of the
 // immutable angle map, so it is NOT done here: the walker emits one job per candidate region and k_lsd_nfa evaluates
-// all jobs of all frames in parallel (one warp per job).  `used` lives in shared memory as a bitmap.
-__global__ void __launch_bounds__(32, 28) k_lsd_regions(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
-    const int lane = threadIdx.x;
-  for (;;) {
-    // frames are pulled from a counter: the grid may be smaller than the batch (sslpl_line_set_max_walkers), which bounds
-    // how many of these long-lived one-warp CTAs (and their registers) sit on every SM next to other kernels
-    int f = 0;
-    if (lane == 0) f = atomicAdd(ws.rejctl + 2, 1);
-    f = __shfl_sync(0xffffffffu, f, 0);
-    if (f >= nframes) break;
+// all jobs of all frames in parallel (one warp per job).
+//
+// ONE CTA PER FRAME, several warps, exact sequential semantics.  The regions of a frame form a sparse dependency graph
+// (tools/sim_spec_walker.cpp: critical path 1/17 of the work at 640x480, 1/100 at 1280x960), but which regions exist and
+// what they depend on is only known by running them.  So the warps run region growing AHEAD of the sequential order and
+// the results are committed strictly IN that order:
+//   * claim  (claim_lock, shared memory only): the next seed, in seed order, that is not in the committed bitmap gets the
+//     next rank `seq` and a slot of a ring (its own list buffer);
+//   * attempt (any warp, speculative): grow / fit / refine exactly as the sequential code would, reading "used" as
+//     committed bitmap | my ticket | live ticket of lower rank (the last one recorded as an assumption), writing only
+//     tickets (LPix.used, global) and its private lists.  A seed already under a live ticket of lower rank is presumed
+//     swallowed; an attempt that loses a pixel to a live attempt of lower rank waits for that rank to retire and starts over;
+//   * commit (commit_lock, in rank order, by whichever warp is idle): the attempt is VALID iff it was not poisoned, none
+//     of the pixels it ever accepted is in the committed bitmap and all the pixels it assumed used are.  Then every
+//     membership test it made had the sequential outcome, so its lists are the sequential ones: its final pixels are
+//     published to the bitmap and its job appended.  Otherwise (and for presumed seeds that were not swallowed after all)
+//     the region is grown on the spot by the "turn holder": everything of lower rank is final, nothing can invalidate it.
+// Bits only go 0 -> 1 and are written only under commit_lock; tickets of retired ranks are garbage by construction.
+__device__ __forceinline__ void l_unlock(int* l) { __threadfence_block(); atomicExch(l, 0); }
+
+struct WalkFrame { const LineGeom* g; const LineWs* ws; int f; unsigned* bits; };
+
+// grow + fit + refine one seed.  Returns 1 = candidate rectangle in *rec, 0 = no job (small or rejected by refine), -1 = abandoned.
+// *n0 = size of the first region, *nfin = pixels that stay used (the list at s_W.reg).
+__device__ __noinline__ int l_one_region(const LineGeom& g, unsigned idx, LRect* rec, int* n0, int* nfin) {
+    WalkCtx& W = s_W;
+    double reg_angle;
+    int n = l_region_grow((int)(idx % (unsigned)g.sw), (int)(idx / (unsigned)g.sw), g.prec, &reg_angle);
+    if (n < 0) return -1;
+    W.acc = n;
+    *n0 = n; *nfin = n;
+    if (n < g.min_reg_size) return 0;
+    l_region2rect(n, reg_angle, g.prec, g.p, rec);
+    const bool okr = l_refine(&n, &reg_angle, g.prec, g.p, rec, 0.7);
+    if (W.abort) return -1;
+    *nfin = n;
+    return okr ? 1 : 0;
+}
+
+__device__ __forceinline__ void l_emit_job(const LineGeom& g, double* dst, const LRect& rec, unsigned idx, int n0, int lane) {
+    if (lane < 13) {
+        const double v[13] = {rec.x1, rec.y1, rec.x2, rec.y2, rec.width, rec.x, rec.y, rec.theta, rec.dx, rec.dy, rec.prec, rec.p, (double)idx * 65536.0 + (double)min(n0, 65535)};
+        double out = v[0];
+#pragma unroll
+        for (int k = 1; k < 13; k++) if (lane == k) out = v[k];
+        dst[lane] = out;
+    }
+}
+
+__device__ __forceinline__ void l_set_bit(unsigned* bits, unsigned pk, int w) { const int q = (int)(pk >> 16) * w + (int)(pk & 0xffff); atomicOr(bits + (q >> 5), 1u << (q & 31)); }
+
+// The turn holder grows the region of seed `idx` for real (commit_lock held, every lower rank committed).
+__device__ __noinline__ void l_turn_region(const WalkFrame& F, unsigned idx, int seq) {
+    const LineGeom& g = *F.g; const LineWs& ws = *F.ws;
+    const int lane = threadIdx.x & 31;
+    const long long t0 = clock64();
+    WalkCtx& W = s_W;
     __syncwarp();
     if (lane == 0) {
-        s_W.w = g.sw; s_W.h = g.sh;
-        s_W.ang = ws.angdeg + f * g.pix_stride; s_W.mod = ws.modgrad + f * g.pix_stride;
-        s_W.pix = ws.pix + f * g.pix_stride; s_W.reg = ws.reg + f * g.pix_stride; s_W.cs0 = ws.cs0 + f * g.pix_stride;
+        W.mode = 1; W.abort = 0; W.seq = seq; W.ticket = (unsigned)(seq + 1) | 0x80000000u;
+        W.reg = ws.reg + (long long)F.f * g.pix_stride; W.base0 = W.reg; W.cap = (int)g.pix_stride; W.nasm = 0; W.acc = 0;
     }
     __syncwarp();
-    const LPix* pix = ws.pix + f * g.pix_stride;
-    const unsigned* seeds = ws.seeds + f * g.pix_stride;
-    const int ns = ws.nseeds[f];
-    double* jobs = ws.jobs + (long long)f * g.seg_cap * 13;
-    int nj = 0;
-    for (int sb = 0; sb < ns; sb += 32) {
-        const bool have = sb + lane < ns;
-        const unsigned mine = have ? seeds[sb + lane] : 0u;                   // 32 seeds per coalesced load
-        unsigned umask = __ballot_sync(0xffffffffu, !have || pix[mine].used != 0u); // their `used` state, one round trip
-        while (~umask) {                                    // angle != NOTDEF holds for every seed
-            const int j = __ffs(~umask) - 1;
-            umask |= (2u << j) - 1u;                        // seeds up to j are done
-            const unsigned idx = __shfl_sync(0xffffffffu, mine, j);
-            double reg_angle;
-            int n = l_region_grow((int)(idx % (unsigned)g.sw), (int)(idx / (unsigned)g.sw), g.prec, &reg_angle);
-            umask |= __ballot_sync(0xffffffffu, !have || pix[mine].used != 0u);    // the region may have swallowed later seeds
-            if (n < g.min_reg_size) continue;
-            LRect rec;
-            l_region2rect(n, reg_angle, g.prec, g.p, &rec);
-            const int n0 = n;
-            const bool okr = l_refine(&n, &reg_angle, g.prec, g.p, &rec, 0.7);
-            umask = ((2u << j) - 1u) | __ballot_sync(0xffffffffu, !have || pix[mine].used != 0u);   // refine can release and re-take pixels
-            if (!okr) continue;
-            if (nj < g.seg_cap && lane < 13) {
-                const double v[13] = {rec.x1, rec.y1, rec.x2, rec.y2, rec.width, rec.x, rec.y, rec.theta, rec.dx, rec.dy, rec.prec, rec.p, (double)idx * 65536.0 + (double)min(n0, 65535)};
-                double out = v[0];
-#pragma unroll
-                for (int k = 1; k < 13; k++) if (lane == k) out = v[k];
-                jobs[(long long)nj * 13 + lane] = out;
-            }
-            nj++;
+    LRect rec; int n0 = 0, nfin = 0;
+    const int r = l_one_region(g, idx, &rec, &n0, &nfin);
+    __syncwarp();
+    for (int i = lane; i < nfin; i += 32) l_set_bit(F.bits, W.reg[i], g.sw);
+    if (r == 1) {
+        const int nj = s_F.nj;
+        if (nj < g.seg_cap) l_emit_job(g, ws.jobs + ((long long)F.f * g.seg_cap + nj) * 13, rec, idx, n0, lane);
+        __syncwarp();
+        if (lane == 0) s_F.nj = nj + 1;
+    }
+    __syncwarp();
+    if (lane == 0) { atomicAdd(ws.wstat + 0, 1ull); atomicAdd(ws.wstat + 1, (unsigned long long)(clock64() - t0)); atomicAdd(ws.wstat + 2, (unsigned long long)nfin); }
+}
+
+// commit slot `k` (rank `seq`); commit_lock held
+__device__ __noinline__ void l_commit_slot(const WalkFrame& F, int k, int seq) {
+    const LineGeom& g = *F.g; const LineWs& ws = *F.ws;
+    const int lane = threadIdx.x & 31;
+    const int st = s_F.state[k];
+    if (s_F.seedpix[k] < 0) return;                               // the sentinel claim that closes the frame
+    const unsigned idx = (unsigned)s_F.seedpix[k];
+    if (l_bit(F.bits, (int)idx)) { if (lane == 0) atomicAdd(ws.wstat + 4, 1ull); return; }     // swallowed by a region of lower rank: nothing to do
+    bool ok = st == SLOT_DONE && !s_F.poison[k];
+    const int acc = s_F.acc[k], nasm = s_F.nasm[k], finoff = s_F.finoff[k], nfin = s_F.nfin[k];
+    const bool small = finoff == 0 && acc + nasm <= WALK_SMALL && !(g.dbg & 2);    // everything needed is in shared memory
+    const unsigned* list = ws.sreg + ((long long)F.f * WALK_RING + k) * WALK_SLOT_CAP;
+    if (ok) {
+        bool bad = false;
+        if (small) {
+            if (lane < acc) { const unsigned pk = s_F.small[k][lane]; bad = l_bit(F.bits, (int)(pk >> 16) * g.sw + (int)(pk & 0xffff)); }
+            else if (lane < acc + nasm) bad = !l_bit(F.bits, (int)s_F.small[k][lane]);
+        } else {
+            for (int i = lane; i < acc; i += 32) { const unsigned pk = __ldcg(list + i); bad |= l_bit(F.bits, (int)(pk >> 16) * g.sw + (int)(pk & 0xffff)); }
+            for (int i = lane; i < nasm; i += 32) bad |= !l_bit(F.bits, (int)__ldcg(list + WALK_SLOT_CAP - 1 - i));
         }
+        ok = !__any_sync(0xffffffffu, bad);
     }
-    if (lane == 0) { ws.njobs[f] = min(nj, g.seg_cap); if (nj > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
+    if (!ok) {
+        if (lane == 0) atomicAdd(ws.wstat + 5 + (st == SLOT_PRESUMED ? 3 : (st != SLOT_DONE ? 0 : (s_F.poison[k] ? 1 : 2))), 1ull);
+        l_turn_region(F, idx, seq);
+        return;
+    }
+    if (lane == 0) { atomicAdd(ws.wstat + 9, 1ull); atomicAdd(ws.wstat + 10, (unsigned long long)nfin); }
+    if (small) { if (lane < nfin) l_set_bit(F.bits, s_F.small[k][lane], g.sw); }
+    else for (int i = lane; i < nfin; i += 32) l_set_bit(F.bits, __ldcg(list + finoff + i), g.sw);
+    if (s_F.job[k]) {
+        const int nj = s_F.nj;
+        if (nj < g.seg_cap && lane < 13) ws.jobs[((long long)F.f * g.seg_cap + nj) * 13 + lane] = __ldcg(ws.sjob + ((long long)F.f * WALK_RING + k) * 13 + lane);
+        __syncwarp();
+        if (lane == 0) s_F.nj = nj + 1;
+    }
     __syncwarp();
+}
+
+// claim the next seed (claim_lock held by this warp): returns the slot, -1 when the ring is full, -2 for the closing sentinel
+__device__ __noinline__ int l_claim(const WalkFrame& F) {
+    const LineGeom& g = *F.g; const LineWs& ws = *F.ws;
+    const int lane = threadIdx.x & 31;
+    const unsigned* seeds = ws.seeds + (long long)F.f * g.pix_stride;
+    const int ns = s_F.ns;
+    const unsigned nclaims = s_F.nclaims;
+    if (s_F.all_claimed || nclaims - l_turn() >= (unsigned)WALK_RING) return -1;
+    const int k = (int)(nclaims % WALK_RING);
+    if (*reinterpret_cast<volatile int*>(&s_F.state[k]) != SLOT_EMPTY) return -1;
+    int cur = (int)s_F.cursor, found = ns;
+    unsigned pixidx = 0;
+    while (cur < ns) {
+        int wb = s_F.win_base;
+        if (cur < wb || cur >= wb + WALK_WIN) {                    // stage the next window of the ordered seed list
+            wb = cur & ~31;
+            for (int i = lane; i < WALK_WIN; i += 32) s_F.win[i] = wb + i < ns ? seeds[wb + i] : 0u;
+            if (lane == 0) s_F.win_base = wb;
+            __syncwarp();
+        }
+        const int i = cur + lane;
+        const bool have = i < ns && i < wb + WALK_WIN;
+        const unsigned mine = have ? s_F.win[i - wb] : 0u;
+        const unsigned fm = __ballot_sync(0xffffffffu, have && !l_bit(F.bits, (int)mine));
+        if (fm) { const int j = __ffs(fm) - 1; found = cur + j; pixidx = __shfl_sync(0xffffffffu, mine, j); break; }
+        cur = min(cur + 32, wb + WALK_WIN);
+    }
+    if (lane == 0) {
+        s_F.seqof[k] = (int)nclaims; s_F.seedpix[k] = found >= ns ? -1 : (int)pixidx; s_F.poison[k] = 0; s_F.job[k] = 0;
+        *reinterpret_cast<volatile int*>(&s_F.state[k]) = found >= ns ? SLOT_ABORTED : SLOT_RUNNING;     // the sentinel has nothing to grow
+        s_F.cursor = (unsigned)min(found + 1, ns);
+        if (found >= ns) s_F.all_claimed = 1;
+        __threadfence_block();
+        s_F.nclaims = nclaims + 1;
+    }
+    __syncwarp();
+    return found >= ns ? -2 : k;
+}
+
+__global__ void __launch_bounds__(WALK_MAXW * 32) k_lsd_regions(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
+    extern __shared__ unsigned s_bits[];                       // committed `used` bitmap of the frame
+    const int lane = threadIdx.x & 31;
+    const int nwords = (int)((g.pix_stride + 31) >> 5);
+  for (;;) {
+    // frames are pulled from a counter: the grid may be smaller than the batch (sslpl_line_set_max_walkers)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int f = atomicAdd(ws.rejctl + 2, 1);
+        s_F.frame = f; s_F.cursor = 0; s_F.nclaims = 0; s_F.turn = 0; s_F.claim_lock = 0; s_F.commit_lock = 0; s_F.all_claimed = 0; s_F.nj = 0; s_F.win_base = -(1 << 30);
+        s_F.ns = f < nframes ? ws.nseeds[f] : 0;
+        for (int k = 0; k < WALK_RING; k++) { s_F.state[k] = SLOT_EMPTY; s_F.poison[k] = 0; }
+    }
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) s_bits[i] = 0u;
+    __syncthreads();
+    const int f = s_F.frame;
+    if (f >= nframes) break;
+    const long long tf0 = clock64();
+    WalkFrame F; F.g = &g; F.ws = &ws; F.f = f; F.bits = s_bits;
+    WalkCtx& W = s_W;
+    if (lane == 0) {
+        W.w = g.sw; W.h = g.sh;
+        W.ang = ws.angdeg + f * g.pix_stride; W.mod = ws.modgrad + f * g.pix_stride;
+        W.pix = ws.pix + f * g.pix_stride; W.cs0 = ws.cs0 + f * g.pix_stride; W.bits = s_bits; W.dbg = g.dbg;
+    }
+    __syncwarp();
+    int myslot = -1, tries = 0, waitfor = -1;                  // an attempt of this warp waiting for rank `waitfor` to retire
+    for (;;) {
+        // ---- 1. commits, by whoever finds the head of the ring finished
+        int did = 0;
+        {
+            int go = 0;
+            if (lane == 0) {
+                const unsigned t = l_turn();
+                if (t < *reinterpret_cast<volatile unsigned*>(&s_F.nclaims)) {
+                    const int st = *reinterpret_cast<volatile int*>(&s_F.state[t % WALK_RING]);
+                    if (st >= SLOT_DONE && atomicCAS(&s_F.commit_lock, 0, 1) == 0) { __threadfence_block(); go = 1; }
+                }
+            }
+            go = __shfl_sync(0xffffffffu, go, 0);
+            if (go) {
+                const long long tc0 = clock64();
+                for (;;) {
+                    const unsigned t = l_turn();
+                    if (t >= *reinterpret_cast<volatile unsigned*>(&s_F.nclaims)) break;
+                    const int k = (int)(t % WALK_RING);
+                    if (*reinterpret_cast<volatile int*>(&s_F.state[k]) < SLOT_DONE) break;
+                    __syncwarp();
+                    l_commit_slot(F, k, (int)t);
+                    __syncwarp();
+                    if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&s_F.state[k]) = SLOT_EMPTY; __threadfence_block(); *reinterpret_cast<volatile unsigned*>(&s_F.turn) = t + 1; }
+                    __syncwarp();
+                    did = 1;
+                }
+                if (lane == 0) { atomicAdd(ws.wstat + 11, (unsigned long long)(clock64() - tc0)); l_unlock(&s_F.commit_lock); }
+                __syncwarp();
+            }
+        }
+        if (did) continue;
+        // ---- 2. an attempt: a new claim, or the repetition of one that had to wait for a lower rank
+        if (myslot < 0) {
+            int go = 0;
+            if (lane == 0 && !*reinterpret_cast<volatile int*>(&s_F.all_claimed) &&
+                *reinterpret_cast<volatile unsigned*>(&s_F.nclaims) - l_turn() < (unsigned)WALK_RING && atomicCAS(&s_F.claim_lock, 0, 1) == 0) { __threadfence_block(); go = 1; }
+            go = __shfl_sync(0xffffffffu, go, 0);
+            if (go) {
+                const long long tk0 = clock64();
+                const int k = l_claim(F);
+                if (lane == 0) { atomicAdd(ws.wstat + 12, (unsigned long long)(clock64() - tk0)); l_unlock(&s_F.claim_lock); }
+                __syncwarp();
+                if (k >= 0) { myslot = k; tries = 0; waitfor = -1; }
+            }
+        }
+        if (myslot >= 0 && (waitfor < 0 || (int)l_turn() > waitfor)) {
+            const int k = myslot;
+            const unsigned idx = (unsigned)s_F.seedpix[k];
+            if (lane == 0) {
+                W.mode = 0; W.abort = 0; W.conflict = -1; W.nasm = 0; W.acc = 0; W.seq = s_F.seqof[k];
+                W.ticket = (unsigned)(W.seq + 1) | ((unsigned)(tries & 127) << 24);
+                W.reg = ws.sreg + ((long long)f * WALK_RING + k) * WALK_SLOT_CAP; W.base0 = W.reg; W.cap = WALK_SLOT_CAP;
+            }
+            __syncwarp();
+            LRect rec; int n0 = 0, nfin = 0;
+            int r = -1;
+            if (l_bit(s_bits, (int)idx)) { if (lane == 0) W.abort = 3; __syncwarp(); }     // swallowed while this attempt waited
+            else r = l_one_region(g, idx, &rec, &n0, &nfin);
+            __syncwarp();
+            if (r < 0 && W.abort == 2 && tries < 100 && !(g.dbg & 1)) {           // a live attempt of lower rank holds a pixel this one needs: repeat after it retires
+                waitfor = W.conflict; tries++;
+                if (lane == 0) atomicAdd(ws.wstat + 13, 1ull);
+                __syncwarp();
+                continue;
+            }
+            if (r == 1) l_emit_job(g, ws.sjob + ((long long)f * WALK_RING + k) * 13, rec, idx, n0, lane);
+            int st = SLOT_DONE;
+            if (r < 0) st = W.abort == 3 ? SLOT_PRESUMED : SLOT_ABORTED;
+            else {
+                const int acc = W.acc, nasm = W.nasm, finoff = (int)(W.reg - W.base0);
+                if (finoff == 0 && acc + nasm <= WALK_SMALL && !(g.dbg & 2)) {   // small attempt: its lists travel through shared memory
+                    if (lane < acc) s_F.small[k][lane] = W.base0[lane];
+                    else if (lane < acc + nasm) s_F.small[k][lane] = W.base0[WALK_SLOT_CAP - 1 - (lane - acc)];
+                }
+                if (lane == 0) { s_F.acc[k] = acc; s_F.nasm[k] = nasm; s_F.finoff[k] = finoff; s_F.nfin[k] = nfin; s_F.job[k] = r == 1; }
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence(); *reinterpret_cast<volatile int*>(&s_F.state[k]) = st; }
+            __syncwarp();
+            myslot = -1;
+            continue;
+        }
+        // ---- 3. done?
+        if (myslot < 0 && *reinterpret_cast<volatile int*>(&s_F.all_claimed) && l_turn() >= *reinterpret_cast<volatile unsigned*>(&s_F.nclaims)) break;
+        __nanosleep(100);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { atomicAdd(ws.wstat + 14, (unsigned long long)(clock64() - tf0)); atomicAdd(ws.wstat + 15, (unsigned long long)s_F.nclaims);
+        ws.njobs[f] = min(s_F.nj, g.seg_cap); if (s_F.nj > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
   }
 }
 
@@ -1246,6 +1583,7 @@ struct sslpl_line {
     int used_smem = 0;
     int sm_count = 148;
     int max_walkers = 0;        // 0 = one walker CTA per frame
+    int walker_warps = 0;       // 0 = automatic (8 or 16 warps per frame)
     int cur_w = 0, cur_h = 0, cur_frames = 0;
     long long launches = 0;
     int* h_err = nullptr;
@@ -1281,6 +1619,7 @@ void make_geometry(const sslpl_line* h, int W, int H, LineGeom& g, std::vector<i
     g.min_reg_size = (int)size_t(-g.log_nt / std::log10(g.p));
     g.seg_cap = (int)(g.pix_stride / std::max(g.min_reg_size, 1)) + 16;
     g.trace_cap = h->trace ? g.seg_cap : 0;
+    g.dbg = getenv("SSLPL_WALKER_DBG") ? atoi(getenv("SSLPL_WALKER_DBG")) : 0;
     if (tab) {
         tab->assign(g.sw + g.sh, make_int2(0, 0));
         for (int axis = 0; axis < 2; axis++) {
@@ -1309,6 +1648,8 @@ void carve(sslpl_line* h, Arena& A, const LineGeom& g, int B) {
     ws.maxgrad = A.take<unsigned long long>(B);
     ws.seeds = A.take<unsigned>((size_t)B * g.pix_stride); ws.nseeds = A.take<int>(B);
     ws.reg = A.take<unsigned>((size_t)B * g.pix_stride);
+    ws.sreg = A.take<unsigned>((size_t)B * WALK_RING * WALK_SLOT_CAP); ws.sjob = A.take<double>((size_t)B * WALK_RING * 13);
+    ws.wstat = A.take<unsigned long long>(16);
     ws.seg = A.take<double>((size_t)B * g.seg_cap * 4); ws.nseg = A.take<int>(B);
     ws.jobs = A.take<double>((size_t)B * g.seg_cap * 13); ws.njobs = A.take<int>(B); ws.jobflag = A.take<int>((size_t)B * g.seg_cap);
     ws.jobnk = A.take<int2>((size_t)B * g.seg_cap); ws.jobnfa = A.take<double>((size_t)B * g.seg_cap);
@@ -1372,7 +1713,13 @@ int run_pipeline(sslpl_line* h, int B) {
     k_lsd_seeds<<<B, SEED_WARPS * 32, 0, st>>>(g, h->ws);
     lmark(h, "lsd_seeds");
     SSLPL_CUDA(cudaMemsetAsync(h->ws.rejctl, 0, 4 * sizeof(int), st));
-    k_lsd_regions<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), 32, 0, st>>>(g, h->ws, B);
+    SSLPL_CUDA(cudaMemsetAsync(h->ws.wstat, 0, 16 * sizeof(unsigned long long), st));
+    {   // one CTA per frame; few frames -> more warps per frame (latency), many frames -> more CTAs per SM (throughput)
+        const int ww = h->walker_warps > 0 ? std::min(h->walker_warps, WALK_MAXW) : (B >= 2 * h->sm_count ? 8 : WALK_MAXW);
+        const size_t smem = (size_t)((g.pix_stride + 31) / 32) * sizeof(unsigned);
+        if ((int)smem > h->used_smem) { SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); h->used_smem = (int)smem; }
+        k_lsd_regions<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), ww * 32, smem, st>>>(g, h->ws, B);
+    }
     lmark(h, "lsd_regions");
     k_lsd_nfa_count<<<dim3(NFA_COUNT_CTAS, B), 128, 0, st>>>(g, h->ws);
     k_lsd_nfa_first<<<dim3(NFA_FIRST_CTAS, B), 128, 0, st>>>(g, h->ws);
@@ -1413,6 +1760,7 @@ int sslpl_line_create(const sslpl_line_params* p, sslpl_line** out) {
     h->p = *p;
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && v > 0) h->sm_count = v; }
     h->trace = getenv("SSLPL_LINE_TRACE") != nullptr;
+    if (const char* e = getenv("SSLPL_WALKER_WARPS")) h->walker_warps = std::max(1, std::min(WALK_MAXW, atoi(e)));   // tuning knob (tests sweep it)
     {   // BinaryDescriptor constructor: local (F_l) and global (F_g) Gaussian weights, widthOfBand 7, 9 bands
         double u = (7 * 3 - 1) / 2, sigma = (7 * 2 + 1) / 2, inv = -1 / (2 * sigma * sigma);
         for (int i = 0; i < 21; i++) { const double d = i - u; h->coef.L[i] = (float)exp(d * d * inv); }
@@ -1544,6 +1892,18 @@ int sslpl_line_download_segments(sslpl_line* h, int frame, float* seg4, int cap,
 
 
 /* debug (SSLPL_LINE_TRACE=1 at handle creation): one row of 10 doubles per region that reached region2rect */
+/* Statistics of the last region-walker launch (16 values): [0] regions grown by the turn holder, [1] their clock cycles, [2] their
+   pixels, [3] -, [4] claims whose seed had been swallowed by commit time, [5] redone by the turn holder: abandoned, [6] poisoned,
+   [7] failed validation, [8] presumed swallowed but not, [9] attempts committed as speculated, [10] their pixels, [11] cycles
+   under the commit lock, [12] under the claim lock, [13] attempts repeated after a lower rank retired, [14] cycles per frame
+   (summed), [15] claims. */
+int sslpl_line_walker_stats(sslpl_line* h, unsigned long long* out16) {
+    SSLPL_REQUIRE(h && out16, SSLPL_ERR_ARG, "null argument");
+    SSLPL_CUDA(cudaSetDevice(h->p.device));
+    SSLPL_CUDA(cudaStreamSynchronize(h->stream));
+    SSLPL_CUDA(cudaMemcpy(out16, h->ws.wstat, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return SSLPL_OK;
+}
 int sslpl_line_debug_trace(sslpl_line* h, int frame, double* out, int cap_rows, int* n) {
     SSLPL_REQUIRE(h && n && frame >= 0 && frame < h->cur_frames, SSLPL_ERR_ARG, "bad argument");
     SSLPL_REQUIRE(h->g.trace_cap > 0, SSLPL_ERR_UNSUPPORTED, "tracing is off (set SSLPL_LINE_TRACE=1 before creating the handle)");
