@@ -344,13 +344,17 @@ struct FrameCtl {               // one per walker CTA
     int claim_lock, commit_lock, all_claimed, nj, frame, ns, win_base;
     unsigned win[WALK_WIN];
     int seqof[WALK_RING], seedpix[WALK_RING], state[WALK_RING], acc[WALK_RING], nasm[WALK_RING], finoff[WALK_RING], nfin[WALK_RING], job[WALK_RING], poison[WALK_RING];
+    double jobv[WALK_RING][13];                 // the pending NFA job of the slot
     unsigned small[WALK_RING][WALK_SMALL];      // acc + nasm <= WALK_SMALL and finoff == 0: accepted list, then the assumed pixels (as indices)
 };
 __shared__ WalkCtx s_Wc[WALK_MAXW];
 __shared__ FrameCtl s_F;
 __shared__ __align__(16) double s_stc[WALK_MAXW][96];     // per warp: staging of a 32-point chunk: 3 quantities x 32
-#define s_W (s_Wc[threadIdx.x >> 5])
-#define s_st (s_stc[threadIdx.x >> 5])
+__shared__ WalkCtx s_W1;                                   // the one-warp throughput kernel keeps its own small context:
+__shared__ __align__(16) double s_st1[96];                 // 28 of its CTAs share an SM
+constexpr int SOLO = 0;                                    // (hidden by the template parameter of the same name inside the helpers)
+#define s_W (*(SOLO ? &s_W1 : &s_Wc[threadIdx.x >> 5]))
+#define s_st (SOLO ? s_st1 : s_stc[threadIdx.x >> 5])
 
 // SLOT_PRESUMED: the seed was under the ticket of a live attempt of lower rank when its turn to be grown came: it is presumed
 // swallowed; the commit checks (and grows it for real if it was not).  SLOT_ABORTED: to be redone by the turn holder.
@@ -361,7 +365,7 @@ __device__ __forceinline__ unsigned l_turn() { return *reinterpret_cast<volatile
 __device__ __forceinline__ bool l_bit(const unsigned* bits, int q) { return (reinterpret_cast<const volatile unsigned*>(bits)[q >> 5] >> (q & 31)) & 1u; }
 // Is ticket m (not mine) held by an attempt that has not been retired yet?  Ranks below `turn` are committed or discarded.
 __device__ __forceinline__ bool l_live(unsigned m, int* seq_out) { const int s = (int)(m & 0xffffffu) - 1; *seq_out = s; return m != 0u && s >= (int)l_turn(); }
-__device__ __forceinline__ void l_release(const WalkCtx& W, int q) { atomicCAS(&W.pix[q].used, W.ticket, 0u); }
+template <int SOLO> __device__ __forceinline__ void l_release(const WalkCtx& W, int q) { if (SOLO) W.pix[q].used = 0u; else atomicCAS(&W.pix[q].used, W.ticket, 0u); }
 
 __device__ __forceinline__ bool l_aligned(float angdeg, double theta, double prec) {
     if (angdeg == NOTDEF_F) return false;
@@ -413,7 +417,7 @@ __device__ __forceinline__ int l_take_resolve(const WalkCtx& W, LTake& t) {
     return (l_live(old, &s) && s < W.seq) ? s : -2;
 }
 
-__device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* reg_angle_out) {
+template <int SOLO> __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* reg_angle_out) {
     WalkCtx& W = s_W;
     const int lane = threadIdx.x & 31, w = W.w, h = W.h;
     LPix* pix = W.pix; unsigned* reg = W.reg; const unsigned* bits = W.bits;
@@ -421,19 +425,20 @@ __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* r
     const int sq = sy * w + sx;                                   // 32-bit pixel indices (sw * sh < 2^31)
     LTake tk; tk.pend = false; tk.q = 0; tk.seen = 0u; tk.old = 0u;
     int failrank = -1;                                            // -1 fine, >= 0 rank to wait for, -2 repeat at once
-    {
+    if (SOLO) { if (lane == 0) { reg[0] = (unsigned)sx | ((unsigned)sy << 16); pix[sq].used = 1u; } }
+    else {
         int fail = 0;
         if (lane == 0) {
             reg[0] = (unsigned)sx | ((unsigned)sy << 16);
             const unsigned m0 = __ldcg(&pix[sq].used);
             int s0;
             if (m0 != T) {
-                if (spec && l_live(m0, &s0) && s0 < myseq) fail = 3;          // an in-flight region of lower rank reached the seed first
-                else { l_take_issue(W, tk, sq, m0); const int r = l_take_resolve(W, tk); if (r >= 0) fail = 3; else if (r == -2) fail = 2; }
+                if (spec && l_live(m0, &s0) && s0 < myseq) fail = 3;          // an in-flight region of lower rank reached the seed first: presumed swallowed
+                else { W.conflict = -1; l_take_issue(W, tk, sq, m0); const int r = l_take_resolve(W, tk); if (r >= 0) fail = 3; else if (r == -2) fail = 2; }
             }
         }
         fail = __shfl_sync(0xffffffffu, fail, 0);
-        if (fail) { W.abort = fail; W.conflict = -1; return -1; }
+        if (fail) { W.abort = fail; return -1; }
     }
     double reg_angle = (double)__ldg(W.ang + sq) * L_DEG;
     const float2 c0 = __ldg(W.cs0 + sq);
@@ -457,12 +462,13 @@ __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* r
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(pix + (yn * w + xn)));
         }
         uint4 v = make_uint4(__float_as_uint(NOTDEF_F), 0u, 0u, 0u);
-        if (valid) v = __ldcg(reinterpret_cast<const uint4*>(pix + q));       // record + ticket in one load (L2: the ticket is mutable)
-        { const int r = l_take_resolve(W, tk); if (r != -1) failrank = (r >= 0 && r > failrank) ? r : (failrank >= 0 ? failrank : r); }   // last step's atomic, while this step's loads fly
+        if (valid) v = SOLO ? *reinterpret_cast<const uint4*>(pix + q) : __ldcg(reinterpret_cast<const uint4*>(pix + q));   // record + ticket in one load (L2: the ticket is mutable)
+        if (!SOLO) { const int r = l_take_resolve(W, tk); if (r != -1) failrank = (r >= 0 && r > failrank) ? r : (failrank >= 0 ? failrank : r); }   // last step's atomic, while this step's loads fly
         const float a = __uint_as_float(v.x), cx = __uint_as_float(v.y), cy = __uint_as_float(v.z);
         const unsigned m = v.w;
         bool cand = false, assumed = false;
-        if (valid && a != NOTDEF_F && m != T && !l_bit(bits, q)) {
+        if (SOLO) cand = valid && a != NOTDEF_F && m == 0u;
+        else if (valid && a != NOTDEF_F && m != T && !l_bit(bits, q)) {
             int s;
             if (spec && l_live(m, &s) && s < myseq) { assumed = true; if (W.dbg & 16) failrank = s > failrank ? s : failrank; }
             else cand = true;
@@ -486,7 +492,7 @@ __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* r
                 const int k0 = __ffs(S0) - 1;
                 const float kx = __shfl_sync(0xffffffffu, cx, k0), ky = __shfl_sync(0xffffffffu, cy, k0);
                 const int q0 = __shfl_sync(0xffffffffu, q, k0);
-                if (lane == k0) { reg[n] = (unsigned)xx | ((unsigned)yy << 16); l_take_issue(W, tk, q, m); }
+                if (lane == k0) { reg[n] = (unsigned)xx | ((unsigned)yy << 16); if (SOLO) pix[q].used = 1u; else l_take_issue(W, tk, q, m); }
                 n++;
                 sumdx += kx; sumdy += ky;
                 reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * L_DEG;
@@ -525,7 +531,7 @@ __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* r
                 const unsigned acc = __ballot_sync(0xffffffffu, actual);
                 A = (S & ((1u << src) - 1u)) | (acc & (1u << src));
             }
-            if ((A >> lane) & 1u) { reg[n + __popc(A & lt)] = (unsigned)xx | ((unsigned)yy << 16); l_take_issue(W, tk, q, m); }
+            if ((A >> lane) & 1u) { reg[n + __popc(A & lt)] = (unsigned)xx | ((unsigned)yy << 16); if (SOLO) pix[q].used = 1u; else l_take_issue(W, tk, q, m); }
             n += __popc(A);
             const float selx = actual ? ax : bx, sely = actual ? ay : by;
             const double sela = actual ? aft : bef;
@@ -536,9 +542,10 @@ __device__ __noinline__ int l_region_grow(int sx, int sy, double prec, double* r
             pending &= ~__ballot_sync(0xffffffffu, mep && (peers & A) != 0u);   // later holders of accepted pixels
         }
         __syncwarp();
-        if (spec && __any_sync(0xffffffffu, failrank != -1)) break;            // lost a pixel: stop growing now
+        if (!SOLO && spec && __any_sync(0xffffffffu, failrank != -1)) break;   // lost a pixel: stop growing now
         i += cnt;
     }
+    if (SOLO) { *reg_angle_out = reg_angle; return n; }
     { const int r = l_take_resolve(W, tk); if (r != -1) failrank = (r >= 0 && r > failrank) ? r : (failrank >= 0 ? failrank : r); }
     const bool lostany = __any_sync(0xffffffffu, failrank != -1);
     failrank = __reduce_max_sync(0xffffffffu, failrank);          // the highest rank to wait for (-1 / -2 lanes do not count)
@@ -557,7 +564,7 @@ __device__ __forceinline__ double l_angle_diff_signed(double a, double b) {
 
 // Sum of the three staged quantities of one chunk, in list order: lane c (c = lane % 3) owns accumulator c, so a
 // point costs one shared load and one add per warp instead of three of each.
-__device__ __noinline__ double l_chunk_sum(const double* sp, int m, double acc) {
+template <int SOLO> __device__ __noinline__ double l_chunk_sum(const double* sp, int m, double acc) {
     if (m == 32) {
         const double2* s2 = reinterpret_cast<const double2*>(sp);
 #pragma unroll
@@ -573,7 +580,7 @@ __device__ __noinline__ double l_chunk_sum(const double* sp, int m, double acc) 
 // the CPU, but only the ADDS are sequential: each lane forms the products of its own point, stages them in shared
 // memory, and lanes 0..2 (replicated over the warp) each walk one of the three staged rows.  The extents are exact
 // min/max.
-__device__ __noinline__ void l_region2rect(int n, double reg_angle, double prec, double p, LRect* out) {
+template <int SOLO> __device__ __noinline__ void l_region2rect(int n, double reg_angle, double prec, double p, LRect* out) {
     const int lane = threadIdx.x & 31, w = s_W.w;
     const unsigned* reg = s_W.reg; const double* __restrict__ mod = s_W.mod;
     double* s0 = s_st; double* s1 = s_st + 32; double* s2 = s_st + 64;
@@ -588,7 +595,7 @@ __device__ __noinline__ void l_region2rect(int n, double reg_angle, double prec,
             s0[lane] = (double)rx * wg; s1[lane] = (double)ry * wg; s2[lane] = wg;
         }
         __syncwarp();
-        acc = l_chunk_sum(sp, min(32, n - b), acc);
+        acc = l_chunk_sum<SOLO>(sp, min(32, n - b), acc);
         __syncwarp();
     }
     double x = __shfl_sync(0xffffffffu, acc, 0), y = __shfl_sync(0xffffffffu, acc, 1);
@@ -605,7 +612,7 @@ __device__ __noinline__ void l_region2rect(int n, double reg_angle, double prec,
             s0[lane] = dy * dy * wg; s1[lane] = dx * dx * wg; s2[lane] = -(dx * dy * wg);      // Ixy -= v  ==  Ixy += -v
         }
         __syncwarp();
-        acc = l_chunk_sum(sp, min(32, n - b), acc);
+        acc = l_chunk_sum<SOLO>(sp, min(32, n - b), acc);
         __syncwarp();
     }
     const double Ixx = __shfl_sync(0xffffffffu, acc, 0), Iyy = __shfl_sync(0xffffffffu, acc, 1), Ixy = __shfl_sync(0xffffffffu, acc, 2);
@@ -647,10 +654,10 @@ __device__ __forceinline__ double l_distsq(double x1, double y1, double x2, doub
 // in DESCENDING position order.  That is computed here chunk-wise with ballots: a descending cursor collects
 // "fillers", an ascending one "holes", matched through a 32-entry shared buffer.  The removed tail's order is
 // irrelevant (those points are only un-marked).
-__device__ __noinline__ bool l_reduce_region_radius(int* n_io, double reg_angle, double prec, double p, LRect* rec, double density, double density_th) {
+template <int SOLO> __device__ __noinline__ bool l_reduce_region_radius(int* n_io, double reg_angle, double prec, double p, LRect* rec, double density, double density_th) {
     const int lane = threadIdx.x & 31, w = s_W.w;
     int n = *n_io;
-    if (s_W.mode == 0) {               // speculative attempt: keep the list as it is (the commit validates every pixel ever accepted) and work on a copy
+    if (!SOLO && s_W.mode == 0) {      // speculative attempt: keep the list as it is (the commit validates every pixel ever accepted) and work on a copy
         if (2 * n + s_W.nasm > s_W.cap) { s_W.abort = 1; return false; }
         for (int i = lane; i < n; i += 32) s_W.reg[n + i] = s_W.reg[i];
         s_W.reg += n; s_W.cap -= n;
@@ -672,7 +679,7 @@ __device__ __noinline__ bool l_reduce_region_radius(int* n_io, double reg_angle,
             if (i < n) {
                 const unsigned pk = reg[i];
                 keep = !(l_distsq(xc, yc, (double)(pk & 0xffff), (double)(pk >> 16)) > radSq);
-                if (!keep) l_release(s_W, (int)(pk >> 16) * w + (int)(pk & 0xffff));
+                if (!keep) l_release<SOLO>(s_W, (int)(pk >> 16) * w + (int)(pk & 0xffff));
             }
             kept += __popc(__ballot_sync(0xffffffffu, keep));
         }
@@ -715,14 +722,14 @@ __device__ __noinline__ bool l_reduce_region_radius(int* n_io, double reg_angle,
         n = m2;
         __syncwarp();
         if (n < 2) { *n_io = n; return false; }
-        l_region2rect(n, reg_angle, prec, p, rec);
+        l_region2rect<SOLO>(n, reg_angle, prec, p, rec);
         density = (double)n / (l_dist(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
     }
     *n_io = n;
     return true;
 }
 
-__device__ __noinline__ bool l_refine(int* n_io, double* reg_angle_io, double prec, double p, LRect* rec, double density_th) {
+template <int SOLO> __device__ __noinline__ bool l_refine(int* n_io, double* reg_angle_io, double prec, double p, LRect* rec, double density_th) {
     const int lane = threadIdx.x & 31, w = s_W.w;
     int n = *n_io;
     double density = (double)n / (l_dist(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
@@ -743,7 +750,7 @@ __device__ __noinline__ bool l_refine(int* n_io, double* reg_angle_io, double pr
         if (i < n) {
             const unsigned pk = reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
             const float ad = ang[ry * w + rx];
-            l_release(s_W, ry * w + rx);
+            l_release<SOLO>(s_W, ry * w + rx);
             in = l_dist(xc, yc, (double)rx, (double)ry) < width;
             const double d = l_angle_diff_signed((double)ad * L_DEG, ang_c);
             // skipped points contribute +0.0, which leaves a running sum unchanged (the sums are never -0.0)
@@ -751,22 +758,22 @@ __device__ __noinline__ bool l_refine(int* n_io, double* reg_angle_io, double pr
         }
         cnt += __popc(__ballot_sync(0xffffffffu, in));
         __syncwarp();
-        acc = l_chunk_sum(sp, min(32, n - b), acc);
+        acc = l_chunk_sum<SOLO>(sp, min(32, n - b), acc);
         __syncwarp();
     }
     const double sum = __shfl_sync(0xffffffffu, acc, 0), s_sum = __shfl_sync(0xffffffffu, acc, 1);
     const double mean_angle = sum / (double)cnt;
     const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
     __syncwarp();
-    if (s_W.mode == 0) { s_W.reg += n; s_W.cap -= n; }            // speculative: the first list stays (validated at commit), the regrown one follows it
-    n = l_region_grow(sx, sy, tau, reg_angle_io);
+    if (!SOLO && s_W.mode == 0) { s_W.reg += n; s_W.cap -= n; }   // speculative: the first list stays (validated at commit), the regrown one follows it
+    n = l_region_grow<SOLO>(sx, sy, tau, reg_angle_io);
     if (n < 0) { *n_io = 0; return false; }
-    if (s_W.mode == 0) s_W.acc += n;
+    if (!SOLO && s_W.mode == 0) s_W.acc += n;
     *n_io = n;
     if (n < 2) return false;
-    l_region2rect(n, *reg_angle_io, prec, p, rec);
+    l_region2rect<SOLO>(n, *reg_angle_io, prec, p, rec);
     density = (double)n / (l_dist(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
-    if (density < density_th) return l_reduce_region_radius(n_io, *reg_angle_io, prec, p, rec, density, density_th);
+    if (density < density_th) return l_reduce_region_radius<SOLO>(n_io, *reg_angle_io, prec, p, rec, density, density_th);
     return true;
 }
 
@@ -998,13 +1005,13 @@ struct WalkFrame { const LineGeom* g; const LineWs* ws; int f; unsigned* bits; }
 __device__ __noinline__ int l_one_region(const LineGeom& g, unsigned idx, LRect* rec, int* n0, int* nfin) {
     WalkCtx& W = s_W;
     double reg_angle;
-    int n = l_region_grow((int)(idx % (unsigned)g.sw), (int)(idx / (unsigned)g.sw), g.prec, &reg_angle);
+    int n = l_region_grow<0>((int)(idx % (unsigned)g.sw), (int)(idx / (unsigned)g.sw), g.prec, &reg_angle);
     if (n < 0) return -1;
     W.acc = n;
     *n0 = n; *nfin = n;
     if (n < g.min_reg_size) return 0;
-    l_region2rect(n, reg_angle, g.prec, g.p, rec);
-    const bool okr = l_refine(&n, &reg_angle, g.prec, g.p, rec, 0.7);
+    l_region2rect<0>(n, reg_angle, g.prec, g.p, rec);
+    const bool okr = l_refine<0>(&n, &reg_angle, g.prec, g.p, rec, 0.7);
     if (W.abort) return -1;
     *nfin = n;
     return okr ? 1 : 0;
@@ -1045,7 +1052,7 @@ __device__ __noinline__ void l_turn_region(const WalkFrame& F, unsigned idx, int
         if (lane == 0) s_F.nj = nj + 1;
     }
     __syncwarp();
-    if (lane == 0) { atomicAdd(ws.wstat + 0, 1ull); atomicAdd(ws.wstat + 1, (unsigned long long)(clock64() - t0)); atomicAdd(ws.wstat + 2, (unsigned long long)nfin); }
+    if (lane == 0 && (g.dbg & 32)) { atomicAdd(ws.wstat + 0, 1ull); atomicAdd(ws.wstat + 1, (unsigned long long)(clock64() - t0)); atomicAdd(ws.wstat + 2, (unsigned long long)nfin); }
 }
 
 // commit slot `k` (rank `seq`); commit_lock held
@@ -1055,7 +1062,7 @@ __device__ __noinline__ void l_commit_slot(const WalkFrame& F, int k, int seq) {
     const int st = s_F.state[k];
     if (s_F.seedpix[k] < 0) return;                               // the sentinel claim that closes the frame
     const unsigned idx = (unsigned)s_F.seedpix[k];
-    if (l_bit(F.bits, (int)idx)) { if (lane == 0) atomicAdd(ws.wstat + 4, 1ull); return; }     // swallowed by a region of lower rank: nothing to do
+    if (l_bit(F.bits, (int)idx)) { if (lane == 0 && (g.dbg & 32)) atomicAdd(ws.wstat + 4, 1ull); return; }     // swallowed by a region of lower rank: nothing to do
     bool ok = st == SLOT_DONE && !s_F.poison[k];
     const int acc = s_F.acc[k], nasm = s_F.nasm[k], finoff = s_F.finoff[k], nfin = s_F.nfin[k];
     const bool small = finoff == 0 && acc + nasm <= WALK_SMALL && !(g.dbg & 2);    // everything needed is in shared memory
@@ -1072,16 +1079,16 @@ __device__ __noinline__ void l_commit_slot(const WalkFrame& F, int k, int seq) {
         ok = !__any_sync(0xffffffffu, bad);
     }
     if (!ok) {
-        if (lane == 0) atomicAdd(ws.wstat + 5 + (st == SLOT_PRESUMED ? 3 : (st != SLOT_DONE ? 0 : (s_F.poison[k] ? 1 : 2))), 1ull);
+        if (lane == 0 && (g.dbg & 32)) atomicAdd(ws.wstat + 5 + (st == SLOT_PRESUMED ? 3 : (st != SLOT_DONE ? 0 : (s_F.poison[k] ? 1 : 2))), 1ull);
         l_turn_region(F, idx, seq);
         return;
     }
-    if (lane == 0) { atomicAdd(ws.wstat + 9, 1ull); atomicAdd(ws.wstat + 10, (unsigned long long)nfin); }
+    if (lane == 0 && (g.dbg & 32)) { atomicAdd(ws.wstat + 9, 1ull); atomicAdd(ws.wstat + 10, (unsigned long long)nfin); }
     if (small) { if (lane < nfin) l_set_bit(F.bits, s_F.small[k][lane], g.sw); }
     else for (int i = lane; i < nfin; i += 32) l_set_bit(F.bits, __ldcg(list + finoff + i), g.sw);
     if (s_F.job[k]) {
         const int nj = s_F.nj;
-        if (nj < g.seg_cap && lane < 13) ws.jobs[((long long)F.f * g.seg_cap + nj) * 13 + lane] = __ldcg(ws.sjob + ((long long)F.f * WALK_RING + k) * 13 + lane);
+        if (nj < g.seg_cap && lane < 13) ws.jobs[((long long)F.f * g.seg_cap + nj) * 13 + lane] = s_F.jobv[k][lane];
         __syncwarp();
         if (lane == 0) s_F.nj = nj + 1;
     }
@@ -1127,6 +1134,7 @@ __device__ __noinline__ int l_claim(const WalkFrame& F) {
     return found >= ns ? -2 : k;
 }
 
+// 128 registers: a build held to 80 (three 8-warp CTAs per SM) spilled and was 15-20 % slower in every configuration measured
 __global__ void __launch_bounds__(WALK_MAXW * 32) k_lsd_regions(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
     extern __shared__ unsigned s_bits[];                       // committed `used` bitmap of the frame
     const int lane = threadIdx.x & 31;
@@ -1181,7 +1189,7 @@ __global__ void __launch_bounds__(WALK_MAXW * 32) k_lsd_regions(const __grid_con
                     __syncwarp();
                     did = 1;
                 }
-                if (lane == 0) { atomicAdd(ws.wstat + 11, (unsigned long long)(clock64() - tc0)); l_unlock(&s_F.commit_lock); }
+                if (lane == 0) { if (g.dbg & 32) atomicAdd(ws.wstat + 11, (unsigned long long)(clock64() - tc0)); l_unlock(&s_F.commit_lock); }
                 __syncwarp();
             }
         }
@@ -1195,7 +1203,7 @@ __global__ void __launch_bounds__(WALK_MAXW * 32) k_lsd_regions(const __grid_con
             if (go) {
                 const long long tk0 = clock64();
                 const int k = l_claim(F);
-                if (lane == 0) { atomicAdd(ws.wstat + 12, (unsigned long long)(clock64() - tk0)); l_unlock(&s_F.claim_lock); }
+                if (lane == 0) { if (g.dbg & 32) atomicAdd(ws.wstat + 12, (unsigned long long)(clock64() - tk0)); l_unlock(&s_F.claim_lock); }
                 __syncwarp();
                 if (k >= 0) { myslot = k; tries = 0; waitfor = -1; }
             }
@@ -1216,11 +1224,11 @@ __global__ void __launch_bounds__(WALK_MAXW * 32) k_lsd_regions(const __grid_con
             __syncwarp();
             if (r < 0 && W.abort == 2 && tries < 100 && !(g.dbg & 1)) {           // a live attempt of lower rank holds a pixel this one needs: repeat after it retires
                 waitfor = W.conflict; tries++;
-                if (lane == 0) atomicAdd(ws.wstat + 13, 1ull);
+                if (lane == 0 && (g.dbg & 32)) atomicAdd(ws.wstat + 13, 1ull);
                 __syncwarp();
                 continue;
             }
-            if (r == 1) l_emit_job(g, ws.sjob + ((long long)f * WALK_RING + k) * 13, rec, idx, n0, lane);
+            if (r == 1) l_emit_job(g, s_F.jobv[k], rec, idx, n0, lane);
             int st = SLOT_DONE;
             if (r < 0) st = W.abort == 3 ? SLOT_PRESUMED : SLOT_ABORTED;
             else {
@@ -1242,8 +1250,58 @@ __global__ void __launch_bounds__(WALK_MAXW * 32) k_lsd_regions(const __grid_con
         __nanosleep(100);
     }
     __syncthreads();
-    if (threadIdx.x == 0) { atomicAdd(ws.wstat + 14, (unsigned long long)(clock64() - tf0)); atomicAdd(ws.wstat + 15, (unsigned long long)s_F.nclaims);
+    if (threadIdx.x == 0) { if (g.dbg & 32) { atomicAdd(ws.wstat + 14, (unsigned long long)(clock64() - tf0)); atomicAdd(ws.wstat + 15, (unsigned long long)s_F.nclaims); }
         ws.njobs[f] = min(s_F.nj, g.seg_cap); if (s_F.nj > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
+  }
+}
+
+// THROUGHPUT form of the same stage for big batches: ONE WARP PER FRAME, no speculation (every instruction is useful work, 72
+// registers, ~28 frames resident per SM; 46 ms latency per frame, ~17 us per frame amortised with >= 3000 frames in flight).
+// sslpl picks it when a call brings at least two frames per SM; smaller calls use the multi-warp walker above (17 ms per frame).
+__global__ void __launch_bounds__(32, 28) k_lsd_regions_solo(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
+    const int lane = threadIdx.x;
+  for (;;) {
+    int f = 0;
+    if (lane == 0) f = atomicAdd(ws.rejctl + 2, 1);
+    f = __shfl_sync(0xffffffffu, f, 0);
+    if (f >= nframes) break;
+    __syncwarp();
+    WalkCtx& W = s_W1;
+    if (lane == 0) {
+        W.w = g.sw; W.h = g.sh; W.mode = 2; W.abort = 0; W.nasm = 0; W.acc = 0; W.cap = (int)g.pix_stride; W.ticket = 1u; W.seq = 0;
+        W.ang = ws.angdeg + f * g.pix_stride; W.mod = ws.modgrad + f * g.pix_stride;
+        W.pix = ws.pix + f * g.pix_stride; W.reg = ws.reg + f * g.pix_stride; W.base0 = W.reg; W.cs0 = ws.cs0 + f * g.pix_stride; W.bits = nullptr;
+    }
+    __syncwarp();
+    const LPix* pix = ws.pix + f * g.pix_stride;
+    const unsigned* seeds = ws.seeds + f * g.pix_stride;
+    const int ns = ws.nseeds[f];
+    double* jobs = ws.jobs + (long long)f * g.seg_cap * 13;
+    int nj = 0;
+    for (int sb = 0; sb < ns; sb += 32) {
+        const bool have = sb + lane < ns;
+        const unsigned mine = have ? seeds[sb + lane] : 0u;                   // 32 seeds per coalesced load
+        unsigned umask = __ballot_sync(0xffffffffu, !have || pix[mine].used != 0u); // their `used` state, one round trip
+        while (~umask) {                                    // angle != NOTDEF holds for every seed
+            const int j = __ffs(~umask) - 1;
+            umask |= (2u << j) - 1u;                        // seeds up to j are done
+            const unsigned idx = __shfl_sync(0xffffffffu, mine, j);
+            double reg_angle;
+            int n = l_region_grow<1>((int)(idx % (unsigned)g.sw), (int)(idx / (unsigned)g.sw), g.prec, &reg_angle);
+            umask |= __ballot_sync(0xffffffffu, !have || pix[mine].used != 0u);    // the region may have swallowed later seeds
+            if (n < g.min_reg_size) continue;
+            LRect rec;
+            l_region2rect<1>(n, reg_angle, g.prec, g.p, &rec);
+            const int n0 = n;
+            const bool okr = l_refine<1>(&n, &reg_angle, g.prec, g.p, &rec, 0.7);
+            umask = ((2u << j) - 1u) | __ballot_sync(0xffffffffu, !have || pix[mine].used != 0u);   // refine can release and re-take pixels
+            if (!okr) continue;
+            if (nj < g.seg_cap) l_emit_job(g, jobs + (long long)nj * 13, rec, idx, n0, lane);
+            nj++;
+        }
+    }
+    if (lane == 0) { ws.njobs[f] = min(nj, g.seg_cap); if (nj > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
+    __syncwarp();
   }
 }
 
@@ -1715,10 +1773,11 @@ int run_pipeline(sslpl_line* h, int B) {
     SSLPL_CUDA(cudaMemsetAsync(h->ws.rejctl, 0, 4 * sizeof(int), st));
     SSLPL_CUDA(cudaMemsetAsync(h->ws.wstat, 0, 16 * sizeof(unsigned long long), st));
     {   // one CTA per frame; few frames -> more warps per frame (latency), many frames -> more CTAs per SM (throughput)
-        const int ww = h->walker_warps > 0 ? std::min(h->walker_warps, WALK_MAXW) : (B >= 2 * h->sm_count ? 8 : WALK_MAXW);
+        const int ww = h->walker_warps < 0 ? 0 : h->walker_warps > 0 ? std::min(h->walker_warps, WALK_MAXW) : (B >= 2 * h->sm_count ? 0 : WALK_MAXW);
         const size_t smem = (size_t)((g.pix_stride + 31) / 32) * sizeof(unsigned);
         if ((int)smem > h->used_smem) { SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); h->used_smem = (int)smem; }
-        k_lsd_regions<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), ww * 32, smem, st>>>(g, h->ws, B);
+        if (ww == 0) k_lsd_regions_solo<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), 32, 0, st>>>(g, h->ws, B);   // throughput: one warp per frame
+        else k_lsd_regions<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), ww * 32, smem, st>>>(g, h->ws, B);
     }
     lmark(h, "lsd_regions");
     k_lsd_nfa_count<<<dim3(NFA_COUNT_CTAS, B), 128, 0, st>>>(g, h->ws);
@@ -1760,7 +1819,7 @@ int sslpl_line_create(const sslpl_line_params* p, sslpl_line** out) {
     h->p = *p;
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && v > 0) h->sm_count = v; }
     h->trace = getenv("SSLPL_LINE_TRACE") != nullptr;
-    if (const char* e = getenv("SSLPL_WALKER_WARPS")) h->walker_warps = std::max(1, std::min(WALK_MAXW, atoi(e)));   // tuning knob (tests sweep it)
+    if (const char* e = getenv("SSLPL_WALKER_WARPS")) h->walker_warps = std::max(-1, std::min(WALK_MAXW, atoi(e)));   // tuning knob (tests sweep it); -1 = the one-warp throughput kernel
     {   // BinaryDescriptor constructor: local (F_l) and global (F_g) Gaussian weights, widthOfBand 7, 9 bands
         double u = (7 * 3 - 1) / 2, sigma = (7 * 2 + 1) / 2, inv = -1 / (2 * sigma * sigma);
         for (int i = 0; i < 21; i++) { const double d = i - u; h->coef.L[i] = (float)exp(d * d * inv); }
