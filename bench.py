@@ -42,10 +42,47 @@ WORKLOADS = {
 NWORDS, NNRATIO = 100, 0.7
 
 
-def gen_frames(cfg, rank, nsets):
+def host_cores():
+    """Host threads this process can really use: the scheduler affinity mask capped by the cgroup CPU quota (os.cpu_count()
+    reports the machine: the 1-GPU lease of round 1 showed 128 CPUs with a 16-CPU cpu.max quota)."""
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except AttributeError:
+        aff = os.cpu_count() or 1
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    eff = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    return eff, {"os_cpu_count": os.cpu_count(), "sched_affinity": aff, "cgroup_quota_cpus": quota}
+
+
+def make_config(args, cfg, world, lines=True, ring=None, nsets=None, B=None):
+    """The `config` object of the JSON line — the same keys and values in both arms (driver: same_config)."""
+    W, H = cfg["width"], cfg["height"]
+    total = cfg["frames_per_gpu"]
+    per_gpu = total // world if args.scaling == "strong" else total
+    c = {"workload": args.workload, "width": W, "height": H, "nfeatures": cfg["nfeatures"], "nlevels": 8,
+         "frames_per_gpu": per_gpu, "halo_frames_per_gpu": 1, "pairs_per_gpu": per_gpu, "vocabulary_nodes": NWORDS,
+         "lines": cfg["nlines"] if lines else 0, "scaling": args.scaling,
+         "parallelism": f"frames sharded x{world}, one all_gather(point+line match tables) per step"}
+    return c
+
+
+def gen_frames(cfg, rank, nsets, B=None):
     """nsets distinct input batches (so that the inputs cycle through more than the 126 MB L2)."""
     import synth
-    B = cfg["frames_per_gpu"] + 1
+    B = B or cfg["frames_per_gpu"] + 1
     sets = []
     for s in range(nsets):
         start = (s * 977 + rank) * B * 3
@@ -87,6 +124,63 @@ def cpu_step(O, cfg, frames, voc, nthreads, lines=True):
     return feats, sum(nm), dt
 
 
+def _cv2_worker(job):
+    """One host process: cv2's own (SIMD, single-threaded) ORB + LSD on a few frames and brute-force matching of consecutive pairs."""
+    import cv2
+    cv2.setNumThreads(1)
+    frames, nfeat, nlines = job
+    orb = cv2.ORB_create(nfeatures=nfeat, scaleFactor=1.2, nlevels=8, edgeThreshold=19, fastThreshold=20)
+    lsd = cv2.createLineSegmentDetector(cv2.LSD_REFINE_ADV)
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    feats, matches, prev = 0, 0, None
+    for k, img in enumerate(frames):
+        kps, desc = orb.detectAndCompute(img, None)
+        seg = lsd.detect(img)[0]
+        nl = 0 if seg is None else min(nlines, len(seg))
+        if k + 1 < len(frames):
+            feats += len(kps) + nl
+        if prev is not None and desc is not None and prev is not None and len(prev) >= 2 and len(desc) >= 2:
+            for m in bf.knnMatch(prev, desc, k=2):
+                if len(m) == 2 and m[0].distance <= 50 and m[0].distance < 0.7 * m[1].distance:
+                    matches += 1
+        prev = desc
+    return feats, matches
+
+
+def cv2_baseline(cfg, frames, cores):
+    """The second CPU line of SURVEY.md 8(d): what OpenCV's own SIMD code achieves on the same frames — cv2.ORB (not the
+    reference's octree selection), cv2's LSD, brute-force 2-NN Hamming with the reference's thresholds; no LBD (opencv_contrib
+    is not installed) and no line matching.  One fresh process per host core (no fork of a CUDA / OpenCV parent),
+    cv2.setNumThreads(1) in each; throughput = all units / the slowest worker's compute time."""
+    import tempfile
+    n = len(frames)
+    per = max(2, (n + cores - 1) // cores)
+    spans = [(i, min(n, i + per + 1)) for i in range(0, n - 1, per)]
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "frames.npy")
+        np.save(path, np.ascontiguousarray(frames))
+        procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cv2-worker", path, str(a), str(b), str(cfg["nfeatures"]), str(cfg["nlines"])],
+                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for a, b in spans]
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+    f = m = 0; tmax = 0.0
+    for o in outs:
+        ff, mm, tt = o.strip().split()[-3:]
+        f += int(ff); m += int(mm); tmax = max(tmax, float(tt))
+    return {"value": (f + m) / tmax, "unit": UNIT, "cores": len(spans), "kind": "cv2-composed",
+            "sample": f"{n - 1} frames+pairs, cv2.ORB_create({cfg['nfeatures']}) + cv2 LSD (REFINE_ADV) + BFMatcher 2-NN, {len(spans)} processes x 1 thread",
+            "note": "cv2.ORB's keypoint selection and cv2's brute-force matcher differ from the reference's octree / BoW-gated search; no LBD"}
+
+
+def cv2_worker_main(argv):
+    path, a, b, nfeat, nlines = argv[0], int(argv[1]), int(argv[2]), int(argv[3]), int(argv[4])
+    frames = np.load(path)[a:b]
+    _cv2_worker((frames[:2], nfeat, nlines))            # warm-up
+    t0 = time.perf_counter()
+    f, m = _cv2_worker((frames, nfeat, nlines))
+    print(f, m, time.perf_counter() - t0)
+    return 0
+
+
 def run_reference(args, cfg):
     """--impl reference: the CPU implementation of the path on the box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -95,7 +189,7 @@ def run_reference(args, cfg):
     import __graft_entry__ as g
     O = g.load_oracle()
     import synth
-    cores = os.cpu_count() or 1
+    cores, core_info = host_cores()
     voc = synth.vocabulary(NWORDS)
     nsample = min(cfg["frames_per_gpu"] + 1, max(9, 4 * cores + 1))      # >= 4 frames per host thread: less tail imbalance
     frames = gen_frames(cfg, 0, 1)[0][:nsample]
@@ -106,13 +200,13 @@ def run_reference(args, cfg):
         f, m, dt = cpu_step(O, cfg, frames, voc, cores)
         tot_units += f + m; tot_s += dt
     val = tot_units / tot_s
-    sample = f"{nsample - 1} frames+pairs of the {args.workload} workload per step, oracle C++ port (-O3), {cores} threads"
+    sample = (f"{nsample - 1} frames+pairs of the {args.workload} workload per step, oracle C++ port (-O3), {cores} threads "
+              f"(affinity {core_info['sched_affinity']}, cgroup quota {core_info['cgroup_quota_cpus']})")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.workload, **{k: cfg[k] for k in ("width", "height", "nfeatures")},
-                       "frames_per_step": nsample - 1, "lines": cfg["nlines"]},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": make_config(args, cfg, args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "host": core_info},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -156,12 +250,16 @@ class ClockSampler:
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--cv2-worker":
+        return cv2_worker_main(sys.argv[2:])
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="batch640", choices=list(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: frames_per_gpu frames on every GPU; strong: BASELINE.json config 5 as written, the workload's frames in total, sharded")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lines", action="store_true", help="ORB + point matching only")
     ap.add_argument("--line-ring", type=int, default=6, help="line handles (streams + workspaces) kept in flight")
@@ -191,6 +289,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))   # fail fast, never hang the box
 
     W, H, NF, Bf, NL = cfg["width"], cfg["height"], cfg["nfeatures"], cfg["frames_per_gpu"], cfg["nlines"]
+    if args.scaling == "strong":
+        assert Bf % world == 0, "strong scaling: the frames must divide over the GPUs"
+        Bf //= world                                    # config 5: 512 frames in total, 512 / N (+ 1 halo frame) per GPU
     LINES = not args.no_lines
     B = Bf + 1                                          # + halo frame (first frame of the next rank's block)
     ext = pkg.ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B, device=local)
@@ -219,7 +320,7 @@ def main():
     voc = synth.vocabulary(NWORDS)
     d_voc = torch.from_numpy(voc).to(dev)
     nsets = max(2, int(np.ceil(160e6 / (B * W * H))))   # cycle > 126 MB of distinct inputs => inputs never L2-resident
-    sets = gen_frames(cfg, rank, nsets)
+    sets = gen_frames(cfg, rank, nsets, B)
     d_sets = [torch.from_numpy(s).to(dev) for s in sets]
     d_match = torch.empty((Bf, cap), dtype=torch.int32, device=dev)
     d_nmatch = torch.empty((Bf,), dtype=torch.int32, device=dev)
@@ -227,6 +328,14 @@ def main():
     d_nlmatch = [torch.zeros((Bf,), dtype=torch.int32, device=dev) for _ in range(R)]
     d_gather = torch.empty((world * Bf, cap), dtype=torch.int32, device=dev) if world > 1 else None
     d_lgather = torch.empty((world * Bf, NL), dtype=torch.int32, device=dev) if world > 1 else None
+    class _DevArr:                                      # a torch view of a device array owned by the library (counts only)
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+    _, _, _nptr, _ = ext.device_results()
+    t_nkp = torch.as_tensor(_DevArr(_nptr, B), device=dev)
+    t_nl = [torch.as_tensor(_DevArr(l.device_results()[3], B), device=dev) for l in lsr]
+    u_pts = torch.zeros((), dtype=torch.int64, device=dev)     # features + matches of the timed loop, summed ON the device,
+    u_lin = [torch.zeros((), dtype=torch.int64, device=dev) for _ in range(R)]   # inside the timed region (no separate counting pass)
     pending = [False] * R
     gather = [world > 1]                                # collectives on/off (off in the rank-0-only profiling pass)
     ev_free = [torch.cuda.Event() for _ in range(R)]    # slot r's tables have been consumed (gathered) on s_pts
@@ -256,11 +365,14 @@ def main():
         lsr[r].extract_batch_device(ptr, B, W, H, W, W * H)
         _, ldesc, _, nl, capl = lsr[r].device_results()
         lmr[r].match_lines_batch_device(ldesc, nl, B, capl, d_lmatch[r].data_ptr(), d_nlmatch[r].data_ptr())
+        with torch.cuda.stream(s_lin[r]):
+            u_lin[r] += t_nl[r][:Bf].sum() + d_nlmatch[r].sum()
         pending[r] = True
 
     def enqueue_points():
         kps, desc, n, c = ext.device_results()
         mt.match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match.data_ptr(), d_nmatch.data_ptr())
+        u_pts.add_(t_nkp[:Bf].sum() + d_nmatch.sum())
         if gather[0]:
             pgather.gather(d_match)
 
@@ -276,6 +388,8 @@ def main():
     def drain():
         for r in range(R):
             finalize_slot(r)
+        if gather[0]:
+            pgather.wait()
 
     def barrier():
         if world > 1:
@@ -290,6 +404,11 @@ def main():
         step_device(i)
     drain()
     ext.sync()
+    for l in lsr:
+        l.sync()
+    u_pts.zero_()
+    for u in u_lin:
+        u.zero_()
     launches0 = launches_now()
     sampler = ClockSampler(local)
     barrier()
@@ -308,6 +427,20 @@ def main():
         l.sync()
     launches = launches_now() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    units_timed = int(u_pts.item()) + sum(int(u.item()) for u in u_lin)      # counted inside the timed region, on the device
+
+    # ---- N > 1: the gathered tables must be the single-GPU tables (every rank checks its rows and all ranks agree) ----
+    gather_check = None
+    if world > 1:
+        torch.cuda.synchronize()
+        pts_full, lin_full = pgather.fulls[pgather.last][:, :cap], pgather.fulls[pgather.last][:, cap:]
+        mine_ok = bool(torch.equal(pts_full[rank * Bf:(rank + 1) * Bf], d_match))
+        hsh = (pgather.fulls[pgather.last].to(torch.int64) * torch.arange(1, pgather.fulls[pgather.last].numel() + 1, device=dev).view_as(pgather.fulls[pgather.last])).sum()
+        hmin = hsh.clone(); dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
+        hmax = hsh.clone(); dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+        okt = torch.tensor([1 if (mine_ok and hmin.item() == hmax.item()) else 0], device=dev); dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        gather_check = {"rows_of_this_rank_equal_local_table": mine_ok, "all_ranks_hold_the_same_tables": bool(hmin.item() == hmax.item()),
+                        "ok_on_every_rank": bool(okt.item()), "checksum": int(hsh.item())}
 
     # ---- e2e: pinned host frames -> H2D -> kernels -> D2H of keypoints, descriptors, lines, counts, match tables ----
     # Both paths are software-pipelined through their public asynchronous entry points (extract_batch_begin): a ring of
@@ -396,7 +529,11 @@ def main():
         return u
 
     def e2e_drain():
-        return sum(e2e_finalize(r) for r in range(R)) + sum(pts_finalize(p) for p in range(PR))
+        u = sum(e2e_finalize(r) for r in range(R)) + sum(pts_finalize(p) for p in range(PR))
+        if world > 1:
+            for pg in pg_e:
+                pg.wait()
+        return u
 
     # units of every distinct input set (untimed): one synchronous pass per set
     per_set = []
@@ -404,7 +541,8 @@ def main():
         u = step_e2e(sidx) + e2e_drain()
         per_set.append(u)
     nkp_avg = float(np.mean(h_out[(nsets - 1) % PR][2][:Bf]))
-    units = sum(per_set[(args.warmup + i) % nsets] for i in range(args.steps))
+    units = units_timed
+    assert units == sum(per_set[(args.warmup + i) % nsets] for i in range(args.steps)), "device count != host count of the same steps"
     t = torch.tensor([ms_total, float(units)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -426,32 +564,41 @@ def main():
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 0.0)
-    if os.environ.get("SSLPL_BENCH_TRACE") and rank == 0:      # diagnostics: GPU busy time / gaps of both loops (torch profiler)
-        from torch.profiler import profile, ProfilerActivity
-        for name, body in (("device", lambda: ([step_device(args.warmup + i) for i in range(8)], drain())),
-                           ("e2e", lambda: ([step_e2e(args.warmup + i) for i in range(8)], e2e_drain()))):
+    # ---- in-pipeline attribution (rank 0, outside the timed regions): CUPTI kernel intervals of a few steps of the SAME pipelined
+    # device loop -> time per kernel per step and the union of GPU-busy time (the serial stage times of `roofline` cannot say
+    # how much of a pipelined step is the region walker)
+    in_pipeline = None
+    if rank == 0 and not os.environ.get("SSLPL_BENCH_NO_TRACE"):
+        try:
+            from torch.profiler import profile, ProfilerActivity
+            NT = 6
+            gather_was = gather[0]; gather[0] = False       # rank 0 alone: no collectives in this pass
             torch.cuda.synchronize()
-            with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-                body(); torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for i in range(NT):
+                    step_device(args.warmup + i)
+                drain(); torch.cuda.synchronize()
+            gather[0] = gather_was
             evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
             iv = sorted((e.time_range.start, e.time_range.end, e.name) for e in evs)
-            if not iv:
-                continue
-            t0, t1 = iv[0][0], max(b for _, b, _ in iv)
-            busy = 0.0; cur_a, cur_b = iv[0][0], iv[0][1]; gaps = []
-            for a, b, _ in iv[1:]:
-                if a > cur_b:
-                    busy += cur_b - cur_a; gaps.append((a - cur_b, cur_b - t0)); cur_a, cur_b = a, b
-                else:
-                    cur_b = max(cur_b, b)
-            busy += cur_b - cur_a
-            per = {}
-            for a, b, n in iv:
-                k = n.split("(")[0][-28:]; per[k] = per.get(k, 0.0) + (b - a)
-            top = sorted(per.items(), key=lambda kv: -kv[1])[:14]
-            print(f"[trace {name}] wall {(t1 - t0) / 1e3:.1f} ms, union busy {busy / 1e3:.1f} ms, largest gaps (us @ offset ms): "
-                  f"{[(round(g), round(o / 1e3, 1)) for g, o in sorted(gaps, reverse=True)[:6]]}", file=sys.stderr)
-            print(f"[trace {name}] kernel/copy time sums (ms): {[(k, round(v / 1e3, 1)) for k, v in top]}", file=sys.stderr)
+            if iv:
+                t0, t1 = iv[0][0], max(bb for _, bb, _ in iv)
+                busy = 0.0; cur_a, cur_b = iv[0][0], iv[0][1]
+                for a_, b_, _ in iv[1:]:
+                    if a_ > cur_b:
+                        busy += cur_b - cur_a; cur_a, cur_b = a_, b_
+                    else:
+                        cur_b = max(cur_b, b_)
+                busy += cur_b - cur_a
+                per = {}
+                for a_, b_, n_ in iv:
+                    k = n_.split("(")[0].split("::")[-1][:40]; per[k] = per.get(k, 0.0) + (b_ - a_)
+                top = sorted(per.items(), key=lambda kv: -kv[1])[:12]
+                in_pipeline = {"steps": NT, "wall_ms_per_step": (t1 - t0) / 1e3 / NT, "gpu_busy_union_ms_per_step": busy / 1e3 / NT,
+                               "kernel_ms_per_step": {k: round(v / 1e3 / NT, 3) for k, v in top},
+                               "how": "torch.profiler (CUPTI) over the pipelined device loop; kernels of different streams overlap, so the sums exceed the wall time"}
+        except Exception as e:
+            in_pipeline = {"unavailable": repr(e)[:200]}
     t = torch.tensor([e2e_ms, float(eu)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -504,7 +651,7 @@ def main():
             "lsd_prep": W * H + 2 * int(0.64 * W * H) + 2 * W * H,
             "lsd_ll_angle": int(0.64 * W * H) * (1 + 4 + 16 + 8 + 8),   # read u8, write angle, packed record, seed cos/sin, norm
             "lsd_seeds": int(0.64 * W * H) * (8 + 8) + 4 * int(0.3 * 0.64 * W * H),   # norm read twice, seed list written
-            "lsd_regions": 33 * int(0.64 * W * H),          # 16 B record + 4 B flag write + 8 B queue + 8 B norm per visited pixel (upper bound: every pixel visited once); latency-bound by definition
+            "lsd_regions": 17 * int(0.64 * W * H),          # angle + modgrad + used of the visited pixels, <= 17 S (latency-bound stage)
             "lsd_nfa": 4 * int(0.64 * W * H),
             "keylines_lbd": W * H + 8 * W * H + 63 * 4 * 60 * NL,
         }
@@ -512,18 +659,24 @@ def main():
         achieved = alg.get(dom, 0) * B / (acc[dom] * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the same
         # 513-frame batch (profiles/r01_ncu_k_lsd_regions_513_final.md, profiles/r01_ncu_orb_kernels_final.md); bytes
-        ncu_traffic = {"lsd_regions": 6.93e9, "fast_score": 0.958e9, "fast_cells": 0.488e9, "blur": 1.005e9} if (args.workload == "batch640" and B == 513) else {}
+        ncu_traffic = {}
+        try:                                            # written by tools/ncu_summary.py from the round's ncu capture of this workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ncu_traffic = tj.get(f"{args.workload}:{B}", {})
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ncu_traffic.get(dom), "traffic_unit": "bytes per launch (ncu dram read+write)", "peak_source": which, "stage_ms": acc,
-                    "note": ("lsd_regions is the order-dependent LSD region walker (one warp per frame): latency-bound by "
-                             "definition, reported against HBM only for completeness" if dom == "lsd_regions" else ""),
+                    "traffic": ncu_traffic.get(dom), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/ncu_traffic.json)", "peak_source": which, "stage_ms": acc,
+                    "algorithmic_bytes_per_launch": alg.get(dom, 0) * B,
+                    "note": ("lsd_regions is the order-dependent LSD region stage: latency / issue bound, reported against HBM "
+                             "with SURVEY 8(d)'s 17 S bytes per frame" if dom == "lsd_regions" else ""),
                     "stage_gbs": {k: alg.get(k, 0) * B / (acc[k] * 1e-3) / 1e9 for k in acc}}
 
     # ---- CPU baseline on the host cores (rank 0, N=1 only) ----
-    cpu = None
+    cpu = None; cpu_cv2 = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         O = g.load_oracle()
-        cores = os.cpu_count() or 1
+        cores, core_info = host_cores()
         ns = min(B, max(9, 4 * cores + 1))              # >= 4 frames per host thread: less tail imbalance
         cpu_step(O, cfg, sets[0][:min(ns, cores + 1)], voc, cores, LINES)
         best = None
@@ -531,20 +684,24 @@ def main():
             f, m, dt = cpu_step(O, cfg, sets[0][:ns], voc, cores, LINES)
             v = (f + m) / dt
             best = v if best is None or v > best else best
-        cpu = {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
+        cpu = {"value": best, "unit": UNIT, "cores": cores, "kind": "port", "host": core_info,
                "sample": f"{ns - 1} frames+pairs of the {args.workload} workload, oracle C++ port, {cores} threads, best of 2"}
+        try:
+            cpu_cv2 = cv2_baseline(cfg, sets[0][:ns], cores)
+        except Exception as e:                          # the second CPU line must never cost the bench line
+            cpu_cv2 = {"unavailable": repr(e)[:200]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
-                "config": {"workload": args.workload, "width": W, "height": H, "nfeatures": NF, "nlevels": 8,
-                           "frames_per_gpu": Bf, "halo_frames_per_gpu": 1, "pairs_per_gpu": Bf, "vocabulary_nodes": NWORDS,
-                           "lines": NL if LINES else 0, "line_ring": R, "parallelism": f"frames sharded x{world}, one all_gather(point+line match tables) per step",
-                           "l2": f"inputs cycle through {nsets} distinct batches ({nsets * B * W * H / 1e6:.0f} MB > 126 MB L2)"},
+                "config": make_config(args, cfg, world, LINES),
+                "run": {"line_ring": R, "l2": f"inputs cycle through {nsets} distinct batches ({nsets * B * W * H / 1e6:.0f} MB > 126 MB L2)",
+                        "units_counted": "on the device inside the timed region"},
                 "e2e": {"value": eu_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_cv2": cpu_cv2,
+                "gather_check": gather_check, "in_pipeline": in_pipeline}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

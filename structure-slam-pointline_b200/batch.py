@@ -51,21 +51,71 @@ def all_gather_tables(local, group=None):
 class PackedGather:
     """ONE all-gather per step for both match tables (north_star: "a single NCCL all-gather of match tables"): the point
     table [per_rank, cap] of this step and a line table [per_rank, nl] travel in one [per_rank, cap + nl] buffer.
-    Buffers are allocated once; all copies are issued on the caller's current stream."""
 
-    def __init__(self, per_rank, cap, nl, world, device, dtype=None):
+    The collective runs on its OWN stream with two buffer sets: the producing stream only records an event and moves on, so
+    ranks are no longer lock-stepped by the all-gather (the gathered tables of step i are complete one step later; `wait()`
+    joins them into the caller's stream).  Buffers are allocated once."""
+
+    def __init__(self, per_rank, cap, nl, world, device, dtype=None, own_stream=True):
         import torch
         dtype = dtype or torch.int32
         self.cap, self.nl, self.world, self.per_rank = cap, nl, world, per_rank
-        self.local = torch.full((per_rank, cap + nl), -1, dtype=dtype, device=device)
-        self.full = torch.empty((world * per_rank, cap + nl), dtype=dtype, device=device)
+        self.nbuf = 2 if own_stream else 1
+        self.locals = [torch.full((per_rank, cap + nl), -1, dtype=dtype, device=device) for _ in range(self.nbuf)]
+        self.fulls = [torch.empty((world * per_rank, cap + nl), dtype=dtype, device=device) for _ in range(self.nbuf)]
+        self.cuda = own_stream and device is not None and getattr(device, "type", str(device)) == "cuda"
+        self.comm = torch.cuda.Stream(device=device) if self.cuda else None
+        self.done = [torch.cuda.Event() for _ in range(self.nbuf)] if self.cuda else None      # all-gather of buffer b finished
+        self.b = 0
+        self.last = None
+
+    # kept for callers that look at the buffers directly
+    @property
+    def local(self):
+        return self.locals[self.b]
+
+    @property
+    def full(self):
+        return self.fulls[self.last if self.last is not None else 0]
+
+    def _reuse(self, b):
+        """The caller's stream may write locals[b] only after the collective that last read it has finished."""
+        if self.cuda and not getattr(self, "_fresh", None) == b:
+            import torch
+            torch.cuda.current_stream().wait_event(self.done[b])
+            self._fresh = b
 
     def stage_lines(self, line_table):
-        self.local[:, self.cap:].copy_(line_table, non_blocking=True)
+        """Line table of a finished ring slot: rides along with the next gather() (copied now, on the caller's stream)."""
+        self._reuse(self.b)
+        self.locals[self.b][:, self.cap:].copy_(line_table, non_blocking=True)
 
     def gather(self, point_table, group=None):
-        """-> (points [total, cap], lines [total, nl]) views of the gathered buffer, rows ordered by global pair id."""
+        """Start the all-gather of (point_table, staged line table).  Returns views of the gathered buffer; with the own stream
+        they are valid after wait()."""
+        import torch
         import torch.distributed as dist
-        self.local[:, :self.cap].copy_(point_table, non_blocking=True)
-        dist.all_gather_into_tensor(self.full, self.local, group=group)
-        return self.full[:, :self.cap], self.full[:, self.cap:]
+        b = self.b
+        self._reuse(b)
+        self.locals[b][:, :self.cap].copy_(point_table, non_blocking=True)
+        if self.cuda:
+            cur = torch.cuda.current_stream()
+            ready = torch.cuda.Event(); ready.record(cur)
+            self.comm.wait_event(ready)
+            with torch.cuda.stream(self.comm):
+                dist.all_gather_into_tensor(self.fulls[b], self.locals[b], group=group)
+                self.done[b].record(self.comm)
+        else:
+            dist.all_gather_into_tensor(self.fulls[b], self.locals[b], group=group)
+        self._fresh = None
+        self.last = b
+        self.b = (b + 1) % self.nbuf
+        return self.fulls[b][:, :self.cap], self.fulls[b][:, self.cap:]
+
+    def wait(self):
+        """Make the caller's current stream wait for every all-gather issued so far."""
+        if self.cuda:
+            import torch
+            cur = torch.cuda.current_stream()
+            for e in self.done:
+                cur.wait_event(e)
