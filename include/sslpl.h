@@ -42,6 +42,7 @@ typedef enum {
 const char* sslpl_last_error(void);          /* thread-local message of the last failing call */
 int  sslpl_version(void);
 int  sslpl_device_count(void);               /* 0 when no CUDA device / driver */
+int  sslpl_default_device(void);             /* CUDA ordinal the reference-side adapters use: $SSLPL_DEVICE, else 0 */
 
 /* pinned host memory for frames / results (so H2D/D2H run at link speed) */
 int  sslpl_host_alloc(void** p, size_t bytes);
@@ -78,6 +79,9 @@ void sslpl_orb_destroy(sslpl_orb* h);
    (ORBextractor.h:63-77) + mnFeaturesPerLevel + umax; each array has nlevels (umax: 16) entries; NULL = skip */
 int  sslpl_orb_tables(const sslpl_orb* h, float* scale, float* invscale, float* sigma2, float* invsigma2,
                       int* nfeat_per_level, int* umax16);
+/* the same tables without a device or a handle (host arithmetic only: the adapter's constructor runs before any frame is seen) */
+int  sslpl_orb_tables_host(int nfeatures, float scaleFactor, int nlevels, float* scale, float* invscale, float* sigma2, float* invsigma2,
+                           int* nfeat_per_level, int* umax16);
 int  sslpl_orb_max_keypoints(const sslpl_orb* h);  /* capacity per frame: sum_l (mnFeaturesPerLevel[l] + 3) */
 
 /* ORBextractor::operator() (ORBextractor.cc:1043) on one HOST frame (CV_8UC1, `pitch` bytes per row).
@@ -189,8 +193,9 @@ int  sslpl_match_bow_batch_device(sslpl_matcher* m, const uint8_t* d_desc, const
    Current frame (n2): descriptors d2, mvKeysUn x2 / y2 / oct2 / angle2, mvuRight (NULL for monocular), claimed2[j] = the
    feature already holds a MapPoint with observations (NULL = none).  Tcw / Tlw: 3x4 row-major poses (Tlw only read when
    !bMono); cam = {fx, fy, cx, cy, mbf, mb}; bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}; scaleFactors[nlevels].
-   Result: assign2[j] = index i of the last-frame MapPoint now held by current feature j, or -1; *nmatches as returned by the
-   reference.  The matcher handle needs max_nodes >= 3072 (grid cells) and at most 8192 features. */
+   Result: assign2[j] = index i of the last-frame MapPoint now held by current feature j; -1 = never assigned; -2 = assigned and
+   then removed by the rotation check (the reference writes NULL there, ORBmatcher.cc:1461: the caller must too); *nmatches as
+   returned by the reference.  The matcher handle needs max_nodes >= 3072 (grid cells) and at most 8192 features. */
 int  sslpl_search_by_projection_frame(sslpl_matcher* m,
         int n1, const uint8_t* valid1, const uint8_t* obs1, const float* Xw, const uint8_t* dmp, const int32_t* oct1, const float* angle1,
         int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* angle2, const float* uright2,
@@ -273,6 +278,32 @@ int  sslpl_line_download_segments(sslpl_line* h, int frame, float* seg4, int cap
 /* debug: with SSLPL_LINE_TRACE=1 in the environment at create time, one row of 10 doubles per LSD region that reached
    region2rect: seed pixel, size before/after refine, log_nfa, x1,y1,x2,y2,width,p (detection scale) */
 int  sslpl_line_debug_trace(sslpl_line* h, int frame, double* out, int cap_rows, int* n);
+
+/* =====================================================================================
+ * (4) Frame level — what Frame::Frame(imGray, ...) does with the two extractors (src/Frame.cc:69-131), the colour conversion in
+ *     front of it (Tracking::GrabImageMonocularWithPL, src/Tracking.cc:148-161) and Frame::UndistortKeyPoints /
+ *     ComputeImageBounds behind it (src/Frame.cc:483-543).  ONE upload of the frame; ORB and LSD+LBD on two streams.
+ * ===================================================================================== */
+typedef struct sslpl_frame sslpl_frame;
+typedef struct { sslpl_orb_params orb; sslpl_line_params line; } sslpl_frame_params;   /* device, max_batch and max size must agree */
+int  sslpl_frame_create(const sslpl_frame_params* p, sslpl_frame** out);
+void sslpl_frame_destroy(sslpl_frame* h);
+sslpl_orb*  sslpl_frame_orb(sslpl_frame* h);     /* the extractors it owns (device results, tables, stage times) */
+sslpl_line* sslpl_frame_line(sslpl_frame* h);
+long long sslpl_frame_launch_count(const sslpl_frame* h);
+/* Camera.fx/fy/cx/cy and k1 k2 p1 p2 [k3] (Tracking.cc:58-86); undistortion is skipped when k1 == 0 (Frame.cc:485) */
+int  sslpl_frame_set_camera(sslpl_frame* h, float fx, float fy, float cx, float cy, const float* dist, int ndist);
+int  sslpl_frame_image_bounds(sslpl_frame* h, int cols, int rows, float* bounds4 /* mnMinX mnMaxX mnMinY mnMaxY */);
+/* channels 1 (grey), 3 or 4 (interleaved 8-bit; rgb_order 1 = RGB[A], 0 = BGR[A] as Camera.RGB says).  Any output pointer but the
+   counts may be NULL.  kps / kps_un / desc hold `cap` entries per frame (>= sslpl_orb_max_keypoints), the line outputs `lcap`. */
+int  sslpl_frame_extract(sslpl_frame* h, const uint8_t* img, int width, int height, int pitch, int channels, int rgb_order,
+                         sslpl_keypoint* kps, sslpl_keypoint* kps_un, uint8_t* desc, int cap, int* nkp,
+                         sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int lcap, int* nl);
+int  sslpl_frame_extract_batch(sslpl_frame* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
+                               int channels, int rgb_order,
+                               sslpl_keypoint* kps, sslpl_keypoint* kps_un, uint8_t* desc, int cap, int* nkp,
+                               sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int lcap, int* nl);
+int  sslpl_frame_device_gray(sslpl_frame* h, const uint8_t** d_gray, int* pitch, size_t* frame_stride);
 
 #ifdef __cplusplus
 }

@@ -177,7 +177,7 @@ void GaussianBlur(InputArray src, OutputArray dst, Size ksize, double sigmaX, do
     orc_gauss7_sigma2_u8(s.data, s.cols, s.rows, (int)s.step, d.data, (int)d.step);
 }
 void cvtColor(InputArray src, OutputArray dst, int code, int) {
-    // 8-bit RGB/BGR(A) -> gray, OpenCV's fixed-point weights: (R*4899 + G*9617 + B*1868 + 8192) >> 14  (pinned to cv2 in tests)
+    // 8-bit RGB/BGR(A) -> gray, OpenCV 4.13's fixed-point weights: (R*9798 + G*19235 + B*3735 + 16384) >> 15  (pinned to cv2 in tests)
     const Mat s = src.getMat();
     const int cn = s.channels();
     assert(s.depth() == CV_8U && (cn == 3 || cn == 4));
@@ -186,7 +186,7 @@ void cvtColor(InputArray src, OutputArray dst, int code, int) {
     for (int y = 0; y < s.rows; y++) for (int x = 0; x < s.cols; x++) {
         const uchar* p = s.ptr(y) + (size_t)x * cn;
         const int r = rgb ? p[0] : p[2], g = p[1], b = rgb ? p[2] : p[0];
-        d.at<uchar>(y, x) = (uchar)((r * 4899 + g * 9617 + b * 1868 + 8192) >> 14);
+        d.at<uchar>(y, x) = (uchar)((r * 9798 + g * 19235 + b * 3735 + 16384) >> 15);
     }
     *dst.m = d;
 }

@@ -339,7 +339,7 @@ class Matcher:
         _check(lib().sslpl_bow_transform(self._h, vocab._h, _p(desc), n, int(levelsup), _p(word), _p(node), _p(w)))
         return word[:n], node[:n], w[:n]
 
-    def search_by_projection_frame(self, last, cur, Tcw, Tlw, cam, bounds, scale_factors, th, mono=True, check_ori=True):
+    def search_by_projection_frame(self, last, cur, Tcw, Tlw, cam, bounds, scale_factors, th, mono=True, check_ori=True, raw=False):
         """ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1331-1473).
         last = dict(valid, obs, Xw[n,3], dmp[n,32], oct, angle); cur = dict(desc[n,32], x, y, oct, angle, uright|None, claimed|None);
         Tcw / Tlw 3x4 (or 4x4) row-major; cam = (fx, fy, cx, cy, mbf, mb); bounds = (minX, maxX, minY, maxY).
@@ -360,7 +360,8 @@ class Matcher:
                                                       n2, _p(d2), _p(x2), _p(y2), _p(oc2), _p(a2), _p(ur), _p(cl), _p(Tc), _p(Tl),
                                                       _p(camv), _p(bnd), _p(sf), len(sf), C.c_float(th), int(mono), int(check_ori),
                                                       _p(out), C.byref(nm)))
-        return nm.value, out[:n2]
+        # -2 = assigned, then removed by the rotation check (the reference writes NULL there, ORBmatcher.cc:1461); -1 = never assigned
+        return nm.value, (out[:n2] if raw else np.where(out[:n2] == -2, -1, out[:n2]).astype(np.int32))
 
     def descriptor_medoid(self, desc, off):
         """ComputeDistinctiveDescriptors (MapPoint.cc:247-312 / MapLine.cpp:246-317) for CSR groups of descriptors."""
@@ -575,6 +576,79 @@ class LSDmatcher:
 
     def DescriptorDistance(self, a, b):                                 # LSDmatcher.cpp:364
         return int(self.ctx.descriptor_distance(a, b)[0])
+
+
+# =====================================================================================================
+# Frame level
+# =====================================================================================================
+class FrameParams(C.Structure):
+    _fields_ = [("orb", OrbParams), ("line", LineParams)]
+
+
+class Frame:
+    """What StructureSLAM::Frame::Frame(imGray, ...) does with the two extractors (src/Frame.cc:69-131): ONE upload of the frame,
+    ORB and LSD+LBD on two streams, optional colour conversion in front (Tracking.cc:148-161) and keypoint undistortion behind
+    (Frame.cc:483-513).  `extract(image)` -> dict(keys, keysUn, desc, keylines, ldesc, lineeq)."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, lsdNFeatures=40,
+                 max_width=1280, max_height=960, max_batch=1, device=0):
+        p = FrameParams(OrbParams(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_width, max_height, max_batch, device),
+                        LineParams(lsdNFeatures, max_width, max_height, max_batch, device))
+        self._h = C.c_void_p()
+        lib().sslpl_frame_create.argtypes = [C.c_void_p, C.c_void_p]
+        _check(lib().sslpl_frame_create(C.byref(p), C.byref(self._h)))
+        lib().sslpl_frame_orb.restype = C.c_void_p; lib().sslpl_frame_orb.argtypes = [C.c_void_p]
+        self.cap = int(lib().sslpl_orb_max_keypoints(C.c_void_p(lib().sslpl_frame_orb(self._h))))
+        self.lcap = lsdNFeatures
+        self.max_batch = max_batch
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().sslpl_frame_destroy.argtypes = [C.c_void_p]
+            lib().sslpl_frame_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def set_camera(self, fx, fy, cx, cy, dist=()):
+        d = np.ascontiguousarray(dist, np.float32)
+        _check(lib().sslpl_frame_set_camera(self._h, C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(d) if len(d) else None, len(d)))
+
+    def image_bounds(self, cols, rows):
+        b = np.zeros(4, np.float32)
+        _check(lib().sslpl_frame_image_bounds(self._h, int(cols), int(rows), _p(b)))
+        return b
+
+    @property
+    def launch_count(self):
+        lib().sslpl_frame_launch_count.restype = C.c_longlong
+        return int(lib().sslpl_frame_launch_count(self._h))
+
+    def extract(self, image, rgb_order=False):
+        """image: HxW (grey) or HxWx3 / HxWx4 uint8 (BGR[A] unless rgb_order)."""
+        assert image.dtype == np.uint8 and image.ndim in (2, 3)
+        image = np.ascontiguousarray(image)
+        cn = 1 if image.ndim == 2 else image.shape[2]
+        h, w = image.shape[:2]
+        kps = np.zeros(self.cap, KEYPOINT_DTYPE); un = np.zeros(self.cap, KEYPOINT_DTYPE); desc = np.zeros((self.cap, 32), np.uint8)
+        kl = np.zeros(self.lcap, KEYLINE_DTYPE); ld = np.zeros((self.lcap, 32), np.uint8); eq = np.zeros((self.lcap, 3), np.float64)
+        n = C.c_int(); nl = C.c_int()
+        _check(lib().sslpl_frame_extract(self._h, _p(image), w, h, image.strides[0], cn, int(rgb_order), _p(kps), _p(un), _p(desc), self.cap,
+                                         C.byref(n), _p(kl), _p(ld), _p(eq), self.lcap, C.byref(nl)))
+        n, nl = n.value, nl.value
+        return dict(keys=kps[:n].copy(), keysUn=un[:n].copy(), desc=desc[:n].copy(), keylines=kl[:nl].copy(), ldesc=ld[:nl].copy(), lineeq=eq[:nl].copy())
+
+    def extract_batch(self, frames, rgb_order=False):
+        """frames: [B, H, W] or [B, H, W, C] uint8 -> dict of per-frame arrays (padded to the capacities) and counts."""
+        frames = np.ascontiguousarray(frames)
+        B, h, w = frames.shape[:3]
+        cn = 1 if frames.ndim == 3 else frames.shape[3]
+        kps = np.zeros((B, self.cap), KEYPOINT_DTYPE); un = np.zeros((B, self.cap), KEYPOINT_DTYPE); desc = np.zeros((B, self.cap, 32), np.uint8)
+        kl = np.zeros((B, self.lcap), KEYLINE_DTYPE); ld = np.zeros((B, self.lcap, 32), np.uint8); eq = np.zeros((B, self.lcap, 3), np.float64)
+        n = np.zeros(B, np.int32); nl = np.zeros(B, np.int32)
+        _check(lib().sslpl_frame_extract_batch(self._h, _p(frames), B, w, h, frames.strides[1], C.c_size_t(frames.strides[0]), cn, int(rgb_order),
+                                               _p(kps), _p(un), _p(desc), self.cap, _p(n), _p(kl), _p(ld), _p(eq), self.lcap, _p(nl)))
+        return dict(keys=kps, keysUn=un, desc=desc, n=n, keylines=kl, ldesc=ld, lineeq=eq, nl=nl)
 
 
 # =====================================================================================================

@@ -1,5 +1,6 @@
 // core.cu — error reporting, version, pinned host memory of libsslpl_b200.
 #include "common.cuh"
+#include <cstdlib>
 #include <cstdarg>
 
 namespace sslpl {
@@ -19,6 +20,10 @@ int sslpl_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+int sslpl_default_device(void) {
+    const char* e = getenv("SSLPL_DEVICE");
+    return e && *e ? atoi(e) : 0;
 }
 int sslpl_host_alloc(void** p, size_t bytes) {
     SSLPL_REQUIRE(p, SSLPL_ERR_ARG, "null argument");

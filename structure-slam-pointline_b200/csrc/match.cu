@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(32) k_proj_match(const __grid_constant__ ProjA
             const int i = i0 + lane;
             bool drop = false;
             if (i < n1 && sel[i] >= 0) { const int b = rbin[i]; drop = (b != k0 && b != k1 && b != k2); }
-            if (drop) assign2[sel[i]] = -1;
+            if (drop) assign2[sel[i]] = -2;                       // assigned, then removed by the rotation check: the reference NULLs it explicitly (:1461)
             nmatches -= __popc(__ballot_sync(0xffffffffu, drop));
         }
     }

@@ -1040,6 +1040,14 @@ int sslpl_orb_tables(const sslpl_orb* h, float* scale, float* invscale, float* s
     return SSLPL_OK;
 }
 
+int sslpl_orb_tables_host(int nfeatures, float scaleFactor, int nlevels, float* scale, float* invscale, float* sigma2, float* invsigma2, int* nfeat, int* umax16) {
+    SSLPL_REQUIRE(nlevels >= 1 && nlevels <= SSLPL_MAX_LEVELS && nfeatures >= 1 && scaleFactor > 1.0f, SSLPL_ERR_ARG, "bad extractor parameters");
+    sslpl_orb tmp;
+    tmp.p.nfeatures = nfeatures; tmp.p.scaleFactor = scaleFactor; tmp.p.nlevels = nlevels;
+    make_tables(&tmp);
+    return sslpl_orb_tables(&tmp, scale, invscale, sigma2, invsigma2, nfeat, umax16);
+}
+
 int sslpl_orb_max_keypoints(const sslpl_orb* h) {
     if (!h) return 0;
     int s = 0; for (int l = 0; l < h->p.nlevels; l++) s += h->nfeat[l] + 16;

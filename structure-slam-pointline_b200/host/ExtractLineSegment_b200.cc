@@ -29,7 +29,7 @@ void LineSegment::ExtractLineSegment(const Mat &img, vector<KeyLine> &keylines, 
     {
         sslpl_line_destroy(ctx.h); ctx.h = NULL;
         sslpl_line_params p; p.lsdNFeatures = lsdNFeatures;
-        p.max_width = img.cols > 1280 ? img.cols : 1280; p.max_height = img.rows > 960 ? img.rows : 960; p.max_batch = 1; p.device = 0;
+        p.max_width = img.cols > ctx.w ? img.cols : ctx.w; p.max_height = img.rows > ctx.hgt ? img.rows : ctx.hgt; p.max_batch = 1; p.device = sslpl_default_device();
         if(sslpl_line_create(&p, &ctx.h) != SSLPL_OK)
             throw std::runtime_error(std::string("sslpl_line_create: ") + sslpl_last_error());
         ctx.w = p.max_width; ctx.hgt = p.max_height;

@@ -20,11 +20,11 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     iniThFAST(_iniThFAST), minThFAST(_minThFAST), mHandle(NULL), mMaxW(0), mMaxH(0)
 {
     mvImagePyramid.resize(nlevels);
-    EnsureHandle(1280, 960);                 // re-created on demand for larger frames
     mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);
     mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
-    Check(sslpl_orb_tables(mHandle, &mvScaleFactor[0], &mvInvScaleFactor[0], &mvLevelSigma2[0], &mvInvLevelSigma2[0], NULL, NULL),
-          "sslpl_orb_tables");
+    // the tables Frame.cc:77-83 reads; the device workspace is created by the first operator() call, for that frame size
+    Check(sslpl_orb_tables_host(nfeatures, (float)scaleFactor, nlevels, &mvScaleFactor[0], &mvInvScaleFactor[0], &mvLevelSigma2[0],
+                                &mvInvLevelSigma2[0], NULL, NULL), "sslpl_orb_tables_host");
 }
 
 ORBextractor::~ORBextractor()
@@ -42,7 +42,7 @@ void ORBextractor::EnsureHandle(int w, int h)
     sslpl_orb_params p;
     p.nfeatures = nfeatures; p.scaleFactor = (float)scaleFactor; p.nlevels = nlevels;
     p.iniThFAST = iniThFAST; p.minThFAST = minThFAST;
-    p.max_width = w > mMaxW ? w : mMaxW; p.max_height = h > mMaxH ? h : mMaxH; p.max_batch = 1; p.device = 0;
+    p.max_width = w > mMaxW ? w : mMaxW; p.max_height = h > mMaxH ? h : mMaxH; p.max_batch = 1; p.device = sslpl_default_device();
     Check(sslpl_orb_create(&p, &mHandle), "sslpl_orb_create");
     mMaxW = p.max_width; mMaxH = p.max_height;
     mKpBuf.resize(sslpl_orb_max_keypoints(mHandle));

@@ -34,7 +34,7 @@ VocabCtx& Voc() { static VocabCtx c; return c; }
 struct BowCtx {
     sslpl_matcher* h;
     BowCtx(): h(NULL) {
-        sslpl_matcher_params p; p.max_features = 8192; p.max_lines = 16; p.max_nodes = 16; p.max_batch = 1; p.device = 0;
+        sslpl_matcher_params p; p.max_features = 8192; p.max_lines = 16; p.max_nodes = 16; p.max_batch = 1; p.device = sslpl_default_device();
         if(sslpl_matcher_create(&p, &h) != SSLPL_OK) throw std::runtime_error(std::string("sslpl_matcher_create: ") + sslpl_last_error());
     }
     ~BowCtx() { sslpl_matcher_destroy(h); }
@@ -67,7 +67,7 @@ void SslplSetVocabularyFile(const std::string &strVocFile)
     VocabCtx &V = Voc();
     std::lock_guard<std::mutex> lock(V.mu);
     sslpl_vocab_destroy(V.v); V.v = NULL;
-    if(sslpl_vocab_load_text(0, strVocFile.c_str(), &V.v, &V.scoring, &V.weighting) != SSLPL_OK)
+    if(sslpl_vocab_load_text(sslpl_default_device(), strVocFile.c_str(), &V.v, &V.scoring, &V.weighting) != SSLPL_OK)
         throw std::runtime_error(std::string("sslpl_vocab_load_text: ") + sslpl_last_error());
 }
 

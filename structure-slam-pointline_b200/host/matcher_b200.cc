@@ -18,7 +18,7 @@ namespace {
 struct MatcherCtx {
     sslpl_matcher* h;
     MatcherCtx(): h(NULL) {
-        sslpl_matcher_params p; p.max_features = 8192; p.max_lines = 1024; p.max_nodes = 100000; p.max_batch = 1; p.device = 0;
+        sslpl_matcher_params p; p.max_features = 8192; p.max_lines = 1024; p.max_nodes = 100000; p.max_batch = 1; p.device = sslpl_default_device();
         if(sslpl_matcher_create(&p, &h) != SSLPL_OK) throw std::runtime_error(std::string("sslpl_matcher_create: ") + sslpl_last_error());
     }
     ~MatcherCtx() { sslpl_matcher_destroy(h); }
@@ -41,16 +41,14 @@ struct Csr {
 void Check(int rc, const char* what) { if(rc != SSLPL_OK) throw std::runtime_error(std::string(what) + ": " + sslpl_last_error()); }
 }
 
-int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)          // ORBmatcher.cc:1650
-{
-    int32_t d = 0;
-    Check(sslpl_descriptor_distance(Ctx(), a.ptr<uchar>(), b.ptr<uchar>(), 1, &d), "sslpl_descriptor_distance");
-    return d;
-}
+// ORBmatcher::DescriptorDistance (ORBmatcher.cc:1650) and LSDmatcher::DescriptorDistance (LSDmatcher.cpp:364) are NOT replaced: the
+// matchers that keep their CPU bodies (SearchByProjection x3, Fuse, SearchBySim3, MapPoint::ComputeDistinctiveDescriptors) call them
+// per descriptor pair inside inner loops, where the reference's 8-word popcount costs nanoseconds and a device round trip would
+// cost tens of microseconds.  The GPU distance exists in batched form only (sslpl_descriptor_distance with n >> 1, the medoid batch).
 
 // ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) — ORBmatcher.cc:1331-1473, the matcher of
 // Tracking::TrackWithMotionModel (Tracking.cc:1227, :1243).  Both call sites fill CurrentFrame.mvpMapPoints with NULL first;
-// this adapter relies on that (a feature that is not assigned ends up NULL, as in the reference after such a fill).
+// features the kernel never touched keep what they held, features removed by the rotation check are set to NULL (:1461).
 int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
 {
     const int n1 = LastFrame.N, n2 = CurrentFrame.N;
@@ -85,7 +83,11 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, 
                                            n2, &d2[0], &x2[0], &y2[0], &o2[0], &a2[0], &ur2[0], &claimed2[0], Tcw, Tlw, cam, bounds,
                                            &CurrentFrame.mvScaleFactors[0], (int)CurrentFrame.mvScaleFactors.size(), th, bMono ? 1 : 0,
                                            mbCheckOrientation ? 1 : 0, &assign[0], &nmatches), "sslpl_search_by_projection_frame");
-    for(int j=0; j<n2; j++) if(assign[j] >= 0) CurrentFrame.mvpMapPoints[j] = LastFrame.mvpMapPoints[assign[j]];
+    for(int j=0; j<n2; j++)
+    {
+        if(assign[j] >= 0) CurrentFrame.mvpMapPoints[j] = LastFrame.mvpMapPoints[assign[j]];
+        else if(assign[j] == -2) CurrentFrame.mvpMapPoints[j] = static_cast<MapPoint*>(NULL);   // removed by the rotation check, ORBmatcher.cc:1461
+    }
     return nmatches;
 }
 
@@ -164,19 +166,14 @@ int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F
 }
 
 // ---- LSDmatcher: the knnMatch-based entry points (LSDmatcher.cpp:143, 257, 286, 329, 382) ----
-int LSDmatcher::DescriptorDistance(const Mat &a, const Mat &b)                   // LSDmatcher.cpp:364
-{
-    int32_t d = 0;
-    Check(sslpl_descriptor_distance(Ctx(), a.ptr<uchar>(), b.ptr<uchar>(), 1, &d), "sslpl_descriptor_distance");
-    return d;
-}
-
+// (With fewer than two train lines cv::knnMatch returns fewer than two neighbours and the reference reads past the end; these
+// bodies return 0 matches then instead of failing.)
 static int LineMatchKF_F(KeyFrame* pKF, Frame &currentF, vector<MapLine*> &vpMapLineMatches)
 {
     const vector<MapLine*> vpMapLinesKF = pKF->GetMapLineMatches();
     vpMapLineMatches = vector<MapLine*>(currentF.NL,static_cast<MapLine*>(NULL));
     const int n1 = pKF->mLineDescriptors.rows, n2 = currentF.mLdesc.rows;
-    if(n1 == 0) return 0;
+    if(n1 == 0 || n2 < 2) return 0;
     std::vector<uint8_t> has1(n1);
     for(int i=0; i<n1; i++) has1[i] = vpMapLinesKF[i] ? 1 : 0;
     std::vector<int32_t> out(std::max(n1, n2)*2);
@@ -192,7 +189,7 @@ int LSDmatcher::SerachForInitialize(Frame &InitialFrame, Frame &CurrentFrame, ve
 {
     LineMatches.clear();
     const int n1 = InitialFrame.mLdesc.rows, n2 = CurrentFrame.mLdesc.rows;
-    if(n1 == 0) return 0;
+    if(n1 == 0 || n2 < 2) return 0;
     std::vector<int32_t> out(std::max(n1, n2)*2);
     int nout = 0, nmatches = 0;
     Check(sslpl_line_match(Ctx(), 1, InitialFrame.mLdesc.ptr<uchar>(), n1, CurrentFrame.mLdesc.ptr<uchar>(), n2, NULL, NULL, &out[0], &nout, &nmatches, NULL), "sslpl_line_match");
@@ -206,7 +203,7 @@ int LSDmatcher::SearchByDescriptor(KeyFrame* pKF, KeyFrame *pKF2, vector<MapLine
     const vector<MapLine*> vpMapLinesKF2 = pKF2->GetMapLineMatches();
     vpMapLineMatches = vector<MapLine*>(vpMapLinesKF.size(),static_cast<MapLine*>(NULL));
     const int n1 = pKF->mLineDescriptors.rows, n2 = pKF2->mLineDescriptors.rows;
-    if(n1 == 0) return 0;
+    if(n1 == 0 || n2 < 2) return 0;
     std::vector<uint8_t> has2(std::max(n2, 1));
     for(int i=0; i<n2; i++) has2[i] = vpMapLinesKF2[i] ? 1 : 0;
     std::vector<int32_t> out(std::max(n1, n2)*2);
@@ -220,7 +217,7 @@ int LSDmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, vector<pa
 {
     vMatchedPairs.clear();
     const int n1 = pKF1->mLineDescriptors.rows, n2 = pKF2->mLineDescriptors.rows;
-    if(n1 == 0) return 0;
+    if(n1 == 0 || n2 < 2) return 0;
     std::vector<uint8_t> has1(n1), has2(std::max(n2, 1));
     for(int i=0; i<n1; i++) has1[i] = pKF1->GetMapLine(i) ? 1 : 0;
     for(int i=0; i<n2; i++) has2[i] = pKF2->GetMapLine(i) ? 1 : 0;
