@@ -202,6 +202,25 @@ int  sslpl_search_by_projection_frame(sslpl_matcher* m,
         const uint8_t* claimed2, const float* Tcw, const float* Tlw, const float* cam, const float* bounds,
         const float* scaleFactors, int nlevels, float th, int bMono, int checkOrientation, int32_t* assign2, int* nmatches);
 
+/* ---- ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th) (ORBmatcher.cc:45-129): the matcher of
+   Tracking::SearchLocalPoints (Tracking.cc:1736), run on every frame.  Per MapPoint, in vector order, what Frame::isInFrustum left on
+   it: inview = mbTrackInView, bad = isBad() (NULL = none), obs = Observations() > 0 (NULL = none), projx/projy = mTrackProjX/Y,
+   projxr = mTrackProjXR (NULL for monocular), level = mnTrackScaleLevel, viewcos = mTrackViewCos, dmp = GetDescriptor().
+   Frame (n2): descriptors, mvKeysUn x / y / octave, mvuRight (NULL), held2[j] = 0 nothing, 1 a MapPoint with observations (skipped),
+   2 a MapPoint without (NULL = all 0).  assign2[j] = index of the MapPoint now written to F.mvpMapPoints[j] (-1: untouched). */
+int  sslpl_search_by_projection_mps(sslpl_matcher* m,
+        int nmp, const uint8_t* inview, const uint8_t* bad, const uint8_t* obs, const float* projx, const float* projy, const float* projxr,
+        const int32_t* level, const float* viewcos, const uint8_t* dmp,
+        int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* uright2, const uint8_t* held2,
+        const float* bounds, const float* scaleFactors, int nlevels, float nnratio, float th, int32_t* assign2, int* nmatches);
+/* ---- ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:408-523,
+   Tracking::MonocularInitialization Tracking.cc:366).  Keypoint fields are those of mvKeysUn; prev_xy[n1][2] = vbPrevMatched is
+   updated like the reference does (:517-520); matches12[n1] = vnMatches12. */
+int  sslpl_search_for_initialization(sslpl_matcher* m,
+        int n1, const uint8_t* d1, const int32_t* oct1, const float* angle1, float* prev_xy,
+        int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* angle2,
+        const float* bounds, float nnratio, int checkOrientation, int windowSize, int32_t* matches12, int* nmatches);
+
 /* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-312) / MapLine::ComputeDistinctiveDescriptors (MapLine.cpp:246-317),
    batched: group g owns descriptors desc[off[g] .. off[g+1]) (HOST buffers, off[0] = 0);
    best_idx[g] = index inside the group of the descriptor with the least median Hamming distance to the others (median =

@@ -308,6 +308,105 @@ extern "C" int orc_search_by_projection_frame(
     return nmatches;
 }
 
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th) — ORBmatcher.cc:45-129, the matcher of
+ * Tracking::SearchLocalPoints (TrackLocalMap, Tracking.cc:1736), run on every frame.  Per MapPoint (in vector order) the fields
+ * Frame::isInFrustum left on it: inview (mbTrackInView), bad (isBad()), projx/projy (mTrackProjX/Y), projxr (mTrackProjXR, may be
+ * NULL), level (mnTrackScaleLevel), viewcos (mTrackViewCos), its descriptor, and obs = Observations() > 0 (a frame feature holding
+ * such a point is skipped by later points, :86-88).  held2[j]: 0 = the frame feature holds nothing, 1 = a MapPoint WITH
+ * observations (skipped), 2 = a MapPoint without (may be replaced).  assign2[j] = index of the MapPoint written to
+ * F.mvpMapPoints[j] (the last writer), -1 none (features that only keep what they held are -1 too). */
+extern "C" int orc_search_by_projection_mps(
+        int nmp, const uint8_t* inview, const uint8_t* bad, const uint8_t* obs, const float* projx, const float* projy, const float* projxr,
+        const int32_t* level, const float* viewcos, const uint8_t* dmp,
+        int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* uright2, const uint8_t* held2,
+        const float* bounds, const float* scaleFactors, float nnratio, float th, int32_t* assign2) {
+    Grid* g = new Grid();
+    g->minX = bounds[0]; g->minY = bounds[2];
+    g->invW = (float)Grid::COLS / (bounds[1] - bounds[0]); g->invH = (float)Grid::ROWS / (bounds[3] - bounds[2]);
+    g->build(n2, x2, y2);
+    std::vector<uint8_t> claimed(n2, 0);
+    for (int j = 0; j < n2; j++) { assign2[j] = -1; claimed[j] = held2 && held2[j] == 1; }
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;                                                       /* :49 */
+    std::vector<int> cand;
+    for (int i = 0; i < nmp; i++) {
+        if (!inview[i]) continue;                                                         /* :54 */
+        if (bad && bad[i]) continue;                                                      /* :57 */
+        const int nPredictedLevel = level[i];
+        float r = viewcos[i] > 0.998 ? 2.5f : 4.0f;                                       /* RadiusByViewingCos :131-137 (double compare) */
+        if (bFactor) r *= th;
+        g->area(projx[i], projy[i], r * scaleFactors[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel, x2, y2, oct2, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : cand) {
+            if (claimed[idx]) continue;                                                   /* :86-88 */
+            if (uright2 && uright2[idx] > 0) {
+                const float er = std::fabs(projxr[i] - uright2[idx]);
+                if (er > r * scaleFactors[nPredictedLevel]) continue;
+            }
+            const int dist = orc_descriptor_distance(dmp + 32 * (size_t)i, d2 + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct2[idx]; bestIdx = idx; }
+            else if (dist < bestDist2) { bestLevel2 = oct2[idx]; bestDist2 = dist; }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2) continue;     /* :117 (int -> float) */
+            assign2[bestIdx] = i; claimed[bestIdx] = obs && obs[i];
+            nmatches++;
+        }
+    }
+    delete g;
+    return nmatches;
+}
+
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) — ORBmatcher.cc:408-523
+ * (Tracking::MonocularInitialization, Tracking.cc:366).  Keypoints are mvKeysUn; prev[2*n1] is vbPrevMatched (in/out). */
+extern "C" int orc_search_for_initialization(
+        int n1, const uint8_t* d1, const int32_t* oct1, const float* angle1,
+        int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* angle2,
+        float* prev, const float* bounds, float nnratio, int checkOri, int windowSize, int32_t* matches12) {
+    Grid* g = new Grid();
+    g->minX = bounds[0]; g->minY = bounds[2];
+    g->invW = (float)Grid::COLS / (bounds[1] - bounds[0]); g->invH = (float)Grid::ROWS / (bounds[3] - bounds[2]);
+    g->build(n2, x2, y2);
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int> matchedDistance(n2, 0x7fffffff), matches21(n2, -1), cand;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int level1 = oct1[i1];
+        if (level1 > 0) continue;                                                         /* :426 */
+        g->area(prev[2 * i1], prev[2 * i1 + 1], (float)windowSize, level1, level1, x2, y2, oct2, cand);
+        if (cand.empty()) continue;
+        int bestDist = 0x7fffffff, bestDist2 = 0x7fffffff, bestIdx2 = -1;
+        for (int i2 : cand) {
+            const int dist = orc_descriptor_distance(d1 + 32 * (size_t)i1, d2 + 32 * (size_t)i2);
+            if (matchedDistance[i2] <= dist) continue;                                    /* :448 */
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if ((float)bestDist < (float)bestDist2 * nnratio) {                          /* :464 */
+                if (matches21[bestIdx2] >= 0) { matches12[matches21[bestIdx2]] = -1; nmatches--; }
+                matches12[i1] = bestIdx2; matches21[bestIdx2] = i1; matchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (checkOri) rotHist[rot_bin(angle1[i1], angle2[bestIdx2])].push_back(i1);
+            }
+        }
+    }
+    delete g;
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i]) if (matches12[idx1] >= 0) { matches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++)                                                       /* :517-520 */
+        if (matches12[i1] >= 0) { prev[2 * i1] = x2[matches12[i1]]; prev[2 * i1 + 1] = y2[matches12[i1]]; }
+    return nmatches;
+}
+
 /* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-312) and MapLine::ComputeDistinctiveDescriptors
    (MapLine.cpp:246-317): for each group of observed descriptors, the one with the least MEDIAN Hamming distance to the rest
    (median = sorted[int(0.5 * (N - 1))], first minimum wins).  Groups in CSR form: off[g] .. off[g+1]. */

@@ -94,6 +94,14 @@ int   orc_search_for_triangulation(const uint8_t* d1, int n1, const uint8_t* d2,
                         const float* x2, const float* y2, const float* a2, const int32_t* oct2,
                         const float* F12, float ex, float ey, const float* scale, const float* sigma2,
                         int checkOri, int32_t* pairs /*2*n1*/);
+/* SearchByProjection(Frame&, vector<MapPoint*>&, th) ORBmatcher.cc:45-129 and SearchForInitialization :408-523 (see match_oracle.cpp) */
+int   orc_search_by_projection_mps(int nmp, const uint8_t* inview, const uint8_t* bad, const uint8_t* obs, const float* projx, const float* projy,
+                                   const float* projxr, const int32_t* level, const float* viewcos, const uint8_t* dmp,
+                                   int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* uright2,
+                                   const uint8_t* held2, const float* bounds, const float* scaleFactors, float nnratio, float th, int32_t* assign2);
+int   orc_search_for_initialization(int n1, const uint8_t* d1, const int32_t* oct1, const float* angle1,
+                                    int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* angle2,
+                                    float* prev, const float* bounds, float nnratio, int checkOri, int windowSize, int32_t* matches12);
 /* Frame::lineDescriptorMAD Frame.cc:190-215 on a knn2 table */
 void  orc_line_mad(const int32_t* knn, int nq, double* nn_mad, double* nn12_mad);
 /* LSDmatcher knn-based entry points. mode: 0 = SearchByProjection(KF,F)/SearchByDescriptor(KF,F) (ratio),

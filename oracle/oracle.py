@@ -241,6 +241,37 @@ def search_by_projection_frame(last, cur, Tcw, Tlw, cam, bounds, scale_factors, 
     return n, out[:n2]
 
 
+def search_by_projection_mps(mp, cur, bounds, scale_factors, nnratio=0.8, th=1.0):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (ORBmatcher.cc:45-129).
+    mp = dict(inview, bad, obs, projx, projy, level, viewcos, desc[, projxr]); cur = dict(desc, x, y, oct[, uright, held])."""
+    nmp = len(mp["inview"]); n2 = len(cur["x"])
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    iv, bad, obs = u8(mp["inview"]), u8(mp["bad"]), u8(mp["obs"])
+    px, py = _f32(mp["projx"]), _f32(mp["projy"]); pxr = _f32(mp["projxr"]) if mp.get("projxr") is not None else None
+    lv = np.ascontiguousarray(mp["level"], np.int32); vc = _f32(mp["viewcos"]); dmp = u8(mp["desc"]).reshape(-1, 32)
+    d2 = u8(cur["desc"]).reshape(-1, 32); x2, y2 = _f32(cur["x"]), _f32(cur["y"]); oc2 = np.ascontiguousarray(cur["oct"], np.int32)
+    ur = _f32(cur["uright"]) if cur.get("uright") is not None else None
+    held = u8(cur["held"]) if cur.get("held") is not None else None
+    out = np.full(max(n2, 1), -1, np.int32)
+    lib().orc_search_by_projection_mps.restype = C.c_int
+    n = lib().orc_search_by_projection_mps(nmp, _p(iv), _p(bad), _p(obs), _p(px), _p(py), _p(pxr) if pxr is not None else None, _p(lv), _p(vc), _p(dmp),
+                                           n2, _p(d2), _p(x2), _p(y2), _p(oc2), _p(ur) if ur is not None else None, _p(held) if held is not None else None,
+                                           _p(_f32(bounds)), _p(_f32(scale_factors)), C.c_float(nnratio), C.c_float(th), _p(out))
+    return n, out[:n2]
+
+
+def search_for_initialization(d1, k1, d2, k2, prev, bounds, nnratio=0.9, check_ori=True, window=100):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:408-523) -> (nmatches, matches12, prev_out)."""
+    d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+    prev = _f32(prev).reshape(-1, 2).copy()
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    lib().orc_search_for_initialization.restype = C.c_int
+    n = lib().orc_search_for_initialization(len(k1), _p(d1), _p(np.ascontiguousarray(k1["octave"], np.int32)), _p(_f32(k1["angle"])),
+                                            len(k2), _p(d2), _p(_f32(k2["x"])), _p(_f32(k2["y"])), _p(np.ascontiguousarray(k2["octave"], np.int32)),
+                                            _p(_f32(k2["angle"])), _p(prev), _p(_f32(bounds)), C.c_float(nnratio), int(check_ori), int(window), _p(m12))
+    return n, m12[:len(k1)], prev
+
+
 def features_in_area(kx, ky, oct, bounds, x, y, r, min_level=-1, max_level=-1):
     """Frame::GetFeaturesInArea (Frame.cc:368-421) over a freshly built grid (AssignFeaturesToGrid, :133-148)."""
     kx = _f32(kx); ky = _f32(ky); oct = np.ascontiguousarray(oct, np.int32)

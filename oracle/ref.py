@@ -134,15 +134,15 @@ def search_by_projection_frame(last, cur, Tcw, Tlw, camv, nlevels, scale, th, mo
 
 
 def search_by_projection_mps(mp, cur, camv, nlevels=8, scale=1.2, nnratio=0.8, th=1.0):
-    """mp = dict(inview, bad, projx, projy, level, viewcos, desc); cur = dict(desc, kps, claimed|None)."""
+    """mp = dict(inview, bad, obs, projx, projy, level, viewcos, desc); cur = dict(desc, kps, claimed|None) (claimed: 0 / 1 / 2)."""
     nmp = len(mp["inview"])
-    iv = np.ascontiguousarray(mp["inview"], np.uint8); bad = np.ascontiguousarray(mp["bad"], np.uint8)
+    iv = np.ascontiguousarray(mp["inview"], np.uint8); bad = np.ascontiguousarray(mp["bad"], np.uint8); obs = np.ascontiguousarray(mp["obs"], np.uint8)
     px = _f32(mp["projx"]); py = _f32(mp["projy"]); lv = np.ascontiguousarray(mp["level"], np.int32); vc = _f32(mp["viewcos"])
     dmp = np.ascontiguousarray(mp["desc"], np.uint8).reshape(-1, 32)
     d2 = np.ascontiguousarray(cur["desc"], np.uint8).reshape(-1, 32); k2 = _kp(cur["kps"]); n2 = len(k2)
     cl = np.ascontiguousarray(cur["claimed"], np.uint8) if cur.get("claimed") is not None else None
     out = np.full(max(n2, 1), -1, np.int32)
-    n = lib().ref_search_by_projection_mps(nmp, _p(iv), _p(bad), _p(px), _p(py), _p(lv), _p(vc), _p(dmp), n2, _p(d2), _p(k2),
+    n = lib().ref_search_by_projection_mps(nmp, _p(iv), _p(bad), _p(obs), _p(px), _p(py), _p(lv), _p(vc), _p(dmp), n2, _p(d2), _p(k2),
                                            _p(cl) if cl is not None else None, _p(_f32(camv)), nlevels, C.c_float(scale),
                                            C.c_float(nnratio), C.c_float(th), _p(out))
     return n, out[:n2]

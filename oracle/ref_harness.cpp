@@ -315,14 +315,16 @@ int ref_search_by_projection_frame(int n1, const uint8_t* valid1, const uint8_t*
    Frame::isInFrustum would have filled (mbTrackInView, mTrackProjX/Y, mnTrackScaleLevel, mTrackViewCos), its descriptor, bad flag.
    claimed2[j]: 0 free, 1 holds a MapPoint WITH observations (skipped), 2 holds a MapPoint without observations (may be overwritten).
    assign2[j] = index of the MapPoint assigned to frame feature j (-1 none, -2 a pre-existing one). */
-int ref_search_by_projection_mps(int nmp, const uint8_t* inview, const uint8_t* bad, const float* projx, const float* projy,
+int ref_search_by_projection_mps(int nmp, const uint8_t* inview, const uint8_t* bad, const uint8_t* obs, const float* projx, const float* projy,
                                  const int32_t* level, const float* viewcos, const uint8_t* dmp,
                                  int n2, const uint8_t* d2, const orc_keypoint* k2, const uint8_t* claimed2,
                                  const float* cam8, int nlevels, float scaleFactor, float nnratio, float th, int32_t* assign2) {
     Scene S;
     Cam cam; memcpy(&cam, cam8, sizeof(cam));
     Frame* F = make_frame(S, cam, nlevels, scaleFactor, k2, n2, d2, nullptr, nullptr, nullptr, 0, nullptr);
-    KeyFrame* KF = make_kf(S, make_frame(S, cam, nlevels, scaleFactor, k2, 0, d2, nullptr, nullptr, nullptr, 0, nullptr));
+    orc_keypoint one; memset(&one, 0, sizeof(one)); one.x = one.y = 10.f;
+    const uint8_t zero32[32] = {0};
+    KeyFrame* KF = make_kf(S, make_frame(S, cam, nlevels, scaleFactor, &one, 1, zero32, nullptr, nullptr, nullptr, 0, nullptr));   // the observer (AddObservation reads mvuRight[idx])
     std::map<MapPoint*, int> index;
     std::vector<MapPoint*> mps;
     for (int i = 0; i < nmp; i++) {
@@ -330,6 +332,7 @@ int ref_search_by_projection_mps(int nmp, const uint8_t* inview, const uint8_t* 
         p->mbTrackInView = inview[i] != 0; p->mbBad = bad && bad[i]; p->mTrackProjX = projx[i]; p->mTrackProjY = projy[i]; p->mTrackProjXR = -1;
         p->mnTrackScaleLevel = level[i]; p->mTrackViewCos = viewcos[i];
         desc_mat(dmp + 32 * (size_t)i, 1).copyTo(p->mDescriptor);
+        if (obs && obs[i]) p->AddObservation(KF, 0);
         mps.push_back(p); index[p] = i;
     }
     if (claimed2) for (int j = 0; j < n2; j++) if (claimed2[j]) {

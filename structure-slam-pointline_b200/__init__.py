@@ -339,6 +339,35 @@ class Matcher:
         _check(lib().sslpl_bow_transform(self._h, vocab._h, _p(desc), n, int(levelsup), _p(word), _p(node), _p(w)))
         return word[:n], node[:n], w[:n]
 
+    def search_by_projection_mps(self, mp, cur, bounds, scale_factors, nnratio=0.8, th=1.0):
+        """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (ORBmatcher.cc:45-129).
+        mp = dict(inview, bad, obs, projx, projy, level, viewcos, desc[, projxr]); cur = dict(desc, x, y, oct[, uright, held])."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32); u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+        nmp = len(mp["inview"]); n2 = len(cur["x"])
+        iv, bad, obs = u8(mp["inview"]), u8(mp["bad"]), u8(mp["obs"])
+        px, py = f32(mp["projx"]), f32(mp["projy"]); pxr = f32(mp["projxr"]) if mp.get("projxr") is not None else None
+        lv = np.ascontiguousarray(mp["level"], np.int32); vc = f32(mp["viewcos"]); dmp = u8(mp["desc"]).reshape(-1, 32)
+        d2 = u8(cur["desc"]).reshape(-1, 32); x2, y2 = f32(cur["x"]), f32(cur["y"]); oc2 = np.ascontiguousarray(cur["oct"], np.int32)
+        ur = f32(cur["uright"]) if cur.get("uright") is not None else None
+        held = u8(cur["held"]) if cur.get("held") is not None else None
+        sf = f32(scale_factors); out = np.full(max(n2, 1), -1, np.int32); nm = C.c_int()
+        _check(lib().sslpl_search_by_projection_mps(self._h, nmp, _p(iv), _p(bad), _p(obs), _p(px), _p(py), _p(pxr) if pxr is not None else None,
+                                                    _p(lv), _p(vc), _p(dmp), n2, _p(d2), _p(x2), _p(y2), _p(oc2), _p(ur) if ur is not None else None,
+                                                    _p(held) if held is not None else None, _p(f32(bounds)), _p(sf), len(sf),
+                                                    C.c_float(nnratio), C.c_float(th), _p(out), C.byref(nm)))
+        return nm.value, out[:n2]
+
+    def search_for_initialization(self, d1, k1, d2, k2, prev, bounds, nnratio=0.9, check_ori=True, window=100):
+        """ORBmatcher::SearchForInitialization (ORBmatcher.cc:408-523) -> (nmatches, matches12, prev_out)."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        prev = f32(prev).reshape(-1, 2).copy()
+        m12 = np.full(max(len(k1), 1), -1, np.int32); nm = C.c_int()
+        _check(lib().sslpl_search_for_initialization(self._h, len(k1), _p(d1), _p(np.ascontiguousarray(k1["octave"], np.int32)), _p(f32(k1["angle"])), _p(prev),
+                                                     len(k2), _p(d2), _p(f32(k2["x"])), _p(f32(k2["y"])), _p(np.ascontiguousarray(k2["octave"], np.int32)),
+                                                     _p(f32(k2["angle"])), _p(f32(bounds)), C.c_float(nnratio), int(check_ori), int(window), _p(m12), C.byref(nm)))
+        return nm.value, m12[:len(k1)], prev
+
     def search_by_projection_frame(self, last, cur, Tcw, Tlw, cam, bounds, scale_factors, th, mono=True, check_ori=True, raw=False):
         """ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (ORBmatcher.cc:1331-1473).
         last = dict(valid, obs, Xw[n,3], dmp[n,32], oct, angle); cur = dict(desc[n,32], x, y, oct, angle, uright|None, claimed|None);

@@ -444,6 +444,184 @@ __global__ void __launch_bounds__(32) k_proj_match(const __grid_constant__ ProjA
 }
 
 // -------------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th) — ORBmatcher.cc:45-129 (Tracking::SearchLocalPoints,
+// every frame) and ORBmatcher::SearchForInitialization — ORBmatcher.cc:408-523.  Both are greedy scans whose later iterations see
+// what earlier ones wrote (a feature that received a MapPoint with observations is skipped; a feature matched at distance d only
+// yields to a strictly smaller distance), so, like k_proj_match, ONE WARP walks the list in order and its lanes share the grid
+// cells of each search window.  The reference's sequential best / second-best update keeps the two smallest candidates in
+// (distance, traversal position) order: that is what the two-key reduction below computes.
+// -------------------------------------------------------------------------------------------------
+constexpr int TH_LOW_I = 50;                        // ORBmatcher.cc:38
+struct WinArgs { float minX, minY, invW, invH, th, nnratio; int bFactor, use_right, checkOri, window; float scale[32]; };
+
+__device__ __forceinline__ void top2_push(unsigned long long& a1, unsigned long long& a2, unsigned long long k) {
+    if (k < a1) { a2 = a1; a1 = k; } else if (k < a2) a2 = k;
+}
+__device__ __forceinline__ void top2_warp(unsigned long long& a1, unsigned long long& a2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
+        const unsigned long long lo = a1 < b1 ? a1 : b1, hi = a1 < b1 ? b1 : a1, m2 = a2 < b2 ? a2 : b2;
+        a1 = lo; a2 = hi < m2 ? hi : m2;
+    }
+}
+// the cell range of Frame::GetFeaturesInArea(x, y, r) (Frame.cc:375-393); false when the window misses the grid
+__device__ __forceinline__ bool grid_window(const WinArgs& A, float x, float y, float r, int& cx0, int& cx1, int& cy0, int& cy1) {
+    cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, A.minX), r), A.invW)));
+    if (cx0 >= GRID_COLS) return false;
+    cx1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, A.minX), r), A.invW)));
+    if (cx1 < 0) return false;
+    cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, A.minY), r), A.invH)));
+    if (cy0 >= GRID_ROWS) return false;
+    cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, A.minY), r), A.invH)));
+    return cy1 >= 0;
+}
+
+__global__ void __launch_bounds__(32) k_proj_match_mps(const __grid_constant__ WinArgs A, int nmp, const uint8_t* flag /* bit0 in view && !bad, bit1 obs>0 */,
+                                                        const float* px, const float* py, const float* pxr, const int* level, const float* viewcos, const uint8_t* dmp,
+                                                        int n2, const uint8_t* d2, const float* x2, const float* y2, const int* oct2, const float* uright2,
+                                                        uint8_t* claimed, const int* goff, const int* gidx, int32_t* assign2, int32_t* nmatch) {
+    const int lane = threadIdx.x;
+    for (int j = lane; j < n2; j += 32) assign2[j] = -1;
+    __syncwarp();
+    int nmatches = 0;
+    for (int i = 0; i < nmp; i++) {
+        const int fl = flag[i];
+        if (!(fl & 1)) continue;                                  // !mbTrackInView || isBad() (:54-58)
+        const int lvl = level[i];
+        float r = (double)viewcos[i] > 0.998 ? 2.5f : 4.0f;       // RadiusByViewingCos (:131-137)
+        if (A.bFactor) r = __fmul_rn(r, A.th);
+        const float rad = __fmul_rn(r, A.scale[lvl]);
+        const float u = px[i], v = py[i];
+        int cx0, cx1, cy0, cy1;
+        if (!grid_window(A, u, v, rad, cx0, cx1, cy0, cy1)) continue;
+        const int minLevel = lvl - 1, maxLevel = lvl;             // GetFeaturesInArea(..., nPredictedLevel-1, nPredictedLevel)
+        const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+        const int ny = cy1 - cy0 + 1, ncell = (cx1 - cx0 + 1) * ny;
+        uint4 a0, a1;
+        load_desc(dmp + (long long)i * 32, a0, a1);
+        unsigned long long b1 = ~0ull, b2 = ~0ull;                // (dist << 40) | (cell rank << 20) | position in the cell
+        for (int c = lane; c < ncell; c += 32) {
+            const int ix = cx0 + c / ny, iy = cy0 + c % ny, cell = ix * GRID_ROWS + iy;
+            const int b = goff[cell], e = goff[cell + 1];
+            for (int q = b; q < e; q++) {
+                const int j = gidx[q];
+                if (checkLevels) { const int o = oct2[j]; if (o < minLevel) continue; if (maxLevel >= 0 && o > maxLevel) continue; }
+                if (!(fabsf(__fsub_rn(x2[j], u)) < rad && fabsf(__fsub_rn(y2[j], v)) < rad)) continue;
+                if (claimed[j]) continue;                         // holds a MapPoint with observations (:86-88)
+                if (A.use_right && uright2[j] > 0) { if (fabsf(__fsub_rn(pxr[i], uright2[j])) > rad) continue; }
+                uint4 c0, c1;
+                load_desc(d2 + (long long)j * 32, c0, c1);
+                const int dist = popc256(a0, a1, c0, c1);
+                if (dist >= 256) continue;                        // never below the initial bestDist = bestDist2 = 256
+                top2_push(b1, b2, ((unsigned long long)dist << 40) | ((unsigned long long)c << 20) | (unsigned)(q - b));
+            }
+        }
+        top2_warp(b1, b2);
+        if (b1 == ~0ull) continue;
+        const int bestDist = (int)(b1 >> 40);
+        if (bestDist <= TH_HIGH) {
+            const int c = (int)((b1 >> 20) & 0xfffff), pos = (int)(b1 & 0xfffff);
+            const int j = gidx[goff[(cx0 + c / ny) * GRID_ROWS + cy0 + c % ny] + pos];
+            int bestDist2 = 256, bestLevel2 = -1;
+            if (b2 != ~0ull) {
+                const int c2 = (int)((b2 >> 20) & 0xfffff), pos2 = (int)(b2 & 0xfffff);
+                bestDist2 = (int)(b2 >> 40); bestLevel2 = oct2[gidx[goff[(cx0 + c2 / ny) * GRID_ROWS + cy0 + c2 % ny] + pos2]];
+            }
+            if (oct2[j] == bestLevel2 && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2)) continue;   // :117
+            if (lane == 0) { assign2[j] = i; claimed[j] = (fl >> 1) & 1; }
+            nmatches++;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) *nmatch = nmatches;
+}
+
+__global__ void __launch_bounds__(32) k_init_match(const __grid_constant__ WinArgs A, int n1, const uint8_t* d1, const int* oct1, const float* angle1,
+                                                    float* prevx, float* prevy, int n2, const uint8_t* d2, const float* x2, const float* y2, const int* oct2,
+                                                    const float* angle2, const int* goff, const int* gidx, int* matchedDist, int* matches21,
+                                                    int32_t* matches12, uint8_t* rbin, int32_t* nmatch) {
+    __shared__ int s_hist[HISTO_LENGTH];
+    __shared__ int s_keep[3];
+    const int lane = threadIdx.x;
+    for (int j = lane; j < n2; j += 32) { matchedDist[j] = 0x7fffffff; matches21[j] = -1; }
+    for (int i = lane; i < n1; i += 32) { matches12[i] = -1; rbin[i] = 255; }
+    if (lane < HISTO_LENGTH) s_hist[lane] = 0;
+    __syncwarp();
+    int nmatches = 0;
+    const float rad = (float)A.window;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int level1 = oct1[i1];
+        if (level1 > 0) continue;                                 // :426
+        const float u = prevx[i1], v = prevy[i1];
+        int cx0, cx1, cy0, cy1;
+        if (!grid_window(A, u, v, rad, cx0, cx1, cy0, cy1)) continue;
+        const int ny = cy1 - cy0 + 1, ncell = (cx1 - cx0 + 1) * ny;
+        uint4 a0, a1;
+        load_desc(d1 + (long long)i1 * 32, a0, a1);
+        unsigned long long b1 = ~0ull, b2 = ~0ull;
+        for (int c = lane; c < ncell; c += 32) {
+            const int ix = cx0 + c / ny, iy = cy0 + c % ny, cell = ix * GRID_ROWS + iy;
+            const int b = goff[cell], e = goff[cell + 1];
+            for (int q = b; q < e; q++) {
+                const int j = gidx[q];
+                { const int o = oct2[j]; if (o < level1 || o > level1) continue; }      // GetFeaturesInArea(..., level1, level1): levels are checked (maxLevel >= 0)
+                if (!(fabsf(__fsub_rn(x2[j], u)) < rad && fabsf(__fsub_rn(y2[j], v)) < rad)) continue;
+                uint4 c0, c1;
+                load_desc(d2 + (long long)j * 32, c0, c1);
+                const int dist = popc256(a0, a1, c0, c1);
+                if (matchedDist[j] <= dist) continue;             // :448
+                top2_push(b1, b2, ((unsigned long long)dist << 40) | ((unsigned long long)c << 20) | (unsigned)(q - b));
+            }
+        }
+        top2_warp(b1, b2);
+        if (b1 == ~0ull) continue;
+        const int bestDist = (int)(b1 >> 40);
+        const float bestDist2 = b2 == ~0ull ? (float)0x7fffffff : (float)(int)(b2 >> 40);
+        if (bestDist <= TH_LOW_I && (float)bestDist < __fmul_rn(bestDist2, A.nnratio)) {       // :462-464
+            const int c = (int)((b1 >> 20) & 0xfffff), pos = (int)(b1 & 0xfffff);
+            const int j = gidx[goff[(cx0 + c / ny) * GRID_ROWS + cy0 + c % ny] + pos];
+            const int old = matches21[j];
+            if (old >= 0) nmatches--;
+            if (lane == 0) {
+                if (old >= 0) matches12[old] = -1;
+                matches12[i1] = j; matches21[j] = i1; matchedDist[j] = bestDist;
+                if (A.checkOri) { const int bin = rot_bin(angle1[i1], angle2[j]); rbin[i1] = (uint8_t)bin; s_hist[bin]++; }
+            }
+            nmatches++;
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    if (A.checkOri) {
+        if (lane == 0) {                                         // ComputeThreeMaxima, ORBmatcher.cc:1604-1645
+            int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                const int sv = s_hist[i];
+                if (sv > max1) { max3 = max2; max2 = max1; max1 = sv; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (sv > max2) { max3 = max2; max2 = sv; ind3 = ind2; ind2 = i; }
+                else if (sv > max3) { max3 = sv; ind3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+            s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+        }
+        __syncwarp();
+        const int k0 = s_keep[0], k1 = s_keep[1], k2 = s_keep[2];
+        for (int i0 = 0; i0 < n1; i0 += 32) {
+            const int i = i0 + lane;
+            bool drop = false;
+            if (i < n1 && rbin[i] != 255) { const int b = rbin[i]; drop = (b != k0 && b != k1 && b != k2) && matches12[i] >= 0; }
+            if (drop) matches12[i] = -1;
+            nmatches -= __popc(__ballot_sync(0xffffffffu, drop));
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < n1; i += 32) { const int j = matches12[i]; if (j >= 0) { prevx[i] = x2[j]; prevy[i] = y2[j]; } }   // :517-520
+    if (lane == 0) *nmatch = nmatches;
+}
+
+// -------------------------------------------------------------------------------------------------
 // MapPoint / MapLine ::ComputeDistinctiveDescriptors (MapPoint.cc:247-312, MapLine.cpp:246-317), batched over groups of
 // observed descriptors (CSR): the descriptor with the least median Hamming distance to the others, first minimum wins.
 // One CTA per group, one thread per row; the median of a row (rank r = int(0.5 (N-1)) of N distances in 0..256) is found by
@@ -1009,6 +1187,120 @@ int sslpl_search_by_projection_frame(sslpl_matcher* m,
     SSLPL_CUDA(cudaMemcpyAsync(assign2, m->out, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, st));
     SSLPL_CUDA(cudaMemcpyAsync(m->h_small, m->nmatch, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SSLPL_CUDA(cudaStreamSynchronize(st));
+    *nmatches = m->h_small[0];
+    return SSLPL_OK;
+}
+
+static void fill_win(WinArgs& A, const float* bounds, const float* scaleFactors, int nlevels) {
+    memset(&A, 0, sizeof(A));
+    A.minX = bounds[0]; A.minY = bounds[2];
+    A.invW = (float)GRID_COLS / (bounds[1] - bounds[0]); A.invH = (float)GRID_ROWS / (bounds[3] - bounds[2]);   // Frame.cc:115-116
+    for (int k = 0; k < nlevels && k < 32; k++) A.scale[k] = scaleFactors ? scaleFactors[k] : 1.f;
+}
+
+int sslpl_search_by_projection_mps(sslpl_matcher* m,
+        int nmp, const uint8_t* inview, const uint8_t* bad, const uint8_t* obs, const float* projx, const float* projy, const float* projxr,
+        const int32_t* level, const float* viewcos, const uint8_t* dmp,
+        int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* uright2, const uint8_t* held2,
+        const float* bounds, const float* scaleFactors, int nlevels, float nnratio, float th, int32_t* assign2, int* nmatches) {
+    SSLPL_REQUIRE(m && assign2 && nmatches && bounds && scaleFactors, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(nmp >= 0 && n2 >= 0 && nmp <= m->cap && n2 <= m->cap && m->cap <= 8192 + 64, SSLPL_ERR_ARG, "nmp / n2 exceed the matcher capacity (<= 8192)");
+    SSLPL_REQUIRE(m->p.max_nodes >= GRID_COLS * GRID_ROWS, SSLPL_ERR_ARG, "the matcher needs max_nodes >= 3072 (64 x 48 grid cells)");
+    SSLPL_REQUIRE(nlevels >= 1 && nlevels <= 32, SSLPL_ERR_ARG, "nlevels out of range");
+    SSLPL_REQUIRE(nmp == 0 || (inview && projx && projy && level && viewcos && dmp), SSLPL_ERR_ARG, "null MapPoint array");
+    SSLPL_REQUIRE(n2 == 0 || (d2 && x2 && y2 && oct2), SSLPL_ERR_ARG, "null frame array");
+    SSLPL_REQUIRE(!uright2 || projxr, SSLPL_ERR_ARG, "stereo frame features need mTrackProjXR");
+    for (int j = 0; j < n2; j++) assign2[j] = -1;
+    *nmatches = 0;
+    if (nmp == 0 || n2 == 0) return SSLPL_OK;
+    for (int i = 0; i < nmp; i++) SSLPL_REQUIRE(level[i] >= 0 && level[i] < nlevels, SSLPL_ERR_ARG, "predicted level outside the scale-factor table");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    const int cap = m->cap, NN = m->p.max_nodes + 1, nc = GRID_COLS * GRID_ROWS;
+    WinArgs A; fill_win(A, bounds, scaleFactors, nlevels);
+    A.th = th; A.nnratio = nnratio; A.bFactor = th != 1.0f; A.use_right = uright2 ? 1 : 0;
+    std::vector<uint8_t> fl(nmp), cl(n2, 0);
+    for (int i = 0; i < nmp; i++) fl[i] = (uint8_t)(((inview[i] && !(bad && bad[i])) ? 1 : 0) | ((obs && obs[i]) ? 2 : 0));
+    if (held2) for (int j = 0; j < n2; j++) cl[j] = held2[j] == 1;
+    float* k0 = m->kpf; float* k1 = m->kpf + (size_t)cap * 7;
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc, dmp, (size_t)nmp * 32, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc + (size_t)cap * 32, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k0, projx, sizeof(float) * nmp, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k0 + (size_t)cap, projy, sizeof(float) * nmp, cudaMemcpyHostToDevice, st));
+    if (projxr) SSLPL_CUDA(cudaMemcpyAsync(k0 + 2 * (size_t)cap, projxr, sizeof(float) * nmp, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k0 + 3 * (size_t)cap, viewcos, sizeof(float) * nmp, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k0 + 4 * (size_t)cap, level, sizeof(int) * nmp, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k1, x2, sizeof(float) * n2, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k1 + (size_t)cap, y2, sizeof(float) * n2, cudaMemcpyHostToDevice, st));
+    if (uright2) SSLPL_CUDA(cudaMemcpyAsync(k1 + 3 * (size_t)cap, uright2, sizeof(float) * n2, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k1 + 4 * (size_t)cap, oct2, sizeof(int) * n2, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->flag, fl.data(), nmp, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->flag + cap, cl.data(), n2, cudaMemcpyHostToDevice, st));
+    m->h_small[0] = n2;
+    SSLPL_CUDA(cudaMemcpyAsync(m->ncnt, m->h_small, sizeof(int), cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));                               // pageable staging vectors go out of scope
+    int* goff = m->off + (NN + 1); int* gidx = m->idx + cap;
+    k_grid_cells<<<(n2 + 127) / 128, 128, 0, st>>>(k1, k1 + cap, n2, A.minX, A.minY, A.invW, A.invH, m->node);
+    k_build_csr<<<1, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->node, 0, m->ncnt, cap, nc, goff, 0, gidx, 0);
+    k_proj_match_mps<<<1, 32, 0, st>>>(A, nmp, m->flag, k0, k0 + cap, k0 + 2 * (size_t)cap, reinterpret_cast<const int*>(k0 + 4 * (size_t)cap), k0 + 3 * (size_t)cap, m->desc,
+                                       n2, m->desc + (size_t)cap * 32, k1, k1 + cap, reinterpret_cast<const int*>(k1 + 4 * (size_t)cap), k1 + 3 * (size_t)cap,
+                                       m->flag + cap, goff, gidx, m->out, m->nmatch);
+    m->launches += 3;
+    SSLPL_CUDA(cudaGetLastError());
+    SSLPL_CUDA(cudaMemcpyAsync(assign2, m->out, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->h_small, m->nmatch, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    *nmatches = m->h_small[0];
+    return SSLPL_OK;
+}
+
+int sslpl_search_for_initialization(sslpl_matcher* m,
+        int n1, const uint8_t* d1, const int32_t* oct1, const float* angle1, float* prev_xy /* [n1][2], in/out */,
+        int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* angle2,
+        const float* bounds, float nnratio, int checkOri, int windowSize, int32_t* matches12, int* nmatches) {
+    SSLPL_REQUIRE(m && matches12 && nmatches && bounds, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(n1 >= 0 && n2 >= 0 && n1 <= m->cap && n2 <= m->cap && m->cap <= 8192 + 64, SSLPL_ERR_ARG, "n1 / n2 exceed the matcher capacity (<= 8192 features)");
+    SSLPL_REQUIRE(m->p.max_nodes >= GRID_COLS * GRID_ROWS, SSLPL_ERR_ARG, "the matcher needs max_nodes >= 3072 (64 x 48 grid cells)");
+    SSLPL_REQUIRE(n1 == 0 || (d1 && oct1 && angle1 && prev_xy), SSLPL_ERR_ARG, "null first-frame array");
+    SSLPL_REQUIRE(n2 == 0 || (d2 && x2 && y2 && oct2 && angle2), SSLPL_ERR_ARG, "null second-frame array");
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    *nmatches = 0;
+    if (n1 == 0 || n2 == 0) return SSLPL_OK;
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    const int cap = m->cap, NN = m->p.max_nodes + 1, nc = GRID_COLS * GRID_ROWS;
+    WinArgs A; fill_win(A, bounds, nullptr, 0);
+    A.nnratio = nnratio; A.checkOri = checkOri ? 1 : 0; A.window = windowSize;
+    std::vector<float> px(n1), py(n1);
+    for (int i = 0; i < n1; i++) { px[i] = prev_xy[2 * i]; py[i] = prev_xy[2 * i + 1]; }
+    float* k0 = m->kpf; float* k1 = m->kpf + (size_t)cap * 7;
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc, d1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->desc + (size_t)cap * 32, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k0, px.data(), sizeof(float) * n1, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k0 + (size_t)cap, py.data(), sizeof(float) * n1, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k0 + 3 * (size_t)cap, angle1, sizeof(float) * n1, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k0 + 4 * (size_t)cap, oct1, sizeof(int) * n1, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k1, x2, sizeof(float) * n2, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k1 + (size_t)cap, y2, sizeof(float) * n2, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k1 + 2 * (size_t)cap, angle2, sizeof(float) * n2, cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaMemcpyAsync(k1 + 4 * (size_t)cap, oct2, sizeof(int) * n2, cudaMemcpyHostToDevice, st));
+    m->h_small[0] = n2;
+    SSLPL_CUDA(cudaMemcpyAsync(m->ncnt, m->h_small, sizeof(int), cudaMemcpyHostToDevice, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    int* goff = m->off + (NN + 1); int* gidx = m->idx + cap;
+    k_grid_cells<<<(n2 + 127) / 128, 128, 0, st>>>(k1, k1 + cap, n2, A.minX, A.minY, A.invW, A.invH, m->node);
+    k_build_csr<<<1, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->node, 0, m->ncnt, cap, nc, goff, 0, gidx, 0);
+    k_init_match<<<1, 32, 0, st>>>(A, n1, m->desc, reinterpret_cast<const int*>(k0 + 4 * (size_t)cap), k0 + 3 * (size_t)cap, k0, k0 + cap,
+                                   n2, m->desc + (size_t)cap * 32, k1, k1 + cap, reinterpret_cast<const int*>(k1 + 4 * (size_t)cap), k1 + 2 * (size_t)cap,
+                                   goff, gidx, m->knn, m->knn + cap, m->out, m->rot, m->nmatch);
+    m->launches += 3;
+    SSLPL_CUDA(cudaGetLastError());
+    SSLPL_CUDA(cudaMemcpyAsync(matches12, m->out, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaMemcpyAsync(px.data(), k0, sizeof(float) * n1, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaMemcpyAsync(py.data(), k0 + cap, sizeof(float) * n1, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->h_small, m->nmatch, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < n1; i++) { prev_xy[2 * i] = px[i]; prev_xy[2 * i + 1] = py[i]; }
     *nmatches = m->h_small[0];
     return SSLPL_OK;
 }

@@ -91,6 +91,57 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, 
     return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th) — ORBmatcher.cc:45-129, called on every frame by
+// Tracking::SearchLocalPoints (Tracking.cc:1736) with the tracking fields Frame::isInFrustum left on each MapPoint.
+int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th)
+{
+    const int nmp = (int)vpMapPoints.size(), n2 = F.N;
+    if(nmp == 0 || n2 == 0) return 0;
+    std::vector<uint8_t> inview(nmp), bad(nmp), obs(nmp), dmp((size_t)nmp*32, 0), held(n2, 0), d2((size_t)n2*32);
+    std::vector<float> px(nmp), py(nmp), pxr(nmp), vc(nmp), x2(n2), y2(n2), ur2(n2);
+    std::vector<int32_t> lvl(nmp), o2(n2), assign(n2);
+    for(int i=0; i<nmp; i++) {
+        MapPoint* p = vpMapPoints[i];
+        inview[i] = p->mbTrackInView ? 1 : 0; bad[i] = p->isBad() ? 1 : 0; obs[i] = p->Observations() > 0 ? 1 : 0;
+        px[i] = p->mTrackProjX; py[i] = p->mTrackProjY; pxr[i] = p->mTrackProjXR; vc[i] = p->mTrackViewCos;
+        lvl[i] = inview[i] ? p->mnTrackScaleLevel : 0;
+        if(inview[i] && !bad[i]) { const cv::Mat d = p->GetDescriptor(); std::copy(d.ptr<uchar>(), d.ptr<uchar>() + 32, &dmp[(size_t)32*i]); }
+    }
+    bool stereo = false;
+    for(int j=0; j<n2; j++) {
+        const cv::KeyPoint &kp = F.mvKeysUn[j];
+        x2[j] = kp.pt.x; y2[j] = kp.pt.y; o2[j] = kp.octave; ur2[j] = F.mvuRight[j]; stereo = stereo || ur2[j] > 0;
+        MapPoint* q = F.mvpMapPoints[j];
+        held[j] = q ? (q->Observations() > 0 ? 1 : 2) : 0;
+        std::copy(F.mDescriptors.ptr<uchar>(j), F.mDescriptors.ptr<uchar>(j) + 32, &d2[(size_t)32*j]);
+    }
+    const float bounds[4] = {F.mnMinX, F.mnMaxX, F.mnMinY, F.mnMaxY};
+    int nmatches = 0;
+    Check(sslpl_search_by_projection_mps(Ctx(), nmp, &inview[0], &bad[0], &obs[0], &px[0], &py[0], &pxr[0], &lvl[0], &vc[0], &dmp[0],
+                                         n2, &d2[0], &x2[0], &y2[0], &o2[0], stereo ? &ur2[0] : NULL, &held[0], bounds,
+                                         &F.mvScaleFactors[0], (int)F.mvScaleFactors.size(), mfNNratio, th, &assign[0], &nmatches), "sslpl_search_by_projection_mps");
+    for(int j=0; j<n2; j++) if(assign[j] >= 0) F.mvpMapPoints[j] = vpMapPoints[assign[j]];
+    return nmatches;
+}
+
+// ORBmatcher::SearchForInitialization — ORBmatcher.cc:408-523 (Tracking::MonocularInitialization, Tracking.cc:366)
+int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12, int windowSize)
+{
+    const int n1 = (int)F1.mvKeysUn.size(), n2 = (int)F2.mvKeysUn.size();
+    vnMatches12 = vector<int>(n1,-1);
+    if(n1 == 0 || n2 == 0) return 0;
+    std::vector<float> a1(n1), prev((size_t)2*n1), x2(n2), y2(n2), a2(n2);
+    std::vector<int32_t> o1(n1), o2(n2), m12(n1);
+    for(int i=0; i<n1; i++) { a1[i] = F1.mvKeysUn[i].angle; o1[i] = F1.mvKeysUn[i].octave; prev[2*i] = vbPrevMatched[i].x; prev[2*i+1] = vbPrevMatched[i].y; }
+    for(int j=0; j<n2; j++) { const cv::KeyPoint &kp = F2.mvKeysUn[j]; x2[j] = kp.pt.x; y2[j] = kp.pt.y; a2[j] = kp.angle; o2[j] = kp.octave; }
+    const float bounds[4] = {F2.mnMinX, F2.mnMaxX, F2.mnMinY, F2.mnMaxY};
+    int nmatches = 0;
+    Check(sslpl_search_for_initialization(Ctx(), n1, F1.mDescriptors.ptr<uchar>(), &o1[0], &a1[0], &prev[0], n2, F2.mDescriptors.ptr<uchar>(),
+                                          &x2[0], &y2[0], &o2[0], &a2[0], bounds, mfNNratio, mbCheckOrientation ? 1 : 0, windowSize, &m12[0], &nmatches), "sslpl_search_for_initialization");
+    for(int i=0; i<n1; i++) { vnMatches12[i] = m12[i]; vbPrevMatched[i] = cv::Point2f(prev[2*i], prev[2*i+1]); }
+    return nmatches;
+}
+
 int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F, vector<MapPoint*> &vpMapPointMatches)   // ORBmatcher.cc:159
 {
     const vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();

@@ -75,12 +75,11 @@ def test_feature_vector_csr_matches_oracle_helper(pkg, oracle):
         assert np.all(node[seg] == ids[k]) and np.all(np.diff(seg) > 0)       # ascending feature indices (FeatureVector.cpp:31-45)
 
 
-def test_orbextractor_adapter_compiles_against_shim():
-    """host/ORBextractor.{h,cc} (the reference's class signature over the C ABI) type-checks against the minimal OpenCV
-    shim in host/shim (no OpenCV C++ in this image).  The adapters that include the reference's own headers are checked
-    against stand-in declarations in test_reference_side_adapters_type_check below."""
+def test_orbextractor_adapter_keeps_the_reference_signature():
+    """host/ORBextractor.h keeps the reference's class surface (include/ORBextractor.h:45-111) and compiles against the OpenCV
+    stand-in of oracle/refshim (no OpenCV C++ in this image; the other adapters are compiled against the reference's real headers below)."""
     H = os.path.join(ROOT, "structure-slam-pointline_b200", "host")
-    r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-Wall", "-I", os.path.join(H, "shim"), "-I", H,
+    r = subprocess.run(["/usr/bin/g++", "-std=c++14", "-fsyntax-only", "-w", "-I", os.path.join(ROOT, "oracle", "refshim"), "-I", H,
                         "-I", os.path.join(ROOT, "include"), os.path.join(H, "ORBextractor.cc")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     hdr = open(os.path.join(H, "ORBextractor.h")).read()
@@ -106,14 +105,18 @@ def test_header_is_plain_c99(tmp_path):
     assert r.returncode == 0, (r.stdout, r.stderr)
 
 
-def test_reference_side_adapters_type_check():
-    """host/{matcher_b200,bow_b200,ExtractLineSegment_b200}.cc include the REFERENCE's headers (ORBmatcher.h, LSDmatcher.h, Frame.h,
-    KeyFrame.h, ExtractLineSegment.h), which cannot be compiled here (OpenCV C++, Eigen, DBoW2, g2o, Pangolin).  tests/refshim holds
-    stand-in declarations of exactly the members the adapters touch (written from the cited header lines): compiling against them
-    type-checks the adapters themselves and every sslpl_* call they make (argument count, order and types)."""
+def test_reference_side_adapters_compile_against_the_reference_headers():
+    """host/*.cc are compiled against the reference's REAL headers (include/ORBmatcher.h, LSDmatcher.h, Frame.h, KeyFrame.h,
+    ExtractLineSegment.h, MapPoint.h, Thirdparty/DBoW2) read in place from /root/reference, with the functional OpenCV / Eigen
+    stand-ins of oracle/refshim (OpenCV C++ is not installed) — the same flags tests/integration/build_ref_link.sh uses to LINK them
+    with the reference's own objects (run on the GPU by tests/test_integration_gpu.py).  Skipped where the reference is absent."""
+    ref = os.environ.get("SSLPL_REFERENCE_DIR", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "src")):
+        import pytest
+        pytest.skip("reference tree absent")
     H = os.path.join(ROOT, "structure-slam-pointline_b200", "host")
-    inc = ["-I", os.path.join(ROOT, "tests", "refshim"), "-I", os.path.join(H, "shim"), "-I", os.path.join(H, "shim", "eigen3"),
-           "-I", os.path.join(ROOT, "include")]
-    for f in ("matcher_b200.cc", "bow_b200.cc", "ExtractLineSegment_b200.cc"):
-        r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-Wall"] + inc + [os.path.join(H, f)], capture_output=True, text=True)
-        assert r.returncode == 0 and "warning" not in r.stderr, (f, r.stderr[-3000:])
+    flags = ["-std=c++14", "-fsyntax-only", "-w", "-include", os.path.join(H, "ORBextractor.h"), "-I", H, "-I", os.path.join(ROOT, "include"),
+             "-I", os.path.join(ROOT, "oracle", "refshim"), "-I", os.path.join(ref, "include"), "-I", ref]
+    for f in ("ORBextractor.cc", "matcher_b200.cc", "bow_b200.cc", "ExtractLineSegment_b200.cc"):
+        r = subprocess.run(["/usr/bin/g++"] + flags + [os.path.join(H, f)], capture_output=True, text=True)
+        assert r.returncode == 0, (f, r.stderr[-3000:])

@@ -219,6 +219,43 @@ def test_search_by_projection_frame(oracle, ref, synth, seed, th, mono, ori, cla
             assert n_r == n_o and np.array_equal(np.where(a_r == -2, -1, a_r), a_o), mod
 
 
+@pytest.mark.parametrize("seed,th,ratio", [(1, 1.0, 0.8), (2, 3.0, 0.8), (3, 1.0, 0.6), (4, 5.0, 0.9)])
+def test_search_by_projection_map_points(oracle, ref, synth, seed, th, ratio):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) :45-129 — Tracking::SearchLocalPoints, every frame."""
+    from scenarios import local_map_scenario
+    mp, cur, bounds, sf = local_map_scenario(oracle, synth, seed, f0=seed)
+    n_o, a_o = oracle.search_by_projection_mps(mp, cur, bounds, sf, ratio, th)
+    n_r, a_r = ref.search_by_projection_mps(mp, cur, ref.cam(500, 500, 320, 240, *bounds), 8, 1.2, ratio, th)
+    assert n_r == n_o and np.array_equal(np.where(a_r == -2, -1, a_r), a_o), (n_r, n_o, int((a_r != a_o).sum()))
+    assert n_o > 300
+    if seed == 1:
+        for mod in ("none_in_view", "all_held", "no_obs"):
+            m2, c2 = dict(mp), dict(cur)
+            if mod == "none_in_view": m2["inview"] = np.zeros_like(mp["inview"])
+            if mod == "all_held": c2["held"] = c2["claimed"] = np.ones(len(cur["x"]), np.uint8)
+            if mod == "no_obs": m2["obs"] = np.zeros_like(mp["obs"])
+            n_o, a_o = oracle.search_by_projection_mps(m2, c2, bounds, sf, ratio, th)
+            n_r, a_r = ref.search_by_projection_mps(m2, c2, ref.cam(500, 500, 320, 240, *bounds), 8, 1.2, ratio, th)
+            assert n_r == n_o and np.array_equal(np.where(a_r == -2, -1, a_r), a_o), mod
+
+
+@pytest.mark.parametrize("f0,window,ratio,ori,nf", [(0, 100, 0.9, True, 2000), (8, 50, 0.9, True, 1000), (16, 100, 0.7, False, 2000), (3, 10, 0.9, True, 1000)])
+def test_search_for_initialization(oracle, ref, synth, f0, window, ratio, ori, nf):
+    """ORBmatcher::SearchForInitialization :408-523 (Tracking::MonocularInitialization, the 2 * nFeatures extractor)."""
+    orc = oracle.OrbOracle(nf, 1.2, 8, 20, 7)
+    k1, d1 = orc.extract(synth.frame(640, 480, f0)); k2, d2 = orc.extract(synth.frame(640, 480, f0 + 2))
+    prev = np.stack([k1["x"], k1["y"]], 1)                                   # Tracking.cc:339-341: vbPrevMatched = keypoints of the first frame
+    bounds = (0.0, 640.0, 0.0, 480.0)
+    n_o, m_o, p_o = oracle.search_for_initialization(d1, k1, d2, k2, prev, bounds, ratio, ori, window)
+    n_r, m_r, p_r = ref.search_for_initialization(d1, k1, d2, k2, prev, ref.cam(500, 500, 320, 240, *bounds), 8, 1.2, ratio, ori, window)
+    assert n_r == n_o and np.array_equal(m_r, m_o) and np.array_equal(p_r, p_o)
+    assert n_o > 50 or window < 20
+    # second call, as Tracking does on the next frame with the updated vbPrevMatched
+    n_o2, m_o2, _ = oracle.search_for_initialization(d1, k1, d2, k2, p_o, bounds, ratio, ori, window)
+    n_r2, m_r2, _ = ref.search_for_initialization(d1, k1, d2, k2, p_r, ref.cam(500, 500, 320, 240, *bounds), 8, 1.2, ratio, ori, window)
+    assert n_r2 == n_o2 and np.array_equal(m_r2, m_o2)
+
+
 def test_descriptor_medoid(oracle, ref):
     """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-312): least-median descriptor of each observation group."""
     rng = np.random.default_rng(8)
