@@ -331,9 +331,11 @@ def main():
     class _DevArr:                                      # a torch view of a device array owned by the library (counts only)
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
-    _, _, _nptr, _ = ext.device_results()
-    t_nkp = torch.as_tensor(_DevArr(_nptr, B), device=dev)
-    t_nl = [torch.as_tensor(_DevArr(l.device_results()[3], B), device=dev) for l in lsr]
+    _views = {}
+    def dev_i32(ptr, n):                                # (the result arrays exist after the handle's first call: looked up per step, cached)
+        if (ptr, n) not in _views:
+            _views[(ptr, n)] = torch.as_tensor(_DevArr(int(ptr), n), device=dev)
+        return _views[(ptr, n)]
     u_pts = torch.zeros((), dtype=torch.int64, device=dev)     # features + matches of the timed loop, summed ON the device,
     u_lin = [torch.zeros((), dtype=torch.int64, device=dev) for _ in range(R)]   # inside the timed region (no separate counting pass)
     pending = [False] * R
@@ -366,13 +368,13 @@ def main():
         _, ldesc, _, nl, capl = lsr[r].device_results()
         lmr[r].match_lines_batch_device(ldesc, nl, B, capl, d_lmatch[r].data_ptr(), d_nlmatch[r].data_ptr())
         with torch.cuda.stream(s_lin[r]):
-            u_lin[r] += t_nl[r][:Bf].sum() + d_nlmatch[r].sum()
+            u_lin[r] += dev_i32(nl, B)[:Bf].sum() + d_nlmatch[r].sum()
         pending[r] = True
 
     def enqueue_points():
         kps, desc, n, c = ext.device_results()
         mt.match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match.data_ptr(), d_nmatch.data_ptr())
-        u_pts.add_(t_nkp[:Bf].sum() + d_nmatch.sum())
+        u_pts.add_(dev_i32(n, B)[:Bf].sum() + d_nmatch.sum())
         if gather[0]:
             pgather.gather(d_match)
 

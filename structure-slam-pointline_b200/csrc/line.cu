@@ -1794,6 +1794,7 @@ int run_pipeline(sslpl_line* h, int B) {
 }
 
 int check_device_err(sslpl_line* h) {
+    if (h->cur_w == 0) { SSLPL_CUDA(cudaStreamSynchronize(h->stream)); return SSLPL_OK; }     // never used yet: no workspace, nothing to report
     SSLPL_CUDA(cudaMemcpyAsync(h->h_err, h->ws.err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     SSLPL_CUDA(cudaStreamSynchronize(h->stream));
     if (*h->h_err) {
