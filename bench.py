@@ -444,107 +444,7 @@ def main():
         gather_check = {"rows_of_this_rank_equal_local_table": mine_ok, "all_ranks_hold_the_same_tables": bool(hmin.item() == hmax.item()),
                         "ok_on_every_rank": bool(okt.item()), "checksum": int(hsh.item())}
 
-    # ---- e2e: pinned host frames -> H2D -> kernels -> D2H of keypoints, descriptors, lines, counts, match tables ----
-    # Both paths are software-pipelined through their public asynchronous entry points (extract_batch_begin): a ring of
-    # R line handles and a ring of 2 point handles, so that the upload of step i+1 overlaps the kernels of step i.  Every
-    # step's results are read back into pinned host memory and consumed (counted) on the host inside the timed region.
-    h_sets = []
-    for s in sets:
-        hp = pkg.host_alloc(s.shape, np.uint8); hp[...] = s; h_sets.append(hp)
-    PR = int(os.environ.get('SSLPL_BENCH_PR', '2'))
-    VARIANT = os.environ.get('SSLPL_E2E_VARIANT', '')       # diagnostics; the reported e2e always uses the default (host buffers)
-    exts, mts, s_p, d_match_e, d_nmatch_e = [ext], [mt], [s_pts], [d_match], [d_nmatch]
-    for _ in range(PR - 1):
-        e_ = pkg.ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B, device=local)
-        m_ = pkg.Matcher(max_features=ext.cap, max_lines=NL, max_nodes=NWORDS, max_batch=B, device=local)
-        st_ = torch.cuda.Stream(device=dev, priority=PRIO)
-        e_.set_stream(st_.cuda_stream); m_.set_stream(st_.cuda_stream)
-        exts.append(e_); mts.append(m_); s_p.append(st_)
-        d_match_e.append(torch.empty_like(d_match)); d_nmatch_e.append(torch.empty_like(d_nmatch))
-    h_out = [(pkg.host_alloc((B, cap), pkg.KEYPOINT_DTYPE), pkg.host_alloc((B, cap, 32), np.uint8), pkg.host_alloc((B,), np.int32)) for _ in range(PR)]
-    h_lout = [(pkg.host_alloc((B, NL), pkg.KEYLINE_DTYPE), pkg.host_alloc((B, NL, 32), np.uint8),
-               pkg.host_alloc((B, NL, 3), np.float64), pkg.host_alloc((B,), np.int32)) for _ in range(R)]
-    h_match = [torch.empty((Bf, cap), dtype=torch.int32).pin_memory() for _ in range(PR)]
-    h_nmatch = [torch.empty((Bf,), dtype=torch.int32).pin_memory() for _ in range(PR)]
-    h_lmatch = [torch.empty((Bf, NL), dtype=torch.int32).pin_memory() for _ in range(R)]
-    h_nlmatch = [torch.zeros((Bf,), dtype=torch.int32).pin_memory() for _ in range(R)]
-    e2e_pending = [False] * R
-    pts_pending = [False] * PR
-
-    pg_e = [pgather] + [sbatch.PackedGather(Bf, cap, NL, world, dev) for _ in range(PR - 1)] if world > 1 else [None] * PR
-
-    def e2e_finalize(r, p=None):
-        """Host-side completion of line slot r: wait for its stream, then the results are in the pinned host buffers.
-        With p given, the slot's match table rides along with point slot p's all-gather; otherwise it is gathered now."""
-        if not e2e_pending[r]:
-            return 0
-        if world > 1:
-            sp = s_p[p] if p is not None else s_pts
-            sp.wait_stream(s_lin[r])
-            with torch.cuda.stream(sp):
-                if p is not None:
-                    pg_e[p].stage_lines(d_lmatch[r])
-                else:
-                    dist.all_gather_into_tensor(d_lgather, d_lmatch[r])
-            ev_free[r].record(sp)
-        lsr[r].sync()                                                          # stream sync + deferred device error check
-        e2e_pending[r] = False
-        return int(h_lout[r][3][:Bf].sum()) + int(h_nlmatch[r].sum())
-
-    def pts_finalize(p):
-        if not pts_pending[p]:
-            return 0
-        exts[p].sync()
-        pts_pending[p] = False
-        return int(h_out[p][2][:Bf].sum()) + int(h_nmatch[p].sum())
-
-    def step_e2e(i):
-        fr = h_sets[i % nsets]
-        u = 0
-        p = i % PR
-        if LINES:
-            r = i % R
-            u += e2e_finalize(r, p)
-            if world > 1:
-                s_lin[r].wait_event(ev_free[r])
-            if VARIANT == "noh2d":
-                lsr[r].extract_batch_device(d_sets[i % nsets].data_ptr(), B, W, H, W, W * H)   # diagnostic only (SSLPL_E2E_VARIANT)
-            else:
-                lsr[r].extract_batch_begin(fr, h_lout[r])                      # H2D + kernels + D2H enqueued on slot r's stream
-            _, ldesc, _, nl, capl = lsr[r].device_results()
-            lmr[r].match_lines_batch_device(ldesc, nl, B, capl, d_lmatch[r].data_ptr(), d_nlmatch[r].data_ptr())
-            with torch.cuda.stream(s_lin[r]):
-                h_lmatch[r].copy_(d_lmatch[r], non_blocking=True); h_nlmatch[r].copy_(d_nlmatch[r], non_blocking=True)
-            e2e_pending[r] = True
-        u += pts_finalize(p)
-        if VARIANT == "noh2d":
-            exts[p].extract_batch_device(d_sets[i % nsets].data_ptr(), B, W, H, W, W * H)
-        else:
-            exts[p].extract_batch_begin(fr, h_out[p])                          # H2D + kernels + D2H on point slot p's stream
-        kps, desc, n, c = exts[p].device_results()
-        mts[p].match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, d_match_e[p].data_ptr(), d_nmatch_e[p].data_ptr())
-        with torch.cuda.stream(s_p[p]):
-            if gather[0]:
-                pg_e[p].gather(d_match_e[p])
-            h_match[p].copy_(d_match_e[p], non_blocking=True); h_nmatch[p].copy_(d_nmatch_e[p], non_blocking=True)
-        pts_pending[p] = True
-        return u
-
-    def e2e_drain():
-        u = sum(e2e_finalize(r) for r in range(R)) + sum(pts_finalize(p) for p in range(PR))
-        if world > 1:
-            for pg in pg_e:
-                pg.wait()
-        return u
-
-    # units of every distinct input set (untimed): one synchronous pass per set
-    per_set = []
-    for sidx in range(nsets):
-        u = step_e2e(sidx) + e2e_drain()
-        per_set.append(u)
-    nkp_avg = float(np.mean(h_out[(nsets - 1) % PR][2][:Bf]))
     units = units_timed
-    assert units == sum(per_set[(args.warmup + i) % nsets] for i in range(args.steps)), "device count != host count of the same steps"
     t = torch.tensor([ms_total, float(units)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -554,18 +454,6 @@ def main():
         units_all = float(units)
     value = units_all / (ms_total * 1e-3)
 
-    for i in range(args.warmup):
-        step_e2e(i)
-    e2e_drain()
-    barrier()
-    e0.record()
-    eu = 0
-    for i in range(args.steps):
-        eu += step_e2e(args.warmup + i)
-    eu += e2e_drain()
-    e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), 0.0)
     # ---- in-pipeline attribution (rank 0, outside the timed regions): CUPTI kernel intervals of a few steps of the SAME pipelined
     # device loop -> time per kernel per step and the union of GPU-busy time (the serial stage times of `roofline` cannot say
     # how much of a pipelined step is the region walker)
@@ -601,18 +489,9 @@ def main():
                                "how": "torch.profiler (CUPTI) over the pipelined device loop; kernels of different streams overlap, so the sums exceed the wall time"}
         except Exception as e:
             in_pipeline = {"unavailable": repr(e)[:200]}
-    t = torch.tensor([e2e_ms, float(eu)], dtype=torch.float64, device=dev)
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        e2e_ms, eu_all = float(tmax[0]), float(tsum[1])
-    else:
-        eu_all = float(eu)
-    h2d = B * W * H * (2 if LINES else 1)               # each extractor uploads the frames through its own host API call
-    d2h = B * cap * (28 + 32) + B * 4 + Bf * cap * 4 + Bf * 4 + (B * NL * (68 + 32 + 24) + B * 4 + Bf * NL * 4 + Bf * 4 if LINES else 0)
-
     # ---- roofline of the dominant kernel (rank 0): CUDA events between the kernels of one handle ----
     roofline = None
+    nkp_avg = float(dev_i32(ext.device_results()[2], B)[:Bf].float().mean().item())
     if rank == 0:
         gather[0] = False                               # this pass runs on rank 0 only: no collectives
         ext.set_profiling(True)
@@ -674,6 +553,109 @@ def main():
                              "with SURVEY 8(d)'s 17 S bytes per frame" if dom == "lsd_regions" else ""),
                     "stage_gbs": {k: alg.get(k, 0) * B / (acc[k] * 1e-3) / 1e9 for k in acc}}
 
+    # ---- e2e: pinned host frames -> ONE H2D per step -> kernels -> D2H of keypoints, descriptors, lines, counts, match tables ----
+    # Through the frame-level entry point (sslpl_frame_extract_batch_begin: what Frame::Frame does with the two extractors): a ring of
+    # FR frame handles, each with its ORB stream and its line stream fed by one upload, so that the upload of step i+1 overlaps the
+    # kernels of step i and the region walkers of FR steps are in flight together.  Every step's results are read back into pinned
+    # host memory and consumed (counted) on the host inside the timed region.
+    nkp_avg_dev = float(dev_i32(ext.device_results()[2], B)[:Bf].float().mean().item())
+    ext.close(); mt.close()
+    for l in lsr:
+        l.close()
+    for m_ in lmr:
+        m_.close()
+    h_sets = []
+    for s_ in sets:
+        hp = pkg.host_alloc(s_.shape, np.uint8); hp[...] = s_; h_sets.append(hp)
+    FR = max(2, R) if LINES else 2
+    frs = [pkg.Frame(NF, 1.2, 8, 20, 7, NL, max_width=W, max_height=H, max_batch=B, device=local) for _ in range(FR)]
+    mts = [pkg.Matcher(max_features=cap, max_lines=NL, max_nodes=NWORDS, max_batch=B, device=local) for _ in range(FR)]
+    lms = [pkg.Matcher(max_features=64, max_lines=NL, max_nodes=2, max_batch=B, device=local) for _ in range(FR)]
+    so = [torch.cuda.ExternalStream(frs[k].stream(0), device=dev) for k in range(FR)]      # the handles' own ORB / line streams
+    sl = [torch.cuda.ExternalStream(frs[k].stream(1), device=dev) for k in range(FR)]
+    for k in range(FR):
+        mts[k].set_stream(frs[k].stream(0)); lms[k].set_stream(frs[k].stream(1))
+    h_res = [dict(keys=pkg.host_alloc((B, cap), pkg.KEYPOINT_DTYPE), desc=pkg.host_alloc((B, cap, 32), np.uint8), n=pkg.host_alloc((B,), np.int32),
+                  keylines=pkg.host_alloc((B, NL), pkg.KEYLINE_DTYPE), ldesc=pkg.host_alloc((B, NL, 32), np.uint8),
+                  lineeq=pkg.host_alloc((B, NL, 3), np.float64), nl=pkg.host_alloc((B,), np.int32)) for _ in range(FR)]
+    dm = [torch.empty((Bf, cap), dtype=torch.int32, device=dev) for _ in range(FR)]; dnm = [torch.empty((Bf,), dtype=torch.int32, device=dev) for _ in range(FR)]
+    dl = [torch.empty((Bf, NL), dtype=torch.int32, device=dev) for _ in range(FR)]; dnl = [torch.zeros((Bf,), dtype=torch.int32, device=dev) for _ in range(FR)]
+    h_match = [torch.empty((Bf, cap), dtype=torch.int32).pin_memory() for _ in range(FR)]
+    h_nmatch = [torch.empty((Bf,), dtype=torch.int32).pin_memory() for _ in range(FR)]
+    h_lmatch = [torch.empty((Bf, NL), dtype=torch.int32).pin_memory() for _ in range(FR)]
+    h_nlmatch = [torch.zeros((Bf,), dtype=torch.int32).pin_memory() for _ in range(FR)]
+    busy = [False] * FR
+    pg_e = [sbatch.PackedGather(Bf, cap, NL, world, dev) for _ in range(FR)] if world > 1 else [None] * FR
+
+    def e2e_finalize(k):
+        """Host-side completion of ring slot k: both streams of the handle have finished, the results are in pinned host memory."""
+        if not busy[k]:
+            return 0
+        frs[k].sync()                                                          # ORB + line streams, deferred device error checks
+        busy[k] = False
+        u = int(h_res[k]["n"][:Bf].sum()) + int(h_nmatch[k].sum())
+        if LINES:
+            u += int(h_res[k]["nl"][:Bf].sum()) + int(h_nlmatch[k].sum())
+        if world > 1:                                                          # both tables of this step in ONE all-gather, on the gather's own stream
+            with torch.cuda.stream(so[k]):
+                pg_e[k].stage_lines(dl[k]); pg_e[k].gather(dm[k])
+        return u
+
+    def step_e2e(i):
+        k = i % FR
+        u = e2e_finalize(k)
+        if world > 1:
+            with torch.cuda.stream(so[k]):
+                pg_e[k].wait()                                                 # the tables of this slot's previous step have been gathered
+        frs[k].extract_batch_begin(h_sets[i % nsets], h_res[k])                # one H2D, ORB and LSD+LBD on two streams, D2H enqueued
+        kps, desc, n, c = frs[k].orb.device_results()
+        mts[k].match_bow_batch_device(desc, kps, n, B, c, d_voc.data_ptr(), NWORDS, NNRATIO, True, dm[k].data_ptr(), dnm[k].data_ptr())
+        with torch.cuda.stream(so[k]):
+            h_match[k].copy_(dm[k], non_blocking=True); h_nmatch[k].copy_(dnm[k], non_blocking=True)
+        if LINES:
+            _, ldesc, _, nl, capl = frs[k].line.device_results()
+            lms[k].match_lines_batch_device(ldesc, nl, B, capl, dl[k].data_ptr(), dnl[k].data_ptr())
+            with torch.cuda.stream(sl[k]):
+                h_lmatch[k].copy_(dl[k], non_blocking=True); h_nlmatch[k].copy_(dnl[k], non_blocking=True)
+        busy[k] = True
+        return u
+
+    def e2e_drain():
+        u = sum(e2e_finalize(k) for k in range(FR))
+        if world > 1:
+            for pg in pg_e:
+                pg.wait()
+            torch.cuda.synchronize()
+        return u
+
+    # units of every distinct input set (untimed, host count): one synchronous pass per set; must equal the device-side count
+    per_set = []
+    for sidx in range(nsets):
+        per_set.append(step_e2e(sidx) + e2e_drain())
+    assert units_timed == sum(per_set[(args.warmup + i) % nsets] for i in range(args.steps)), "device count != host count of the same steps"
+
+    for i in range(args.warmup):
+        step_e2e(i)
+    e2e_drain()
+    barrier()
+    e0.record()
+    eu = 0
+    for i in range(args.steps):
+        eu += step_e2e(args.warmup + i)
+    eu += e2e_drain()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    t = torch.tensor([e2e_ms, float(eu)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        e2e_ms, eu_all = float(tmax[0]), float(tsum[1])
+    else:
+        eu_all = float(eu)
+    h2d = B * W * H                                     # ONE upload per step (the frame-level entry point feeds both extractors)
+    d2h = B * cap * (28 + 32) + B * 4 + Bf * cap * 4 + Bf * 4 + (B * NL * (68 + 32 + 24) + B * 4 + Bf * NL * 4 + Bf * 4 if LINES else 0)
+
     # ---- CPU baseline on the host cores (rank 0, N=1 only) ----
     cpu = None; cpu_cv2 = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -698,17 +680,25 @@ def main():
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
                 "config": make_config(args, cfg, world, LINES),
-                "run": {"line_ring": R, "l2": f"inputs cycle through {nsets} distinct batches ({nsets * B * W * H / 1e6:.0f} MB > 126 MB L2)",
+                "run": {"line_ring": R, "e2e_frame_handles": FR, "l2": f"inputs cycle through {nsets} distinct batches ({nsets * B * W * H / 1e6:.0f} MB > 126 MB L2)",
                         "units_counted": "on the device inside the timed region"},
                 "e2e": {"value": eu_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_cv2": cpu_cv2,
                 "gather_check": gather_check, "in_pipeline": in_pipeline}
-        print(json.dumps(line))
+        print(json.dumps(line)); sys.stdout.flush()
+    # orderly teardown: the matchers run on the frame handles' streams, so they go first
+    torch.cuda.synchronize()
+    for m_ in mts + lms:
+        m_.close()
+    for f_ in frs:
+        f_.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    rc = main()
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(rc)          # handles are closed in order above; skip interpreter-exit destructors (arbitrary order across CUDA objects)

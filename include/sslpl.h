@@ -322,6 +322,13 @@ int  sslpl_frame_extract_batch(sslpl_frame* h, const uint8_t* imgs, int nframes,
                                int channels, int rgb_order,
                                sslpl_keypoint* kps, sslpl_keypoint* kps_un, uint8_t* desc, int cap, int* nkp,
                                sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int lcap, int* nl);
+/* asynchronous form: enqueue only (pinned host buffers), finish with sslpl_frame_sync */
+int  sslpl_frame_extract_batch_begin(sslpl_frame* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
+                                     int channels, int rgb_order,
+                                     sslpl_keypoint* kps, sslpl_keypoint* kps_un, uint8_t* desc, int cap, int* nkp,
+                                     sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int lcap, int* nl);
+int  sslpl_frame_sync(sslpl_frame* h);
+void* sslpl_frame_stream(sslpl_frame* h, int which /* 0 = ORB stream, 1 = line stream */);
 int  sslpl_frame_device_gray(sslpl_frame* h, const uint8_t** d_gray, int* pitch, size_t* frame_stride);
 
 #ifdef __cplusplus

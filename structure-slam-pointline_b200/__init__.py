@@ -120,8 +120,17 @@ class ORBextractor:
         self.max_batch = max_batch
         self.cap = int(lib().sslpl_orb_max_keypoints(self._h))
 
+    @classmethod
+    def _borrow(cls, ptr, nfeatures, scaleFactor, nlevels, max_batch):
+        """A view of an extractor owned by somebody else (Frame): same methods, never destroyed from here."""
+        self = cls.__new__(cls)
+        self.nfeatures, self.scaleFactor, self.nlevels, self.max_batch = nfeatures, scaleFactor, nlevels, max_batch
+        self._h = C.c_void_p(ptr); self._borrowed = True
+        self.cap = int(lib().sslpl_orb_max_keypoints(self._h))
+        return self
+
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
+        if getattr(self, "_h", None) is not None and self._h.value and not getattr(self, "_borrowed", False):
             lib().sslpl_orb_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -627,9 +636,30 @@ class Frame:
         lib().sslpl_frame_create.argtypes = [C.c_void_p, C.c_void_p]
         _check(lib().sslpl_frame_create(C.byref(p), C.byref(self._h)))
         lib().sslpl_frame_orb.restype = C.c_void_p; lib().sslpl_frame_orb.argtypes = [C.c_void_p]
-        self.cap = int(lib().sslpl_orb_max_keypoints(C.c_void_p(lib().sslpl_frame_orb(self._h))))
+        lib().sslpl_frame_line.restype = C.c_void_p; lib().sslpl_frame_line.argtypes = [C.c_void_p]
+        lib().sslpl_frame_stream.restype = C.c_void_p; lib().sslpl_frame_stream.argtypes = [C.c_void_p, C.c_int]
+        self.orb = ORBextractor._borrow(lib().sslpl_frame_orb(self._h), nfeatures, scaleFactor, nlevels, max_batch)
+        self.line = LineSegment._borrow(lib().sslpl_frame_line(self._h), lsdNFeatures, max_batch)
+        self.cap = self.orb.cap
         self.lcap = lsdNFeatures
         self.max_batch = max_batch
+
+    def stream(self, which):
+        """CUDA stream handle of the ORB (0) or line (1) side."""
+        return int(lib().sslpl_frame_stream(self._h, int(which)))
+
+    def extract_batch_begin(self, frames, out):
+        """Asynchronous: frames [B, H, W] uint8 in pinned memory (host_alloc); out = dict(keys, desc, n, keylines, ldesc, lineeq, nl) of
+        pinned arrays with the handle's capacities.  Finish with sync()."""
+        B, h, w = frames.shape[:3]
+        cn = 1 if frames.ndim == 3 else frames.shape[3]
+        assert out["keys"].shape[1] == self.cap and out["keylines"].shape[1] == self.lcap
+        _check(lib().sslpl_frame_extract_batch_begin(self._h, _p(frames), B, w, h, frames.strides[1], C.c_size_t(frames.strides[0]), cn, 0,
+                                                     _p(out["keys"]), None, _p(out["desc"]), self.cap, _p(out["n"]),
+                                                     _p(out["keylines"]), _p(out["ldesc"]), _p(out["lineeq"]), self.lcap, _p(out["nl"])))
+
+    def sync(self):
+        _check(lib().sslpl_frame_sync(self._h))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -694,8 +724,14 @@ class LineSegment:
         self.cap = lsdNFeatures
         self.max_batch = max_batch
 
+    @classmethod
+    def _borrow(cls, ptr, lsdNFeatures, max_batch):
+        self = cls.__new__(cls)
+        self._h = C.c_void_p(ptr); self._borrowed = True; self.cap = lsdNFeatures; self.max_batch = max_batch
+        return self
+
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
+        if getattr(self, "_h", None) is not None and self._h.value and not getattr(self, "_borrowed", False):
             lib().sslpl_line_destroy(self._h)
             self._h = C.c_void_p()
 

@@ -112,6 +112,7 @@ void sslpl_frame_destroy(sslpl_frame* h) {
     delete h;
 }
 
+void* sslpl_frame_stream(sslpl_frame* h, int which) { return h ? (which ? (void*)h->s_line : (void*)h->s_orb) : nullptr; }
 sslpl_orb* sslpl_frame_orb(sslpl_frame* h) { return h ? h->orb : nullptr; }
 sslpl_line* sslpl_frame_line(sslpl_frame* h) { return h ? h->line : nullptr; }
 long long sslpl_frame_launch_count(const sslpl_frame* h) { return h ? h->launches + sslpl_orb_launch_count(h->orb) + sslpl_line_launch_count(h->line) : 0; }
@@ -147,10 +148,12 @@ int sslpl_frame_image_bounds(sslpl_frame* h, int cols, int rows, float* bounds4)
     return SSLPL_OK;
 }
 
-int sslpl_frame_extract_batch(sslpl_frame* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
-                              int channels, int rgb_order,
-                              sslpl_keypoint* kps, sslpl_keypoint* kps_un, uint8_t* desc, int cap, int* nkp,
-                              sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int lcap, int* nl) {
+/* enqueue only: the upload, both extractions and the result copies; finish with sslpl_frame_sync.  With pinned host buffers
+   (sslpl_host_alloc) nothing here waits for the device, so consecutive calls on different handles overlap. */
+int sslpl_frame_extract_batch_begin(sslpl_frame* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
+                                    int channels, int rgb_order,
+                                    sslpl_keypoint* kps, sslpl_keypoint* kps_un, uint8_t* desc, int cap, int* nkp,
+                                    sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int lcap, int* nl) {
     SSLPL_REQUIRE(h && imgs && nkp && nl, SSLPL_ERR_ARG, "null argument");
     SSLPL_REQUIRE(nframes >= 1 && nframes <= h->p.orb.max_batch, SSLPL_ERR_ARG, "nframes exceeds max_batch");
     SSLPL_REQUIRE(width >= 16 && height >= 16 && width <= h->p.orb.max_width && height <= h->p.orb.max_height, SSLPL_ERR_ARG, "frame size out of range");
@@ -163,7 +166,9 @@ int sslpl_frame_extract_batch(sslpl_frame* h, const uint8_t* imgs, int nframes, 
     h->last_pitch = gp; h->last_stride = gs;
     // ---- one upload
     if (channels == 1) {
-        for (int f = 0; f < nframes; f++)
+        if (nframes == 1 || frame_stride == (size_t)pitch * height)      // contiguous frames: one 2-D copy over all rows
+            SSLPL_CUDA(cudaMemcpy2DAsync(h->d_gray, gp, imgs, pitch, width, (size_t)height * nframes, cudaMemcpyHostToDevice, h->s_orb));
+        else for (int f = 0; f < nframes; f++)
             SSLPL_CUDA(cudaMemcpy2DAsync(h->d_gray + f * gs, gp, imgs + f * frame_stride, pitch, width, height, cudaMemcpyHostToDevice, h->s_orb));
     } else {
         const size_t rowb = (size_t)width * channels, need = rowb * height * nframes;
@@ -195,7 +200,11 @@ int sslpl_frame_extract_batch(sslpl_frame* h, const uint8_t* imgs, int nframes, 
     }
     // ---- results
     SSLPL_CUDA(cudaMemcpyAsync(nkp, d_n, sizeof(int) * nframes, cudaMemcpyDeviceToHost, h->s_orb));
-    for (int f = 0; f < nframes; f++) {
+    if (cap == c2) {                                                     // same stride on both sides: one copy per array
+        if (kps) SSLPL_CUDA(cudaMemcpyAsync(kps, d_kps, sizeof(sslpl_keypoint) * (size_t)c2 * nframes, cudaMemcpyDeviceToHost, h->s_orb));
+        if (kps_un) SSLPL_CUDA(cudaMemcpyAsync(kps_un, h->d_un, sizeof(sslpl_keypoint) * (size_t)c2 * nframes, cudaMemcpyDeviceToHost, h->s_orb));
+        if (desc) SSLPL_CUDA(cudaMemcpyAsync(desc, d_desc, (size_t)c2 * 32 * nframes, cudaMemcpyDeviceToHost, h->s_orb));
+    } else for (int f = 0; f < nframes; f++) {
         if (kps) SSLPL_CUDA(cudaMemcpyAsync(kps + (size_t)f * cap, d_kps + (size_t)f * c2, sizeof(sslpl_keypoint) * c2, cudaMemcpyDeviceToHost, h->s_orb));
         if (kps_un) SSLPL_CUDA(cudaMemcpyAsync(kps_un + (size_t)f * cap, h->d_un + (size_t)f * c2, sizeof(sslpl_keypoint) * c2, cudaMemcpyDeviceToHost, h->s_orb));
         if (desc) SSLPL_CUDA(cudaMemcpyAsync(desc + (size_t)f * cap * 32, d_desc + (size_t)f * c2 * 32, (size_t)c2 * 32, cudaMemcpyDeviceToHost, h->s_orb));
@@ -204,14 +213,32 @@ int sslpl_frame_extract_batch(sslpl_frame* h, const uint8_t* imgs, int nframes, 
     rc = sslpl_line_device_results(h->line, &d_kl, &d_ld, &d_eq, &d_nl, &cl);
     if (rc != SSLPL_OK) return rc;
     SSLPL_CUDA(cudaMemcpyAsync(nl, d_nl, sizeof(int) * nframes, cudaMemcpyDeviceToHost, h->s_line));
-    for (int f = 0; f < nframes; f++) {
+    if (lcap == cl) {
+        if (kl) SSLPL_CUDA(cudaMemcpyAsync(kl, d_kl, sizeof(sslpl_keyline) * (size_t)cl * nframes, cudaMemcpyDeviceToHost, h->s_line));
+        if (ldesc) SSLPL_CUDA(cudaMemcpyAsync(ldesc, d_ld, (size_t)cl * 32 * nframes, cudaMemcpyDeviceToHost, h->s_line));
+        if (lineeq) SSLPL_CUDA(cudaMemcpyAsync(lineeq, d_eq, sizeof(double) * 3 * (size_t)cl * nframes, cudaMemcpyDeviceToHost, h->s_line));
+    } else for (int f = 0; f < nframes; f++) {
         if (kl) SSLPL_CUDA(cudaMemcpyAsync(kl + (size_t)f * lcap, d_kl + (size_t)f * cl, sizeof(sslpl_keyline) * cl, cudaMemcpyDeviceToHost, h->s_line));
         if (ldesc) SSLPL_CUDA(cudaMemcpyAsync(ldesc + (size_t)f * lcap * 32, d_ld + (size_t)f * cl * 32, (size_t)cl * 32, cudaMemcpyDeviceToHost, h->s_line));
         if (lineeq) SSLPL_CUDA(cudaMemcpyAsync(lineeq + (size_t)f * lcap * 3, d_eq + (size_t)f * cl * 3, sizeof(double) * 3 * cl, cudaMemcpyDeviceToHost, h->s_line));
     }
-    rc = sslpl_orb_sync(h->orb);
+    return SSLPL_OK;
+}
+
+int sslpl_frame_sync(sslpl_frame* h) {
+    SSLPL_REQUIRE(h, SSLPL_ERR_ARG, "null handle");
+    const int rc = sslpl_orb_sync(h->orb);
     const int rc2 = sslpl_line_sync(h->line);
     return rc != SSLPL_OK ? rc : rc2;
+}
+
+int sslpl_frame_extract_batch(sslpl_frame* h, const uint8_t* imgs, int nframes, int width, int height, int pitch, size_t frame_stride,
+                              int channels, int rgb_order,
+                              sslpl_keypoint* kps, sslpl_keypoint* kps_un, uint8_t* desc, int cap, int* nkp,
+                              sslpl_keyline* kl, uint8_t* ldesc, double* lineeq, int lcap, int* nl) {
+    const int rc = sslpl_frame_extract_batch_begin(h, imgs, nframes, width, height, pitch, frame_stride, channels, rgb_order, kps, kps_un, desc, cap, nkp,
+                                                   kl, ldesc, lineeq, lcap, nl);
+    return rc != SSLPL_OK ? rc : sslpl_frame_sync(h);
 }
 
 int sslpl_frame_extract(sslpl_frame* h, const uint8_t* img, int width, int height, int pitch, int channels, int rgb_order,
