@@ -523,8 +523,7 @@ def main():
             ncand += len(ext.candidates(l, frame=0)[0])
         alg = {   # algorithmic bytes per frame, SURVEY.md 8(d) byte table
             "pyramid": 2 * P - W * H - ext.level_size(7)[0] * ext.level_size(7)[1],
-            "fast_score": P + 5 * ncand,        # the FAST+NMS stage figure (read P, write 5C) is charged to the score kernel
-            "fast_cells": P + 5 * ncand,        # reads the u8 score plane (P) and writes the candidates
+            "fast": P + 5 * ncand,              # the FAST+NMS stage figure: read the pyramid once, write the candidates
             "blur": 2 * P,
             "orient_desc": (749 + 512 + 32 + 28 + 4) * nkp_avg,
             "octree": 8 * ncand,
@@ -559,11 +558,12 @@ def main():
     # kernels of step i and the region walkers of FR steps are in flight together.  Every step's results are read back into pinned
     # host memory and consumed (counted) on the host inside the timed region.
     nkp_avg_dev = float(dev_i32(ext.device_results()[2], B)[:Bf].float().mean().item())
-    ext.close(); mt.close()
+    mt.close()
+    for m_ in lmr:                # matchers first: they run on the extractors' streams
+        m_.close()
+    ext.close()
     for l in lsr:
         l.close()
-    for m_ in lmr:
-        m_.close()
     h_sets = []
     for s_ in sets:
         hp = pkg.host_alloc(s_.shape, np.uint8); hp[...] = s_; h_sets.append(hp)
@@ -695,10 +695,14 @@ def main():
         f_.close()
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    # leave here: the tensors of this frame alias device memory of the handles closed above, and their destructors (run on return)
+    # were seen to fault inside torch at interpreter exit; everything has been printed, synchronised and closed in order
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
+    import faulthandler; faulthandler.enable()
     rc = main()
     sys.stdout.flush(); sys.stderr.flush()
     os._exit(rc)          # handles are closed in order above; skip interpreter-exit destructors (arbitrary order across CUDA objects)

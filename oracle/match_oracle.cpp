@@ -584,3 +584,240 @@ extern "C" int orc_line_match(int mode, const uint8_t* d1, int n1, const uint8_t
     if (nout) *nout = k;
     return nmatches;
 }
+
+/* ================================================================================================================
+ * line projection matchers and Fuse.  Each reference function is split where the product splits it:
+ * a projection stage (per map element: gates + projected quantities; host arithmetic in the reference's own Mat types)
+ * and a search stage (Hamming scan over the frame's features; the device part).  orc_*_project restate the first,
+ * orc_line_window_search / orc_fuse_*_search the second; tests/test_ref_parity_cpu.py composes them against the reference.
+ * ================================================================================================================ */
+namespace {
+/* Rcw * X + tcw through cv::gemm's float path (3x3 * 3x1 + 3x1: products summed left to right, addend last) */
+inline void rt_apply(const float* T, const float* X, float* out) {
+    for (int r = 0; r < 3; r++) {
+        float s = T[4 * r] * X[0]; s = s + T[4 * r + 1] * X[1]; s = s + T[4 * r + 2] * X[2];
+        out[r] = s + T[4 * r + 3];
+    }
+}
+/* Frame::GetLinesInArea (Frame.cc:423-460) = KeyFrame::GetLinesInArea (KeyFrame.cc:651-684), one line */
+inline bool line_in_area(float x1, float y1, float x2, float y2, float r, int minLevel, int maxLevel, float ptx, float pty, float angle, int octave) {
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel > 0);
+    const float distance = (0.5 * (x1 + x2) - ptx) * (0.5 * (x1 + x2) - ptx) + (0.5 * (y1 + y2) - pty) * (0.5 * (y1 + y2) - pty);
+    if (distance > r * r) return false;
+    const float slope = (y1 - y2) / (x1 - x2) - angle;
+    if (slope > r * 0.01) return false;
+    if (bCheckLevels) {
+        if (octave < minLevel) return false;
+        if (maxLevel >= 0 && octave > maxLevel) return false;
+    }
+    return true;
+}
+}  // namespace
+
+/* Projection stage of LSDmatcher::SearchByProjection(Frame& Current, const Frame& Last, th, bMono) — LSDmatcher.cpp:22-96.
+ * valid1[i]: pML && !pML->isBad() && !mvbLineOutlier[i]; Pw: GetWorldPos() narrowed to float as the Mat_<float> initialisers do (:48-49);
+ * oct1[i] = LastFrame.mvKeys[i].octave (:84 reads the POINT keypoint of the same index).  Out: active, proj (x1 y1 x2 y2),
+ * radius, minLevel, maxLevel per line. */
+extern "C" void orc_line_project_frame(int nl1, const uint8_t* valid1, const float* Pw, const int32_t* oct1,
+                                       const float* Tcw, const float* Tlw, const float* cam /* fx fy cx cy mb */, const float* bounds,
+                                       const float* scaleFactors, float th, int bMono,
+                                       uint8_t* active, float* proj, float* radius, int32_t* minLevel, int32_t* maxLevel) {
+    const float fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3], mb = cam[4];
+    double twc[3];                                              /* twc = -Rcw.t()*tcw: transposed operand, double accumulation */
+    for (int r = 0; r < 3; r++) twc[r] = -((double)Tcw[0 * 4 + r] * Tcw[3] + (double)Tcw[1 * 4 + r] * Tcw[7] + (double)Tcw[2 * 4 + r] * Tcw[11]);
+    const float twcf[3] = {(float)twc[0], (float)twc[1], (float)twc[2]};
+    float tlc[3]; rt_apply(Tlw, twcf, tlc);
+    const bool bForward = tlc[2] > mb && !bMono, bBackward = -tlc[2] > mb && !bMono;
+    for (int i = 0; i < nl1; i++) {
+        active[i] = 0; radius[i] = 0; minLevel[i] = maxLevel[i] = -1;
+        for (int k = 0; k < 4; k++) proj[4 * i + k] = 0;
+        if (!valid1[i]) continue;
+        float SPc[3], EPc[3];
+        rt_apply(Tcw, Pw + 6 * (size_t)i, SPc); rt_apply(Tcw, Pw + 6 * (size_t)i + 3, EPc);
+        if (SPc[2] < 0.0f || EPc[2] < 0.0f) continue;
+        const float invz1 = 1.0f / SPc[2];
+        const float u1 = fx * SPc[0] * invz1 + cx, v1 = fy * SPc[1] * invz1 + cy;
+        if (u1 < bounds[0] || u1 > bounds[1]) continue;
+        if (v1 < bounds[2] || v1 > bounds[3]) continue;
+        const float invz2 = 1.0f / EPc[2];
+        const float u2 = fx * EPc[0] * invz2 + cx, v2 = fy * EPc[1] * invz2 + cy;
+        if (u2 < bounds[0] || u2 > bounds[1]) continue;
+        if (v2 < bounds[2] || v2 > bounds[3]) continue;
+        const int o = oct1[i];
+        active[i] = 1; proj[4 * i] = u1; proj[4 * i + 1] = v1; proj[4 * i + 2] = u2; proj[4 * i + 3] = v2;
+        radius[i] = th * scaleFactors[o];
+        if (bForward) { minLevel[i] = o; maxLevel[i] = -1; }
+        else if (bBackward) { minLevel[i] = 0; maxLevel[i] = o; }
+        else { minLevel[i] = o - 1; maxLevel[i] = o + 1; }
+    }
+}
+
+/* Projection stage of LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, th) — LSDmatcher.cpp:185-208: the fields
+ * Frame::isInFrustum left on the MapLine (mbTrackInView, mnTrackScaleLevel, mTrackViewCos) become radius and level range. */
+extern "C" void orc_line_project_mls(int nml, const uint8_t* inview, const uint8_t* bad, const int32_t* level, const float* viewcos,
+                                     const float* scaleFactors, float th, uint8_t* active, float* radius, int32_t* minLevel, int32_t* maxLevel) {
+    const bool bFactor = th != 1.0;
+    for (int i = 0; i < nml; i++) {
+        active[i] = inview[i] && !(bad && bad[i]);
+        float r = viewcos[i] > 0.998 ? 5.0f : 8.0f;             /* RadiusByViewingCos :550-556 */
+        if (bFactor) r *= th;
+        radius[i] = active[i] ? r * scaleFactors[level[i]] : 0.f;
+        minLevel[i] = level[i] - 1; maxLevel[i] = level[i];
+    }
+}
+
+/* Search stage shared by both line SearchByProjection overloads (LSDmatcher.cpp:98-137 = :210-251).  kl2: pt.x, pt.y, angle of
+ * mvKeylinesUn; oct2 their octave; held2[j]: 1 = the frame line holds a MapLine WITH observations (skipped), otherwise free;
+ * obs[i]: the MapLine has observations (so a line it is written to is skipped by later MapLines).  assign2[j] = last writer. */
+extern "C" int orc_line_window_search(int nml, const uint8_t* active, const uint8_t* obs, const float* proj, const float* radius,
+                                      const int32_t* minLevel, const int32_t* maxLevel, const uint8_t* dml,
+                                      int nl2, const uint8_t* ld2, const float* kl2, const int32_t* oct2, const uint8_t* held2,
+                                      float nnratio, int32_t* assign2) {
+    std::vector<uint8_t> claimed(nl2, 0);
+    for (int j = 0; j < nl2; j++) { assign2[j] = -1; claimed[j] = held2 && held2[j] == 1; }
+    int nmatches = 0;
+    for (int i = 0; i < nml; i++) {
+        if (!active[i]) continue;
+        const float* p = proj + 4 * (size_t)i;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx = 0; idx < nl2; idx++) {
+            if (!line_in_area(p[0], p[1], p[2], p[3], radius[i], minLevel[i], maxLevel[i], kl2[3 * idx], kl2[3 * idx + 1], kl2[3 * idx + 2], oct2[idx])) continue;
+            if (claimed[idx]) continue;
+            const int dist = orc_descriptor_distance(dml + 32 * (size_t)i, ld2 + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct2[idx]; bestIdx = idx; }
+            else if (dist < bestDist2) { bestLevel2 = oct2[idx]; bestDist2 = dist; }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2) continue;
+            assign2[bestIdx] = i; claimed[bestIdx] = obs && obs[i];
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+/* Projection stage of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) — ORBmatcher.cc:828-894.  skip[i]: !pMP || isBad() ||
+ * IsInKeyFrame(pKF); minInv/maxInv: Get{Min,Max}DistanceInvariance(); maxRaw: mfMaxDistance (PredictScale, MapPoint.cc:390-405,
+ * logf through `using namespace std`).  cam: fx fy cx cy bf. */
+extern "C" void orc_fuse_project_points(int nmp, const uint8_t* skip, const float* Xw, const float* normal, const float* minInv, const float* maxInv,
+                                        const float* maxRaw, const float* Tcw, const float* Ow, const float* cam, const float* bounds,
+                                        int nlevels, float logScaleFactor, uint8_t* active, float* u, float* v, float* ur, int32_t* level) {
+    const float fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3], bf = cam[4];
+    for (int i = 0; i < nmp; i++) {
+        active[i] = 0; u[i] = v[i] = ur[i] = 0; level[i] = 0;
+        if (skip[i]) continue;
+        const float* X = Xw + 3 * (size_t)i;
+        float pc[3]; rt_apply(Tcw, X, pc);
+        if (pc[2] < 0.0f) continue;
+        const float invz = 1 / pc[2];
+        const float x = pc[0] * invz, y = pc[1] * invz;
+        const float uu = fx * x + cx, vv = fy * y + cy;
+        if (!(uu >= bounds[0] && uu < bounds[1] && vv >= bounds[2] && vv < bounds[3])) continue;      /* KeyFrame::IsInImage KeyFrame.cc:686-689 */
+        const float PO[3] = {X[0] - Ow[0], X[1] - Ow[1], X[2] - Ow[2]};
+        const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);   /* cv::norm: double accumulation */
+        if (dist3D < minInv[i] || dist3D > maxInv[i]) continue;
+        const float* Pn = normal + 3 * (size_t)i;
+        const double dot = (double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2];          /* Mat::dot: double accumulation */
+        if (dot < 0.5 * dist3D) continue;
+        const float ratio = maxRaw[i] / dist3D;
+        int nScale = (int)std::ceil(logf(ratio) / logScaleFactor);
+        if (nScale < 0) nScale = 0; else if (nScale >= nlevels) nScale = nlevels - 1;
+        active[i] = 1; u[i] = uu; v[i] = vv; ur[i] = uu - bf * invz; level[i] = nScale;
+    }
+}
+
+/* Search stage of ORBmatcher::Fuse — ORBmatcher.cc:896-950: best_idx[i] = nearest KeyFrame feature in the window (first in
+ * GetFeaturesInArea order on ties) or -1, best_dist[i] its distance (256 when none).  The caller fuses when best_dist <= TH_LOW. */
+extern "C" void orc_fuse_points_search(int nmp, const uint8_t* active, const float* u, const float* v, const float* ur, const int32_t* level, const uint8_t* dmp,
+                                       int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* uright2,
+                                       const float* bounds, const float* scaleFactors, const float* invLevelSigma2, float th,
+                                       int32_t* best_idx, int32_t* best_dist) {
+    Grid* g = new Grid();
+    g->minX = bounds[0]; g->minY = bounds[2];
+    g->invW = (float)Grid::COLS / (bounds[1] - bounds[0]); g->invH = (float)Grid::ROWS / (bounds[3] - bounds[2]);
+    g->build(n2, x2, y2);
+    std::vector<int> cand;
+    for (int i = 0; i < nmp; i++) {
+        best_idx[i] = -1; best_dist[i] = 256;
+        if (!active[i]) continue;
+        const int nPredictedLevel = level[i];
+        const float radius = th * scaleFactors[nPredictedLevel];
+        g->area(u[i], v[i], radius, -1, -1, x2, y2, oct2, cand);                         /* KeyFrame::GetFeaturesInArea KeyFrame.cc:610-649: no level test */
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            const int kpLevel = oct2[idx];
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            if (uright2 && uright2[idx] >= 0) {
+                const float ex = u[i] - x2[idx], ey = v[i] - y2[idx], er = ur[i] - uright2[idx];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * invLevelSigma2[kpLevel] > 7.8) continue;
+            } else {
+                const float ex = u[i] - x2[idx], ey = v[i] - y2[idx];
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * invLevelSigma2[kpLevel] > 5.99) continue;
+            }
+            const int dist = orc_descriptor_distance(dmp + 32 * (size_t)i, d2 + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        best_idx[i] = bestIdx; best_dist[i] = bestDist;
+    }
+    delete g;
+}
+
+/* Projection stage of LSDmatcher::Fuse — LSDmatcher.cpp:417-497.  skip[i]: !pML || isBad(); Pw as in orc_line_project_frame;
+ * normal: GetNormal() narrowed to float (:489); maxRaw: mfMaxDistance of MapLine::PredictScale (MapLine.cpp:386-395, NOT clamped:
+ * a level outside [0, nlevels) makes the reference read mvScaleFactors out of bounds, here the line is dropped and level keeps the value). */
+extern "C" void orc_fuse_project_lines(int nml, const uint8_t* skip, const float* Pw, const float* normal, const float* minInv, const float* maxInv,
+                                       const float* maxRaw, const float* Tcw, const float* Ow, const float* cam, const float* bounds,
+                                       int nlevels, float logScaleFactor, uint8_t* active, float* proj, int32_t* level) {
+    const float fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+    for (int i = 0; i < nml; i++) {
+        active[i] = 0; level[i] = 0;
+        for (int k = 0; k < 4; k++) proj[4 * i + k] = 0;
+        if (skip[i]) continue;
+        const float* SP = Pw + 6 * (size_t)i; const float* EP = SP + 3;
+        float SPc[3], EPc[3];
+        rt_apply(Tcw, SP, SPc); rt_apply(Tcw, EP, EPc);
+        if (SPc[2] < 0.0f || EPc[2] < 0.0f) continue;
+        const float invz1 = 1.0f / SPc[2];
+        const float u1 = fx * SPc[0] * invz1 + cx, v1 = fy * SPc[1] * invz1 + cy;
+        if (u1 < bounds[0] || u1 > bounds[1]) continue;
+        if (v1 < bounds[2] || v1 > bounds[3]) continue;
+        const float invz2 = 1.0f / EPc[2];
+        const float u2 = fx * EPc[0] * invz2 + cx, v2 = fy * EPc[1] * invz2 + cy;
+        if (u2 < bounds[0] || u2 > bounds[1]) continue;
+        if (v2 < bounds[2] || v2 > bounds[3]) continue;
+        float OM[3];
+        for (int k = 0; k < 3; k++) OM[k] = 0.5f * (SP[k] + EP[k]) - Ow[k];               /* 0.5*(SP+EP) - Ow: float, halving is exact */
+        const float dist = (float)std::sqrt((double)OM[0] * OM[0] + (double)OM[1] * OM[1] + (double)OM[2] * OM[2]);
+        if (dist < minInv[i] || dist > maxInv[i]) continue;
+        const float* pn = normal + 3 * (size_t)i;
+        const double dot = (double)OM[0] * pn[0] + (double)OM[1] * pn[1] + (double)OM[2] * pn[2];
+        if (dot < 0.5 * dist) continue;
+        const float ratio = maxRaw[i] / dist;
+        const int lvl = (int)std::ceil(logf(ratio) / logScaleFactor);
+        level[i] = lvl;
+        if (lvl < 0 || lvl >= nlevels) continue;
+        active[i] = 1; proj[4 * i] = u1; proj[4 * i + 1] = v1; proj[4 * i + 2] = u2; proj[4 * i + 3] = v2;
+    }
+}
+
+/* Search stage of LSDmatcher::Fuse — LSDmatcher.cpp:499-523: oct2 = mvKeyLines[idx].octave; best_dist INT_MAX when nothing qualified */
+extern "C" void orc_fuse_lines_search(int nml, const uint8_t* active, const float* proj, const int32_t* level, const uint8_t* dml,
+                                      int nl2, const uint8_t* ld2, const float* kl2, const int32_t* oct2, const float* scaleFactors, float th,
+                                      int32_t* best_idx, int32_t* best_dist) {
+    for (int i = 0; i < nml; i++) {
+        best_idx[i] = -1; best_dist[i] = 0x7fffffff;
+        if (!active[i]) continue;
+        const float* p = proj + 4 * (size_t)i;
+        const int nPredictedLevel = level[i];
+        const float radius = th * scaleFactors[nPredictedLevel];
+        for (int idx = 0; idx < nl2; idx++) {
+            if (!line_in_area(p[0], p[1], p[2], p[3], radius, -1, -1, kl2[3 * idx], kl2[3 * idx + 1], kl2[3 * idx + 2], oct2[idx])) continue;
+            const int klLevel = oct2[idx];
+            if (klLevel < nPredictedLevel - 1 || klLevel > nPredictedLevel) continue;
+            const int dist = orc_descriptor_distance(dml + 32 * (size_t)i, ld2 + 32 * (size_t)idx);
+            if (dist < best_dist[i]) { best_dist[i] = dist; best_idx[i] = idx; }
+        }
+    }
+}

@@ -102,6 +102,28 @@ int   orc_search_by_projection_mps(int nmp, const uint8_t* inview, const uint8_t
 int   orc_search_for_initialization(int n1, const uint8_t* d1, const int32_t* oct1, const float* angle1,
                                     int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* angle2,
                                     float* prev, const float* bounds, float nnratio, int checkOri, int windowSize, int32_t* matches12);
+/* line projection matchers (LSDmatcher.cpp:22-141, :185-255) and Fuse (ORBmatcher.cc:828-973, LSDmatcher.cpp:417-548),
+   each split into its projection stage and its search stage (see match_oracle.cpp) */
+void  orc_line_project_frame(int nl1, const uint8_t* valid1, const float* Pw, const int32_t* oct1, const float* Tcw, const float* Tlw,
+                             const float* cam, const float* bounds, const float* scaleFactors, float th, int bMono,
+                             uint8_t* active, float* proj, float* radius, int32_t* minLevel, int32_t* maxLevel);
+void  orc_line_project_mls(int nml, const uint8_t* inview, const uint8_t* bad, const int32_t* level, const float* viewcos,
+                           const float* scaleFactors, float th, uint8_t* active, float* radius, int32_t* minLevel, int32_t* maxLevel);
+int   orc_line_window_search(int nml, const uint8_t* active, const uint8_t* obs, const float* proj, const float* radius,
+                             const int32_t* minLevel, const int32_t* maxLevel, const uint8_t* dml,
+                             int nl2, const uint8_t* ld2, const float* kl2, const int32_t* oct2, const uint8_t* held2, float nnratio, int32_t* assign2);
+void  orc_fuse_project_points(int nmp, const uint8_t* skip, const float* Xw, const float* normal, const float* minInv, const float* maxInv,
+                              const float* maxRaw, const float* Tcw, const float* Ow, const float* cam, const float* bounds,
+                              int nlevels, float logScaleFactor, uint8_t* active, float* u, float* v, float* ur, int32_t* level);
+void  orc_fuse_points_search(int nmp, const uint8_t* active, const float* u, const float* v, const float* ur, const int32_t* level, const uint8_t* dmp,
+                             int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* uright2,
+                             const float* bounds, const float* scaleFactors, const float* invLevelSigma2, float th, int32_t* best_idx, int32_t* best_dist);
+void  orc_fuse_project_lines(int nml, const uint8_t* skip, const float* Pw, const float* normal, const float* minInv, const float* maxInv,
+                             const float* maxRaw, const float* Tcw, const float* Ow, const float* cam, const float* bounds,
+                             int nlevels, float logScaleFactor, uint8_t* active, float* proj, int32_t* level);
+void  orc_fuse_lines_search(int nml, const uint8_t* active, const float* proj, const int32_t* level, const uint8_t* dml,
+                            int nl2, const uint8_t* ld2, const float* kl2, const int32_t* oct2, const float* scaleFactors, float th,
+                            int32_t* best_idx, int32_t* best_dist);
 /* Frame::lineDescriptorMAD Frame.cc:190-215 on a knn2 table */
 void  orc_line_mad(const int32_t* knn, int nq, double* nn_mad, double* nn12_mad);
 /* LSDmatcher knn-based entry points. mode: 0 = SearchByProjection(KF,F)/SearchByDescriptor(KF,F) (ratio),

@@ -272,6 +272,86 @@ def search_for_initialization(d1, k1, d2, k2, prev, bounds, nnratio=0.9, check_o
     return n, m12[:len(k1)], prev
 
 
+def _u8(a):
+    return np.ascontiguousarray(a, np.uint8)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, np.int32)
+
+
+def line_project_frame(valid1, Pw, oct1, Tcw, Tlw, cam5, bounds, scale_factors, th, mono=True):
+    """Projection stage of LSDmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (LSDmatcher.cpp:22-96)
+    -> dict(active, proj[n,4], radius, min_level, max_level)."""
+    n = len(valid1)
+    out = dict(active=np.zeros(n, np.uint8), proj=np.zeros((n, 4), np.float32), radius=np.zeros(n, np.float32),
+               min_level=np.zeros(n, np.int32), max_level=np.zeros(n, np.int32))
+    lib().orc_line_project_frame(n, _p(_u8(valid1)), _p(_f32(Pw)), _p(_i32(oct1)), _p(_f32(Tcw)), _p(_f32(Tlw)), _p(_f32(cam5)), _p(_f32(bounds)),
+                                 _p(_f32(scale_factors)), C.c_float(th), int(mono), _p(out["active"]), _p(out["proj"]), _p(out["radius"]),
+                                 _p(out["min_level"]), _p(out["max_level"]))
+    return out
+
+
+def line_project_mls(inview, bad, level, viewcos, scale_factors, th=1.0):
+    """Projection stage of LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, th) (LSDmatcher.cpp:185-208)."""
+    n = len(inview)
+    out = dict(active=np.zeros(n, np.uint8), radius=np.zeros(n, np.float32), min_level=np.zeros(n, np.int32), max_level=np.zeros(n, np.int32))
+    lib().orc_line_project_mls(n, _p(_u8(inview)), _p(_u8(bad)), _p(_i32(level)), _p(_f32(viewcos)), _p(_f32(scale_factors)), C.c_float(th),
+                               _p(out["active"]), _p(out["radius"]), _p(out["min_level"]), _p(out["max_level"]))
+    return out
+
+
+def line_window_search(q, obs, dml, ld2, kl2, oct2, held2=None, nnratio=0.8):
+    """Search stage of both line SearchByProjection overloads (LSDmatcher.cpp:98-137, :210-251).  q = dict(active, proj, radius,
+    min_level, max_level); kl2[n,3] = pt.x, pt.y, angle -> (nmatches, assign2)."""
+    nml = len(q["active"]); nl2 = len(oct2)
+    out = np.full(max(nl2, 1), -1, np.int32)
+    lib().orc_line_window_search.restype = C.c_int
+    n = lib().orc_line_window_search(nml, _p(_u8(q["active"])), _p(_u8(obs)), _p(_f32(q["proj"])), _p(_f32(q["radius"])), _p(_i32(q["min_level"])),
+                                     _p(_i32(q["max_level"])), _p(_u8(dml)), nl2, _p(_u8(ld2)), _p(_f32(kl2)), _p(_i32(oct2)),
+                                     _p(_u8(held2)) if held2 is not None else None, C.c_float(nnratio), _p(out))
+    return n, out[:nl2]
+
+
+def fuse_project_points(skip, Xw, normal, min_inv, max_inv, max_raw, Tcw, Ow, cam5, bounds, nlevels, log_scale_factor):
+    """Projection stage of ORBmatcher::Fuse (ORBmatcher.cc:828-894) -> dict(active, u, v, ur, level)."""
+    n = len(skip)
+    out = dict(active=np.zeros(n, np.uint8), u=np.zeros(n, np.float32), v=np.zeros(n, np.float32), ur=np.zeros(n, np.float32), level=np.zeros(n, np.int32))
+    lib().orc_fuse_project_points(n, _p(_u8(skip)), _p(_f32(Xw)), _p(_f32(normal)), _p(_f32(min_inv)), _p(_f32(max_inv)), _p(_f32(max_raw)),
+                                  _p(_f32(Tcw)), _p(_f32(Ow)), _p(_f32(cam5)), _p(_f32(bounds)), int(nlevels), C.c_float(log_scale_factor),
+                                  _p(out["active"]), _p(out["u"]), _p(out["v"]), _p(out["ur"]), _p(out["level"]))
+    return out
+
+
+def fuse_points_search(q, dmp, d2, x2, y2, oct2, uright2, bounds, scale_factors, inv_level_sigma2, th=3.0):
+    """Search stage of ORBmatcher::Fuse (ORBmatcher.cc:896-950) -> (best_idx, best_dist)."""
+    n = len(q["active"])
+    bi = np.full(max(n, 1), -1, np.int32); bd = np.full(max(n, 1), 256, np.int32)
+    lib().orc_fuse_points_search(n, _p(_u8(q["active"])), _p(_f32(q["u"])), _p(_f32(q["v"])), _p(_f32(q["ur"])), _p(_i32(q["level"])), _p(_u8(dmp)),
+                                 len(x2), _p(_u8(d2)), _p(_f32(x2)), _p(_f32(y2)), _p(_i32(oct2)), _p(_f32(uright2)) if uright2 is not None else None,
+                                 _p(_f32(bounds)), _p(_f32(scale_factors)), _p(_f32(inv_level_sigma2)), C.c_float(th), _p(bi), _p(bd))
+    return bi[:n], bd[:n]
+
+
+def fuse_project_lines(skip, Pw, normal, min_inv, max_inv, max_raw, Tcw, Ow, cam5, bounds, nlevels, log_scale_factor):
+    """Projection stage of LSDmatcher::Fuse (LSDmatcher.cpp:417-497) -> dict(active, proj[n,4], level)."""
+    n = len(skip)
+    out = dict(active=np.zeros(n, np.uint8), proj=np.zeros((n, 4), np.float32), level=np.zeros(n, np.int32))
+    lib().orc_fuse_project_lines(n, _p(_u8(skip)), _p(_f32(Pw)), _p(_f32(normal)), _p(_f32(min_inv)), _p(_f32(max_inv)), _p(_f32(max_raw)),
+                                 _p(_f32(Tcw)), _p(_f32(Ow)), _p(_f32(cam5)), _p(_f32(bounds)), int(nlevels), C.c_float(log_scale_factor),
+                                 _p(out["active"]), _p(out["proj"]), _p(out["level"]))
+    return out
+
+
+def fuse_lines_search(q, dml, ld2, kl2, oct2, scale_factors, th=3.0):
+    """Search stage of LSDmatcher::Fuse (LSDmatcher.cpp:499-523) -> (best_idx, best_dist)."""
+    n = len(q["active"])
+    bi = np.full(max(n, 1), -1, np.int32); bd = np.full(max(n, 1), 0x7fffffff, np.int32)
+    lib().orc_fuse_lines_search(n, _p(_u8(q["active"])), _p(_f32(q["proj"])), _p(_i32(q["level"])), _p(_u8(dml)), len(oct2), _p(_u8(ld2)), _p(_f32(kl2)),
+                                _p(_i32(oct2)), _p(_f32(scale_factors)), C.c_float(th), _p(bi), _p(bd))
+    return bi[:n], bd[:n]
+
+
 def features_in_area(kx, ky, oct, bounds, x, y, r, min_level=-1, max_level=-1):
     """Frame::GetFeaturesInArea (Frame.cc:368-421) over a freshly built grid (AssignFeaturesToGrid, :133-148)."""
     kx = _f32(kx); ky = _f32(ky); oct = np.ascontiguousarray(oct, np.int32)

@@ -533,4 +533,194 @@ void ref_cvt_gray(const uint8_t* src, int w, int h, int cn, int rgb, uint8_t* ds
     memcpy(dst, d.data, (size_t)w * h);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// line projection matchers and Fuse (src/LSDmatcher.cpp, src/ORBmatcher.cc, unmodified)
+// ------------------------------------------------------------------------------------------------
+namespace {
+void set_keylines(Frame* F, int nl, const float* kl, const int32_t* oct) {      // pt.x, pt.y, angle per line; the octave
+    for (int j = 0; j < nl; j++) {
+        KeyLine& k = F->mvKeylinesUn[j];
+        memset(&k, 0, sizeof(k));
+        k.pt.x = kl[3 * j]; k.pt.y = kl[3 * j + 1]; k.angle = kl[3 * j + 2]; k.octave = oct[j]; k.class_id = j;
+    }
+}
+MapLine* make_ml(Scene& S, KeyFrame* kf, const double* P6, const uint8_t* desc) {
+    Vector6d P; for (int k = 0; k < 6; k++) P(k) = P6 ? P6[k] : (k == 2 || k == 5 ? 1.0 : (k == 3 ? 1.0 : 0.0));
+    MapLine* l = new MapLine(P, kf, &S.map); S.mls.push_back(l);
+    if (desc) desc_mat(desc, 1).copyTo(l->mLDescriptor);
+    return l;
+}
+KeyFrame* make_observer(Scene& S, const Cam& cam, int nlevels, float scaleFactor) {   // a KeyFrame with one feature and one line, to be an observation of
+    orc_keypoint one; memset(&one, 0, sizeof(one)); one.x = one.y = 10.f;
+    const uint8_t zero32[32] = {0};
+    return make_kf(S, make_frame(S, cam, nlevels, scaleFactor, &one, 1, zero32, nullptr, nullptr, nullptr, 0, nullptr, zero32, 1));
+}
+}  // namespace
+
+/* LSDmatcher::SearchByProjection(Frame& Current, const Frame& Last, th, bMono) :22-141.  state1[i]: 0 no MapLine, 1 good, 2 bad, 3 good but
+   mvbLineOutlier; obs1[i]: the MapLine has an observation; oct1[i] = LastFrame.mvKeys[i].octave (the Last frame gets nl1 keypoints);
+   held2[j]: 0 free, 1 a MapLine WITH observations, 2 one without.  assign2[j] = index of the Last-frame line whose MapLine sits there
+   afterwards (-1 none, -2 the pre-existing one). */
+int ref_line_projection_frame(int nl1, const uint8_t* state1, const uint8_t* obs1, const double* Pw6, const uint8_t* dml, const int32_t* oct1,
+                              int nl2, const uint8_t* ld2, const float* kl2, const int32_t* oct2, const uint8_t* held2,
+                              const float* Tcw, const float* Tlw, const float* cam8, float mb, int nlevels, float scaleFactor, float nnratio, float th, int mono,
+                              int32_t* assign2) {
+    Scene S;
+    Cam cam; memcpy(&cam, cam8, sizeof(cam));
+    std::vector<orc_keypoint> k1((size_t)std::max(nl1, 1)); memset(k1.data(), 0, k1.size() * sizeof(orc_keypoint));
+    for (int i = 0; i < nl1; i++) { k1[i].x = k1[i].y = 20.f; k1[i].octave = oct1[i]; }
+    std::vector<uint8_t> zero((size_t)std::max(nl1, 1) * 32, 0);
+    Frame* L = make_frame(S, cam, nlevels, scaleFactor, k1.data(), nl1, zero.data(), nullptr, nullptr, nullptr, 0, Tlw, zero.data(), nl1);
+    KeyFrame* KFl = make_kf(S, L);
+    Frame* Cf = make_frame(S, cam, nlevels, scaleFactor, k1.data(), 0, nullptr, nullptr, nullptr, nullptr, 0, Tcw, ld2, nl2);
+    Cf->mb = mb;
+    set_keylines(Cf, nl2, kl2, oct2);
+    std::map<MapLine*, int> index;
+    for (int i = 0; i < nl1; i++) if (state1[i]) {
+        MapLine* l = make_ml(S, KFl, Pw6 + 6 * (size_t)i, dml + 32 * (size_t)i);
+        if (obs1[i]) l->AddObservation(KFl, i);
+        if (state1[i] == 2) l->mbBad = true;
+        if (state1[i] == 3) L->mvbLineOutlier[i] = true;
+        L->mvpMapLines[i] = l; index[l] = i;
+    }
+    if (held2) for (int j = 0; j < nl2; j++) if (held2[j]) {
+        MapLine* l = make_ml(S, KFl, nullptr, nullptr); if (held2[j] == 1) l->AddObservation(KFl, 0); Cf->mvpMapLines[j] = l; index[l] = -2;
+    }
+    LSDmatcher matcher(nnratio, true);
+    const int n = matcher.SearchByProjection(*Cf, *L, th, mono != 0);
+    for (int j = 0; j < nl2; j++) { MapLine* l = Cf->mvpMapLines[j]; assign2[j] = l ? index[l] : -1; }
+    return n;
+}
+
+/* LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, th) :185-255 (Tracking::SearchLocalLines, Tracking.cc:1783) */
+int ref_line_projection_mls(int nml, const uint8_t* inview, const uint8_t* bad, const uint8_t* obs, const float* proj4, const int32_t* level,
+                            const float* viewcos, const uint8_t* dml, int nl2, const uint8_t* ld2, const float* kl2, const int32_t* oct2,
+                            const uint8_t* held2, const float* cam8, int nlevels, float scaleFactor, float nnratio, float th, int32_t* assign2) {
+    Scene S;
+    Cam cam; memcpy(&cam, cam8, sizeof(cam));
+    orc_keypoint none; memset(&none, 0, sizeof(none));
+    Frame* F = make_frame(S, cam, nlevels, scaleFactor, &none, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, ld2, nl2);
+    set_keylines(F, nl2, kl2, oct2);
+    KeyFrame* KF = make_observer(S, cam, nlevels, scaleFactor);
+    std::map<MapLine*, int> index;
+    std::vector<MapLine*> mls;
+    for (int i = 0; i < nml; i++) {
+        MapLine* l = make_ml(S, KF, nullptr, dml + 32 * (size_t)i);
+        l->mbTrackInView = inview[i] != 0; l->mbBad = bad && bad[i];
+        l->mTrackProjX1 = proj4[4 * i]; l->mTrackProjY1 = proj4[4 * i + 1]; l->mTrackProjX2 = proj4[4 * i + 2]; l->mTrackProjY2 = proj4[4 * i + 3];
+        l->mnTrackScaleLevel = level[i]; l->mTrackViewCos = viewcos[i];
+        if (obs && obs[i]) l->AddObservation(KF, 0);
+        mls.push_back(l); index[l] = i;
+    }
+    if (held2) for (int j = 0; j < nl2; j++) if (held2[j]) {
+        MapLine* l = make_ml(S, KF, nullptr, nullptr); if (held2[j] == 1) l->AddObservation(KF, 0); F->mvpMapLines[j] = l; index[l] = -2;
+    }
+    LSDmatcher matcher(nnratio, true);
+    const int n = matcher.SearchByProjection(*F, mls, th);
+    for (int j = 0; j < nl2; j++) { MapLine* l = F->mvpMapLines[j]; assign2[j] = l ? index[l] : -1; }
+    return n;
+}
+
+/* ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) :828-973.  state[i]: 0 NULL entry, 1 good, 2 bad, 3 already observed by the KeyFrame;
+   nobs[i]: observations in other KeyFrames; minDist/maxDist: mfMinDistance/mfMaxDistance.  kfobs[j]: -1 the KeyFrame feature holds no MapPoint,
+   >= 0 it holds one with that many OTHER observations.  fused_idx[i]: the KeyFrame feature MapPoint i ended up at or was replaced into
+   (-1: not fused); Ow3, minInv, maxInv, logScale: what the reference's accessors return (inputs of the oracle's projection stage). */
+int ref_fuse_points(int nmp, const uint8_t* state, const int32_t* nobs, const float* Xw, const float* normal, const float* minDist, const float* maxDist,
+                    const uint8_t* dmp, int n2, const uint8_t* d2, const orc_keypoint* k2, const float* uright2, const int32_t* kfobs,
+                    const float* Tcw, const float* cam8, float mbf, int nlevels, float scaleFactor, float th,
+                    int32_t* fused_idx, float* Ow3, float* minInv, float* maxInv, float* logScale) {
+    Scene S;
+    Cam cam; memcpy(&cam, cam8, sizeof(cam));
+    Frame* F = make_frame(S, cam, nlevels, scaleFactor, k2, n2, d2, nullptr, nullptr, nullptr, 0, Tcw);
+    F->mbf = mbf; F->mb = mbf / cam.fx;
+    if (uright2) for (int j = 0; j < n2; j++) F->mvuRight[j] = uright2[j];
+    KeyFrame* KF = make_kf(S, F);
+    int maxobs = 0;
+    for (int i = 0; i < nmp; i++) maxobs = std::max(maxobs, nobs[i]);
+    for (int j = 0; j < n2; j++) maxobs = std::max(maxobs, kfobs[j]);
+    std::vector<KeyFrame*> observers;
+    for (int k = 0; k < maxobs; k++) observers.push_back(make_observer(S, cam, nlevels, scaleFactor));
+    for (int j = 0; j < n2; j++) if (kfobs[j] >= 0) {
+        const float far[3] = {0, 0, 1000};
+        MapPoint* q = make_mp(S, KF, far);
+        desc_mat(d2 + 32 * (size_t)j, 1).copyTo(q->mDescriptor);
+        q->AddObservation(KF, j); KF->AddMapPoint(q, j);
+        for (int k = 0; k < kfobs[j]; k++) q->AddObservation(observers[k], 0);
+    }
+    std::vector<MapPoint*> mps(nmp, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < nmp; i++) {
+        if (!state[i]) continue;
+        MapPoint* p = make_mp(S, observers.empty() ? KF : observers[0], Xw + 3 * (size_t)i);
+        mat_from(normal + 3 * (size_t)i, 3, 1).copyTo(p->mNormalVector);
+        p->mfMinDistance = minDist[i]; p->mfMaxDistance = maxDist[i];
+        desc_mat(dmp + 32 * (size_t)i, 1).copyTo(p->mDescriptor);
+        for (int k = 0; k < nobs[i]; k++) p->AddObservation(observers[k], 0);
+        if (state[i] == 2) p->mbBad = true;
+        if (state[i] == 3) p->AddObservation(KF, 0);
+        mps[i] = p;
+        if (minInv) { minInv[i] = p->GetMinDistanceInvariance(); maxInv[i] = p->GetMaxDistanceInvariance(); }
+    }
+    if (Ow3) { cv::Mat Ow = KF->GetCameraCenter(); for (int k = 0; k < 3; k++) Ow3[k] = Ow.at<float>(k); }
+    if (logScale) *logScale = KF->mfLogScaleFactor;
+    ORBmatcher matcher(0.6f, true);
+    const int n = matcher.Fuse(KF, mps, th);
+    for (int i = 0; i < nmp; i++) {
+        fused_idx[i] = -1;
+        MapPoint* p = mps[i];
+        if (!p || state[i] != 1) continue;
+        int hops = 0;
+        while (p && p->isBad() && hops++ < 8) p = p->GetReplaced();
+        if (p && !p->isBad() && p->IsInKeyFrame(KF)) fused_idx[i] = p->GetIndexInKeyFrame(KF);
+    }
+    return n;
+}
+
+/* LSDmatcher::Fuse(KeyFrame*, const vector<MapLine*>&, th) :417-548; arguments as ref_fuse_points (Pw6 doubles, normal doubles: Vector3d) */
+int ref_fuse_lines(int nml, const uint8_t* state, const int32_t* nobs, const double* Pw6, const double* normal, const float* minDist, const float* maxDist,
+                   const uint8_t* dml, int nl2, const uint8_t* ld2, const float* kl2, const int32_t* oct2, const int32_t* kfobs,
+                   const float* Tcw, const float* cam8, int nlevels, float scaleFactor, float th,
+                   int32_t* fused_idx, float* Ow3, float* minInv, float* maxInv, float* logScale) {
+    Scene S;
+    Cam cam; memcpy(&cam, cam8, sizeof(cam));
+    orc_keypoint none; memset(&none, 0, sizeof(none));
+    Frame* F = make_frame(S, cam, nlevels, scaleFactor, &none, 0, nullptr, nullptr, nullptr, nullptr, 0, Tcw, ld2, nl2);
+    set_keylines(F, nl2, kl2, oct2);
+    KeyFrame* KF = make_kf(S, F);
+    int maxobs = 0;
+    for (int i = 0; i < nml; i++) maxobs = std::max(maxobs, nobs[i]);
+    for (int j = 0; j < nl2; j++) maxobs = std::max(maxobs, kfobs[j]);
+    std::vector<KeyFrame*> observers;
+    for (int k = 0; k < maxobs; k++) observers.push_back(make_observer(S, cam, nlevels, scaleFactor));
+    for (int j = 0; j < nl2; j++) if (kfobs[j] >= 0) {
+        MapLine* q = make_ml(S, KF, nullptr, ld2 + 32 * (size_t)j);
+        q->AddObservation(KF, j); KF->AddMapLine(q, j);
+        for (int k = 0; k < kfobs[j]; k++) q->AddObservation(observers[k], 0);
+    }
+    std::vector<MapLine*> mls(nml, static_cast<MapLine*>(NULL));
+    for (int i = 0; i < nml; i++) {
+        if (!state[i]) continue;
+        MapLine* l = make_ml(S, observers.empty() ? KF : observers[0], Pw6 + 6 * (size_t)i, dml + 32 * (size_t)i);
+        l->mNormalVector << normal[3 * i], normal[3 * i + 1], normal[3 * i + 2];
+        l->mfMinDistance = minDist[i]; l->mfMaxDistance = maxDist[i];
+        for (int k = 0; k < nobs[i]; k++) l->AddObservation(observers[k], 0);
+        if (state[i] == 2) l->mbBad = true;
+        mls[i] = l;
+        if (minInv) { minInv[i] = l->GetMinDistanceInvariance(); maxInv[i] = l->GetMaxDistanceInvariance(); }
+    }
+    if (Ow3) { cv::Mat Ow = KF->GetCameraCenter(); for (int k = 0; k < 3; k++) Ow3[k] = Ow.at<float>(k); }
+    if (logScale) *logScale = KF->mfLogScaleFactor;
+    LSDmatcher matcher(0.6f, true);
+    const int n = matcher.Fuse(KF, mls, th);
+    for (int i = 0; i < nml; i++) {
+        fused_idx[i] = -1;
+        MapLine* l = mls[i];
+        if (!l || state[i] != 1) continue;
+        int hops = 0;
+        while (l && l->isBad() && hops++ < 8) l = l->GetReplaced();
+        if (l && !l->isBad() && l->IsInKeyFrame(KF)) fused_idx[i] = l->GetIndexInKeyFrame(KF);
+    }
+    return n;
+}
+
 }  // extern "C"

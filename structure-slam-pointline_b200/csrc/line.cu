@@ -1844,7 +1844,8 @@ int sslpl_line_create(const sslpl_line_params* p, sslpl_line** out) {
 void sslpl_line_destroy(sslpl_line* h) {
     if (!h) return;
     cudaSetDevice(h->p.device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    // an external stream may already be gone (its owner was destroyed first): never touch it here
+    if (h->stream && h->stream == h->own_stream) cudaStreamSynchronize(h->own_stream); else cudaDeviceSynchronize();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto e : h->ev) cudaEventDestroy(e);
     if (h->arena) cudaFree(h->arena);

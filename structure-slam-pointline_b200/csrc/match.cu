@@ -926,7 +926,8 @@ int sslpl_matcher_create(const sslpl_matcher_params* p, sslpl_matcher** out) {
 void sslpl_matcher_destroy(sslpl_matcher* m) {
     if (!m) return;
     cudaSetDevice(m->p.device);
-    if (m->stream) cudaStreamSynchronize(m->stream);
+    // an external stream may already be gone (its owner was destroyed first): never touch it here
+    if (m->stream && m->stream == m->own_stream) cudaStreamSynchronize(m->own_stream); else cudaDeviceSynchronize();
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->arena) cudaFree(m->arena);
     if (m->scratch) cudaFree(m->scratch);

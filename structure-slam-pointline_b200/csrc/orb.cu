@@ -39,19 +39,18 @@ struct LevelGeom {
     int pool_cap; long long pool_off;
     int xtab_off, ytab_off;          // resize tables (int2 entries)
     int tile_base, tiles_x, tiles_y; // blur tiles (64x32 over the whole level)
-    int fs_base, fs_tx, fs_ty;       // FAST score tiles (64x32 over the detection window [16,w-16)x[16,h-16))
     float scale, patch_size;
 };
 
 struct OrbGeom {
-    int nlevels, total_cells, total_tiles, kp_total_cap, iniTh, minTh, sort_cap, total_fs_tiles;
+    int nlevels, total_cells, total_tiles, kp_total_cap, iniTh, minTh, sort_cap;
     long long pyr_stride, blur_stride, cand_stride, key_stride, pool_stride;
     int umax[16];
     LevelGeom lv[MAXL];
 };
 
 struct OrbWs {
-    uint8_t* pyr; uint8_t* blur; uint8_t* score;
+    uint8_t* pyr; uint8_t* blur;
     uint32_t* cand; int* cell_cnt; int* cell_off;
     uint32_t* kxyr; int* knode;
     short4* nbox; int* ncnt; int* nq; uint8_t* nalive; unsigned* nbest; int* scan; int* ord;
@@ -220,89 +219,27 @@ __device__ __forceinline__ void stage_box(uint8_t* s_img, uint64_t* s_bar, const
     }
 }
 
-// FAST score map of the detection window, 64x32 tiles.  Phase A: every pixel runs the cheap opposite-pair test and
-// the survivors are compacted into a queue (ballot + popc); phase B: the full 16-ring score only for queued pixels,
-// all lanes busy.  Scores (0 = not a corner at minThFAST) go to a u8 plane with the level's geometry.
-template <bool TMA>
-__global__ void __launch_bounds__(256) k_fast_score(const __grid_constant__ OrbGeom g, OrbWs ws, View v, const CUtensorMap* tm) {
-    __shared__ __align__(128) uint8_t s_img[TL_IH * TL_P];
-    __shared__ __align__(16) uint8_t s_sc[TL_H * TL_W];
-    __shared__ unsigned short s_q[TL_H * TL_W];
-    __shared__ int s_qn;
-    __shared__ __align__(8) uint64_t s_bar;
-    const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-    int l = 0;
-    while (l + 1 < g.nlevels && tile >= g.lv[l + 1].fs_base) l++;
-    const LevelGeom& L = g.lv[l];
-    const int t = tile - L.fs_base, ty = t / L.fs_tx, tx = t - ty * L.fs_tx;
-    const int x0 = MINB + tx * TL_W, y0 = MINB + ty * TL_H;
-    int pitch;
-    const uint8_t* img = level_ptr(g, ws, v, l, f, &pitch);
-    if (tid == 0) s_qn = 0;
-    for (int i = tid; i < TL_H * TL_W / 4; i += 256) reinterpret_cast<uint32_t*>(s_sc)[i] = 0u;
-    stage_box<TMA>(s_img, &s_bar, tm, img, pitch, L.w, L.h, l, f, x0 - TL_X, y0 - 3);
-    if (TMA) __syncthreads();                   // s_qn / s_sc initialisation
-    const int vw = min(TL_W, L.maxBX - x0), vh = min(TL_H, L.maxBY - y0);     // valid part of the tile
-    const int th = g.minTh;
-    // phase A: the opposite-pair test on 4 pixels per thread with byte-SIMD video instructions
-    const unsigned T4 = 0x01010101u * (unsigned)th;
-#pragma unroll
-    for (int it = 0; it < 2; it++) {
-        const int gidx = it * 256 + tid, r = gidx >> 4, c4 = (gidx & 15) * 4;          // 16 four-pixel groups per row
-        unsigned pm = 0;
-        if (r < vh && c4 < vw) {
-            const unsigned* row = reinterpret_cast<const unsigned*>(&s_img[(r + 3) * TL_P + TL_X + c4]);
-            const unsigned C = row[0];
-            const unsigned Rt = __byte_perm(row[0], row[1], 0x6543), Lf = __byte_perm(row[-1], row[0], 0x4321);   // x+3, x-3
-            const unsigned Dn = row[3 * (TL_P / 4)], Up = row[-3 * (TL_P / 4)];                                   // y+3 (k=0), y-3 (k=8)
-            // A_k: centre brighter than ring_k by more than th; B_k: darker
-            const unsigned A0 = __vcmpgtu4(__vsubus4(C, Dn), T4), A8 = __vcmpgtu4(__vsubus4(C, Up), T4);
-            const unsigned A4 = __vcmpgtu4(__vsubus4(C, Rt), T4), A12 = __vcmpgtu4(__vsubus4(C, Lf), T4);
-            const unsigned B0 = __vcmpgtu4(__vsubus4(Dn, C), T4), B8 = __vcmpgtu4(__vsubus4(Up, C), T4);
-            const unsigned B4 = __vcmpgtu4(__vsubus4(Rt, C), T4), B12 = __vcmpgtu4(__vsubus4(Lf, C), T4);
-            pm = (((A0 | A8) & (A4 | A12)) | ((B0 | B8) & (B4 | B12))) & 0x01010101u;
-            if (c4 + 4 > vw) pm &= (1u << (8 * (vw - c4))) - 1u;                        // clip the last group of a partial tile
-        }
-        const int cnt = __popc(pm);
-        int inc = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t2; }
-        int base = 0;
-        if (lane == 31 && inc) base = atomicAdd(&s_qn, inc);
-        base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
-        const int p0 = r * TL_W + c4;
-#pragma unroll
-        for (int k = 0; k < 4; k++) if (pm & (1u << (8 * k))) s_q[base++] = (unsigned short)(p0 + k);
-    }
-    __syncthreads();
-    // phase B
-    const int nq = s_qn;
-    for (int qi = tid; qi < nq; qi += 256) {
-        const int p = s_q[qi], r = p >> 6, c = p & 63;
-        s_sc[p] = (uint8_t)fast_score_tile(&s_img[(r + 3) * TL_P + c + TL_X], TL_P, th);
-    }
-    __syncthreads();
-    uint8_t* out = ws.score + (long long)f * g.blur_stride + L.blur_off + (long long)y0 * L.bpitch + x0;
-    if (vw == TL_W) {
-        for (int i = tid; i < vh * 4; i += 256) {
-            const int r = i >> 2, part = i & 3;
-            *reinterpret_cast<uint4*>(out + (long long)r * L.bpitch + part * 16) = reinterpret_cast<const uint4*>(s_sc)[r * 4 + part];
-        }
-    } else {
-        for (int i = tid; i < vh * vw; i += 256) { const int r = i / vw, c = i - r * vw; out[(long long)r * L.bpitch + c] = s_sc[r * TL_W + c]; }
-    }
-}
-
 constexpr int FAST_MAXC = 60;                 // wCell, hCell < 60 (ceil(w / floor(w/30)) < 60)
 constexpr int FAST_TP = FAST_MAXC + 4;        // pitch of the per-cell score tile (1-px zero halo)
+constexpr int FC_ROWS = 36 + TL_IH;           // staged rows: two 96x38 boxes, the second one 36 rows down (36*96 is a multiple of 128)
 
-// One CTA per cell: in-cell NMS + ordered compaction on the score map.  Equivalent to the reference's per-cell
-// cv::FAST(th=20) with fallback cv::FAST(th=7) (ORBextractor.cc:809-816): NMS inside the cell's detection area with
-// outside pixels = 0, keep survivors >= iniTh or, if none, all survivors (SURVEY.md A.3 [probe]).
-__global__ void __launch_bounds__(128) k_fast_cells(const __grid_constant__ OrbGeom g, OrbWs ws) {
-    __shared__ uint8_t s_sc[(FAST_MAXC + 2) * FAST_TP];
+// One CTA per 30-px cell, the whole FAST stage in shared memory: stage the cell's (aw+6)x(ah+6) image box (TMA, the box
+// starts on the 16-byte boundary at or before iniX), score it in two phases, in-cell NMS, 20/7 rule, ordered compaction.
+//   phase A  the opposite-pair test on 4 pixels per thread with byte-SIMD video instructions; survivors are queued
+//   phase B  the full 16-ring score only for queued pixels, all lanes busy
+// Equivalent to the reference's per-cell cv::FAST(th=20) with fallback cv::FAST(th=7) (ORBextractor.cc:789-829): NMS
+// inside the cell's detection area with outside pixels = 0, keep survivors >= iniTh or, if none, all survivors
+// (SURVEY.md A.3 [probe]).  The detection areas of the cells are disjoint, so no pixel is scored twice and no score
+// ever leaves the SM.
+template <bool TMA>
+__global__ void __launch_bounds__(128) k_fast(const __grid_constant__ OrbGeom g, OrbWs ws, View v, const CUtensorMap* tm) {
+    __shared__ __align__(128) uint8_t s_img[FC_ROWS * TL_P];
+    __shared__ __align__(4) uint8_t s_sc[(FAST_MAXC + 2) * FAST_TP];
+    __shared__ unsigned short s_q[FAST_MAXC * FAST_MAXC];
     __shared__ int s_warp[33];
-    const int cell = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    __shared__ int s_qn;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int cell = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     int l = 0;
     while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cell_base) l++;
     const LevelGeom& L = g.lv[l];
@@ -313,11 +250,79 @@ __global__ void __launch_bounds__(128) k_fast_cells(const __grid_constant__ OrbG
     const int cw = maxX - iniX, ch = maxY - iniY;
     if (iniX >= L.maxBX - 6 || iniY >= L.maxBY - 3 || cw < 7 || ch < 7) { if (tid == 0) *cnt_out = 0; return; }
     const int aw = cw - 6, ah = ch - 6, area = aw * ah;
-    const uint8_t* sc = ws.score + (long long)f * g.blur_stride + L.blur_off + (long long)(iniY + 3) * L.bpitch + iniX + 3;
-    for (int i = tid; i < (aw + 2) * (ah + 2); i += 128) {
-        const int y = i / (aw + 2), x = i - y * (aw + 2);
-        const bool halo = (y == 0 || y == ah + 1 || x == 0 || x == aw + 1);
-        s_sc[y * FAST_TP + x] = halo ? (uint8_t)0 : __ldg(sc + (long long)(y - 1) * L.bpitch + (x - 1));
+    const int bx = iniX & ~15, xo = iniX + 3 - bx;          // smem column of the first detection pixel, 3..18
+    int pitch;
+    const uint8_t* img = level_ptr(g, ws, v, l, f, &pitch);
+    const bool two = ch > TL_IH;
+    if (TMA) {
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tm + l)) : "memory");
+            mbar_expect_tx(&s_bar, (two ? 2 : 1) * TL_P * TL_IH);
+            tma_load_3d(s_img, tm + l, bx, iniY, f, &s_bar);
+            if (two) tma_load_3d(s_img + 36 * TL_P, tm + l, bx, iniY + 36, f, &s_bar);   // rows 36, 37 arrive twice with the same bytes
+        }
+    } else {
+        const bool al = ((reinterpret_cast<uintptr_t>(img) | (unsigned)pitch) & 3) == 0;
+        const int rows = min(ch, FC_ROWS), wmax = (pitch - bx) / 4 - 1;
+        if (al) {
+            for (int i = tid; i < rows * (TL_P / 4); i += 128) {
+                const int r = i / (TL_P / 4), wi = i - r * (TL_P / 4);
+                reinterpret_cast<uint32_t*>(s_img)[i] =
+                    __ldg(reinterpret_cast<const uint32_t*>(img + (long long)min(iniY + r, L.h - 1) * pitch + bx) + min(wi, wmax));
+            }
+        } else {
+            for (int i = tid; i < rows * TL_P; i += 128) {
+                const int r = i / TL_P, c = i - r * TL_P;
+                s_img[i] = __ldg(img + (long long)min(iniY + r, L.h - 1) * pitch + min(bx + c, L.w - 1));
+            }
+        }
+    }
+    if (tid == 0) s_qn = 0;
+    for (int i = tid; i < (ah + 2) * (FAST_TP / 4); i += 128) reinterpret_cast<uint32_t*>(s_sc)[i] = 0u;
+    if (TMA) mbar_wait(&s_bar, 0);
+    __syncthreads();
+    const int th = g.minTh;
+    // phase A on the aligned word grid of the staged box: groups g0, g0+4, ... cover [xo, xo+aw)
+    const unsigned T4 = 0x01010101u * (unsigned)th;
+    const int g0 = xo & ~3, ng = (xo + aw - g0 + 3) >> 2, ngroups = ah * ng;
+    for (int gb = 0; gb < ngroups; gb += 128) {
+        const int gidx = gb + tid;
+        unsigned pm = 0;
+        int r = 0, c4 = 0;
+        if (gidx < ngroups) {
+            r = gidx / ng; c4 = g0 + 4 * (gidx - r * ng);
+            const unsigned* row = reinterpret_cast<const unsigned*>(&s_img[(r + 3) * TL_P + c4]);
+            const unsigned C = row[0];
+            const unsigned Rt = __byte_perm(row[0], row[1], 0x6543), Lf = __byte_perm(row[-1], row[0], 0x4321);   // x+3, x-3
+            const unsigned Dn = row[3 * (TL_P / 4)], Up = row[-3 * (TL_P / 4)];                                   // y+3 (k=0), y-3 (k=8)
+            // A_k: centre brighter than ring_k by more than th; B_k: darker
+            const unsigned A0 = __vcmpgtu4(__vsubus4(C, Dn), T4), A8 = __vcmpgtu4(__vsubus4(C, Up), T4);
+            const unsigned A4 = __vcmpgtu4(__vsubus4(C, Rt), T4), A12 = __vcmpgtu4(__vsubus4(C, Lf), T4);
+            const unsigned B0 = __vcmpgtu4(__vsubus4(Dn, C), T4), B8 = __vcmpgtu4(__vsubus4(Up, C), T4);
+            const unsigned B4 = __vcmpgtu4(__vsubus4(Rt, C), T4), B12 = __vcmpgtu4(__vsubus4(Lf, C), T4);
+            pm = (((A0 | A8) & (A4 | A12)) | ((B0 | B8) & (B4 | B12))) & 0x01010101u;
+            if (c4 < xo) pm &= ~0u << (8 * (xo - c4));                                    // clip the first and the last group of a row
+            if (c4 + 4 > xo + aw) pm &= (1u << (8 * (xo + aw - c4))) - 1u;
+        }
+        const int cnt = __popc(pm);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t2; }
+        int base = 0;
+        if (lane == 31 && inc) base = atomicAdd(&s_qn, inc);
+        base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+        const int p0 = (r << 6) + c4 - xo;
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (pm & (1u << (8 * k))) s_q[base++] = (unsigned short)(p0 + k);
+    }
+    __syncthreads();
+    // phase B
+    const int nq = s_qn;
+    for (int qi = tid; qi < nq; qi += 128) {
+        const int p = s_q[qi], r = p >> 6, c = p & 63;
+        s_sc[(r + 1) * FAST_TP + c + 1] = (uint8_t)fast_score_tile(&s_img[(r + 3) * TL_P + c + xo], TL_P, th);
     }
     __syncthreads();
     const int chunk = (area + 127) / 128;                  // <= 28
@@ -789,7 +794,7 @@ void make_geometry(const sslpl_orb* h, int W, int H, OrbGeom& g, std::vector<int
     g.nlevels = L; g.iniTh = h->p.iniThFAST; g.minTh = h->p.minThFAST;
     for (int i = 0; i < 16; i++) g.umax[i] = h->umax[i];
     long long pyr = 0, blur = 0, cand = 0, key = 0, pool = 0;
-    int cells = 0, tiles = 0, kpc = 0, rt = 0, maxN = 2, fst = 0;
+    int cells = 0, tiles = 0, kpc = 0, rt = 0, maxN = 2;
     for (int l = 0; l < L; l++) {
         LevelGeom& G = g.lv[l];
         G.w = cvRoundF((float)W * h->invscale[l]); G.h = cvRoundF((float)H * h->invscale[l]);     // ORBextractor.cc:1111-1112
@@ -813,11 +818,9 @@ void make_geometry(const sslpl_orb* h, int W, int H, OrbGeom& g, std::vector<int
         G.xtab_off = rt; rt += G.w; G.ytab_off = rt; rt += G.h;
         G.tiles_x = (G.w + BLUR_TW - 1) / BLUR_TW; G.tiles_y = (G.h + BLUR_TH - 1) / BLUR_TH;
         G.tile_base = tiles; tiles += G.tiles_x * G.tiles_y;
-        G.fs_tx = G.ncells ? (G.maxBX - MINB + TL_W - 1) / TL_W : 0; G.fs_ty = G.ncells ? (G.maxBY - MINB + TL_H - 1) / TL_H : 0;
-        G.fs_base = fst; fst += G.fs_tx * G.fs_ty;
         G.scale = h->scale[l]; G.patch_size = (float)(int)(31 * h->scale[l]);                      // :836 (int truncation)
     }
-    g.total_cells = cells; g.total_tiles = tiles; g.kp_total_cap = kpc; g.total_fs_tiles = fst;
+    g.total_cells = cells; g.total_tiles = tiles; g.kp_total_cap = kpc;
     g.pyr_stride = pyr; g.blur_stride = blur; g.cand_stride = cand; g.key_stride = key; g.pool_stride = pool;
     int sc = 2; while (sc < maxN) sc <<= 1;
     g.sort_cap = sc;
@@ -846,7 +849,6 @@ int carve(sslpl_orb* h, Arena& A, const OrbGeom& g, int B, int W, int H) {
     h->d_input = A.take<uint8_t>((size_t)B * align_up(W, 16) * H + 256);
     ws.pyr = A.take<uint8_t>((size_t)B * g.pyr_stride + 256);
     ws.blur = A.take<uint8_t>((size_t)B * g.blur_stride + 256);
-    ws.score = A.take<uint8_t>((size_t)B * g.blur_stride + 256);
     ws.cand = A.take<uint32_t>((size_t)B * g.cand_stride);
     ws.cell_cnt = A.take<int>((size_t)B * g.total_cells);
     ws.cell_off = A.take<int>((size_t)B * g.total_cells);
@@ -942,13 +944,11 @@ int run_pipeline(sslpl_orb* h, int B) {
         } else h->tm0_base = nullptr;
     }
     if (g.total_cells > 0) {
-        if (tma) k_fast_score<true><<<dim3(g.total_fs_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
-        else k_fast_score<false><<<dim3(g.total_fs_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
-        mark(h, "fast_score");
-        k_fast_cells<<<dim3(g.total_cells, B), 128, 0, st>>>(g, h->ws);
-        h->launches += 2;
+        if (tma) k_fast<true><<<dim3(g.total_cells, B), 128, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
+        else k_fast<false><<<dim3(g.total_cells, B), 128, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
+        h->launches++;
     }
-    mark(h, "fast_cells");
+    mark(h, "fast");
     k_octree<<<dim3(g.nlevels, B), 256, h->octree_smem, st>>>(g, h->ws); h->launches++;
     mark(h, "octree");
     if (tma) k_blur<true><<<dim3(g.total_tiles, B), 256, 0, st>>>(g, h->ws, h->view, h->ws.tmaps);
@@ -1019,7 +1019,8 @@ int sslpl_orb_create(const sslpl_orb_params* p, sslpl_orb** out) {
 void sslpl_orb_destroy(sslpl_orb* h) {
     if (!h) return;
     cudaSetDevice(h->p.device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    // an external stream may already be gone (its owner was destroyed first): never touch it here
+    if (h->stream && h->stream == h->own_stream) cudaStreamSynchronize(h->own_stream); else cudaDeviceSynchronize();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto e : h->ev) cudaEventDestroy(e);
     if (h->arena) cudaFree(h->arena);
