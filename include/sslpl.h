@@ -221,6 +221,40 @@ int  sslpl_search_for_initialization(sslpl_matcher* m,
         int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* angle2,
         const float* bounds, float nnratio, int checkOrientation, int windowSize, int32_t* matches12, int* nmatches);
 
+/* ---- Line projection matchers and Fuse.  Each reference function is a projection stage (per map element:
+   gates and projected quantities, arithmetic in the reference's own cv::Mat / Eigen types - it stays in the adapter, host/matcher_b200.cc,
+   which calls the reference's own accessors, e.g. MapPoint::PredictScale) followed by a search stage (the Hamming scan over the frame's
+   features), which is what these entry points run on the device.  HOST buffers; results identical to the reference's loops.
+
+   sslpl_line_search_by_projection: search stage of LSDmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (LSDmatcher.cpp:98-137)
+   and of LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, th) (:210-251).  Per MapLine, in the reference's visiting order:
+   active (passed the gates), obs (Observations() > 0), proj[4] = projected end points x1 y1 x2 y2, radius, [minLevel, maxLevel] as handed to
+   Frame::GetLinesInArea (Frame.cc:423-460), its descriptor.  Frame lines: descriptors, kl2[3] = pt.x pt.y angle of mvKeylinesUn, octaves,
+   held2 (1 = holds a MapLine WITH observations: never a candidate).  assign2[j] = index of the MapLine written to mvpMapLines[j] (the last
+   writer; -1 none), *nmatches = the function's return value. */
+int  sslpl_line_search_by_projection(sslpl_matcher* m, int nml, const uint8_t* active, const uint8_t* obs, const float* proj, const float* radius,
+        const int32_t* minLevel, const int32_t* maxLevel, const uint8_t* dml,
+        int nl2, const uint8_t* ld2, const float* kl2, const int32_t* oct2, const uint8_t* held2,
+        float nnratio, int32_t* assign2, int* nmatches);
+/* Search stage of LSDmatcher::Fuse(KeyFrame*, const vector<MapLine*>&, th) (LSDmatcher.cpp:495-523): per MapLine the projected end points and
+   the level MapLine::PredictScale returned; KeyFrame lines as above (oct2 = mvKeyLines[].octave).  best_idx[i] = nearest KeyFrame line of the
+   window at level in [level-1, level] (first on ties; -1 none), best_dist[i] (INT_MAX when none); the caller fuses when best_dist <= 50.
+   A level outside [0, nlevels) (PredictScale is not clamped, MapLine.cpp:386-395; the reference then reads mvScaleFactors out of bounds)
+   drops the line. */
+int  sslpl_fuse_lines_search(sslpl_matcher* m, int nml, const uint8_t* active, const float* proj, const int32_t* level, const uint8_t* dml,
+        int nl2, const uint8_t* ld2, const float* kl2, const int32_t* oct2, const float* scaleFactors, int nlevels, float th,
+        int32_t* best_idx, int32_t* best_dist);
+/* Search stage of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (ORBmatcher.cc:889-950): per MapPoint its projection (u, v, ur =
+   u - bf / z; ur may be NULL when the KeyFrame has no stereo features) and predicted level; KeyFrame features: descriptors, mvKeysUn x / y /
+   octave, mvuRight (NULL = monocular), image bounds, mvScaleFactors, mvInvLevelSigma2.  Window = KeyFrame::GetFeaturesInArea(u, v,
+   th * scale[level]) (KeyFrame.cc:610-649), level gate, chi-square gate (5.99 mono / 7.8 stereo), nearest descriptor (first in the grid
+   traversal order on ties).  best_idx[i] (-1 none), best_dist[i] (256 none); the caller fuses when best_dist <= 50. */
+int  sslpl_fuse_points_search(sslpl_matcher* m, int nmp, const uint8_t* active, const float* u, const float* v, const float* ur,
+        const int32_t* level, const uint8_t* dmp,
+        int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* uright2,
+        const float* bounds, const float* scaleFactors, const float* invLevelSigma2, int nlevels, float th,
+        int32_t* best_idx, int32_t* best_dist);
+
 /* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-312) / MapLine::ComputeDistinctiveDescriptors (MapLine.cpp:246-317),
    batched: group g owns descriptors desc[off[g] .. off[g+1]) (HOST buffers, off[0] = 0);
    best_idx[g] = index inside the group of the descriptor with the least median Hamming distance to the others (median =

@@ -157,6 +157,71 @@ def search_for_initialization(d1, k1, d2, k2, prev, camv, nlevels=8, scale=1.2, 
     return n, m12[:len(k1)], prev
 
 
+def _u8(a):
+    return np.ascontiguousarray(a, np.uint8)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def line_projection_frame(last, cur, Tcw, Tlw, camv, mb, nlevels=8, scale=1.2, nnratio=0.8, th=3.0, mono=True):
+    """LSDmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) :22-141.  last = dict(state, obs, Pw[n,6] f64, dml, oct);
+    cur = dict(ld, kl[n,3], oct, held) -> (nmatches, assign2)."""
+    nl1, nl2 = len(last["state"]), len(cur["oct"])
+    out = np.full(max(nl2, 1), -1, np.int32)
+    lib().ref_line_projection_frame.restype = C.c_int
+    n = lib().ref_line_projection_frame(nl1, _p(_u8(last["state"])), _p(_u8(last["obs"])), _p(_f64(last["Pw"])), _p(_u8(last["dml"])), _p(_i32(last["oct"])),
+                                        nl2, _p(_u8(cur["ld"])), _p(_f32(cur["kl"])), _p(_i32(cur["oct"])),
+                                        _p(_u8(cur["held"])) if cur.get("held") is not None else None,
+                                        _p(_f32(np.asarray(Tcw)[:3, :4])), _p(_f32(np.asarray(Tlw)[:3, :4])), _p(_f32(camv)), C.c_float(mb), nlevels,
+                                        C.c_float(scale), C.c_float(nnratio), C.c_float(th), int(mono), _p(out))
+    return n, out[:nl2]
+
+
+def line_projection_mls(ml, cur, camv, nlevels=8, scale=1.2, nnratio=0.8, th=1.0):
+    """LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, th) :185-255."""
+    nml, nl2 = len(ml["inview"]), len(cur["oct"])
+    out = np.full(max(nl2, 1), -1, np.int32)
+    lib().ref_line_projection_mls.restype = C.c_int
+    n = lib().ref_line_projection_mls(nml, _p(_u8(ml["inview"])), _p(_u8(ml["bad"])), _p(_u8(ml["obs"])), _p(_f32(ml["proj"])), _p(_i32(ml["level"])),
+                                      _p(_f32(ml["viewcos"])), _p(_u8(ml["desc"])), nl2, _p(_u8(cur["ld"])), _p(_f32(cur["kl"])), _p(_i32(cur["oct"])),
+                                      _p(_u8(cur["held"])) if cur.get("held") is not None else None, _p(_f32(camv)), nlevels, C.c_float(scale),
+                                      C.c_float(nnratio), C.c_float(th), _p(out))
+    return n, out[:nl2]
+
+
+def fuse_points(mp, kf, Tcw, camv, mbf, nlevels=8, scale=1.2, th=3.0):
+    """ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) :828-973 -> (nFused, fused_idx, dict(Ow, min_inv, max_inv, log_scale))."""
+    nmp = len(mp["state"]); k2 = _kp(kf["kps"]); n2 = len(k2)
+    fi = np.full(max(nmp, 1), -1, np.int32); Ow = np.zeros(3, np.float32); mi = np.zeros(max(nmp, 1), np.float32); ma = np.zeros(max(nmp, 1), np.float32)
+    ls = C.c_float()
+    ur = _f32(kf["uright"]) if kf.get("uright") is not None else None
+    lib().ref_fuse_points.restype = C.c_int
+    n = lib().ref_fuse_points(nmp, _p(_u8(mp["state"])), _p(_i32(mp["nobs"])), _p(_f32(mp["Xw"])), _p(_f32(mp["normal"])), _p(_f32(mp["min_raw"])),
+                              _p(_f32(mp["max_raw"])), _p(_u8(mp["desc"])), n2, _p(_u8(kf["desc"])), _p(k2), _p(ur) if ur is not None else None,
+                              _p(_i32(kf["kfobs"])), _p(_f32(np.asarray(Tcw)[:3, :4])), _p(_f32(camv)), C.c_float(mbf), nlevels, C.c_float(scale), C.c_float(th),
+                              _p(fi), _p(Ow), _p(mi), _p(ma), C.byref(ls))
+    return n, fi[:nmp], dict(Ow=Ow, min_inv=mi[:nmp], max_inv=ma[:nmp], log_scale=ls.value)
+
+
+def fuse_lines(ml, kf, Tcw, camv, nlevels=8, scale=1.2, th=3.0):
+    """LSDmatcher::Fuse(KeyFrame*, const vector<MapLine*>&, th) :417-548 -> (nFused, fused_idx, dict(Ow, min_inv, max_inv, log_scale))."""
+    nml = len(ml["state"]); nl2 = len(kf["oct"])
+    fi = np.full(max(nml, 1), -1, np.int32); Ow = np.zeros(3, np.float32); mi = np.zeros(max(nml, 1), np.float32); ma = np.zeros(max(nml, 1), np.float32)
+    ls = C.c_float()
+    lib().ref_fuse_lines.restype = C.c_int
+    n = lib().ref_fuse_lines(nml, _p(_u8(ml["state"])), _p(_i32(ml["nobs"])), _p(_f64(ml["Pw"])), _p(_f64(ml["normal"])), _p(_f32(ml["min_raw"])),
+                             _p(_f32(ml["max_raw"])), _p(_u8(ml["desc"])), nl2, _p(_u8(kf["ld"])), _p(_f32(kf["kl"])), _p(_i32(kf["oct"])), _p(_i32(kf["kfobs"])),
+                             _p(_f32(np.asarray(Tcw)[:3, :4])), _p(_f32(camv)), nlevels, C.c_float(scale), C.c_float(th),
+                             _p(fi), _p(Ow), _p(mi), _p(ma), C.byref(ls))
+    return n, fi[:nml], dict(Ow=Ow, min_inv=mi[:nml], max_inv=ma[:nml], log_scale=ls.value)
+
+
 def features_in_area(kps, camv, x, y, r, min_level=-1, max_level=-1):
     k = _kp(kps); out = np.empty(max(len(k), 1), np.int32)
     n = lib().ref_features_in_area(len(k), _p(k), _p(_f32(camv)), C.c_float(x), C.c_float(y), C.c_float(r), int(min_level), int(max_level),

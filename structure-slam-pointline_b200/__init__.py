@@ -366,6 +366,39 @@ class Matcher:
                                                     C.c_float(nnratio), C.c_float(th), _p(out), C.byref(nm)))
         return nm.value, out[:n2]
 
+    def line_search_by_projection(self, q, obs, dml, ld2, kl2, oct2, held2=None, nnratio=0.8):
+        """Search stage of LSDmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (LSDmatcher.cpp:98-137) and of
+        LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, th) (:210-251).  q = dict(active, proj[n,4], radius, min_level,
+        max_level) per MapLine (the projection stage's outputs), obs = Observations() > 0, dml their descriptors; ld2 / kl2[n,3] (pt.x,
+        pt.y, angle) / oct2 / held2 the frame's lines -> (nmatches, assign2)."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32); u8 = lambda a: np.ascontiguousarray(a, np.uint8); i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        nml = len(q["active"]); nl2 = len(oct2)
+        out = np.full(max(nl2, 1), -1, np.int32); nm = C.c_int()
+        _check(lib().sslpl_line_search_by_projection(self._h, nml, _p(u8(q["active"])), _p(u8(obs)), _p(f32(q["proj"])), _p(f32(q["radius"])),
+                                                     _p(i32(q["min_level"])), _p(i32(q["max_level"])), _p(u8(dml)), nl2, _p(u8(ld2)), _p(f32(kl2)), _p(i32(oct2)),
+                                                     _p(u8(held2)) if held2 is not None else None, C.c_float(nnratio), _p(out), C.byref(nm)))
+        return nm.value, out[:nl2]
+
+    def fuse_lines_search(self, q, dml, ld2, kl2, oct2, scale_factors, th=3.0):
+        """Search stage of LSDmatcher::Fuse (LSDmatcher.cpp:495-523).  q = dict(active, proj[n,4], level) -> (best_idx, best_dist)."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32); u8 = lambda a: np.ascontiguousarray(a, np.uint8); i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        n = len(q["active"]); sf = f32(scale_factors)
+        bi = np.full(max(n, 1), -1, np.int32); bd = np.full(max(n, 1), 0x7fffffff, np.int32)
+        _check(lib().sslpl_fuse_lines_search(self._h, n, _p(u8(q["active"])), _p(f32(q["proj"])), _p(i32(q["level"])), _p(u8(dml)), len(oct2), _p(u8(ld2)),
+                                             _p(f32(kl2)), _p(i32(oct2)), _p(sf), len(sf), C.c_float(th), _p(bi), _p(bd)))
+        return bi[:n], bd[:n]
+
+    def fuse_points_search(self, q, dmp, d2, x2, y2, oct2, uright2, bounds, scale_factors, inv_level_sigma2, th=3.0):
+        """Search stage of ORBmatcher::Fuse (ORBmatcher.cc:889-950).  q = dict(active, u, v, ur, level) -> (best_idx, best_dist)."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32); u8 = lambda a: np.ascontiguousarray(a, np.uint8); i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        n = len(q["active"]); sf = f32(scale_factors)
+        bi = np.full(max(n, 1), -1, np.int32); bd = np.full(max(n, 1), 256, np.int32)
+        ur2 = f32(uright2) if uright2 is not None else None
+        _check(lib().sslpl_fuse_points_search(self._h, n, _p(u8(q["active"])), _p(f32(q["u"])), _p(f32(q["v"])), _p(f32(q["ur"])), _p(i32(q["level"])), _p(u8(dmp)),
+                                              len(x2), _p(u8(d2)), _p(f32(x2)), _p(f32(y2)), _p(i32(oct2)), _p(ur2) if ur2 is not None else None,
+                                              _p(f32(bounds)), _p(sf), _p(f32(inv_level_sigma2)), len(sf), C.c_float(th), _p(bi), _p(bd)))
+        return bi[:n], bd[:n]
+
     def search_for_initialization(self, d1, k1, d2, k2, prev, bounds, nnratio=0.9, check_ori=True, window=100):
         """ORBmatcher::SearchForInitialization (ORBmatcher.cc:408-523) -> (nmatches, matches12, prev_out)."""
         f32 = lambda a: np.ascontiguousarray(a, np.float32)

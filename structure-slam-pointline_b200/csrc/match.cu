@@ -14,6 +14,7 @@
 namespace sslpl {
 
 constexpr int TH_LOW = 50;          // ORBmatcher.cc:38
+constexpr int MAX_DYN_SMEM = 227 * 1024;   // per-CTA shared memory of sm_100 (opt-in above 48 KB)
 constexpr int HISTO_LENGTH = 30;    // ORBmatcher.cc:39
 
 // A set of frames in HBM (strides in elements of the respective type)
@@ -537,6 +538,160 @@ __global__ void __launch_bounds__(32) k_proj_match_mps(const __grid_constant__ W
     if (lane == 0) *nmatch = nmatches;
 }
 
+// ---------------- line projection search, Fuse search ----------------
+// Frame::GetLinesInArea (Frame.cc:423-460) = KeyFrame::GetLinesInArea (KeyFrame.cc:651-684) for one frame line: the mid-point test is
+// evaluated in double and narrowed (as the mixed float/double expression of the reference is), without FMA contraction.
+struct LineWin { double mx, my; float r2, r, slope; double rs; int minLevel, maxLevel; bool checkLevels; };
+__device__ __forceinline__ LineWin line_win(float x1, float y1, float x2, float y2, float r, int minLevel, int maxLevel) {
+    LineWin w;
+    w.mx = __dmul_rn(0.5, (double)__fadd_rn(x1, x2)); w.my = __dmul_rn(0.5, (double)__fadd_rn(y1, y2));
+    w.r = r; w.r2 = __fmul_rn(r, r);
+    w.slope = __fdiv_rn(__fsub_rn(y1, y2), __fsub_rn(x1, x2));
+    w.rs = __dmul_rn((double)r, 0.01);
+    w.minLevel = minLevel; w.maxLevel = maxLevel; w.checkLevels = (minLevel > 0) || (maxLevel > 0);
+    return w;
+}
+__device__ __forceinline__ bool line_in_area(const LineWin& w, float ptx, float pty, float angle, int octave) {
+    const double dx = __dsub_rn(w.mx, (double)ptx), dy = __dsub_rn(w.my, (double)pty);
+    const float distance = __double2float_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    if (distance > w.r2) return false;
+    const float slope = __fsub_rn(w.slope, angle);
+    if ((double)slope > w.rs) return false;
+    if (w.checkLevels) {
+        if (octave < w.minLevel) return false;
+        if (w.maxLevel >= 0 && octave > w.maxLevel) return false;
+    }
+    return true;
+}
+
+// Search stage of both LSDmatcher::SearchByProjection overloads (LSDmatcher.cpp:98-137 = :210-251).  The MapLines are visited in
+// vector order by ONE warp, because a frame line taken by a MapLine with observations is skipped by the later ones (:104-106);
+// the lanes share the scan over the frame's lines.  keys: (distance << 32) | line index = the scan order of the reference.
+__global__ void __launch_bounds__(32) k_line_window_search(int nml, const uint8_t* flag /* bit0 active, bit1 obs>0 */, const float4* proj, const float* radius,
+                                                            const int* minLevel, const int* maxLevel, const uint8_t* dml,
+                                                            int nl2, const uint8_t* ld2, const float* kl2, const int* oct2, uint8_t* claimed,
+                                                            float nnratio, int32_t* assign2, int32_t* nmatch) {
+    const int lane = threadIdx.x;
+    for (int j = lane; j < nl2; j += 32) assign2[j] = -1;
+    __syncwarp();
+    int nmatches = 0;
+    for (int i = 0; i < nml; i++) {
+        const int fl = flag[i];
+        if (!(fl & 1)) continue;
+        const float4 p = proj[i];
+        const LineWin w = line_win(p.x, p.y, p.z, p.w, radius[i], minLevel[i], maxLevel[i]);
+        uint4 a0, a1;
+        load_desc(dml + (long long)i * 32, a0, a1);
+        unsigned long long b1 = ~0ull, b2 = ~0ull;
+        for (int j = lane; j < nl2; j += 32) {
+            if (!line_in_area(w, kl2[3 * j], kl2[3 * j + 1], kl2[3 * j + 2], oct2[j])) continue;
+            if (claimed[j]) continue;
+            uint4 c0, c1;
+            load_desc(ld2 + (long long)j * 32, c0, c1);
+            const int dist = popc256(a0, a1, c0, c1);
+            if (dist >= 256) continue;                            // never below the initial bestDist = bestDist2 = 256
+            top2_push(b1, b2, ((unsigned long long)dist << 32) | (unsigned)j);
+        }
+        top2_warp(b1, b2);
+        if (b1 == ~0ull) continue;
+        const int bestDist = (int)(b1 >> 32);
+        if (bestDist <= TH_HIGH) {
+            const int j = (int)(b1 & 0xffffffffu);
+            int bestDist2 = 256, bestLevel2 = -1;
+            if (b2 != ~0ull) { bestDist2 = (int)(b2 >> 32); bestLevel2 = oct2[(int)(b2 & 0xffffffffu)]; }
+            if (oct2[j] == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;
+            if (lane == 0) { assign2[j] = i; claimed[j] = (fl >> 1) & 1; }
+            nmatches++;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) *nmatch = nmatches;
+}
+
+// Search stage of LSDmatcher::Fuse (LSDmatcher.cpp:499-523): independent per MapLine, one warp each
+__global__ void __launch_bounds__(128) k_line_fuse_search(int nml, const uint8_t* active, const float4* proj, const int* level, const uint8_t* dml,
+                                                           int nl2, const uint8_t* ld2, const float* kl2, const int* oct2, const float* scale, float th,
+                                                           int32_t* best_idx, int32_t* best_dist) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= nml) return;
+    unsigned long long b = ~0ull;
+    if (active[i]) {
+        const int lvl = level[i];
+        const float4 p = proj[i];
+        const LineWin w = line_win(p.x, p.y, p.z, p.w, __fmul_rn(th, scale[lvl]), -1, -1);
+        uint4 a0, a1;
+        load_desc(dml + (long long)i * 32, a0, a1);
+        for (int j = lane; j < nl2; j += 32) {
+            const int o = oct2[j];
+            if (!line_in_area(w, kl2[3 * j], kl2[3 * j + 1], kl2[3 * j + 2], o)) continue;
+            if (o < lvl - 1 || o > lvl) continue;
+            uint4 c0, c1;
+            load_desc(ld2 + (long long)j * 32, c0, c1);
+            const unsigned long long k = ((unsigned long long)popc256(a0, a1, c0, c1) << 32) | (unsigned)j;
+            b = k < b ? k : b;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o); b = t < b ? t : b; }
+    }
+    if (lane == 0) { best_idx[i] = b == ~0ull ? -1 : (int)(b & 0xffffffffu); best_dist[i] = b == ~0ull ? 0x7fffffff : (int)(b >> 32); }
+}
+
+// Search stage of ORBmatcher::Fuse (ORBmatcher.cc:896-950): independent per MapPoint, one warp each over the grid cells of the window
+__global__ void __launch_bounds__(128) k_point_fuse_search(const __grid_constant__ WinArgs A, int nmp, const uint8_t* active, const float* pu, const float* pv, const float* pur,
+                                                            const int* level, const uint8_t* dmp, const uint8_t* d2, const float* x2, const float* y2, const int* oct2,
+                                                            const float* uright2, const float* invSigma2, const int* goff, const int* gidx,
+                                                            int32_t* best_idx, int32_t* best_dist) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= nmp) return;
+    unsigned long long b = ~0ull;
+    int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
+    if (active[i]) {
+        const int lvl = level[i];
+        const float u = pu[i], v = pv[i], ur = pur[i];
+        const float rad = __fmul_rn(A.th, A.scale[lvl]);
+        if (grid_window(A, u, v, rad, cx0, cx1, cy0, cy1)) {
+            const int ny = cy1 - cy0 + 1, ncell = (cx1 - cx0 + 1) * ny;
+            uint4 a0, a1;
+            load_desc(dmp + (long long)i * 32, a0, a1);
+            for (int c = lane; c < ncell; c += 32) {
+                const int ix = cx0 + c / ny, iy = cy0 + c % ny, cell = ix * GRID_ROWS + iy;
+                const int qb = goff[cell], qe = goff[cell + 1];
+                for (int q = qb; q < qe; q++) {
+                    const int j = gidx[q];
+                    const float kx = x2[j], ky = y2[j];
+                    if (!(fabsf(__fsub_rn(kx, u)) < rad && fabsf(__fsub_rn(ky, v)) < rad)) continue;     // KeyFrame::GetFeaturesInArea KeyFrame.cc:642
+                    const int o = oct2[j];
+                    if (o < lvl - 1 || o > lvl) continue;                                                 // :905
+                    const float ex = __fsub_rn(u, kx), ey = __fsub_rn(v, ky);
+                    float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                    const float kr = A.use_right ? uright2[j] : -1.f;
+                    if (kr >= 0) {                                                                        // stereo chi-square, 3 dof (:908-921)
+                        const float er = __fsub_rn(ur, kr);
+                        e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                        if ((double)__fmul_rn(e2, invSigma2[o]) > 7.8) continue;
+                    } else if ((double)__fmul_rn(e2, invSigma2[o]) > 5.99) continue;                      // :923-932
+                    uint4 c0, c1;
+                    load_desc(d2 + (long long)j * 32, c0, c1);
+                    const int dist = popc256(a0, a1, c0, c1);
+                    if (dist >= 256) continue;                                                            // bestDist starts at 256, strict <
+                    const unsigned long long k = ((unsigned long long)dist << 40) | ((unsigned long long)c << 20) | (unsigned)(q - qb);
+                    b = k < b ? k : b;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o); b = t < b ? t : b; }
+        }
+    }
+    if (lane == 0) {
+        int bi = -1, bd = 256;
+        if (b != ~0ull) {
+            const int ny = cy1 - cy0 + 1, c = (int)((b >> 20) & 0xfffff), pos = (int)(b & 0xfffff);
+            bi = gidx[goff[(cx0 + c / ny) * GRID_ROWS + cy0 + c % ny] + pos]; bd = (int)(b >> 40);
+        }
+        best_idx[i] = bi; best_dist[i] = bd;
+    }
+}
+
 __global__ void __launch_bounds__(32) k_init_match(const __grid_constant__ WinArgs A, int n1, const uint8_t* d1, const int* oct1, const float* angle1,
                                                     float* prevx, float* prevy, int n2, const uint8_t* d2, const float* x2, const float* y2, const int* oct2,
                                                     const float* angle2, const int* goff, const int* gidx, int* matchedDist, int* matches21,
@@ -779,6 +934,13 @@ int carve(sslpl_matcher* m, Arena& A) {
     return 0;
 }
 
+// carve `count` elements out of a scratch arena and start their upload
+template <class T> T* stage(Arena& A, const T* host, size_t count, cudaStream_t st, cudaError_t& err) {
+    T* d = A.take<T>(count + 8);
+    if (host && count && err == cudaSuccess) err = cudaMemcpyAsync(d, host, sizeof(T) * count, cudaMemcpyHostToDevice, st);
+    return d;
+}
+
 int upload_featvec(sslpl_matcher* m, int slot, const sslpl_featvec* fv, int n) {
     const int NN = m->p.max_nodes + 1;
     SSLPL_REQUIRE(fv && fv->nn >= 0 && fv->nn <= m->p.max_nodes, SSLPL_ERR_ARG, "feature vector has more nodes than max_nodes");
@@ -895,6 +1057,8 @@ void line_mad(const int32_t* knn, int nq, double* nn_mad, double* nn12_mad) {
 
 extern "C" {
 
+void sslpl_matcher_destroy(sslpl_matcher* m);
+
 int sslpl_matcher_create(const sslpl_matcher_params* p, sslpl_matcher** out) {
     SSLPL_REQUIRE(p && out, SSLPL_ERR_ARG, "null argument");
     SSLPL_REQUIRE(p->max_features >= 1 && p->max_lines >= 0 && p->max_nodes >= 1 && p->max_batch >= 1, SSLPL_ERR_ARG, "bad matcher capacity");
@@ -909,16 +1073,20 @@ int sslpl_matcher_create(const sslpl_matcher_params* p, sslpl_matcher** out) {
     m->arena_size = A.used + (1 << 16);
     cudaError_t e = cudaMalloc(&m->arena, m->arena_size);
     if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", m->arena_size, cudaGetErrorString(e)); delete m; return SSLPL_ERR_CUDA; }
-    SSLPL_CUDA(cudaMemset(m->arena, 0, m->arena_size));
+    cudaError_t e2 = cudaMemset(m->arena, 0, m->arena_size);
     Arena B; B.base = m->arena; B.size = m->arena_size; carve(m, B);
-    SSLPL_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
     m->stream = m->own_stream;
-    SSLPL_CUDA(cudaHostAlloc((void**)&m->h_small, 64 * sizeof(int32_t), cudaHostAllocDefault));
-    {
+    if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&m->h_small, 64 * sizeof(int32_t), cudaHostAllocDefault);
+    if (e2 == cudaSuccess) {
         std::vector<int> iota(p->max_nodes + 1);
         for (int i = 0; i <= p->max_nodes; i++) iota[i] = i;
-        SSLPL_CUDA(cudaMemcpy(m->iota, iota.data(), sizeof(int) * iota.size(), cudaMemcpyHostToDevice));
+        e2 = cudaMemcpy(m->iota, iota.data(), sizeof(int) * iota.size(), cudaMemcpyHostToDevice);
     }
+    // the two kernels with data-dependent dynamic shared memory may use the whole 227 KB of an sm_100 CTA
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_bow_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_build_csr, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    if (e2 != cudaSuccess) { set_error("sslpl_matcher_create: %s", cudaGetErrorString(e2)); sslpl_matcher_destroy(m); return SSLPL_ERR_CUDA; }
     *out = m;
     return SSLPL_OK;
 }
@@ -980,6 +1148,7 @@ int sslpl_bow_assign(sslpl_matcher* m, const uint8_t* desc, int n, const uint8_t
     cudaStream_t st = m->stream;
     SSLPL_CUDA(cudaMemcpyAsync(m->desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
     SSLPL_CUDA(cudaMemcpyAsync(m->cent, centroids, (size_t)nc * 32, cudaMemcpyHostToDevice, st));
+    SSLPL_REQUIRE((size_t)(nc * 32) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "too many centroids for one shared-memory tile (nc <= 7264)");
     k_bow_assign<<<dim3((n + 127) / 128, 1), 128, nc * 32, st>>>(m->desc, 0, nullptr, n, n, m->cent, nc, m->node, 0); m->launches++;
     SSLPL_CUDA(cudaGetLastError());
     SSLPL_CUDA(cudaMemcpyAsync(node, m->node, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
@@ -1087,6 +1256,7 @@ static int bow_batch_tail(sslpl_matcher* m, const uint8_t* d_desc, const sslpl_k
                           float nnratio, int checkOri, int32_t* d_match, int32_t* d_nmatch) {
     cudaStream_t st = m->stream;
     const int npairs = nframes - 1, fc = m->p.max_features + 64, NN = m->p.max_nodes + 1;
+    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 227 KB)");
     k_build_csr<<<nframes, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->b_node, fc, d_n, cap, nc, m->b_off, NN + 1, m->b_idx, fc);
     m->launches += 1;
     fill(m, d_match, (long long)npairs * cap, -1);
@@ -1116,6 +1286,7 @@ int sslpl_match_bow_batch_device(sslpl_matcher* m, const uint8_t* d_desc, const 
     SSLPL_REQUIRE(cap >= 1 && cap <= m->p.max_features + 64 && nc >= 1 && nc <= m->p.max_nodes, SSLPL_ERR_ARG, "cap or nc exceeds the matcher capacity");
     SSLPL_CUDA(cudaSetDevice(m->p.device));
     const int fc = m->p.max_features + 64;
+    SSLPL_REQUIRE((size_t)(nc * 32) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "too many centroids for one shared-memory tile (nc <= 7264)");
     k_bow_assign<<<dim3((cap + 127) / 128, nframes), 128, nc * 32, m->stream>>>(d_desc, (long long)cap * 32, d_n, 0, cap, d_centroids, nc, m->b_node, fc);
     m->launches += 1;
     return bow_batch_tail(m, d_desc, d_kps, d_n, nframes, cap, nc, nnratio, checkOri, d_match, d_nmatch);
@@ -1179,6 +1350,7 @@ int sslpl_search_by_projection_frame(sslpl_matcher* m,
     SSLPL_CUDA(cudaStreamSynchronize(st));                               // fl (pageable) and h_small are reused by the caller / next call
     int* goff = m->off + (NN + 1); int* gidx = m->idx + cap;
     k_grid_cells<<<(n2 + 127) / 128, 128, 0, st>>>(k1, k1 + cap, n2, A.minX, A.minY, A.invW, A.invH, m->node);
+    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 227 KB)");
     k_build_csr<<<1, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->node, 0, m->ncnt, cap, nc, goff, 0, gidx, 0);
     k_proj_match<<<1, 32, 0, st>>>(A, n1, m->flag, k0, m->desc, reinterpret_cast<const int*>(k0 + 4 * (size_t)cap), k0 + 3 * (size_t)cap,
                                    n2, m->desc + (size_t)cap * 32, k1, k1 + cap, reinterpret_cast<const int*>(k1 + 4 * (size_t)cap), k1 + 2 * (size_t)cap,
@@ -1242,6 +1414,7 @@ int sslpl_search_by_projection_mps(sslpl_matcher* m,
     SSLPL_CUDA(cudaStreamSynchronize(st));                               // pageable staging vectors go out of scope
     int* goff = m->off + (NN + 1); int* gidx = m->idx + cap;
     k_grid_cells<<<(n2 + 127) / 128, 128, 0, st>>>(k1, k1 + cap, n2, A.minX, A.minY, A.invW, A.invH, m->node);
+    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 227 KB)");
     k_build_csr<<<1, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->node, 0, m->ncnt, cap, nc, goff, 0, gidx, 0);
     k_proj_match_mps<<<1, 32, 0, st>>>(A, nmp, m->flag, k0, k0 + cap, k0 + 2 * (size_t)cap, reinterpret_cast<const int*>(k0 + 4 * (size_t)cap), k0 + 3 * (size_t)cap, m->desc,
                                        n2, m->desc + (size_t)cap * 32, k1, k1 + cap, reinterpret_cast<const int*>(k1 + 4 * (size_t)cap), k1 + 3 * (size_t)cap,
@@ -1290,6 +1463,7 @@ int sslpl_search_for_initialization(sslpl_matcher* m,
     SSLPL_CUDA(cudaStreamSynchronize(st));
     int* goff = m->off + (NN + 1); int* gidx = m->idx + cap;
     k_grid_cells<<<(n2 + 127) / 128, 128, 0, st>>>(k1, k1 + cap, n2, A.minX, A.minY, A.invW, A.invH, m->node);
+    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 227 KB)");
     k_build_csr<<<1, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->node, 0, m->ncnt, cap, nc, goff, 0, gidx, 0);
     k_init_match<<<1, 32, 0, st>>>(A, n1, m->desc, reinterpret_cast<const int*>(k0 + 4 * (size_t)cap), k0 + 3 * (size_t)cap, k0, k0 + cap,
                                    n2, m->desc + (size_t)cap * 32, k1, k1 + cap, reinterpret_cast<const int*>(k1 + 4 * (size_t)cap), k1 + 2 * (size_t)cap,
@@ -1309,6 +1483,130 @@ int sslpl_search_for_initialization(sslpl_matcher* m,
 // Frame::GetFeaturesInArea on its own (Frame.cc:368-421) is host logic over the same CSR; the matcher above is its only
 // device consumer.  (The per-frame grid build is k_grid_cells + k_build_csr.)
 
+// ---------------- line projection search and Fuse search ----------------
+static int ensure_scratch(sslpl_matcher* m, size_t need) {           // grow-only scratch shared by the entry points below
+    if (need <= m->scratch_size) return SSLPL_OK;
+    SSLPL_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->scratch) cudaFree(m->scratch);
+    m->scratch = nullptr; m->scratch_size = 0;
+    cudaError_t e = cudaMalloc(&m->scratch, need);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); return SSLPL_ERR_CUDA; }
+    m->scratch_size = need;
+    return SSLPL_OK;
+}
+
+int sslpl_line_search_by_projection(sslpl_matcher* m, int nml, const uint8_t* active, const uint8_t* obs, const float* proj, const float* radius,
+                                    const int32_t* minLevel, const int32_t* maxLevel, const uint8_t* dml,
+                                    int nl2, const uint8_t* ld2, const float* kl2, const int32_t* oct2, const uint8_t* held2,
+                                    float nnratio, int32_t* assign2, int* nmatches) {
+    SSLPL_REQUIRE(m && nmatches && nml >= 0 && nl2 >= 0, SSLPL_ERR_ARG, "null argument");
+    SSLPL_REQUIRE(nml == 0 || (active && proj && radius && minLevel && maxLevel && dml), SSLPL_ERR_ARG, "null MapLine array");
+    SSLPL_REQUIRE(nl2 == 0 || (ld2 && kl2 && oct2 && assign2), SSLPL_ERR_ARG, "null frame-line array");
+    for (int j = 0; j < nl2; j++) assign2[j] = -1;
+    *nmatches = 0;
+    if (nml == 0 || nl2 == 0) return SSLPL_OK;
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    const size_t need = (size_t)nml * (1 + 16 + 4 + 4 + 4 + 32) + (size_t)nl2 * (32 + 12 + 4 + 1 + 4) + 16 * 256 + 4096;
+    if (int rc = ensure_scratch(m, need)) return rc;
+    std::vector<uint8_t> fl(nml), cl(nl2, 0);
+    for (int i = 0; i < nml; i++) fl[i] = (uint8_t)((active[i] ? 1 : 0) | ((obs && obs[i]) ? 2 : 0));
+    if (held2) for (int j = 0; j < nl2; j++) cl[j] = held2[j] == 1;
+    Arena A; A.base = m->scratch; A.used = 0;
+    cudaError_t e = cudaSuccess;
+    uint8_t* d_fl = stage(A, fl.data(), nml, st, e); float* d_proj = stage(A, proj, (size_t)4 * nml, st, e); float* d_rad = stage(A, radius, nml, st, e);
+    int32_t* d_min = stage(A, minLevel, nml, st, e); int32_t* d_max = stage(A, maxLevel, nml, st, e); uint8_t* d_dml = stage(A, dml, (size_t)32 * nml, st, e);
+    uint8_t* d_ld2 = stage(A, ld2, (size_t)32 * nl2, st, e); float* d_kl2 = stage(A, kl2, (size_t)3 * nl2, st, e); int32_t* d_oct = stage(A, oct2, nl2, st, e);
+    uint8_t* d_cl = stage(A, cl.data(), nl2, st, e); int32_t* d_out = A.take<int32_t>(nl2 + 8);
+    SSLPL_CUDA(e);
+    SSLPL_CUDA(cudaStreamSynchronize(st));                               // the pageable staging vectors go out of scope
+    k_line_window_search<<<1, 32, 0, st>>>(nml, d_fl, reinterpret_cast<const float4*>(d_proj), d_rad, d_min, d_max, d_dml, nl2, d_ld2, d_kl2, d_oct, d_cl,
+                                           nnratio, d_out, m->nmatch);
+    m->launches++;
+    SSLPL_CUDA(cudaGetLastError());
+    SSLPL_CUDA(cudaMemcpyAsync(assign2, d_out, sizeof(int32_t) * nl2, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaMemcpyAsync(m->h_small, m->nmatch, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    *nmatches = m->h_small[0];
+    return SSLPL_OK;
+}
+
+int sslpl_fuse_lines_search(sslpl_matcher* m, int nml, const uint8_t* active, const float* proj, const int32_t* level, const uint8_t* dml,
+                            int nl2, const uint8_t* ld2, const float* kl2, const int32_t* oct2, const float* scaleFactors, int nlevels, float th,
+                            int32_t* best_idx, int32_t* best_dist) {
+    SSLPL_REQUIRE(m && nml >= 0 && nl2 >= 0 && scaleFactors && nlevels >= 1 && nlevels <= 32, SSLPL_ERR_ARG, "bad argument");
+    SSLPL_REQUIRE(nml == 0 || (active && proj && level && dml && best_idx && best_dist), SSLPL_ERR_ARG, "null MapLine array");
+    SSLPL_REQUIRE(nl2 == 0 || (ld2 && kl2 && oct2), SSLPL_ERR_ARG, "null KeyFrame-line array");
+    for (int i = 0; i < nml; i++) { best_idx[i] = -1; best_dist[i] = 0x7fffffff; }
+    if (nml == 0 || nl2 == 0) return SSLPL_OK;
+    std::vector<uint8_t> act(nml);
+    for (int i = 0; i < nml; i++) act[i] = active[i] && level[i] >= 0 && level[i] < nlevels;      // MapLine::PredictScale is not clamped: out-of-pyramid levels are dropped
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    const size_t need = (size_t)nml * (1 + 16 + 4 + 32 + 8) + (size_t)nl2 * (32 + 12 + 4) + 16 * 256 + 4096;
+    if (int rc = ensure_scratch(m, need)) return rc;
+    Arena A; A.base = m->scratch; A.used = 0;
+    cudaError_t e = cudaSuccess;
+    uint8_t* d_act = stage(A, act.data(), nml, st, e); float* d_proj = stage(A, proj, (size_t)4 * nml, st, e); int32_t* d_lvl = stage(A, level, nml, st, e);
+    uint8_t* d_dml = stage(A, dml, (size_t)32 * nml, st, e); uint8_t* d_ld2 = stage(A, ld2, (size_t)32 * nl2, st, e);
+    float* d_kl2 = stage(A, kl2, (size_t)3 * nl2, st, e); int32_t* d_oct = stage(A, oct2, nl2, st, e); float* d_sc = stage(A, scaleFactors, nlevels, st, e);
+    int32_t* d_bi = A.take<int32_t>(nml + 8); int32_t* d_bd = A.take<int32_t>(nml + 8);
+    SSLPL_CUDA(e);
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    k_line_fuse_search<<<(nml + 3) / 4, 128, 0, st>>>(nml, d_act, reinterpret_cast<const float4*>(d_proj), d_lvl, d_dml, nl2, d_ld2, d_kl2, d_oct, d_sc, th, d_bi, d_bd);
+    m->launches++;
+    SSLPL_CUDA(cudaGetLastError());
+    SSLPL_CUDA(cudaMemcpyAsync(best_idx, d_bi, sizeof(int32_t) * nml, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaMemcpyAsync(best_dist, d_bd, sizeof(int32_t) * nml, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    return SSLPL_OK;
+}
+
+int sslpl_fuse_points_search(sslpl_matcher* m, int nmp, const uint8_t* active, const float* u, const float* v, const float* ur, const int32_t* level, const uint8_t* dmp,
+                             int n2, const uint8_t* d2, const float* x2, const float* y2, const int32_t* oct2, const float* uright2,
+                             const float* bounds, const float* scaleFactors, const float* invLevelSigma2, int nlevels, float th,
+                             int32_t* best_idx, int32_t* best_dist) {
+    SSLPL_REQUIRE(m && nmp >= 0 && n2 >= 0 && bounds && scaleFactors && invLevelSigma2 && nlevels >= 1 && nlevels <= 32, SSLPL_ERR_ARG, "bad argument");
+    SSLPL_REQUIRE(n2 <= m->cap && m->cap <= 8192 + 64, SSLPL_ERR_ARG, "n2 exceeds the matcher capacity (<= 8192 features)");
+    SSLPL_REQUIRE(m->p.max_nodes >= GRID_COLS * GRID_ROWS, SSLPL_ERR_ARG, "the matcher needs max_nodes >= 3072 (64 x 48 grid cells)");
+    SSLPL_REQUIRE(nmp == 0 || (active && u && v && level && dmp && best_idx && best_dist), SSLPL_ERR_ARG, "null MapPoint array");
+    SSLPL_REQUIRE(n2 == 0 || (d2 && x2 && y2 && oct2), SSLPL_ERR_ARG, "null KeyFrame array");
+    for (int i = 0; i < nmp; i++) { best_idx[i] = -1; best_dist[i] = 256; }
+    if (nmp == 0 || n2 == 0) return SSLPL_OK;
+    for (int i = 0; i < nmp; i++) SSLPL_REQUIRE(!active[i] || (level[i] >= 0 && level[i] < nlevels), SSLPL_ERR_ARG, "predicted level outside the pyramid");
+    SSLPL_CUDA(cudaSetDevice(m->p.device));
+    cudaStream_t st = m->stream;
+    const int cap = m->cap, NN = m->p.max_nodes + 1, nc = GRID_COLS * GRID_ROWS;
+    WinArgs A; fill_win(A, bounds, scaleFactors, nlevels);
+    A.th = th; A.use_right = uright2 ? 1 : 0;
+    const size_t need = (size_t)nmp * (1 + 12 + 4 + 32 + 8) + (size_t)n2 * (32 + 16) + 32 * 4 + 16 * 256 + 4096;
+    if (int rc = ensure_scratch(m, need)) return rc;
+    Arena S; S.base = m->scratch; S.used = 0;
+    cudaError_t e = cudaSuccess;
+    std::vector<float> urz;
+    if (!ur) { urz.assign(nmp, 0.f); ur = urz.data(); }
+    uint8_t* d_act = stage(S, active, nmp, st, e); float* d_u = stage(S, u, nmp, st, e); float* d_v = stage(S, v, nmp, st, e); float* d_ur = stage(S, ur, nmp, st, e);
+    int32_t* d_lvl = stage(S, level, nmp, st, e); uint8_t* d_dmp = stage(S, dmp, (size_t)32 * nmp, st, e);
+    uint8_t* d_d2 = stage(S, d2, (size_t)32 * n2, st, e); float* d_x2 = stage(S, x2, n2, st, e); float* d_y2 = stage(S, y2, n2, st, e);
+    int32_t* d_oct = stage(S, oct2, n2, st, e); float* d_ur2 = stage(S, uright2, uright2 ? n2 : 0, st, e); float* d_is2 = stage(S, invLevelSigma2, nlevels, st, e);
+    int32_t* d_bi = S.take<int32_t>(nmp + 8); int32_t* d_bd = S.take<int32_t>(nmp + 8);
+    m->h_small[0] = n2;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m->ncnt, m->h_small, sizeof(int), cudaMemcpyHostToDevice, st);
+    SSLPL_CUDA(e);
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    int* goff = m->off + (NN + 1); int* gidx = m->idx + cap;
+    k_grid_cells<<<(n2 + 127) / 128, 128, 0, st>>>(d_x2, d_y2, n2, A.minX, A.minY, A.invW, A.invH, m->node);
+    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 227 KB)");
+    k_build_csr<<<1, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->node, 0, m->ncnt, cap, nc, goff, 0, gidx, 0);
+    k_point_fuse_search<<<(nmp + 3) / 4, 128, 0, st>>>(A, nmp, d_act, d_u, d_v, d_ur, d_lvl, d_dmp, d_d2, d_x2, d_y2, d_oct, d_ur2, d_is2, goff, gidx, d_bi, d_bd);
+    m->launches += 3;
+    SSLPL_CUDA(cudaGetLastError());
+    SSLPL_CUDA(cudaMemcpyAsync(best_idx, d_bi, sizeof(int32_t) * nmp, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaMemcpyAsync(best_dist, d_bd, sizeof(int32_t) * nmp, cudaMemcpyDeviceToHost, st));
+    SSLPL_CUDA(cudaStreamSynchronize(st));
+    return SSLPL_OK;
+}
+
 // ---------------- descriptor medoids ----------------
 int sslpl_descriptor_medoid_batch(sslpl_matcher* m, const uint8_t* desc, const int32_t* off, int ngroups, int32_t* best_idx, int32_t* best_median) {
     SSLPL_REQUIRE(m && off && ngroups >= 0 && (ngroups == 0 || (best_idx && best_median)), SSLPL_ERR_ARG, "null argument");
@@ -1319,14 +1617,7 @@ int sslpl_descriptor_medoid_batch(sslpl_matcher* m, const uint8_t* desc, const i
     SSLPL_CUDA(cudaSetDevice(m->p.device));
     cudaStream_t st = m->stream;
     const size_t need = align_up((size_t)total * 32 + 256, 256) + align_up(sizeof(int32_t) * (size_t)(ngroups + 1), 256) + 2 * align_up(sizeof(int32_t) * (size_t)ngroups, 256);
-    if (need > m->scratch_size) {                                        // grow-only scratch of this entry point
-        SSLPL_CUDA(cudaStreamSynchronize(st));
-        if (m->scratch) cudaFree(m->scratch);
-        m->scratch = nullptr; m->scratch_size = 0;
-        cudaError_t e = cudaMalloc(&m->scratch, need);
-        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); return SSLPL_ERR_CUDA; }
-        m->scratch_size = need;
-    }
+    if (int rc = ensure_scratch(m, need)) return rc;
     Arena A; A.base = m->scratch; A.used = 0;
     uint8_t* d_desc = A.take<uint8_t>((size_t)total * 32 + 32); int32_t* d_off = A.take<int32_t>(ngroups + 1);
     int32_t* d_bi = A.take<int32_t>(ngroups); int32_t* d_bm = A.take<int32_t>(ngroups);

@@ -9,6 +9,7 @@
 #include "ORBmatcher.h"
 #include "LSDmatcher.h"
 #include "sslpl.h"
+#include <set>
 #include <stdexcept>
 #include <string>
 
@@ -277,6 +278,233 @@ int LSDmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, vector<pa
     Check(sslpl_line_match(Ctx(), 3, pKF1->mLineDescriptors.ptr<uchar>(), n1, pKF2->mLineDescriptors.ptr<uchar>(), n2, &has1[0], &has2[0], &out[0], &nout, &nmatches, NULL), "sslpl_line_match");
     for(int k=0; k<nout; k++) vMatchedPairs.push_back(make_pair((size_t)out[2*k], (size_t)out[2*k+1]));
     return nmatches;
+}
+
+
+// ---- line projection matchers and Fuse ----
+// Each of these reference functions is a projection stage (per map element: gates + projected quantities) followed by a Hamming search over
+// the frame's features.  The projection stage stays here, written with the reference's own cv::Mat / Eigen expressions and accessors (so its
+// arithmetic IS the reference's: cv::gemm, cv::norm, Mat::dot, MapPoint::PredictScale); the search stage runs on the device
+// (sslpl_line_search_by_projection, sslpl_fuse_lines_search, sslpl_fuse_points_search); Fuse's bookkeeping (Replace / AddObservation) is
+// applied afterwards in vector order, re-testing isBad() / IsInKeyFrame() as the reference's loop would see them at that point.
+namespace {
+struct FlatLines {
+    int n; std::vector<uint8_t> desc, held; std::vector<float> kl; std::vector<int32_t> oct;
+    FlatLines(const std::vector<KeyLine> &v, const cv::Mat &d): n((int)v.size()), desc((size_t)v.size()*32 + 32), held(v.size() + 1, 0), kl(3*v.size() + 3), oct(v.size() + 1) {
+        for(int j=0; j<n; j++) {
+            kl[3*j] = v[j].pt.x; kl[3*j+1] = v[j].pt.y; kl[3*j+2] = v[j].angle; oct[j] = v[j].octave;
+            std::copy(d.ptr<uchar>(j), d.ptr<uchar>(j) + 32, &desc[(size_t)32*j]);
+        }
+    }
+};
+struct LineQueries {
+    std::vector<uint8_t> active, obs, desc; std::vector<float> proj, radius; std::vector<int32_t> minLevel, maxLevel, level;
+    explicit LineQueries(int n): active(n + 1, 0), obs(n + 1, 0), desc((size_t)n*32 + 32, 0), proj(4*(size_t)n + 4, 0.f), radius(n + 1, 0.f), minLevel(n + 1, -1), maxLevel(n + 1, -1), level(n + 1, 0) {}
+    void Set(int i, MapLine* pML, float u1, float v1, float u2, float v2) {
+        active[i] = 1; obs[i] = pML->Observations() > 0 ? 1 : 0;
+        proj[4*i] = u1; proj[4*i+1] = v1; proj[4*i+2] = u2; proj[4*i+3] = v2;
+        const cv::Mat d = pML->GetDescriptor();
+        std::copy(d.ptr<uchar>(), d.ptr<uchar>() + 32, &desc[(size_t)32*i]);
+    }
+};
+// Both end points of a MapLine through Rcw, tcw and the pinhole model; false when either lies behind the camera or outside the image bounds
+// (LSDmatcher.cpp:45-82 = :439-476)
+bool ProjectLine(MapLine* pML, const cv::Mat &Rcw, const cv::Mat &tcw, float fx, float fy, float cx, float cy, float minX, float maxX, float minY, float maxY,
+                 cv::Mat &SP, cv::Mat &EP, float &u1, float &v1, float &u2, float &v2)
+{
+    const Vector6d P = pML->GetWorldPos();
+    SP = (cv::Mat_<float>(3, 1) << P(0), P(1), P(2));
+    EP = (cv::Mat_<float>(3, 1) << P(3), P(4), P(5));
+    const cv::Mat SPc = Rcw * SP + tcw, EPc = Rcw * EP + tcw;
+    const float z1 = SPc.at<float>(2), z2 = EPc.at<float>(2);
+    if(z1 < 0.0f || z2 < 0.0f) return false;
+    const float invz1 = 1.0f / z1;
+    u1 = fx * SPc.at<float>(0) * invz1 + cx; v1 = fy * SPc.at<float>(1) * invz1 + cy;
+    if(u1 < minX || u1 > maxX || v1 < minY || v1 > maxY) return false;
+    const float invz2 = 1.0f / z2;
+    u2 = fx * EPc.at<float>(0) * invz2 + cx; v2 = fy * EPc.at<float>(1) * invz2 + cy;
+    if(u2 < minX || u2 > maxX || v2 < minY || v2 > maxY) return false;
+    return true;
+}
+int RunLineSearch(const LineQueries &Q, int nml, FlatLines &L, float nnratio, std::vector<int32_t> &assign)
+{
+    int nmatches = 0;
+    assign.assign(L.n + 1, -1);
+    Check(sslpl_line_search_by_projection(Ctx(), nml, &Q.active[0], &Q.obs[0], &Q.proj[0], &Q.radius[0], &Q.minLevel[0], &Q.maxLevel[0], &Q.desc[0],
+                                          L.n, &L.desc[0], &L.kl[0], &L.oct[0], &L.held[0], nnratio, &assign[0], &nmatches), "sslpl_line_search_by_projection");
+    return nmatches;
+}
+}
+
+// LSDmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) — LSDmatcher.cpp:22-141
+int LSDmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
+{
+    const int nl1 = LastFrame.NL;
+    if(nl1 == 0 || CurrentFrame.NL == 0) return 0;
+    const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0, 3).colRange(0, 3), tcw = CurrentFrame.mTcw.rowRange(0, 3).col(3);
+    const cv::Mat twc = -Rcw.t()*tcw;
+    const cv::Mat Rlw = LastFrame.mTcw.rowRange(0, 3).colRange(0, 3), tlw = LastFrame.mTcw.rowRange(0, 3).col(3);
+    const cv::Mat tlc = Rlw*twc+tlw;
+    const bool bForward = tlc.at<float>(2)>CurrentFrame.mb && !bMono;
+    const bool bBackward = -tlc.at<float>(2)>CurrentFrame.mb && !bMono;
+    LineQueries Q(nl1);
+    for(int i=0; i<nl1; i++) {
+        MapLine* pML = LastFrame.mvpMapLines[i];
+        if(!pML || pML->isBad() || LastFrame.mvbLineOutlier[i]) continue;
+        cv::Mat SP, EP; float u1, v1, u2, v2;
+        if(!ProjectLine(pML, Rcw, tcw, CurrentFrame.fx, CurrentFrame.fy, CurrentFrame.cx, CurrentFrame.cy,
+                        CurrentFrame.mnMinX, CurrentFrame.mnMaxX, CurrentFrame.mnMinY, CurrentFrame.mnMaxY, SP, EP, u1, v1, u2, v2)) continue;
+        const int nLastOctave = LastFrame.mvKeys[i].octave;            // the POINT keypoint of the same index, as the reference reads it (:84)
+        Q.Set(i, pML, u1, v1, u2, v2);
+        Q.radius[i] = th*CurrentFrame.mvScaleFactors[nLastOctave];
+        if(bForward) { Q.minLevel[i] = nLastOctave; Q.maxLevel[i] = -1; }
+        else if(bBackward) { Q.minLevel[i] = 0; Q.maxLevel[i] = nLastOctave; }
+        else { Q.minLevel[i] = nLastOctave-1; Q.maxLevel[i] = nLastOctave+1; }
+    }
+    FlatLines L(CurrentFrame.mvKeylinesUn, CurrentFrame.mLdesc);
+    for(int j=0; j<L.n; j++) { MapLine* q = CurrentFrame.mvpMapLines[j]; L.held[j] = q ? (q->Observations() > 0 ? 1 : 2) : 0; }
+    std::vector<int32_t> assign;
+    const int nmatches = RunLineSearch(Q, nl1, L, mfNNratio, assign);
+    for(int j=0; j<L.n; j++) if(assign[j] >= 0) CurrentFrame.mvpMapLines[j] = LastFrame.mvpMapLines[assign[j]];
+    return nmatches;
+}
+
+// LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, th) — LSDmatcher.cpp:185-255 (Tracking::SearchLocalLines, Tracking.cc:1783)
+int LSDmatcher::SearchByProjection(Frame &F, const std::vector<MapLine *> &vpMapLines, const float th)
+{
+    const int nml = (int)vpMapLines.size();
+    if(nml == 0 || F.NL == 0) return 0;
+    const bool bFactor = th!=1.0;
+    LineQueries Q(nml);
+    for(int i=0; i<nml; i++) {
+        MapLine* pML = vpMapLines[i];
+        if(!pML || pML->isBad() || !pML->mbTrackInView) continue;
+        const int nPredictLevel = pML->mnTrackScaleLevel;
+        float r = RadiusByViewingCos(pML->mTrackViewCos);
+        if(bFactor) r*=th;
+        Q.Set(i, pML, pML->mTrackProjX1, pML->mTrackProjY1, pML->mTrackProjX2, pML->mTrackProjY2);
+        Q.radius[i] = r*F.mvScaleFactors[nPredictLevel];
+        Q.minLevel[i] = nPredictLevel-1; Q.maxLevel[i] = nPredictLevel;
+    }
+    FlatLines L(F.mvKeylinesUn, F.mLdesc);
+    for(int j=0; j<L.n; j++) { MapLine* q = F.mvpMapLines[j]; L.held[j] = q ? (q->Observations() > 0 ? 1 : 2) : 0; }
+    std::vector<int32_t> assign;
+    const int nmatches = RunLineSearch(Q, nml, L, mfNNratio, assign);
+    for(int j=0; j<L.n; j++) if(assign[j] >= 0) F.mvpMapLines[j] = vpMapLines[assign[j]];
+    return nmatches;
+}
+
+// LSDmatcher::Fuse(KeyFrame*, const vector<MapLine*>&, th) — LSDmatcher.cpp:417-548 (LocalMapping::SearchInNeighbors, LocalMapping.cc:1243, :1264)
+int LSDmatcher::Fuse(KeyFrame *pKF, const vector<MapLine *> &vpMapLines, const float th)
+{
+    const int nml = (int)vpMapLines.size();
+    if(nml == 0 || pKF->NL == 0) return 0;
+    const cv::Mat Rcw = pKF->GetRotation(), tcw = pKF->GetTranslation(), Ow = pKF->GetCameraCenter();
+    LineQueries Q(nml);
+    for(int i=0; i<nml; i++) {
+        MapLine* pML = vpMapLines[i];
+        if(!pML || pML->isBad()) continue;
+        cv::Mat SP, EP; float u1, v1, u2, v2;
+        if(!ProjectLine(pML, Rcw, tcw, pKF->fx, pKF->fy, pKF->cx, pKF->cy, pKF->mnMinX, pKF->mnMaxX, pKF->mnMinY, pKF->mnMaxY, SP, EP, u1, v1, u2, v2)) continue;
+        const float maxDistance = pML->GetMaxDistanceInvariance(), minDistance = pML->GetMinDistanceInvariance();
+        const cv::Mat OM = 0.5 * (SP + EP) - Ow;
+        const float dist = cv::norm(OM);
+        if(dist < minDistance || dist > maxDistance) continue;
+        const Vector3d Pn = pML->GetNormal();
+        const cv::Mat pn = (cv::Mat_<float>(3, 1) << Pn(0), Pn(1), Pn(2));
+        if(OM.dot(pn)<0.5*dist) continue;
+        Q.Set(i, pML, u1, v1, u2, v2);
+        Q.level[i] = pML->PredictScale(dist, pKF->mfLogScaleFactor);   // not clamped by the reference: levels outside the pyramid are dropped by the search
+    }
+    FlatLines L(pKF->mvKeyLines, pKF->mLineDescriptors);
+    std::vector<int32_t> bestIdx(nml + 1, -1), bestDist(nml + 1, 0x7fffffff);
+    Check(sslpl_fuse_lines_search(Ctx(), nml, &Q.active[0], &Q.proj[0], &Q.level[0], &Q.desc[0], L.n, &L.desc[0], &L.kl[0], &L.oct[0],
+                                  &pKF->mvScaleFactors[0], (int)pKF->mvScaleFactors.size(), th, &bestIdx[0], &bestDist[0]), "sslpl_fuse_lines_search");
+    int nFused=0;
+    std::set<MapLine*> recomputed;       // MapLines whose descriptor a Replace() of this loop recomputed (MapLine.cpp:216)
+    for(int i=0; i<nml; i++) {
+        MapLine* pML = vpMapLines[i];
+        if(!Q.active[i] || pML->isBad()) continue;                     // isBad(): an earlier iteration may have replaced it
+        if(recomputed.count(pML)) {                                    // (no IsInKeyFrame test in this function: such a line is searched again, with its new descriptor)
+            const cv::Mat d = pML->GetDescriptor();
+            std::copy(d.ptr<uchar>(), d.ptr<uchar>() + 32, &Q.desc[(size_t)32*i]);
+            Check(sslpl_fuse_lines_search(Ctx(), 1, &Q.active[i], &Q.proj[4*i], &Q.level[i], &Q.desc[(size_t)32*i], L.n, &L.desc[0], &L.kl[0], &L.oct[0],
+                                          &pKF->mvScaleFactors[0], (int)pKF->mvScaleFactors.size(), th, &bestIdx[i], &bestDist[i]), "sslpl_fuse_lines_search");
+        }
+        if(bestIdx[i] < 0 || bestDist[i] > TH_LOW) continue;
+        MapLine* pMLinKF = pKF->GetMapLine(bestIdx[i]);
+        if(pMLinKF) {
+            if(!pMLinKF->isBad()) {
+                if(pMLinKF->Observations()>pML->Observations()) { pML->Replace(pMLinKF); recomputed.insert(pMLinKF); }
+                else { pMLinKF->Replace(pML); recomputed.insert(pML); }
+            }
+        } else {
+            pML->AddObservation(pKF,bestIdx[i]);
+            pKF->AddMapLine(pML,bestIdx[i]);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+
+// ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) — ORBmatcher.cc:828-973 (LocalMapping::SearchInNeighbors, LocalMapping.cc:1206, :1226)
+int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const float th)
+{
+    const int nMPs = (int)vpMapPoints.size(), n2 = pKF->N;
+    if(nMPs == 0 || n2 == 0) return 0;
+    const cv::Mat Rcw = pKF->GetRotation(), tcw = pKF->GetTranslation(), Ow = pKF->GetCameraCenter();
+    const float &fx = pKF->fx, &fy = pKF->fy, &cx = pKF->cx, &cy = pKF->cy, &bf = pKF->mbf;
+    std::vector<uint8_t> active(nMPs, 0), dmp((size_t)nMPs*32, 0), d2((size_t)n2*32);
+    std::vector<float> pu(nMPs, 0.f), pv(nMPs, 0.f), pur(nMPs, 0.f), x2(n2), y2(n2), ur2(n2);
+    std::vector<int32_t> lvl(nMPs, 0), o2(n2), bestIdx(nMPs, -1), bestDist(nMPs, 256);
+    for(int i=0; i<nMPs; i++) {
+        MapPoint* pMP = vpMapPoints[i];
+        if(!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+        const cv::Mat p3Dw = pMP->GetWorldPos();
+        const cv::Mat p3Dc = Rcw*p3Dw + tcw;
+        if(p3Dc.at<float>(2)<0.0f) continue;
+        const float invz = 1/p3Dc.at<float>(2);
+        const float x = p3Dc.at<float>(0)*invz, y = p3Dc.at<float>(1)*invz;
+        const float u = fx*x+cx, v = fy*y+cy;
+        if(!pKF->IsInImage(u,v)) continue;
+        const float maxDistance = pMP->GetMaxDistanceInvariance(), minDistance = pMP->GetMinDistanceInvariance();
+        const cv::Mat PO = p3Dw-Ow;
+        const float dist3D = cv::norm(PO);
+        if(dist3D<minDistance || dist3D>maxDistance) continue;
+        const cv::Mat Pn = pMP->GetNormal();
+        if(PO.dot(Pn)<0.5*dist3D) continue;
+        active[i] = 1; pu[i] = u; pv[i] = v; pur[i] = u-bf*invz; lvl[i] = pMP->PredictScale(dist3D,pKF);
+        const cv::Mat d = pMP->GetDescriptor();
+        std::copy(d.ptr<uchar>(), d.ptr<uchar>() + 32, &dmp[(size_t)32*i]);
+    }
+    bool stereo = false;
+    for(int j=0; j<n2; j++) {
+        const cv::KeyPoint &kp = pKF->mvKeysUn[j];
+        x2[j] = kp.pt.x; y2[j] = kp.pt.y; o2[j] = kp.octave; ur2[j] = pKF->mvuRight[j]; stereo = stereo || ur2[j] >= 0;
+        std::copy(pKF->mDescriptors.ptr<uchar>(j), pKF->mDescriptors.ptr<uchar>(j) + 32, &d2[(size_t)32*j]);
+    }
+    const float bounds[4] = {(float)pKF->mnMinX, (float)pKF->mnMaxX, (float)pKF->mnMinY, (float)pKF->mnMaxY};
+    Check(sslpl_fuse_points_search(Ctx(), nMPs, &active[0], &pu[0], &pv[0], &pur[0], &lvl[0], &dmp[0], n2, &d2[0], &x2[0], &y2[0], &o2[0], stereo ? &ur2[0] : NULL,
+                                   bounds, &pKF->mvScaleFactors[0], &pKF->mvInvLevelSigma2[0], (int)pKF->mvScaleFactors.size(), th, &bestIdx[0], &bestDist[0]),
+          "sslpl_fuse_points_search");
+    int nFused=0;
+    for(int i=0; i<nMPs; i++) {
+        MapPoint* pMP = vpMapPoints[i];
+        // re-test what an earlier iteration may have changed (a duplicate entry fused, or this point replaced): the reference tests it at :847
+        if(!active[i] || bestIdx[i] < 0 || bestDist[i] > TH_LOW || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+        MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx[i]);
+        if(pMPinKF) {
+            if(!pMPinKF->isBad()) {
+                if(pMPinKF->Observations()>pMP->Observations()) pMP->Replace(pMPinKF);
+                else pMPinKF->Replace(pMP);
+            }
+        } else {
+            pMP->AddObservation(pKF,bestIdx[i]);
+            pKF->AddMapPoint(pMP,bestIdx[i]);
+        }
+        nFused++;
+    }
+    return nFused;
 }
 
 } // namespace StructureSLAM

@@ -7,8 +7,8 @@
 //   * the adapters of structure-slam-pointline_b200/host/ (ORBextractor.cc, ExtractLineSegment_b200.cc, matcher_b200.cc, bow_b200.cc);
 //   * libsslpl_b200.so.
 // It then does what Tracking does with them: Frame::Frame(imGray, ...) (Frame.cc:69 -> the adapters' ORB and LSD extraction on the
-// GPU), Frame::ComputeBoW with a DBoW2 vocabulary, KeyFrame construction, ORBmatcher::SearchByBoW / SearchByProjection and
-// LSDmatcher::SearchByProjection through the adapters, and dumps inputs and outputs as .npy files for tests/test_integration_gpu.py,
+// GPU), Frame::ComputeBoW with a DBoW2 vocabulary, KeyFrame construction, ORBmatcher::SearchByBoW / SearchByProjection / Fuse and
+// LSDmatcher::SearchByProjection (KeyFrame and MapLine forms) / Fuse through the adapters, and dumps inputs and outputs as .npy files for tests/test_integration_gpu.py,
 // which holds them against the fixtures frozen from the reference and against oracle/_ref.
 #include <cstdio>
 #include <cstdint>
@@ -147,6 +147,101 @@ int main(int argc, char** argv) {
         for (int j = 0; j < F2.NL; j++) o[j] = m[j] ? lindex[m[j]] : -1;
         o[F2.NL] = n;
         npy(out, "line_match2", "<i4", o.data(), 4, {o.size()});
+    }
+    // ---- SURVEY.md 8(f) row 3 through the adapters: Fuse (points, lines) and LSDmatcher::SearchByProjection(Frame&, MapLines) ----
+    std::fill(F2.mvpMapPoints.begin(), F2.mvpMapPoints.end(), static_cast<MapPoint*>(NULL));     // forget the tracking matches made above
+    std::fill(F2.mvpMapLines.begin(), F2.mvpMapLines.end(), static_cast<MapLine*>(NULL));
+    KeyFrame* KF2 = new KeyFrame(F2, &map, &db);                     // pose = the Tcw set above
+    {   // ORBmatcher::Fuse(KeyFrame*, vector<MapPoint*>) — LocalMapping::SearchInNeighbors (LocalMapping.cc:1206)
+        std::vector<MapPoint*> mps(F1.mvpMapPoints);
+        std::vector<float> nrm((size_t)3 * F1.N, 0.f), dmin(F1.N, 0.f), dmax(F1.N, 0.f);
+        for (auto& kv : index) {
+            MapPoint* p = kv.first;
+            if (!p->isBad()) p->UpdateNormalAndDepth();                // MapPoint.cc:314-358: normal, mfMinDistance, mfMaxDistance from its observation in KF
+            const int i = kv.second;
+            for (int k = 0; k < 3; k++) nrm[3 * i + k] = p->mNormalVector.empty() ? 0.f : p->mNormalVector.at<float>(k);
+            dmin[i] = p->mfMinDistance; dmax[i] = p->mfMaxDistance;
+        }
+        npy(out, "fuse_normal", "<f4", nrm.data(), 4, {(size_t)F1.N, 3});
+        npy(out, "fuse_dmin", "<f4", dmin.data(), 4, {dmin.size()}); npy(out, "fuse_dmax", "<f4", dmax.data(), 4, {dmax.size()});
+        std::vector<int32_t> kfobs(F2.N, -1);
+        for (int j = 0; j < F2.N; j += 7) {                           // some KeyFrame features already hold a MapPoint (the Replace branch)
+            cv::Mat X = (cv::Mat_<float>(3, 1) << 0.f, 0.f, 1000.f);
+            MapPoint* q = new MapPoint(X, KF2, &map);
+            F2.mDescriptors.row(j).copyTo(q->mDescriptor);
+            q->AddObservation(KF2, j); KF2->AddMapPoint(q, j); kfobs[j] = 0;
+        }
+        npy(out, "fuse_kfobs", "<i4", kfobs.data(), 4, {kfobs.size()});
+        ORBmatcher matcher(0.6f, true);
+        const int n = matcher.Fuse(KF2, mps, 3.0f);
+        std::vector<int32_t> o(F1.N + 1, -1);
+        for (int i = 0; i < F1.N; i++) {
+            MapPoint* p = mps[i];
+            if (!p || state[i] != 1) continue;
+            int hops = 0;
+            while (p && p->isBad() && hops++ < 8) p = p->GetReplaced();
+            if (p && !p->isBad() && p->IsInKeyFrame(KF2)) o[i] = p->GetIndexInKeyFrame(KF2);
+        }
+        o[F1.N] = n;
+        npy(out, "fuse_idx", "<i4", o.data(), 4, {o.size()});
+    }
+    {   // LSDmatcher::Fuse(KeyFrame*, vector<MapLine*>) (LocalMapping.cc:1243) and LSDmatcher::SearchByProjection(Frame&, MapLines, th) (Tracking.cc:1783)
+        const int nl = F1.NL;
+        std::vector<MapLine*> mls(nl, static_cast<MapLine*>(NULL));
+        std::vector<double> pw((size_t)6 * nl, 0.0), nrm((size_t)3 * nl, 0.0);
+        std::vector<float> dmin(nl, 0.f), dmax(nl, 0.f), proj((size_t)4 * nl, 0.f);
+        std::vector<uint8_t> lstate(nl, 0);
+        for (int i = 0; i < nl; i++) if (i % 9 != 4) {
+            const KeyLine& k = F1.mvKeylinesUn[i];
+            const double z = 2.0 + 0.01 * i;
+            Vector6d P;
+            P << (double)(float)((k.startPointX - 319.5f) / 481.2f * z), (double)(float)((k.startPointY - 239.5f) / 480.f * z), (double)(float)z,
+                 (double)(float)((k.endPointX - 319.5f) / 481.2f * z), (double)(float)((k.endPointY - 239.5f) / 480.f * z), (double)(float)z;
+            MapLine* l = new MapLine(P, KF, &map);
+            F1.mLdesc.row(i).copyTo(l->mLDescriptor);
+            l->AddObservation(KF, i);
+            Vector3d mid; mid << 0.5 * (P(0) + P(3)), 0.5 * (P(1) + P(4)), 0.5 * (P(2) + P(5));
+            const double d = mid.norm();
+            l->mNormalVector << (double)(float)(mid(0) / d), (double)(float)(mid(1) / d), (double)(float)(mid(2) / d);
+            l->mfMaxDistance = (float)(d * (i % 3 == 0 ? 1.15 : 1.0)); l->mfMinDistance = l->mfMaxDistance / 3.f;   // predicted level 1 or 0
+            l->mbTrackInView = (i % 11 != 7); l->mnTrackScaleLevel = 0; l->mTrackViewCos = (i % 2) ? 0.9999f : 0.9f;
+            l->mTrackProjX1 = k.startPointX; l->mTrackProjY1 = k.startPointY; l->mTrackProjX2 = k.endPointX; l->mTrackProjY2 = k.endPointY;
+            if (i % 13 == 6) l->mbBad = true;
+            mls[i] = l; lstate[i] = l->mbBad ? 2 : 1;
+            for (int c = 0; c < 6; c++) pw[6 * i + c] = P(c);
+            for (int c = 0; c < 3; c++) nrm[3 * i + c] = l->mNormalVector(c);
+            dmin[i] = l->mfMinDistance; dmax[i] = l->mfMaxDistance;
+            proj[4 * i] = k.startPointX; proj[4 * i + 1] = k.startPointY; proj[4 * i + 2] = k.endPointX; proj[4 * i + 3] = k.endPointY;
+        }
+        npy(out, "lfuse_state", "|u1", lstate.data(), 1, {lstate.size()}); npy(out, "lfuse_pw", "<f8", pw.data(), 8, {(size_t)nl, 6});
+        npy(out, "lfuse_normal", "<f8", nrm.data(), 8, {(size_t)nl, 3}); npy(out, "lfuse_dmin", "<f4", dmin.data(), 4, {dmin.size()});
+        npy(out, "lfuse_dmax", "<f4", dmax.data(), 4, {dmax.size()}); npy(out, "lproj", "<f4", proj.data(), 4, {(size_t)nl, 4});
+        {   // SearchByProjection(Frame&, MapLines) first: it only writes F2.mvpMapLines
+            LSDmatcher lm(0.8f, true);
+            std::fill(F2.mvpMapLines.begin(), F2.mvpMapLines.end(), static_cast<MapLine*>(NULL));
+            const int n = lm.SearchByProjection(F2, mls, 3.0f);
+            std::map<MapLine*, int> li; for (int i = 0; i < nl; i++) if (mls[i]) li[mls[i]] = i;
+            std::vector<int32_t> o(F2.NL + 1, -1);
+            for (int j = 0; j < F2.NL; j++) o[j] = F2.mvpMapLines[j] ? li[F2.mvpMapLines[j]] : -1;
+            o[F2.NL] = n;
+            npy(out, "lproj_assign2", "<i4", o.data(), 4, {o.size()});
+        }
+        std::vector<int32_t> kfobs(F2.NL, -1);
+        Vector6d P0; P0 << 0.0, 0.0, 1.0, 1.0, 0.0, 1.0;
+        for (int j = 0; j < F2.NL; j += 5) { MapLine* q = new MapLine(P0, KF2, &map); F2.mLdesc.row(j).copyTo(q->mLDescriptor); q->AddObservation(KF2, j); KF2->AddMapLine(q, j); kfobs[j] = 0; }
+        npy(out, "lfuse_kfobs", "<i4", kfobs.data(), 4, {kfobs.size()});
+        LSDmatcher lm(0.6f, true);
+        const int n = lm.Fuse(KF2, mls, 10.0f);
+        std::vector<int32_t> o(nl + 1, -1);
+        for (int i = 0; i < nl; i++) {
+            MapLine* l = mls[i];
+            if (!l || lstate[i] != 1) continue;
+            int hops = 0;
+            while (l && l->isBad() && hops++ < 8) l = l->GetReplaced();
+            if (l && !l->isBad() && l->IsInKeyFrame(KF2)) o[i] = l->GetIndexInKeyFrame(KF2);
+        }
+        o[nl] = n;
+        npy(out, "lfuse_idx", "<i4", o.data(), 4, {o.size()});
     }
     printf("ref_link_test ok: N=%d/%d NL=%d/%d\n", F1.N, F2.N, F1.NL, F2.NL);
     return 0;

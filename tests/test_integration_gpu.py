@@ -65,3 +65,26 @@ def test_reference_objects_plus_adapters_on_the_gpu(pkg, oracle, icl_gray, tmp_p
     n_r, m_r, _ = R.line_match(0, L("f1_ldesc"), L("f2_ldesc"), L("has_ml1"), None)
     got = L("line_match2")
     assert got[-1] == n_r and np.array_equal(got[:-1], m_r)
+    # ---- SURVEY.md 8(f) row 3 through the adapters, against the reference's own bodies (oracle/_ref) on the inputs the program dumped
+    state = L("state1")
+    mp = dict(state=state, nobs=np.ones(len(state), np.int32), Xw=L("proj_Xw"), normal=L("fuse_normal"), min_raw=L("fuse_dmin"), max_raw=L("fuse_dmax"), desc=d1)
+    kf = dict(desc=d2, kps=k2, uright=None, kfobs=L("fuse_kfobs"))
+    n_r, f_r, _ = R.fuse_points(mp, kf, np.vstack([Tcw, [0, 0, 0, 1]]).astype(np.float32), camv, 0.0, 8, 1.2, 3.0)
+    got = L("fuse_idx")
+    assert got[-1] == n_r and np.array_equal(got[:-1], f_r) and n_r > 300, (got[-1], n_r, int((got[:-1] != f_r).sum()))
+    kl2 = L("f2_keylines").view(pkg.KEYLINE_DTYPE)
+    cur = dict(ld=L("f2_ldesc"), kl=np.stack([kl2["pt_x"], kl2["pt_y"], kl2["angle"]], 1), oct=kl2["octave"].astype(np.int32), held=None)
+    ls = L("lfuse_state")
+    ml = dict(inview=np.array([(i % 11 != 7) for i in range(len(ls))], np.uint8) * (ls > 0), bad=(ls == 2).astype(np.uint8), obs=(ls > 0).astype(np.uint8),
+              proj=L("lproj"), level=np.zeros(len(ls), np.int32), viewcos=np.where(np.arange(len(ls)) % 2, 0.9999, 0.9).astype(np.float32), desc=L("f1_ldesc"))
+    keep = np.nonzero(ls > 0)[0]                                       # the program passes NULL for the others; the harness has no NULL entries
+    mlk = {k: v[keep] for k, v in ml.items()}
+    n_r, a_r = R.line_projection_mls(mlk, cur, camv, 8, 1.2, 0.8, 3.0)
+    got = L("lproj_assign2")
+    assert got[-1] == n_r and np.array_equal(got[:-1], np.where(a_r >= 0, keep[np.maximum(a_r, 0)], -1)) and n_r > 5, (got[-1], n_r)
+    mlf = dict(state=np.where(ls == 1, 1, np.where(ls == 2, 2, 0)).astype(np.uint8), nobs=np.ones(len(ls), np.int32), Pw=L("lfuse_pw"), normal=L("lfuse_normal"),
+               min_raw=L("lfuse_dmin"), max_raw=L("lfuse_dmax"), desc=L("f1_ldesc"))
+    kfl = dict(ld=cur["ld"], kl=cur["kl"], oct=cur["oct"], kfobs=L("lfuse_kfobs"))
+    n_r, f_r, _ = R.fuse_lines(mlf, kfl, np.vstack([Tcw, [0, 0, 0, 1]]).astype(np.float32), camv, 8, 1.2, 10.0)
+    got = L("lfuse_idx")
+    assert got[-1] == n_r and np.array_equal(got[:-1], f_r) and n_r > 5, (got[-1], n_r, int((got[:-1] != f_r).sum()))

@@ -69,3 +69,50 @@ def test_oracle_frame_lines_equal_reference_fixtures(oracle, icl_gray):
     order = np.lexsort((np.arange(len(k)), gy, gx))
     order = order[(gx[order] >= 0) & (gx[order] < 64) & (gy[order] >= 0) & (gy[order] < 48)]
     assert np.array_equal(order, g["grid_idx"])
+
+
+def row3_cases(oracle, synth):
+    """The scenarios tools/make_ref_golden.py froze the reference on, with the oracle's projection stage
+    applied: name -> (search arguments for the search stage, expected result keys in ref_row3.npz)."""
+    from scenarios import line_scenario, local_lines_scenario, fuse_points_scenario, fuse_lines_scenario
+    g = load("ref_row3.npz")
+    c = {}
+    sc = line_scenario(oracle, synth, 2, f0=2, stereo_sign=1)
+    last, cur = sc["last"], sc["cur"]
+    q = oracle.line_project_frame(last["state"] == 1, last["Pw"], last["oct"], sc["Tcw"][:3], sc["Tlw"][:3], sc["cam5"], sc["bounds"], sc["sf"], 20.0, False)
+    c["lpf"] = ((q, last["obs"], last["dml"], cur["ld"], cur["kl"], cur["oct"], cur["held"], 0.8), int(g["lpf_n"]), g["lpf_assign"])
+    ml, cur, sf = local_lines_scenario(oracle, synth, 2, f0=2)
+    q = oracle.line_project_mls(ml["inview"], ml["bad"], ml["level"], ml["viewcos"], sf, 3.0); q["proj"] = ml["proj"]
+    c["lpm"] = ((q, ml["obs"], ml["desc"], cur["ld"], cur["kl"], cur["oct"], cur["held"], 0.8), int(g["lpm_n"]), g["lpm_assign"])
+    for tag, stereo in (("mono", False), ("stereo", True)):
+        sc = fuse_points_scenario(oracle, synth, 2, f0=2, stereo=stereo)
+        mp, kf = sc["mp"], sc["kf"]
+        q = oracle.fuse_project_points(mp["state"] != 1, mp["Xw"], mp["normal"], g[f"fp_{tag}_min_inv"], g[f"fp_{tag}_max_inv"], mp["max_raw"], sc["Tcw"][:3],
+                                       g[f"fp_{tag}_Ow"], sc["cam5"], sc["bounds"], 8, float(g[f"fp_{tag}_log_scale"]))
+        c[f"fp_{tag}"] = ((q, mp["desc"], kf["desc"], kf["x"], kf["y"], kf["oct"], kf["uright"], sc["bounds"], sc["sf"], sc["inv_sigma2"], 3.0),
+                          int(g[f"fp_{tag}_n"]), g[f"fp_{tag}_idx"])
+    sc = fuse_lines_scenario(oracle, synth, 2, f0=2)
+    ml, kf = sc["ml"], sc["kf"]
+    q = oracle.fuse_project_lines(g["fl_state"] != 1, ml["Pw"], ml["normal"], g["fl_min_inv"], g["fl_max_inv"], ml["max_raw"], sc["Tcw"][:3], g["fl_Ow"],
+                                  sc["cam5"], sc["bounds"], 8, float(g["fl_log_scale"]))
+    c["fl"] = ((q, ml["desc"], kf["ld"], kf["kl"], kf["oct"], sc["sf"], 10.0), int(g["fl_n"]), g["fl_idx"])
+    return c
+
+
+def fused_from(q, bi, bd):
+    return np.where((np.asarray(q["active"]) != 0) & (bd <= 50) & (bi >= 0), bi, -1)
+
+
+def test_oracle_row3_equals_reference_fixtures(oracle, synth):
+    c = row3_cases(oracle, synth)
+    for k in ("lpf", "lpm"):
+        args, n, a = c[k]
+        n_o, a_o = oracle.line_window_search(*args)
+        assert n_o == n and np.array_equal(a_o, a), k
+    for k in ("fp_mono", "fp_stereo"):
+        args, n, f = c[k]
+        f_o = fused_from(args[0], *oracle.fuse_points_search(*args))
+        assert np.array_equal(f_o, f) and n == (f >= 0).sum(), k
+    args, n, f = c["fl"]
+    f_o = fused_from(args[0], *oracle.fuse_lines_search(*args))
+    assert np.array_equal(f_o, f) and n == (f >= 0).sum()

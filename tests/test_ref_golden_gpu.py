@@ -57,3 +57,22 @@ def test_gpu_frame_lines_equal_reference_fixtures(pkg, icl_gray):
     for fld in ("startPointX", "startPointY", "endPointX", "endPointY", "pt_x", "pt_y"):
         assert np.max(np.abs(kl[fld] - gk[fld])) <= 1e-4, fld
     assert np.max(np.abs(kl["angle"] - gk["angle"])) <= 1e-3 and np.allclose(eq, g["lineeq"], rtol=1e-9, atol=1e-9)
+
+
+def test_gpu_row3_equals_reference_fixtures(pkg, oracle, synth):
+    """Line projection matchers and Fuse: the device search stage on the frozen scenarios (the oracle only
+    prepares the projection-stage inputs, as the adapter does with the reference's own accessors) against the reference's results."""
+    from test_ref_golden_cpu import row3_cases, fused_from
+    c = row3_cases(oracle, synth)
+    mt = pkg.Matcher(max_features=2048, max_lines=512, max_nodes=3072)
+    for k in ("lpf", "lpm"):
+        args, n, a = c[k]
+        n_g, a_g = mt.line_search_by_projection(*args)
+        assert n_g == n and np.array_equal(a_g, a), k
+    for k in ("fp_mono", "fp_stereo"):
+        args, n, f = c[k]
+        f_g = fused_from(args[0], *mt.fuse_points_search(*args))
+        assert np.array_equal(f_g, f) and n == (f >= 0).sum(), k
+    args, n, f = c["fl"]
+    f_g = fused_from(args[0], *mt.fuse_lines_search(*args))
+    assert np.array_equal(f_g, f) and n == (f >= 0).sum()

@@ -381,3 +381,86 @@ def test_frame_constructor(oracle, ref, icl_gray):
     for c, r in [(0, 0), (10, 7), (32, 24), (63, 47), (40, 13)]:
         cell = fr["grid_idx"][fr["grid_off"][c * 48 + r]:fr["grid_off"][c * 48 + r + 1]]
         assert np.array_equal(cell, np.flatnonzero((gx == c) & (gy == r)))
+
+
+# ------------------------------------------------------------------------------------------------
+# line projection matchers and Fuse
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,th,mono,sign,ratio", [(1, 20.0, True, 0, 0.8), (2, 20.0, False, 1, 0.8), (3, 40.0, False, -1, 0.9), (4, 10.0, True, 0, 0.6)])
+def test_line_search_by_projection_frame(oracle, ref, synth, seed, th, mono, sign, ratio):
+    """LSDmatcher::SearchByProjection(Frame& Current, const Frame& Last, th, bMono) :22-141, forward / backward / mono level ranges."""
+    from scenarios import line_scenario
+    sc = line_scenario(oracle, synth, seed, f0=seed, stereo_sign=sign)
+    last, cur = sc["last"], sc["cur"]
+    q = oracle.line_project_frame(last["state"] == 1, last["Pw"], last["oct"], sc["Tcw"][:3], sc["Tlw"][:3], sc["cam5"], sc["bounds"], sc["sf"], th, mono)
+    n_o, a_o = oracle.line_window_search(q, last["obs"], last["dml"], cur["ld"], cur["kl"], cur["oct"], cur["held"], ratio)
+    cam = ref.cam(*sc["cam5"][:4], *sc["bounds"])
+    n_r, a_r = ref.line_projection_frame(last, cur, sc["Tcw"], sc["Tlw"], cam, sc["cam5"][4], 8, 1.2, ratio, th, mono)
+    assert n_r == n_o and np.array_equal(np.where(a_r == -2, -1, a_r), a_o), (n_r, n_o, int((a_r != a_o).sum()))
+    assert n_o > 5 and q["active"].sum() > 100
+
+
+@pytest.mark.parametrize("seed,th,ratio", [(1, 1.0, 0.8), (2, 3.0, 0.8), (3, 1.0, 0.6), (4, 0.5, 0.9)])
+def test_line_search_by_projection_mls(oracle, ref, synth, seed, th, ratio):
+    """LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, th) :185-255 — Tracking::SearchLocalLines (Tracking.cc:1783)."""
+    from scenarios import local_lines_scenario
+    ml, cur, sf = local_lines_scenario(oracle, synth, seed, f0=seed)
+    q = oracle.line_project_mls(ml["inview"], ml["bad"], ml["level"], ml["viewcos"], sf, th); q["proj"] = ml["proj"]
+    n_o, a_o = oracle.line_window_search(q, ml["obs"], ml["desc"], cur["ld"], cur["kl"], cur["oct"], cur["held"], ratio)
+    n_r, a_r = ref.line_projection_mls(ml, cur, ref.cam(500, 500, 320, 240, 0, 640, 0, 480), 8, 1.2, ratio, th)
+    assert n_r == n_o and np.array_equal(np.where(a_r == -2, -1, a_r), a_o), (n_r, n_o, int((a_r != a_o).sum()))
+    assert n_o > 30
+    if seed == 1:
+        for mod in ("none_in_view", "all_held", "no_obs"):
+            m2, c2 = dict(ml), dict(cur)
+            if mod == "none_in_view": m2["inview"] = np.zeros_like(ml["inview"])
+            if mod == "all_held": c2["held"] = np.ones(len(cur["oct"]), np.uint8)
+            if mod == "no_obs": m2["obs"] = np.zeros_like(ml["obs"])
+            q = oracle.line_project_mls(m2["inview"], m2["bad"], m2["level"], m2["viewcos"], sf, th); q["proj"] = m2["proj"]
+            n_o, a_o = oracle.line_window_search(q, m2["obs"], m2["desc"], c2["ld"], c2["kl"], c2["oct"], c2["held"], ratio)
+            n_r, a_r = ref.line_projection_mls(m2, c2, ref.cam(500, 500, 320, 240, 0, 640, 0, 480), 8, 1.2, ratio, th)
+            assert n_r == n_o and np.array_equal(np.where(a_r == -2, -1, a_r), a_o), mod
+
+
+def _fused(bi, bd, active):
+    return np.where((np.asarray(active) != 0) & (bd <= 50) & (bi >= 0), bi, -1)
+
+
+@pytest.mark.parametrize("seed,th,stereo", [(1, 3.0, False), (2, 3.0, True), (3, 5.0, False), (4, 1.5, True)])
+def test_fuse_points(oracle, ref, synth, seed, th, stereo):
+    """ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) :828-973 (LocalMapping::SearchInNeighbors): projection gates, PredictScale,
+    chi-square gates (mono / stereo), nearest descriptor; every fused MapPoint ends up at (or is replaced into) the feature the search chose."""
+    from scenarios import fuse_points_scenario
+    sc = fuse_points_scenario(oracle, synth, seed, f0=seed, stereo=stereo)
+    mp, kf = sc["mp"], sc["kf"]
+    cam = ref.cam(*sc["cam5"][:4], *sc["bounds"])
+    n_r, f_r, acc = ref.fuse_points(mp, kf, sc["Tcw"], cam, sc["cam5"][4], 8, 1.2, th)
+    q = oracle.fuse_project_points(mp["state"] != 1, mp["Xw"], mp["normal"], acc["min_inv"], acc["max_inv"], mp["max_raw"], sc["Tcw"][:3], acc["Ow"],
+                                   sc["cam5"], sc["bounds"], 8, acc["log_scale"])
+    bi, bd = oracle.fuse_points_search(q, mp["desc"], kf["desc"], kf["x"], kf["y"], kf["oct"], kf["uright"], sc["bounds"], sc["sf"], sc["inv_sigma2"], th)
+    f_o = _fused(bi, bd, q["active"])
+    assert np.array_equal(f_r, f_o), (int((f_r != f_o).sum()), np.nonzero(f_r != f_o)[0][:8])
+    assert n_r == int((f_o >= 0).sum())
+    assert n_r > 150 and q["active"].sum() < (mp["state"] == 1).sum()          # the gates dropped some
+
+
+@pytest.mark.parametrize("seed,th", [(1, 3.0), (2, 5.0), (3, 10.0)])
+def test_fuse_lines(oracle, ref, synth, seed, th):
+    """LSDmatcher::Fuse(KeyFrame*, const vector<MapLine*>&, th) :417-548."""
+    from scenarios import fuse_lines_scenario
+    sc = fuse_lines_scenario(oracle, synth, seed, f0=seed)
+    ml, kf = sc["ml"], sc["kf"]
+    cam = ref.cam(*sc["cam5"][:4], *sc["bounds"])
+    # MapLine::PredictScale is not clamped (MapLine.cpp:386-395): a level outside the pyramid makes the reference read mvScaleFactors out of
+    # bounds, so the comparison keeps to lines whose level is inside (the oracle and the product drop the others)
+    q0 = oracle.fuse_project_lines(ml["state"] != 1, ml["Pw"], ml["normal"], ml["min_raw"] * np.float32(0.8), ml["max_raw"] * np.float32(1.2), ml["max_raw"],
+                                   sc["Tcw"][:3], np.zeros(3), sc["cam5"], sc["bounds"], 8, np.log(np.float32(1.2)))
+    ml = dict(ml); ml["state"] = np.where((q0["level"] < 0) | (q0["level"] >= 8), 0, ml["state"]).astype(np.uint8)
+    n_r, f_r, acc = ref.fuse_lines(ml, kf, sc["Tcw"], cam, 8, 1.2, th)
+    q = oracle.fuse_project_lines(ml["state"] != 1, ml["Pw"], ml["normal"], acc["min_inv"], acc["max_inv"], ml["max_raw"], sc["Tcw"][:3], acc["Ow"],
+                                  sc["cam5"], sc["bounds"], 8, acc["log_scale"])
+    bi, bd = oracle.fuse_lines_search(q, ml["desc"], kf["ld"], kf["kl"], kf["oct"], sc["sf"], th)
+    f_o = _fused(bi, bd, q["active"])
+    assert np.array_equal(f_r, f_o), (int((f_r != f_o).sum()), np.nonzero(f_r != f_o)[0][:8])
+    assert n_r == int((f_o >= 0).sum())
+    assert n_r > 10

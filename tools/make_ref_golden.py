@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools")); sys.p
 import cv2
 import synth
 from oracle import oracle as O, ref as R
-from scenarios import projection_scenario
+from scenarios import projection_scenario, line_scenario, local_lines_scenario, fuse_points_scenario, fuse_lines_scenario
 
 G = os.path.join(ROOT, "tests", "golden")
 
@@ -77,10 +77,40 @@ def main():
     fr = R.frame_from_image(icl)
     np.savez_compressed(os.path.join(G, "ref_frame.npz"), keylines=fr["keylines"], ldesc=fr["ldesc"], lineeq=fr["lineeq"],
                         grid_off=fr["grid_off"], grid_idx=fr["grid_idx"])
-    for f in ("ref_orb.npz", "ref_match.npz", "ref_frame.npz"):
+    row3()
+    for f in ("ref_orb.npz", "ref_match.npz", "ref_frame.npz", "ref_row3.npz"):
         p = os.path.join(G, f)
         print(f, os.path.getsize(p), hashlib.sha1(open(p, "rb").read()).hexdigest()[:12])
 
 
+def row3():
+    """the reference's line projection matchers and Fuse on the deterministic scenarios of tests/scenarios.py"""
+    r = {}
+    sc = line_scenario(O, synth, 2, f0=2, stereo_sign=1)
+    cam = R.cam(*sc["cam5"][:4], *sc["bounds"])
+    n, a = R.line_projection_frame(sc["last"], sc["cur"], sc["Tcw"], sc["Tlw"], cam, sc["cam5"][4], 8, 1.2, 0.8, 20.0, False)
+    r["lpf_n"] = np.int32(n); r["lpf_assign"] = np.where(a == -2, -1, a)
+    ml, cur, sf = local_lines_scenario(O, synth, 2, f0=2)
+    n, a = R.line_projection_mls(ml, cur, R.cam(500, 500, 320, 240, 0, 640, 0, 480), 8, 1.2, 0.8, 3.0)
+    r["lpm_n"] = np.int32(n); r["lpm_assign"] = np.where(a == -2, -1, a)
+    for tag, stereo in (("mono", False), ("stereo", True)):
+        sc = fuse_points_scenario(O, synth, 2, f0=2, stereo=stereo)
+        n, f, acc = R.fuse_points(sc["mp"], sc["kf"], sc["Tcw"], R.cam(*sc["cam5"][:4], *sc["bounds"]), sc["cam5"][4], 8, 1.2, 3.0)
+        r[f"fp_{tag}_n"] = np.int32(n); r[f"fp_{tag}_idx"] = f
+        r[f"fp_{tag}_Ow"] = acc["Ow"]; r[f"fp_{tag}_min_inv"] = acc["min_inv"]; r[f"fp_{tag}_max_inv"] = acc["max_inv"]; r[f"fp_{tag}_log_scale"] = np.float32(acc["log_scale"])
+    sc = fuse_lines_scenario(O, synth, 2, f0=2)
+    ml = dict(sc["ml"])
+    q0 = O.fuse_project_lines(ml["state"] != 1, ml["Pw"], ml["normal"], ml["min_raw"] * np.float32(0.8), ml["max_raw"] * np.float32(1.2), ml["max_raw"],
+                              sc["Tcw"][:3], np.zeros(3), sc["cam5"], sc["bounds"], 8, np.log(np.float32(1.2)))
+    ml["state"] = np.where((q0["level"] < 0) | (q0["level"] >= 8), 0, ml["state"]).astype(np.uint8)      # keep to levels inside the pyramid (see the test)
+    n, f, acc = R.fuse_lines(ml, sc["kf"], sc["Tcw"], R.cam(*sc["cam5"][:4], *sc["bounds"]), 8, 1.2, 10.0)
+    r["fl_state"] = ml["state"]; r["fl_n"] = np.int32(n); r["fl_idx"] = f
+    r["fl_Ow"] = acc["Ow"]; r["fl_min_inv"] = acc["min_inv"]; r["fl_max_inv"] = acc["max_inv"]; r["fl_log_scale"] = np.float32(acc["log_scale"])
+    np.savez_compressed(os.path.join(G, "ref_row3.npz"), **r)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "row3":
+        row3()
+    else:
+        main()
