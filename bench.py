@@ -444,6 +444,37 @@ def main():
         gather_check = {"rows_of_this_rank_equal_local_table": mine_ok, "all_ranks_hold_the_same_tables": bool(hmin.item() == hmax.item()),
                         "ok_on_every_rank": bool(okt.item()), "checksum": int(hsh.item())}
 
+    # ---- the same small job at every N ("gathered tables bit-equal to the 1-GPU run"): 64 frame pairs of the
+    # synthetic sequence 0..64, split into world contiguous blocks (+ one halo frame each), extracted, matched, all-gathered; the
+    # checksum of the gathered [64, cap + NL] table does not depend on N, so the lines printed at N = 1, 2, 4, 8 must agree on it.
+    table_check = None
+    if 64 % world == 0:
+        G = 64; per = G // world
+        d_chk = torch.from_numpy(synth.batch(W, H, per + 1, start=rank * per)).to(dev)
+        t_pts = torch.full((per, cap), -1, dtype=torch.int32, device=dev); t_np = torch.zeros((per,), dtype=torch.int32, device=dev)
+        t_lin = torch.full((per, max(NL, 1)), -1, dtype=torch.int32, device=dev); t_nl = torch.zeros((per,), dtype=torch.int32, device=dev)
+        ext.extract_batch_device(d_chk.data_ptr(), per + 1, W, H, W, W * H)
+        kps_, desc_, n_, c_ = ext.device_results()
+        mt.match_bow_batch_device(desc_, kps_, n_, per + 1, c_, d_voc.data_ptr(), NWORDS, NNRATIO, True, t_pts.data_ptr(), t_np.data_ptr())
+        if LINES:
+            s_lin[0].wait_stream(s_pts)
+            lsr[0].extract_batch_device(d_chk.data_ptr(), per + 1, W, H, W, W * H)
+            _, ld_, _, nl_, capl_ = lsr[0].device_results()
+            lmr[0].match_lines_batch_device(ld_, nl_, per + 1, capl_, t_lin.data_ptr(), t_nl.data_ptr())
+            s_pts.wait_stream(s_lin[0])
+        packed = torch.cat([t_pts, t_lin[:, :NL]], 1).contiguous() if LINES else t_pts
+        if world > 1:
+            full = torch.empty((G, packed.shape[1]), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(full, packed)
+        else:
+            full = packed
+        wts = torch.arange(1, full.numel() + 1, device=dev, dtype=torch.int64).view_as(full)
+        table_check = {"frames": "synthetic 0..64 (64 pairs), %d per GPU + 1 halo" % per, "rows": G, "cols": int(full.shape[1]),
+                       "matches": int((full >= 0).sum().item()), "checksum": int(((full.to(torch.int64) + 2) * wts).sum().item())}
+        ext.sync()
+        for l in lsr[:1]:
+            l.sync()
+
     units = units_timed
     t = torch.tensor([ms_total, float(units)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -685,7 +716,7 @@ def main():
                 "e2e": {"value": eu_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_cv2": cpu_cv2,
-                "gather_check": gather_check, "in_pipeline": in_pipeline}
+                "gather_check": gather_check, "table_check": table_check, "in_pipeline": in_pipeline}
         print(json.dumps(line)); sys.stdout.flush()
     # orderly teardown: the matchers run on the frame handles' streams, so they go first
     torch.cuda.synchronize()

@@ -14,7 +14,7 @@
 namespace sslpl {
 
 constexpr int TH_LOW = 50;          // ORBmatcher.cc:38
-constexpr int MAX_DYN_SMEM = 227 * 1024;   // per-CTA shared memory of sm_100 (opt-in above 48 KB)
+constexpr int MAX_DYN_SMEM = 200 * 1024;   // dynamic shared memory the two data-dependent kernels may ask for (sm_100: 227 KB per CTA, static included)
 constexpr int HISTO_LENGTH = 30;    // ORBmatcher.cc:39
 
 // A set of frames in HBM (strides in elements of the respective type)
@@ -1148,7 +1148,7 @@ int sslpl_bow_assign(sslpl_matcher* m, const uint8_t* desc, int n, const uint8_t
     cudaStream_t st = m->stream;
     SSLPL_CUDA(cudaMemcpyAsync(m->desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
     SSLPL_CUDA(cudaMemcpyAsync(m->cent, centroids, (size_t)nc * 32, cudaMemcpyHostToDevice, st));
-    SSLPL_REQUIRE((size_t)(nc * 32) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "too many centroids for one shared-memory tile (nc <= 7264)");
+    SSLPL_REQUIRE((size_t)(nc * 32) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "too many centroids for one shared-memory tile (nc <= 6400)");
     k_bow_assign<<<dim3((n + 127) / 128, 1), 128, nc * 32, st>>>(m->desc, 0, nullptr, n, n, m->cent, nc, m->node, 0); m->launches++;
     SSLPL_CUDA(cudaGetLastError());
     SSLPL_CUDA(cudaMemcpyAsync(node, m->node, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
@@ -1256,7 +1256,7 @@ static int bow_batch_tail(sslpl_matcher* m, const uint8_t* d_desc, const sslpl_k
                           float nnratio, int checkOri, int32_t* d_match, int32_t* d_nmatch) {
     cudaStream_t st = m->stream;
     const int npairs = nframes - 1, fc = m->p.max_features + 64, NN = m->p.max_nodes + 1;
-    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 227 KB)");
+    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 200 KB)");
     k_build_csr<<<nframes, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->b_node, fc, d_n, cap, nc, m->b_off, NN + 1, m->b_idx, fc);
     m->launches += 1;
     fill(m, d_match, (long long)npairs * cap, -1);
@@ -1286,7 +1286,7 @@ int sslpl_match_bow_batch_device(sslpl_matcher* m, const uint8_t* d_desc, const 
     SSLPL_REQUIRE(cap >= 1 && cap <= m->p.max_features + 64 && nc >= 1 && nc <= m->p.max_nodes, SSLPL_ERR_ARG, "cap or nc exceeds the matcher capacity");
     SSLPL_CUDA(cudaSetDevice(m->p.device));
     const int fc = m->p.max_features + 64;
-    SSLPL_REQUIRE((size_t)(nc * 32) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "too many centroids for one shared-memory tile (nc <= 7264)");
+    SSLPL_REQUIRE((size_t)(nc * 32) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "too many centroids for one shared-memory tile (nc <= 6400)");
     k_bow_assign<<<dim3((cap + 127) / 128, nframes), 128, nc * 32, m->stream>>>(d_desc, (long long)cap * 32, d_n, 0, cap, d_centroids, nc, m->b_node, fc);
     m->launches += 1;
     return bow_batch_tail(m, d_desc, d_kps, d_n, nframes, cap, nc, nnratio, checkOri, d_match, d_nmatch);
@@ -1350,7 +1350,7 @@ int sslpl_search_by_projection_frame(sslpl_matcher* m,
     SSLPL_CUDA(cudaStreamSynchronize(st));                               // fl (pageable) and h_small are reused by the caller / next call
     int* goff = m->off + (NN + 1); int* gidx = m->idx + cap;
     k_grid_cells<<<(n2 + 127) / 128, 128, 0, st>>>(k1, k1 + cap, n2, A.minX, A.minY, A.invW, A.invH, m->node);
-    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 227 KB)");
+    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 200 KB)");
     k_build_csr<<<1, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->node, 0, m->ncnt, cap, nc, goff, 0, gidx, 0);
     k_proj_match<<<1, 32, 0, st>>>(A, n1, m->flag, k0, m->desc, reinterpret_cast<const int*>(k0 + 4 * (size_t)cap), k0 + 3 * (size_t)cap,
                                    n2, m->desc + (size_t)cap * 32, k1, k1 + cap, reinterpret_cast<const int*>(k1 + 4 * (size_t)cap), k1 + 2 * (size_t)cap,
@@ -1414,7 +1414,7 @@ int sslpl_search_by_projection_mps(sslpl_matcher* m,
     SSLPL_CUDA(cudaStreamSynchronize(st));                               // pageable staging vectors go out of scope
     int* goff = m->off + (NN + 1); int* gidx = m->idx + cap;
     k_grid_cells<<<(n2 + 127) / 128, 128, 0, st>>>(k1, k1 + cap, n2, A.minX, A.minY, A.invW, A.invH, m->node);
-    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 227 KB)");
+    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 200 KB)");
     k_build_csr<<<1, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->node, 0, m->ncnt, cap, nc, goff, 0, gidx, 0);
     k_proj_match_mps<<<1, 32, 0, st>>>(A, nmp, m->flag, k0, k0 + cap, k0 + 2 * (size_t)cap, reinterpret_cast<const int*>(k0 + 4 * (size_t)cap), k0 + 3 * (size_t)cap, m->desc,
                                        n2, m->desc + (size_t)cap * 32, k1, k1 + cap, reinterpret_cast<const int*>(k1 + 4 * (size_t)cap), k1 + 3 * (size_t)cap,
@@ -1463,7 +1463,7 @@ int sslpl_search_for_initialization(sslpl_matcher* m,
     SSLPL_CUDA(cudaStreamSynchronize(st));
     int* goff = m->off + (NN + 1); int* gidx = m->idx + cap;
     k_grid_cells<<<(n2 + 127) / 128, 128, 0, st>>>(k1, k1 + cap, n2, A.minX, A.minY, A.invW, A.invH, m->node);
-    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 227 KB)");
+    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 200 KB)");
     k_build_csr<<<1, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->node, 0, m->ncnt, cap, nc, goff, 0, gidx, 0);
     k_init_match<<<1, 32, 0, st>>>(A, n1, m->desc, reinterpret_cast<const int*>(k0 + 4 * (size_t)cap), k0 + 3 * (size_t)cap, k0, k0 + cap,
                                    n2, m->desc + (size_t)cap * 32, k1, k1 + cap, reinterpret_cast<const int*>(k1 + 4 * (size_t)cap), k1 + 2 * (size_t)cap,
@@ -1596,7 +1596,7 @@ int sslpl_fuse_points_search(sslpl_matcher* m, int nmp, const uint8_t* active, c
     SSLPL_CUDA(cudaStreamSynchronize(st));
     int* goff = m->off + (NN + 1); int* gidx = m->idx + cap;
     k_grid_cells<<<(n2 + 127) / 128, 128, 0, st>>>(d_x2, d_y2, n2, A.minX, A.minY, A.invW, A.invH, m->node);
-    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 227 KB)");
+    SSLPL_REQUIRE((size_t)((nc + 1 + cap) * sizeof(int)) <= (size_t)MAX_DYN_SMEM, SSLPL_ERR_CAPACITY, "nodes + features exceed the shared memory of one CTA ((nc + 1 + cap) * 4 <= 200 KB)");
     k_build_csr<<<1, 128, (nc + 1 + cap) * sizeof(int), st>>>(m->node, 0, m->ncnt, cap, nc, goff, 0, gidx, 0);
     k_point_fuse_search<<<(nmp + 3) / 4, 128, 0, st>>>(A, nmp, d_act, d_u, d_v, d_ur, d_lvl, d_dmp, d_d2, d_x2, d_y2, d_oct, d_ur2, d_is2, goff, gidx, d_bi, d_bd);
     m->launches += 3;

@@ -225,8 +225,9 @@ constexpr int FC_ROWS = 36 + TL_IH;           // staged rows: two 96x38 boxes, t
 
 // One CTA per 30-px cell, the whole FAST stage in shared memory: stage the cell's (aw+6)x(ah+6) image box (TMA, the box
 // starts on the 16-byte boundary at or before iniX), score it in two phases, in-cell NMS, 20/7 rule, ordered compaction.
-//   phase A  the opposite-pair test on 4 pixels per thread with byte-SIMD video instructions; survivors are queued
-//   phase B  the full 16-ring score only for queued pixels, all lanes busy
+//   phase A   the opposite-pair test on 4 pixels per thread with byte-SIMD video instructions; survivors are queued (~25 % of the pixels)
+//   phase B1  the exact 9-arc corner test on 16-bit ring masks for the queued pixels; corners re-queued (~4 %)
+//   phase B2  the full 16-ring score only for corners, all lanes busy; NMS walks the corner queue, survivors land in per-row bit masks
 // Equivalent to the reference's per-cell cv::FAST(th=20) with fallback cv::FAST(th=7) (ORBextractor.cc:789-829): NMS
 // inside the cell's detection area with outside pixels = 0, keep survivors >= iniTh or, if none, all survivors
 // (SURVEY.md A.3 [probe]).  The detection areas of the cells are disjoint, so no pixel is scored twice and no score
@@ -236,8 +237,9 @@ __global__ void __launch_bounds__(128) k_fast(const __grid_constant__ OrbGeom g,
     __shared__ __align__(128) uint8_t s_img[FC_ROWS * TL_P];
     __shared__ __align__(4) uint8_t s_sc[(FAST_MAXC + 2) * FAST_TP];
     __shared__ unsigned short s_q[FAST_MAXC * FAST_MAXC];
+    __shared__ unsigned long long s_rowall[FAST_MAXC], s_rowhi[FAST_MAXC];
     __shared__ int s_warp[33];
-    __shared__ int s_qn;
+    __shared__ int s_qn, s_qc;
     __shared__ __align__(8) uint64_t s_bar;
     const int cell = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     int l = 0;
@@ -279,20 +281,24 @@ __global__ void __launch_bounds__(128) k_fast(const __grid_constant__ OrbGeom g,
             }
         }
     }
-    if (tid == 0) s_qn = 0;
+    if (tid == 0) { s_qn = 0; s_qc = 0; }
     for (int i = tid; i < (ah + 2) * (FAST_TP / 4); i += 128) reinterpret_cast<uint32_t*>(s_sc)[i] = 0u;
+    if (tid < FAST_MAXC) { s_rowall[tid] = 0ull; s_rowhi[tid] = 0ull; }
     if (TMA) mbar_wait(&s_bar, 0);
     __syncthreads();
     const int th = g.minTh;
+    const unsigned ltmask = (1u << lane) - 1u;
     // phase A on the aligned word grid of the staged box: groups g0, g0+4, ... cover [xo, xo+aw)
     const unsigned T4 = 0x01010101u * (unsigned)th;
     const int g0 = xo & ~3, ng = (xo + aw - g0 + 3) >> 2, ngroups = ah * ng;
+    const float inv_ng = __frcp_rn((float)ng);
     for (int gb = 0; gb < ngroups; gb += 128) {
         const int gidx = gb + tid;
         unsigned pm = 0;
         int r = 0, c4 = 0;
         if (gidx < ngroups) {
-            r = gidx / ng; c4 = g0 + 4 * (gidx - r * ng);
+            r = __float2int_rz(__fmul_rn((float)gidx + 0.5f, inv_ng));                  // gidx / ng (exact: the quotient is >= 0.5/ng away from an integer)
+            c4 = g0 + 4 * (gidx - r * ng);
             const unsigned* row = reinterpret_cast<const unsigned*>(&s_img[(r + 3) * TL_P + c4]);
             const unsigned C = row[0];
             const unsigned Rt = __byte_perm(row[0], row[1], 0x6543), Lf = __byte_perm(row[-1], row[0], 0x4321);   // x+3, x-3
@@ -306,51 +312,87 @@ __global__ void __launch_bounds__(128) k_fast(const __grid_constant__ OrbGeom g,
             if (c4 < xo) pm &= ~0u << (8 * (xo - c4));                                    // clip the first and the last group of a row
             if (c4 + 4 > xo + aw) pm &= (1u << (8 * (xo + aw - c4))) - 1u;
         }
+        // warp prefix of the 0..4 survivors per lane from three ballots (the order inside the queue does not matter)
         const int cnt = __popc(pm);
-        int inc = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t2; }
+        const unsigned b0 = __ballot_sync(0xffffffffu, cnt & 1), b1 = __ballot_sync(0xffffffffu, cnt & 2), b2 = __ballot_sync(0xffffffffu, cnt & 4);
+        const int tot = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
         int base = 0;
-        if (lane == 31 && inc) base = atomicAdd(&s_qn, inc);
-        base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+        if (lane == 0 && tot) base = atomicAdd(&s_qn, tot);
+        base = __shfl_sync(0xffffffffu, base, 0) + __popc(b0 & ltmask) + 2 * __popc(b1 & ltmask) + 4 * __popc(b2 & ltmask);
         const int p0 = (r << 6) + c4 - xo;
 #pragma unroll
         for (int k = 0; k < 4; k++) if (pm & (1u << (8 * k))) s_q[base++] = (unsigned short)(p0 + k);
     }
     __syncthreads();
-    // phase B
+    // phase B1: the exact corner test (9 contiguous ring pixels all brighter or all darker by more than th <=> score >= th) for the queued
+    // pixels, on 16-bit arc masks built with byte-SIMD compares; corners are compacted IN PLACE (entries are read a block of 128 ahead of
+    // where the survivors are written)
     const int nq = s_qn;
-    for (int qi = tid; qi < nq; qi += 128) {
+    for (int qb = 0; qb < nq; qb += 128) {
+        const int qi = qb + tid;
+        bool corner = false;
+        int p = 0;
+        if (qi < nq) {
+            p = s_q[qi];
+            const uint8_t* P = &s_img[((p >> 6) + 3) * TL_P + (p & 63) + xo];
+            const unsigned v = P[0];
+            const unsigned LO4 = 0x01010101u * (unsigned)max((int)v - th, 0), HI4 = 0x01010101u * (unsigned)min((int)v + th, 255);
+            const unsigned W0 = P[3 * TL_P] | (P[3 * TL_P + 1] << 8) | (P[2 * TL_P + 2] << 16) | (P[TL_P + 3] << 24);                    // ring 0..3
+            const unsigned W1 = P[3] | (P[-TL_P + 3] << 8) | (P[-2 * TL_P + 2] << 16) | (P[-3 * TL_P + 1] << 24);                       // 4..7
+            const unsigned W2 = P[-3 * TL_P] | (P[-3 * TL_P - 1] << 8) | (P[-2 * TL_P - 2] << 16) | (P[-TL_P - 3] << 24);               // 8..11
+            const unsigned W3 = P[-3] | (P[TL_P - 3] << 8) | (P[2 * TL_P - 2] << 16) | (P[3 * TL_P - 1] << 24);                         // 12..15
+            // byte masks -> 4 bits each: (m & 0x08040201) * 0x01010101 >> 24
+#define SSLPL_NIB(m) ((((m) & 0x08040201u) * 0x01010101u) >> 24)
+            const unsigned br = SSLPL_NIB(__vcmpltu4(W0, LO4)) | (SSLPL_NIB(__vcmpltu4(W1, LO4)) << 4) | (SSLPL_NIB(__vcmpltu4(W2, LO4)) << 8) | (SSLPL_NIB(__vcmpltu4(W3, LO4)) << 12);
+            const unsigned dk = SSLPL_NIB(__vcmpgtu4(W0, HI4)) | (SSLPL_NIB(__vcmpgtu4(W1, HI4)) << 4) | (SSLPL_NIB(__vcmpgtu4(W2, HI4)) << 8) | (SSLPL_NIB(__vcmpgtu4(W3, HI4)) << 12);
+#undef SSLPL_NIB
+            unsigned xb = br | (br << 16), xd = dk | (dk << 16);                          // the ring twice: runs may wrap
+            unsigned ab = xb & (xb >> 1), ad = xd & (xd >> 1);
+            ab &= ab >> 2; ad &= ad >> 2;
+            ab &= ab >> 4; ad &= ad >> 4;
+            ab &= xb >> 8; ad &= xd >> 8;                                                 // bit k: ring k..k+8 all set
+            corner = ((ab | ad) & 0xffffu) != 0u;
+        }
+        const unsigned cb = __ballot_sync(0xffffffffu, corner);
+        __syncthreads();                                                                 // every entry of this block has been read
+        int base = 0;
+        if (lane == 0 && cb) base = atomicAdd(&s_qc, __popc(cb));
+        base = __shfl_sync(0xffffffffu, base, 0) + __popc(cb & ltmask);
+        if (corner) s_q[base] = (unsigned short)p;
+    }
+    __syncthreads();
+    // phase B2: the score of the corners, all lanes busy
+    const int nc = s_qc;
+    for (int qi = tid; qi < nc; qi += 128) {
         const int p = s_q[qi], r = p >> 6, c = p & 63;
         s_sc[(r + 1) * FAST_TP + c + 1] = (uint8_t)fast_score_tile(&s_img[(r + 3) * TL_P + c + xo], TL_P, th);
     }
     __syncthreads();
-    const int chunk = (area + 127) / 128;                  // <= 28
-    const int pb = min(area, tid * chunk), pe = min(area, pb + chunk);
-    uint32_t m_all = 0, m_hi = 0;
-    for (int p = pb; p < pe; p++) {
-        const int y = p / aw, x = p - y * aw;
+    // in-cell NMS of the corners; survivors as one bit per pixel in a 64-bit mask per row (all, and those >= iniTh)
+    for (int qi = tid; qi < nc; qi += 128) {
+        const int p = s_q[qi], y = p >> 6, x = p & 63;
         const uint8_t* c = &s_sc[(y + 1) * FAST_TP + x + 1];
-        const int s = c[0];
-        if (s != 0 && s > c[-1] && s > c[1] && s > c[-FAST_TP - 1] && s > c[-FAST_TP] && s > c[-FAST_TP + 1] &&
-            s > c[FAST_TP - 1] && s > c[FAST_TP] && s > c[FAST_TP + 1]) {
-            m_all |= 1u << (p - pb);
-            if (s >= g.iniTh) m_hi |= 1u << (p - pb);
+        const int sc = c[0];
+        if (sc > c[-1] && sc > c[1] && sc > c[-FAST_TP - 1] && sc > c[-FAST_TP] && sc > c[-FAST_TP + 1] &&
+            sc > c[FAST_TP - 1] && sc > c[FAST_TP] && sc > c[FAST_TP + 1]) {
+            atomicOr(&s_rowall[y], 1ull << x);
+            if (sc >= g.iniTh) atomicOr(&s_rowhi[y], 1ull << x);
         }
     }
-    const int any_hi = __syncthreads_or(m_hi != 0);
-    const uint32_t m = any_hi ? m_hi : m_all;
+    __syncthreads();
+    const unsigned long long mh = tid < ah ? s_rowhi[tid] : 0ull;
+    const int any_hi = __syncthreads_or(mh != 0ull);
+    unsigned long long m = tid < ah ? (any_hi ? mh : s_rowall[tid]) : 0ull;             // thread = row: raster order by an exclusive scan over the rows
     int total;
-    int off = block_exclusive_scan(__popc(m), s_warp, &total);
+    int off = block_exclusive_scan(__popcll(m), s_warp, &total);
     uint32_t* out = ws.cand + (long long)f * g.cand_stride + L.cand_off + (long long)ci * L.cell_cap;
     const int ox = iniX + 3 - MINB, oy = iniY + 3 - MINB;   // coordinates relative to (minBorderX, minBorderY)
-    for (int p = pb; p < pe; p++)
-        if (m & (1u << (p - pb))) {
-            const int y = p / aw, x = p - y * aw;
-            const int s = s_sc[(y + 1) * FAST_TP + x + 1];
-            if (off < L.cell_cap) out[off] = (uint32_t)(x + ox) | ((uint32_t)(y + oy) << 12) | ((uint32_t)s << 24);
-            off++;
-        }
+    for (; m; m &= m - 1ull) {
+        const int x = __ffsll((long long)m) - 1;
+        const int sc = s_sc[(tid + 1) * FAST_TP + x + 1];
+        if (off < L.cell_cap) out[off] = (uint32_t)(x + ox) | ((uint32_t)(tid + oy) << 12) | ((uint32_t)sc << 24);
+        off++;
+    }
     if (tid == 0) { *cnt_out = min(total, L.cell_cap); if (total > L.cell_cap) atomicOr(ws.err, DERR_KEY_OVERFLOW); }
 }
 

@@ -7,6 +7,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+BORDERLINE_OK = set()          # tags of inputs allowed one borderline LSD segment of difference (see _check_frame); empty: none is needed
+
 
 def _check_frame(pkg, oracle, img, nfeat, tag, vs_cv2=True):
     ls = pkg.LineSegment(nfeat, max_width=img.shape[1], max_height=img.shape[0])
@@ -18,17 +20,23 @@ def _check_frame(pkg, oracle, img, nfeat, tag, vs_cv2=True):
     if raw.shape != oraw.shape or np.max(np.abs(raw - oraw), initial=0) > 1e-4:
         # LSD decides whether the extreme pixels of a region are inside its rectangle from the LAST BIT of
         # cos/sin(theta) (they lie exactly on the end edges).  glibc mis-rounds ~0.14% of those; the device rounds
-        # correctly (ddtrig.h).  A residual flip may add/remove ONE borderline segment (|log NFA| small); anything
-        # beyond that is a failure.
+        # correctly (ddtrig.h).  Such a flip may add/remove ONE borderline segment (|log NFA| small).  It is tolerated only for
+        # the inputs listed in BORDERLINE_OK (none of the committed test inputs needs it), and even then every KeyLine and LBD
+        # descriptor of the segments both sides found is still compared.
+        assert tag in BORDERLINE_OK, f"{tag}: LSD segments differ (GPU {len(raw)}, oracle {len(oraw)})"
         so = {tuple(np.round(r, 3)) for r in oraw}; sg = {tuple(np.round(r, 3)) for r in raw}
         assert len(so ^ sg) <= 1 and abs(len(raw) - len(oraw)) <= 1, f"{tag}: {len(so ^ sg)} segments differ (GPU {len(raw)}, oracle {len(oraw)})"
         res = cv2.createLineSegmentDetector(cv2.LSD_REFINE_ADV).detect(img)
         for seg in so - sg:
             j = [tuple(np.round(r, 3)) for r in oraw].index(seg)
             assert abs(float(res[3].ravel()[j])) < 3.0, f"{tag}: non-borderline segment missing (log NFA {res[3].ravel()[j]})"
-        import warnings
-        warnings.warn(f"{tag}: one borderline LSD segment differs (libm last-bit dependence of the reference)")
-        return len(raw), len(raw)
+        key = lambda k: (round(float(k["startPointX"]), 3), round(float(k["startPointY"]), 3), round(float(k["endPointX"]), 3), round(float(k["endPointY"]), 3))
+        oidx = {key(k): i for i, k in enumerate(okl)}
+        common = [(i, oidx[key(k)]) for i, k in enumerate(kl) if key(k) in oidx]
+        assert len(common) >= min(len(kl), len(okl)) - 1
+        for i, j in common:
+            assert kl["numOfPixels"][i] == okl["numOfPixels"][j] and np.array_equal(ld[i], old[j]), f"{tag}: KeyLine / LBD of a common segment differs"
+        return len(kl), len(raw)
     if vs_cv2:
         ref = cv2.createLineSegmentDetector(cv2.LSD_REFINE_ADV).detect(img)[0]
         ref = np.zeros((0, 4), np.float32) if ref is None else ref.reshape(-1, 4)
