@@ -42,6 +42,7 @@ struct LineGeom {
     int min_reg_size;
     int trace_cap;              // rows of the debug trace per frame (0 = off)
     int dbg;                    // SSLPL_WALKER_DBG bit mask (bring-up switches of the region walker)
+    int dbg_seed;               // SSLPL_WALKER_SEED: pixel index whose first region list is printed (bring-up)
 };
 
 // What region growing reads per neighbour, in one 16-byte load: level-line angle (degrees, NOTDEF_F when undefined),
@@ -53,7 +54,9 @@ struct LineWs {
     float* angdeg; LPix* pix; float2* cs0; double* modgrad;
     unsigned long long* maxgrad; unsigned* seeds; int* nseeds;
     unsigned* reg;              // region pixel list (x | y << 16) of the turn holder (whole-frame capacity)
-    unsigned* sreg;             // per frame: WALK_RING speculation slots x WALK_SLOT_CAP list entries
+    unsigned* sreg;             // per frame: WALK_RING speculation slots x WALK_SLOT_CAP list entries (v3: one list of V3_LIST entries per worker)
+    unsigned* dlist;            // v3, per frame: V3_DPOOL entries (see V3Shared::dl_off)
+    unsigned char* rcode;       // v3, per frame: one byte per rank: the try it committed with | 0x80 if it released pixels, 0xff = none
     double* sjob;               // per frame: one pending NFA job (13 doubles) per speculation slot
     unsigned long long* wstat;  // walker statistics (whole launch): see sslpl_line_walker_stats
     double* seg;                // raw rectangles: x1,y1,x2,y2 (detection scale, before +0.5)
@@ -338,6 +341,7 @@ struct WalkCtx {                // context of one walker warp (k_lsd_regions): s
     int abort;                  // speculative attempt abandoned: 1 = capacity, 2 = a live attempt of LOWER rank holds a pixel it needs
     int conflict;               // abort == 2: that rank (the attempt can be repeated once it has been retired)
     unsigned ticket;
+    int dirty, ndeps; unsigned dep[2];   // v3: released pixels; tickets of live lower attempts whose pixels were assumed used
 };
 struct FrameCtl {               // one per walker CTA
     unsigned cursor, nclaims, turn;
@@ -353,8 +357,9 @@ __shared__ __align__(16) double s_stc[WALK_MAXW][96];     // per warp: staging o
 __shared__ WalkCtx s_W1;                                   // the one-warp throughput kernel keeps its own small context:
 __shared__ __align__(16) double s_st1[96];                 // 28 of its CTAs share an SM
 constexpr int SOLO = 0;                                    // (hidden by the template parameter of the same name inside the helpers)
-#define s_W (*(SOLO ? &s_W1 : &s_Wc[threadIdx.x >> 5]))
-#define s_st (SOLO ? s_st1 : s_stc[threadIdx.x >> 5])
+// SOLO: 0 = multi-warp walker of round 2a (k_lsd_regions), 1 / 2 = one warp per frame (round-2a form / lean), 3 = multi-warp walker v3
+#define s_W (*((SOLO == 1 || SOLO == 2) ? &s_W1 : &s_Wc[threadIdx.x >> 5]))
+#define s_st ((SOLO == 1 || SOLO == 2) ? s_st1 : s_stc[threadIdx.x >> 5])
 
 // SLOT_PRESUMED: the seed was under the ticket of a live attempt of lower rank when its turn to be grown came: it is presumed
 // swallowed; the commit checks (and grows it for real if it was not).  SLOT_ABORTED: to be redone by the turn holder.
@@ -365,7 +370,13 @@ __device__ __forceinline__ unsigned l_turn() { return *reinterpret_cast<volatile
 __device__ __forceinline__ bool l_bit(const unsigned* bits, int q) { return (reinterpret_cast<const volatile unsigned*>(bits)[q >> 5] >> (q & 31)) & 1u; }
 // Is ticket m (not mine) held by an attempt that has not been retired yet?  Ranks below `turn` are committed or discarded.
 __device__ __forceinline__ bool l_live(unsigned m, int* seq_out) { const int s = (int)(m & 0xffffffu) - 1; *seq_out = s; return m != 0u && s >= (int)l_turn(); }
-template <int SOLO> __device__ __forceinline__ void l_release(const WalkCtx& W, int q) { if (SOLO) W.pix[q].used = 0u; else atomicCAS(&W.pix[q].used, W.ticket, 0u); }
+// (v3: a released pixel keeps the ticket with bit 31 set: it is free for everybody, but an attempt of LOWER rank that takes it still
+//  poisons the releasing attempt, whose first growth went over a pixel that the sequential order gives to the lower rank)
+template <int SOLO> __device__ __forceinline__ void l_release(const WalkCtx& W, int q) {
+    if (SOLO == 1 || SOLO == 2) W.pix[q].used = 0u;
+    else if (SOLO == 3) atomicCAS(&W.pix[q].used, W.ticket, W.ticket | 0x80000000u);
+    else atomicCAS(&W.pix[q].used, W.ticket, 0u);
+}
 
 __device__ __forceinline__ bool l_aligned(float angdeg, double theta, double prec) {
     if (angdeg == NOTDEF_F) return false;
@@ -555,6 +566,116 @@ template <int SOLO> __device__ __noinline__ int l_region_grow(int sx, int sy, do
     return n;
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// region_grow, LEAN form (one warp per frame, round 2b).  Same sequential semantics as l_region_grow<1>, restructured around
+// the measured dependent-chain latencies of sm_100a (tools/lat_probe.cu: SHFL 37, MATCH 72, FDIV 57, double alignment test 82,
+// L1 hit 50, L2 hit 280, LDS 34 cycles), because the walker is one warp following one chain:
+//   * the region list's tail lives in a shared-memory ring (the frontier is read with LDS, not through L1/L2; the full list
+//     still goes to global memory for region2rect / refine, fire and forget);
+//   * the alignment test runs on the float DEGREES that both operands come from (|theta - a| <= prec is decided in float
+//     when it is further than 2e-3 deg from the threshold or from the 270-degree fold; closer than that the reference's
+//     double formula decides) — no FP64 and no conversions on the chain;
+//   * the region angle is LAZY: a round tests every pending lane against the exact current angle; the first passing lane k0
+//     is accepted (exact), and every later lane whose outcome cannot change while at most K = popc(passing) more unit
+//     vectors are added to the sums is decided in the same round without recomputing the angle.  The bound is rigorous:
+//     the scan reaches lane l after accepting at most K_l = (first holders among the passing lanes before l) unit vectors, each
+//     within prec + E of S, so S has turned by at most atan(sum |sin phi_i| / |S|) <= 57.3 deg * sin(prec + E) * K_l / |S|;
+//     cv::fastAtan2 is within E = 0.00956 deg of atan2 (measured over 5e8 inputs; 2E = 0.0202 used), float rounding of the
+//     sums is < 3e-4 deg, the rest of the 0.0215 deg is slack.  tools/sim_lean_grow.cpp runs this lane by lane against the
+//     oracle's sequential region_grow (every call of four frames identical).
+//     The round stops before the first lane that is not robust in that sense; only then is the angle recomputed on the
+//     chain.  For big regions (|S| ~ n) nearly every step is ONE round with no atan2 before the next step's loads;
+//   * the angle of the next step is recomputed after that step's loads have been issued (it overlaps their latency);
+//   * duplicates (the same pixel seen from two queue entries) come from one MATCH issued under the record load;
+//   * accepted pixels warm L1 with the six sectors of their 3x3 neighbourhood (consumed one step later).
+// -------------------------------------------------------------------------------------------------
+__device__ int l_region_grow_v3(int sx, int sy, double prec, double* reg_angle_out);
+constexpr int LEAN_RING = 1024;
+__shared__ unsigned s_ring1[LEAN_RING];
+
+__device__ __noinline__ int l_region_grow_lean(int sx, int sy, double prec, double* reg_angle_out) {
+    WalkCtx& W = s_W1;
+    const int lane = threadIdx.x & 31, w = W.w, h = W.h;
+    LPix* pix = W.pix; unsigned* reg = W.reg;
+    const int sq = sy * w + sx;
+    if (lane == 0) { const unsigned pk0 = (unsigned)sx | ((unsigned)sy << 16); reg[0] = pk0; s_ring1[0] = pk0; pix[sq].used = 1u; }
+    float th = __ldg(W.ang + sq);                                // degrees; the region angle is (double)th * L_DEG throughout
+    const float2 c0 = __ldg(W.cs0 + sq);
+    float sumdx = c0.x, sumdy = c0.y;
+    float rM = rsqrtf(sumdx * sumdx + sumdy * sumdy);
+    bool dirty = false;                                          // th / rM are older than the sums
+    int n = 1;
+    const float pdeg = (float)(prec * (180.0 / L_PI));
+    const float coef = (float)(57.2958 * 1.0002 * sin(prec + 0.0006));     // degrees the sums can turn per (accepted vector / |S|): see above
+    const bool rob_ok = prec < 0.78;                             // <= 45 deg: then prec + B <= 75.2 deg < 90 and the reference's fold at 270 deg is the circular distance
+    const int slot = lane >> 3, nb = (lane & 7) + ((lane & 7) >= 4 ? 1 : 0);
+    const int ox = nb % 3 - 1, oy = nb / 3 - 1;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned sink = 0u, wu0 = 0u, wu1 = 0u, wu2 = 0u, wu3 = 0u, wu4 = 0u, wu5 = 0u;
+    __syncwarp();
+    for (int i = 0; i < n;) {
+        const int cnt = min(4, n - i);
+        unsigned pk = 0;
+        { const int j = i + slot; if (slot < cnt) pk = (n - j <= LEAN_RING) ? s_ring1[j & (LEAN_RING - 1)] : reg[j]; }
+        const int xx = (int)(pk & 0xffff) + ox, yy = (int)(pk >> 16) + oy, q = yy * w + xx;
+        const bool valid = slot < cnt && (unsigned)xx < (unsigned)w && (unsigned)yy < (unsigned)h;
+        uint4 v = make_uint4(__float_as_uint(NOTDEF_F), 0u, 0u, 1u);
+        if (valid) v = *reinterpret_cast<const uint4*>(pix + q);
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? q : ~lane);     // under the load
+        sink ^= wu0 ^ wu1 ^ wu2 ^ wu3 ^ wu4 ^ wu5;                                   // last step's warm-up loads have landed by now
+        if (dirty) { th = fast_atan2_deg(sumdy, sumdx); rM = rsqrtf(sumdx * sumdx + sumdy * sumdy); dirty = false; }
+        const float a = __uint_as_float(v.x), cx = __uint_as_float(v.y), cy = __uint_as_float(v.z);
+        unsigned pending = __ballot_sync(0xffffffffu, valid && a != NOTDEF_F && v.w == 0u);
+        while (pending) {
+            const bool mep = (pending >> lane) & 1u;
+            const float d = fabsf(th - a);
+            const float e = d > 270.f ? 360.f - d : d;
+            bool pass = e <= pdeg;
+            const bool near = fabsf(e - pdeg) < 2e-3f || fabsf(d - 270.f) < 2e-3f;
+            if (__any_sync(0xffffffffu, mep && near)) { if (near) pass = l_aligned_rad((double)a * L_DEG, (double)th * L_DEG, prec); }
+            const unsigned P = __ballot_sync(0xffffffffu, mep && pass);
+            if (!P) break;                                        // nobody passes at the current angle: all rejected
+            const int k0 = __ffs(P) - 1;
+            const unsigned P1 = P & ~__ballot_sync(0xffffffffu, pass && mep && (peers & P & lt) != 0u);   // first holders among the passing lanes
+            const float x = (float)__popc(P1 & lt) * rM;          // (vectors the scan can have added before this lane) / |S|
+            bool robust = false;
+            if (rob_ok && x <= 0.5f) { const float B = coef * x + 0.0215f; robust = pass ? (e <= pdeg - B) : (e >= pdeg + B); }
+            const unsigned NR = __ballot_sync(0xffffffffu, mep && lane > k0 && !robust);
+            const unsigned below = NR ? ((NR & (0u - NR)) - 1u) : 0xffffffffu;       // lanes before the first non-robust one
+            const unsigned A = P1 & below;                        // accepted in this round, in scan order
+            for (unsigned Tm = A; Tm; Tm &= Tm - 1u) {            // the sums, in scan order
+                const int mm = __ffs(Tm) - 1;
+                sumdx += __shfl_sync(0xffffffffu, cx, mm); sumdy += __shfl_sync(0xffffffffu, cy, mm);
+            }
+            if ((A >> lane) & 1u) {
+                const int pos = n + __popc(A & lt);
+                const unsigned me = (unsigned)xx | ((unsigned)yy << 16);
+                s_ring1[pos & (LEAN_RING - 1)] = me; reg[pos] = me; pix[q].used = 1u;
+                const int xa = max(xx - 1, 0), xb = min(xx + 1, w - 1), ya = max(yy - 1, 0), yb = min(yy + 1, h - 1);
+                const unsigned* r0 = reinterpret_cast<const unsigned*>(pix + ya * w), * r1 = reinterpret_cast<const unsigned*>(pix + yy * w), * r2 = reinterpret_cast<const unsigned*>(pix + yb * w);
+                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(wu0) : "l"(r0 + 4 * xa));
+                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(wu1) : "l"(r0 + 4 * xb));
+                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(wu2) : "l"(r1 + 4 * xa));
+                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(wu3) : "l"(r1 + 4 * xb));
+                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(wu4) : "l"(r2 + 4 * xa));
+                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(wu5) : "l"(r2 + 4 * xb));
+            }
+            n += __popc(A);
+            pending &= ~below;                                    // everything before the first non-robust lane is resolved
+            pending &= ~__ballot_sync(0xffffffffu, mep && (peers & A) != 0u);        // later holders of accepted pixels
+            dirty = true;
+            if (pending) { th = fast_atan2_deg(sumdy, sumdx); rM = rsqrtf(sumdx * sumdx + sumdy * sumdy); dirty = false; }
+        }
+        __syncwarp();
+        i += cnt;
+    }
+    if (dirty) th = fast_atan2_deg(sumdy, sumdx);
+    if (sink == 0x9e3779b9u && n < 0) reg[0] = sink;             // keeps the warm-up loads alive (never true)
+    *reg_angle_out = (double)th * L_DEG;
+    return n;
+}
+
 __device__ __forceinline__ double l_angle_diff_signed(double a, double b) {
     double d = a - b;
     while (d <= -L_PI) d += L_2PI;
@@ -657,7 +778,7 @@ __device__ __forceinline__ double l_distsq(double x1, double y1, double x2, doub
 template <int SOLO> __device__ __noinline__ bool l_reduce_region_radius(int* n_io, double reg_angle, double prec, double p, LRect* rec, double density, double density_th) {
     const int lane = threadIdx.x & 31, w = s_W.w;
     int n = *n_io;
-    if (!SOLO && s_W.mode == 0) {      // speculative attempt: keep the list as it is (the commit validates every pixel ever accepted) and work on a copy
+    if ((SOLO == 0 || SOLO == 3) && s_W.mode == 0) {  // speculative attempt: keep the list as it is (the commit validates every pixel ever accepted) and work on a copy
         if (2 * n + s_W.nasm > s_W.cap) { s_W.abort = 1; return false; }
         for (int i = lane; i < n; i += 32) s_W.reg[n + i] = s_W.reg[i];
         s_W.reg += n; s_W.cap -= n;
@@ -734,6 +855,7 @@ template <int SOLO> __device__ __noinline__ bool l_refine(int* n_io, double* reg
     int n = *n_io;
     double density = (double)n / (l_dist(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
     if (density >= density_th) return true;
+    if constexpr (SOLO == 3) { if (lane == 0) s_W.dirty = 1; }      // pixels get released: attempts that assumed them used cannot be validated
     const unsigned* reg = s_W.reg; const float* __restrict__ ang = s_W.ang;
     const unsigned p0 = reg[0];
     const int sx = p0 & 0xffff, sy = p0 >> 16;
@@ -765,10 +887,12 @@ template <int SOLO> __device__ __noinline__ bool l_refine(int* n_io, double* reg
     const double mean_angle = sum / (double)cnt;
     const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
     __syncwarp();
-    if (!SOLO && s_W.mode == 0) { s_W.reg += n; s_W.cap -= n; }   // speculative: the first list stays (validated at commit), the regrown one follows it
-    n = l_region_grow<SOLO>(sx, sy, tau, reg_angle_io);
+    if ((SOLO == 0 || SOLO == 3) && s_W.mode == 0) { s_W.reg += n; s_W.cap -= n; }   // speculative: the first list stays (validated at commit), the regrown one follows it
+    if constexpr (SOLO == 2) n = l_region_grow_lean(sx, sy, tau, reg_angle_io);
+    else if constexpr (SOLO == 3) n = l_region_grow_v3(sx, sy, tau, reg_angle_io);
+    else n = l_region_grow<SOLO>(sx, sy, tau, reg_angle_io);
     if (n < 0) { *n_io = 0; return false; }
-    if (!SOLO && s_W.mode == 0) s_W.acc += n;
+    if ((SOLO == 0 || SOLO == 3) && s_W.mode == 0) s_W.acc += n;
     *n_io = n;
     if (n < 2) return false;
     l_region2rect<SOLO>(n, *reg_angle_io, prec, p, rec);
@@ -1305,6 +1429,618 @@ __global__ void __launch_bounds__(32, 28) k_lsd_regions_solo(const __grid_consta
   }
 }
 
+// The same loop over the frame's seeds with the LEAN region growing (l_region_grow_lean): the shipped one-warp walker.
+// k_lsd_regions_solo stays for A/B runs (SSLPL_WALKER_LEAN=0).
+__global__ void __launch_bounds__(32, 28) k_lsd_regions_lean(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
+    const int lane = threadIdx.x;
+  for (;;) {
+    int f = 0;
+    if (lane == 0) f = atomicAdd(ws.rejctl + 2, 1);
+    f = __shfl_sync(0xffffffffu, f, 0);
+    if (f >= nframes) break;
+    __syncwarp();
+    WalkCtx& W = s_W1;
+    if (lane == 0) {
+        W.w = g.sw; W.h = g.sh; W.mode = 2; W.abort = 0; W.nasm = 0; W.acc = 0; W.cap = (int)g.pix_stride; W.ticket = 1u; W.seq = 0;
+        W.ang = ws.angdeg + f * g.pix_stride; W.mod = ws.modgrad + f * g.pix_stride;
+        W.pix = ws.pix + f * g.pix_stride; W.reg = ws.reg + f * g.pix_stride; W.base0 = W.reg; W.cs0 = ws.cs0 + f * g.pix_stride; W.bits = nullptr;
+    }
+    __syncwarp();
+    const LPix* pix = ws.pix + f * g.pix_stride;
+    const unsigned* seeds = ws.seeds + f * g.pix_stride;
+    const int ns = ws.nseeds[f];
+    double* jobs = ws.jobs + (long long)f * g.seg_cap * 13;
+    int nj = 0;
+    for (int sb = 0; sb < ns; sb += 32) {
+        const bool have = sb + lane < ns;
+        const unsigned mine = have ? seeds[sb + lane] : 0u;                   // 32 seeds per coalesced load
+        unsigned umask = __ballot_sync(0xffffffffu, !have || pix[mine].used != 0u); // their `used` state, one round trip
+        while (~umask) {                                    // angle != NOTDEF holds for every seed
+            const int j = __ffs(~umask) - 1;
+            umask |= (2u << j) - 1u;                        // seeds up to j are done
+            const unsigned idx = __shfl_sync(0xffffffffu, mine, j);
+            double reg_angle;
+            int n = l_region_grow_lean((int)(idx % (unsigned)g.sw), (int)(idx / (unsigned)g.sw), g.prec, &reg_angle);
+#ifdef SSLPL_V3_DEBUG
+            if ((int)idx == g.dbg_seed) { __syncwarp(); for (int i = lane; i < n; i += 32) printf("L1 %d %u %u\n", i, W.reg[i] & 0xffff, W.reg[i] >> 16); __syncwarp(); }
+#endif
+            umask |= __ballot_sync(0xffffffffu, !have || pix[mine].used != 0u);    // the region may have swallowed later seeds
+            if (n < g.min_reg_size) continue;
+            LRect rec;
+            l_region2rect<2>(n, reg_angle, g.prec, g.p, &rec);
+            const int n0 = n;
+            const bool okr = l_refine<2>(&n, &reg_angle, g.prec, g.p, &rec, 0.7);
+            umask = ((2u << j) - 1u) | __ballot_sync(0xffffffffu, !have || pix[mine].used != 0u);   // refine can release and re-take pixels
+            if (!okr) continue;
+            if (nj < g.seg_cap) l_emit_job(g, jobs + (long long)nj * 13, rec, idx, n0, lane);
+            nj++;
+        }
+    }
+    if (lane == 0) { ws.njobs[f] = min(nj, g.seg_cap); if (nj > g.seg_cap) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
+    __syncwarp();
+  }
+}
+
+
+// =================================================================================================
+// Multi-warp region walker, v3 (round 2b).  Same idea as k_lsd_regions — regions are grown AHEAD of the sequential order
+// by several warps and retired strictly IN that order — with the two costs that dominated it removed (measured on one
+// 640x480 frame: 58 % of the frame's cycles under the commit lock, 3600 cycles per commit, every invalid attempt regrown
+// under that lock while 15 warps wait):
+//   * RETIRING AN ATTEMPT IS O(1).  "Used" is not a bitmap that a commit has to fill but a property of the ticket found in
+//     LPix.used: a ticket (rank, try) of a retired rank is USED iff that try is the one the rank committed with.  That
+//     is try 0 unless the rank's bit is set in a 64k-bit exception map in shared memory (then one byte per rank in global
+//     memory says which try, if any).  So a commit writes one byte, maybe one bit, advances `turn`; there are no lists to
+//     validate, no bits to set, no list storage per slot (the lists belong to the worker and die with the attempt);
+//   * validity is tracked where it is decided: an attempt that takes a pixel from a live attempt of higher rank POISONS it;
+//     an attempt that meets a pixel held by a live attempt of LOWER rank assumes it used and records that attempt as a
+//     dependency (two at most), valid iff it commits with that very try without ever having released a pixel;
+//   * warp 0 is the CONTROL warp (claims seeds in order into a ring of 1024 tiny slots, retires the head); the others are
+//     workers that pick the lowest runnable slot.  No locks.  An invalid attempt goes back to the ring with try + 1; the
+//     head of the ring can neither meet a live lower rank nor be poisoned, so its attempt always commits.
+// Region growing is the lean form (float-degree test, lazy angle, list tail in shared memory) with tickets taken by CAS whose
+// result is looked at one step later.
+// =================================================================================================
+constexpr int V3_MAXW = 16;            // warps per CTA: 1 control + up to 15 workers
+constexpr int V3_RING = 1024;          // ranks in flight (claimed, not retired)
+constexpr int V3_LIST = 8192;          // list entries of a worker (ws.sreg); bigger regions are regrown as head with the frame-sized list
+constexpr int V3_LRING = 512;          // tail of the worker's list kept in shared memory
+constexpr int V3_RANKS = 65536;        // ranks per frame (exception bits, rcode bytes)
+constexpr int V3_DPOOL = 131072;       // per frame: list entries of the attempts that released pixels, kept until they retire
+static_assert(V3_MAXW * V3_LIST <= WALK_RING * WALK_SLOT_CAP, "the workers' lists live in ws.sreg");
+enum { V3_EMPTY = 0, V3_READY = 1, V3_RUNNING = 2, V3_DONE = 3, V3_PRESUMED = 4, V3_VOID = 5 };
+enum { V3F_JOB = 1, V3F_DIRTY = 2, V3F_RAN = 4 };      // slot flags; bits 4..5 = number of dependencies
+
+struct V3Shared {
+    volatile unsigned turn, nclaims;     // ranks [turn, nclaims) are live; slot of rank r = r % V3_RING
+    unsigned cursor;
+    int ns, nj, all_claimed, frame, done, nready, scanhint, win_base, overflow;
+    unsigned win[WALK_WIN];
+    int state[V3_RING];
+    int seed[V3_RING];
+    int wait[V3_RING];                   // READY: runnable once turn > wait
+    int dl_off[V3_RING], dl_n[V3_RING];  // DONE, dirty: where the pixels it ever accepted are kept until it retires (ws.dlist)
+    int dl_used;
+    unsigned dep[V3_RING][2];
+    unsigned char tryno[V3_RING], poison[V3_RING], flag[V3_RING];
+    unsigned excbits[V3_RANKS / 32];     // rank retired with something else than "try 0 committed" although a try ran
+    unsigned lring[1];                   // [warps][V3_LRING] follows
+};
+extern __shared__ __align__(16) unsigned char s_v3raw[];
+__device__ __forceinline__ V3Shared& v3s() { return *reinterpret_cast<V3Shared*>(s_v3raw); }
+
+__device__ __forceinline__ int v3_rank(unsigned m) { return (int)(m & 0xffffffu) - 1; }
+__device__ __forceinline__ int v3_try(unsigned m) { return (int)((m >> 24) & 0x7fu); }
+// What is a foreign, non-zero ticket to the attempt of rank `myseq`?  0 free (stale), 1 used (committed), 2 held by a live attempt
+// of lower rank, 3 held by a live attempt of higher rank.
+__device__ __forceinline__ int v3_classify(unsigned m, int myseq, const unsigned char* __restrict__ rcode) {
+    V3Shared& S = v3s();
+    if (m & 0x80000000u) return 0;                                // released by its attempt
+    const int r = v3_rank(m), y = v3_try(m);
+    if (r >= (int)S.turn) {
+        const int yy = *reinterpret_cast<volatile unsigned char*>(&S.tryno[r & (V3_RING - 1)]);
+        if (r >= (int)S.turn) {                                   // still live: the slot was rank r's when it was read
+            if (yy != y) return 0;                                // an earlier, abandoned try of a live rank
+            return r < myseq ? 2 : 3;
+        }
+    }
+    if (!((reinterpret_cast<volatile unsigned*>(S.excbits)[r >> 5] >> (r & 31)) & 1u)) return y == 0 ? 1 : 0;
+    const unsigned code = __ldcg(rcode + r);
+    return (code != 0xffu && (int)(code & 0x7fu) == y) ? 1 : 0;
+}
+__device__ __forceinline__ void v3_poison(unsigned m) {
+    V3Shared& S = v3s();
+    const int r = v3_rank(m);
+    if (r >= (int)S.turn) *reinterpret_cast<volatile unsigned char*>(&S.poison[r & (V3_RING - 1)]) = (unsigned char)(v3_try(m) + 1);
+}
+// Result of the atomic issued one step earlier: -1 the pixel is mine, >= 0 the live attempt of lower rank that holds it (repeat after
+// it has retired), -2 lost to anybody else (repeat at once).
+__device__ __forceinline__ int v3_take_resolve(const WalkCtx& W, LTake& t, const unsigned char* rcode) {
+    if (!t.pend) return -1;
+    t.pend = false;
+    const unsigned old = t.old;
+#ifdef SSLPL_V3_DEBUG
+    if ((W.dbg & 16) && t.q == W.nasm) printf("RES T %x seen %x old %x mode %d turn %u\n", W.ticket, t.seen, old, W.mode, v3s().turn);
+#endif
+    if (W.mode != 0 || old == t.seen) {
+        // mine now.  Whoever held it alive, or had held and released it, with a higher rank grew over a pixel that is mine: poisoned
+        const unsigned o = old & 0x7fffffffu;
+        if (o != 0u && o != W.ticket && v3_classify(o, W.seq, rcode) == 3) v3_poison(o);
+        return -1;
+    }
+    if (old != 0u && v3_classify(old, W.seq, rcode) == 2) return v3_rank(old);
+    return -2;
+}
+
+__device__ __noinline__ int l_region_grow_v3(int sx, int sy, double prec, double* reg_angle_out) {
+    WalkCtx& W = s_Wc[threadIdx.x >> 5];
+    V3Shared& S = v3s();
+    unsigned* ring = S.lring + (threadIdx.x >> 5) * V3_LRING;
+    const int lane = threadIdx.x & 31, w = W.w, h = W.h;
+    LPix* pix = W.pix; unsigned* reg = W.reg;
+    const unsigned char* rcode = reinterpret_cast<const unsigned char*>(W.bits);      // per-rank commit codes of this frame (global)
+    const unsigned T = W.ticket; const int myseq = W.seq; const bool spec = W.mode == 0;
+    const int cap = W.cap;
+    const int sq = sy * w + sx;
+    LTake tk; tk.pend = false; tk.q = 0; tk.seen = 0u; tk.old = 0u;
+    int failrank = -1;
+    {
+        int fail = 0;
+        if (lane == 0) {
+            const unsigned pk0 = (unsigned)sx | ((unsigned)sy << 16);
+            reg[0] = pk0; ring[0] = pk0;
+            const unsigned m0 = __ldcg(&pix[sq].used);
+            if (m0 != T) {
+                const int c = m0 == 0u ? 0 : v3_classify(m0, myseq, rcode);
+                if (c == 1) fail = 4;                                          // committed meanwhile: nothing to grow
+                else if (c == 2) { fail = 3; W.conflict = (int)m0; }           // under a live attempt of lower rank: presumed swallowed
+                else {
+                    l_take_issue(W, tk, sq, m0);
+                    const int r = v3_take_resolve(W, tk, rcode);
+                    if (r != -1) { fail = 2; W.conflict = r >= 0 ? r : -1; }
+                }
+            }
+        }
+        fail = __shfl_sync(0xffffffffu, fail, 0);
+        if (fail) { if (lane == 0) W.abort = fail; __syncwarp(); return -1; }
+    }
+    float th = __ldg(W.ang + sq);
+    const float2 c0 = __ldg(W.cs0 + sq);
+    float sumdx = c0.x, sumdy = c0.y;
+    float rM = rsqrtf(sumdx * sumdx + sumdy * sumdy);
+    bool dirty = false;
+    int n = 1;
+    const float pdeg = (float)(prec * (180.0 / L_PI));
+    const float coef = (float)(57.2958 * 1.0002 * sin(prec + 0.0006));
+    const bool rob_ok = prec < 0.78;
+    const int slot = lane >> 3, nb = (lane & 7) + ((lane & 7) >= 4 ? 1 : 0);
+    const int ox = nb % 3 - 1, oy = nb / 3 - 1;
+    const unsigned lt = (1u << lane) - 1u;
+    __syncwarp();
+    for (int i = 0; i < n;) {
+        const int cnt = min(4, n - i);
+        unsigned pk = 0;
+        { const int j = i + slot; if (slot < cnt) pk = (n - j <= V3_LRING) ? ring[j & (V3_LRING - 1)] : reg[j]; }
+        const int xx = (int)(pk & 0xffff) + ox, yy = (int)(pk >> 16) + oy, q = yy * w + xx;
+        const bool valid = slot < cnt && (unsigned)xx < (unsigned)w && (unsigned)yy < (unsigned)h;
+        uint4 v = make_uint4(__float_as_uint(NOTDEF_F), 0u, 0u, 0u);
+        if (valid) v = __ldcg(reinterpret_cast<const uint4*>(pix + q));          // record + ticket (tickets change under atomics: L2)
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? q : ~lane);
+        { const int r = v3_take_resolve(W, tk, rcode); if (r != -1) failrank = (r >= 0 && r > failrank) ? r : (failrank >= 0 ? failrank : r); }
+        if (dirty) { th = fast_atan2_deg(sumdy, sumdx); rM = rsqrtf(sumdx * sumdx + sumdy * sumdy); dirty = false; }
+        const float a = __uint_as_float(v.x), cx = __uint_as_float(v.y), cy = __uint_as_float(v.z);
+        const unsigned m = v.w;
+        bool cand = false, lower = false;
+        if (valid && a != NOTDEF_F && m != T) {
+            if (m == 0u) cand = true;
+            else { const int c = v3_classify(m, myseq, rcode); cand = c == 0 || c == 3; lower = c == 2; }
+        }
+#ifdef SSLPL_V3_DEBUG
+        if ((W.dbg & 16) && valid && q == W.nasm) printf("SEE T %x m %x cand %d lower %d turn %u\n", T, m, (int)cand, (int)lower, S.turn);
+#endif
+        for (unsigned lm = __ballot_sync(0xffffffffu, lower); lm;) {              // remember whose pixels were assumed used
+            const unsigned t = __shfl_sync(0xffffffffu, m, __ffs(lm) - 1);
+            if (lane == 0) {
+                const int nd = W.ndeps;
+                if (!((nd > 0 && W.dep[0] == t) || (nd > 1 && W.dep[1] == t))) { if (nd < 2) { W.dep[nd] = t; W.ndeps = nd + 1; } else W.abort = 5; }
+            }
+            lm &= ~__ballot_sync(0xffffffffu, lower && m == t);
+        }
+        unsigned pending = __ballot_sync(0xffffffffu, cand);
+        while (pending) {
+            const bool mep = (pending >> lane) & 1u;
+            const float d = fabsf(th - a);
+            const float e = d > 270.f ? 360.f - d : d;
+            bool pass = e <= pdeg;
+            const bool near = fabsf(e - pdeg) < 2e-3f || fabsf(d - 270.f) < 2e-3f;
+            if (__any_sync(0xffffffffu, mep && near)) { if (near) pass = l_aligned_rad((double)a * L_DEG, (double)th * L_DEG, prec); }
+            const unsigned P = __ballot_sync(0xffffffffu, mep && pass);
+            if (!P) break;
+            const int k0 = __ffs(P) - 1;
+            const unsigned P1 = P & ~__ballot_sync(0xffffffffu, pass && mep && (peers & P & lt) != 0u);
+            const float x = (float)__popc(P1 & lt) * rM;
+            bool robust = false;
+            if (rob_ok && x <= 0.5f) { const float B = coef * x + 0.0215f; robust = pass ? (e <= pdeg - B) : (e >= pdeg + B); }
+            const unsigned NR = __ballot_sync(0xffffffffu, mep && lane > k0 && !robust);
+            const unsigned below = NR ? ((NR & (0u - NR)) - 1u) : 0xffffffffu;
+            const unsigned A = P1 & below;
+            if (n + __popc(A) > cap) { if (lane == 0) W.abort = 1; __syncwarp(); return -1; }
+            for (unsigned Tm = A; Tm; Tm &= Tm - 1u) {
+                const int mm = __ffs(Tm) - 1;
+                sumdx += __shfl_sync(0xffffffffu, cx, mm); sumdy += __shfl_sync(0xffffffffu, cy, mm);
+            }
+            if ((A >> lane) & 1u) {
+                const int pos = n + __popc(A & lt);
+                const unsigned me = (unsigned)xx | ((unsigned)yy << 16);
+                ring[pos & (V3_LRING - 1)] = me; reg[pos] = me;
+#ifdef SSLPL_V3_DEBUG
+                if ((W.dbg & 16) && q == W.nasm) printf("TAKE T %x q (%d,%d) seen %x mode %d pos %d turn %u\n", T, xx, yy, m, W.mode, pos, S.turn);
+#endif
+                l_take_issue(W, tk, q, m);
+            }
+            n += __popc(A);
+            pending &= ~below;
+            pending &= ~__ballot_sync(0xffffffffu, mep && (peers & A) != 0u);
+            dirty = true;
+            if (pending) { th = fast_atan2_deg(sumdy, sumdx); rM = rsqrtf(sumdx * sumdx + sumdy * sumdy); dirty = false; }
+        }
+        __syncwarp();
+        if (spec && (__any_sync(0xffffffffu, failrank != -1) || W.abort)) break;    // lost a pixel / too many dependencies: stop now
+        if (spec && !(W.dbg & 64) && *reinterpret_cast<volatile unsigned char*>(&S.poison[myseq & (V3_RING - 1)]) == (unsigned char)((T >> 24) + 1u)) { if (lane == 0) { W.abort = 2; W.conflict = -1; } __syncwarp(); return -1; }   // a lower rank took one of my pixels: this try is void
+        i += cnt;
+    }
+    { const int r = v3_take_resolve(W, tk, rcode); if (r != -1) failrank = (r >= 0 && r > failrank) ? r : (failrank >= 0 ? failrank : r); }
+    const bool lostany = __any_sync(0xffffffffu, failrank != -1);
+    failrank = __reduce_max_sync(0xffffffffu, failrank);
+    if (W.abort) return -1;
+    if (lostany) { if (lane == 0) { W.abort = 2; W.conflict = failrank >= 0 ? failrank : -1; } __syncwarp(); return -1; }
+    if (dirty) th = fast_atan2_deg(sumdy, sumdx);
+    *reg_angle_out = (double)th * L_DEG;
+    return n;
+}
+
+// grow + fit + refine one seed as attempt (W.seq, try): 1 = candidate rectangle in *rec, 0 = no job, -1 = abandoned (W.abort)
+__device__ __noinline__ int v3_one_region(const LineGeom& g, unsigned idx, LRect* rec, int* n0) {
+    WalkCtx& W = s_Wc[threadIdx.x >> 5];
+    double reg_angle;
+    int n = l_region_grow_v3((int)(idx % (unsigned)g.sw), (int)(idx / (unsigned)g.sw), g.prec, &reg_angle);
+    if (n < 0) return -1;
+    *n0 = n;
+    W.acc = n;
+#ifdef SSLPL_V3_DEBUG
+    if ((int)idx == g.dbg_seed) { __syncwarp(); for (int i = (threadIdx.x & 31); i < n; i += 32) printf("L3 %d %u %u %u\n", i, W.reg[i] & 0xffff, W.reg[i] >> 16, W.ticket); __syncwarp(); }
+#endif
+    if (n < g.min_reg_size) return 0;
+    l_region2rect<3>(n, reg_angle, g.prec, g.p, rec);
+    const bool okr = l_refine<3>(&n, &reg_angle, g.prec, g.p, rec, 0.7);
+    if (W.abort) return -1;
+    return okr ? 1 : 0;
+}
+
+// One pass of the RETIRER over the head of the ring (a whole warp; returns whether anything moved).  Runs of PRESUMED slots — the
+// seeds a region swallowed while it was live come right behind it in seed order — are looked at 32 at a time (one ticket load per
+// lane) and retired together; DONE / VOID slots one by one (their validity can depend on the slot before).
+__device__ bool v3_retire_pass(const LineGeom& g, const LineWs& ws, int f, unsigned char* rcode, unsigned long long* cnt) {
+    V3Shared& S = v3s();
+    const int lane = threadIdx.x & 31;
+    const LPix* pix = ws.pix + (long long)f * g.pix_stride;
+    bool progress = false;
+    for (;;) {
+        const unsigned t = S.turn, nc = S.nclaims;
+        if (t >= nc) break;
+        const int k = (int)(t & (V3_RING - 1));
+        const int st = *reinterpret_cast<volatile int*>(&S.state[k]);
+        if (st == V3_PRESUMED) {
+            const unsigned r = t + (unsigned)lane;
+            const int kk = (int)(r & (V3_RING - 1));
+            const bool pres = r < nc && *reinterpret_cast<volatile int*>(&S.state[kk]) == V3_PRESUMED;
+            const unsigned pm = __ballot_sync(0xffffffffu, pres);
+            const int len = __ffs(~pm) - 1 < 0 ? 32 : __ffs(~pm) - 1;            // leading PRESUMED slots
+            __threadfence_block();
+            int c = 0;
+            if (lane < len) { const unsigned m = __ldcg(&pix[S.seed[kk]].used); c = m == 0u ? 0 : v3_classify(m, (int)r, rcode); }
+            const unsigned sw = __ballot_sync(0xffffffffu, lane < len && c == 1);
+            const int nsw = __ffs(~sw) - 1 < 0 ? 32 : __ffs(~sw) - 1;             // leading swallowed ones: they retire together
+            bool ran = false;
+            if (lane < nsw) {
+                rcode[r] = 0xffu;
+                ran = (S.flag[kk] & V3F_RAN) != 0;
+                if (ran) atomicOr(&S.excbits[r >> 5], 1u << (r & 31));
+                *reinterpret_cast<volatile int*>(&S.state[kk]) = V3_EMPTY;
+            }
+            if (__any_sync(0xffffffffu, ran)) __threadfence(); else __threadfence_block();
+            __syncwarp();
+            if (nsw > 0) { if (lane == 0) S.turn = t + (unsigned)nsw; cnt[4] += (unsigned long long)nsw; progress = true; }
+            if (nsw < len) {                                                       // the new head was not swallowed after all: it grows now
+                if (lane == nsw) { S.wait[kk] = -1; atomicMin(&S.scanhint, (int)r); __threadfence_block(); atomicAdd(&S.nready, 1); *reinterpret_cast<volatile int*>(&S.state[kk]) = V3_READY; }
+                cnt[5]++; progress = true;
+                __syncwarp();
+                break;
+            }
+            __syncwarp();
+            continue;
+        }
+        if (st != V3_DONE && st != V3_VOID) break;
+        __threadfence_block();
+        bool relbad = false;                                      // a pixel it accepted and released is used by a region of lower rank
+        if (st == V3_DONE && (S.flag[k] & V3F_DIRTY) && S.dl_n[k] > 0) {
+            const unsigned* dl = ws.dlist + (long long)f * V3_DPOOL + S.dl_off[k];
+            const int nn = S.dl_n[k];
+            bool bad = false;
+            for (int i = lane; i < nn; i += 32) {
+                const unsigned pk = __ldcg(dl + i);
+                const unsigned tg = __ldcg(&pix[(int)(pk >> 16) * g.sw + (int)(pk & 0xffff)].used);
+                if (tg != 0u && !(tg & 0x80000000u) && v3_rank(tg) != (int)t && v3_classify(tg, (int)t, rcode) == 1) bad = true;
+            }
+            relbad = __any_sync(0xffffffffu, bad);
+        }
+        int act = 0;                                              // 1 retire (| 4 with a job, | 8 exception), 2 back to READY
+        if (lane == 0) {
+            const int y = S.tryno[k], fl = S.flag[k];
+            if (st == V3_DONE) {
+                const bool pois = *reinterpret_cast<volatile unsigned char*>(&S.poison[k]) == (unsigned char)(y + 1);
+                bool ok = !pois && !relbad;
+                const int nd = (fl >> 4) & 3;
+                for (int d = 0; d < nd && ok; d++) { const unsigned tk = S.dep[k][d]; ok = __ldcg(rcode + v3_rank(tk)) == (unsigned)v3_try(tk); }   // committed with that try, nothing released
+#ifdef SSLPL_V3_DEBUG
+                if ((g.dbg & 16) && t < 64) printf("RET rank %u try %d flags %x poison %d -> %s\n", t, y, fl, (int)S.poison[k], ok ? "commit" : "redo");
+#endif
+                if (ok) {
+                    rcode[t] = (unsigned char)(y | ((fl & V3F_DIRTY) ? 0x80 : 0));
+                    if (y != 0) S.excbits[t >> 5] |= 1u << (t & 31);
+                    act = 1 | ((fl & V3F_JOB) ? 4 : 0) | (y != 0 ? 8 : 0);
+                    cnt[0]++;
+                } else {
+                    S.tryno[k] = (unsigned char)min(y + 1, 126); S.poison[k] = 0; S.flag[k] = V3F_RAN; S.wait[k] = -1;
+                    act = 2;
+                    cnt[pois ? 1 : 2]++;
+                }
+            } else {
+                rcode[t] = 0xffu;
+                if (fl & V3F_RAN) S.excbits[t >> 5] |= 1u << (t & 31);
+                act = 1 | ((fl & V3F_RAN) ? 8 : 0);
+                cnt[3]++;
+            }
+        }
+        act = __shfl_sync(0xffffffffu, act, 0);
+        if (act & 1) {
+            if (act & 4) {
+                const int nj = S.nj;
+                if (nj < g.seg_cap && lane < 13) ws.jobs[((long long)f * g.seg_cap + nj) * 13 + lane] = __ldcg(ws.sjob + ((long long)f * V3_RING + k) * 13 + lane);
+                if (lane == 0) S.nj = nj + 1;
+            }
+            __syncwarp();
+            if (lane == 0) { if (act & 8) __threadfence(); *reinterpret_cast<volatile int*>(&S.state[k]) = V3_EMPTY; __threadfence_block(); S.turn = t + 1; }
+        } else {
+            if (lane == 0) { atomicMin(&S.scanhint, (int)t); __threadfence_block(); atomicAdd(&S.nready, 1); *reinterpret_cast<volatile int*>(&S.state[k]) = V3_READY; }
+        }
+        __syncwarp();
+        progress = true;
+        if (!(act & 1)) break;                                    // the head runs again: nothing behind it can retire
+    }
+    return progress;
+}
+
+// One pass of the CLAIMER: the next 32 seeds of the ordered list are looked at together (one ticket load per lane) and every one
+// that is not used by a committed region gets the next rank and a slot — READY, or PRESUMED swallowed if it is under a live ticket.
+__device__ bool v3_claim_pass(const LineGeom& g, const LineWs& ws, int f, unsigned char* rcode) {
+    V3Shared& S = v3s();
+    const int lane = threadIdx.x & 31;
+    const LPix* pix = ws.pix + (long long)f * g.pix_stride;
+    const unsigned* seeds = ws.seeds + (long long)f * g.pix_stride;
+    const int ns = S.ns;
+    if (S.all_claimed) return false;
+    const unsigned nc = S.nclaims;
+    if (nc - S.turn >= (unsigned)(V3_RING - 33) || *reinterpret_cast<volatile int*>(&S.nready) >= (((g.dbg >> 8) & 0xff) ? ((g.dbg >> 8) & 0xff) : 1) * (int)(blockDim.x >> 5)) return false;
+    if (nc >= (unsigned)(V3_RANKS - 33)) { if (lane == 0) { S.overflow = 1; S.all_claimed = 1; } __syncwarp(); return true; }
+    const int cur = (int)S.cursor;
+    if (cur >= ns) { if (lane == 0) S.all_claimed = 1; __syncwarp(); return true; }
+    const int i = cur + lane;
+    const bool have = i < ns;
+    const unsigned mine = have ? seeds[i] : 0u;
+    unsigned m = 0; int cls = 1;
+    if (have) { m = __ldcg(&pix[mine].used); cls = m == 0u ? 0 : v3_classify(m, 0x7fffffff, rcode); }     // any live ticket is of lower rank than a new claim
+    const unsigned fm = __ballot_sync(0xffffffffu, have && cls != 1);
+    const int nfree = __popc(__ballot_sync(0xffffffffu, have && cls == 0));
+    if (have && cls != 1) {
+        const unsigned r = nc + (unsigned)__popc(fm & ((1u << lane) - 1u));
+        const int k = (int)(r & (V3_RING - 1));
+        S.seed[k] = (int)mine; S.tryno[k] = 0; S.poison[k] = 0; S.flag[k] = 0; S.wait[k] = -1;
+        if (cls != 0) S.dep[k][0] = m;
+        __threadfence_block();
+        *reinterpret_cast<volatile int*>(&S.state[k]) = cls != 0 ? V3_PRESUMED : V3_READY;
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+        if (nfree) atomicAdd(&S.nready, nfree);
+        S.cursor = (unsigned)min(cur + 32, ns);
+        __threadfence_block();
+        S.nclaims = nc + (unsigned)__popc(fm);
+    }
+    __syncwarp();
+    return true;
+}
+
+__device__ void v3_worker(const LineGeom& g, const LineWs& ws, int f, unsigned char* rcode) {
+    V3Shared& S = v3s();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WalkCtx& W = s_Wc[wid];
+    unsigned idle = 0;
+    const bool stat = (g.dbg & 32) != 0;
+    unsigned long long c_busy = 0, c_idle = 0, n_conf = 0, n_cap = 0, n_head = 0, c_abort = 0, c_idle_wait = 0;
+    for (;;) {
+        if (*reinterpret_cast<volatile int*>(&S.done)) break;
+        const long long tw0 = stat ? clock64() : 0;
+        // ---- pick the lowest runnable slot
+        const unsigned t = S.turn, nc = S.nclaims;
+        int from = max((int)t, *reinterpret_cast<volatile int*>(&S.scanhint));
+        int got = -1; bool sawready = false;
+        for (int b = from; b < (int)nc && got < 0; b += 32) {
+            const int r = b + lane;
+            bool ready = false, run = false;
+            if (r < (int)nc) {
+                const int k = r & (V3_RING - 1);
+                ready = *reinterpret_cast<volatile int*>(&S.state[k]) == V3_READY;
+                if (ready) {
+                    // an attempt that lost a pixel to a live attempt of lower rank runs again once that one has finished GROWING (its
+                    // tickets are then what it will commit with, and become a dependency) — not only after it has retired
+                    const int wt = *reinterpret_cast<volatile int*>(&S.wait[k]);
+                    if (wt == r) run = r == (int)t;                            // (out of list space / too many dependencies: only as head)
+                    else {
+                        run = wt < (int)t;
+                        if (!run && !(g.dbg & 128)) { const int sw = *reinterpret_cast<volatile int*>(&S.state[wt & (V3_RING - 1)]); run = sw != V3_READY && sw != V3_RUNNING; }
+                    }
+                }
+            }
+            const unsigned rm = __ballot_sync(0xffffffffu, run);
+            if (!sawready) {
+                const unsigned am = __ballot_sync(0xffffffffu, ready);
+                if (am) sawready = true;
+                else if (lane == 0 && b == from && b + 32 <= (int)nc) atomicCAS(&S.scanhint, from, b + 32);     // nothing READY here: later scans start further on
+            }
+            if (rm) {
+                const int r0 = b + __ffs(rm) - 1;
+                int ok = 0;
+                if (lane == 0) ok = atomicCAS(&S.state[r0 & (V3_RING - 1)], V3_READY, V3_RUNNING) == V3_READY;
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                if (ok) got = r0; else break;                     // somebody else took it: scan again
+            }
+        }
+        if (got < 0) { idle = min(idle + 1, 8u); __nanosleep(32u << min(idle, 4u)); if (stat) { const long long dd = clock64() - tw0; c_idle += dd; if (sawready) c_idle_wait += dd; } continue; }
+        idle = 0;
+        const long long tw1 = stat ? clock64() : 0;
+        if (stat) c_idle += tw1 - tw0;
+        const int r = got, k = r & (V3_RING - 1);
+        __threadfence_block();
+        const unsigned idx = (unsigned)S.seed[k];
+        const int y = S.tryno[k];
+        const bool head = r == (int)S.turn;                       // nothing of lower rank is live: the frame-sized list is free for it
+        if (lane == 0) {
+            atomicSub(&S.nready, 1);
+            W.mode = head ? 1 : 0; W.abort = 0; W.conflict = -1; W.seq = r; W.ticket = (unsigned)(r + 1) | ((unsigned)y << 24);
+            W.dirty = 0; W.ndeps = 0; W.nasm = g.dbg_seed; W.acc = 0;
+            if (head) { W.reg = ws.reg + (long long)f * g.pix_stride; W.cap = (int)g.pix_stride; }
+            else { W.reg = ws.sreg + ((long long)f * V3_MAXW + wid) * V3_LIST; W.cap = V3_LIST; }
+            W.base0 = W.reg;
+        }
+        __syncwarp();
+        LRect rec; int n0 = 0;
+        const int res = v3_one_region(g, idx, &rec, &n0);
+        __syncwarp();
+#ifdef SSLPL_V3_DEBUG
+        if ((g.dbg & 16) && lane == 0 && r < 64) printf("W%02d rank %d try %d seed (%d,%d) %s res %d abort %d conflict %d n0 %d ndeps %d [%x %x] dirty %d turn %u\n", wid, r, y, (int)(idx % (unsigned)g.sw), (int)(idx / (unsigned)g.sw), head ? "HEAD" : "spec", res, W.abort, W.conflict, n0, W.ndeps, W.dep[0], W.dep[1], W.dirty, S.turn);
+#endif
+        int res2 = res;
+        if (res >= 0 && W.dirty && W.mode == 0) {
+            // it released pixels: whether one of them belongs to a region of lower rank can only be told when it retires — the pixels
+            // it ever accepted (first growth + re-growth, W.base0[0 .. W.acc)) wait in the frame's pool
+            const int nacc = W.acc;
+            int off = 0;
+            if (lane == 0) off = atomicAdd(&S.dl_used, nacc);
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (off + nacc > V3_DPOOL) { if (lane == 0) W.abort = 1; res2 = -1; }        // pool exhausted: run it again as head
+            else {
+                unsigned* dst = ws.dlist + (long long)f * V3_DPOOL + off;
+                for (int i = lane; i < nacc; i += 32) dst[i] = W.base0[i];
+                if (lane == 0) { S.dl_off[k] = off; S.dl_n[k] = nacc; }
+            }
+            __syncwarp();
+        } else if (lane == 0) S.dl_n[k] = 0;
+        __syncwarp();
+        if (res2 >= 0) {
+            if (res == 1) l_emit_job(g, ws.sjob + ((long long)f * V3_RING + k) * 13, rec, idx, n0, lane);
+            __syncwarp();
+            if (lane == 0) {
+                const int nd = W.ndeps;
+                for (int d = 0; d < nd; d++) S.dep[k][d] = W.dep[d];
+                S.flag[k] = (unsigned char)(V3F_RAN | (res == 1 ? V3F_JOB : 0) | (W.dirty ? V3F_DIRTY : 0) | (nd << 4));
+                __threadfence();
+                *reinterpret_cast<volatile int*>(&S.state[k]) = V3_DONE;
+            }
+        } else if (lane == 0) {
+            const int ab = W.abort;
+            // (both can also come out of refine's re-growth, after this try has put tickets on pixels: the try number moves on)
+            if (ab == 4) { S.tryno[k] = (unsigned char)min(y + 1, 126); S.flag[k] = V3F_RAN; __threadfence_block(); *reinterpret_cast<volatile int*>(&S.state[k]) = V3_VOID; }   // the seed is used by a committed region
+            else if (ab == 3) { S.tryno[k] = (unsigned char)min(y + 1, 126); S.poison[k] = 0; S.flag[k] = V3F_RAN; S.dep[k][0] = (unsigned)W.conflict; __threadfence_block(); *reinterpret_cast<volatile int*>(&S.state[k]) = V3_PRESUMED; }
+            else {
+                // 2: lost a pixel to a live attempt of lower rank (run again after it has retired) or to a race (run again at once);
+                // 1 / 5: out of list space / more than two dependencies: run again as head
+                S.tryno[k] = (unsigned char)min(y + 1, 126); S.poison[k] = 0; S.flag[k] = V3F_RAN;
+                int wt = ab == 2 ? W.conflict : r;            // wait == r: only as head (turn > r - 1 is checked as wait - 1 < turn below)
+                if (y >= 100) wt = r;
+                S.wait[k] = wt;
+                atomicMin(&S.scanhint, r);
+                __threadfence_block();
+                atomicAdd(&S.nready, 1);
+                *reinterpret_cast<volatile int*>(&S.state[k]) = V3_READY;
+                n_conf++;
+            }
+        }
+        __syncwarp();
+        if (stat) { const long long d = clock64() - tw1; c_busy += d; if (res < 0) c_abort += d; if (head) n_head++; }
+    }
+    if (stat && lane == 0) {
+        atomicAdd(ws.wstat + 6, n_conf); atomicAdd(ws.wstat + 7, n_cap); atomicAdd(ws.wstat + 10, c_busy); atomicAdd(ws.wstat + 11, c_idle);
+        atomicAdd(ws.wstat + 12, c_abort); atomicAdd(ws.wstat + 15, n_head); atomicAdd(ws.wstat + 7, c_idle_wait);
+    }
+}
+
+__global__ void __launch_bounds__(V3_MAXW * 32) k_lsd_regions_v3(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
+    V3Shared& S = v3s();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int f = atomicAdd(ws.rejctl + 2, 1);
+        S.frame = f; S.turn = 0; S.nclaims = 0; S.cursor = 0; S.nj = 0; S.all_claimed = 0; S.done = 0; S.nready = 0; S.dl_used = 0; S.scanhint = 0; S.win_base = -(1 << 30); S.overflow = 0;
+        S.ns = f < nframes ? ws.nseeds[f] : 0;
+    }
+    for (int i = threadIdx.x; i < V3_RING; i += blockDim.x) { S.state[i] = V3_EMPTY; S.wait[i] = -1; S.tryno[i] = 0; S.poison[i] = 0; S.flag[i] = 0; }
+    for (int i = threadIdx.x; i < V3_RANKS / 32; i += blockDim.x) S.excbits[i] = 0u;
+    __syncthreads();
+    const int f = S.frame;
+    if (f >= nframes) break;
+    unsigned char* rcode = ws.rcode + (long long)f * V3_RANKS;
+    if (lane == 0) {
+        WalkCtx& W = s_Wc[wid];
+        W.w = g.sw; W.h = g.sh; W.dbg = g.dbg;
+        W.ang = ws.angdeg + f * g.pix_stride; W.mod = ws.modgrad + f * g.pix_stride;
+        W.pix = ws.pix + f * g.pix_stride; W.cs0 = ws.cs0 + f * g.pix_stride; W.bits = reinterpret_cast<const unsigned*>(rcode);
+    }
+    __syncwarp();
+    {
+        // warp 0 claims (and works once every seed has been claimed), warp 1 retires, the others work; with two warps, warp 0 does both
+        const bool two = blockDim.x == 64;
+        const bool stat = (g.dbg & 32) != 0;
+        unsigned long long cnt[6] = {0, 0, 0, 0, 0, 0}, c_ret = 0, c_claim = 0, c_idle = 0;
+        if (wid == 0 || (wid == 1 && !two)) {
+            for (;;) {
+                const long long t0 = stat ? clock64() : 0;
+                bool p1 = false, p2 = false;
+                if (wid == 0) p1 = v3_claim_pass(g, ws, f, rcode);
+                const long long t1 = stat ? clock64() : 0;
+                if (wid == 1 || two) {
+                    p2 = v3_retire_pass(g, ws, f, rcode, cnt);
+                    if (S.all_claimed && S.turn >= S.nclaims) { if (lane == 0) { __threadfence_block(); S.done = 1; } __syncwarp(); break; }
+                }
+                if (stat) { const long long t2 = clock64(); if (p1) c_claim += t1 - t0; else c_idle += t1 - t0; if (p2) c_ret += t2 - t1; else c_idle += t2 - t1; }
+                if (wid == 0 && !two && S.all_claimed) break;       // nothing left to claim: become a worker
+                if (!p1 && !p2) __nanosleep(32);
+            }
+            if (stat && lane == 0) {
+                for (int i = 0; i < 6; i++) atomicAdd(ws.wstat + i, cnt[i]);
+                atomicAdd(ws.wstat + 8, c_ret); atomicAdd(ws.wstat + 9, c_claim); atomicAdd(ws.wstat + 14, c_idle);
+                if (wid == 0) atomicAdd(ws.wstat + 13, (unsigned long long)S.nclaims);
+            }
+            if (wid == 0 && !two) v3_worker(g, ws, f, rcode);
+        } else v3_worker(g, ws, f, rcode);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { ws.njobs[f] = min(S.nj, g.seg_cap); if (S.nj > g.seg_cap || S.overflow) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
+  }
+}
+
 // NFA of every candidate region of every frame, in three data-parallel steps (grids are sized by the work, not by the
 // per-frame capacity seg_cap, which is ~13k slots of which a few hundred are used):
 //   k_lsd_nfa_count   one warp per job: the rectangle scan (total / aligned pixel counts)
@@ -1642,6 +2378,9 @@ struct sslpl_line {
     int sm_count = 148;
     int max_walkers = 0;        // 0 = one walker CTA per frame
     int walker_warps = 0;       // 0 = automatic (8 or 16 warps per frame)
+    int walker_v3 = 0;          // multi-warp walker: 1 = v3 (control warp + workers, O(1) retire), 0 = the round-2a form
+    int used_smem3 = 0;
+    int walker_lean = 1;        // one-warp walker: 1 = lean region growing (shipped), 0 = the round-2a form (SSLPL_WALKER_LEAN=0)
     int cur_w = 0, cur_h = 0, cur_frames = 0;
     long long launches = 0;
     int* h_err = nullptr;
@@ -1678,6 +2417,7 @@ void make_geometry(const sslpl_line* h, int W, int H, LineGeom& g, std::vector<i
     g.seg_cap = (int)(g.pix_stride / std::max(g.min_reg_size, 1)) + 16;
     g.trace_cap = h->trace ? g.seg_cap : 0;
     g.dbg = getenv("SSLPL_WALKER_DBG") ? atoi(getenv("SSLPL_WALKER_DBG")) : 0;
+    g.dbg_seed = getenv("SSLPL_WALKER_SEED") ? atoi(getenv("SSLPL_WALKER_SEED")) : -1;
     if (tab) {
         tab->assign(g.sw + g.sh, make_int2(0, 0));
         for (int axis = 0; axis < 2; axis++) {
@@ -1706,7 +2446,7 @@ void carve(sslpl_line* h, Arena& A, const LineGeom& g, int B) {
     ws.maxgrad = A.take<unsigned long long>(B);
     ws.seeds = A.take<unsigned>((size_t)B * g.pix_stride); ws.nseeds = A.take<int>(B);
     ws.reg = A.take<unsigned>((size_t)B * g.pix_stride);
-    ws.sreg = A.take<unsigned>((size_t)B * WALK_RING * WALK_SLOT_CAP); ws.sjob = A.take<double>((size_t)B * WALK_RING * 13);
+    ws.sreg = A.take<unsigned>((size_t)B * WALK_RING * WALK_SLOT_CAP); ws.sjob = A.take<double>((size_t)B * V3_RING * 13); ws.rcode = A.take<unsigned char>((size_t)B * V3_RANKS); ws.dlist = A.take<unsigned>((size_t)B * V3_DPOOL);
     ws.wstat = A.take<unsigned long long>(16);
     ws.seg = A.take<double>((size_t)B * g.seg_cap * 4); ws.nseg = A.take<int>(B);
     ws.jobs = A.take<double>((size_t)B * g.seg_cap * 13); ws.njobs = A.take<int>(B); ws.jobflag = A.take<int>((size_t)B * g.seg_cap);
@@ -1776,7 +2516,13 @@ int run_pipeline(sslpl_line* h, int B) {
         const int ww = h->walker_warps < 0 ? 0 : h->walker_warps > 0 ? std::min(h->walker_warps, WALK_MAXW) : (B >= 2 * h->sm_count ? 0 : WALK_MAXW);
         const size_t smem = (size_t)((g.pix_stride + 31) / 32) * sizeof(unsigned);
         if ((int)smem > h->used_smem) { SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); h->used_smem = (int)smem; }
-        if (ww == 0) k_lsd_regions_solo<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), 32, 0, st>>>(g, h->ws, B);   // throughput: one warp per frame
+        if (ww >= 2 && h->walker_v3) {
+            const size_t sm3 = sizeof(V3Shared) + (size_t)ww * V3_LRING * sizeof(unsigned);
+            if ((int)sm3 > h->used_smem3) { SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); h->used_smem3 = (int)sm3; }
+            k_lsd_regions_v3<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), ww * 32, sm3, st>>>(g, h->ws, B);
+        }
+        else if (ww == 0 && h->walker_lean) k_lsd_regions_lean<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), 32, 0, st>>>(g, h->ws, B);   // one warp per frame
+        else if (ww == 0) k_lsd_regions_solo<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), 32, 0, st>>>(g, h->ws, B);              // round-2a form (A/B)
         else k_lsd_regions<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), ww * 32, smem, st>>>(g, h->ws, B);
     }
     lmark(h, "lsd_regions");
@@ -1820,6 +2566,8 @@ int sslpl_line_create(const sslpl_line_params* p, sslpl_line** out) {
     h->p = *p;
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && v > 0) h->sm_count = v; }
     h->trace = getenv("SSLPL_LINE_TRACE") != nullptr;
+    if (const char* e = getenv("SSLPL_WALKER_V3")) h->walker_v3 = atoi(e) != 0;
+    if (const char* e = getenv("SSLPL_WALKER_LEAN")) h->walker_lean = atoi(e) != 0;
     if (const char* e = getenv("SSLPL_WALKER_WARPS")) h->walker_warps = std::max(-1, std::min(WALK_MAXW, atoi(e)));   // tuning knob (tests sweep it); -1 = the one-warp throughput kernel
     {   // BinaryDescriptor constructor: local (F_l) and global (F_g) Gaussian weights, widthOfBand 7, 9 bands
         double u = (7 * 3 - 1) / 2, sigma = (7 * 2 + 1) / 2, inv = -1 / (2 * sigma * sigma);
