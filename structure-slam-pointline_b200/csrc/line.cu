@@ -1502,7 +1502,10 @@ __global__ void __launch_bounds__(32, 28) k_lsd_regions_lean(const __grid_consta
 // result is looked at one step later.
 // =================================================================================================
 constexpr int V3_MAXW = 16;            // warps per CTA: 1 control + up to 15 workers
-constexpr int V3_RING = 1024;          // ranks in flight (claimed, not retired)
+#ifndef SSLPL_V3_RING
+#define SSLPL_V3_RING 1024
+#endif
+constexpr int V3_RING = SSLPL_V3_RING; // ranks in flight (claimed, not retired)
 constexpr int V3_LIST = 8192;          // list entries of a worker (ws.sreg); bigger regions are regrown as head with the frame-sized list
 constexpr int V3_LRING = 512;          // tail of the worker's list kept in shared memory
 constexpr int V3_RANKS = 65536;        // ranks per frame (exception bits, rcode bytes)
@@ -1521,6 +1524,7 @@ struct V3Shared {
     int wait[V3_RING];                   // READY: runnable once turn > wait
     int dl_off[V3_RING], dl_n[V3_RING];  // DONE, dirty: where the pixels it ever accepted are kept until it retires (ws.dlist)
     int dl_used;
+    int nblocked;                        // READY slots that wait for an attempt of lower rank (they do not count against the claim throttle)
     unsigned dep[V3_RING][2];
     unsigned char tryno[V3_RING], poison[V3_RING], flag[V3_RING];
     unsigned excbits[V3_RANKS / 32];     // rank retired with something else than "try 0 committed" although a try ran
@@ -1831,7 +1835,8 @@ __device__ bool v3_claim_pass(const LineGeom& g, const LineWs& ws, int f, unsign
     const int ns = S.ns;
     if (S.all_claimed) return false;
     const unsigned nc = S.nclaims;
-    if (nc - S.turn >= (unsigned)(V3_RING - 33) || *reinterpret_cast<volatile int*>(&S.nready) >= (((g.dbg >> 8) & 0xff) ? ((g.dbg >> 8) & 0xff) : 1) * (int)(blockDim.x >> 5)) return false;
+    if (nc - S.turn >= (unsigned)(V3_RING - 33)) { if ((g.dbg & 32) && (threadIdx.x & 31) == 0) atomicAdd(ws.wstat + 6, 1ull); return false; }
+    if (*reinterpret_cast<volatile int*>(&S.nready) - *reinterpret_cast<volatile int*>(&S.nblocked) >= (((g.dbg >> 8) & 0xff) ? ((g.dbg >> 8) & 0xff) : 1) * (int)(blockDim.x >> 5)) return false;
     if (nc >= (unsigned)(V3_RANKS - 33)) { if (lane == 0) { S.overflow = 1; S.all_claimed = 1; } __syncwarp(); return true; }
     const int cur = (int)S.cursor;
     if (cur >= ns) { if (lane == 0) S.all_claimed = 1; __syncwarp(); return true; }
@@ -1918,6 +1923,7 @@ __device__ void v3_worker(const LineGeom& g, const LineWs& ws, int f, unsigned c
         const bool head = r == (int)S.turn;                       // nothing of lower rank is live: the frame-sized list is free for it
         if (lane == 0) {
             atomicSub(&S.nready, 1);
+            if (S.wait[k] >= 0) atomicSub(&S.nblocked, 1);
             W.mode = head ? 1 : 0; W.abort = 0; W.conflict = -1; W.seq = r; W.ticket = (unsigned)(r + 1) | ((unsigned)y << 24);
             W.dirty = 0; W.ndeps = 0; W.nasm = g.dbg_seed; W.acc = 0;
             if (head) { W.reg = ws.reg + (long long)f * g.pix_stride; W.cap = (int)g.pix_stride; }
@@ -1970,6 +1976,7 @@ __device__ void v3_worker(const LineGeom& g, const LineWs& ws, int f, unsigned c
                 int wt = ab == 2 ? W.conflict : r;            // wait == r: only as head (turn > r - 1 is checked as wait - 1 < turn below)
                 if (y >= 100) wt = r;
                 S.wait[k] = wt;
+                if (wt >= 0) atomicAdd(&S.nblocked, 1);
                 atomicMin(&S.scanhint, r);
                 __threadfence_block();
                 atomicAdd(&S.nready, 1);
@@ -1993,7 +2000,7 @@ __global__ void __launch_bounds__(V3_MAXW * 32) k_lsd_regions_v3(const __grid_co
     __syncthreads();
     if (threadIdx.x == 0) {
         const int f = atomicAdd(ws.rejctl + 2, 1);
-        S.frame = f; S.turn = 0; S.nclaims = 0; S.cursor = 0; S.nj = 0; S.all_claimed = 0; S.done = 0; S.nready = 0; S.dl_used = 0; S.scanhint = 0; S.win_base = -(1 << 30); S.overflow = 0;
+        S.frame = f; S.turn = 0; S.nclaims = 0; S.cursor = 0; S.nj = 0; S.all_claimed = 0; S.done = 0; S.nready = 0; S.nblocked = 0; S.dl_used = 0; S.scanhint = 0; S.win_base = -(1 << 30); S.overflow = 0;
         S.ns = f < nframes ? ws.nseeds[f] : 0;
     }
     for (int i = threadIdx.x; i < V3_RING; i += blockDim.x) { S.state[i] = V3_EMPTY; S.wait[i] = -1; S.tryno[i] = 0; S.poison[i] = 0; S.flag[i] = 0; }
@@ -2378,7 +2385,7 @@ struct sslpl_line {
     int sm_count = 148;
     int max_walkers = 0;        // 0 = one walker CTA per frame
     int walker_warps = 0;       // 0 = automatic (8 or 16 warps per frame)
-    int walker_v3 = 0;          // multi-warp walker: 1 = v3 (control warp + workers, O(1) retire), 0 = the round-2a form
+    int walker_v3 = -1;         // multi-warp walker: 1 = v3 (control warps + workers, O(1) retire), 0 = the round-2a form, -1 = by frame size
     int used_smem3 = 0;
     int walker_lean = 1;        // one-warp walker: 1 = lean region growing (shipped), 0 = the round-2a form (SSLPL_WALKER_LEAN=0)
     int cur_w = 0, cur_h = 0, cur_frames = 0;
@@ -2513,10 +2520,15 @@ int run_pipeline(sslpl_line* h, int B) {
     SSLPL_CUDA(cudaMemsetAsync(h->ws.rejctl, 0, 4 * sizeof(int), st));
     SSLPL_CUDA(cudaMemsetAsync(h->ws.wstat, 0, 16 * sizeof(unsigned long long), st));
     {   // one CTA per frame; few frames -> more warps per frame (latency), many frames -> more CTAs per SM (throughput)
-        const int ww = h->walker_warps < 0 ? 0 : h->walker_warps > 0 ? std::min(h->walker_warps, WALK_MAXW) : (B >= 2 * h->sm_count ? 0 : WALK_MAXW);
+        // automatic choice (measured, B200): big batches -> one warp per frame (throughput); one or a few frames -> a multi-warp CTA per
+        // frame: v3 with 8 warps up to ~0.3 M detection-scale pixels (15.0 ms against 17.2 ms per 640x480 frame), the round-2a walker with
+        // 16 warps above that (69 ms against 115 ms per 1280x960 frame: v3's deeper speculation loses more work there than it overlaps)
+        const bool small = g.pix_stride <= 300000;
+        const bool v3 = h->walker_v3 > 0 || (h->walker_v3 < 0 && small);
+        const int ww = h->walker_warps < 0 ? 0 : h->walker_warps > 0 ? std::min(h->walker_warps, WALK_MAXW) : (B >= 2 * h->sm_count ? 0 : (v3 ? 8 : WALK_MAXW));
         const size_t smem = (size_t)((g.pix_stride + 31) / 32) * sizeof(unsigned);
         if ((int)smem > h->used_smem) { SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); h->used_smem = (int)smem; }
-        if (ww >= 2 && h->walker_v3) {
+        if (ww >= 2 && v3) {
             const size_t sm3 = sizeof(V3Shared) + (size_t)ww * V3_LRING * sizeof(unsigned);
             if ((int)sm3 > h->used_smem3) { SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); h->used_smem3 = (int)sm3; }
             k_lsd_regions_v3<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), ww * 32, sm3, st>>>(g, h->ws, B);
@@ -2566,7 +2578,7 @@ int sslpl_line_create(const sslpl_line_params* p, sslpl_line** out) {
     h->p = *p;
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && v > 0) h->sm_count = v; }
     h->trace = getenv("SSLPL_LINE_TRACE") != nullptr;
-    if (const char* e = getenv("SSLPL_WALKER_V3")) h->walker_v3 = atoi(e) != 0;
+    if (const char* e = getenv("SSLPL_WALKER_V3")) h->walker_v3 = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("SSLPL_WALKER_LEAN")) h->walker_lean = atoi(e) != 0;
     if (const char* e = getenv("SSLPL_WALKER_WARPS")) h->walker_warps = std::max(-1, std::min(WALK_MAXW, atoi(e)));   // tuning knob (tests sweep it); -1 = the one-warp throughput kernel
     {   // BinaryDescriptor constructor: local (F_l) and global (F_g) Gaussian weights, widthOfBand 7, 9 bands

@@ -14,6 +14,6 @@ ls.set_profiling(True)
 for _ in range(3): ls.extract_batch(frames)
 print("warps", W, {k: round(v, 2) for k, v in ls.stage_ms().items()})
 st = list(ls.walker_stats().values())
-names = ["commits", "redo_poison", "redo_dep", "void", "presumed_swallowed", "presumed_not", "abort_conflict", "worker_idle_with_waiting_ready_Mcyc", "ctl_retire_Mcyc", "ctl_claim_Mcyc",
+names = ["commits", "redo_poison", "redo_dep", "void", "presumed_swallowed", "presumed_not", "claimer_ringfull_passes(+aborts)", "worker_idle_with_waiting_ready_Mcyc", "ctl_retire_Mcyc", "ctl_claim_Mcyc",
          "worker_busy_Mcyc", "worker_idle_Mcyc", "worker_abort_Mcyc", "claims", "ctl_idle_Mcyc", "head_attempts"]
 print({n: (round(v / 1e6, 2) if n.endswith("Mcyc") else v) for n, v in zip(names, st)})
