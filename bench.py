@@ -448,7 +448,7 @@ def main():
     # synthetic sequence 0..64, split into world contiguous blocks (+ one halo frame each), extracted, matched, all-gathered; the
     # checksum of the gathered [64, cap + NL] table does not depend on N, so the lines printed at N = 1, 2, 4, 8 must agree on it.
     table_check = None
-    if 64 % world == 0:
+    if 64 % world == 0 and 64 // world + 1 <= B:            # (the handles are sized for the workload's batch: single1280 holds 17 frames)
         G = 64; per = G // world
         d_chk = torch.from_numpy(synth.batch(W, H, per + 1, start=rank * per)).to(dev)
         t_pts = torch.full((per, cap), -1, dtype=torch.int32, device=dev); t_np = torch.zeros((per,), dtype=torch.int32, device=dev)

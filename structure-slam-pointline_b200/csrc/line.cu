@@ -357,9 +357,10 @@ __shared__ __align__(16) double s_stc[WALK_MAXW][96];     // per warp: staging o
 __shared__ WalkCtx s_W1;                                   // the one-warp throughput kernel keeps its own small context:
 __shared__ __align__(16) double s_st1[96];                 // 28 of its CTAs share an SM
 constexpr int SOLO = 0;                                    // (hidden by the template parameter of the same name inside the helpers)
-// SOLO: 0 = multi-warp walker of round 2a (k_lsd_regions), 1 / 2 = one warp per frame (round-2a form / lean), 3 = multi-warp walker v3
-#define s_W (*((SOLO == 1 || SOLO == 2) ? &s_W1 : &s_Wc[threadIdx.x >> 5]))
-#define s_st ((SOLO == 1 || SOLO == 2) ? s_st1 : s_stc[threadIdx.x >> 5])
+// SOLO: 0 = multi-warp walker of round 2a (k_lsd_regions), 1 / 2 = one warp per frame (round-2a form / lean), 3 = multi-warp walker v3,
+// 4 = lane-parallel walker (one warp per frame; the cooperative routines work on the region of one lane)
+#define s_W (*((SOLO == 1 || SOLO == 2 || SOLO == 4) ? &s_W1 : &s_Wc[threadIdx.x >> 5]))
+#define s_st ((SOLO == 1 || SOLO == 2 || SOLO == 4) ? s_st1 : s_stc[threadIdx.x >> 5])
 
 // SLOT_PRESUMED: the seed was under the ticket of a live attempt of lower rank when its turn to be grown came: it is presumed
 // swallowed; the commit checks (and grows it for real if it was not).  SLOT_ABORTED: to be redone by the turn holder.
@@ -374,7 +375,7 @@ __device__ __forceinline__ bool l_live(unsigned m, int* seq_out) { const int s =
 //  poisons the releasing attempt, whose first growth went over a pixel that the sequential order gives to the lower rank)
 template <int SOLO> __device__ __forceinline__ void l_release(const WalkCtx& W, int q) {
     if (SOLO == 1 || SOLO == 2) W.pix[q].used = 0u;
-    else if (SOLO == 3) atomicCAS(&W.pix[q].used, W.ticket, W.ticket | 0x80000000u);
+    else if (SOLO == 3 || SOLO == 4) atomicCAS(&W.pix[q].used, W.ticket, W.ticket | 0x80000000u);
     else atomicCAS(&W.pix[q].used, W.ticket, 0u);
 }
 
@@ -778,7 +779,7 @@ __device__ __forceinline__ double l_distsq(double x1, double y1, double x2, doub
 template <int SOLO> __device__ __noinline__ bool l_reduce_region_radius(int* n_io, double reg_angle, double prec, double p, LRect* rec, double density, double density_th) {
     const int lane = threadIdx.x & 31, w = s_W.w;
     int n = *n_io;
-    if ((SOLO == 0 || SOLO == 3) && s_W.mode == 0) {  // speculative attempt: keep the list as it is (the commit validates every pixel ever accepted) and work on a copy
+    if ((SOLO == 0 || SOLO == 3 || SOLO == 4) && s_W.mode == 0) {  // speculative attempt: keep the list as it is (the commit validates every pixel ever accepted) and work on a copy
         if (2 * n + s_W.nasm > s_W.cap) { s_W.abort = 1; return false; }
         for (int i = lane; i < n; i += 32) s_W.reg[n + i] = s_W.reg[i];
         s_W.reg += n; s_W.cap -= n;
@@ -1429,8 +1430,10 @@ __global__ void __launch_bounds__(32, 28) k_lsd_regions_solo(const __grid_consta
   }
 }
 
-// The same loop over the frame's seeds with the LEAN region growing (l_region_grow_lean): the shipped one-warp walker.
-// k_lsd_regions_solo stays for A/B runs (SSLPL_WALKER_LEAN=0).
+// The same loop over the frame's seeds with the LEAN region growing (l_region_grow_lean).  Alone it takes the same time as
+// k_lsd_regions_solo (49.5 vs 50.6 ms for 148 frames), with several launches overlapping it is slower (38.5 vs 29.2 ms per bench
+// step): it executes 5 % MORE warp instructions (the lazy-angle bookkeeping costs what the removed FP64 saved), and a lone warp's time
+// is instructions x ~8 cycles.  Kept for A/B runs (SSLPL_WALKER_LEAN=1) and as the base of the v3 and lane-parallel growth.
 __global__ void __launch_bounds__(32, 28) k_lsd_regions_lean(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
     const int lane = threadIdx.x;
   for (;;) {
@@ -1827,7 +1830,7 @@ __device__ bool v3_retire_pass(const LineGeom& g, const LineWs& ws, int f, unsig
 
 // One pass of the CLAIMER: the next 32 seeds of the ordered list are looked at together (one ticket load per lane) and every one
 // that is not used by a committed region gets the next rank and a slot — READY, or PRESUMED swallowed if it is under a live ticket.
-__device__ bool v3_claim_pass(const LineGeom& g, const LineWs& ws, int f, unsigned char* rcode) {
+__device__ bool v3_claim_pass(const LineGeom& g, const LineWs& ws, int f, unsigned char* rcode, int limit = 0) {
     V3Shared& S = v3s();
     const int lane = threadIdx.x & 31;
     const LPix* pix = ws.pix + (long long)f * g.pix_stride;
@@ -1836,7 +1839,7 @@ __device__ bool v3_claim_pass(const LineGeom& g, const LineWs& ws, int f, unsign
     if (S.all_claimed) return false;
     const unsigned nc = S.nclaims;
     if (nc - S.turn >= (unsigned)(V3_RING - 33)) { if ((g.dbg & 32) && (threadIdx.x & 31) == 0) atomicAdd(ws.wstat + 6, 1ull); return false; }
-    if (*reinterpret_cast<volatile int*>(&S.nready) - *reinterpret_cast<volatile int*>(&S.nblocked) >= (((g.dbg >> 8) & 0xff) ? ((g.dbg >> 8) & 0xff) : 1) * (int)(blockDim.x >> 5)) return false;
+    if (*reinterpret_cast<volatile int*>(&S.nready) - *reinterpret_cast<volatile int*>(&S.nblocked) >= (limit ? limit : (((g.dbg >> 8) & 0xff) ? ((g.dbg >> 8) & 0xff) : 1) * (int)(blockDim.x >> 5))) return false;
     if (nc >= (unsigned)(V3_RANKS - 33)) { if (lane == 0) { S.overflow = 1; S.all_claimed = 1; } __syncwarp(); return true; }
     const int cur = (int)S.cursor;
     if (cur >= ns) { if (lane == 0) S.all_claimed = 1; __syncwarp(); return true; }
@@ -2045,6 +2048,439 @@ __global__ void __launch_bounds__(V3_MAXW * 32) k_lsd_regions_v3(const __grid_co
     }
     __syncthreads();
     if (threadIdx.x == 0) { ws.njobs[f] = min(S.nj, g.seg_cap); if (S.nj > g.seg_cap || S.overflow) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
+  }
+}
+
+// =================================================================================================
+// LANE-PARALLEL region walker (round 2b, k_lsd_regions_lanes): ONE WARP PER FRAME, every LANE grows its own region.
+// The one-warp walkers spend ~230 warp instructions per growth step on 32 neighbour tests of ONE region, almost all of it
+// warp-uniform bookkeeping: a lone warp retires one instruction every ~8 cycles, so the stage is bound by instruction count.
+// Here region growing is the plain scalar loop of lsd.cpp run by each lane on a different seed (same protocol as the multi-warp
+// walker v3: ranks in seed order, tickets in LPix.used, poison / dependencies / released-pixel lists, strictly ordered retire —
+// v3_retire_pass and v3_claim_pass are used as they are), so that one warp instruction serves up to 32 regions.  A neighbour is
+// accepted with a SYNCHRONOUS compare-and-swap (nothing to roll back, no "lost a pixel" aborts).  The region angle is lazy per
+// lane (exact fastAtan2 only when a test is within the drift bound of the threshold).  What is cheap per region but long in code
+// — rectangle fit with its ordered double sums, density, refine's release and tau, reduce_region_radius — runs warp-cooperatively
+// with the existing routines (template mode 4) for one finished lane at a time.
+// =================================================================================================
+constexpr int LN_LIST = 4096;          // list entries per lane (32 lanes x 4096 = ws.sreg of a frame); bigger regions run as head on ws.reg
+enum { LN_IDLE = 0, LN_GROW = 1, LN_POST = 2 };
+
+template <int SOLO> __device__ __forceinline__ bool l4_exact_pass(float a, float th, float pdeg, double prec) {
+    const float d = fabsf(th - a);
+    const float e = d > 270.f ? 360.f - d : d;
+    bool pass = e <= pdeg;
+    if (fabsf(e - pdeg) < 2e-3f || fabsf(d - 270.f) < 2e-3f) pass = l_aligned_rad((double)a * L_DEG, (double)th * L_DEG, prec);
+    return pass;
+}
+
+// refine, first half (lsd.cpp refine up to the re-growth): nothing to do if the density is fine (returns true); otherwise every
+// pixel is released, tau is formed from the angles near the seed and, for a speculative attempt, the list pointer moves behind the
+// first list (which stays: every pixel ever accepted is looked at when the attempt retires).
+__device__ __noinline__ bool l4_refine_begin(int n, const LRect* rec, double density_th, double* tau_out) {
+    constexpr int SOLO = 4;
+    const int lane = threadIdx.x & 31, w = s_W.w;
+    const double density = (double)n / (l_dist(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
+    if (density >= density_th) return true;
+    if (lane == 0) s_W.dirty = 1;
+    const unsigned* reg = s_W.reg; const float* __restrict__ ang = s_W.ang;
+    const unsigned p0 = reg[0];
+    const int sx = p0 & 0xffff, sy = p0 >> 16;
+    const double xc = (double)sx, yc = (double)sy;
+    const double ang_c = (double)ang[sy * w + sx] * L_DEG;
+    const double width = rec->width;
+    double* s0 = s_st; double* s1 = s_st + 32;
+    const double* sp = s_st + (lane & 1) * 32;
+    double acc = 0; int cnt = 0;
+#pragma unroll 1
+    for (int b = 0; b < n; b += 32) {
+        const int i = b + lane;
+        bool in = false;
+        if (i < n) {
+            const unsigned pk = reg[i]; const int rx = pk & 0xffff, ry = pk >> 16;
+            const float ad = ang[ry * w + rx];
+            l_release<SOLO>(s_W, ry * w + rx);
+            in = l_dist(xc, yc, (double)rx, (double)ry) < width;
+            const double d = l_angle_diff_signed((double)ad * L_DEG, ang_c);
+            s0[lane] = in ? d : 0.0; s1[lane] = in ? d * d : 0.0;
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, in));
+        __syncwarp();
+        acc = l_chunk_sum<SOLO>(sp, min(32, n - b), acc);
+        __syncwarp();
+    }
+    const double sum = __shfl_sync(0xffffffffu, acc, 0), s_sum = __shfl_sync(0xffffffffu, acc, 1);
+    const double mean_angle = sum / (double)cnt;
+    *tau_out = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
+    __syncwarp();
+    return false;
+}
+
+struct LaneAtt {
+    int st, slot, rank, mode, phase, tryno;
+    unsigned T;
+    unsigned* list; int cap;          // the list being grown (behind the first list during a speculative re-growth)
+    int i, n, kacc, n0, acc;
+    float sx, sy, th, rM, pdeg, coefX; double prec; int robok;
+    int ndeps; unsigned dep0, dep1;
+    int abortc, conflict, dirty;
+    unsigned seedidx;
+};
+
+struct LaneFrame { int w, h; LPix* pix; const float* ang; const float2* cs0; const unsigned char* rcode; };
+
+// take pixel q (ticket seen in `m`) for the lane's attempt: 1 taken, 0 it is used after all (committed, or held by a live attempt of
+// lower rank: recorded as a dependency), -1 give up (abortc set)
+__device__ __forceinline__ int ln_take(LaneAtt& A, const LaneFrame& F, int q, unsigned m) {
+    for (int tries = 0; tries < 8; tries++) {
+        const unsigned old = A.mode ? atomicExch(&F.pix[q].used, A.T) : atomicCAS(&F.pix[q].used, m, A.T);
+        if (A.mode || old == m) {
+            const unsigned o = old & 0x7fffffffu;
+            if (o != 0u && o != A.T && v3_classify(o, A.rank, F.rcode) == 3) v3_poison(o);
+            return 1;
+        }
+        m = old;                                                  // somebody changed it in between: look again
+        if (m == A.T) return 0;
+        const int c = m == 0u ? 0 : v3_classify(m, A.rank, F.rcode);
+        if (c == 1) return 0;
+        if (c == 2) {
+            if (!((A.ndeps > 0 && A.dep0 == m) || (A.ndeps > 1 && A.dep1 == m))) { if (A.ndeps == 0) A.dep0 = m; else if (A.ndeps == 1) A.dep1 = m; else { A.abortc = 5; return -1; } A.ndeps++; }
+            return 0;
+        }
+    }
+    A.abortc = 5;                                                 // contended: run it again as head
+    return -1;
+}
+
+// start (or restart, for refine's re-growth) the growth of the lane's attempt from its seed with tolerance prec
+__device__ __forceinline__ void ln_begin(LaneAtt& A, const LaneFrame& F, double prec) {
+    const int sq = (int)A.seedidx;
+    const unsigned m0 = __ldcg(&F.pix[sq].used);
+    if (m0 != A.T) {
+        const int c = m0 == 0u ? 0 : v3_classify(m0, A.rank, F.rcode);
+        if (c == 1) { A.abortc = 4; return; }
+        if (c == 2) { A.abortc = 3; A.conflict = (int)m0; return; }
+        const int t = ln_take(A, F, sq, m0);
+        if (t == 0) { A.abortc = 2; A.conflict = -1; return; }   // lost the seed between the look and the take: look again from the start
+        if (t < 0) return;
+    }
+    A.list[0] = (unsigned)(sq % F.w) | ((unsigned)(sq / F.w) << 16);
+    A.n = 1; A.i = 0; A.kacc = 0;
+    A.th = __ldg(F.ang + sq);
+    const float2 c0 = __ldg(F.cs0 + sq);
+    A.sx = c0.x; A.sy = c0.y; A.rM = rsqrtf(c0.x * c0.x + c0.y * c0.y);
+    A.prec = prec; A.pdeg = (float)(prec * (180.0 / L_PI));
+    A.robok = prec < 0.78;
+    A.coefX = (float)(57.2958 * 1.0002 * sin(prec + 0.17453 + 0.0006));     // vectors accepted within prec + 10 deg of the sums at the last exact angle
+    A.st = LN_GROW;
+}
+
+// one queue entry of the lane's region: the 3x3 scan of lsd.cpp's region_grow, neighbour by neighbour, in order
+__device__ __forceinline__ void ln_step(LaneAtt& A, const LaneFrame& F) {
+    const unsigned pk = A.list[A.i];
+    const int x0 = (int)(pk & 0xffff), y0 = (int)(pk >> 16);
+    uint4 v[8]; int qq[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {                                  // the eight records in flight together
+        const int nb = j + (j >= 4 ? 1 : 0);                       // 0..8 without the centre (4)
+        const int xx = x0 + nb % 3 - 1, yy = y0 + nb / 3 - 1;
+        const bool ok = (unsigned)xx < (unsigned)F.w && (unsigned)yy < (unsigned)F.h;
+        qq[j] = ok ? yy * F.w + xx : -1;
+        v[j] = make_uint4(__float_as_uint(NOTDEF_F), 0u, 0u, 0u);
+        if (ok) v[j] = __ldcg(reinterpret_cast<const uint4*>(F.pix + qq[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (A.abortc) break;
+        const float a = __uint_as_float(v[j].x);
+        const unsigned m = v[j].w;
+        if (qq[j] < 0 || a == NOTDEF_F || m == A.T) continue;
+        if (m != 0u) {
+            const int c = v3_classify(m, A.rank, F.rcode);
+            if (c == 1) continue;
+            if (c == 2) {
+                if (!((A.ndeps > 0 && A.dep0 == m) || (A.ndeps > 1 && A.dep1 == m))) { if (A.ndeps == 0) A.dep0 = m; else if (A.ndeps == 1) A.dep1 = m; else { A.abortc = 5; break; } A.ndeps++; }
+                continue;
+            }
+        }
+        // the alignment test against the region angle as the sequential scan has it now
+        bool pass;
+        if (A.kacc == 0) pass = l4_exact_pass<4>(a, A.th, A.pdeg, A.prec);
+        else {
+            const float d = fabsf(A.th - a);
+            const float e = d > 270.f ? 360.f - d : d;
+            const float B = A.coefX * (float)A.kacc * A.rM + 0.0215f;
+            const bool ok = A.robok && B <= 10.f;
+            if (ok && e <= A.pdeg - B) pass = true;
+            else if (ok && e >= A.pdeg + B) pass = false;
+            else {
+                A.th = fast_atan2_deg(A.sy, A.sx); A.rM = rsqrtf(A.sx * A.sx + A.sy * A.sy); A.kacc = 0;
+                pass = l4_exact_pass<4>(a, A.th, A.pdeg, A.prec);
+            }
+        }
+        if (!pass) continue;
+        if (A.n >= A.cap) { A.abortc = 1; break; }
+        const int t = ln_take(A, F, qq[j], m);
+        if (t < 0) break;
+        if (t == 0) continue;
+        const int nb = j + (j >= 4 ? 1 : 0);
+        A.list[A.n++] = (unsigned)(x0 + nb % 3 - 1) | ((unsigned)(y0 + nb / 3 - 1) << 16);
+        A.sx += __uint_as_float(v[j].y); A.sy += __uint_as_float(v[j].z);
+        A.kacc++;
+    }
+    A.i++;
+}
+
+__global__ void __launch_bounds__(32, 8) k_lsd_regions_lanes(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
+    constexpr int SOLO = 4;
+    V3Shared& S = v3s();
+    const int lane = threadIdx.x;
+    const unsigned lt = (1u << lane) - 1u;
+  for (;;) {
+    __syncwarp();
+    if (lane == 0) {
+        const int f = atomicAdd(ws.rejctl + 2, 1);
+        S.frame = f; S.turn = 0; S.nclaims = 0; S.cursor = 0; S.nj = 0; S.all_claimed = 0; S.done = 0; S.nready = 0; S.nblocked = 0; S.dl_used = 0; S.scanhint = 0; S.win_base = -(1 << 30); S.overflow = 0;
+        S.ns = f < nframes ? ws.nseeds[f] : 0;
+    }
+    for (int i = lane; i < V3_RING; i += 32) { S.state[i] = V3_EMPTY; S.wait[i] = -1; S.tryno[i] = 0; S.poison[i] = 0; S.flag[i] = 0; S.dl_n[i] = 0; }
+    for (int i = lane; i < V3_RANKS / 32; i += 32) S.excbits[i] = 0u;
+    __syncwarp();
+    const int f = S.frame;
+    if (f >= nframes) break;
+    unsigned char* rcode = ws.rcode + (long long)f * V3_RANKS;
+    LaneFrame F; F.w = g.sw; F.h = g.sh; F.pix = ws.pix + f * g.pix_stride; F.ang = ws.angdeg + f * g.pix_stride; F.cs0 = ws.cs0 + f * g.pix_stride; F.rcode = rcode;
+    if (lane == 0) {
+        WalkCtx& W = s_W1;
+        W.w = g.sw; W.h = g.sh; W.dbg = g.dbg;
+        W.ang = F.ang; W.mod = ws.modgrad + f * g.pix_stride; W.pix = F.pix; W.cs0 = F.cs0; W.bits = reinterpret_cast<const unsigned*>(rcode);
+    }
+    __syncwarp();
+    unsigned* const mylist = ws.sreg + ((long long)f * 32 + lane) * LN_LIST;
+    unsigned* const biglist = ws.reg + (long long)f * g.pix_stride;
+    LaneAtt A; A.st = LN_IDLE; A.abortc = 0; A.ndeps = 0; A.dep0 = A.dep1 = 0u; A.n = 0; A.i = 0; A.kacc = 0; A.mode = 0; A.phase = 0; A.dirty = 0; A.acc = 0; A.n0 = 0;
+    A.slot = 0; A.rank = 0; A.tryno = 0; A.T = 0u; A.list = mylist; A.cap = LN_LIST; A.sx = A.sy = A.th = A.rM = A.pdeg = A.coefX = 0.f; A.prec = 0; A.robok = 0; A.conflict = -1; A.seedidx = 0u;
+    unsigned long long dummy[6] = {0, 0, 0, 0, 0, 0};
+    const bool stat = (g.dbg & 32) != 0;
+    unsigned long long c_ret = 0, c_asg = 0, c_grow = 0, c_post = 0, n_iter = 0, n_round = 0, n_act = 0, n_post = 0;
+    for (;;) {
+        const long long q0 = stat ? clock64() : 0;
+        // ---- retire the head of the ring while it is finished (the whole warp, cooperatively)
+        {
+            const unsigned t = S.turn;
+            const int hs = t < S.nclaims ? *reinterpret_cast<volatile int*>(&S.state[t & (V3_RING - 1)]) : V3_EMPTY;
+            if (hs == V3_DONE || hs == V3_PRESUMED || hs == V3_VOID) v3_retire_pass(g, ws, f, rcode, dummy);
+        }
+        if (S.all_claimed && S.turn >= S.nclaims) break;
+        const long long q1 = stat ? clock64() : 0;
+        // ---- finished lanes that need no cooperative work publish their own slot: regions below the minimum size, and every abort
+        if (A.st == LN_POST && (A.abortc || (A.phase == 0 && A.n < g.min_reg_size))) {
+            const int slot = A.slot, y = A.tryno;
+            if (!A.abortc) {
+                S.dep[slot][0] = A.dep0; S.dep[slot][1] = A.dep1; S.dl_n[slot] = 0;
+                S.flag[slot] = (unsigned char)(V3F_RAN | (A.ndeps << 4));
+                __threadfence_block();
+                *reinterpret_cast<volatile int*>(&S.state[slot]) = V3_DONE;
+            } else if (A.abortc == 4) { S.tryno[slot] = (unsigned char)min(y + 1, 126); S.flag[slot] = V3F_RAN; __threadfence_block(); *reinterpret_cast<volatile int*>(&S.state[slot]) = V3_VOID; }
+            else if (A.abortc == 3) { S.tryno[slot] = (unsigned char)min(y + 1, 126); S.poison[slot] = 0; S.flag[slot] = V3F_RAN; S.dep[slot][0] = (unsigned)A.conflict; __threadfence_block(); *reinterpret_cast<volatile int*>(&S.state[slot]) = V3_PRESUMED; }
+            else {
+                S.tryno[slot] = (unsigned char)min(y + 1, 126); S.poison[slot] = 0; S.flag[slot] = V3F_RAN;
+                int wt = A.abortc == 2 ? A.conflict : A.rank;
+                if (y >= 100) wt = A.rank;
+                S.wait[slot] = wt;
+                if (wt >= 0) atomicAdd(&S.nblocked, 1);
+                atomicMin(&S.scanhint, A.rank);
+                __threadfence_block();
+                atomicAdd(&S.nready, 1);
+                *reinterpret_cast<volatile int*>(&S.state[slot]) = V3_READY;
+            }
+            A.st = LN_IDLE; A.abortc = 0;
+        }
+        __syncwarp();
+        const unsigned idle = __ballot_sync(0xffffffffu, A.st == LN_IDLE);
+        if (idle) {
+            for (int pass = 0; pass < 3 && !S.all_claimed && *reinterpret_cast<volatile int*>(&S.nready) - *reinterpret_cast<volatile int*>(&S.nblocked) < __popc(idle) + 8; pass++)
+                if (!v3_claim_pass(g, ws, f, rcode, 1 << 20)) break;
+            // ---- hand runnable slots to the idle lanes, lowest ranks first
+            const unsigned t = S.turn, nc = S.nclaims;
+            int from = max((int)t, *reinterpret_cast<volatile int*>(&S.scanhint));
+            unsigned left = idle;
+            bool sawready = false;
+            for (int b = from; b < (int)nc && left; b += 32) {
+                const int r = b + lane;
+                bool ready = false, run = false;
+                if (r < (int)nc) {
+                    const int k = r & (V3_RING - 1);
+                    ready = *reinterpret_cast<volatile int*>(&S.state[k]) == V3_READY;
+                    if (ready) {
+                        const int wt = *reinterpret_cast<volatile int*>(&S.wait[k]);
+                        if (wt == r) run = r == (int)t;
+                        else { run = wt < (int)t; if (!run) { const int sw = *reinterpret_cast<volatile int*>(&S.state[wt & (V3_RING - 1)]); run = sw != V3_READY && sw != V3_RUNNING; } }
+                    }
+                }
+                const unsigned rm = __ballot_sync(0xffffffffu, run);
+                if (!sawready) { if (__ballot_sync(0xffffffffu, ready)) sawready = true; else if (lane == 0 && b == from && b + 32 <= (int)nc) atomicCAS(&S.scanhint, from, b + 32); }
+                // the j-th idle lane takes the j-th runnable slot of this block
+                const int take = min(__popc(rm), __popc(left));
+                if (take) {
+                    const bool mine = ((left >> lane) & 1u) && __popc(left & lt) < take;
+                    if (mine) {
+                        const int r0 = b + (int)__fns(rm, 0, __popc(left & lt) + 1);
+                        const int k = r0 & (V3_RING - 1);
+                        *reinterpret_cast<volatile int*>(&S.state[k]) = V3_RUNNING;       // one warp per frame: nobody competes for the slot
+                        atomicSub(&S.nready, 1);
+                        if (S.wait[k] >= 0) atomicSub(&S.nblocked, 1);
+                        A.slot = k; A.rank = r0; A.tryno = S.tryno[k]; A.seedidx = (unsigned)S.seed[k];
+                        A.T = (unsigned)(r0 + 1) | ((unsigned)A.tryno << 24);
+                        A.mode = r0 == (int)t ? 1 : 0;
+                        A.list = A.mode ? biglist : mylist; A.cap = A.mode ? (int)g.pix_stride : LN_LIST;
+                        A.phase = 0; A.abortc = 0; A.conflict = -1; A.ndeps = 0; A.dirty = 0; A.acc = 0; A.n0 = 0; A.n = 0; A.i = 0;
+                        ln_begin(A, F, g.prec);
+                        if (A.abortc) A.st = LN_POST;              // (settled at the top of the next iteration)
+                    }
+                    left &= ~__ballot_sync(0xffffffffu, mine);
+                }
+            }
+        }
+        const long long q2 = stat ? clock64() : 0;
+        // ---- growth: every busy lane expands one queue entry of its own region
+        {
+            if (stat) { n_round++; n_act += __popc(__ballot_sync(0xffffffffu, A.st == LN_GROW)); }
+            if (A.st == LN_GROW) {
+                if (A.mode == 0 && *reinterpret_cast<volatile unsigned char*>(&S.poison[A.slot]) == (unsigned char)(A.tryno + 1)) { A.abortc = 2; A.conflict = -1; }
+                if (!A.abortc && A.i < A.n) ln_step(A, F);
+                if (A.abortc || A.i >= A.n) A.st = LN_POST;
+            }
+            __syncwarp();
+        }
+        const long long q3 = stat ? clock64() : 0;
+        if (stat) { c_ret += q1 - q0; c_asg += q2 - q1; c_grow += q3 - q2; n_iter++; }
+        // ---- post: one finished lane at a time, the warp works on its region together (lowest rank first)
+        for (;;) {
+            const bool coop = A.st == LN_POST && !A.abortc && !(A.phase == 0 && A.n < g.min_reg_size);
+            const unsigned pm = __ballot_sync(0xffffffffu, coop);
+            if (!pm) { if (stat) c_post += clock64() - q3; break; }
+            n_post++;
+            int best = coop ? A.rank : 0x7fffffff;
+            best = __reduce_min_sync(0xffffffffu, best);
+            const int L = __ffs(__ballot_sync(0xffffffffu, coop && A.rank == best)) - 1;
+            // the lane's attempt, broadcast
+            const int abortc = __shfl_sync(0xffffffffu, A.abortc, L), slot = __shfl_sync(0xffffffffu, A.slot, L), rank = __shfl_sync(0xffffffffu, A.rank, L);
+            const int mode = __shfl_sync(0xffffffffu, A.mode, L), phase = __shfl_sync(0xffffffffu, A.phase, L), tryno = __shfl_sync(0xffffffffu, A.tryno, L);
+            int n = __shfl_sync(0xffffffffu, A.n, L);
+            const unsigned long long lp = __shfl_sync(0xffffffffu, (unsigned long long)A.list, L);
+            unsigned* list = reinterpret_cast<unsigned*>(lp);
+            const int cap = __shfl_sync(0xffffffffu, A.cap, L);
+            const unsigned T = __shfl_sync(0xffffffffu, A.T, L), seedidx = __shfl_sync(0xffffffffu, A.seedidx, L);
+            int res = -1;            // -1 aborted, 0 no job, 1 job, 2 keeps growing (re-growth started)
+            LRect rec;
+            if (!abortc) {
+                // region angle at the end of the growth: exact
+                float th = __shfl_sync(0xffffffffu, A.th, L);
+                { const float sx = __shfl_sync(0xffffffffu, A.sx, L), sy = __shfl_sync(0xffffffffu, A.sy, L); if (__shfl_sync(0xffffffffu, A.kacc, L) > 0) th = fast_atan2_deg(sy, sx); }
+                double reg_angle = (double)th * L_DEG;
+                __syncwarp();
+                if (lane == 0) { WalkCtx& W = s_W1; W.reg = list; W.base0 = mode ? biglist : (ws.sreg + ((long long)f * 32 + L) * LN_LIST); W.cap = cap; W.mode = mode; W.ticket = T; W.seq = rank; W.abort = 0; W.dirty = 0; W.nasm = 0; }
+                __syncwarp();
+                int n0 = __shfl_sync(0xffffffffu, A.n0, L), acc = __shfl_sync(0xffffffffu, A.acc, L);
+                if (phase == 0) {
+                    n0 = n; acc = n;
+                    if (lane == 0) s_W1.acc = acc;
+                    __syncwarp();
+                    if (n < g.min_reg_size) res = 0;
+                    else {
+                        l_region2rect<SOLO>(n, reg_angle, g.prec, g.p, &rec);
+                        double tau;
+                        if (l4_refine_begin(n, &rec, 0.7, &tau)) res = 1;
+                        else {
+                            // re-growth from the seed with tolerance tau: the lane goes back to growing (behind its first list if speculative)
+                            if (lane == L) {
+                                A.dirty = 1; A.phase = 1; A.n0 = n0; A.acc = acc;
+                                if (mode == 0) { A.list += n; A.cap -= n; }
+                                if (A.cap < 8) A.abortc = 1; else ln_begin(A, F, tau);
+                                if (A.abortc) A.st = LN_POST;         // settled in the next round of this loop
+                            }
+                            res = 2;
+                        }
+                    }
+                } else {
+                    if (mode == 0) acc += n;
+                    if (lane == 0) { s_W1.acc = acc; s_W1.dirty = 1; }
+                    __syncwarp();
+                    if (n < 2) res = 0;
+                    else {
+                        l_region2rect<SOLO>(n, reg_angle, g.prec, g.p, &rec);
+                        const double density = (double)n / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+                        bool okr = true;
+                        if (density < 0.7) { int nn = n; okr = l_reduce_region_radius<SOLO>(&nn, reg_angle, g.prec, g.p, &rec, density, 0.7); if (s_W1.abort) okr = false; }
+                        res = s_W1.abort ? -1 : (okr ? 1 : 0);
+                    }
+                }
+                __syncwarp();
+                if (res == 2) continue;
+                // publish
+                const int dirty = phase == 1 ? 1 : 0;
+                int res2 = res;
+                if (res >= 0 && dirty && mode == 0) {
+                    int off = 0;
+                    if (lane == 0) off = atomicAdd(&S.dl_used, acc);
+                    off = __shfl_sync(0xffffffffu, off, 0);
+                    if (off + acc > V3_DPOOL) res2 = -2;
+                    else {
+                        unsigned* dst = ws.dlist + (long long)f * V3_DPOOL + off;
+                        const unsigned* src = ws.sreg + ((long long)f * 32 + L) * LN_LIST;
+                        for (int i = lane; i < acc; i += 32) dst[i] = src[i];
+                        if (lane == 0) { S.dl_off[slot] = off; S.dl_n[slot] = acc; }
+                    }
+                } else if (lane == 0) S.dl_n[slot] = 0;
+                __syncwarp();
+                if (res2 >= 0) {
+                    if (res == 1) l_emit_job(g, ws.sjob + ((long long)f * V3_RING + slot) * 13, rec, seedidx, n0, lane);
+                    __syncwarp();
+                    const int nd = __shfl_sync(0xffffffffu, A.ndeps, L);
+                    const unsigned d0 = __shfl_sync(0xffffffffu, A.dep0, L), d1 = __shfl_sync(0xffffffffu, A.dep1, L);
+                    if (lane == 0) {
+                        S.dep[slot][0] = d0; S.dep[slot][1] = d1;
+                        S.flag[slot] = (unsigned char)(V3F_RAN | (res == 1 ? V3F_JOB : 0) | (dirty ? V3F_DIRTY : 0) | (nd << 4));
+                        __threadfence();
+                        *reinterpret_cast<volatile int*>(&S.state[slot]) = V3_DONE;
+                    }
+                    __syncwarp();
+                    if (lane == L) A.st = LN_IDLE;
+                    continue;
+                }
+            }
+            // aborted (by the growth, by the cooperative part, or no room for its released-pixel list)
+            {
+                int ab = abortc ? abortc : (res == -1 ? (s_W1.abort ? s_W1.abort : 1) : 1);
+                const int conflict = __shfl_sync(0xffffffffu, A.conflict, L);
+                if (lane == 0) {
+                    const int y = tryno;
+                    if (ab == 4) { S.tryno[slot] = (unsigned char)min(y + 1, 126); S.flag[slot] = V3F_RAN; __threadfence_block(); *reinterpret_cast<volatile int*>(&S.state[slot]) = V3_VOID; }
+                    else if (ab == 3) { S.tryno[slot] = (unsigned char)min(y + 1, 126); S.poison[slot] = 0; S.flag[slot] = V3F_RAN; S.dep[slot][0] = (unsigned)conflict; __threadfence_block(); *reinterpret_cast<volatile int*>(&S.state[slot]) = V3_PRESUMED; }
+                    else {
+                        S.tryno[slot] = (unsigned char)min(y + 1, 126); S.poison[slot] = 0; S.flag[slot] = V3F_RAN;
+                        int wt = ab == 2 ? conflict : rank;
+                        if (y >= 100) wt = rank;
+                        S.wait[slot] = wt;
+                        if (wt >= 0) atomicAdd(&S.nblocked, 1);
+                        atomicMin(&S.scanhint, rank);
+                        __threadfence_block();
+                        atomicAdd(&S.nready, 1);
+                        *reinterpret_cast<volatile int*>(&S.state[slot]) = V3_READY;
+                    }
+                }
+                __syncwarp();
+                if (lane == L) { A.st = LN_IDLE; A.abortc = 0; }
+            }
+        }
+    }
+    __syncwarp();
+    if (stat && lane == 0) {
+        atomicAdd(ws.wstat + 0, n_iter); atomicAdd(ws.wstat + 1, n_round); atomicAdd(ws.wstat + 2, n_act); atomicAdd(ws.wstat + 3, n_post);
+        atomicAdd(ws.wstat + 8, c_ret); atomicAdd(ws.wstat + 9, c_asg); atomicAdd(ws.wstat + 10, c_grow); atomicAdd(ws.wstat + 11, c_post); atomicAdd(ws.wstat + 13, (unsigned long long)S.nclaims);
+    }
+    if (lane == 0) { ws.njobs[f] = min(S.nj, g.seg_cap); if (S.nj > g.seg_cap || S.overflow) atomicOr(ws.err, DERR_LSD_OVERFLOW); }
   }
 }
 
@@ -2385,9 +2821,10 @@ struct sslpl_line {
     int sm_count = 148;
     int max_walkers = 0;        // 0 = one walker CTA per frame
     int walker_warps = 0;       // 0 = automatic (8 or 16 warps per frame)
-    int walker_v3 = -1;         // multi-warp walker: 1 = v3 (control warps + workers, O(1) retire), 0 = the round-2a form, -1 = by frame size
-    int used_smem3 = 0;
-    int walker_lean = 1;        // one-warp walker: 1 = lean region growing (shipped), 0 = the round-2a form (SSLPL_WALKER_LEAN=0)
+    int walker_v3 = 0;          // multi-warp walker: 0 = the round-2a form (shipped), 1 = v3 (control warps + workers, O(1) retire), -1 = v3 by frame size
+    int used_smem3 = 0, used_smem4 = 0;
+    int walker_lanes = 0;       // one warp per frame, lane-parallel region growing (SSLPL_WALKER_LANES=1)
+    int walker_lean = 0;        // one-warp walker: 0 = the round-2a form (shipped: faster when several launches overlap), 1 = lean region growing (SSLPL_WALKER_LEAN=1)
     int cur_w = 0, cur_h = 0, cur_frames = 0;
     long long launches = 0;
     int* h_err = nullptr;
@@ -2521,14 +2958,20 @@ int run_pipeline(sslpl_line* h, int B) {
     SSLPL_CUDA(cudaMemsetAsync(h->ws.wstat, 0, 16 * sizeof(unsigned long long), st));
     {   // one CTA per frame; few frames -> more warps per frame (latency), many frames -> more CTAs per SM (throughput)
         // automatic choice (measured, B200): big batches -> one warp per frame (throughput); one or a few frames -> a multi-warp CTA per
-        // frame: v3 with 8 warps up to ~0.3 M detection-scale pixels (15.0 ms against 17.2 ms per 640x480 frame), the round-2a walker with
-        // 16 warps above that (69 ms against 115 ms per 1280x960 frame: v3's deeper speculation loses more work there than it overlaps)
+        // frame, the round-2a walker with 16 warps.  v3 (SSLPL_WALKER_V3=1, 8 warps) is level with it on 640x480 frames (15.0-17.0 ms over
+        // runs against 17.2 ms) and behind on 1280x960 (115 ms against 69 ms: its deeper speculation loses more work than it overlaps), so
+        // it is not the default; SSLPL_WALKER_V3=-1 picks it by frame size (up to ~0.3 M detection-scale pixels)
         const bool small = g.pix_stride <= 300000;
         const bool v3 = h->walker_v3 > 0 || (h->walker_v3 < 0 && small);
         const int ww = h->walker_warps < 0 ? 0 : h->walker_warps > 0 ? std::min(h->walker_warps, WALK_MAXW) : (B >= 2 * h->sm_count ? 0 : (v3 ? 8 : WALK_MAXW));
         const size_t smem = (size_t)((g.pix_stride + 31) / 32) * sizeof(unsigned);
         if ((int)smem > h->used_smem) { SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); h->used_smem = (int)smem; }
-        if (ww >= 2 && v3) {
+        if (h->walker_lanes && ww == 0) {
+            const size_t sm4 = sizeof(V3Shared);
+            if ((int)sm4 > h->used_smem4) { SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4)); h->used_smem4 = (int)sm4; }
+            k_lsd_regions_lanes<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), 32, sm4, st>>>(g, h->ws, B);
+        }
+        else if (ww >= 2 && v3) {
             const size_t sm3 = sizeof(V3Shared) + (size_t)ww * V3_LRING * sizeof(unsigned);
             if ((int)sm3 > h->used_smem3) { SSLPL_CUDA(cudaFuncSetAttribute(k_lsd_regions_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); h->used_smem3 = (int)sm3; }
             k_lsd_regions_v3<<<(h->max_walkers > 0 ? std::min(B, h->max_walkers) : B), ww * 32, sm3, st>>>(g, h->ws, B);
@@ -2578,7 +3021,8 @@ int sslpl_line_create(const sslpl_line_params* p, sslpl_line** out) {
     h->p = *p;
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && v > 0) h->sm_count = v; }
     h->trace = getenv("SSLPL_LINE_TRACE") != nullptr;
-    if (const char* e = getenv("SSLPL_WALKER_V3")) h->walker_v3 = atoi(e) != 0 ? 1 : 0;
+    if (const char* e = getenv("SSLPL_WALKER_LANES")) h->walker_lanes = atoi(e) != 0;
+    if (const char* e = getenv("SSLPL_WALKER_V3")) h->walker_v3 = atoi(e) < 0 ? -1 : (atoi(e) != 0 ? 1 : 0);
     if (const char* e = getenv("SSLPL_WALKER_LEAN")) h->walker_lean = atoi(e) != 0;
     if (const char* e = getenv("SSLPL_WALKER_WARPS")) h->walker_warps = std::max(-1, std::min(WALK_MAXW, atoi(e)));   // tuning knob (tests sweep it); -1 = the one-warp throughput kernel
     {   // BinaryDescriptor constructor: local (F_l) and global (F_g) Gaussian weights, widthOfBand 7, 9 bands

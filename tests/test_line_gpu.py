@@ -124,7 +124,8 @@ WALKERS = [("one warp, round-2a form", {"SSLPL_WALKER_WARPS": "-1", "SSLPL_WALKE
            ("v3, 2 warps", {"SSLPL_WALKER_WARPS": "2", "SSLPL_WALKER_V3": "1"}),
            ("v3, 3 warps", {"SSLPL_WALKER_WARPS": "3", "SSLPL_WALKER_V3": "1"}),
            ("v3, 8 warps", {"SSLPL_WALKER_WARPS": "8", "SSLPL_WALKER_V3": "1"}),
-           ("v3, 16 warps", {"SSLPL_WALKER_WARPS": "16", "SSLPL_WALKER_V3": "1"})]
+           ("v3, 16 warps", {"SSLPL_WALKER_WARPS": "16", "SSLPL_WALKER_V3": "1"}),
+           ("lane-parallel (experimental)", {"SSLPL_WALKER_WARPS": "-1", "SSLPL_WALKER_LANES": "1"})]
 
 
 @pytest.mark.parametrize("name,env", WALKERS, ids=[w[0] for w in WALKERS])
@@ -133,11 +134,11 @@ def test_every_region_walker_is_the_sequential_one(pkg, oracle, synth, icl_gray,
     the handle picks one by batch and frame size.  Each of them, forced through the environment knobs that the handle reads when it
     is created, has to reproduce the sequential detector: same raw segments, KeyLines and LBD bytes as the oracle, several runs each
     (the multi-warp forms are timing dependent by construction)."""
-    for k in ("SSLPL_WALKER_WARPS", "SSLPL_WALKER_LEAN", "SSLPL_WALKER_V3"):
+    for k in ("SSLPL_WALKER_WARPS", "SSLPL_WALKER_LEAN", "SSLPL_WALKER_V3", "SSLPL_WALKER_LANES"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    reps = 1 if name.startswith("one warp") else 4
+    reps = 1 if name.startswith("one warp") else (2 if name.startswith("lane") else 4)
     for tag, img in (("icl", icl_gray), ("syn3", synth.frame(640, 480, 3)), ("syn8", synth.frame(640, 480, 8))):
         for _ in range(reps):
             _check_frame(pkg, oracle, img, 40, f"{name}/{tag}", vs_cv2=False)

@@ -11,7 +11,10 @@ fr = [int(a) for a in sys.argv[3:]] or [0, 3, 8]
 os.environ["SSLPL_LINE_TRACE"] = "1"
 os.environ["SSLPL_WALKER_WARPS"] = "-1"; os.environ.pop("SSLPL_WALKER_V3", None)
 ref = pkg.LineSegment(40, max_width=640, max_height=480, max_batch=1)
-os.environ["SSLPL_WALKER_WARPS"] = W; os.environ["SSLPL_WALKER_V3"] = "1"
+if W == "lanes":
+    os.environ["SSLPL_WALKER_WARPS"] = "-1"; os.environ["SSLPL_WALKER_LANES"] = "1"
+else:
+    os.environ["SSLPL_WALKER_WARPS"] = W; os.environ["SSLPL_WALKER_V3"] = "1"
 v3 = pkg.LineSegment(40, max_width=640, max_height=480, max_batch=1)
 bad = 0
 for f in fr:
