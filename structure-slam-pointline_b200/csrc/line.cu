@@ -1383,7 +1383,10 @@ __global__ void __launch_bounds__(WALK_MAXW * 32) k_lsd_regions(const __grid_con
 // THROUGHPUT form of the same stage for big batches: ONE WARP PER FRAME, no speculation (every instruction is useful work, 72
 // registers, ~28 frames resident per SM; 46 ms latency per frame, ~17 us per frame amortised with >= 3000 frames in flight).
 // sslpl picks it when a call brings at least two frames per SM; smaller calls use the multi-warp walker above (17 ms per frame).
-__global__ void __launch_bounds__(32, 28) k_lsd_regions_solo(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
+#ifndef SSLPL_SOLO_MINB
+#define SSLPL_SOLO_MINB 28
+#endif
+__global__ void __launch_bounds__(32, SSLPL_SOLO_MINB) k_lsd_regions_solo(const __grid_constant__ LineGeom g, LineWs ws, int nframes) {
     const int lane = threadIdx.x;
   for (;;) {
     int f = 0;
