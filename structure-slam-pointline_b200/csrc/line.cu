@@ -1501,7 +1501,7 @@ __global__ void __launch_bounds__(32, 28) k_lsd_regions_lean(const __grid_consta
 //   * validity is tracked where it is decided: an attempt that takes a pixel from a live attempt of higher rank POISONS it;
 //     an attempt that meets a pixel held by a live attempt of LOWER rank assumes it used and records that attempt as a
 //     dependency (two at most), valid iff it commits with that very try without ever having released a pixel;
-//   * warp 0 is the CONTROL warp (claims seeds in order into a ring of 1024 tiny slots, retires the head); the others are
+//   * warp 0 is the CONTROL warp (claims seeds in order into a ring of 256 tiny slots (more ranks in flight only add wasted speculation: 14.4-15.0 ms per frame at 128-256, 17.9 at 1024, 30.7 at 4096), retires the head); the others are
 //     workers that pick the lowest runnable slot.  No locks.  An invalid attempt goes back to the ring with try + 1; the
 //     head of the ring can neither meet a live lower rank nor be poisoned, so its attempt always commits.
 // Region growing is the lean form (float-degree test, lazy angle, list tail in shared memory) with tickets taken by CAS whose
@@ -1509,7 +1509,7 @@ __global__ void __launch_bounds__(32, 28) k_lsd_regions_lean(const __grid_consta
 // =================================================================================================
 constexpr int V3_MAXW = 16;            // warps per CTA: 1 control + up to 15 workers
 #ifndef SSLPL_V3_RING
-#define SSLPL_V3_RING 1024
+#define SSLPL_V3_RING 256
 #endif
 constexpr int V3_RING = SSLPL_V3_RING; // ranks in flight (claimed, not retired)
 constexpr int V3_LIST = 8192;          // list entries of a worker (ws.sreg); bigger regions are regrown as head with the frame-sized list
