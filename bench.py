@@ -345,7 +345,8 @@ def main():
     # One NCCL all-gather per step (north_star: "a single NCCL all-gather of match tables"): the point table of this step and
     # the line table of the ring slot that has just completed travel together in one [Bf, cap + NL] buffer (batch.PackedGather).
     from sslpl_b200 import batch as sbatch
-    pgather = sbatch.PackedGather(Bf, cap, NL, world, dev) if world > 1 else None
+    GBUF = int(os.environ.get("SSLPL_GATHER_BUFS", "4"))      # buffer sets of the packed all-gather: a rank may run 3 steps ahead of the slowest gather
+    pgather = sbatch.PackedGather(Bf, cap, NL, world, dev, nbuf=GBUF) if world > 1 else None
 
     def finalize_slot(r, defer=False):
         """Join slot r's line results into the points stream; gather them across ranks (now, or with this step's point table)."""
@@ -616,7 +617,7 @@ def main():
     h_lmatch = [torch.empty((Bf, NL), dtype=torch.int32).pin_memory() for _ in range(FR)]
     h_nlmatch = [torch.zeros((Bf,), dtype=torch.int32).pin_memory() for _ in range(FR)]
     busy = [False] * FR
-    pg_e = [sbatch.PackedGather(Bf, cap, NL, world, dev) for _ in range(FR)] if world > 1 else [None] * FR
+    pg_e = [sbatch.PackedGather(Bf, cap, NL, world, dev, nbuf=GBUF) for _ in range(FR)] if world > 1 else [None] * FR
 
     def e2e_finalize(k):
         """Host-side completion of ring slot k: both streams of the handle have finished, the results are in pinned host memory."""

@@ -56,11 +56,11 @@ class PackedGather:
     ranks are no longer lock-stepped by the all-gather (the gathered tables of step i are complete one step later; `wait()`
     joins them into the caller's stream).  Buffers are allocated once."""
 
-    def __init__(self, per_rank, cap, nl, world, device, dtype=None, own_stream=True):
+    def __init__(self, per_rank, cap, nl, world, device, dtype=None, own_stream=True, nbuf=2):
         import torch
         dtype = dtype or torch.int32
         self.cap, self.nl, self.world, self.per_rank = cap, nl, world, per_rank
-        self.nbuf = 2 if own_stream else 1
+        self.nbuf = max(2, int(nbuf)) if own_stream else 1     # buffer sets: a rank may run nbuf - 1 steps ahead of the slowest all-gather
         self.locals = [torch.full((per_rank, cap + nl), -1, dtype=dtype, device=device) for _ in range(self.nbuf)]
         self.fulls = [torch.empty((world * per_rank, cap + nl), dtype=dtype, device=device) for _ in range(self.nbuf)]
         self.cuda = own_stream and device is not None and getattr(device, "type", str(device)) == "cuda"
