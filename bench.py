@@ -262,7 +262,7 @@ def main():
                     help="weak: frames_per_gpu frames on every GPU; strong: BASELINE.json config 5 as written, the workload's frames in total, sharded")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lines", action="store_true", help="ORB + point matching only")
-    ap.add_argument("--line-ring", type=int, default=6, help="line handles (streams + workspaces) kept in flight")
+    ap.add_argument("--line-ring", type=int, default=10, help="line / frame handles (streams + workspaces) kept in flight (measured: 10 gives the shortest step, device-resident and end to end; 6, 8, 12, 14 are 1-2 ms slower)")
     ap.add_argument("--walkers-per-sm", type=float, default=0.0, help="per line handle: resident LSD region walkers per SM (0 = one per frame)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
