@@ -3160,7 +3160,9 @@ int sslpl_line_download_segments(sslpl_line* h, int frame, float* seg4, int cap,
 
 
 /* debug (SSLPL_LINE_TRACE=1 at handle creation): one row of 10 doubles per region that reached region2rect */
-/* Statistics of the last region-walker launch (16 values): [0] regions grown by the turn holder, [1] their clock cycles, [2] their
+/* Statistics of the last region-walker launch (16 values; collected with SSLPL_WALKER_DBG=32).  For the round-2a multi-warp walker as
+   listed below; the v3 and lane-parallel walkers fill the same array with their own counters (tools/v3_stats.py, tools/lanes_stats.py
+   name them).  Round-2a: [0] regions grown by the turn holder, [1] their clock cycles, [2] their
    pixels, [3] -, [4] claims whose seed had been swallowed by commit time, [5] redone by the turn holder: abandoned, [6] poisoned,
    [7] failed validation, [8] presumed swallowed but not, [9] attempts committed as speculated, [10] their pixels, [11] cycles
    under the commit lock, [12] under the claim lock, [13] attempts repeated after a lower rank retired, [14] cycles per frame
