@@ -84,7 +84,9 @@ struct Taps7 { int k[7]; };
 // Packed arithmetic: the horizontal pass is two dp4a per output on byte windows cut out of three aligned words with funnel
 // shifts; its u16 results are stored as vertical PAIRS (row r | row r+1 << 16) so that the vertical pass is four dp2a per
 // output.  All taps are < 256 and every partial sum < 65536, so the packed forms are exact.
-__global__ void __launch_bounds__(256) k_sep7(const __grid_constant__ LineGeom g, LView v, uint8_t* out, long long out_stride, Taps7 t) {
+// One launch filters the SAME staged input tile with two tap sets (LSD's 7-tap pre-blur and the 5-tap blur of the LBD stage): the tile
+// is read from global memory once (round 2b; two launches of the one-filter form before).  out1 == nullptr: one filter only.
+__global__ void __launch_bounds__(256) k_sep7(const __grid_constant__ LineGeom g, LView v, uint8_t* out0, uint8_t* out1, long long out_stride, Taps7 t0, Taps7 t1) {
     constexpr int IW = LT_W + 6, IP = LT_W + 8, IH = LT_H + 6;           // IP % 4 == 0: rows of s_in are word aligned
     __shared__ __align__(4) uint8_t s_in[IH * IP];
     __shared__ __align__(16) unsigned s_pair[IH * LT_W];                 // [r][x] = row r | row r+1 << 16
@@ -92,39 +94,46 @@ __global__ void __launch_bounds__(256) k_sep7(const __grid_constant__ LineGeom g
     const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x, x0 = tx * LT_W, y0 = ty * LT_H;
     const uint8_t* img = v.base + f * v.frame_stride;
-    const unsigned T0 = (unsigned)t.k[0] | ((unsigned)t.k[1] << 8) | ((unsigned)t.k[2] << 16) | ((unsigned)t.k[3] << 24);
-    const unsigned T1 = (unsigned)t.k[4] | ((unsigned)t.k[5] << 8) | ((unsigned)t.k[6] << 16);
     for (int yy = wid; yy < IH; yy += 8) {                               // a warp per input row: no per-element division
         const uint8_t* src = img + (long long)reflect101(y0 + yy - 3, g.h) * v.pitch;
         for (int xx = lane; xx < IW; xx += 32) s_in[yy * IP + xx] = __ldg(src + reflect101(x0 + xx - 3, g.w));
     }
     __syncthreads();
-    for (int i = tid; i < IH * (LT_W / 4); i += 256) {
-        const int yy = i / (LT_W / 4), x4 = (i - yy * (LT_W / 4)) * 4;
-        const unsigned* w = reinterpret_cast<const unsigned*>(&s_in[yy * IP + x4]);
-        const unsigned w0 = w[0], w1 = w[1], w2 = w[2];                  // bytes x4 .. x4+11 (output k uses bytes k .. k+6)
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        uint8_t* out = pass ? out1 : out0;
+        if (!out) break;
+        const Taps7& t = pass ? t1 : t0;
+        const unsigned T0 = (unsigned)t.k[0] | ((unsigned)t.k[1] << 8) | ((unsigned)t.k[2] << 16) | ((unsigned)t.k[3] << 24);
+        const unsigned T1 = (unsigned)t.k[4] | ((unsigned)t.k[5] << 8) | ((unsigned)t.k[6] << 16);
+        for (int i = tid; i < IH * (LT_W / 4); i += 256) {
+            const int yy = i / (LT_W / 4), x4 = (i - yy * (LT_W / 4)) * 4;
+            const unsigned* w = reinterpret_cast<const unsigned*>(&s_in[yy * IP + x4]);
+            const unsigned w0 = w[0], w1 = w[1], w2 = w[2];                  // bytes x4 .. x4+11 (output k uses bytes k .. k+6)
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const unsigned A = k ? __funnelshift_r(w0, w1, 8 * k) : w0, B = k ? __funnelshift_r(w1, w2, 8 * k) : w1;
-            const unsigned r = __dp4a(A, T0, __dp4a(B, T1, 0u));
-            s_half[(yy * LT_W + x4 + k) * 2] = (unsigned short)r;                          // low half of pair row yy
-            if (yy > 0) s_half[((yy - 1) * LT_W + x4 + k) * 2 + 1] = (unsigned short)r;    // high half of pair row yy-1
+            for (int k = 0; k < 4; k++) {
+                const unsigned A = k ? __funnelshift_r(w0, w1, 8 * k) : w0, B = k ? __funnelshift_r(w1, w2, 8 * k) : w1;
+                const unsigned r = __dp4a(A, T0, __dp4a(B, T1, 0u));
+                s_half[(yy * LT_W + x4 + k) * 2] = (unsigned short)r;                          // low half of pair row yy
+                if (yy > 0) s_half[((yy - 1) * LT_W + x4 + k) * 2 + 1] = (unsigned short)r;    // high half of pair row yy-1
+            }
         }
-    }
-    __syncthreads();
-    uint8_t* o = out + f * out_stride;
-    const unsigned C01 = (unsigned)t.k[0] | ((unsigned)t.k[1] << 8), C23 = (unsigned)t.k[2] | ((unsigned)t.k[3] << 8);
-    const unsigned C45 = (unsigned)t.k[4] | ((unsigned)t.k[5] << 8), C6 = (unsigned)t.k[6];
-    for (int i = tid; i < LT_H * (LT_W / 4); i += 256) {
-        const int yy = i / (LT_W / 4), x4 = (i - yy * (LT_W / 4)) * 4;
-        if (y0 + yy >= g.h || x0 + x4 >= g.w) continue;
-        const uint4 p0 = *reinterpret_cast<const uint4*>(&s_pair[yy * LT_W + x4]), p2 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 2) * LT_W + x4]);
-        const uint4 p4 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 4) * LT_W + x4]), p6 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 6) * LT_W + x4]);
-        const unsigned a0 = __dp2a_lo(p0.x, C01, __dp2a_lo(p2.x, C23, __dp2a_lo(p4.x, C45, __dp2a_lo(p6.x, C6, 32768u))));
-        const unsigned a1 = __dp2a_lo(p0.y, C01, __dp2a_lo(p2.y, C23, __dp2a_lo(p4.y, C45, __dp2a_lo(p6.y, C6, 32768u))));
-        const unsigned a2 = __dp2a_lo(p0.z, C01, __dp2a_lo(p2.z, C23, __dp2a_lo(p4.z, C45, __dp2a_lo(p6.z, C6, 32768u))));
-        const unsigned a3 = __dp2a_lo(p0.w, C01, __dp2a_lo(p2.w, C23, __dp2a_lo(p4.w, C45, __dp2a_lo(p6.w, C6, 32768u))));
-        *reinterpret_cast<uint32_t*>(o + (long long)(y0 + yy) * g.bpitch + x0 + x4) = (a0 >> 16) | ((a1 >> 16) << 8) | ((a2 >> 16) << 16) | ((a3 >> 16) << 24);
+        __syncthreads();
+        uint8_t* o = out + f * out_stride;
+        const unsigned C01 = (unsigned)t.k[0] | ((unsigned)t.k[1] << 8), C23 = (unsigned)t.k[2] | ((unsigned)t.k[3] << 8);
+        const unsigned C45 = (unsigned)t.k[4] | ((unsigned)t.k[5] << 8), C6 = (unsigned)t.k[6];
+        for (int i = tid; i < LT_H * (LT_W / 4); i += 256) {
+            const int yy = i / (LT_W / 4), x4 = (i - yy * (LT_W / 4)) * 4;
+            if (y0 + yy >= g.h || x0 + x4 >= g.w) continue;
+            const uint4 p0 = *reinterpret_cast<const uint4*>(&s_pair[yy * LT_W + x4]), p2 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 2) * LT_W + x4]);
+            const uint4 p4 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 4) * LT_W + x4]), p6 = *reinterpret_cast<const uint4*>(&s_pair[(yy + 6) * LT_W + x4]);
+            const unsigned a0 = __dp2a_lo(p0.x, C01, __dp2a_lo(p2.x, C23, __dp2a_lo(p4.x, C45, __dp2a_lo(p6.x, C6, 32768u))));
+            const unsigned a1 = __dp2a_lo(p0.y, C01, __dp2a_lo(p2.y, C23, __dp2a_lo(p4.y, C45, __dp2a_lo(p6.y, C6, 32768u))));
+            const unsigned a2 = __dp2a_lo(p0.z, C01, __dp2a_lo(p2.z, C23, __dp2a_lo(p4.z, C45, __dp2a_lo(p6.z, C6, 32768u))));
+            const unsigned a3 = __dp2a_lo(p0.w, C01, __dp2a_lo(p2.w, C23, __dp2a_lo(p4.w, C45, __dp2a_lo(p6.w, C6, 32768u))));
+            *reinterpret_cast<uint32_t*>(o + (long long)(y0 + yy) * g.bpitch + x0 + x4) = (a0 >> 16) | ((a1 >> 16) << 8) | ((a2 >> 16) << 16) | ((a3 >> 16) << 24);
+        }
+        __syncthreads();                                                  // s_pair is rewritten by the second filter
     }
 }
 
@@ -2948,8 +2957,7 @@ int run_pipeline(sslpl_line* h, int B) {
     const dim3 tiles(g.tiles_x * g.tiles_y, B);
     h->ev_n = 0;
     lmark(h, "start");
-    k_sep7<<<tiles, 256, 0, st>>>(g, h->view, h->ws.blur7, g.blur_stride, t7);
-    k_sep7<<<tiles, 256, 0, st>>>(g, h->view, h->ws.blur5, g.blur_stride, t5);
+    k_sep7<<<tiles, 256, 0, st>>>(g, h->view, h->ws.blur7, h->ws.blur5, g.blur_stride, t7, t5);      // both blurs from one staged tile
     k_resize_exact<<<dim3((g.sw + 31) / 32, (g.sh + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
     lmark(h, "lsd_prep");
     SSLPL_CUDA(cudaMemsetAsync(h->ws.maxgrad, 0, sizeof(unsigned long long) * B, st));
@@ -2992,7 +3000,7 @@ int run_pipeline(sslpl_line* h, int B) {
     k_sobel<<<dim3((g.w + 127) / 128, (g.h + 7) / 8, B), dim3(32, 8), 0, st>>>(g, h->ws);
     k_lbd<<<dim3(g.kl_cap, B), 64, 0, st>>>(g, h->ws, h->coef);
     lmark(h, "keylines_lbd");
-    h->launches += 12;     // kernels only (the two small memsets are not counted)
+    h->launches += 11;     // kernels only (the two small memsets are not counted)
     SSLPL_CUDA(cudaGetLastError());
     return SSLPL_OK;
 }
