@@ -24,6 +24,11 @@ import sys
 import threading
 import time
 
+# The loops below keep ~30 CUDA streams busy (ten frame / line handles with two streams each, matchers, the gather's stream).  With the
+# default of 8 hardware connections streams share queues and falsely serialise (measured: end-to-end step 28.3 ms at 8, 25.8-26.1 ms at 32).
+# Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -720,7 +725,7 @@ def main():
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
                 "config": make_config(args, cfg, world, LINES),
-                "run": {"line_ring": R, "primed": "every ring handle called once before the warm-up steps", "e2e_frame_handles": FR, "l2": f"inputs cycle through {nsets} distinct batches ({nsets * B * W * H / 1e6:.0f} MB > 126 MB L2)",
+                "run": {"line_ring": R, "primed": "every ring handle called once before the warm-up steps", "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "e2e_frame_handles": FR, "l2": f"inputs cycle through {nsets} distinct batches ({nsets * B * W * H / 1e6:.0f} MB > 126 MB L2)",
                         "units_counted": "on the device inside the timed region"},
                 "e2e": {"value": eu_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps},
